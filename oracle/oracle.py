@@ -1,0 +1,219 @@
+"""
+oracle.py -- ctypes front-end of the CPU ORACLE (oracle/wfo*.c + oracle/network.py).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / `--impl reference` legs. The product (wflow.jl_b200/) never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libwfo.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("wfo_vertical.c", "wfo_routing.c", "wfo.h", "wfo_math.h")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"],
+                              stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class _Net(C.Structure):
+    _fields_ = [("n", C.c_int64), ("up_ptr", C.c_void_p), ("up_idx", C.c_void_p),
+                ("n_levels", C.c_int64), ("level_ptr", C.c_void_p), ("level_sub", C.c_void_p),
+                ("n_sub", C.c_int64), ("sub_ptr", C.c_void_p), ("sub_nodes", C.c_void_p),
+                ("sub_pos", C.c_void_p)]
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("n", C.c_int64), ("nriv", C.c_int64), ("N", C.c_int64),
+                ("gash", C.c_int32), ("has_lai", C.c_int32), ("snow", C.c_int32),
+                ("glacier", C.c_int32), ("soil_infiltration_reduction", C.c_int32),
+                ("kv_profile", C.c_int32), ("adaptive", C.c_int32), ("nthreads", C.c_int32),
+                ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
+                ("ssf_alpha_coefficient", C.c_double)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.wfo_field_name.restype = C.c_char_p
+        L.wfo_new.restype = C.c_void_p
+        L.wfo_cfg.restype = C.POINTER(_Cfg)
+        L.wfo_cfg.argtypes = [C.c_void_p]
+        L.wfo_free.argtypes = [C.c_void_p]
+        L.wfo_set_ptr.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.wfo_set_iptr.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.wfo_set_network.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Net)]
+        for f in ("wfo_update_land_hydrology_model", "wfo_update_subsurface_flow_model",
+                  "wfo_update_soil_water_storage", "wfo_surface_routing",
+                  "wfo_update_overland_flow_model", "wfo_update_river_flow_model",
+                  "wfo_update_model"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_double]
+            getattr(L, f).restype = None
+        for f in ("wfo_exchange_recharge", "wfo_update_total_water_storage",
+                  "wfo_update_diagnostic_vars", "wfo_update_lateral_inflow_overland",
+                  "wfo_update_lateral_inflow_river"):
+            getattr(L, f).argtypes = [C.c_void_p]
+            getattr(L, f).restype = None
+        L.wfo_sweep.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.wfo_sweep.restype = C.c_int
+        d = C.c_double
+        pd = C.POINTER(C.c_double)
+
+        def sig(name, args, res=None):
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
+
+        sig("wfo_rainfall_interception_gash", [d] * 7 + [pd])
+        sig("wfo_rainfall_interception_modrut", [d] * 6 + [pd])
+        sig("wfo_precipitation_hbv", [d] * 4 + [pd])
+        sig("wfo_snowpack_hbv", [d] * 9 + [pd])
+        sig("wfo_glacier_hbv", [d] * 9 + [pd])
+        sig("wfo_infiltration", [d] * 7 + [pd])
+        sig("wfo_unsatzone_flow_layer", [d] * 5 + [pd])
+        sig("wfo_vwc_brooks_corey", [d] * 5, d)
+        sig("wfo_head_brooks_corey", [d] * 5, d)
+        sig("wfo_feddes_h3", [d] * 3, d)
+        sig("wfo_rwu_reduction_feddes", [d] * 6, d)
+        sig("wfo_soil_temperature", [d] * 3, d)
+        sig("wfo_infiltration_reduction_factor", [d, d, C.c_int, C.c_int], d)
+        sig("wfo_soil_evaporation_unsaturated_store", [d, d, d, C.c_int64, d, d], d)
+        sig("wfo_soil_evaporation_saturated_store", [d, C.c_int64, d, d, d, d], d)
+        sig("wfo_actual_infiltration_soil_path", [d] * 6 + [pd])
+        sig("wfo_scurve", [d] * 4, d)
+        sig("wfo_kinematic_wave", [d] * 6 + [pd, C.POINTER(C.c_int64)])
+        sig("wfo_kw_ssf_newton_raphson", [d] * 5, d)
+        sig("wfo_ssf_celerity", [d] * 6 + [C.c_int], d)
+        sig("wfo_kinematic_wave_ssf", [C.c_void_p] + [d] * 11 + [C.c_int64, pd])
+        sig("wfo_water_table_change", [C.c_void_p, d, d, C.c_int64, d, pd])
+        sig("wfo_stable_timestep_surface", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, d,
+                                            C.c_void_p], d)
+        sig("wfo_round_sigdigits12", [d], d)
+        sig("wfo_cld", [d, d], d)
+        _lib = L
+    return _lib
+
+
+def field_table():
+    L = lib()
+    return [(L.wfo_field_name(i).decode(), L.wfo_field_kind(i)) for i in range(L.wfo_num_fields())]
+
+
+INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_indices")
+
+
+def call_out(fn_name, nout, *args):
+    """Call a scalar oracle kernel that writes `nout` doubles to its trailing out[] argument."""
+    out = (C.c_double * nout)()
+    getattr(lib(), fn_name)(*args, out)
+    return tuple(out)
+
+
+def _csr(lists):
+    ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    for k, l in enumerate(lists):
+        ptr[k + 1] = ptr[k] + len(l)
+    idx = np.concatenate([np.asarray(l, dtype=np.int64) for l in lists]) if lists else np.zeros(0, np.int64)
+    return ptr, np.ascontiguousarray(idx, dtype=np.int64)
+
+
+class OracleModel:
+    """Owns numpy arrays for every field and walks them with the C oracle.
+
+    `fields`: dict name -> ndarray (land scalars (n,), layered (n, N) cell-major like Julia's
+    Vector{SVector{N}}, river (nriv,)); missing fields are allocated as NaN (MISSING_VALUE).
+    `net_land` / `net_river`: dicts from oracle.network.build_domain_network (1-based).
+    """
+
+    def __init__(self, cfg: dict, fields: dict, net_land: dict, net_river: dict):
+        L = lib()
+        self._L = L
+        self.h = L.wfo_new()
+        c = L.wfo_cfg(self.h).contents
+        n, nriv, N = int(cfg["n"]), int(cfg["nriv"]), int(cfg["N"])
+        c.n, c.nriv, c.N = n, nriv, N
+        for k in ("gash", "has_lai", "snow", "glacier", "soil_infiltration_reduction",
+                  "kv_profile", "adaptive"):
+            setattr(c, k, int(cfg.get(k, 0)))
+        c.nthreads = int(cfg.get("nthreads", 0))
+        c.dt_land = float(cfg.get("dt_land", 3600.0))
+        c.dt_river = float(cfg.get("dt_river", 900.0))
+        c.dt_ssf = float(cfg.get("dt_ssf", 86400.0))
+        c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
+        self.cfg = dict(cfg)
+        self.f = {}
+        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,)}
+        for name, kind in field_table():
+            if name in fields and fields[name] is not None:
+                a = np.ascontiguousarray(np.array(fields[name], dtype=np.float64, copy=True))
+                assert a.shape == shapes[kind], (name, a.shape, shapes[kind])
+            else:
+                a = np.full(shapes[kind], np.nan)
+            self.f[name] = a
+            L.wfo_set_ptr(self.h, name.encode(), a.ctypes.data)
+        for name in INT_FIELDS:
+            size = nriv if name == "river_land_indices" else n
+            if name in fields and fields[name] is not None:
+                a = np.ascontiguousarray(np.array(fields[name], dtype=np.int64, copy=True))
+            else:
+                a = np.zeros(size, dtype=np.int64)
+            self.f[name] = a
+            L.wfo_set_iptr(self.h, name.encode(), a.ctypes.data)
+        self._keep = []
+        for which, net in ((0, net_land), (1, net_river)):
+            s = _Net()
+            s.n = len(net["order"])
+            arrs = {}
+            arrs["up_ptr"] = np.ascontiguousarray(net["up_ptr"], dtype=np.int64)
+            arrs["up_idx"] = np.ascontiguousarray(net["up_idx"] - 1, dtype=np.int64)
+            lp, ls = _csr(net["order_of_subdomains"])
+            arrs["level_ptr"], arrs["level_sub"] = lp, ls - 1
+            sp, sn = _csr(net["order_subdomain"])
+            _, si = _csr(net["subdomain_indices"])
+            arrs["sub_ptr"], arrs["sub_nodes"], arrs["sub_pos"] = sp, sn - 1, si - 1
+            s.n_levels = len(net["order_of_subdomains"])
+            s.n_sub = len(net["order_subdomain"])
+            for k, a in arrs.items():
+                a = np.ascontiguousarray(a, dtype=np.int64)
+                arrs[k] = a
+                setattr(s, k, a.ctypes.data)
+            self._keep.append((s, arrs))
+            L.wfo_set_network(self.h, which, C.byref(s))
+
+    def __del__(self):
+        try:
+            self._L.wfo_free(self.h)
+        except Exception:
+            pass
+
+    # names mirror the reference's update functions
+    def update_land_hydrology_model(self, dt): self._L.wfo_update_land_hydrology_model(self.h, dt)
+    def exchange_recharge(self): self._L.wfo_exchange_recharge(self.h)
+    def update_subsurface_flow_model(self, dt): self._L.wfo_update_subsurface_flow_model(self.h, dt)
+    def update_soil_water_storage(self, dt): self._L.wfo_update_soil_water_storage(self.h, dt)
+    def surface_routing(self, dt): self._L.wfo_surface_routing(self.h, dt)
+    def update_lateral_inflow_overland(self): self._L.wfo_update_lateral_inflow_overland(self.h)
+    def update_lateral_inflow_river(self): self._L.wfo_update_lateral_inflow_river(self.h)
+    def update_overland_flow_model(self, dt): self._L.wfo_update_overland_flow_model(self.h, dt)
+    def update_river_flow_model(self, dt): self._L.wfo_update_river_flow_model(self.h, dt)
+    def update_total_water_storage(self): self._L.wfo_update_total_water_storage(self.h)
+    def update_diagnostic_vars(self): self._L.wfo_update_diagnostic_vars(self.h)
+    def update_model(self, dt): self._L.wfo_update_model(self.h, dt)
+
+    def sweep(self, name, dt=0.0):
+        rc = self._L.wfo_sweep(self.h, name.encode(), dt)
+        if rc != 0:
+            raise KeyError(name)

@@ -1,0 +1,566 @@
+/*
+ * wfo_routing.c -- CPU ORACLE (test infrastructure, see wfo.h): kinematic-wave routing
+ * (lateral subsurface, overland, river), walked exactly like the reference: serial levels of
+ * `order_of_subdomains`, threads over the sub-domains of one level, serial toposort walk
+ * inside a sub-domain (Wflow/src/routing/surface/surface_kinwave.jl:293-341,492-566;
+ * routing/subsurface/lateral_subsurface_flow.jl:198-273).
+ */
+#include "wfo.h"
+#include "wfo_math.h"
+#include <stdlib.h>
+#include <string.h>
+
+#define PFOR _Pragma("omp parallel for schedule(static)")
+
+static double kin_wave_min_flow_qroot(void) {
+  /* routing/utils.jl:2 : KIN_WAVE_MIN_FLOW^0.2 (Julia Float64^Float64 = correctly rounded pow;
+   * the exact value 1e-6 is representable to <1ulp, pow() returns it) */
+  static double v = 0.0;
+  if (v == 0.0) v = pow(WFO_KIN_WAVE_MIN_FLOW, 0.2);
+  return v;
+}
+
+/* Julia cld(x::Float64, y::Float64) = round((x - mod(x, -y)) / y)  (Base div.jl) */
+double wfo_cld(double x, double y) {
+  double ny = -y;
+  double r = fmod(x, ny), md;
+  if (r == 0.0) md = copysign(r, ny);
+  else if ((r > 0.0) != (ny > 0.0)) md = r + ny;
+  else md = r;
+  return rint((x - md) / y);
+}
+
+/* Julia round(v; sigdigits = 12) for v >= 0 (Base floatfuncs.jl: hidigit = 1+floor(log10|v|),
+ * _round_invstep with 10.0^digits) */
+double wfo_round_sigdigits12(double v) {
+  if (v == 0.0 || !isfinite(v)) return v;
+  static const double p10[] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,
+                               1e8,  1e9,  1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                               1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  int h = 1 + (int)floor(log10(fabs(v)));
+  int digits = 12 - h;
+  if (digits >= 0) {
+    double sm = digits <= 22 ? p10[digits] : pow(10.0, (double)digits);
+    double y = rint(v * sm);
+    double r = y / sm;
+    return isfinite(r) ? r : v;
+  } else {
+    double s = -digits <= 22 ? p10[-digits] : pow(10.0, (double)(-digits));
+    double y = rint(v / s);
+    double r = y * s;
+    return isfinite(r) ? r : v;
+  }
+}
+
+/* routing/surface/surface_process.jl:24-70 */
+void wfo_kinematic_wave(double q_in, double q_prev, double q_lat, double alpha, double dt,
+                        double dx, double out[2], int64_t* iters) {
+  int64_t it = 0;
+  if (q_in + q_prev + q_lat == 0.0) { /* `≈ 0.0` with atol = 0 is exact equality */
+    out[0] = 0.0; out[1] = 0.0;
+    if (iters) *iters = 0;
+    return;
+  }
+  const double qroot = kin_wave_min_flow_qroot();
+  double dt_dx = dt / dx;
+  double u_prev = q_prev >= 0.0 ? jl_pow(q_prev, 0.2) : 0.0;
+  double constant_term = dt_dx * q_in + alpha * u_prev * u_prev * u_prev + dt * q_lat;
+  double u = u_prev > 0.0 ? u_prev : cbrt(constant_term / alpha);
+  const int max_iters = 3000;
+  const double epsilon = 1.0e-12;
+  double const_1 = 5.0 * dt_dx, const_2 = 3.0 * alpha;
+  for (int k = 0; k < max_iters; ++k) {
+    double u2 = u * u;
+    double u3 = u2 * u;
+    double f_u = u3 * (dt_dx * u2 + alpha) - constant_term;
+    if (fabs(f_u) <= epsilon) break;
+    double df_u = u2 * (const_1 * u2 + const_2);
+    u -= f_u / df_u;
+    if (isnan(u) || u <= 0.0) u = qroot;
+    ++it;
+  }
+  u = jl_max(u, qroot);
+  double u3 = u * u * u;
+  out[1] = alpha * u3;
+  out[0] = u3 * u * u;
+  if (iters) *iters = it;
+}
+
+/* routing/subsurface/subsurface_process.jl:6-51 ; profile 0 exponential, 1 exponential_constant */
+double wfo_ssf_celerity(double zi, double slope, double sy, double kh_0, double f, double z_exp,
+                        int profile) {
+  double z = zi;
+  if (profile == 1) z = zi < z_exp ? zi : z_exp;
+  return (kh_0 * exp(-f * z) * slope) / sy;
+}
+
+/* routing/subsurface/subsurface_process.jl:57-78 */
+double wfo_kw_ssf_newton_raphson(double q, double constant_term, double celerity, double dt,
+                                 double dx) {
+  const double epsilon = 1.0e-12;
+  const int max_iters = 3000;
+  int count = 0;
+  double dt_dx = dt / dx;
+  double celerity_inv = 1.0 / celerity;
+  double df = dt_dx + celerity_inv;
+  for (;;) {
+    double f = dt_dx * q + celerity_inv * q - constant_term;
+    q -= (f / df);
+    if (isnan(q)) q = 0.0;
+    q = jl_max(q, WFO_KIN_WAVE_MIN_FLOW);
+    if (fabs(f) <= epsilon || count >= max_iters) break;
+    ++count;
+  }
+  return q;
+}
+
+/* utils.jl:1090-1131 */
+void wfo_water_table_change(wfo_model* m, double net_flux, double sy, int64_t i, double dt,
+                            double out[2]) {
+  const int64_t N = m->cfg.N;
+  const double* ult = m->unsaturated_layer_thickness + i * N;
+  const double* uld = m->unsaturated_layer_depth + i * N;
+  double theta_e = m->theta_s[i] - m->theta_r[i];
+  double dh;
+  if (net_flux <= 0.0) {
+    dh = net_flux * dt / sy;
+  } else {
+    dh = 0.0;
+    for (int64_t k = m->n_unsatlayers[i] - 1; k >= 0; --k) {
+      double capacity = jl_max(ult[k] * theta_e - uld[k], 0.0) / dt;
+      double flux_layer = jl_min(net_flux, capacity);
+      if (capacity <= net_flux) dh += ult[k];
+      else {
+        double syd = theta_e - (uld[k] / ult[k]);
+        dh += flux_layer * dt / syd;
+      }
+      net_flux -= flux_layer;
+      if (net_flux == 0.0) break;
+    }
+  }
+  out[0] = dh;
+  out[1] = jl_max(net_flux, 0.0);
+}
+
+/* soil/soil.jl:1213-1259 */
+static void update_ustorelayerdepth(wfo_model* m, double zi_prev, double zi, int64_t i) {
+  const int64_t N = m->cfg.N;
+  double* uld = m->unsaturated_layer_depth + i * N;
+  double* ult = m->unsaturated_layer_thickness + i * N;
+  int64_t nu_prev = m->n_unsatlayers[i];
+  double ult_prev[16], ult_new[16];
+  for (int64_t k = 0; k < N; ++k) ult_prev[k] = ult[k];
+  /* set_layerthickness (utils.jl:390-404) */
+  const double* cum = m->cumulative_layer_depth + i * (N + 1);
+  const double* alt = m->actual_layer_thickness + i * N;
+  int64_t nu = N;
+  for (int64_t k = 0; k < N; ++k) {
+    ult_new[k] = alt[k] * NAN;
+    if (zi > cum[k + 1]) ult_new[k] = alt[k];
+    else if (zi - cum[k] > 0.0) ult_new[k] = zi - cum[k];
+    if (isnan(ult_new[k])) --nu;
+  }
+  if (zi < zi_prev) {
+    for (int64_t k1 = nu; k1 <= nu_prev; ++k1) { /* 1-based layer index */
+      if (k1 == 0) continue;
+      if (isnan(ult_new[k1 - 1])) uld[k1 - 1] = 0.0;
+      else {
+        double scale = ult_new[k1 - 1] / ult_prev[k1 - 1];
+        uld[k1 - 1] = scale * uld[k1 - 1];
+      }
+    }
+  } else {
+    for (int64_t k1 = nu_prev; k1 <= nu; ++k1) {
+      if (k1 == 0) continue;
+      double tp = isnan(ult_prev[k1 - 1]) ? 0.0 : ult_prev[k1 - 1];
+      double delta = ult_new[k1 - 1] - tp;
+      uld[k1 - 1] = uld[k1 - 1] + delta * (m->theta_fc[i] - m->theta_r[i]);
+    }
+  }
+  m->n_unsatlayers[i] = nu;
+  for (int64_t k = 0; k < N; ++k) ult[k] = ult_new[k];
+  m->water_table_depth[i] = zi;
+}
+
+/* routing/subsurface/subsurface_process.jl:89-172 (KhExponential / KhExponentialConstant) */
+void wfo_kinematic_wave_ssf(wfo_model* m, double q_in, double q_prev, double zi_prev,
+                            double q_net_bnds, double slope, double sy, double d, double dt,
+                            double dx, double dw, double q_max, int64_t i, double out[4]) {
+  if (q_in + q_prev == 0.0 && q_net_bnds <= 0.0) {
+    out[0] = 0.0; out[1] = d; out[2] = 0.0; out[3] = 0.0;
+    return;
+  }
+  const int prof = m->cfg.kv_profile;
+  const double kh_0 = m->kh_0[i], f = m->hydraulic_conductivity_scale_parameter[i];
+  const double z_exp = prof == 1 ? m->z_exp[i] : 0.0;
+  double q = (q_prev + q_in) / 2.0;
+  double celerity = wfo_ssf_celerity(zi_prev, slope, sy, kh_0, f, z_exp, prof);
+  double constant_term = (dt / dx) * (q_in + q_net_bnds) + q_prev / celerity;
+  q = wfo_kw_ssf_newton_raphson(q, constant_term, celerity, dt, dx);
+  q = jl_min(q, (q_max * dw));
+  double net_flux = (q_in + q_net_bnds - q) / (dw * dx);
+  double o[2];
+  wfo_water_table_change(m, net_flux, sy, i, dt, o);
+  double dh = o[0], exfilt = o[1];
+  double zi = zi_prev - dh;
+  if (zi > d) {
+    double q_excess = (dw * dx) * sy * (zi - d) / dt;
+    q = jl_max(q - q_excess, WFO_KIN_WAVE_MIN_FLOW);
+  }
+  zi = jl_clamp(zi, 0.0, d);
+  const double max_delta_zi = 0.1;
+  int64_t its = (int64_t)ceil(wfo_round_sigdigits12(fabs(zi - zi_prev) / max_delta_zi));
+  if (its > 1) {
+    double dt_s = dt / (double)its;
+    double q_sum = 0.0, exfilt_sum = 0.0, net_flux_sum = 0.0;
+    for (int64_t k = 0; k < its; ++k) {
+      celerity = wfo_ssf_celerity(zi_prev, slope, sy, kh_0, f, z_exp, prof);
+      constant_term = (dt_s / dx) * q_in + q_prev / celerity + q_net_bnds * (dt_s / dx);
+      q = wfo_kw_ssf_newton_raphson(q_prev, constant_term, celerity, dt_s, dx);
+      q = jl_min(q, (q_max * dw));
+      net_flux = (q_in + q_net_bnds - q) / (dw * dx);
+      wfo_water_table_change(m, net_flux, sy, i, dt_s, o);
+      dh = o[0]; exfilt = o[1];
+      zi = zi_prev - dh;
+      if (zi > d) {
+        double q_excess = (dw * dx) * sy * (zi - d) / dt_s;
+        q = jl_max(q - q_excess, WFO_KIN_WAVE_MIN_FLOW);
+      }
+      zi = jl_clamp(zi, 0.0, d);
+      update_ustorelayerdepth(m, zi_prev, zi, i);
+      exfilt_sum += exfilt;
+      net_flux_sum += net_flux;
+      q_sum += q;
+      q_prev = q;
+      zi_prev = zi;
+    }
+    q = q_sum / (double)its;
+    exfilt = exfilt_sum / (double)its;
+    net_flux = net_flux_sum / (double)its;
+  } else {
+    update_ustorelayerdepth(m, zi_prev, zi, i);
+  }
+  out[0] = q; out[1] = zi; out[2] = exfilt; out[3] = net_flux;
+}
+
+/* Statistics.quantile! (type 7, alpha = beta = 1) on v[0..k) ; sorts v */
+static int cmp_double(const void* a, const void* b) {
+  double x = *(const double*)a, y = *(const double*)b;
+  return (x > y) - (x < y);
+}
+static double quantile7(double* v, int64_t n, double p) {
+  qsort(v, (size_t)n, sizeof(double), cmp_double);
+  double mm = 1.0 + p * (1.0 - 1.0 - 1.0);
+  double aleph = (double)n * p + mm;
+  int64_t j = (int64_t)trunc(aleph);
+  if (j < 1) j = 1;
+  if (j > n - 1) j = n - 1;
+  double g = jl_clamp(aleph - (double)j, 0.0, 1.0);
+  double a, b;
+  if (n == 1) { a = v[0]; b = v[0]; }
+  else { a = v[j - 1]; b = v[j]; }
+  if (isfinite(a) && isfinite(b)) return a + g * (b - a);
+  return (1.0 - g) * a + g * b;
+}
+
+/* routing/surface/surface_kinwave.jl:674-704 */
+double wfo_stable_timestep_surface(const double* q, const double* alpha, const double* len,
+                                   int64_t n, double p, double* work) {
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (q[i] > WFO_KIN_WAVE_MIN_FLOW) {
+      double c = 1.0 / (alpha[i] * 0.6 * jl_pow(q[i], (0.6 - 1.0)));
+      work[k++] = len[i] / c;
+    }
+  }
+  if (k == 1) return work[0];
+  if (k > 0) return quantile7(work, k, p);
+  return 600.0;
+}
+
+/* routing/subsurface/lateral_subsurface_flow.jl:314-344 */
+static double stable_timestep_ssf(wfo_model* m) {
+  const int prof = m->cfg.kv_profile;
+  int64_t k = 0;
+  double dt_min = INFINITY;
+  for (int64_t i = 0; i < m->cfg.n; ++i) {
+    if (m->ssf_water_table_depth[i] > 0.0) {
+      ++k;
+      double c = wfo_ssf_celerity(m->ssf_water_table_depth[i], m->slope[i], m->specific_yield[i],
+                                  m->kh_0[i], m->hydraulic_conductivity_scale_parameter[i],
+                                  prof == 1 ? m->z_exp[i] : 0.0, prof);
+      dt_min = jl_min(dt_min, m->flow_length[i] / c);
+    }
+  }
+  if (k == 0) dt_min = 0.5;
+  return dt_min * m->cfg.ssf_alpha_coefficient;
+}
+
+/* routing/timestepping.jl:11-16 */
+static double check_timestepsize(double dt_s, double t, double dt) {
+  if (t + dt_s > dt) dt_s = dt - t;
+  return dt_s;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* lateral subsurface flow                                                                  */
+/* ---------------------------------------------------------------------------------------- */
+
+/* lateral_subsurface_flow.jl:198-273 */
+static void kinwave_subsurface_update(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->land;
+  for (int64_t lv = 0; lv < nw->n_levels; ++lv) {
+    const int64_t s0 = nw->level_ptr[lv], s1 = nw->level_ptr[lv + 1];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t s = s0; s < s1; ++s) {
+      const int64_t sub = nw->level_sub[s];
+      for (int64_t e = nw->sub_ptr[sub]; e < nw->sub_ptr[sub + 1]; ++e) {
+        const int64_t v = nw->sub_nodes[e], pos = nw->sub_pos[e];
+        double qin = 0.0, tor = 0.0;
+        for (int64_t u = nw->up_ptr[pos]; u < nw->up_ptr[pos + 1]; ++u) {
+          const int64_t j = nw->up_idx[u];
+          qin += m->ssf_q[j] * (1.0 - m->flow_fraction_to_river[j]);
+          tor += m->ssf_q[j] * m->flow_fraction_to_river[j];
+        }
+        m->ssf_q_in[v] = qin;
+        m->ssf_to_river_cumulative[v] += tor * dt;
+        double o[4];
+        wfo_kinematic_wave_ssf(m, m->ssf_q_in[v], m->ssf_q[v], m->ssf_water_table_depth[v],
+                               m->ssf_q_net_bnds[v], m->slope[v], m->specific_yield[v],
+                               m->ssf_soil_thickness[v], dt, m->flow_length[v], m->flow_width[v],
+                               m->ssf_q_max[v], v, o);
+        m->ssf_q[v] = o[0];
+        m->ssf_water_table_depth[v] = o[1];
+        m->ssf_q_in_cumulative[v] += m->ssf_q_in[v] * dt;
+        m->ssf_q_cumulative[v] += m->ssf_q[v] * dt;
+        m->ssf_exfiltwater_cumulative[v] += o[2] * dt;
+        m->ssf_q_net_cumulative[v] += o[3] * m->area[v] * dt;
+        m->ssf_head[v] = m->ssf_top[v] - m->ssf_water_table_depth[v];
+        m->ssf_storage[v] = m->specific_yield[v] *
+                            (m->ssf_soil_thickness[v] - m->ssf_water_table_depth[v]) * m->area[v];
+      }
+    }
+  }
+}
+
+/* sbm_model.jl:74-81 */
+void wfo_exchange_recharge(wfo_model* m) {
+  PFOR for (int64_t i = 0; i < m->cfg.n; ++i) {
+    m->recharge_rate[i] = m->recharge[i];
+    m->ssf_water_table_depth[i] = m->water_table_depth[i];
+  }
+}
+
+/* lateral_subsurface_flow.jl:279-304 ; groundwater.jl:606-638 ; boundary_conditions.jl:12-21,219-236 */
+void wfo_update_subsurface_flow_model(wfo_model* m, double dt) {
+  const int64_t n = m->cfg.n;
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->ssf_to_river_cumulative[i] = 0.0;
+    m->recharge_flux_cumulative[i] = 0.0;
+    m->ssf_exfiltwater_cumulative[i] = 0.0;
+    m->ssf_q_in_cumulative[i] = 0.0;
+    m->ssf_q_cumulative[i] = 0.0;
+    m->ssf_q_net_cumulative[i] = 0.0;
+  }
+  double t = 0.0;
+  m->substeps_ssf = 0;
+  while (t < dt) {
+    double dt_s = m->cfg.adaptive ? stable_timestep_ssf(m) : m->cfg.dt_ssf;
+    dt_s = check_timestepsize(dt_s, t, dt);
+    PFOR for (int64_t i = 0; i < n; ++i) {
+      m->ssf_q_net_bnds[i] = 0.0;
+      double flux = m->recharge_rate[i] * m->area[i];
+      if (m->ssf_water_table_depth[i] >= m->ssf_soil_thickness[i]) flux = jl_max(0.0, flux);
+      m->recharge_flux[i] = flux;
+      m->recharge_flux_cumulative[i] += flux * dt_s;
+      m->ssf_q_net_bnds[i] += flux;
+    }
+    kinwave_subsurface_update(m, dt_s);
+    t += dt_s;
+    m->substeps_ssf++;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->recharge_flux_average[i] = m->recharge_flux_cumulative[i] / dt;
+    m->ssf_q_in_average[i] = m->ssf_q_in_cumulative[i] / dt;
+    m->ssf_q_average[i] = m->ssf_q_cumulative[i] / dt;
+    m->ssf_q_net_average[i] = m->ssf_q_net_cumulative[i] / dt;
+    m->ssf_exfiltwater_average[i] = m->ssf_exfiltwater_cumulative[i] / dt;
+    m->ssf_to_river_average[i] = m->ssf_to_river_cumulative[i] / dt;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* overland flow                                                                            */
+/* ---------------------------------------------------------------------------------------- */
+
+/* surface_kinwave.jl:293-341 */
+static void kinwave_land_update(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->land;
+  PFOR for (int64_t i = 0; i < m->cfg.n; ++i) m->olf_qin[i] = 0.0;
+  for (int64_t lv = 0; lv < nw->n_levels; ++lv) {
+    const int64_t s0 = nw->level_ptr[lv], s1 = nw->level_ptr[lv + 1];
+    int64_t it_sum = 0, calls = 0, maxit = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : it_sum, calls) reduction(max : maxit)
+    for (int64_t s = s0; s < s1; ++s) {
+      const int64_t sub = nw->level_sub[s];
+      for (int64_t e = nw->sub_ptr[sub]; e < nw->sub_ptr[sub + 1]; ++e) {
+        const int64_t v = nw->sub_nodes[e], pos = nw->sub_pos[e];
+        double tor = 0.0, qin = 0.0;
+        for (int64_t u = nw->up_ptr[pos]; u < nw->up_ptr[pos + 1]; ++u) {
+          const int64_t j = nw->up_idx[u];
+          tor += m->olf_q[j] * m->flow_fraction_to_river[j];
+          qin += m->olf_q[j] * (1.0 - m->flow_fraction_to_river[j]);
+        }
+        m->olf_to_river_cumulative[v] += tor * dt;
+        if (m->surface_flow_width[v] > 0.0) m->olf_qin[v] = qin;
+        double o[2];
+        int64_t it;
+        wfo_kinematic_wave(m->olf_qin[v], m->olf_q[v], m->olf_qlat[v], m->olf_alpha[v], dt,
+                           m->flow_length[v], o, &it);
+        it_sum += it; calls += 1; if (it > maxit) maxit = it;
+        m->olf_q[v] = o[0];
+        if (m->surface_flow_width[v] > 0.0) m->olf_h[v] = o[1] / m->surface_flow_width[v];
+        m->olf_storage[v] = m->flow_length[v] * m->surface_flow_width[v] * m->olf_h[v];
+        m->olf_q_cumulative[v] += m->olf_q[v] * dt;
+        m->olf_qin_cumulative[v] += m->olf_qin[v] * dt;
+      }
+    }
+    m->newton_iters_land += it_sum; m->newton_calls_land += calls;
+    if (maxit > m->newton_maxit_land) m->newton_maxit_land = maxit;
+  }
+}
+
+/* surface_kinwave.jl:740-766 (no drains, no water demand) */
+void wfo_update_lateral_inflow_overland(wfo_model* m) {
+  PFOR for (int64_t i = 0; i < m->cfg.n; ++i)
+    m->olf_inwater[i] = (m->net_runoff[i] + 0.0) * m->area[i] + 0.0;
+}
+
+/* surface_kinwave.jl:347-385 */
+void wfo_update_overland_flow_model(wfo_model* m, double dt) {
+  const int64_t n = m->cfg.n;
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->olf_qlat[i] = m->olf_inwater[i] / m->flow_length[i];
+    m->olf_q_cumulative[i] = 0.0;
+    m->olf_qin_cumulative[i] = 0.0;
+    m->olf_to_river_cumulative[i] = 0.0;
+  }
+  double t = 0.0;
+  m->substeps_land = 0;
+  while (t < dt) {
+    double dt_s = m->cfg.adaptive
+                      ? wfo_stable_timestep_surface(m->olf_q, m->olf_alpha, m->flow_length, n,
+                                                    0.02, m->scratch)
+                      : m->cfg.dt_land;
+    dt_s = check_timestepsize(dt_s, t, dt);
+    kinwave_land_update(m, dt_s);
+    t += dt_s;
+    m->substeps_land++;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->olf_q_average[i] = m->olf_q_cumulative[i] / dt;
+    m->olf_to_river_average[i] = m->olf_to_river_cumulative[i] / dt;
+    m->olf_qin_average[i] = m->olf_qin_cumulative[i] / dt;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* river flow                                                                               */
+/* ---------------------------------------------------------------------------------------- */
+
+/* surface_kinwave.jl:492-566 (no reservoirs, no floodplain) */
+static void kinwave_river_update(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->river;
+  PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) m->riv_qin[i] = 0.0;
+  for (int64_t lv = 0; lv < nw->n_levels; ++lv) {
+    const int64_t s0 = nw->level_ptr[lv], s1 = nw->level_ptr[lv + 1];
+    int64_t it_sum = 0, calls = 0, maxit = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : it_sum, calls) reduction(max : maxit)
+    for (int64_t s = s0; s < s1; ++s) {
+      const int64_t sub = nw->level_sub[s];
+      for (int64_t e = nw->sub_ptr[sub]; e < nw->sub_ptr[sub + 1]; ++e) {
+        const int64_t v = nw->sub_nodes[e], pos = nw->sub_pos[e];
+        double qs = 0.0;
+        for (int64_t u = nw->up_ptr[pos]; u < nw->up_ptr[pos + 1]; ++u) qs += m->riv_q[nw->up_idx[u]];
+        m->riv_qin[v] += qs;
+        double inflow;
+        if (m->riv_external_inflow[v] < 0.0) {
+          double abstraction = jl_min(-m->riv_external_inflow[v], (m->riv_storage[v] / dt) * 0.80);
+          m->riv_actual_external_abstraction_cumulative[v] += abstraction * dt;
+          inflow = -abstraction / m->riv_flow_length[v];
+        } else {
+          inflow = m->riv_external_inflow[v] / m->riv_flow_length[v];
+        }
+        inflow -= m->riv_abstraction[v] / m->riv_flow_length[v];
+        double o[2];
+        int64_t it;
+        wfo_kinematic_wave(m->riv_qin[v], m->riv_q[v], m->riv_qlat[v] + inflow, m->riv_alpha[v], dt,
+                           m->riv_flow_length[v], o, &it);
+        it_sum += it; calls += 1; if (it > maxit) maxit = it;
+        m->riv_q[v] = o[0];
+        m->riv_h[v] = o[1] / m->riv_flow_width[v];
+        m->riv_storage[v] = m->riv_flow_length[v] * o[1];
+        m->riv_q_cumulative[v] += m->riv_q[v] * dt;
+        m->riv_qin_cumulative[v] += m->riv_qin[v] * dt;
+      }
+    }
+    m->newton_iters_river += it_sum; m->newton_calls_river += calls;
+    if (maxit > m->newton_maxit_river) m->newton_maxit_river = maxit;
+  }
+}
+
+/* surface_kinwave.jl:710-734 */
+void wfo_update_lateral_inflow_river(wfo_model* m) {
+  PFOR for (int64_t r = 0; r < m->cfg.nriv; ++r) {
+    const int64_t li = m->river_land_indices[r];
+    m->riv_inwater[r] = ((m->ssf_to_river_average[li] + m->olf_to_river_average[li]) +
+                         m->net_runoff_river[li] * m->area[li]) + 0.0 * m->area[li];
+  }
+}
+
+/* surface_kinwave.jl:613-662 */
+void wfo_update_river_flow_model(wfo_model* m, double dt) {
+  const int64_t n = m->cfg.nriv;
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->riv_qlat[i] = m->riv_inwater[i] / m->riv_flow_length[i];
+    m->riv_q_cumulative[i] = 0.0;
+    m->riv_actual_external_abstraction_cumulative[i] = 0.0;
+    m->riv_qin_cumulative[i] = 0.0;
+  }
+  double t = 0.0;
+  m->substeps_river = 0;
+  while (t < dt) {
+    double dt_s = m->cfg.adaptive
+                      ? wfo_stable_timestep_surface(m->riv_q, m->riv_alpha, m->riv_flow_length, n,
+                                                    0.05, m->scratch)
+                      : m->cfg.dt_river;
+    dt_s = check_timestepsize(dt_s, t, dt);
+    kinwave_river_update(m, dt_s);
+    t += dt_s;
+    m->substeps_river++;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->riv_q_average[i] = m->riv_q_cumulative[i] / dt;
+    m->riv_actual_external_abstraction_average[i] =
+        m->riv_actual_external_abstraction_cumulative[i] / dt;
+    m->riv_qin_average[i] = m->riv_qin_cumulative[i] / dt;
+  }
+}
+
+/* surface_routing.jl:7-46 */
+void wfo_surface_routing(wfo_model* m, double dt) {
+  wfo_update_lateral_inflow_overland(m);
+  wfo_update_overland_flow_model(m, dt);
+  wfo_update_lateral_inflow_river(m);
+  wfo_update_river_flow_model(m, dt);
+}
+
+/* sbm_model.jl:60-92 */
+void wfo_update_model(wfo_model* m, double dt) {
+  wfo_update_land_hydrology_model(m, dt);
+  wfo_exchange_recharge(m);
+  wfo_update_subsurface_flow_model(m, dt);
+  wfo_update_soil_water_storage(m, dt);
+  wfo_surface_routing(m, dt);
+  wfo_update_total_water_storage(m);
+}

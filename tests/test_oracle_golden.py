@@ -1,0 +1,471 @@
+"""
+Pins the CPU oracle (oracle/) against the reference's own known-answer tests
+(/root/reference/Wflow/test/*.jl, transcribed; file:line cited per test). Tolerance is the
+reference's own `≈` (isapprox default rtol = sqrt(eps) ≈ 1.5e-8); we use 1e-9.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from oracle import network as nw
+from oracle import oracle as orc
+
+RT = 1e-9
+
+
+def approx(x):
+    return pytest.approx(x, rel=RT, abs=1e-300)
+
+
+def test_gash_land_process_1_60():
+    dt = 86400.0
+    p = 2.0833333333333333e-7
+    out = orc.call_out("wfo_rainfall_interception_gash", 4, 0.0, 0.11, 0.24, p, 0.0015,
+                       4.6296296296296295e-8, dt)
+    assert out == (p, 0.0, 0.0, 0.0015)
+    out = orc.call_out("wfo_rainfall_interception_gash", 4, 0.003, 0.11, 0.24, p, 0.0015,
+                       4.6296296296296295e-8, dt)
+    assert out[0] == approx(1.5703703703703703e-7)
+    assert out[1] == approx(4.6296296296296295e-8)
+    assert out[2] == approx(5.0e-9)
+    assert out[3] == 0.0015
+    out = orc.call_out("wfo_rainfall_interception_gash", 4, 0.003, 0.11, 0.24,
+                       1.1574074074074074e-8, 0.0015, 4.6296296296296295e-8, dt)
+    assert out[0] == approx(2.7777777777777776e-9)
+    assert out[1] == approx(8.518518518518518e-9)
+    assert out[2] == approx(2.7777777777777777e-10)
+
+
+def test_gash_zero_ratio_nan_path():
+    # App. A-3 of SURVEY: E/R == 0 -> -Smax/(0*dt)*log(1) = -Inf*0 = NaN -> small-storm branch
+    out = orc.call_out("wfo_rainfall_interception_gash", 4, 0.003, 0.0, 0.24, 1e-7, 0.0, 1e-6,
+                       86400.0)
+    fi = 1.0 - 1.1 * 0.24
+    assert out[1] == fi * 1e-7
+
+
+def test_modrut_land_process_62_99():
+    dt = 86400.0
+    out = orc.call_out("wfo_rainfall_interception_modrut", 4, 9.953703703703703e-8,
+                       4.398148148148148e-8, 0.0015, 0.45, 0.0028, dt)
+    assert out[0] == approx(4.4791666666666666e-8)
+    assert out[1] == approx(4.398148148148148e-8)
+    assert out[2] == approx(4.479166666666667e-9)
+    assert out[3] == approx(0.002043)
+    out = orc.call_out("wfo_rainfall_interception_modrut", 4, 1.1574074074074074e-8,
+                       4.398148148148148e-8, out[3], 0.95, 0.0028, dt)
+    assert out[0] == approx(1.099537037037037e-8)
+    assert out[1] == approx(2.3645833333333334e-8)
+    assert out[2] == approx(5.787037037037037e-10)
+    assert out[3] == pytest.approx(0.0, abs=1e-18)
+
+
+def test_precipitation_hbv_land_process_101_140():
+    p = 3.4837962962962964e-7
+    out = orc.call_out("wfo_precipitation_hbv", 2, p, 273.69, 2.0, 273.15)
+    assert out[0] == approx(8.012731481481482e-8)
+    assert out[1] == approx(2.682523148148148e-7)
+    assert orc.call_out("wfo_precipitation_hbv", 2, p, 273.69, 0.0, 273.15) == (0.0, p)
+    assert orc.call_out("wfo_precipitation_hbv", 2, p, 272.15, 0.0, 273.15) == (p, 0.0)
+
+
+def test_snowpack_hbv_land_process_142_191():
+    args = (0.2015, 0.015, 8.012731481481482e-8, 2.682523148148148e-7)
+    out = orc.call_out("wfo_snowpack_hbv", 5, *args, 273.69, 273.15, 2.8935185185185185e-8, 0.10,
+                       86400.0)
+    for got, want in zip(out, (0.207073, 0.0207073, 0.22778030000000002, 1.5625e-8,
+                               2.1782060185185186e-7)):
+        assert got == approx(want)
+    # the reference test rebinds `snow_water` to the first call's output before the second call
+    args = (0.2015, out[1], 8.012731481481482e-8, 2.682523148148148e-7)
+    out = orc.call_out("wfo_snowpack_hbv", 5, *args, 272.65, 273.15, 2.8935185185185185e-8, 0.10,
+                       86400.0)
+    for got, want in zip(out, (0.20848550000000002, 0.02084855, 0.22933404999999998, 0.0,
+                               2.658940972222222e-7)):
+        assert got == pytest.approx(want, rel=RT, abs=1e-18)
+
+
+def test_glacier_hbv_land_process_193_219():
+    out = orc.call_out("wfo_glacier_hbv", 4, 0.35, 0.5, 0.0095, 278.15, 273.15,
+                       3.935185185185185e-8, 2.3148148148148148e-6, 9.259259259259259e-8, 86400.0)
+    for got, want in zip(out, (0.008835, 2.199074074074074e-8, 0.4849, 1.9675925925925924e-7)):
+        assert got == approx(want)
+
+
+def test_infiltration_land_process_221_241():
+    out = orc.call_out("wfo_infiltration", 2, 3.18287037037037e-7, 0.2, 5.787037037037037e-7,
+                       5.787037037037037e-8, 0.0235, 1.0, 86400.0)
+    assert out[1] == approx(5.787037037037037e-9)
+
+
+def test_unsatzone_flow_layer_land_process_243_261():
+    # The reference ASSIGNS (does not assert) usd_new/sum_ast here; usd_new matches, and
+    # the assigned sum_ast (1.6255e-7) equals sum_ast*dt of the restated value.
+    out = orc.call_out("wfo_unsatzone_flow_layer", 2, 0.043500000000000004, 2.962962962962963e-6,
+                       0.135, 12.6, 86400.0)
+    assert out[0] == approx(0.04349983744545384)
+    assert out[1] * 86400.0 == pytest.approx(1.6255454615829024e-7, rel=1e-6)
+    assert orc.call_out("wfo_unsatzone_flow_layer", 2, 0.0, 2.962962962962963e-6, 0.135, 12.6,
+                        86400.0) == (0.0, 0.0)
+
+
+def test_brooks_corey_land_process_263_293():
+    L = orc.lib()
+    h = L.wfo_head_brooks_corey(0.25, 0.6, 0.15, 10.5, -0.1)
+    assert h == approx(-0.9062998208338441)
+    assert L.wfo_vwc_brooks_corey(h, -0.1, 0.6, 0.15, 10.5) == approx(0.25 + 0.15)
+    h = L.wfo_head_brooks_corey(0.25, 0.6, 0.15, 2.0, -0.1)
+    assert h == -0.1
+    assert L.wfo_vwc_brooks_corey(h, -0.1, 0.6, 0.15, 2.0) == approx(0.6)
+
+
+def test_feddes_land_process_295_361():
+    L = orc.lib()
+    assert L.wfo_feddes_h3(-3.0, -6.0, 5.787037037037037e-9) == -6.0
+    assert L.wfo_feddes_h3(-3.0, -6.0, 3.472222222222222e-8) == approx(-4.5)
+    assert L.wfo_feddes_h3(-3.0, -6.0, 8.680555555555556e-8) == approx(-3.0)
+    f = lambda h, a: L.wfo_rwu_reduction_feddes(h, -0.1, -1.0, -3.0, -150.0, a)
+    for a, want in ((0.0, (0.0, 1.4 / 1.47, 1.0, 4 / 9, 0.0)), (0.5, (0.0, 1.4 / 1.47, 1.0, 1.0, 1.0))):
+        for h, w in zip((-160.0, -10.0, -1.5, -0.5, -0.05), want):
+            assert f(h, a) == pytest.approx(w, rel=RT, abs=1e-15)
+
+
+def test_soil_temperature_and_infiltration_reduction_land_process_363_392():
+    L = orc.lib()
+    assert L.wfo_soil_temperature(274.15, 2.0, 274.65) == approx(275.15)
+    assert L.wfo_infiltration_reduction_factor(273.25, 0.3, 1, 1) == approx(0.8325096069489968)
+    assert L.wfo_infiltration_reduction_factor(273.25, 0.3, 1, 0) == 1.0
+
+
+def test_soil_evaporation_land_process_394_464():
+    L = orc.lib()
+    a = (3.49537037037037e-9, 0.00123, 0.1)
+    assert L.wfo_soil_evaporation_unsaturated_store(*a, 0, 0.3, 0.241) == 0.0
+    assert L.wfo_soil_evaporation_unsaturated_store(*a, 1, 0.3, 0.241) == approx(5.946480713078224e-11)
+    assert L.wfo_soil_evaporation_unsaturated_store(*a, 2, 0.3, 0.241) == approx(1.783944213923467e-10)
+    # pinned NEGATIVE value: no clamp at zero
+    assert L.wfo_soil_evaporation_saturated_store(1.4467592592592592e-9, 0, 0.1, 0.3,
+                                                  0.32205961644649506, 86400.0) == approx(-7.455083714039237e-7)
+    assert L.wfo_soil_evaporation_saturated_store(1.4467592592592592e-9, 2, 0.1, 0.3,
+                                                  0.32205961644649506, 86400.0) == 0.0
+
+
+def test_actual_infiltration_soil_path_land_process_466_501():
+    out = orc.call_out("wfo_actual_infiltration_soil_path", 2, 1.883101851851852e-8,
+                       1.883101851851852e-8, 0.1, 2.645787037037037e-6, 5.787037037037037e-8, 0.9)
+    assert out[0] == approx(1.6947916666666665e-8)
+    assert out[1] == approx(1.883101851851852e-9)
+    assert orc.call_out("wfo_actual_infiltration_soil_path", 2, 1.883101851851852e-8, 0.0, 0.1,
+                        2.645787037037037e-6, 5.787037037037037e-8, 0.9) == (0.0, 0.0)
+
+
+def test_scurve_utils_66_77():
+    L = orc.lib()
+    out = L.wfo_scurve(2.0, 0.0, 3.0, 2.5)
+    assert out == approx(0.3325863502664285)
+    f = math.pi
+    assert f * L.wfo_scurve(2.0, 0.0 + math.log(f) / 2.5, f * 3.0, 2.5) == approx(out)
+
+
+def test_julia_numeric_helpers():
+    L = orc.lib()
+    # cld(x, y) = round((x - mod(x, -y))/y): exact ceil-division on floats
+    assert L.wfo_cld(0.0, 2e-4) == 0.0
+    assert L.wfo_cld(1e-9, 2e-4) == 1.0
+    assert L.wfo_cld(2e-4, 2e-4) == 1.0
+    assert L.wfo_cld(4.1e-4, 2e-4) == 3.0
+    # round(v; sigdigits = 12)
+    assert L.wfo_round_sigdigits12(2.0000000000003) == 2.0
+    assert L.wfo_round_sigdigits12(2.00000000001) == 2.00000000001
+    assert L.wfo_round_sigdigits12(0.0) == 0.0
+    assert L.wfo_round_sigdigits12(0.123456789012345) == 0.123456789012
+
+
+# ---------------------------------------------------------------------------------------------
+# struct-level tests (Wflow/test/soil.jl), driven through a 1-cell OracleModel
+# ---------------------------------------------------------------------------------------------
+def one_cell(N, fields, cfg=None, ints=None):
+    c = dict(n=1, nriv=0, N=N, gash=1, has_lai=0, snow=0, glacier=0, kv_profile=0)
+    c.update(cfg or {})
+    f = {}
+    for k, v in fields.items():
+        a = np.array(v, dtype=np.float64)
+        f[k] = a.reshape(1, -1) if a.size > 1 else a.reshape(1)
+    for k, v in (ints or {}).items():
+        f[k] = np.array(v, dtype=np.int64).reshape(1)
+    empty = dict(order=np.zeros(0, np.int64), up_ptr=np.zeros(1, np.int64), up_idx=np.zeros(0, np.int64),
+                 order_of_subdomains=[], order_subdomain=[], subdomain_indices=[])
+    land = dict(order=np.array([1]), up_ptr=np.array([0, 0]), up_idx=np.zeros(0, np.int64),
+                order_of_subdomains=[np.array([1])], order_subdomain=[np.array([1])],
+                subdomain_indices=[np.array([1])])
+    return orc.OracleModel(c, f, land, empty)
+
+
+def test_update_bc_soil_model_soil_1_64():
+    m = one_cell(1, dict(soil_fraction=[0.2397957498236932],
+                         potential_evaporation=[6.712962769799762e-9],
+                         canopy_potevap=[5.103222828877092e-9],
+                         interception_rate=[3.408447494157563e-10],
+                         canopy_gap_fraction=[0.3487189230509198], water_fraction=[0.0],
+                         river_fraction=[0.0], runoff_land=[0.0], runoff_river=[0.0],
+                         runoff_water_flux_surface=[2.8572021597728237e-9]))
+    m.sweep("update_bc_soil_model")
+    assert m.f["potential_transpiration"][0] == approx(4.762378079461335e-9)
+    assert m.f["potential_soilevaporation"][0] == approx(1.6097399409226706e-9)
+    assert m.f["soil_water_flux_surface"][0] == approx(2.8572021597728237e-9)
+
+
+def test_unsaturated_zone_flow_soil_66_106():
+    nan = np.nan
+    m = one_cell(6, dict(
+        unsaturated_layer_thickness=[0.05, 0.005081648613929929, nan, nan, nan, nan],
+        unsaturated_layer_depth=[0.0012855527211118947, 0.00020814868098590806, 0.0, 0.0, 0.0, 0.0],
+        theta_s=[0.4414711594581604], theta_r=[0.08942600339651108], kv_0=[4.21465379220468e-6],
+        hydraulic_conductivity_scale_parameter=[3.3079576678574085],
+        vertical_hydraulic_conductivity_factor=[1.0] * 6,
+        brooks_corey_exponent=[9.121646881103516, 9.247220993041992, 9.514554023742676,
+                               9.675407409667969, 9.831438064575195, 9.716856956481934],
+        infiltration=[2.635886044866978e-10]), ints=dict(n_unsatlayers=[2]))
+    m.sweep("unsaturated_zone_flow", 86400.0)
+    np.testing.assert_allclose(m.f["unsaturated_layer_depth"][0],
+                               [0.0013083267609636298, 0.00020814799974448514, 0, 0, 0, 0], rtol=RT)
+    assert m.f["transfer"][0] == approx(8.065015493937412e-15)
+
+
+def test_soil_evaporation_soil_108_137():
+    nan = np.nan
+    m = one_cell(6, dict(
+        potential_soilevaporation=[3.2407407407407403e-8],
+        unsaturated_layer_thickness=[0.05, 0.021472680450878443, nan, nan, nan, nan],
+        unsaturated_layer_depth=[0.001537249298366254, 4.8213268138994254e-11, 0.0, 0.0, 0.0, 0.0],
+        water_table_depth=[0.07147268045087844], theta_s=[0.44], theta_r=[0.09], theta_fc=[0.275],
+        actual_layer_thickness=[0.05, 0.1, 0.05, 0.2, 0.8, 0.8],
+        drainable_water_depth=[0.32113323174500624]), ints=dict(n_unsatlayers=[2]))
+    m.sweep("soil_evaporation", 86400.0)
+    assert m.f["soil_evaporation_saturated_zone"][0] == 0
+    assert m.f["soil_evaporation"][0] == approx(2.846757959937507e-9)
+    assert m.f["drainable_water_depth"][0] == approx(0.32113323174500624)
+
+
+def test_transpiration_soil_139_190():
+    nan = np.nan
+    m = one_cell(4, dict(
+        h3_high=[-4.0], h3_low=[-10.0], potential_transpiration=[5.965093586654767e-10],
+        water_table_depth=[0.10689587841733061],
+        unsaturated_layer_thickness=[0.1, 0.006895878417330607, nan, nan],
+        unsaturated_layer_depth=[0.010932797715287601, 0.000862043215499364, 0.0, 0.0],
+        rooting_depth=[0.453],
+        rootfraction=[0.22075055187637968, 0.6622516556291391, 0.11699779249448124, 0.0],
+        actual_layer_thickness=[0.1, 0.3, 0.2, nan],
+        cumulative_layer_depth=[0.0, 0.1, 0.4, 0.6, nan],
+        brooks_corey_exponent=[9.53970437651816, 10.007558316712927, 10.603868189606647,
+                               10.662998826419395],
+        theta_s=[0.4790319800376892], theta_r=[0.17089612782001495], air_entry_pressure=[-0.1],
+        h1=[0.0], h2=[-1.0], h3=[-10.0], h4=[-160.0], alpha_h1=[1.0],
+        wet_root_distribution_parameter=[-500000.0], drainable_water_depth=[0.07240310797113221]),
+        ints=dict(n_unsatlayers=[2]))
+    m.sweep("transpiration", 86400.0)
+    assert m.f["actual_evaporation_unsaturated_store"][0] == approx(5.965093586654767e-10)
+    assert m.f["actual_evaporation_saturated_zone"][0] == pytest.approx(0.0, abs=1e-18)
+    assert m.f["drainable_water_depth"][0] == approx(0.07240310797113221)
+    assert m.f["transpiration"][0] == approx(5.965093586654767e-10)
+
+
+def test_capillary_flux_soil_192_228():
+    m = one_cell(6, dict(
+        rooting_depth=[0.38410000000000005], kv_0=[2.335691087962963e-5],
+        hydraulic_conductivity_scale_parameter=[1.29274],
+        vertical_hydraulic_conductivity_factor=[1.0] * 6, water_table_depth=[1.2663358900000001],
+        unsaturated_layer_thickness=[0.05, 0.1, 0.05, 0.2, 0.8, 0.06633589243],
+        unsaturated_layer_depth=[0.008874129508377954, 0.018187210520563293, 0.00854476050597162,
+                                 0.017279406870498257, 0.14778493107547983, 0.01251769175241036],
+        actual_evaporation_unsaturated_store=[6.120061149641203e-9],
+        unsaturated_store_capacity=[0.3131741519821792],
+        drainable_water_depth=[0.16902603585525694], cap_hmax=[2.0], cap_n=[2.0],
+        theta_s=[0.4868114888668], theta_r=[0.0711537748575]), ints=dict(n_unsatlayers=[6]))
+    m.sweep("capillary_flux", 86400.0)
+    assert m.f["actual_capillary_flux"][0] == approx(8.235506588899334e-10)
+
+
+def test_update_soil_water_storage_soil_230_309():
+    m = one_cell(4, dict(
+        runoff=[0.0], water_table_depth=[1.2445135404970034],
+        unsaturated_layer_thickness=[0.1, 0.3, 0.8, 0.044513540497003304],
+        unsaturated_layer_depth=[0.014408928105784874, 0.01946108750081377, 0.12591094235311145,
+                                 0.007223489814154271],
+        actual_layer_thickness=[0.1, 0.3, 0.8, 0.8], theta_s=[0.4831694066524056],
+        theta_r=[0.12372369319200516], theta_fc=[0.28599992944511926], rooting_depth=[0.38],
+        cumulative_layer_depth=[0.0, 0.1, 0.4, 1.2, 2.0], soil_thickness=[2.0],
+        soil_water_capacity=[0.7188914269208908], saturation_excess_water=[0.0],
+        infiltration_excess=[0.0], runoff_land=[0.0], actual_open_water_evaporation_land=[0.0],
+        ssf_exfiltwater_average=[0.0]),
+        ints=dict(n_unsatlayers=[4], number_of_layers=[4]))
+    m.update_soil_water_storage(86400.0)
+    f = m.f
+    assert f["runoff"][0] == pytest.approx(0.0, abs=1e-18)
+    assert f["unsaturated_store_capacity"][0] == approx(0.28033060970129986)
+    assert f["saturated_water_depth"][0] == approx(0.27155636944572653)
+    assert f["drainable_water_depth"][0] == approx(0.14895887025738955)
+    assert f["exfiltration_saturated_water"][0] == 0.0
+    np.testing.assert_allclose(f["volumetric_water_content"][0],
+                               [0.2678129742498539, 0.1885939848613844, 0.2811123711333945,
+                                0.4721985172668562], rtol=RT)
+    np.testing.assert_allclose(f["relative_volumetric_water_content"][0],
+                               [55.42837989378741, 39.03268341595556, 58.18091279434587,
+                                97.72939072000436], rtol=RT)
+    assert f["volumetric_water_content_root_zone"][0] == approx(0.20944108733203426)
+    assert f["relative_volumetric_water_content_root_zone"][0] == approx(43.34734038380604)
+    assert f["total_soil_water_storage"][0] == approx(0.43856081721959095)
+
+
+def test_water_table_change_utils_241_277():
+    m = one_cell(5, dict(
+        unsaturated_layer_depth=[0.1, 0.125, 0.15, 0.17500000000000002, 0.2],
+        unsaturated_layer_thickness=[0.11, 0.145, 0.17, 0.20500000000000002, 0.24],
+        theta_s=[0.98], theta_r=[0.02]), ints=dict(n_unsatlayers=[5]))
+    out = (C.c_double * 2)()
+    orc.lib().wfo_water_table_change(m.h, -1.1574074074074073e-5, 0.43, 0, 86400.0, out)
+    assert out[0] == approx(-2.3255813953488373) and out[1] == 0.0
+    orc.lib().wfo_water_table_change(m.h, 5.787037037037037e-7, 0.43, 0, 86400.0, out)
+    assert out[0] == approx(0.4243119266055048) and out[1] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# routing (Wflow/test/routing_process.jl)
+# ---------------------------------------------------------------------------------------------
+def test_kinematic_wave_routing_process_1_20():
+    it = C.c_int64()
+    out = (C.c_double * 2)()
+    orc.lib().wfo_kinematic_wave(1.104e-6, 0.0, 1.142e-6, 2.586, 600.0, 1061.375, out, C.byref(it))
+    assert out[0] == approx(1.09308660753423e-6)
+    assert out[1] == approx(0.0006852061693892164)
+    assert it.value == 2  # 2 Newton iterations for this case
+    orc.lib().wfo_kinematic_wave(0.0, 0.0, 0.0, 2.586, 600.0, 1061.375, out, C.byref(it))
+    assert (out[0], out[1]) == (0.0, 0.0)
+
+
+def test_ssf_celerity_routing_process_22_37():
+    L = orc.lib()
+    assert L.wfo_ssf_celerity(0.3, 0.00586, 0.274, 0.0002795374658372667, 1.8001038115471601,
+                              0.0, 0) == approx(3.4838105601686665e-6)
+    assert L.wfo_ssf_celerity(0.3, 0.00586, 0.274, 0.0002795374658372667, 1.8001038115471601,
+                              0.2, 1) == approx(4.170921791220723e-6)
+
+
+def test_kw_ssf_newton_raphson_routing_process_39_48():
+    assert orc.lib().wfo_kw_ssf_newton_raphson(0.008738344907407408, 77.774, 0.0001418287037037037,
+                                               86400.0, 1103.816) == approx(0.01090947420564454)
+
+
+SSF_SHARED = dict(actual_layer_thickness=[0.1, 0.3, 0.8, 0.8],
+                  cumulative_layer_depth=[0.0, 0.1, 0.4, 1.2, 2.0],
+                  theta_s=[0.48642662167549133], theta_r=[0.11939866840839386],
+                  theta_fc=[0.28219206182657536], kh_0=[0.002379589787235966],
+                  hydraulic_conductivity_scale_parameter=[1.0141291422769427])
+
+
+def _ssf(m, *a):
+    out = (C.c_double * 4)()
+    orc.lib().wfo_kinematic_wave_ssf(m.h, *a, 0, out)
+    return tuple(out)
+
+
+def test_kinematic_wave_ssf_routing_process_100_253():
+    slope, sy, d, dt = 0.4522336721420288, 0.20423455984891598, 2.0, 86400.0
+    dx, dw = 1117.0150713112287, 517.495693771673
+    m = one_cell(4, dict(SSF_SHARED,
+                         unsaturated_layer_thickness=[0.1, 0.3, 0.11983408703759733, np.nan],
+                         unsaturated_layer_depth=[0.0001909439890049523, 0.01627933934181815,
+                                                  0.019508197676020186, 0.0],
+                         water_table_depth=[0.5198340870375974]),
+                 ints=dict(n_unsatlayers=[3], number_of_layers=[4]))
+    # first case exercises the inner sub-iteration loop (|dzi| > 0.1 m)
+    q, zi, exf, nf = _ssf(m, 0.0, 0.30038365579798126, 0.0005198340870375973,
+                          0.005618827458801466, slope, sy, d, dt, dx, dw, 0.0009215296489248933)
+    assert q == approx(0.23130576097772237)
+    assert zi == approx(0.1656875455413981)
+    assert exf == pytest.approx(0.0, abs=1e-18)
+    assert nf == approx(-3.904277181728481e-7)
+    # q_in + q_prev == 0 and q_net <= 0
+    assert _ssf(m, 0.0, 0.0, 0.0, 0.0, slope, sy, d, dt, dx, dw, 0.0009215296489248933) == (
+        0.0, d, 0.0, 0.0)
+    # exponential-constant profile
+    m2 = one_cell(4, dict(SSF_SHARED, z_exp=[0.2],
+                          unsaturated_layer_thickness=[0.1, 0.3, 0.348312461531486, np.nan],
+                          unsaturated_layer_depth=[0.0001909439890049523, 0.01627933934181815,
+                                                   0.058425012193036086, 0.0],
+                          water_table_depth=[0.748312461531486]),
+                  cfg=dict(kv_profile=1), ints=dict(n_unsatlayers=[3], number_of_layers=[4]))
+    q, zi, exf, nf = _ssf(m2, 0.0, 0.627032986563781, 0.748312461531486, 0.008957349820205272,
+                          slope, sy, d, dt, dx, dw, 0.0017762382461437296)
+    assert q == approx(0.5171363105669935)
+    assert zi == approx(1.1202203724020348)
+    assert exf == pytest.approx(0.0, abs=1e-18)
+    assert nf == approx(-8.791255611224121e-7)
+
+
+def test_kinwave_river_update_routing_process_290_383():
+    """2-node river graph. The reservoir on node 1 is out of scope; its pinned outflow
+    (3.0009999145314317) is injected as qin[2] exactly as update_reservoir_model! does
+    (surface_kinwave.jl:441-489)."""
+    L = orc.lib()
+    q = np.array([0.5499295110293246, 3.0005238507869465])
+    alpha = np.array([2.544585458995107, 2.5507721996678145])
+    length = np.array([1059.8125, 951.96875])
+    width = 94.73094177246094
+    work = np.zeros(2)
+    dt = L.wfo_stable_timestep_surface(q.ctypes.data, alpha.ctypes.data, length.ctypes.data, 2,
+                                       0.05, work.ctypes.data)
+    assert dt == approx(994.6119029285007)
+    out = (C.c_double * 2)()
+    L.wfo_kinematic_wave(0.0, q[0], 0.0, alpha[0], dt, length[0], out, None)
+    q1, a1 = out[0], out[1]
+    assert q1 == approx(0.37903337592185243)
+    assert a1 / width == approx(0.01500830539624011)
+    assert length[0] * a1 == approx(1506.7893805755937)
+    assert q1 * dt == approx(376.9911072990474)
+    L.wfo_kinematic_wave(3.0009999145314317 + q1, q[1], 0.0, alpha[1], dt, length[1], out, None)
+    assert out[0] == approx(3.1969698861305855)
+    assert out[1] / width == approx(0.05407828963124342)
+    assert length[1] * out[1] == approx(4876.828625285123)
+    assert out[0] * dt == approx(3179.744302049454)
+
+
+# ---------------------------------------------------------------------------------------------
+# indexing artefacts (Wflow/test/subdomains.jl:48-87)
+# ---------------------------------------------------------------------------------------------
+def test_streamorder_subbasins_subdomains_48_87():
+    down = np.zeros(16, dtype=np.int64)
+    for a, b in ((1, 3), (2, 3), (3, 4), (4, 5), (5, 6), (7, 9), (8, 9), (9, 4), (10, 12),
+                 (11, 12), (12, 16), (13, 15), (14, 15), (15, 16), (16, 5)):
+        down[a - 1] = b
+    g = nw.DiGraph1(down)
+    toposort = nw.topological_sort_by_dfs(g)
+    strord = nw.stream_order(g, toposort)
+    subbas = nw.subbasins(g, strord, toposort, 2)
+    subbas_fill = nw.fillnodata_upstream(g, toposort, subbas, 0)
+    graph_subbas = nw.graph_from_nodes(g, subbas, subbas_fill)
+    toposort_subbas = nw.topological_sort_by_dfs(graph_subbas)
+    dist = nw.distances_undirected(graph_subbas, int(toposort_subbas[-1]))
+    max_dist = max(int(dist.max()), 1)
+    order = nw.subbasins_order(graph_subbas, int(toposort_subbas[-1]), max_dist)
+    assert strord.tolist() == [1, 1, 2, 3, 4, 4, 1, 1, 2, 1, 1, 2, 1, 1, 2, 3]
+    assert strord[toposort[-1] - 1] == 4
+    assert subbas.tolist() == [0, 0, 5, 6, 0, 7, 0, 0, 4, 0, 0, 2, 0, 0, 1, 3]
+    assert subbas_fill.tolist() == [5, 5, 5, 6, 7, 7, 4, 4, 4, 2, 2, 2, 1, 1, 1, 3]
+    assert toposort_subbas.tolist() == [5, 4, 6, 2, 1, 3, 7]
+    assert max_dist == 2
+    assert [list(o) for o in order] == [[1, 2, 4, 5], [3, 6], [7]]
+
+
+def test_subdomains_single_thread_subdomains_25_31():
+    down = np.array([2, 3, 0, 3], dtype=np.int64)
+    g = nw.DiGraph1(down)
+    order = nw.topological_sort_by_dfs(g)
+    so = nw.stream_order(g, order)
+    a, b, c = nw.kinwave_set_subdomains(g, order, np.array([3]), so, 5, 1)
+    assert [x.tolist() for x in a] == [[1]]
+    assert b[0].tolist() == [1, 2, 3, 4]
+    assert c[0].tolist() == order.tolist()
