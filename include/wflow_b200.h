@@ -1,0 +1,191 @@
+/*
+ * wflow_b200.h -- C ABI of libwflow_b200.so: the B200 (sm_100a) implementation of Wflow.jl's
+ * per-timestep hot path for the `sbm` model type (SBM vertical land update + kinematic-wave
+ * routing of subsurface, overland and river flow).
+ *
+ * The reference has NO plugin/FFI API for this path (pure Julia, multiple dispatch). The entry
+ * points below are what Julia methods of the reference's `update!`-style functions would
+ * `ccall` (INTEGRATION.md shows the shim); each one cites the Julia function it replaces.
+ * All paths are relative to /root/reference/Wflow/src.
+ *
+ * Conventions: `extern "C"`, plain pointers and sizes, every call returns int32 status
+ * (0 = ok; message via wflowb200_last_error). Never throws across the ABI. Host arrays are
+ * owned by the caller and never retained after the call returns. Indices crossing the ABI are
+ * Julia `Int` (int64, 1-based). One handle per GPU; calls on a handle are not re-entrant.
+ * There is NO CPU fallback: every entry point fails with WFLOWB200_ERR_CUDA if no device.
+ */
+#ifndef WFLOW_B200_H
+#define WFLOW_B200_H
+#include <stdint.h>
+#include "wflow_b200_fields.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFLOWB200_OK 0
+#define WFLOWB200_ERR_ARG 1
+#define WFLOWB200_ERR_CUDA 2
+#define WFLOWB200_ERR_STATE 3
+#define WFLOWB200_ERR_GRAPH 4 /* cycle in the drainage graph (routing/utils.jl:26-31) */
+
+typedef struct WflowB200 WflowB200;
+
+/* Field ids: enum in WFLOWB200_FIELDS order. */
+enum {
+#define X(name, kind) WFLOWB200_F_##name,
+  WFLOWB200_FIELDS(X)
+#undef X
+  WFLOWB200_NUM_FIELDS
+};
+
+/* int64 per-cell arrays */
+#define WFLOWB200_I_number_of_layers 0   /* SbmSoilParameters.number_of_layers  soil/soil.jl:91 */
+#define WFLOWB200_I_n_unsatlayers 1      /* SbmSoilVariables.n_unsatlayers      soil/soil.jl:21 */
+
+/* The flags of config_structure.jl:62-115 (ModelSection) that change the hot path. */
+typedef struct {
+  int64_t n;                   /* active land cells  length(domain.land.network.indices)       */
+  int64_t nriv;                /* river cells        length(domain.river.network.indices)      */
+  int32_t n_layers;            /* maximum_number_of_layers = len(soil_layer__thickness)+1      */
+  int32_t device;              /* CUDA device ordinal                                          */
+  int32_t gash;                /* 1: Gash (dt >= 23 h), 0: modified Rutter         sbm.jl:26-33 */
+  int32_t has_lai;             /* !isnothing(leaf_area_index)                  canopy.jl:65,128 */
+  int32_t snow;                /* snow__flag                                                   */
+  int32_t glacier;             /* glacier__flag (only with snow, sbm.jl:41-54)                 */
+  int32_t soil_infiltration_reduction; /* soil_infiltration_reduction__flag                    */
+  int32_t kv_profile;          /* 0 exponential, 1 exponential_constant                        */
+  int32_t adaptive;            /* kinematic_wave__adaptive_time_step_flag                      */
+  int32_t nthreads;            /* Threads.nthreads() the artefacts should be built for
+                                  (subdomains.jl:176: 1 -> single sub-domain)                  */
+  int32_t land_streamorder_min;  /* land_streamorder__min_count  (5)                           */
+  int32_t river_streamorder_min; /* river_streamorder__min_count (6)                           */
+  double dt_land;              /* land_kinematic_wave__time_step       (3600 s)                */
+  double dt_river;             /* river_kinematic_wave__time_step      (900 s)                 */
+  double dt_ssf;               /* subsurface_kinematic_wave__time_step (86400 s)               */
+  double ssf_alpha_coefficient;/* subsurface_kinematic_wave__alpha_coefficient                 */
+  double kin_wave_min_flow_qroot; /* KIN_WAVE_MIN_FLOW^0.2 as the host evaluates it
+                                  (routing/utils.jl:2); 0 -> library uses pow(1e-30, 0.2)      */
+} WflowB200Config;
+
+/* The drainage network as the Julia model holds it (network.jl:48-81,175-208). */
+typedef struct {
+  int64_t d1, d2;                    /* size(subcatch_2d): Julia dimension order               */
+  const int64_t* indices;            /* 2n: CartesianIndex (i, j) pairs, 1-based, column-major
+                                        ascending (utils.jl:85-99)                             */
+  const uint8_t* ldd;                /* n: land local_drain_direction (PCRaster 1..9)          */
+  const int64_t* river_land_indices; /* nriv: NetworkRiver.land_indices, 1-based, ascending    */
+} WflowB200Domain;
+
+/* artefact ids for wflowb200_get_artifact (all returned as 1-based int64, reference layout) */
+#define WFLOWB200_A_ORDER 0            /* network.order (topological_sort_by_dfs)              */
+#define WFLOWB200_A_STREAMORDER 1      /* network.streamorder                                  */
+#define WFLOWB200_A_UPSTREAM_PTR 2     /* upstream_nodes as CSR by TOPOSORT POSITION: ptr n+1
+                                          (0-based offsets)                                    */
+#define WFLOWB200_A_UPSTREAM_IDX 3     /* ... node ids, ascending within a list                */
+#define WFLOWB200_A_SUBDOMAIN_LEVEL_PTR 4 /* order_of_subdomains CSR offsets                   */
+#define WFLOWB200_A_SUBDOMAIN_LEVEL_IDX 5 /* order_of_subdomains sub-domain ids                */
+#define WFLOWB200_A_SUBDOMAIN_PTR 6    /* CSR offsets of order_subdomain / subdomain_indices   */
+#define WFLOWB200_A_SUBDOMAIN_ORDER 7  /* order_subdomain (node ids)                           */
+#define WFLOWB200_A_SUBDOMAIN_INDICES 8 /* subdomain_indices (toposort positions)              */
+#define WFLOWB200_A_LDD 9              /* ldd after flowgraph's pit fix-up                     */
+#define WFLOWB200_A_WAVE_LEVEL_PTR 10  /* B200 wavefront: offsets of the topological-depth levels
+                                          in device order                                      */
+#define WFLOWB200_A_WAVE_PERM 11       /* B200 wavefront: node id held by each device slot     */
+
+#define WFLOWB200_DOMAIN_LAND 0
+#define WFLOWB200_DOMAIN_RIVER 1
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Replaces the construction of NetworkLand/NetworkRiver artefacts (network.jl:87-133,214-278,
+ * subdomains.jl:169-255, utils.jl:61-71) and allocates every model array in HBM (NaN-filled,
+ * like `fill(MISSING_VALUE, n)`). */
+int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom, WflowB200** out);
+void wflowb200_destroy(WflowB200* h);
+const char* wflowb200_last_error(const WflowB200* h); /* h may be NULL: error of a failed create */
+
+/* ---- field table ---------------------------------------------------------------------- */
+int32_t wflowb200_num_fields(void);
+const char* wflowb200_field_name(int32_t field_id);
+int32_t wflowb200_field_kind(int32_t field_id);
+int32_t wflowb200_field_id(const char* name); /* -1 if unknown */
+
+/* ---- host <-> device state (BMI get_value_ptr/set_value bmi.jl:208-248; set_states!
+ *      sbm_model.jl:104-193; output writers io.jl:815-885) ----------------------------- */
+
+/* Copy a host array into the device field. Element (cell c, layer k) is read from
+ * src[c*stride_cell + k*stride_layer]; Julia's Vector{SVector{N,Float64}} is
+ * (stride_cell = N, stride_layer = 1). Scalars: stride_cell = 1, stride_layer ignored. */
+int32_t wflowb200_set_field(WflowB200* h, int32_t field_id, const double* src,
+                            int64_t stride_cell, int64_t stride_layer);
+int32_t wflowb200_get_field(WflowB200* h, int32_t field_id, double* dst, int64_t stride_cell,
+                            int64_t stride_layer);
+int32_t wflowb200_set_field_i64(WflowB200* h, int32_t which, const int64_t* src);
+int32_t wflowb200_get_field_i64(WflowB200* h, int32_t which, int64_t* dst);
+
+/* update_forcing! hand-off (io.jl:108-160 -> AtmosphericForcing forcing.jl:2-10): three host
+ * vectors [m s-1, m s-1, K]; copied H2D asynchronously on the library's copy stream through
+ * pinned staging; the next update_* call waits for it on the device. */
+int32_t wflowb200_set_forcing(WflowB200* h, const double* precipitation,
+                              const double* potential_evaporation, const double* temperature);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+
+/* update_land_hydrology_model!(land, routing, domain, config, dt)            sbm.jl:82-132 */
+int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt);
+/* recharge / water-table hand-off between soil and subsurface flow     sbm_model.jl:74-81 */
+int32_t wflowb200_exchange_recharge(WflowB200* h);
+/* update_subsurface_flow_model!(ssf, soil, domain, dt)  lateral_subsurface_flow.jl:279-304 */
+int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt);
+/* update_soil_water_storage!(soil, external_models, dt)               soil/soil.jl:1294-1392 */
+int32_t wflowb200_update_soil_water_storage(WflowB200* h, double dt);
+/* update_lateral_inflow!(overland, ...)               routing/surface/surface_kinwave.jl:740-766 */
+int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h);
+/* update_overland_flow_model!(overland, domain.land, dt)              surface_kinwave.jl:347-385 */
+int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt);
+/* update_lateral_inflow!(river, ...)                                  surface_kinwave.jl:710-734 */
+int32_t wflowb200_update_lateral_inflow_river(WflowB200* h);
+/* update_river_flow_model!(river, domain, clock, dt)                  surface_kinwave.jl:613-662 */
+int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt);
+/* update_total_water_storage!(land, domain, routing)                          sbm.jl:143-182 */
+int32_t wflowb200_update_total_water_storage(WflowB200* h);
+/* update_model!(model::AbstractModel{<:SbmModel}): all of the above, in order, state resident
+ * on the device                                                          sbm_model.jl:60-92 */
+int32_t wflowb200_update_model(WflowB200* h, double dt);
+/* block until all device work of this handle is done */
+int32_t wflowb200_synchronize(WflowB200* h);
+
+/* ---- artefacts and statistics --------------------------------------------------------- */
+
+/* Copy an indexing artefact (1-based int64, reference layout). If dst is NULL only *len_out is
+ * set. */
+int32_t wflowb200_get_artifact(WflowB200* h, int32_t domain, int32_t artifact_id, int64_t* dst,
+                               int64_t capacity, int64_t* len_out);
+
+/* Host-only variant (no device needed): build just the indexing artefacts of a domain, e.g. to
+ * check them against the Julia model's `network` fields before moving a model to the GPU. */
+typedef struct WflowB200Network WflowB200Network;
+int32_t wflowb200_network_build(const WflowB200Config* cfg, const WflowB200Domain* dom,
+                                WflowB200Network** out);
+int32_t wflowb200_network_get(const WflowB200Network* net, int32_t domain, int32_t artifact_id,
+                              int64_t* dst, int64_t capacity, int64_t* len_out);
+void wflowb200_network_destroy(WflowB200Network* net);
+
+typedef struct {
+  int64_t newton_calls_land, newton_iters_land, newton_maxit_land;
+  int64_t newton_calls_river, newton_iters_river, newton_maxit_river;
+  int64_t substeps_land, substeps_river, substeps_ssf;
+  int64_t wave_levels_land, wave_levels_river;
+  int64_t kernel_launches;      /* kernels of this library launched since create            */
+  double ms_land_hydrology, ms_subsurface, ms_soil_storage, ms_overland, ms_river,
+      ms_total_storage;         /* CUDA-event time of the last update_model call, per stage  */
+} WflowB200Stats;
+int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out);
+/* enable per-stage CUDA-event timing inside update_model (off by default) */
+int32_t wflowb200_set_timing(WflowB200* h, int32_t enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

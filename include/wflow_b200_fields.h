@@ -1,0 +1,81 @@
+/*
+ * wflow_b200_fields.h -- the Float64 arrays of the Julia model structs that live on the device.
+ *
+ * X(name, kind): kind 0 = land scalar (n), 1 = land layered (n x N), 2 = land layered+1
+ * (n x (N+1)), 3 = river scalar (nriv). Names are the reference's struct field names; a
+ * component prefix is added where two structs share a name (snow_/glacier_/ssf_/olf_/riv_/
+ * recharge_/runoff_/soil_).
+ *
+ * Reference structs (all under /root/reference/Wflow/src):
+ *   AtmosphericForcing forcing.jl:2-10; VegetationParameters vegetation/parameters.jl:2-19;
+ *   InterceptionVariables canopy.jl:4-16, GashParameters :19-23; SnowHbv* snow/snow.jl:4-45;
+ *   Glacier* glacier/glacier.jl:4-60; OpenWaterRunoff* surfacewater/runoff.jl:4-27;
+ *   LandParameters domain.jl:2-29; SbmSoilParameters soil/soil.jl:87-150, SbmSoilBC :203-211,
+ *   SbmSoilVariables :4-84, Kv* :213-244; LateralSsf* routing/subsurface/
+ *   lateral_subsurface_flow.jl:2-54, RechargeVariables boundary_conditions.jl:204-213;
+ *   OverLandFlowVariables routing/surface/surface_kinwave.jl:154-178, LandFlowBC :181-185;
+ *   RiverFlowVariables :5-29, RiverFlowBC routing/surface/surface_flow.jl:9-34.
+ */
+#ifndef WFLOW_B200_FIELDS_H
+#define WFLOW_B200_FIELDS_H
+
+#define WFLOWB200_FIELDS(X) \
+  X(precipitation, 0) X(potential_evaporation, 0) X(temperature, 0) \
+  X(leaf_area_index, 0) X(storage_specific_leaf, 0) X(storage_wood, 0) \
+  X(light_extinction_coefficient, 0) X(canopy_gap_fraction, 0) X(maximum_canopy_storage, 0) \
+  X(crop_coefficient, 0) X(rooting_depth, 0) \
+  X(evaporation_to_precipitation_ratio, 0) X(canopy_potevap, 0) X(interception_rate, 0) \
+  X(canopy_storage, 0) X(stemflow, 0) X(throughfall, 0) \
+  X(temperature_threshold_snowfall, 0) X(temperature_interval_snowfall, 0) \
+  X(temperature_threshold_melt, 0) X(degree_day_factor, 0) X(water_holding_capacity, 0) \
+  X(snow_storage, 0) X(snow_water, 0) X(snow_water_equivalent, 0) X(snow_melt, 0) \
+  X(snow_runoff, 0) X(effective_precip, 0) X(snow_precip, 0) X(liquid_precip, 0) \
+  X(glacier_temperature_threshold_melt, 0) X(glacier_degree_day_factor, 0) \
+  X(glacier_snow_to_ice_fraction, 0) X(glacier_fraction, 0) X(glacier_store, 0) \
+  X(glacier_melt, 0) \
+  X(runoff_water_flux_surface, 0) X(waterdepth_land, 0) X(waterdepth_river, 0) \
+  X(runoff_river, 0) X(net_runoff_river, 0) X(runoff_land, 0) \
+  X(actual_open_water_evaporation_land, 0) X(actual_open_water_evaporation_river, 0) \
+  X(river_fraction, 0) X(water_fraction, 0) X(area, 0) X(slope, 0) X(flow_length, 0) \
+  X(flow_width, 0) X(surface_flow_width, 0) X(flow_fraction_to_river, 0) \
+  X(theta_s, 0) X(theta_r, 0) X(theta_fc, 0) X(soil_water_capacity, 0) \
+  X(vertical_hydraulic_conductivity_factor, 1) X(air_entry_pressure, 0) X(soil_thickness, 0) \
+  X(actual_layer_thickness, 1) X(cumulative_layer_depth, 2) \
+  X(infiltration_capacity_compacted_soil, 0) X(infiltration_capacity_soil, 0) \
+  X(maximum_leakage, 0) X(cap_hmax, 0) X(cap_n, 0) X(brooks_corey_exponent, 1) X(w_soil, 0) \
+  X(cf_soil, 0) X(compacted_soil_area_fraction, 0) X(wet_root_distribution_parameter, 0) \
+  X(rootfraction, 1) X(h1, 0) X(h2, 0) X(h3_high, 0) X(h3_low, 0) X(h4, 0) X(alpha_h1, 0) \
+  X(soil_fraction, 0) X(kv_0, 0) X(hydraulic_conductivity_scale_parameter, 0) X(z_exp, 0) \
+  X(soil_water_flux_surface, 0) X(potential_transpiration, 0) X(potential_soilevaporation, 0) \
+  X(h3, 0) X(unsaturated_store_capacity, 0) X(unsaturated_layer_depth, 1) \
+  X(unsaturated_layer_thickness, 1) X(saturated_water_depth, 0) X(drainable_water_depth, 0) \
+  X(water_table_depth, 0) X(transpiration, 0) X(actual_evaporation_unsaturated_store, 0) \
+  X(soil_evaporation, 0) X(soil_evaporation_saturated_zone, 0) X(actual_capillary_flux, 0) \
+  X(actual_evaporation_saturated_zone, 0) X(actual_evapotranspiration, 0) \
+  X(actual_infiltration, 0) X(actual_infiltration_soil, 0) \
+  X(actual_infiltration_compacted_soil, 0) X(infiltration, 0) X(infiltration_excess, 0) \
+  X(saturation_excess_water, 0) X(exfiltration_saturated_water, 0) X(excess_water_soil, 0) \
+  X(excess_water_compacted_soil, 0) X(runoff, 0) X(net_runoff, 0) \
+  X(volumetric_water_content, 1) X(relative_volumetric_water_content, 1) \
+  X(root_zone_storage, 0) X(volumetric_water_content_root_zone, 0) \
+  X(relative_volumetric_water_content_root_zone, 0) X(unsaturated_store_depth, 0) \
+  X(transfer, 0) X(recharge, 0) X(actual_leakage, 0) X(total_storage, 0) \
+  X(total_soil_water_storage, 0) X(soil_surface_temperature, 0) X(f_infiltration_reduction, 0) \
+  X(kh_0, 0) X(ssf_soil_thickness, 0) X(specific_yield, 0) X(ssf_top, 0) \
+  X(ssf_water_table_depth, 0) X(ssf_head, 0) X(ssf_exfiltwater_cumulative, 0) \
+  X(ssf_exfiltwater_average, 0) X(ssf_q, 0) X(ssf_q_cumulative, 0) X(ssf_q_average, 0) \
+  X(ssf_q_in, 0) X(ssf_q_in_cumulative, 0) X(ssf_q_in_average, 0) X(ssf_q_max, 0) \
+  X(ssf_to_river_cumulative, 0) X(ssf_to_river_average, 0) X(ssf_q_net_bnds, 0) \
+  X(ssf_q_net_cumulative, 0) X(ssf_q_net_average, 0) X(ssf_storage, 0) \
+  X(recharge_rate, 0) X(recharge_flux, 0) X(recharge_flux_cumulative, 0) \
+  X(recharge_flux_average, 0) \
+  X(olf_alpha, 0) X(olf_inwater, 0) X(olf_q, 0) X(olf_qlat, 0) X(olf_qin, 0) \
+  X(olf_qin_cumulative, 0) X(olf_qin_average, 0) X(olf_q_cumulative, 0) X(olf_q_average, 0) \
+  X(olf_storage, 0) X(olf_h, 0) X(olf_to_river_cumulative, 0) X(olf_to_river_average, 0) \
+  X(riv_flow_length, 3) X(riv_flow_width, 3) X(riv_alpha, 3) X(riv_external_inflow, 3) \
+  X(riv_abstraction, 3) X(riv_actual_external_abstraction_cumulative, 3) \
+  X(riv_actual_external_abstraction_average, 3) X(riv_inwater, 3) X(riv_q, 3) \
+  X(riv_qlat, 3) X(riv_qin, 3) X(riv_qin_cumulative, 3) X(riv_qin_average, 3) \
+  X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3)
+
+#endif

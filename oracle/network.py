@@ -241,7 +241,7 @@ def kinwave_set_subdomains(g: DiGraph1, toposort, index_pit, streamorder, min_st
     """subdomains.jl:169-255. Returns (subbas_order, indices_subbas, topo_subbas) as lists of
     int64 arrays (1-based)."""
     n = len(toposort)
-    if nthreads <= 1:
+    if nthreads <= 1 or n == 0:  # (n == 0 is not reachable in the reference: no river cells)
         return ([np.array([1], dtype=np.int64)], [np.arange(1, n + 1, dtype=np.int64)],
                 [np.asarray(toposort, dtype=np.int64)])
     index_pit = np.asarray(index_pit, dtype=np.int64)

@@ -67,6 +67,8 @@ def lib():
                   "wfo_update_lateral_inflow_river"):
             getattr(L, f).argtypes = [C.c_void_p]
             getattr(L, f).restype = None
+        L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.wfo_get_stats.restype = None
         L.wfo_sweep.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.wfo_sweep.restype = C.c_int
         d = C.c_double
@@ -111,6 +113,22 @@ def field_table():
     L = lib()
     return [(L.wfo_field_name(i).decode(), L.wfo_field_kind(i)) for i in range(L.wfo_num_fields())]
 
+
+# Non-NaN defaults of the reference's structs (canopy.jl:11, runoff.jl:26, soil.jl:71-83,
+# lateral_subsurface_flow.jl:9-38, boundary_conditions.jl:204-213, surface_kinwave.jl:5-29,
+# 154-185, surface_flow.jl:9-34); every other field starts as MISSING_VALUE (NaN).
+ZERO_DEFAULTS = (
+    "canopy_storage", "waterdepth_river", "unsaturated_store_depth", "total_storage",
+    "ssf_exfiltwater_cumulative", "ssf_exfiltwater_average", "ssf_q_cumulative", "ssf_q_average",
+    "ssf_q_in_cumulative", "ssf_q_in_average", "ssf_to_river_cumulative", "ssf_to_river_average",
+    "ssf_q_net_cumulative", "ssf_q_net_average", "recharge_flux", "recharge_flux_cumulative",
+    "olf_inwater", "olf_q", "olf_qlat", "olf_qin", "olf_qin_cumulative", "olf_qin_average",
+    "olf_q_cumulative", "olf_q_average", "olf_storage", "olf_h", "olf_to_river_cumulative",
+    "olf_to_river_average", "riv_external_inflow", "riv_abstraction",
+    "riv_actual_external_abstraction_cumulative", "riv_actual_external_abstraction_average",
+    "riv_inwater", "riv_q", "riv_qlat", "riv_qin", "riv_qin_cumulative", "riv_qin_average",
+    "riv_q_cumulative", "riv_q_average", "riv_storage", "riv_h")
+VALUE_DEFAULTS = {"f_infiltration_reduction": 1.0, "soil_surface_temperature": 10.0 + 273.15}
 
 INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_indices")
 
@@ -160,6 +178,10 @@ class OracleModel:
             if name in fields and fields[name] is not None:
                 a = np.ascontiguousarray(np.array(fields[name], dtype=np.float64, copy=True))
                 assert a.shape == shapes[kind], (name, a.shape, shapes[kind])
+            elif name in ZERO_DEFAULTS:
+                a = np.zeros(shapes[kind])
+            elif name in VALUE_DEFAULTS:
+                a = np.full(shapes[kind], VALUE_DEFAULTS[name])
             else:
                 a = np.full(shapes[kind], np.nan)
             self.f[name] = a
@@ -212,6 +234,15 @@ class OracleModel:
     def update_total_water_storage(self): self._L.wfo_update_total_water_storage(self.h)
     def update_diagnostic_vars(self): self._L.wfo_update_diagnostic_vars(self.h)
     def update_model(self, dt): self._L.wfo_update_model(self.h, dt)
+
+    def newton_stats(self):
+        """Counters kept by wfo_routing.c (the struct tail after the network blocks)."""
+        out = (C.c_int64 * 9)()
+        self._L.wfo_get_stats(self.h, out)
+        keys = ("newton_iters_land", "newton_iters_river", "newton_calls_land",
+                "newton_calls_river", "newton_maxit_land", "newton_maxit_river",
+                "substeps_land", "substeps_river", "substeps_ssf")
+        return dict(zip(keys, list(out)))
 
     def sweep(self, name, dt=0.0):
         rc = self._L.wfo_sweep(self.h, name.encode(), dt)

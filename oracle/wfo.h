@@ -171,6 +171,7 @@ void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182
 void wfo_update_model(wfo_model*, double dt);                  /* sbm_model.jl:60-92 */
 void wfo_update_diagnostic_vars(wfo_model*);                   /* soil.jl:1400-1436 */
 int  wfo_sweep(wfo_model*, const char* name, double dt);                   /* test hook */
+void wfo_get_stats(wfo_model*, int64_t out[9]);
 
 /* scalar kernels exported for the known-answer tests */
 void wfo_rainfall_interception_gash(double cmax, double e_r, double gap, double p, double cs,

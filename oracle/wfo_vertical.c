@@ -806,3 +806,10 @@ int wfo_sweep(wfo_model* m, const char* name, double dt) {
   if (!strcmp(name, "update_snow_model")) { update_snow_model(m, dt); return 0; }
   return -1;
 }
+
+void wfo_get_stats(wfo_model* m, int64_t out[9]) {
+  out[0] = m->newton_iters_land; out[1] = m->newton_iters_river;
+  out[2] = m->newton_calls_land; out[3] = m->newton_calls_river;
+  out[4] = m->newton_maxit_land; out[5] = m->newton_maxit_river;
+  out[6] = m->substeps_land; out[7] = m->substeps_river; out[8] = m->substeps_ssf;
+}

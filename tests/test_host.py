@@ -1,0 +1,139 @@
+"""CPU-side tests of the product: the C-ABI library loads and exports every symbol the header
+declares, the host-built indexing artefacts are bit-exact against the oracle's independent
+restatement, and the product fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity  # noqa: E402
+from oracle.oracle import _csr  # noqa: E402
+
+
+def test_library_exports_every_header_symbol(pkg):
+    L = pkg._lib.lib()
+    syms = pkg.header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), f"libwflow_b200.so does not export {s}"
+
+
+def test_field_table_matches_oracle_schema(pkg):
+    """The product and the oracle keep separate field lists; they must agree on names/kinds for
+    every product field (the oracle has a few extra fields for profiles not yet on the GPU)."""
+    from oracle import oracle as orc
+    prod = dict(pkg._lib.field_table())
+    ora = dict(orc.field_table())
+    for name, kind in prod.items():
+        assert ora.get(name) == kind, name
+    L = pkg._lib.lib()
+    assert L.wflowb200_field_id(b"olf_q") == list(prod).index("olf_q")
+    assert L.wflowb200_field_id(b"nope") == -1
+
+
+@pytest.mark.parametrize("d1,d2,ml,mr,seed,nthreads", [
+    (40, 60, 5, 6, 42, 8), (120, 200, 3, 3, 1, 2), (64, 512, 2, 4, 9, 8), (200, 100, 4, 2, 3, 4),
+    (50, 50, 5, 6, 7, 1), (1, 30, 1, 1, 2, 8), (30, 1, 1, 1, 2, 8)])
+def test_indexing_artifacts_bit_exact(pkg, d1, d2, ml, mr, seed, nthreads):
+    cfg, dom, _ = pkg.synthetic.make_basin(d1, d2, seed=seed, nthreads=nthreads)
+    cfg["land_streamorder_min"], cfg["river_streamorder_min"] = ml, mr
+    art = pkg.build_network_artifacts(cfg, dom)
+    land, river = parity.oracle_networks(cfg, dom)
+    for name, o in (("land", land), ("river", river)):
+        a = art[name]
+        assert np.array_equal(a["order"], o["order"]), name
+        assert np.array_equal(a["streamorder"], o["streamorder"]), name
+        assert np.array_equal(a["upstream_ptr"], o["up_ptr"]), name
+        assert np.array_equal(a["upstream_idx"], o["up_idx"]), name
+        assert np.array_equal(a["ldd"], o["ldd"]), name
+        lp, li = _csr(o["order_of_subdomains"])
+        assert np.array_equal(a["subdomain_level_ptr"], lp), name
+        assert np.array_equal(a["subdomain_level_idx"], li), name
+        sp, so = _csr(o["order_subdomain"])
+        _, si = _csr(o["subdomain_indices"])
+        assert np.array_equal(a["subdomain_ptr"], sp), name
+        assert np.array_equal(a["subdomain_order"], so), name
+        assert np.array_equal(a["subdomain_indices"], si), name
+
+
+def test_masked_raster_artifacts_and_pit_fixup(pkg):
+    mask = np.ones((37, 53), dtype=bool)
+    mask[:5, :7] = False
+    mask[20:, 40:] = False
+    cfg, dom, _ = pkg.synthetic.make_basin(37, 53, seed=4, mask=mask)
+    # hand the library the raw LDD of the unmasked raster (it still points out of the mask):
+    # flowgraph must turn exactly those cells into pits (routing/utils.jl:20-24)
+    _, ldd_full, _, _ = pkg.synthetic.scheidegger_ldd(37, 53, 4)
+    raw = ldd_full[np.nonzero(mask.ravel(order="F"))[0]]
+    assert (raw != dom["ldd"]).any()
+    dom2 = dict(dom, ldd=raw)
+    art = pkg.build_network_artifacts(cfg, dom2)
+    assert np.array_equal(art["land"]["ldd"], dom["ldd"])
+    land, _ = parity.oracle_networks(cfg, dom2)
+    assert np.array_equal(art["land"]["order"], land["order"])
+
+
+def test_wavefront_levels_are_a_valid_schedule(pkg):
+    """Every drainage edge spans exactly one wavefront level (the invariant the skewed
+    wavefront relies on), and slots inside a level are ascending node ids."""
+    cfg, dom, _ = pkg.synthetic.make_basin(90, 140, seed=5)
+    a = pkg.build_network_artifacts(cfg, dom)["land"]
+    perm, lp = a["wave_perm"], a["wave_level_ptr"]
+    n = cfg["n"]
+    assert sorted(perm.tolist()) == list(range(1, n + 1))
+    level = np.zeros(n, dtype=np.int64)
+    for l in range(len(lp) - 1):
+        seg = perm[lp[l]:lp[l + 1]]
+        assert np.all(np.diff(seg) > 0)
+        level[seg - 1] = l
+    down = dom["down"]
+    has = down > 0
+    assert np.all(level[down[has] - 1] == level[has] + 1)
+    assert np.all(level[~has] == len(lp) - 2)
+
+
+def test_cycle_is_rejected(pkg):
+    # two cells pointing at each other: 6 (east, +1 in d1) and 4 (west)
+    cfg = dict(n_layers=4, nthreads=1)
+    dom = dict(d1=2, d2=1, indices=np.array([[1, 1], [2, 1]]), ldd=np.array([6, 4], np.uint8),
+               river_land_indices=np.zeros(0, np.int64))
+    with pytest.raises(RuntimeError, match="cycle"):
+        pkg.build_network_artifacts(cfg, dom)
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg, dom, fields = pkg.synthetic.make_basin(8, 8, seed=1)
+    with pytest.raises(pkg.WflowB200Error, match="no CUDA device|CUDA"):
+        pkg.SbmModel(cfg, dom, fields)
+
+
+def test_oracle_water_balance_and_determinism(pkg):
+    """The oracle itself: river-reach water balance closes (reference invariant,
+    test/run_sbm.jl:1238-1264) and thread count does not change results."""
+    cfg, dom, fields = pkg.synthetic.make_basin(48, 64, seed=13)
+    dt = cfg["dt"]
+    ora = parity.make_oracle(cfg, dom, fields)
+    for step in range(3):
+        p, e, t = pkg.synthetic.make_forcing(13, step, dom["gid"], dt)
+        ora.f["precipitation"][:], ora.f["potential_evaporation"][:], ora.f["temperature"][:] = p, e, t
+        r0 = ora.f["riv_storage"].copy()
+        ora.update_model(dt)
+    f = ora.f
+    err = (f["riv_storage"] - r0) - (f["riv_qin_average"] + f["riv_inwater"] - f["riv_q_average"]) * dt
+    assert np.max(np.abs(err) / np.maximum(np.abs(f["riv_q_average"] * dt), 1.0)) < 1e-6
+    assert not np.isnan(f["total_storage"]).any()
+    # single sub-domain walk (nthreads = 1 artefacts) gives the same numbers
+    cfg1 = dict(cfg, nthreads=1)
+    ora1 = parity.make_oracle(cfg1, dom, fields)
+    for step in range(3):
+        p, e, t = pkg.synthetic.make_forcing(13, step, dom["gid"], dt)
+        ora1.f["precipitation"][:], ora1.f["potential_evaporation"][:], ora1.f["temperature"][:] = p, e, t
+        ora1.update_model(dt)
+    for k in ("riv_q", "olf_q", "ssf_q", "water_table_depth", "total_storage"):
+        assert np.array_equal(ora1.f[k], f[k]), k

@@ -1,0 +1,686 @@
+// api.cu -- the C ABI of libwflow_b200.so (include/wflow_b200.h): handle lifetime, HBM layout,
+// host<->device field transfer through the slot permutation, and the orchestration of the hot
+// path (update_model!, sbm_model.jl:60-92). No CPU fallback: every entry point needs the device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wflow_b200.h"
+#include "kernels.cuh"
+#include "model.cuh"
+#include "network.hpp"
+
+using namespace wfb;
+
+namespace {
+
+const char* kFieldNames[] = {
+#define X(name, kind) #name,
+    WFLOWB200_FIELDS(X)
+#undef X
+};
+const int kFieldKinds[] = {
+#define X(name, kind) kind,
+    WFLOWB200_FIELDS(X)
+#undef X
+};
+std::string g_create_error;
+
+struct DomainDev {
+  Network nw;
+  int32_t* node_of_slot = nullptr;  // device, 0-based node id per slot
+  int32_t* level_ptr = nullptr;
+  int32_t* level_of = nullptr;
+  int32_t* up_ptr = nullptr;
+  int32_t* up_idx = nullptr;
+  DevNet dev{};
+};
+
+// NetworkLand + NetworkRiver artefacts (network.jl:87-133,214-278; domain.jl:80-125).
+int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, Network& land,
+                       Network& river, std::string& errmsg) {
+  std::string err;
+  const int64_t n = cfg->n, nriv = cfg->nriv;
+  if (!build_graph(land, dom->d1, dom->d2, dom->indices, dom->ldd, n, err) ||
+      !build_artifacts(land, cfg->nthreads, cfg->land_streamorder_min, nullptr, err)) {
+    errmsg = "land network: " + err;
+    return WFLOWB200_ERR_GRAPH;
+  }
+  std::vector<int64_t> ridx(2 * (size_t)nriv), rso(nriv);
+  std::vector<uint8_t> rldd(nriv);
+  for (int64_t r = 0; r < nriv; ++r) {
+    const int64_t li = dom->river_land_indices[r];
+    if (li < 1 || li > n || (r && li <= dom->river_land_indices[r - 1])) {
+      errmsg = "river_land_indices must be ascending 1-based land indices";
+      return WFLOWB200_ERR_ARG;
+    }
+    ridx[2 * r] = dom->indices[2 * (li - 1)];
+    ridx[2 * r + 1] = dom->indices[2 * (li - 1) + 1];
+    rldd[r] = land.ldd[li - 1];
+    rso[r] = land.streamorder[li - 1];  // network.jl:245
+  }
+  if (!build_graph(river, dom->d1, dom->d2, ridx.data(), rldd.data(), nriv, err) ||
+      !build_artifacts(river, cfg->nthreads, cfg->river_streamorder_min, rso.data(), err)) {
+    errmsg = "river network: " + err;
+    return WFLOWB200_ERR_GRAPH;
+  }
+  return WFLOWB200_OK;
+}
+
+int32_t copy_artifact(const Network& nw, int32_t id, int64_t* dst, int64_t capacity,
+                      int64_t* len_out, std::string& errmsg) {
+  std::vector<int64_t> tmp;
+  const std::vector<int64_t>* src = nullptr;
+  switch (id) {
+    case WFLOWB200_A_ORDER: src = &nw.order; break;
+    case WFLOWB200_A_STREAMORDER: src = &nw.streamorder; break;
+    case WFLOWB200_A_UPSTREAM_PTR: src = &nw.up_ptr; break;
+    case WFLOWB200_A_UPSTREAM_IDX: src = &nw.up_idx; break;
+    case WFLOWB200_A_SUBDOMAIN_LEVEL_PTR: src = &nw.lvl_ptr; break;
+    case WFLOWB200_A_SUBDOMAIN_LEVEL_IDX: src = &nw.lvl_idx; break;
+    case WFLOWB200_A_SUBDOMAIN_PTR: src = &nw.sub_ptr; break;
+    case WFLOWB200_A_SUBDOMAIN_ORDER: src = &nw.sub_order; break;
+    case WFLOWB200_A_SUBDOMAIN_INDICES: src = &nw.sub_indices; break;
+    case WFLOWB200_A_LDD: tmp.assign(nw.ldd.begin(), nw.ldd.end()); src = &tmp; break;
+    case WFLOWB200_A_WAVE_LEVEL_PTR: src = &nw.wave_level_ptr; break;
+    case WFLOWB200_A_WAVE_PERM: src = &nw.perm; break;
+    default: errmsg = "bad artefact id"; return WFLOWB200_ERR_ARG;
+  }
+  *len_out = (int64_t)src->size();
+  if (dst) {
+    if (capacity < *len_out) { errmsg = "artefact buffer too small"; return WFLOWB200_ERR_ARG; }
+    memcpy(dst, src->data(), src->size() * sizeof(int64_t));
+  }
+  return WFLOWB200_OK;
+}
+
+}  // namespace
+
+struct WflowB200Network {
+  Network land, river;
+};
+
+struct WflowB200 {
+  WflowB200Config cfg{};
+  int n = 0, nriv = 0, N = 0, ns = 0, nrs = 0;
+  DomainDev land, river;
+  DevFields f{};
+  KCfg kc{};
+  double* pool = nullptr;  // one HBM allocation holding every Float64 field
+  size_t pool_doubles = 0;
+  std::vector<double*> field_ptr;
+  int32_t* riv_of_land = nullptr;
+  double* d_stage = nullptr;  // device staging for set/get (n*(N+1) doubles, >= 3n)
+  size_t stage_doubles = 0;
+  double* h_pinned = nullptr;  // pinned host staging for forcing (3n doubles)
+  double* d_forcing = nullptr; // device staging for forcing (3n doubles)
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
+  bool forcing_pending = false;
+  unsigned* d_barrier = nullptr;
+  RoutingStats* d_stats = nullptr;
+  double* d_dts = nullptr;  // sub-step lengths, 3 x kMaxSub
+  unsigned long long* d_count = nullptr;
+  double* d_min = nullptr;
+  int grid_olf = 0, grid_riv = 0, grid_ssf = 0;
+  int64_t launches = 0;
+  int64_t sub_land = 0, sub_river = 0, sub_ssf = 0;
+  bool timing = false;
+  // the discharge fields flip between their two parity buffers (routing.cu)
+  double* field_ptr_current(int id) const {
+    if (id == WFLOWB200_F_olf_q) return f.olf_q;
+    if (id == WFLOWB200_F_riv_q) return f.riv_q;
+    if (id == WFLOWB200_F_ssf_q) return f.ssf_q;
+    return field_ptr[id];
+  }
+  cudaEvent_t ev[7] = {};
+  float ms[6] = {};
+  std::string err;
+};
+
+namespace {
+
+constexpr int kMaxSub = 8192;
+constexpr int kBlock = 256;
+
+int32_t fail(WflowB200* h, int32_t code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (expr);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(h, WFLOWB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+int layers_of(const WflowB200* h, int kind) { return kind == 1 ? h->N : kind == 2 ? h->N + 1 : 1; }
+
+template <class T>
+cudaError_t upload_i32(const std::vector<T>& src, int32_t** dst, int64_t offset) {
+  std::vector<int32_t> tmp(src.size());
+  for (size_t i = 0; i < src.size(); ++i) tmp[i] = (int32_t)(src[i] + offset);
+  cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(tmp.size(), 1) * sizeof(int32_t));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+}
+
+// Device copies of the wavefront artefacts of one domain.
+int32_t upload_domain(WflowB200* h, DomainDev& d) {
+  const Network& nw = d.nw;
+  const int64_t n = nw.n;
+  CUDA_TRY(h, upload_i32(nw.perm, &d.node_of_slot, -1));
+  CUDA_TRY(h, upload_i32(nw.wave_level_ptr, &d.level_ptr, 0));
+  std::vector<int64_t> level_of(n), up_ptr(n + 1, 0), up_idx;
+  for (int64_t l = 0; l < nw.n_wave_levels; ++l)
+    for (int64_t p = nw.wave_level_ptr[l]; p < nw.wave_level_ptr[l + 1]; ++p) level_of[p] = l;
+  up_idx.reserve(nw.in_idx.size());
+  for (int64_t p = 0; p < n; ++p) {
+    const int64_t v = nw.perm[p] - 1;  // in-neighbours are already ascending by node id
+    for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e)
+      up_idx.push_back(nw.slot_of[nw.in_idx[e] - 1]);
+    up_ptr[p + 1] = (int64_t)up_idx.size();
+  }
+  CUDA_TRY(h, upload_i32(level_of, &d.level_of, 0));
+  CUDA_TRY(h, upload_i32(up_ptr, &d.up_ptr, 0));
+  CUDA_TRY(h, upload_i32(up_idx, &d.up_idx, 0));
+  d.dev.n = (int32_t)n;
+  d.dev.n_levels = (int32_t)nw.n_wave_levels;
+  d.dev.level_ptr = d.level_ptr;
+  d.dev.level_of = d.level_of;
+  d.dev.up_ptr = d.up_ptr;
+  d.dev.up_idx = d.up_idx;
+  return WFLOWB200_OK;
+}
+
+void free_domain(DomainDev& d) {
+  cudaFree(d.node_of_slot); cudaFree(d.level_ptr); cudaFree(d.level_of);
+  cudaFree(d.up_ptr); cudaFree(d.up_idx);
+}
+
+// The reference's `while t < dt` sub-stepping with a fixed internal step
+// (surface_kinwave.jl:371-379; routing/timestepping.jl:11-16), evaluated on the host.
+int fixed_substeps(double dt, double dt_fixed, std::vector<double>& out) {
+  out.clear();
+  if (!(dt_fixed > 0.0)) return -1;
+  double t = 0.0;
+  while (t < dt) {
+    double dt_s = dt_fixed;
+    if (t + dt_s > dt) dt_s = dt - t;
+    out.push_back(dt_s);
+    t += dt_s;
+    if ((int)out.size() > kMaxSub) return -1;
+  }
+  return (int)out.size();
+}
+
+int32_t wait_forcing(WflowB200* h) {
+  if (h->forcing_pending) {
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->forcing_ready, 0));
+    h->launches += launch_gather_forcing(h->f, h->d_forcing, h->land.node_of_slot, h->n, h->stream);
+    CUDA_TRY(h, cudaEventRecord(h->forcing_consumed, h->stream));
+    h->forcing_pending = false;
+  }
+  return WFLOWB200_OK;
+}
+
+int32_t check_launch(WflowB200* h, int rc, const char* what) {
+  if (rc < 0) return fail(h, WFLOWB200_ERR_CUDA, std::string(what) + ": launch failed (" +
+                                                     std::to_string(rc) + ")");
+  h->launches += rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(h, WFLOWB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return WFLOWB200_OK;
+}
+
+// Run one routing component with the fixed-step skewed wavefront.
+template <class Launch>
+int32_t run_wave(WflowB200* h, double dt, double dt_fixed, int slot, int grid, int64_t& substeps,
+                 double** q_a, double** q_b, Launch launch, const char* what) {
+  std::vector<double> dts;
+  const int S = fixed_substeps(dt, dt_fixed, dts);
+  if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
+  double* d_dts = h->d_dts + (size_t)slot * kMaxSub;
+  CUDA_TRY(h, cudaMemcpyAsync(d_dts, dts.data(), S * sizeof(double), cudaMemcpyHostToDevice,
+                              h->stream));
+  WaveLaunch w{};
+  w.barrier = h->d_barrier + slot * 32;
+  w.stats = h->d_stats;
+  w.dts = d_dts;
+  w.S = S;
+  w.dt = dt;
+  w.grid = grid;
+  w.block = kBlock;
+  int32_t rc = check_launch(h, launch(w), what);
+  if (rc) return rc;
+  substeps = S;
+  if (S & 1) std::swap(*q_a, *q_b);  // the last sub-step wrote the other parity buffer
+  return WFLOWB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t wflowb200_num_fields(void) { return WFLOWB200_NUM_FIELDS; }
+const char* wflowb200_field_name(int32_t id) {
+  return (id >= 0 && id < WFLOWB200_NUM_FIELDS) ? kFieldNames[id] : nullptr;
+}
+int32_t wflowb200_field_kind(int32_t id) {
+  return (id >= 0 && id < WFLOWB200_NUM_FIELDS) ? kFieldKinds[id] : -1;
+}
+int32_t wflowb200_field_id(const char* name) {
+  for (int i = 0; i < WFLOWB200_NUM_FIELDS; ++i)
+    if (!strcmp(name, kFieldNames[i])) return i;
+  return -1;
+}
+const char* wflowb200_last_error(const WflowB200* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom, WflowB200** out) {
+  if (!cfg || !dom || !out) return fail(nullptr, WFLOWB200_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n <= 0 || cfg->nriv < 0 || cfg->n_layers < 1 || cfg->n_layers > 8)
+    return fail(nullptr, WFLOWB200_ERR_ARG, "n > 0, nriv >= 0, 1 <= n_layers <= 8 required");
+  if (cfg->n > 0x7fffff00LL) return fail(nullptr, WFLOWB200_ERR_ARG, "n exceeds int32 slots");
+  if (cfg->kv_profile != 0 && cfg->kv_profile != 1)
+    return fail(nullptr, WFLOWB200_ERR_ARG,
+                "only exponential / exponential_constant conductivity profiles are implemented");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, WFLOWB200_ERR_CUDA, "no CUDA device: libwflow_b200 has no CPU fallback");
+  if (cudaSetDevice(cfg->device) != cudaSuccess)
+    return fail(nullptr, WFLOWB200_ERR_CUDA, "cudaSetDevice failed");
+
+  WflowB200* h = new WflowB200();
+  h->cfg = *cfg;
+  h->n = (int)cfg->n; h->nriv = (int)cfg->nriv; h->N = cfg->n_layers;
+  h->ns = (h->n + 31) / 32 * 32;
+  h->nrs = (h->nriv + 31) / 32 * 32;
+  if (h->cfg.kin_wave_min_flow_qroot == 0.0) h->cfg.kin_wave_min_flow_qroot = std::pow(1e-30, 0.2);
+  auto bail = [&](int32_t code) { g_create_error = h->err; wflowb200_destroy(h); return code; };
+
+  // ---- indexing artefacts (host) ---------------------------------------------------------
+  {
+    int32_t rc = build_networks(cfg, dom, h->land.nw, h->river.nw, h->err);
+    if (rc) return bail(rc);
+  }
+
+  // ---- HBM layout ------------------------------------------------------------------------
+  size_t total = 0;
+  std::vector<size_t> off(WFLOWB200_NUM_FIELDS);
+  for (int i = 0; i < WFLOWB200_NUM_FIELDS; ++i) {
+    off[i] = total;
+    const int k = kFieldKinds[i];
+    total += k == 3 ? (size_t)h->nrs : (size_t)h->ns * layers_of(h, k);
+  }
+  const size_t off_q2 = total;
+  total += 2 * (size_t)h->ns + (size_t)h->nrs;
+  h->pool_doubles = total;
+#define TRY_CREATE(expr)                                                       \
+  do {                                                                         \
+    cudaError_t e_ = (expr);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      h->err = std::string(#expr) + ": " + cudaGetErrorString(e_);             \
+      return bail(WFLOWB200_ERR_CUDA);                                         \
+    }                                                                          \
+  } while (0)
+  TRY_CREATE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  TRY_CREATE(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  TRY_CREATE(cudaEventCreateWithFlags(&h->forcing_ready, cudaEventDisableTiming));
+  TRY_CREATE(cudaEventCreateWithFlags(&h->forcing_consumed, cudaEventDisableTiming));
+  for (auto& e : h->ev) TRY_CREATE(cudaEventCreate(&e));
+  TRY_CREATE(cudaMalloc((void**)&h->pool, total * sizeof(double)));
+  h->field_ptr.resize(WFLOWB200_NUM_FIELDS);
+  for (int i = 0; i < WFLOWB200_NUM_FIELDS; ++i) h->field_ptr[i] = h->pool + off[i];
+  {
+    int i = 0;
+#define X(name, kind) h->f.name = h->field_ptr[i++];
+    WFLOWB200_FIELDS(X)
+#undef X
+  }
+  h->f.olf_q2 = h->pool + off_q2;
+  h->f.ssf_q2 = h->pool + off_q2 + h->ns;
+  h->f.riv_q2 = h->pool + off_q2 + 2 * (size_t)h->ns;
+  // MISSING_VALUE everywhere, then the reference's non-NaN defaults
+  launch_fill(h->pool, (long long)total, NAN, h->stream);
+  auto fill = [&](double* p, int kind, double v) {
+    launch_fill(p, kind == 3 ? h->nrs : (long long)h->ns * layers_of(h, kind), v, h->stream);
+  };
+  fill(h->f.canopy_storage, 0, 0.0);            // canopy.jl:11
+  fill(h->f.waterdepth_river, 0, 0.0);          // runoff.jl:26
+  fill(h->f.unsaturated_store_depth, 0, 0.0);   // soil.jl:71
+  fill(h->f.total_storage, 0, 0.0);             // soil.jl:77
+  fill(h->f.f_infiltration_reduction, 0, 1.0);  // soil.jl:83
+  fill(h->f.soil_surface_temperature, 0, 10.0 + 273.15);  // soil.jl:81
+  {
+    double* zeros_land[] = {h->f.ssf_exfiltwater_cumulative, h->f.ssf_exfiltwater_average,
+                            h->f.ssf_q_cumulative, h->f.ssf_q_average, h->f.ssf_q_in_cumulative,
+                            h->f.ssf_q_in_average, h->f.ssf_to_river_cumulative,
+                            h->f.ssf_to_river_average, h->f.ssf_q_net_cumulative,
+                            h->f.ssf_q_net_average, h->f.recharge_flux,
+                            h->f.recharge_flux_cumulative, h->f.olf_inwater, h->f.olf_q,
+                            h->f.olf_qlat, h->f.olf_qin, h->f.olf_qin_cumulative,
+                            h->f.olf_qin_average, h->f.olf_q_cumulative, h->f.olf_q_average,
+                            h->f.olf_storage, h->f.olf_h, h->f.olf_to_river_cumulative,
+                            h->f.olf_to_river_average};
+    for (double* p : zeros_land) fill(p, 0, 0.0);
+    double* zeros_riv[] = {h->f.riv_external_inflow, h->f.riv_abstraction,
+                           h->f.riv_actual_external_abstraction_cumulative,
+                           h->f.riv_actual_external_abstraction_average, h->f.riv_inwater,
+                           h->f.riv_q, h->f.riv_qlat, h->f.riv_qin, h->f.riv_qin_cumulative,
+                           h->f.riv_qin_average, h->f.riv_q_cumulative, h->f.riv_q_average,
+                           h->f.riv_storage, h->f.riv_h};
+    for (double* p : zeros_riv) fill(p, 3, 0.0);
+  }
+  TRY_CREATE(cudaMalloc((void**)&h->f.number_of_layers, (size_t)h->ns * sizeof(int32_t)));
+  TRY_CREATE(cudaMalloc((void**)&h->f.n_unsatlayers, (size_t)h->ns * sizeof(int32_t)));
+  TRY_CREATE(cudaMemset(h->f.number_of_layers, 0, (size_t)h->ns * sizeof(int32_t)));
+  TRY_CREATE(cudaMemset(h->f.n_unsatlayers, 0, (size_t)h->ns * sizeof(int32_t)));
+
+  if (upload_domain(h, h->land) || upload_domain(h, h->river)) return bail(WFLOWB200_ERR_CUDA);
+  {
+    std::vector<int64_t> riv_land_slot(h->nriv), riv_of_land(h->n, -1);
+    for (int p = 0; p < h->nriv; ++p) {
+      const int64_t rnode = h->river.nw.perm[p] - 1;
+      const int64_t lnode = dom->river_land_indices[rnode] - 1;
+      riv_land_slot[p] = h->land.nw.slot_of[lnode];
+      riv_of_land[riv_land_slot[p]] = p;
+    }
+    TRY_CREATE(upload_i32(riv_land_slot, &h->f.riv_land_slot, 0));
+    TRY_CREATE(upload_i32(riv_of_land, &h->riv_of_land, 0));
+  }
+  h->stage_doubles = std::max<size_t>((size_t)h->n * (h->N + 1), (size_t)3 * h->n);
+  TRY_CREATE(cudaMalloc((void**)&h->d_stage, h->stage_doubles * sizeof(double)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_forcing, (size_t)3 * h->n * sizeof(double)));
+  TRY_CREATE(cudaMallocHost((void**)&h->h_pinned, (size_t)3 * h->n * sizeof(double)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_barrier, 3 * 32 * sizeof(unsigned)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
+  TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_dts, 3 * kMaxSub * sizeof(double)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_min, sizeof(double)));
+
+  h->kc.n = h->n; h->kc.nriv = h->nriv; h->kc.ns = h->ns; h->kc.nrs = h->nrs;
+  h->kc.gash = cfg->gash; h->kc.has_lai = cfg->has_lai; h->kc.snow = cfg->snow;
+  h->kc.glacier = cfg->glacier;
+  h->kc.soil_infiltration_reduction = cfg->soil_infiltration_reduction;
+  h->kc.kv_profile = cfg->kv_profile;
+  h->kc.qroot = h->cfg.kin_wave_min_flow_qroot;
+
+  // persistent cooperative grids: as many co-resident CTAs as the device holds
+  h->grid_olf = wave_max_grid(0, h->N, kBlock, cfg->device);
+  h->grid_riv = wave_max_grid(1, h->N, kBlock, cfg->device);
+  h->grid_ssf = wave_max_grid(2, h->N, kBlock, cfg->device);
+  if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
+    h->err = "cooperative occupancy query failed";
+    return bail(WFLOWB200_ERR_CUDA);
+  }
+  TRY_CREATE(cudaStreamSynchronize(h->stream));
+#undef TRY_CREATE
+  *out = h;
+  return WFLOWB200_OK;
+}
+
+void wflowb200_destroy(WflowB200* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
+  cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
+  cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_barrier);
+  cudaFree(h->d_stats); cudaFree(h->d_dts); cudaFree(h->d_count); cudaFree(h->d_min);
+  free_domain(h->land); free_domain(h->river);
+  if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
+  if (h->forcing_consumed) cudaEventDestroy(h->forcing_consumed);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+}
+
+static int32_t field_common(WflowB200* h, int32_t id, int64_t sc, int64_t sl, int& kind,
+                            int& layers, int& count, size_t& extent) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  if (id < 0 || id >= WFLOWB200_NUM_FIELDS) return fail(h, WFLOWB200_ERR_ARG, "bad field id");
+  kind = kFieldKinds[id];
+  layers = layers_of(h, kind);
+  count = kind == 3 ? h->nriv : h->n;
+  if (layers == 1) {
+    if (sc != 1) return fail(h, WFLOWB200_ERR_ARG, "scalar fields need stride_cell == 1");
+  } else if (!((sc == layers && sl == 1) || (sc == 1 && sl == count))) {
+    return fail(h, WFLOWB200_ERR_ARG,
+                "layered fields need a dense layout: (stride_cell = layers, stride_layer = 1) "
+                "or (stride_cell = 1, stride_layer = n)");
+  }
+  extent = (size_t)count * layers;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t sc, int64_t sl) {
+  int kind, layers, count; size_t extent;
+  int32_t rc = field_common(h, id, sc, sl, kind, layers, count, extent);
+  if (rc) return rc;
+  if (!src) return fail(h, WFLOWB200_ERR_ARG, "null src");
+  if (count == 0) return WFLOWB200_OK;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, src, extent * sizeof(double), cudaMemcpyHostToDevice,
+                              h->stream));
+  const DomainDev& d = kind == 3 ? h->river : h->land;
+  h->launches += launch_gather_field(h->field_ptr_current(id), h->d_stage, d.node_of_slot, count,
+                                     kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, int64_t sl) {
+  int kind, layers, count; size_t extent;
+  int32_t rc = field_common(h, id, sc, sl, kind, layers, count, extent);
+  if (rc) return rc;
+  if (!dst) return fail(h, WFLOWB200_ERR_ARG, "null dst");
+  if (count == 0) return WFLOWB200_OK;
+  rc = wait_forcing(h);
+  if (rc) return rc;
+  const DomainDev& d = kind == 3 ? h->river : h->land;
+  h->launches += launch_scatter_field(h->d_stage, h->field_ptr_current(id), d.node_of_slot, count,
+                                      kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
+  CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_stage, extent * sizeof(double), cudaMemcpyDeviceToHost,
+                              h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_set_field_i64(WflowB200* h, int32_t which, const int64_t* src) {
+  if (!h || !src) return WFLOWB200_ERR_ARG;
+  if (which != 0 && which != 1) return fail(h, WFLOWB200_ERR_ARG, "bad int field");
+  std::vector<int32_t> tmp(h->n);
+  for (int p = 0; p < h->n; ++p) tmp[p] = (int32_t)src[h->land.nw.perm[p] - 1];
+  int32_t* dst = which == 0 ? h->f.number_of_layers : h->f.n_unsatlayers;
+  CUDA_TRY(h, cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_get_field_i64(WflowB200* h, int32_t which, int64_t* dst) {
+  if (!h || !dst) return WFLOWB200_ERR_ARG;
+  if (which != 0 && which != 1) return fail(h, WFLOWB200_ERR_ARG, "bad int field");
+  std::vector<int32_t> tmp(h->n);
+  const int32_t* src = which == 0 ? h->f.number_of_layers : h->f.n_unsatlayers;
+  CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < h->n; ++p) dst[h->land.nw.perm[p] - 1] = tmp[p];
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_set_forcing(WflowB200* h, const double* P, const double* PET, const double* T) {
+  if (!h || !P || !PET || !T) return WFLOWB200_ERR_ARG;
+  // the previous forcing must have been consumed before the staging buffers are reused
+  CUDA_TRY(h, cudaEventSynchronize(h->forcing_consumed));
+  const size_t nb = (size_t)h->n * sizeof(double);
+  memcpy(h->h_pinned, P, nb);
+  memcpy(h->h_pinned + h->n, PET, nb);
+  memcpy(h->h_pinned + 2 * (size_t)h->n, T, nb);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_forcing, h->h_pinned, 3 * nb, cudaMemcpyHostToDevice,
+                              h->copy_stream));
+  CUDA_TRY(h, cudaEventRecord(h->forcing_ready, h->copy_stream));
+  h->forcing_pending = true;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  int32_t rc = wait_forcing(h);
+  if (rc) return rc;
+  return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->stream),
+                      "update_land_hydrology_model");
+}
+
+int32_t wflowb200_exchange_recharge(WflowB200* h) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  return check_launch(h, launch_exchange_recharge(h->f, h->kc, h->stream), "exchange_recharge");
+}
+
+int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  return run_wave(h, dt, h->cfg.dt_ssf, 2, h->grid_ssf, h->sub_ssf, &h->f.ssf_q, &h->f.ssf_q2,
+                  [&](const WaveLaunch& w) {
+                    return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
+                  }, "update_subsurface_flow_model");
+}
+
+int32_t wflowb200_update_soil_water_storage(WflowB200* h, double dt) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  (void)dt;
+  return check_launch(h, launch_soil_water_storage(h->f, h->kc, h->N, h->stream),
+                      "update_soil_water_storage");
+}
+
+int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  return check_launch(h, launch_lateral_inflow_overland(h->f, h->kc, h->stream),
+                      "update_lateral_inflow(overland)");
+}
+
+int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  return run_wave(h, dt, h->cfg.dt_land, 0, h->grid_olf, h->sub_land, &h->f.olf_q, &h->f.olf_q2,
+                  [&](const WaveLaunch& w) {
+                    return launch_overland_wave(h->f, h->kc, h->land.dev, w, h->stream);
+                  }, "update_overland_flow_model");
+}
+
+int32_t wflowb200_update_lateral_inflow_river(WflowB200* h) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  return check_launch(h, launch_lateral_inflow_river(h->f, h->kc, h->stream),
+                      "update_lateral_inflow(river)");
+}
+
+int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  if (h->nriv == 0) return WFLOWB200_OK;
+  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  return run_wave(h, dt, h->cfg.dt_river, 1, h->grid_riv, h->sub_river, &h->f.riv_q, &h->f.riv_q2,
+                  [&](const WaveLaunch& w) {
+                    return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
+                  }, "update_river_flow_model");
+}
+
+int32_t wflowb200_update_total_water_storage(WflowB200* h) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  return check_launch(h, launch_total_water_storage(h->f, h->kc, h->riv_of_land, h->stream),
+                      "update_total_water_storage");
+}
+
+int32_t wflowb200_update_model(WflowB200* h, double dt) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  int32_t rc;
+  auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->ev[i], h->stream); };
+  mark(0);
+  if ((rc = wflowb200_update_land_hydrology_model(h, dt))) return rc;
+  if ((rc = wflowb200_exchange_recharge(h))) return rc;
+  mark(1);
+  if ((rc = wflowb200_update_subsurface_flow_model(h, dt))) return rc;
+  mark(2);
+  if ((rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater
+  mark(3);
+  if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
+  mark(4);
+  if ((rc = wflowb200_update_lateral_inflow_river(h))) return rc;
+  if ((rc = wflowb200_update_river_flow_model(h, dt))) return rc;
+  mark(5);
+  if ((rc = wflowb200_update_total_water_storage(h))) return rc;
+  mark(6);
+  if (h->timing) {
+    CUDA_TRY(h, cudaEventSynchronize(h->ev[6]));
+    for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&h->ms[i], h->ev[i], h->ev[i + 1]);
+  }
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_synchronize(WflowB200* h) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_get_artifact(WflowB200* h, int32_t domain, int32_t id, int64_t* dst,
+                               int64_t capacity, int64_t* len_out) {
+  if (!h || !len_out) return WFLOWB200_ERR_ARG;
+  const Network& nw = domain == WFLOWB200_DOMAIN_RIVER ? h->river.nw : h->land.nw;
+  return copy_artifact(nw, id, dst, capacity, len_out, h->err);
+}
+
+int32_t wflowb200_network_build(const WflowB200Config* cfg, const WflowB200Domain* dom,
+                                WflowB200Network** out) {
+  if (!cfg || !dom || !out) return fail(nullptr, WFLOWB200_ERR_ARG, "null argument");
+  WflowB200Network* net = new WflowB200Network();
+  int32_t rc = build_networks(cfg, dom, net->land, net->river, g_create_error);
+  if (rc) { delete net; *out = nullptr; return rc; }
+  *out = net;
+  return WFLOWB200_OK;
+}
+int32_t wflowb200_network_get(const WflowB200Network* net, int32_t domain, int32_t id,
+                              int64_t* dst, int64_t capacity, int64_t* len_out) {
+  if (!net || !len_out) return WFLOWB200_ERR_ARG;
+  const Network& nw = domain == WFLOWB200_DOMAIN_RIVER ? net->river : net->land;
+  return copy_artifact(nw, id, dst, capacity, len_out, g_create_error);
+}
+void wflowb200_network_destroy(WflowB200Network* net) { delete net; }
+
+int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
+  if (!h || !out) return WFLOWB200_ERR_ARG;
+  RoutingStats rs{};
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(&rs, h->d_stats, sizeof(rs), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  out->newton_calls_land = (int64_t)rs.newton_calls_land;
+  out->newton_iters_land = (int64_t)rs.newton_iters_land;
+  out->newton_maxit_land = (int64_t)rs.newton_maxit_land;
+  out->newton_calls_river = (int64_t)rs.newton_calls_river;
+  out->newton_iters_river = (int64_t)rs.newton_iters_river;
+  out->newton_maxit_river = (int64_t)rs.newton_maxit_river;
+  out->substeps_land = h->sub_land; out->substeps_river = h->sub_river;
+  out->substeps_ssf = h->sub_ssf;
+  out->wave_levels_land = h->land.nw.n_wave_levels;
+  out->wave_levels_river = h->river.nw.n_wave_levels;
+  out->kernel_launches = h->launches;
+  out->ms_land_hydrology = h->ms[0]; out->ms_subsurface = h->ms[1];
+  out->ms_soil_storage = h->ms[2]; out->ms_overland = h->ms[3]; out->ms_river = h->ms[4];
+  out->ms_total_storage = h->ms[5];
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_set_timing(WflowB200* h, int32_t enabled) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  h->timing = enabled != 0;
+  return WFLOWB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// network.hpp -- host-side construction of the drainage-network indexing artefacts.
+//
+// Reproduces, bit-exactly, what the reference builds at model initialisation
+// (all paths under /root/reference/Wflow/src):
+//   flowgraph                      routing/utils.jl:6-33
+//   topological_sort_by_dfs        Graphs.jl 1.14.0 (call sites network.jl:99,244; utils.jl:66)
+//   stream_order                   subdomains.jl:32-47
+//   kinwave_set_subdomains         subdomains.jl:169-255 (+ subbasins :55-82, fillnodata_upstream
+//                                  :8-24, graph_from_nodes :127-143, subbasins_order :93-120)
+//   filter_upstream_nodes          utils.jl:61-71 (lists indexed by TOPOSORT POSITION)
+// and adds the B200-specific artefact: topological-depth levels (distance to the basin outlet)
+// with a level-major device ordering, so that every drainage edge spans exactly one level.
+//
+// Every graph on this path is a forest with out-degree <= 1, stored as `down` (1-based
+// downstream id, 0 = none) plus a CSR of in-neighbours sorted ascending (Graphs.jl keeps
+// adjacency lists sorted). Algorithms are O(n) and written for this representation; they are
+// not a transcription of Graphs.jl.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace wfb {
+
+struct Network {
+  int64_t n = 0;
+  std::vector<uint8_t> ldd;            // after the pit fix-up of flowgraph
+  std::vector<int64_t> down;           // 1-based downstream node id, 0 = pit / none
+  std::vector<int64_t> in_ptr, in_idx; // CSR of in-neighbours (1-based ids, ascending)
+  std::vector<int64_t> order;          // topological_sort_by_dfs (1-based ids)
+  std::vector<int64_t> streamorder;    // Strahler
+  std::vector<int64_t> up_ptr, up_idx; // upstream_nodes by toposort position
+  // sub-domain partition (order_of_subdomains / order_subdomain / subdomain_indices)
+  std::vector<int64_t> lvl_ptr, lvl_idx, sub_ptr, sub_order, sub_indices;
+  // B200 wavefront
+  int64_t n_wave_levels = 0;
+  std::vector<int64_t> wave_level_ptr; // n_wave_levels + 1 offsets into device order
+  std::vector<int64_t> perm;           // device slot -> node id (1-based)
+  std::vector<int64_t> slot_of;        // node id - 1 -> device slot (0-based)
+};
+
+// Build `down` from a gridded LDD (flowgraph). `indices` holds 2n CartesianIndex pairs.
+// Returns false (and sets err) on a cycle.
+bool build_graph(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, const uint8_t* ldd,
+                 int64_t n, std::string& err);
+// order, stream order (unless `streamorder_override` given), upstream CSR, partition, wavefront.
+bool build_artifacts(Network& nw, int nthreads, int min_streamorder,
+                     const int64_t* streamorder_override, std::string& err);
+
+}  // namespace wfb

@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's per-timestep interface for the `sbm` model type, on top
+of the C ABI (include/wflow_b200.h). Method names follow the Julia functions they stand for
+(`update_land_hydrology_model!` -> `update_land_hydrology_model`, ...; all under
+/root/reference/Wflow/src, cited in the header). Julia itself is not available in this image,
+so this Python class plays the role of the Julia shim shown in INTEGRATION.md.
+
+The model state lives in HBM; `get`/`set` move one array (BMI get_value_ptr / set_value,
+bmi.jl:208-248). Layered arrays cross this interface cell-major, shape (n, N), like Julia's
+Vector{SVector{N,Float64}}.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+INT_FIELDS = {"number_of_layers": 0, "n_unsatlayers": 1}
+
+
+class WflowB200Error(RuntimeError):
+    pass
+
+
+class SbmModel:
+    """One handle = one GPU. `cfg` keys follow WflowB200Config; `domain` holds d1, d2,
+    indices (n, 2) 1-based CartesianIndex pairs in column-major order, ldd (n,) uint8 and
+    river_land_indices (nriv,) 1-based."""
+
+    def __init__(self, cfg: dict, domain: dict, fields: dict | None = None, device: int = 0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self._table = _lib.field_table()
+        self._ids = {name: i for i, (name, _) in enumerate(self._table)}
+        self._kinds = {name: k for name, k in self._table}
+        idx = np.ascontiguousarray(domain["indices"], dtype=np.int64)
+        ldd = np.ascontiguousarray(domain["ldd"], dtype=np.uint8)
+        rli = np.ascontiguousarray(domain["river_land_indices"], dtype=np.int64)
+        self.n, self.nriv, self.N = len(ldd), len(rli), int(cfg["n_layers"])
+        c = _lib.Config()
+        c.n, c.nriv, c.n_layers, c.device = self.n, self.nriv, self.N, device
+        for k in ("gash", "has_lai", "snow", "glacier", "soil_infiltration_reduction",
+                  "kv_profile", "adaptive"):
+            setattr(c, k, int(cfg.get(k, 0)))
+        c.nthreads = int(cfg.get("nthreads", 1))
+        c.land_streamorder_min = int(cfg.get("land_streamorder_min", 5))
+        c.river_streamorder_min = int(cfg.get("river_streamorder_min", 6))
+        c.dt_land = float(cfg.get("dt_land", 3600.0))
+        c.dt_river = float(cfg.get("dt_river", 900.0))
+        c.dt_ssf = float(cfg.get("dt_ssf", 86400.0))
+        c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
+        c.kin_wave_min_flow_qroot = float(cfg.get("kin_wave_min_flow_qroot", 1e-30 ** 0.2))
+        d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
+                        rli.ctypes.data)
+        rc = self._L.wflowb200_create(C.byref(c), C.byref(d), C.byref(self._h))
+        if rc != 0:
+            msg = self._L.wflowb200_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise WflowB200Error(f"wflowb200_create failed ({rc}): {msg}")
+        self.cfg = dict(cfg)
+        if fields:
+            for name, a in fields.items():
+                if a is not None and (name in self._ids or name in INT_FIELDS):
+                    self.set(name, a)
+
+    # ---- lifetime ----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.wflowb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WflowB200Error(f"libwflow_b200 error {rc}: "
+                                 f"{self._L.wflowb200_last_error(self._h).decode()}")
+
+    # ---- state transfer ----------------------------------------------------------------
+    def _shape(self, name):
+        k = self._kinds[name]
+        return {0: (self.n,), 1: (self.n, self.N), 2: (self.n, self.N + 1), 3: (self.nriv,)}[k]
+
+    def set(self, name: str, a) -> None:
+        if name in INT_FIELDS:
+            a = np.ascontiguousarray(a, dtype=np.int64)
+            assert a.shape == (self.n,), (name, a.shape)
+            self._check(self._L.wflowb200_set_field_i64(self._h, INT_FIELDS[name], a.ctypes.data))
+            return
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        shape = self._shape(name)
+        if a.shape != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+        layers = shape[1] if len(shape) == 2 else 1
+        self._check(self._L.wflowb200_set_field(self._h, self._ids[name], a.ctypes.data,
+                                                layers, 1))
+
+    def get(self, name: str) -> np.ndarray:
+        if name in INT_FIELDS:
+            a = np.zeros(self.n, dtype=np.int64)
+            self._check(self._L.wflowb200_get_field_i64(self._h, INT_FIELDS[name], a.ctypes.data))
+            return a
+        shape = self._shape(name)
+        a = np.empty(shape, dtype=np.float64)
+        layers = shape[1] if len(shape) == 2 else 1
+        self._check(self._L.wflowb200_get_field(self._h, self._ids[name], a.ctypes.data,
+                                                layers, 1))
+        return a
+
+    def field_names(self):
+        return [n for n, _ in self._table] + list(INT_FIELDS)
+
+    def set_forcing(self, precipitation, potential_evaporation, temperature) -> None:
+        """AtmosphericForcing hand-off (forcing.jl:2-10), asynchronous H2D."""
+        p = np.ascontiguousarray(precipitation, dtype=np.float64)
+        e = np.ascontiguousarray(potential_evaporation, dtype=np.float64)
+        t = np.ascontiguousarray(temperature, dtype=np.float64)
+        assert p.shape == e.shape == t.shape == (self.n,)
+        self._check(self._L.wflowb200_set_forcing(self._h, p.ctypes.data, e.ctypes.data,
+                                                  t.ctypes.data))
+
+    # ---- the hot path (names of the reference functions) ---------------------------------
+    def update_land_hydrology_model(self, dt):
+        self._check(self._L.wflowb200_update_land_hydrology_model(self._h, dt))
+
+    def exchange_recharge(self):
+        self._check(self._L.wflowb200_exchange_recharge(self._h))
+
+    def update_subsurface_flow_model(self, dt):
+        self._check(self._L.wflowb200_update_subsurface_flow_model(self._h, dt))
+
+    def update_soil_water_storage(self, dt):
+        self._check(self._L.wflowb200_update_soil_water_storage(self._h, dt))
+
+    def update_lateral_inflow_overland(self):
+        self._check(self._L.wflowb200_update_lateral_inflow_overland(self._h))
+
+    def update_overland_flow_model(self, dt):
+        self._check(self._L.wflowb200_update_overland_flow_model(self._h, dt))
+
+    def update_lateral_inflow_river(self):
+        self._check(self._L.wflowb200_update_lateral_inflow_river(self._h))
+
+    def update_river_flow_model(self, dt):
+        self._check(self._L.wflowb200_update_river_flow_model(self._h, dt))
+
+    def surface_routing(self, dt):
+        """surface_routing! (routing/surface/surface_routing.jl:7-46)."""
+        self.update_lateral_inflow_overland()
+        self.update_overland_flow_model(dt)
+        self.update_lateral_inflow_river()
+        self.update_river_flow_model(dt)
+
+    def update_total_water_storage(self):
+        self._check(self._L.wflowb200_update_total_water_storage(self._h))
+
+    def update_model(self, dt):
+        """update_model!(model::AbstractModel{<:SbmModel}) (sbm_model.jl:60-92)."""
+        self._check(self._L.wflowb200_update_model(self._h, dt))
+
+    def synchronize(self):
+        self._check(self._L.wflowb200_synchronize(self._h))
+
+    # ---- artefacts / statistics ----------------------------------------------------------
+    def artifact(self, domain: str, name: str) -> np.ndarray:
+        dom = {"land": 0, "river": 1}[domain]
+        n = C.c_int64()
+        aid = _lib.ARTIFACTS[name]
+        self._check(self._L.wflowb200_get_artifact(self._h, dom, aid, None, 0, C.byref(n)))
+        a = np.zeros(n.value, dtype=np.int64)
+        self._check(self._L.wflowb200_get_artifact(self._h, dom, aid, a.ctypes.data, n.value,
+                                                   C.byref(n)))
+        return a
+
+    def artifacts(self, domain: str) -> dict:
+        return {k: self.artifact(domain, k) for k in _lib.ARTIFACTS}
+
+    def set_timing(self, enabled: bool):
+        self._check(self._L.wflowb200_set_timing(self._h, int(enabled)))
+
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        self._check(self._L.wflowb200_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}

@@ -1,0 +1,297 @@
+"""Synthetic wflow_sbm basins for tests and benchmarks: a Scheidegger-type
+random D8 forest, parameters drawn per cell +-20 % around the Moselle means asserted in
+/root/reference/Wflow/test/run_sbm.jl:98-406, cold-start states as in
+Wflow/src/soil/soil.jl:164-198, and counter-based forcing. Everything is a pure function of
+(seed, cell id, step), so any shard of a raster can be generated independently.
+
+The init-time derivations that the Julia model constructors perform are restated here with
+the reference's formulas (cited inline); they are host-side set-up, not part of the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays."""
+    with np.errstate(over="ignore"):
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def u01(seed: int, stream: int, idx: np.ndarray) -> np.ndarray:
+    """Counter-based uniform [0, 1): a pure function of (seed, stream, cell id)."""
+    with np.errstate(over="ignore"):
+        k = (np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+             + np.uint64(stream) * np.uint64(0xD1B54A32D192ED03))
+        x = _mix(idx.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + k)
+        x = _mix(x + np.uint64(0x632BE59BD9B4E019))
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def _pm20(seed, stream, idx, mean):
+    return mean * (0.8 + 0.4 * u01(seed, stream, idx))
+
+
+def jl_pow(x, y):
+    """Wflow's pow(x, y) = exp(y * log(x)) (utils.jl:470)."""
+    with np.errstate(divide="ignore"):
+        return np.exp(y * np.log(x))
+
+
+def scheidegger_ldd(d1: int, d2: int, seed: int, mask: np.ndarray | None = None):
+    """Random D8 forest: cell (i, j) drains to (i + delta, j + 1), delta in {-1, 0, +1};
+    the last row and cells draining out of the active domain are pits (LDD 5).
+    Returns (indices (n,2) 1-based column-major, ldd uint8 (n,), down (n,) 1-based, 0 = pit,
+    gid (n,) global cell id)."""
+    if mask is None:
+        lin = np.arange(d1 * d2, dtype=np.int64)
+    else:
+        lin = np.nonzero(np.asarray(mask, dtype=bool).ravel(order="F"))[0].astype(np.int64)
+    i = lin % d1 + 1
+    j = lin // d1 + 1
+    delta = np.floor(u01(seed, 1, lin) * 3.0).astype(np.int64) - 1
+    ti = i + delta
+    delta = np.where((ti < 1) | (ti > d1), 0, delta)
+    ti = i + delta
+    tlin = j * d1 + (ti - 1)  # (ti, j + 1)
+    pos = np.searchsorted(lin, tlin)
+    posc = np.minimum(pos, len(lin) - 1)
+    ok = (j < d2) & (pos < len(lin)) & (lin[posc] == tlin)
+    ldd = np.where(ok, 8 + delta, 5).astype(np.uint8)  # (-1,+1) = 7, (0,+1) = 8, (+1,+1) = 9
+    down = np.where(ok, posc + 1, 0).astype(np.int64)
+    indices = np.stack([i, j], axis=1).astype(np.int64)
+    return indices, ldd, down, lin
+
+
+def upstream_cells(indices: np.ndarray, down: np.ndarray) -> np.ndarray:
+    """Number of cells draining through each cell (itself included); rows are processed in
+    increasing j because every edge goes from row j to row j + 1."""
+    n = len(down)
+    acc = np.ones(n, dtype=np.int64)
+    j = indices[:, 1]
+    order = np.argsort(j, kind="stable")
+    js = j[order]
+    bounds = np.searchsorted(js, np.arange(js.min(), js.max() + 2))
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        nodes = order[a:b]
+        d = down[nodes]
+        m = d > 0
+        np.add.at(acc, d[m] - 1, acc[nodes[m]])
+    return acc
+
+
+def set_layerthickness(ref_depth, cum_depth, thickness):
+    """utils.jl:390-404, vectorised over cells: (n,), (N+1,) or (n,N+1), (N,) or (n,N)."""
+    n = len(ref_depth)
+    thickness = np.broadcast_to(thickness, (n, thickness.shape[-1]))
+    cum_depth = np.broadcast_to(cum_depth, (n, cum_depth.shape[-1]))
+    out = np.full(thickness.shape, np.nan)
+    with np.errstate(invalid="ignore"):
+        for k in range(thickness.shape[1]):
+            full = ref_depth > cum_depth[:, k + 1]
+            part = ~full & (ref_depth - cum_depth[:, k] > 0.0)
+            out[full, k] = thickness[full, k]
+            out[part, k] = (ref_depth - cum_depth[:, k])[part]
+    return out
+
+
+def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
+               soil_layer_thickness_mm=(100, 300, 800), mask=None, river_fraction_target=0.116,
+               cell_length: float = 1000.0, snow: bool = True, glacier: bool = False,
+               kv_profile: int = 0, nthreads: int = 8, adaptive: bool = False,
+               soil_infiltration_reduction: bool = False, id_offset: int = 0,
+               external_inflow: bool = False):
+    """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
+    the reference's field names; layered arrays are cell-major (n, N)."""
+    indices, ldd, down, lin = scheidegger_ldd(d1, d2, seed, mask)
+    gid = lin + np.int64(id_offset)
+    n = len(ldd)
+    N = len(soil_layer_thickness_mm) + 1
+    acc = upstream_cells(indices, down)
+    # river mask: largest upstream areas, fraction ~ Moselle's 5809 / 50063
+    if river_fraction_target > 0:
+        thr = np.quantile(acc, 1.0 - river_fraction_target)
+        river = acc >= max(thr, 2)
+    else:
+        river = np.zeros(n, dtype=bool)
+    river_land_indices = np.nonzero(river)[0].astype(np.int64) + 1
+    nriv = len(river_land_indices)
+
+    F = {}
+    r = lambda stream, mean: _pm20(seed, stream, gid, mean)
+    # ---- vegetation / interception / snow (run_sbm.jl:98-142) ------------------------------
+    F["leaf_area_index"] = r(10, 1.06)
+    F["storage_specific_leaf"] = r(11, 8.94e-5)
+    F["storage_wood"] = r(12, 1.96e-4)
+    F["light_extinction_coefficient"] = r(13, 0.674)
+    F["crop_coefficient"] = np.ones(n)
+    F["canopy_gap_fraction"] = np.exp(-F["light_extinction_coefficient"] * F["leaf_area_index"])
+    F["maximum_canopy_storage"] = (F["storage_specific_leaf"] * F["leaf_area_index"]
+                                   + F["storage_wood"])
+    F["evaporation_to_precipitation_ratio"] = r(14, 0.1)
+    F["canopy_storage"] = np.zeros(n)
+    F["temperature_threshold_snowfall"] = np.full(n, 273.15)
+    F["temperature_interval_snowfall"] = np.full(n, 2.0)
+    F["temperature_threshold_melt"] = np.full(n, 273.15)
+    F["degree_day_factor"] = r(15, 4.348e-8)
+    F["water_holding_capacity"] = np.full(n, 0.1)
+    F["snow_storage"] = np.zeros(n)
+    F["snow_water"] = np.zeros(n)
+    if glacier:
+        F["glacier_temperature_threshold_melt"] = np.full(n, 273.15)
+        F["glacier_degree_day_factor"] = r(16, 3.0e-3 / 86400.0)
+        F["glacier_snow_to_ice_fraction"] = np.full(n, 0.001 / 86400.0)
+        F["glacier_fraction"] = np.where(u01(seed, 17, gid) < 0.05, 0.4, 0.0)
+        F["glacier_store"] = np.full(n, 5.5)
+    # ---- soil (run_sbm.jl:196-324, App. D) ---------------------------------------------------
+    theta_s = r(20, 0.4409)
+    theta_r = r(21, 0.1657)
+    frac_fc = r(22, 0.512)
+    theta_fc = theta_r + (theta_s - theta_r) * frac_fc
+    soil_thickness = r(23, 1.838)
+    F["theta_s"], F["theta_r"], F["theta_fc"] = theta_s, theta_r, theta_fc
+    F["soil_thickness"] = soil_thickness
+    cfg_thick = np.array([t * 1e-3 for t in soil_layer_thickness_mm] + [np.nan])
+    cum_cfg = np.concatenate([[0.0], np.cumsum(cfg_thick)])  # soil.jl:327-332
+    alt = set_layerthickness(soil_thickness, cum_cfg, cfg_thick)
+    F["actual_layer_thickness"] = alt
+    F["cumulative_layer_depth"] = np.concatenate([np.zeros((n, 1)), np.cumsum(alt, axis=1)], axis=1)
+    nlayers = (N - np.isnan(alt).sum(axis=1)).astype(np.int64)
+    F["number_of_layers"] = nlayers
+    bc_means = [9.43, 9.82, 10.24, 10.24, 10.24, 10.24, 10.24, 10.24]
+    F["brooks_corey_exponent"] = np.stack([r(30 + k, bc_means[k]) for k in range(N)], axis=1)
+    F["vertical_hydraulic_conductivity_factor"] = np.ones((n, N))
+    F["air_entry_pressure"] = np.full(n, -0.1)
+    F["h1"], F["h2"] = np.zeros(n), np.full(n, -1.0)
+    F["h3_high"], F["h3_low"], F["h4"] = np.full(n, -4.0), np.full(n, -10.0), np.full(n, -160.0)
+    F["alpha_h1"] = np.ones(n)
+    F["w_soil"], F["cf_soil"] = np.full(n, 0.1125), np.full(n, 0.038)
+    # mostly Moselle-like (0.013), with 5 % "urban" cells that shed infiltration-excess runoff
+    urban = u01(seed, 46, gid) < 0.05
+    F["compacted_soil_area_fraction"] = np.where(urban, r(47, 0.6), r(40, 0.013))
+    F["infiltration_capacity_compacted_soil"] = r(41, 5.787e-8)
+    F["kv_0"] = r(42, 4.846e-6)
+    F["infiltration_capacity_soil"] = F["kv_0"] * F["vertical_hydraulic_conductivity_factor"][:, 0]
+    F["hydraulic_conductivity_scale_parameter"] = r(43, 3.304)
+    if kv_profile == 1:
+        F["z_exp"] = r(44, 0.6)
+    F["maximum_leakage"] = np.zeros(n)
+    F["cap_hmax"], F["cap_n"] = np.full(n, 2.0), np.full(n, 2.0)
+    F["wet_root_distribution_parameter"] = np.full(n, -5.0e5)
+    rd = np.minimum(soil_thickness * 0.99, r(45, 0.370))  # sbm.jl:57-58
+    F["rooting_depth"] = rd
+    # default root fraction (soil.jl:537-563)
+    cld = F["cumulative_layer_depth"]
+    rootfraction = np.zeros((n, N))
+    with np.errstate(invalid="ignore"):
+        for k in range(N):
+            full = (rd - cld[:, k]) >= alt[:, k]
+            part = np.maximum((rd - cld[:, k]) / rd, 0.0)
+            rootfraction[:, k] = np.where(full, alt[:, k] / rd, part)
+    rootfraction[rd <= 0.0] = 0.0
+    F["rootfraction"] = np.nan_to_num(rootfraction, nan=0.0)
+    F["soil_water_capacity"] = soil_thickness * (theta_s - theta_r)
+    # cold states (soil.jl:164-198)
+    F["saturated_water_depth"] = 0.85 * F["soil_water_capacity"]
+    F["unsaturated_layer_depth"] = np.zeros((n, N))
+    F["soil_surface_temperature"] = np.full(n, 10.0 + 273.15)
+    zi = np.maximum(0.0, soil_thickness - F["saturated_water_depth"] / (theta_s - theta_r))
+    F["water_table_depth"] = zi
+    # ---- shared land parameters (domain.jl:218-261, utils.jl:418-466) ------------------------
+    xl = yl = cell_length
+    area = np.full(n, xl * yl)
+    diag = ~np.isin(ldd, (2, 8, 4, 6))  # our LDD only has 5, 7, 8, 9
+    F["area"] = area
+    F["flow_length"] = np.where(diag, np.hypot(xl, yl), yl)
+    F["flow_width"] = np.where(diag, (xl * yl) / np.hypot(xl, yl), xl)
+    F["slope"] = np.maximum(r(50, 0.0947), 1e-5)
+    riv_len_land = _pm20(seed, 51, gid, cell_length) * 0.5 + 0.5 * cell_length
+    riv_wid_land = np.maximum(2.0, 0.8 * np.sqrt(acc.astype(np.float64)))
+    F["river_fraction"] = np.where(river, np.minimum(riv_len_land * riv_wid_land / area, 1.0), 0.0)
+    # open water (lakes, ponds) on 30 % of the cells: land runoff feeding the overland wave
+    wf = np.where(u01(seed, 55, gid) < 0.3, 0.05 * u01(seed, 56, gid), 0.0)
+    F["water_fraction"] = np.maximum(wf - F["river_fraction"], 0.0)  # domain.jl:296
+    land_area = (1.0 - F["river_fraction"]) * area
+    F["surface_flow_width"] = np.where(river, land_area / F["flow_length"], F["flow_width"])
+    # get_flow_fraction_to_river (utils.jl:493-510)
+    f2r = np.zeros(n)
+    has_down = down > 0
+    dn = np.where(has_down, down - 1, 0)
+    sel = has_down & river[dn] & (ldd != ldd[dn])
+    f2r[sel] = F["slope"][sel] / (F["slope"][dn[sel]] + F["slope"][sel])
+    F["flow_fraction_to_river"] = f2r
+    # ---- overland flow (surface_kinwave.jl:32-44,188-219) ------------------------------------
+    mannings_land = r(52, 0.484)
+    F["olf_alpha"] = (jl_pow(mannings_land / np.sqrt(F["slope"]), 0.6)
+                      * jl_pow(F["surface_flow_width"], (2.0 / 3.0) * 0.6))
+    for k in ("olf_q", "olf_h", "olf_storage", "olf_qin", "olf_qlat", "olf_inwater"):
+        F[k] = np.zeros(n)
+    # ---- lateral subsurface flow (lateral_subsurface_flow.jl:84-141, utils.jl:916-937) -------
+    khfrac = r(53, 100.0)
+    F["kh_0"] = khfrac * F["kv_0"]
+    F["ssf_soil_thickness"] = soil_thickness.copy()
+    F["specific_yield"] = np.maximum(theta_s - theta_fc, 0.02)
+    F["ssf_top"] = 100.0 + 50.0 * u01(seed, 54, gid)
+    fpar = F["hydraulic_conductivity_scale_parameter"]
+    if kv_profile == 0:
+        F["ssf_q_max"] = ((F["kh_0"] * F["slope"]) / fpar) * (1.0 - np.exp(-fpar * soil_thickness))
+        F["ssf_q"] = (((F["kh_0"] * F["slope"]) / fpar)
+                      * (np.exp(-fpar * zi) - np.exp(-fpar * soil_thickness)) * F["flow_width"])
+    else:  # exponential_constant (utils.jl:940-985)
+        z_exp = F["z_exp"]
+        ssf_constant = F["kh_0"] * np.exp(-fpar * z_exp) * F["slope"] * (soil_thickness - z_exp)
+        F["ssf_q_max"] = (((F["kh_0"] * F["slope"]) / fpar) * (1.0 - np.exp(-fpar * z_exp))
+                          + ssf_constant)
+        q_exp = (((F["kh_0"] * F["slope"]) / fpar) * (np.exp(-fpar * zi) - np.exp(-fpar * z_exp))
+                 + ssf_constant)
+        q_const = F["kh_0"] * np.exp(-fpar * zi) * F["slope"] * (soil_thickness - zi)
+        F["ssf_q"] = np.where(zi < z_exp, q_exp, q_const) * F["flow_width"]
+    F["ssf_water_table_depth"] = zi.copy()
+    F["ssf_head"] = F["ssf_top"] - zi
+    F["ssf_storage"] = F["specific_yield"] * (soil_thickness - zi) * area
+    # ---- river (surface_kinwave.jl:67-90, domain.jl:263-277) ---------------------------------
+    ridx = river_land_indices - 1
+    rg = gid[ridx]
+    F["riv_flow_length"] = riv_len_land[ridx]
+    F["riv_flow_width"] = riv_wid_land[ridx]
+    riv_slope = np.maximum(_pm20(seed, 60, rg, 0.0031), 1e-5)
+    riv_n = _pm20(seed, 61, rg, 0.0305)
+    bankfull = _pm20(seed, 62, rg, 1.10)
+    F["riv_alpha"] = (jl_pow(riv_n / np.sqrt(riv_slope), 0.6)
+                      * jl_pow(F["riv_flow_width"] + bankfull, (2.0 / 3.0) * 0.6))
+    F["riv_external_inflow"] = np.zeros(nriv)
+    if external_inflow and nriv:
+        F["riv_external_inflow"] = np.where(u01(seed, 63, rg) < 0.02, -0.05, 0.0)
+    F["riv_abstraction"] = np.zeros(nriv)
+    for k in ("riv_q", "riv_h", "riv_storage", "riv_qin", "riv_qlat", "riv_inwater"):
+        F[k] = np.zeros(nriv)
+
+    cfg = dict(n=n, nriv=nriv, n_layers=N, N=N, gash=int(dt >= 23 * 3600.0), has_lai=1,
+               snow=int(snow), glacier=int(glacier),
+               soil_infiltration_reduction=int(soil_infiltration_reduction),
+               kv_profile=kv_profile, adaptive=int(adaptive), nthreads=nthreads,
+               land_streamorder_min=5, river_streamorder_min=6, dt_land=3600.0, dt_river=900.0,
+               dt_ssf=86400.0, ssf_alpha_coefficient=1.0, dt=dt,
+               kin_wave_min_flow_qroot=1e-30 ** 0.2)
+    domain = dict(d1=d1, d2=d2, indices=indices, ldd=ldd, river_land_indices=river_land_indices,
+                  down=down, gid=gid, upstream_cells=acc)
+    return cfg, domain, F
+
+
+def make_forcing(seed: int, step: int, gid: np.ndarray, dt: float = 86400.0):
+    """Forcing of one model step in SI (m s-1, m s-1, K): P = 0 w.p. 0.6 else Exp(3 mm d-1);
+    PET ~ U(0.2, 1.2) mm d-1; T ~ N(275.5, 4) K (Box-Muller)."""
+    s = 1000 + 8 * step
+    wet = u01(seed, s, gid) >= 0.6
+    p_mm_day = np.where(wet, -3.0 * np.log1p(-u01(seed, s + 1, gid)), 0.0)
+    pet_mm_day = 0.2 + u01(seed, s + 2, gid)
+    u1 = np.maximum(u01(seed, s + 3, gid), 1e-300)
+    u2 = u01(seed, s + 4, gid)
+    temp = 275.5 + 4.0 * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    mm_per_day = (1.0 / 86400.0) * 1e-3
+    return p_mm_day * mm_per_day, pet_mm_day * mm_per_day, temp
