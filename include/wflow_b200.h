@@ -178,12 +178,24 @@ typedef struct {
   int64_t substeps_land, substeps_river, substeps_ssf;
   int64_t wave_levels_land, wave_levels_river;
   int64_t kernel_launches;      /* kernels of this library launched since create            */
-  double ms_land_hydrology, ms_subsurface, ms_soil_storage, ms_overland, ms_river,
-      ms_total_storage;         /* CUDA-event time of the last update_model call, per stage  */
+  /* CUDA-event time [ms] per stage, accumulated over the update_model calls made while timing
+   * was enabled (wflowb200_set_timing resets them): */
+  double ms_land_hydrology;     /* land_hydrology_kernel alone (V1)                          */
+  double ms_subsurface;         /* subsurface_wave_kernel                                    */
+  double ms_soil_storage;       /* soil_water_storage_kernel (V2)                            */
+  double ms_overland;           /* overland_wave_kernel                                      */
+  double ms_river;              /* river_wave_kernel                                         */
+  double ms_total_storage;      /* total_water_storage_kernel (V3)                           */
+  double ms_glue;               /* scatter / exchange / lateral-inflow / forcing-gather      */
+  int64_t timed_steps;
 } WflowB200Stats;
 int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out);
-/* enable per-stage CUDA-event timing inside update_model (off by default) */
+/* enable per-stage CUDA-event timing inside update_model (off by default); resets the sums */
 int32_t wflowb200_set_timing(WflowB200* h, int32_t enabled);
+/* Device-side stopwatch on the handle's compute stream (CUDA events): start records an event,
+ * stop records another, waits for it and returns the elapsed milliseconds between the two. */
+int32_t wflowb200_timer_start(WflowB200* h);
+int32_t wflowb200_timer_stop(WflowB200* h, double* elapsed_ms);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,8 @@ class Stats(C.Structure):
         "newton_iters_river", "newton_maxit_river", "substeps_land", "substeps_river",
         "substeps_ssf", "wave_levels_land", "wave_levels_river", "kernel_launches")] + [
         (k, C.c_double) for k in ("ms_land_hydrology", "ms_subsurface", "ms_soil_storage",
-                                  "ms_overland", "ms_river", "ms_total_storage")]
+                                  "ms_overland", "ms_river", "ms_total_storage", "ms_glue")] + [
+        ("timed_steps", C.c_int64)]
 
 
 ARTIFACTS = dict(order=0, streamorder=1, upstream_ptr=2, upstream_idx=3, subdomain_level_ptr=4,
@@ -94,6 +95,8 @@ def lib():
     L.wflowb200_get_artifact.argtypes = [vp, i32, i32, vp, i64, C.POINTER(i64)]
     L.wflowb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.wflowb200_set_timing.argtypes = [vp, i32]
+    L.wflowb200_timer_start.argtypes = [vp]
+    L.wflowb200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -3,6 +3,7 @@
 // path (update_model!, sbm_model.jl:60-92). No CPU fallback: every entry point needs the device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -135,15 +136,22 @@ struct WflowB200 {
     if (id == WFLOWB200_F_ssf_q) return f.ssf_q;
     return field_ptr[id];
   }
-  cudaEvent_t ev[7] = {};
-  float ms[6] = {};
+  cudaEvent_t ev[12] = {};
+  cudaEvent_t tm[2] = {};
+  double ms[7] = {};
+  int64_t timed_steps = 0;
   std::string err;
 };
 
 namespace {
 
 constexpr int kMaxSub = 8192;
-constexpr int kBlock = 256;
+// CTA sizes of the persistent wavefront kernels. The grid barrier costs one same-address L2
+// atomic per CTA (serialised, ~14 ns each), so the surface kernels run ONE 1024-thread CTA per
+// SM (148 arrivals) rather than many small CTAs; the subsurface kernel is register-heavy
+// (soil column in registers) and runs one 256-thread CTA per SM.
+constexpr int kBlockSurface = 1024;
+constexpr int kBlockSsf = 256;
 
 int32_t fail(WflowB200* h, int32_t code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -239,7 +247,7 @@ int32_t check_launch(WflowB200* h, int rc, const char* what) {
 // Run one routing component with the fixed-step skewed wavefront.
 template <class Launch>
 int32_t run_wave(WflowB200* h, double dt, double dt_fixed, int slot, int grid, int64_t& substeps,
-                 double** q_a, double** q_b, Launch launch, const char* what) {
+                 double** q_a, double** q_b, int block, Launch launch, const char* what) {
   std::vector<double> dts;
   const int S = fixed_substeps(dt, dt_fixed, dts);
   if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
@@ -253,7 +261,8 @@ int32_t run_wave(WflowB200* h, double dt, double dt_fixed, int slot, int grid, i
   w.S = S;
   w.dt = dt;
   w.grid = grid;
-  w.block = kBlock;
+  w.block = block;
+  { const char* dbg = getenv("WFB_WAVE_DEBUG"); w.debug = dbg ? atoi(dbg) : 0; }
   int32_t rc = check_launch(h, launch(w), what);
   if (rc) return rc;
   substeps = S;
@@ -334,6 +343,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaEventCreateWithFlags(&h->forcing_ready, cudaEventDisableTiming));
   TRY_CREATE(cudaEventCreateWithFlags(&h->forcing_consumed, cudaEventDisableTiming));
   for (auto& e : h->ev) TRY_CREATE(cudaEventCreate(&e));
+  for (auto& e : h->tm) TRY_CREATE(cudaEventCreate(&e));
   TRY_CREATE(cudaMalloc((void**)&h->pool, total * sizeof(double)));
   h->field_ptr.resize(WFLOWB200_NUM_FIELDS);
   for (int i = 0; i < WFLOWB200_NUM_FIELDS; ++i) h->field_ptr[i] = h->pool + off[i];
@@ -413,9 +423,9 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->kc.qroot = h->cfg.kin_wave_min_flow_qroot;
 
   // persistent cooperative grids: as many co-resident CTAs as the device holds
-  h->grid_olf = wave_max_grid(0, h->N, kBlock, cfg->device);
-  h->grid_riv = wave_max_grid(1, h->N, kBlock, cfg->device);
-  h->grid_ssf = wave_max_grid(2, h->N, kBlock, cfg->device);
+  h->grid_olf = wave_max_grid(0, h->N, kBlockSurface, cfg->device);
+  h->grid_riv = wave_max_grid(1, h->N, kBlockSurface, cfg->device);
+  h->grid_ssf = wave_max_grid(2, h->N, kBlockSsf, cfg->device);
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "cooperative occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -438,6 +448,7 @@ void wflowb200_destroy(WflowB200* h) {
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
   if (h->forcing_consumed) cudaEventDestroy(h->forcing_consumed);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->tm) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -536,6 +547,9 @@ int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   int32_t rc = wait_forcing(h);
   if (rc) return rc;
+  if (h->nriv > 0) {  // river h -> land grid (runoff.jl:77-79)
+    if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
+  }
   return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->stream),
                       "update_land_hydrology_model");
 }
@@ -549,7 +563,7 @@ int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
   return run_wave(h, dt, h->cfg.dt_ssf, 2, h->grid_ssf, h->sub_ssf, &h->f.ssf_q, &h->f.ssf_q2,
-                  [&](const WaveLaunch& w) {
+                  kBlockSsf, [&](const WaveLaunch& w) {
                     return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
                   }, "update_subsurface_flow_model");
 }
@@ -571,7 +585,7 @@ int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
   return run_wave(h, dt, h->cfg.dt_land, 0, h->grid_olf, h->sub_land, &h->f.olf_q, &h->f.olf_q2,
-                  [&](const WaveLaunch& w) {
+                  kBlockSurface, [&](const WaveLaunch& w) {
                     return launch_overland_wave(h->f, h->kc, h->land.dev, w, h->stream);
                   }, "update_overland_flow_model");
 }
@@ -587,7 +601,7 @@ int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
   if (h->nriv == 0) return WFLOWB200_OK;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
   return run_wave(h, dt, h->cfg.dt_river, 1, h->grid_riv, h->sub_river, &h->f.riv_q, &h->f.riv_q2,
-                  [&](const WaveLaunch& w) {
+                  kBlockSurface, [&](const WaveLaunch& w) {
                     return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
                   }, "update_river_flow_model");
 }
@@ -603,23 +617,35 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   int32_t rc;
   auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->ev[i], h->stream); };
   mark(0);
-  if ((rc = wflowb200_update_land_hydrology_model(h, dt))) return rc;
-  if ((rc = wflowb200_exchange_recharge(h))) return rc;
+  if ((rc = wait_forcing(h))) return rc;
+  if (h->nriv > 0) {  // river h -> land grid (runoff.jl:77-79)
+    if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
+  }
   mark(1);
-  if ((rc = wflowb200_update_subsurface_flow_model(h, dt))) return rc;
+  if ((rc = check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->stream),
+                         "update_land_hydrology_model"))) return rc;
   mark(2);
-  if ((rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater
+  if ((rc = wflowb200_exchange_recharge(h))) return rc;
   mark(3);
-  if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
+  if ((rc = wflowb200_update_subsurface_flow_model(h, dt))) return rc;
   mark(4);
-  if ((rc = wflowb200_update_lateral_inflow_river(h))) return rc;
-  if ((rc = wflowb200_update_river_flow_model(h, dt))) return rc;
+  if ((rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater
   mark(5);
-  if ((rc = wflowb200_update_total_water_storage(h))) return rc;
+  if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
   mark(6);
+  if ((rc = wflowb200_update_lateral_inflow_river(h))) return rc;
+  mark(7);
+  if ((rc = wflowb200_update_river_flow_model(h, dt))) return rc;
+  mark(8);
+  if ((rc = wflowb200_update_total_water_storage(h))) return rc;
+  mark(9);
   if (h->timing) {
-    CUDA_TRY(h, cudaEventSynchronize(h->ev[6]));
-    for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&h->ms[i], h->ev[i], h->ev[i + 1]);
+    CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
+    float d[9];
+    for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&d[i], h->ev[i], h->ev[i + 1]);
+    h->ms[0] += d[1]; h->ms[1] += d[3]; h->ms[2] += d[4]; h->ms[3] += d[5]; h->ms[4] += d[7];
+    h->ms[5] += d[8]; h->ms[6] += d[0] + d[2] + d[6];
+    h->timed_steps++;
   }
   return WFLOWB200_OK;
 }
@@ -673,13 +699,31 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
   out->kernel_launches = h->launches;
   out->ms_land_hydrology = h->ms[0]; out->ms_subsurface = h->ms[1];
   out->ms_soil_storage = h->ms[2]; out->ms_overland = h->ms[3]; out->ms_river = h->ms[4];
-  out->ms_total_storage = h->ms[5];
+  out->ms_total_storage = h->ms[5]; out->ms_glue = h->ms[6];
+  out->timed_steps = h->timed_steps;
   return WFLOWB200_OK;
 }
 
 int32_t wflowb200_set_timing(WflowB200* h, int32_t enabled) {
   if (!h) return WFLOWB200_ERR_ARG;
   h->timing = enabled != 0;
+  for (auto& m : h->ms) m = 0.0;
+  h->timed_steps = 0;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_timer_start(WflowB200* h) {
+  if (!h) return WFLOWB200_ERR_ARG;
+  CUDA_TRY(h, cudaEventRecord(h->tm[0], h->stream));
+  return WFLOWB200_OK;
+}
+int32_t wflowb200_timer_stop(WflowB200* h, double* elapsed_ms) {
+  if (!h || !elapsed_ms) return WFLOWB200_ERR_ARG;
+  CUDA_TRY(h, cudaEventRecord(h->tm[1], h->stream));
+  CUDA_TRY(h, cudaEventSynchronize(h->tm[1]));
+  float ms = 0.f;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->tm[0], h->tm[1]));
+  *elapsed_ms = ms;
   return WFLOWB200_OK;
 }
 

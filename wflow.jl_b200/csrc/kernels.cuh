@@ -6,6 +6,7 @@
 
 namespace wfb {
 
+int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
@@ -27,6 +28,7 @@ struct WaveLaunch {
   double dt;                // model time step (for the averages)
   int grid;                 // cooperative grid size
   int block;
+  int debug;                // bit0: skip node work, bit1: skip barrier (timing experiments only)
 };
 
 int wave_max_grid(int kind, int n_layers, int block, int device);  // co-resident blocks

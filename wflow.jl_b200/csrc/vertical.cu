@@ -607,16 +607,17 @@ total_water_storage_kernel(const DevFields f, const KCfg c, const int32_t* __res
     default: return -1;                               \
   }
 
+int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s) {
+  if (c.nriv == 0) return 0;
+  scatter_river_depth_kernel<<<(c.nriv + 255) / 256, 256, 0, s>>>(f, c);
+  return 1;
+}
+
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           cudaStream_t s) {
-  int launches = 0;
-  if (c.nriv > 0) {
-    scatter_river_depth_kernel<<<(c.nriv + 255) / 256, 256, 0, s>>>(f, c);
-    ++launches;
-  }
   const int grid = (c.n + 255) / 256;
   WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<grid, 256, 0, s>>>(f, c, dt)));
-  return launches + 1;
+  return 1;
 }
 
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s) {

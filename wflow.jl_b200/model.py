@@ -183,6 +183,14 @@ class SbmModel:
     def set_timing(self, enabled: bool):
         self._check(self._L.wflowb200_set_timing(self._h, int(enabled)))
 
+    def timer_start(self):
+        self._check(self._L.wflowb200_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self._L.wflowb200_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def stats(self) -> dict:
         s = _lib.Stats()
         self._check(self._L.wflowb200_get_stats(self._h, C.byref(s)))
