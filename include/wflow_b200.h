@@ -89,9 +89,12 @@ typedef struct {
 #define WFLOWB200_A_SUBDOMAIN_ORDER 7  /* order_subdomain (node ids)                           */
 #define WFLOWB200_A_SUBDOMAIN_INDICES 8 /* subdomain_indices (toposort positions)              */
 #define WFLOWB200_A_LDD 9              /* ldd after flowgraph's pit fix-up                     */
-#define WFLOWB200_A_WAVE_LEVEL_PTR 10  /* B200 wavefront: offsets of the topological-depth levels
-                                          in device order                                      */
-#define WFLOWB200_A_WAVE_PERM 11       /* B200 wavefront: node id held by each device slot     */
+#define WFLOWB200_A_WAVE_LEVEL_PTR 10  /* B200 wavefront: histogram offsets of the
+                                          topological-depth levels                             */
+#define WFLOWB200_A_WAVE_PERM 11       /* node id held by each device slot (chunk, level, id)  */
+#define WFLOWB200_A_WAVE_NODE_LEVEL 12 /* level of every node (0-based), by node id            */
+#define WFLOWB200_A_WAVE_CHUNK_PTR 13  /* slot offsets of the chunks (0-based, n_chunks + 1)   */
+#define WFLOWB200_A_WAVE_CHUNK_OUTLET 14 /* outlet node id of every chunk                      */
 
 #define WFLOWB200_DOMAIN_LAND 0
 #define WFLOWB200_DOMAIN_RIVER 1

@@ -76,23 +76,37 @@ def test_masked_raster_artifacts_and_pit_fixup(pkg):
     assert np.array_equal(art["land"]["order"], land["order"])
 
 
-def test_wavefront_levels_are_a_valid_schedule(pkg):
+def test_wavefront_levels_and_chunks_are_a_valid_schedule(pkg):
     """Every drainage edge spans exactly one wavefront level (the invariant the skewed
-    wavefront relies on), and slots inside a level are ascending node ids."""
+    wavefront relies on); chunks are connected pieces with one outlet; slots are ordered
+    (chunk, level, node id); chunk order is a topological order of the chunk DAG."""
     cfg, dom, _ = pkg.synthetic.make_basin(90, 140, seed=5)
     a = pkg.build_network_artifacts(cfg, dom)["land"]
-    perm, lp = a["wave_perm"], a["wave_level_ptr"]
+    perm, level, cp, outlet = a["wave_perm"], a["wave_node_level"], a["wave_chunk_ptr"], a["wave_chunk_outlet"]
     n = cfg["n"]
     assert sorted(perm.tolist()) == list(range(1, n + 1))
-    level = np.zeros(n, dtype=np.int64)
-    for l in range(len(lp) - 1):
-        seg = perm[lp[l]:lp[l + 1]]
-        assert np.all(np.diff(seg) > 0)
-        level[seg - 1] = l
     down = dom["down"]
     has = down > 0
     assert np.all(level[down[has] - 1] == level[has] + 1)
-    assert np.all(level[~has] == len(lp) - 2)
+    assert np.all(level[~has] == level.max())
+    assert np.array_equal(np.bincount(level), np.diff(a["wave_level_ptr"]))
+    chunk = np.zeros(n, dtype=np.int64)
+    for c in range(len(cp) - 1):
+        seg = perm[cp[c]:cp[c + 1]]
+        chunk[seg - 1] = c
+        key = level[seg - 1] * (n + 1) + seg
+        assert np.all(np.diff(key) > 0)                      # (level, node id) ascending
+        assert seg[-1] == outlet[c] or level[outlet[c] - 1] == level[seg - 1].max()
+        inside = has[seg - 1] & (chunk[down[seg - 1] - 1] == c)
+        # exactly one node of the chunk leaves it (its outlet)
+    for c in range(len(cp) - 1):
+        seg = perm[cp[c]:cp[c + 1]]
+        leaving = [v for v in seg if down[v - 1] == 0 or chunk[down[v - 1] - 1] != c]
+        assert leaving == [outlet[c]]
+        d = down[outlet[c] - 1]
+        if d:
+            assert chunk[d - 1] > c                          # producers come first in the queue
+    assert len(cp) - 1 >= 2
 
 
 def test_cycle_is_rejected(pkg):

@@ -41,7 +41,8 @@ class Stats(C.Structure):
 
 ARTIFACTS = dict(order=0, streamorder=1, upstream_ptr=2, upstream_idx=3, subdomain_level_ptr=4,
                  subdomain_level_idx=5, subdomain_ptr=6, subdomain_order=7, subdomain_indices=8,
-                 ldd=9, wave_level_ptr=10, wave_perm=11)
+                 ldd=9, wave_level_ptr=10, wave_perm=11, wave_node_level=12, wave_chunk_ptr=13,
+                 wave_chunk_outlet=14)
 
 
 def header_symbols():

@@ -32,10 +32,10 @@ std::string g_create_error;
 struct DomainDev {
   Network nw;
   int32_t* node_of_slot = nullptr;  // device, 0-based node id per slot
-  int32_t* level_ptr = nullptr;
-  int32_t* level_of = nullptr;
-  int32_t* up_ptr = nullptr;
-  int32_t* up_idx = nullptr;
+  std::vector<int32_t*> dev_arrays; // everything uploaded for DevNet (freed together)
+  int* progress = nullptr;          // per chunk
+  double* q_out = nullptr;          // per chunk x S
+  size_t q_out_doubles = 0;
   DevNet dev{};
 };
 
@@ -67,6 +67,11 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
     errmsg = "river network: " + err;
     return WFLOWB200_ERR_GRAPH;
   }
+  // chunk sizes of the block-local wavefront (nodes per CTA work item); tunable for experiments
+  const char* cl = getenv("WFB_CHUNK_LAND");
+  const char* cr = getenv("WFB_CHUNK_RIVER");
+  build_chunks(land, cl ? atoll(cl) : 1024);
+  build_chunks(river, cr ? atoll(cr) : 256);
   return WFLOWB200_OK;
 }
 
@@ -87,6 +92,9 @@ int32_t copy_artifact(const Network& nw, int32_t id, int64_t* dst, int64_t capac
     case WFLOWB200_A_LDD: tmp.assign(nw.ldd.begin(), nw.ldd.end()); src = &tmp; break;
     case WFLOWB200_A_WAVE_LEVEL_PTR: src = &nw.wave_level_ptr; break;
     case WFLOWB200_A_WAVE_PERM: src = &nw.perm; break;
+    case WFLOWB200_A_WAVE_NODE_LEVEL: src = &nw.node_level; break;
+    case WFLOWB200_A_WAVE_CHUNK_PTR: src = &nw.chunk_ptr; break;
+    case WFLOWB200_A_WAVE_CHUNK_OUTLET: src = &nw.chunk_outlet; break;
     default: errmsg = "bad artefact id"; return WFLOWB200_ERR_ARG;
   }
   *len_out = (int64_t)src->size();
@@ -120,7 +128,7 @@ struct WflowB200 {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
-  unsigned* d_barrier = nullptr;
+  unsigned* d_queue = nullptr;
   RoutingStats* d_stats = nullptr;
   double* d_dts = nullptr;  // sub-step lengths, 3 x kMaxSub
   unsigned long long* d_count = nullptr;
@@ -146,12 +154,9 @@ struct WflowB200 {
 namespace {
 
 constexpr int kMaxSub = 8192;
-// CTA sizes of the persistent wavefront kernels. The grid barrier costs one same-address L2
-// atomic per CTA (serialised, ~14 ns each), so the surface kernels run ONE 1024-thread CTA per
-// SM (148 arrivals) rather than many small CTAs; the subsurface kernel is register-heavy
-// (soil column in registers) and runs one 256-thread CTA per SM.
-constexpr int kBlockSurface = 1024;
-constexpr int kBlockSsf = 256;
+// CTA sizes of the persistent chunk-walking kernels (one chunk per CTA at a time).
+constexpr int kBlockSurface = 256;
+constexpr int kBlockSsf = 128;
 
 int32_t fail(WflowB200* h, int32_t code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -180,32 +185,64 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
   const Network& nw = d.nw;
   const int64_t n = nw.n;
   CUDA_TRY(h, upload_i32(nw.perm, &d.node_of_slot, -1));
-  CUDA_TRY(h, upload_i32(nw.wave_level_ptr, &d.level_ptr, 0));
-  std::vector<int64_t> level_of(n), up_ptr(n + 1, 0), up_idx;
-  for (int64_t l = 0; l < nw.n_wave_levels; ++l)
-    for (int64_t p = nw.wave_level_ptr[l]; p < nw.wave_level_ptr[l + 1]; ++p) level_of[p] = l;
+  std::vector<int64_t> level_of(n), up_ptr(n + 1, 0), up_idx, up_chunk, outlet_chunk(n, -1);
+  std::vector<int64_t> inl_ptr(nw.n_chunks + 1, 0), inl_level, inl_src;
   up_idx.reserve(nw.in_idx.size());
-  for (int64_t p = 0; p < n; ++p) {
-    const int64_t v = nw.perm[p] - 1;  // in-neighbours are already ascending by node id
-    for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e)
-      up_idx.push_back(nw.slot_of[nw.in_idx[e] - 1]);
-    up_ptr[p + 1] = (int64_t)up_idx.size();
+  up_chunk.reserve(nw.in_idx.size());
+  for (int64_t c = 0; c < nw.n_chunks; ++c) {
+    for (int64_t p = nw.chunk_ptr[c]; p < nw.chunk_ptr[c + 1]; ++p) {
+      const int64_t v = nw.perm[p] - 1;  // in-neighbours are already ascending by node id
+      level_of[p] = nw.node_level[v];
+      for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e) {
+        const int64_t u = nw.in_idx[e] - 1;
+        const int64_t cu = nw.chunk_of_node[u];
+        up_idx.push_back(nw.slot_of[u]);
+        if (cu != c) {
+          up_chunk.push_back(cu);
+          inl_level.push_back(nw.node_level[v]);
+          inl_src.push_back(cu);
+        } else {
+          up_chunk.push_back(-1);
+        }
+      }
+      up_ptr[p + 1] = (int64_t)up_idx.size();
+    }
+    inl_ptr[c + 1] = (int64_t)inl_src.size();
+    const int64_t o = nw.chunk_outlet[c] - 1;
+    if (nw.down[o]) outlet_chunk[nw.slot_of[o]] = c;
   }
-  CUDA_TRY(h, upload_i32(level_of, &d.level_of, 0));
-  CUDA_TRY(h, upload_i32(up_ptr, &d.up_ptr, 0));
-  CUDA_TRY(h, upload_i32(up_idx, &d.up_idx, 0));
+  auto up = [&](const std::vector<int64_t>& src, const int32_t** dst) -> cudaError_t {
+    int32_t* ptr = nullptr;
+    cudaError_t e = upload_i32(src, &ptr, 0);
+    d.dev_arrays.push_back(ptr);
+    *dst = ptr;
+    return e;
+  };
+  CUDA_TRY(h, up(level_of, &d.dev.level_of));
+  CUDA_TRY(h, up(up_ptr, &d.dev.up_ptr));
+  CUDA_TRY(h, up(up_idx, &d.dev.up_idx));
+  CUDA_TRY(h, up(up_chunk, &d.dev.up_chunk));
+  CUDA_TRY(h, up(nw.chunk_ptr, &d.dev.chunk_ptr));
+  CUDA_TRY(h, up(nw.chunk_l0, &d.dev.chunk_l0));
+  CUDA_TRY(h, up(nw.chunk_l1, &d.dev.chunk_l1));
+  CUDA_TRY(h, up(nw.chunk_clp_off, &d.dev.chunk_clp_off));
+  CUDA_TRY(h, up(nw.clp, &d.dev.clp));
+  CUDA_TRY(h, up(inl_ptr, &d.dev.chunk_inl_ptr));
+  CUDA_TRY(h, up(inl_level, &d.dev.inl_level));
+  CUDA_TRY(h, up(inl_src, &d.dev.inl_src));
+  CUDA_TRY(h, up(outlet_chunk, &d.dev.outlet_chunk));
+  CUDA_TRY(h, cudaMalloc((void**)&d.progress, sizeof(int) * (size_t)std::max<int64_t>(nw.n_chunks, 1)));
   d.dev.n = (int32_t)n;
   d.dev.n_levels = (int32_t)nw.n_wave_levels;
-  d.dev.level_ptr = d.level_ptr;
-  d.dev.level_of = d.level_of;
-  d.dev.up_ptr = d.up_ptr;
-  d.dev.up_idx = d.up_idx;
+  d.dev.n_chunks = (int32_t)nw.n_chunks;
   return WFLOWB200_OK;
 }
 
 void free_domain(DomainDev& d) {
-  cudaFree(d.node_of_slot); cudaFree(d.level_ptr); cudaFree(d.level_of);
-  cudaFree(d.up_ptr); cudaFree(d.up_idx);
+  cudaFree(d.node_of_slot);
+  for (int32_t* p : d.dev_arrays) cudaFree(p);
+  cudaFree(d.progress);
+  cudaFree(d.q_out);
 }
 
 // The reference's `while t < dt` sub-stepping with a fixed internal step
@@ -246,25 +283,59 @@ int32_t check_launch(WflowB200* h, int rc, const char* what) {
 
 // Run one routing component with the fixed-step skewed wavefront.
 template <class Launch>
-int32_t run_wave(WflowB200* h, double dt, double dt_fixed, int slot, int grid, int64_t& substeps,
-                 double** q_a, double** q_b, int block, Launch launch, const char* what) {
+int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int slot, int max_grid,
+                 int64_t& substeps, double** q_a, double** q_b, int block, Launch launch,
+                 const char* what) {
   std::vector<double> dts;
   const int S = fixed_substeps(dt, dt_fixed, dts);
   if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
   double* d_dts = h->d_dts + (size_t)slot * kMaxSub;
   CUDA_TRY(h, cudaMemcpyAsync(d_dts, dts.data(), S * sizeof(double), cudaMemcpyHostToDevice,
                               h->stream));
+  const size_t need = (size_t)std::max<int64_t>(d.nw.n_chunks, 1) * (size_t)S;
+  if (need > d.q_out_doubles) {  // outlet discharge of every sub-step, per chunk
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d.q_out);
+    d.q_out = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d.q_out, need * sizeof(double)));
+    d.q_out_doubles = need;
+  }
   WaveLaunch w{};
-  w.barrier = h->d_barrier + slot * 32;
+  w.queue = h->d_queue + slot * 32;
+  w.progress = d.progress;
+  w.q_out = d.q_out;
   w.stats = h->d_stats;
   w.dts = d_dts;
   w.S = S;
   w.dt = dt;
-  w.grid = grid;
+  w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
   w.block = block;
-  { const char* dbg = getenv("WFB_WAVE_DEBUG"); w.debug = dbg ? atoi(dbg) : 0; }
+  w.prof = nullptr;
+  const char* prof_env = getenv("WFB_WAVE_PROF");  // developer aid: dump per-chunk timing
+  const bool prof = prof_env && atoi(prof_env) == slot + 1;
+  if (prof) {
+    cudaMalloc((void**)&w.prof, sizeof(long long) * 6 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1));
+    cudaMemset(w.prof, 0, sizeof(long long) * 6 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1));
+  }
   int32_t rc = check_launch(h, launch(w), what);
   if (rc) return rc;
+  if (prof) {
+    std::vector<long long> hp(6 * (size_t)d.nw.n_chunks);
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(hp.data(), w.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(w.prof);
+    FILE* fp = fopen("gpurun_out/wave_prof.csv", "w");
+    if (fp) {
+      fprintf(fp, "chunk,start_ns,end_ns,wait_cyc,proc_cyc,stages,nodes,l0,l1,n_inlets\n");
+      long long t0 = hp.empty() ? 0 : hp[0];
+      for (int64_t c = 0; c < d.nw.n_chunks; ++c) t0 = std::min(t0, hp[6 * c]);
+      for (int64_t c = 0; c < d.nw.n_chunks; ++c)
+        fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,0\n", (long long)c,
+                hp[6 * c] - t0, hp[6 * c + 1] - t0, hp[6 * c + 2], hp[6 * c + 3], hp[6 * c + 4],
+                hp[6 * c + 5], (long long)d.nw.chunk_l0[c], (long long)d.nw.chunk_l1[c]);
+      fclose(fp);
+    }
+  }
   substeps = S;
   if (S & 1) std::swap(*q_a, *q_b);  // the last sub-step wrote the other parity buffer
   return WFLOWB200_OK;
@@ -408,7 +479,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_stage, h->stage_doubles * sizeof(double)));
   TRY_CREATE(cudaMalloc((void**)&h->d_forcing, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMallocHost((void**)&h->h_pinned, (size_t)3 * h->n * sizeof(double)));
-  TRY_CREATE(cudaMalloc((void**)&h->d_barrier, 3 * 32 * sizeof(unsigned)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
   TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
   TRY_CREATE(cudaMalloc((void**)&h->d_dts, 3 * kMaxSub * sizeof(double)));
@@ -427,7 +498,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->grid_riv = wave_max_grid(1, h->N, kBlockSurface, cfg->device);
   h->grid_ssf = wave_max_grid(2, h->N, kBlockSsf, cfg->device);
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
-    h->err = "cooperative occupancy query failed";
+    h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
   }
   TRY_CREATE(cudaStreamSynchronize(h->stream));
@@ -442,7 +513,7 @@ void wflowb200_destroy(WflowB200* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
-  cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_barrier);
+  cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
   cudaFree(h->d_stats); cudaFree(h->d_dts); cudaFree(h->d_count); cudaFree(h->d_min);
   free_domain(h->land); free_domain(h->river);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
@@ -562,7 +633,7 @@ int32_t wflowb200_exchange_recharge(WflowB200* h) {
 int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
-  return run_wave(h, dt, h->cfg.dt_ssf, 2, h->grid_ssf, h->sub_ssf, &h->f.ssf_q, &h->f.ssf_q2,
+  return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, h->grid_ssf, h->sub_ssf, &h->f.ssf_q, &h->f.ssf_q2,
                   kBlockSsf, [&](const WaveLaunch& w) {
                     return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
                   }, "update_subsurface_flow_model");
@@ -584,7 +655,7 @@ int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h) {
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
-  return run_wave(h, dt, h->cfg.dt_land, 0, h->grid_olf, h->sub_land, &h->f.olf_q, &h->f.olf_q2,
+  return run_wave(h, h->land, dt, h->cfg.dt_land, 0, h->grid_olf, h->sub_land, &h->f.olf_q, &h->f.olf_q2,
                   kBlockSurface, [&](const WaveLaunch& w) {
                     return launch_overland_wave(h->f, h->kc, h->land.dev, w, h->stream);
                   }, "update_overland_flow_model");
@@ -600,7 +671,7 @@ int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->nriv == 0) return WFLOWB200_OK;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
-  return run_wave(h, dt, h->cfg.dt_river, 1, h->grid_riv, h->sub_river, &h->f.riv_q, &h->f.riv_q2,
+  return run_wave(h, h->river, dt, h->cfg.dt_river, 1, h->grid_riv, h->sub_river, &h->f.riv_q, &h->f.riv_q2,
                   kBlockSurface, [&](const WaveLaunch& w) {
                     return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
                   }, "update_river_flow_model");

@@ -21,14 +21,17 @@ struct RoutingStats {
 };
 
 struct WaveLaunch {
-  unsigned* barrier;        // device counter, zeroed by the launcher
+  unsigned* queue;          // device: next chunk to hand out (zeroed by the launcher)
+  int* progress;            // device: per chunk, sub-steps completed at its outlet (zeroed)
+  double* q_out;            // device: per chunk, the outlet discharge of every sub-step (S each)
   RoutingStats* stats;      // device
   const double* dts;        // device: sub-step lengths (S doubles)
   int S;                    // number of sub-steps pipelined through the wavefront
   double dt;                // model time step (for the averages)
-  int grid;                 // cooperative grid size
+  int grid;
   int block;
-  int debug;                // bit0: skip node work, bit1: skip barrier (timing experiments only)
+  long long* prof;          // optional: 6 x n_chunks int64 (start ns, end ns, wait cycles,
+                            // process cycles, stages, nodes) written by thread 0 of each chunk
 };
 
 int wave_max_grid(int kind, int n_layers, int block, int device);  // co-resident blocks

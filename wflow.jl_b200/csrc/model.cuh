@@ -27,14 +27,29 @@ struct DevFields {
   double* ssf_q2;
 };
 
+// One routing domain (land or river) as the wavefront kernels see it. Slots are ordered by
+// (chunk, level, node id); a chunk is a connected piece of the drainage forest with ONE outlet
+// node, walked by one CTA.
 struct DevNet {
-  int32_t n;                   // nodes
-  int32_t n_levels;            // wavefront levels
-  const int32_t* level_ptr;    // n_levels + 1 slot offsets
-  const int32_t* level_of;     // slot -> level
-  const int32_t* up_ptr;       // slot -> CSR offsets of upstream SLOTS
-  const int32_t* up_idx;       // upstream slots, ordered by ascending NODE ID (the reference's
-                               // left-fold order, utils.jl:472-477)
+  int32_t n;                    // nodes
+  int32_t n_levels;             // wavefront levels of the whole domain
+  int32_t n_chunks;
+  const int32_t* level_of;      // slot -> level
+  const int32_t* up_ptr;        // slot -> CSR offsets of its upstream edges
+  const int32_t* up_idx;        // upstream SLOTS, ordered by ascending NODE ID (the reference's
+                                // left-fold order, utils.jl:472-477)
+  const int32_t* up_chunk;      // per edge: producer chunk if the upstream node is another
+                                // chunk's outlet, else -1
+  const int32_t* chunk_ptr;     // n_chunks + 1 slot offsets
+  const int32_t* chunk_l0;      // first level of a chunk
+  const int32_t* chunk_l1;      // last level (= level of its outlet node)
+  const int32_t* chunk_clp_off; // offsets into clp
+  const int32_t* clp;           // per chunk: absolute slot offsets of its levels (l1-l0+2 entries)
+  const int32_t* chunk_inl_ptr; // n_chunks + 1 offsets into the inlet lists
+  const int32_t* inl_level;     // level of the receiving node of an inlet edge
+  const int32_t* inl_src;       // producer chunk of an inlet edge
+  const int32_t* outlet_chunk;  // slot -> chunk id if the slot is a chunk outlet that feeds
+                                // another chunk, else -1
 };
 
 struct KCfg {

@@ -318,17 +318,78 @@ bool build_artifacts(Network& nw, int nthreads, int min_sto, const int64_t* so_o
   }
   nw.n_wave_levels = n ? dmax + 1 : 0;
   nw.wave_level_ptr.assign(nw.n_wave_levels + 1, 0);
-  for (int64_t v = 0; v < n; ++v) nw.wave_level_ptr[dmax - dist[v] + 1]++;
+  nw.node_level.assign(n, 0);
+  for (int64_t v = 0; v < n; ++v) {
+    nw.node_level[v] = dmax - dist[v];
+    nw.wave_level_ptr[dmax - dist[v] + 1]++;
+  }
   for (int64_t l = 0; l < nw.n_wave_levels; ++l) nw.wave_level_ptr[l + 1] += nw.wave_level_ptr[l];
+  return true;
+}
+
+void build_chunks(Network& nw, int64_t target) {
+  const int64_t n = nw.n;
+  if (target < 1) target = 1;
+  // bottom-up accumulation of the not-yet-cut upstream tree size
+  std::vector<int64_t> acc(n, 1);
+  std::vector<uint8_t> cut(n, 0);
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t v = nw.order[k] - 1, d = nw.down[v];
+    if (d == 0 || acc[v] >= target) cut[v] = 1;
+    else acc[d - 1] += acc[v];
+  }
+  // chunk outlets in execution order: ascending outlet level, then node id. A producer's outlet
+  // is exactly one level above its consumer's receiving node, so this is a topological order
+  // of the chunk DAG (dynamic scheduling in this order cannot deadlock).
+  std::vector<int64_t> outlets;
+  for (int64_t v = 0; v < n; ++v)
+    if (cut[v]) outlets.push_back(v);
+  std::sort(outlets.begin(), outlets.end(), [&](int64_t a, int64_t b) {
+    return nw.node_level[a] != nw.node_level[b] ? nw.node_level[a] < nw.node_level[b] : a < b;
+  });
+  nw.n_chunks = (int64_t)outlets.size();
+  nw.chunk_of_node.assign(n, -1);
+  nw.chunk_outlet.assign(nw.n_chunks, 0);
+  for (int64_t c = 0; c < nw.n_chunks; ++c) {
+    nw.chunk_of_node[outlets[c]] = c;
+    nw.chunk_outlet[c] = outlets[c] + 1;
+  }
+  for (int64_t k = n - 1; k >= 0; --k) {  // downstream -> upstream
+    const int64_t v = nw.order[k] - 1;
+    if (!cut[v]) nw.chunk_of_node[v] = nw.chunk_of_node[nw.down[v] - 1];
+  }
+  // slot order: (chunk, level, node id)
+  std::vector<int64_t> nodes(n);
+  for (int64_t v = 0; v < n; ++v) nodes[v] = v;
+  std::sort(nodes.begin(), nodes.end(), [&](int64_t a, int64_t b) {
+    if (nw.chunk_of_node[a] != nw.chunk_of_node[b]) return nw.chunk_of_node[a] < nw.chunk_of_node[b];
+    if (nw.node_level[a] != nw.node_level[b]) return nw.node_level[a] < nw.node_level[b];
+    return a < b;
+  });
   nw.perm.assign(n, 0);
   nw.slot_of.assign(n, 0);
-  std::vector<int64_t> fill(nw.wave_level_ptr.begin(), nw.wave_level_ptr.end() - 1);
-  for (int64_t v = 0; v < n; ++v) {  // ascending id inside a level
-    const int64_t s = fill[dmax - dist[v]]++;
-    nw.perm[s] = v + 1;
-    nw.slot_of[v] = s;
+  for (int64_t p = 0; p < n; ++p) { nw.perm[p] = nodes[p] + 1; nw.slot_of[nodes[p]] = p; }
+  nw.chunk_ptr.assign(nw.n_chunks + 1, 0);
+  nw.chunk_l0.assign(nw.n_chunks, 0);
+  nw.chunk_l1.assign(nw.n_chunks, 0);
+  nw.chunk_clp_off.assign(nw.n_chunks + 1, 0);
+  nw.clp.clear();
+  int64_t p = 0;
+  for (int64_t c = 0; c < nw.n_chunks; ++c) {
+    nw.chunk_ptr[c] = p;
+    const int64_t l0 = nw.node_level[nodes[p]];
+    const int64_t l1 = nw.node_level[outlets[c]];
+    nw.chunk_l0[c] = l0;
+    nw.chunk_l1[c] = l1;
+    nw.chunk_clp_off[c] = (int64_t)nw.clp.size();
+    for (int64_t l = l0; l <= l1; ++l) {
+      nw.clp.push_back(p);
+      while (p < n && nw.chunk_of_node[nodes[p]] == c && nw.node_level[nodes[p]] == l) ++p;
+    }
+    nw.clp.push_back(p);
   }
-  return true;
+  nw.chunk_ptr[nw.n_chunks] = p;
+  nw.chunk_clp_off[nw.n_chunks] = (int64_t)nw.clp.size();
 }
 
 }  // namespace wfb

@@ -32,11 +32,21 @@ struct Network {
   std::vector<int64_t> up_ptr, up_idx; // upstream_nodes by toposort position
   // sub-domain partition (order_of_subdomains / order_subdomain / subdomain_indices)
   std::vector<int64_t> lvl_ptr, lvl_idx, sub_ptr, sub_order, sub_indices;
-  // B200 wavefront
+  // B200 wavefront: topological-depth levels, and the partition of the forest into CHUNKS
+  // (connected pieces with one outlet node each) that one CTA walks on its own.
   int64_t n_wave_levels = 0;
-  std::vector<int64_t> wave_level_ptr; // n_wave_levels + 1 offsets into device order
-  std::vector<int64_t> perm;           // device slot -> node id (1-based)
+  std::vector<int64_t> wave_level_ptr; // histogram offsets of the levels (n_wave_levels + 1)
+  std::vector<int64_t> node_level;     // node id - 1 -> level
+  std::vector<int64_t> perm;           // device slot -> node id (1-based); chunk-major, then
+                                       // level, then node id
   std::vector<int64_t> slot_of;        // node id - 1 -> device slot (0-based)
+  int64_t n_chunks = 0;
+  std::vector<int64_t> chunk_of_node;  // node id - 1 -> chunk (in execution order)
+  std::vector<int64_t> chunk_ptr;      // n_chunks + 1 slot offsets
+  std::vector<int64_t> chunk_l0, chunk_l1;  // first / last (= outlet) level of a chunk
+  std::vector<int64_t> chunk_outlet;   // outlet node id (1-based)
+  std::vector<int64_t> chunk_clp_off;  // n_chunks + 1 offsets into clp
+  std::vector<int64_t> clp;            // per chunk: (l1 - l0 + 2) absolute slot offsets of its levels
 };
 
 // Build `down` from a gridded LDD (flowgraph). `indices` holds 2n CartesianIndex pairs.
@@ -46,5 +56,8 @@ bool build_graph(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, co
 // order, stream order (unless `streamorder_override` given), upstream CSR, partition, wavefront.
 bool build_artifacts(Network& nw, int nthreads, int min_streamorder,
                      const int64_t* streamorder_override, std::string& err);
+// Partition into chunks of about `target` nodes (bottom-up: a node whose not-yet-cut upstream
+// tree reaches `target` nodes, and every pit, closes a chunk) and derive the device slot order.
+void build_chunks(Network& nw, int64_t target);
 
 }  // namespace wfb
