@@ -33,9 +33,8 @@ struct DomainDev {
   Network nw;
   int32_t* node_of_slot = nullptr;  // device, 0-based node id per slot
   std::vector<int32_t*> dev_arrays; // everything uploaded for DevNet (freed together)
-  int* progress = nullptr;          // per chunk
-  double* q_out = nullptr;          // per chunk x S
-  size_t q_out_doubles = 0;
+  unsigned long long* q_out = nullptr;  // per chunk x S x NV published outlet values
+  size_t q_out_words = 0;
   DevNet dev{};
 };
 
@@ -70,8 +69,8 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
   // chunk sizes of the block-local wavefront (nodes per CTA work item); tunable for experiments
   const char* cl = getenv("WFB_CHUNK_LAND");
   const char* cr = getenv("WFB_CHUNK_RIVER");
-  build_chunks(land, cl ? atoll(cl) : 1024);
-  build_chunks(river, cr ? atoll(cr) : 256);
+  build_chunks(land, std::min<int64_t>(cl ? atoll(cl) : WFB_CHUNK_NODES, WFB_CHUNK_NODES));
+  build_chunks(river, std::min<int64_t>(cr ? atoll(cr) : WFB_CHUNK_NODES, WFB_CHUNK_NODES));
   return WFLOWB200_OK;
 }
 
@@ -130,20 +129,13 @@ struct WflowB200 {
   bool forcing_pending = false;
   unsigned* d_queue = nullptr;
   RoutingStats* d_stats = nullptr;
-  double* d_dts = nullptr;  // sub-step lengths, 3 x kMaxSub
   unsigned long long* d_count = nullptr;
   double* d_min = nullptr;
   int grid_olf = 0, grid_riv = 0, grid_ssf = 0;
   int64_t launches = 0;
   int64_t sub_land = 0, sub_river = 0, sub_ssf = 0;
   bool timing = false;
-  // the discharge fields flip between their two parity buffers (routing.cu)
-  double* field_ptr_current(int id) const {
-    if (id == WFLOWB200_F_olf_q) return f.olf_q;
-    if (id == WFLOWB200_F_riv_q) return f.riv_q;
-    if (id == WFLOWB200_F_ssf_q) return f.ssf_q;
-    return field_ptr[id];
-  }
+  size_t smem_olf = 0, smem_riv = 0, smem_ssf = 0;
   cudaEvent_t ev[12] = {};
   cudaEvent_t tm[2] = {};
   double ms[7] = {};
@@ -154,9 +146,6 @@ struct WflowB200 {
 namespace {
 
 constexpr int kMaxSub = 8192;
-// CTA sizes of the persistent chunk-walking kernels (one chunk per CTA at a time).
-constexpr int kBlockSurface = 256;
-constexpr int kBlockSsf = 128;
 
 int32_t fail(WflowB200* h, int32_t code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -185,32 +174,39 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
   const Network& nw = d.nw;
   const int64_t n = nw.n;
   CUDA_TRY(h, upload_i32(nw.perm, &d.node_of_slot, -1));
-  std::vector<int64_t> level_of(n), up_ptr(n + 1, 0), up_idx, up_chunk, outlet_chunk(n, -1);
+  std::vector<int64_t> level_local(n), up_ptr(n + 1, 0), up_src, chunk_nlev(nw.n_chunks),
+      chunk_feeds(nw.n_chunks);
   std::vector<int64_t> inl_ptr(nw.n_chunks + 1, 0), inl_level, inl_src;
-  up_idx.reserve(nw.in_idx.size());
-  up_chunk.reserve(nw.in_idx.size());
+  up_src.reserve(nw.in_idx.size());
+  int64_t max_inlets = 0;
   for (int64_t c = 0; c < nw.n_chunks; ++c) {
-    for (int64_t p = nw.chunk_ptr[c]; p < nw.chunk_ptr[c + 1]; ++p) {
+    const int64_t p0 = nw.chunk_ptr[c];
+    if (nw.chunk_ptr[c + 1] - p0 > WFB_CHUNK_NODES)
+      return fail(h, WFLOWB200_ERR_STATE, "chunk exceeds WFB_CHUNK_NODES");
+    int64_t k = 0;  // inlet number inside the chunk
+    for (int64_t p = p0; p < nw.chunk_ptr[c + 1]; ++p) {
       const int64_t v = nw.perm[p] - 1;  // in-neighbours are already ascending by node id
-      level_of[p] = nw.node_level[v];
+      level_local[p] = nw.node_level[v] - nw.chunk_l0[c];
       for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e) {
         const int64_t u = nw.in_idx[e] - 1;
         const int64_t cu = nw.chunk_of_node[u];
-        up_idx.push_back(nw.slot_of[u]);
         if (cu != c) {
-          up_chunk.push_back(cu);
-          inl_level.push_back(nw.node_level[v]);
+          up_src.push_back(WFB_CHUNK_NODES + k++);
+          inl_level.push_back(level_local[p]);
           inl_src.push_back(cu);
         } else {
-          up_chunk.push_back(-1);
+          up_src.push_back(nw.slot_of[u] - p0);
         }
       }
-      up_ptr[p + 1] = (int64_t)up_idx.size();
+      up_ptr[p + 1] = (int64_t)up_src.size();
     }
     inl_ptr[c + 1] = (int64_t)inl_src.size();
-    const int64_t o = nw.chunk_outlet[c] - 1;
-    if (nw.down[o]) outlet_chunk[nw.slot_of[o]] = c;
+    max_inlets = std::max(max_inlets, k);
+    chunk_nlev[c] = nw.chunk_l1[c] - nw.chunk_l0[c] + 1;
+    chunk_feeds[c] = nw.down[nw.chunk_outlet[c] - 1] ? 1 : 0;
   }
+  if (WFB_CHUNK_NODES + max_inlets > 65535)
+    return fail(h, WFLOWB200_ERR_STATE, "too many inlet edges in one chunk");
   auto up = [&](const std::vector<int64_t>& src, const int32_t** dst) -> cudaError_t {
     int32_t* ptr = nullptr;
     cudaError_t e = upload_i32(src, &ptr, 0);
@@ -218,30 +214,25 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
     *dst = ptr;
     return e;
   };
-  CUDA_TRY(h, up(level_of, &d.dev.level_of));
-  CUDA_TRY(h, up(up_ptr, &d.dev.up_ptr));
-  CUDA_TRY(h, up(up_idx, &d.dev.up_idx));
-  CUDA_TRY(h, up(up_chunk, &d.dev.up_chunk));
   CUDA_TRY(h, up(nw.chunk_ptr, &d.dev.chunk_ptr));
-  CUDA_TRY(h, up(nw.chunk_l0, &d.dev.chunk_l0));
-  CUDA_TRY(h, up(nw.chunk_l1, &d.dev.chunk_l1));
-  CUDA_TRY(h, up(nw.chunk_clp_off, &d.dev.chunk_clp_off));
-  CUDA_TRY(h, up(nw.clp, &d.dev.clp));
+  CUDA_TRY(h, up(chunk_nlev, &d.dev.chunk_nlev));
+  CUDA_TRY(h, up(chunk_feeds, &d.dev.chunk_feeds));
+  CUDA_TRY(h, up(level_local, &d.dev.level_local));
+  CUDA_TRY(h, up(up_ptr, &d.dev.up_ptr));
+  CUDA_TRY(h, up(up_src, &d.dev.up_src));
   CUDA_TRY(h, up(inl_ptr, &d.dev.chunk_inl_ptr));
   CUDA_TRY(h, up(inl_level, &d.dev.inl_level));
   CUDA_TRY(h, up(inl_src, &d.dev.inl_src));
-  CUDA_TRY(h, up(outlet_chunk, &d.dev.outlet_chunk));
-  CUDA_TRY(h, cudaMalloc((void**)&d.progress, sizeof(int) * (size_t)std::max<int64_t>(nw.n_chunks, 1)));
   d.dev.n = (int32_t)n;
   d.dev.n_levels = (int32_t)nw.n_wave_levels;
   d.dev.n_chunks = (int32_t)nw.n_chunks;
+  d.dev.max_inlets = (int32_t)max_inlets;
   return WFLOWB200_OK;
 }
 
 void free_domain(DomainDev& d) {
   cudaFree(d.node_of_slot);
   for (int32_t* p : d.dev_arrays) cudaFree(p);
-  cudaFree(d.progress);
   cudaFree(d.q_out);
 }
 
@@ -281,63 +272,36 @@ int32_t check_launch(WflowB200* h, int rc, const char* what) {
   return WFLOWB200_OK;
 }
 
-// Run one routing component with the fixed-step skewed wavefront.
+// Run one routing component with the fixed-step skewed wavefront. kind: 0 overland, 1 river,
+// 2 subsurface; nv = values published per node and sub-step.
 template <class Launch>
-int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int slot, int max_grid,
-                 int64_t& substeps, double** q_a, double** q_b, int block, Launch launch,
-                 const char* what) {
+int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kind, int nv,
+                 int max_grid, size_t smem, int64_t& substeps, Launch launch, const char* what) {
   std::vector<double> dts;
   const int S = fixed_substeps(dt, dt_fixed, dts);
   if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
-  double* d_dts = h->d_dts + (size_t)slot * kMaxSub;
-  CUDA_TRY(h, cudaMemcpyAsync(d_dts, dts.data(), S * sizeof(double), cudaMemcpyHostToDevice,
-                              h->stream));
-  const size_t need = (size_t)std::max<int64_t>(d.nw.n_chunks, 1) * (size_t)S;
-  if (need > d.q_out_doubles) {  // outlet discharge of every sub-step, per chunk
+  const size_t need = (size_t)std::max<int64_t>(d.nw.n_chunks, 1) * (size_t)S * (size_t)nv;
+  if (need > d.q_out_words) {  // outlet values of every sub-step, per chunk
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d.q_out);
     d.q_out = nullptr;
-    CUDA_TRY(h, cudaMalloc((void**)&d.q_out, need * sizeof(double)));
-    d.q_out_doubles = need;
+    d.q_out_words = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&d.q_out, need * sizeof(unsigned long long)));
+    d.q_out_words = need;
   }
   WaveLaunch w{};
-  w.queue = h->d_queue + slot * 32;
-  w.progress = d.progress;
+  w.queue = h->d_queue + kind * 32;
   w.q_out = d.q_out;
   w.stats = h->d_stats;
-  w.dts = d_dts;
   w.S = S;
+  w.dt_fixed = dts[0];
+  w.dt_last = dts[S - 1];
   w.dt = dt;
   w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
-  w.block = block;
-  w.prof = nullptr;
-  const char* prof_env = getenv("WFB_WAVE_PROF");  // developer aid: dump per-chunk timing
-  const bool prof = prof_env && atoi(prof_env) == slot + 1;
-  if (prof) {
-    cudaMalloc((void**)&w.prof, sizeof(long long) * 6 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1));
-    cudaMemset(w.prof, 0, sizeof(long long) * 6 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1));
-  }
+  w.smem = smem;
   int32_t rc = check_launch(h, launch(w), what);
   if (rc) return rc;
-  if (prof) {
-    std::vector<long long> hp(6 * (size_t)d.nw.n_chunks);
-    cudaStreamSynchronize(h->stream);
-    cudaMemcpy(hp.data(), w.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(w.prof);
-    FILE* fp = fopen("gpurun_out/wave_prof.csv", "w");
-    if (fp) {
-      fprintf(fp, "chunk,start_ns,end_ns,wait_cyc,proc_cyc,stages,nodes,l0,l1,n_inlets\n");
-      long long t0 = hp.empty() ? 0 : hp[0];
-      for (int64_t c = 0; c < d.nw.n_chunks; ++c) t0 = std::min(t0, hp[6 * c]);
-      for (int64_t c = 0; c < d.nw.n_chunks; ++c)
-        fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,0\n", (long long)c,
-                hp[6 * c] - t0, hp[6 * c + 1] - t0, hp[6 * c + 2], hp[6 * c + 3], hp[6 * c + 4],
-                hp[6 * c + 5], (long long)d.nw.chunk_l0[c], (long long)d.nw.chunk_l1[c]);
-      fclose(fp);
-    }
-  }
   substeps = S;
-  if (S & 1) std::swap(*q_a, *q_b);  // the last sub-step wrote the other parity buffer
   return WFLOWB200_OK;
 }
 
@@ -398,8 +362,6 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     const int k = kFieldKinds[i];
     total += k == 3 ? (size_t)h->nrs : (size_t)h->ns * layers_of(h, k);
   }
-  const size_t off_q2 = total;
-  total += 2 * (size_t)h->ns + (size_t)h->nrs;
   h->pool_doubles = total;
 #define TRY_CREATE(expr)                                                       \
   do {                                                                         \
@@ -424,9 +386,6 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     WFLOWB200_FIELDS(X)
 #undef X
   }
-  h->f.olf_q2 = h->pool + off_q2;
-  h->f.ssf_q2 = h->pool + off_q2 + h->ns;
-  h->f.riv_q2 = h->pool + off_q2 + 2 * (size_t)h->ns;
   // MISSING_VALUE everywhere, then the reference's non-NaN defaults
   launch_fill(h->pool, (long long)total, NAN, h->stream);
   auto fill = [&](double* p, int kind, double v) {
@@ -482,7 +441,6 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
   TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
-  TRY_CREATE(cudaMalloc((void**)&h->d_dts, 3 * kMaxSub * sizeof(double)));
   TRY_CREATE(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
   TRY_CREATE(cudaMalloc((void**)&h->d_min, sizeof(double)));
 
@@ -494,9 +452,12 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->kc.qroot = h->cfg.kin_wave_min_flow_qroot;
 
   // persistent cooperative grids: as many co-resident CTAs as the device holds
-  h->grid_olf = wave_max_grid(0, h->N, kBlockSurface, cfg->device);
-  h->grid_riv = wave_max_grid(1, h->N, kBlockSurface, cfg->device);
-  h->grid_ssf = wave_max_grid(2, h->N, kBlockSsf, cfg->device);
+  h->smem_olf = wave_smem(0, h->land.dev.max_inlets);
+  h->smem_riv = wave_smem(1, h->river.dev.max_inlets);
+  h->smem_ssf = wave_smem(2, h->land.dev.max_inlets);
+  h->grid_olf = wave_max_grid(0, h->N, h->smem_olf, cfg->device);
+  h->grid_riv = wave_max_grid(1, h->N, h->smem_riv, cfg->device);
+  h->grid_ssf = wave_max_grid(2, h->N, h->smem_ssf, cfg->device);
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -514,7 +475,7 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
-  cudaFree(h->d_stats); cudaFree(h->d_dts); cudaFree(h->d_count); cudaFree(h->d_min);
+  cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
   free_domain(h->land); free_domain(h->river);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
   if (h->forcing_consumed) cudaEventDestroy(h->forcing_consumed);
@@ -552,7 +513,7 @@ int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t
   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, src, extent * sizeof(double), cudaMemcpyHostToDevice,
                               h->stream));
   const DomainDev& d = kind == 3 ? h->river : h->land;
-  h->launches += launch_gather_field(h->field_ptr_current(id), h->d_stage, d.node_of_slot, count,
+  h->launches += launch_gather_field(h->field_ptr[id], h->d_stage, d.node_of_slot, count,
                                      kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return WFLOWB200_OK;
@@ -567,7 +528,7 @@ int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, i
   rc = wait_forcing(h);
   if (rc) return rc;
   const DomainDev& d = kind == 3 ? h->river : h->land;
-  h->launches += launch_scatter_field(h->d_stage, h->field_ptr_current(id), d.node_of_slot, count,
+  h->launches += launch_scatter_field(h->d_stage, h->field_ptr[id], d.node_of_slot, count,
                                       kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_stage, extent * sizeof(double), cudaMemcpyDeviceToHost,
                               h->stream));
@@ -633,8 +594,8 @@ int32_t wflowb200_exchange_recharge(WflowB200* h) {
 int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
-  return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, h->grid_ssf, h->sub_ssf, &h->f.ssf_q, &h->f.ssf_q2,
-                  kBlockSsf, [&](const WaveLaunch& w) {
+  return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
+                  [&](const WaveLaunch& w) {
                     return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
                   }, "update_subsurface_flow_model");
 }
@@ -655,8 +616,8 @@ int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h) {
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
-  return run_wave(h, h->land, dt, h->cfg.dt_land, 0, h->grid_olf, h->sub_land, &h->f.olf_q, &h->f.olf_q2,
-                  kBlockSurface, [&](const WaveLaunch& w) {
+  return run_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, h->grid_olf, h->smem_olf, h->sub_land,
+                  [&](const WaveLaunch& w) {
                     return launch_overland_wave(h->f, h->kc, h->land.dev, w, h->stream);
                   }, "update_overland_flow_model");
 }
@@ -671,8 +632,8 @@ int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->nriv == 0) return WFLOWB200_OK;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
-  return run_wave(h, h->river, dt, h->cfg.dt_river, 1, h->grid_riv, h->sub_river, &h->f.riv_q, &h->f.riv_q2,
-                  kBlockSurface, [&](const WaveLaunch& w) {
+  return run_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
+                  [&](const WaveLaunch& w) {
                     return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
                   }, "update_river_flow_model");
 }

@@ -21,20 +21,21 @@ struct RoutingStats {
 };
 
 struct WaveLaunch {
-  unsigned* queue;          // device: next chunk to hand out (zeroed by the launcher)
-  int* progress;            // device: per chunk, sub-steps completed at its outlet (zeroed)
-  double* q_out;            // device: per chunk, the outlet discharge of every sub-step (S each)
-  RoutingStats* stats;      // device
-  const double* dts;        // device: sub-step lengths (S doubles)
-  int S;                    // number of sub-steps pipelined through the wavefront
-  double dt;                // model time step (for the averages)
+  unsigned* queue;            // device: next chunk to hand out (zeroed by the launcher)
+  unsigned long long* q_out;  // device: per chunk, the value(s) its outlet publishes in every
+                              // sub-step (bit patterns, S x NV each; all-ones = not yet written)
+  RoutingStats* stats;        // device
+  int S;                      // number of sub-steps pipelined through the wavefront
+  double dt_fixed, dt_last;   // sub-step lengths: S - 1 times dt_fixed, then dt_last
+  double dt;                  // model time step (for the averages)
   int grid;
-  int block;
-  long long* prof;          // optional: 6 x n_chunks int64 (start ns, end ns, wait cycles,
-                            // process cycles, stages, nodes) written by thread 0 of each chunk
+  size_t smem;                // dynamic shared memory of the kernel (wave_smem)
 };
 
-int wave_max_grid(int kind, int n_layers, int block, int device);  // co-resident blocks
+// kind: 0 overland, 1 river, 2 subsurface
+int wave_block();
+size_t wave_smem(int kind, int max_inlets);
+int wave_max_grid(int kind, int n_layers, size_t smem, int device);  // co-resident CTAs
 int launch_overland_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
                          cudaStream_t s);
 int launch_river_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,

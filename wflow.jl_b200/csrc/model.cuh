@@ -20,36 +20,29 @@ struct DevFields {
   int32_t* number_of_layers;   // land
   int32_t* n_unsatlayers;      // land
   int32_t* riv_land_slot;      // river slot -> land slot
-  // double-buffered discharges of the skewed wavefront (see routing.cu); buffer 0 aliases the
-  // canonical field when `*_phase` == 0
-  double* olf_q2;
-  double* riv_q2;
-  double* ssf_q2;
 };
 
 // One routing domain (land or river) as the wavefront kernels see it. Slots are ordered by
 // (chunk, level, node id); a chunk is a connected piece of the drainage forest with ONE outlet
-// node, walked by one CTA.
+// node (its last slot) and at most WFB_CHUNK_NODES nodes: one CTA walks it, one thread per node.
+#define WFB_CHUNK_NODES 256
 struct DevNet {
   int32_t n;                    // nodes
   int32_t n_levels;             // wavefront levels of the whole domain
   int32_t n_chunks;
-  const int32_t* level_of;      // slot -> level
-  const int32_t* up_ptr;        // slot -> CSR offsets of its upstream edges
-  const int32_t* up_idx;        // upstream SLOTS, ordered by ascending NODE ID (the reference's
-                                // left-fold order, utils.jl:472-477)
-  const int32_t* up_chunk;      // per edge: producer chunk if the upstream node is another
-                                // chunk's outlet, else -1
+  int32_t max_inlets;           // largest number of inlet edges of any chunk
   const int32_t* chunk_ptr;     // n_chunks + 1 slot offsets
-  const int32_t* chunk_l0;      // first level of a chunk
-  const int32_t* chunk_l1;      // last level (= level of its outlet node)
-  const int32_t* chunk_clp_off; // offsets into clp
-  const int32_t* clp;           // per chunk: absolute slot offsets of its levels (l1-l0+2 entries)
+  const int32_t* chunk_nlev;    // number of levels a chunk spans
+  const int32_t* chunk_feeds;   // 1 if the chunk's outlet drains into another chunk
+  const int32_t* level_local;   // slot -> level inside its chunk (0 = the chunk's first level)
+  const int32_t* up_ptr;        // slot -> CSR offsets of its upstream edges (n + 1)
+  const int32_t* up_src;        // per edge, ordered by ascending upstream NODE ID (the
+                                // reference's left-fold order, utils.jl:472-477): index of the
+                                // source inside the chunk (< WFB_CHUNK_NODES), or
+                                // WFB_CHUNK_NODES + k for the chunk's k-th inlet edge
   const int32_t* chunk_inl_ptr; // n_chunks + 1 offsets into the inlet lists
-  const int32_t* inl_level;     // level of the receiving node of an inlet edge
+  const int32_t* inl_level;     // local level of the receiving node of an inlet edge
   const int32_t* inl_src;       // producer chunk of an inlet edge
-  const int32_t* outlet_chunk;  // slot -> chunk id if the slot is a chunk outlet that feeds
-                                // another chunk, else -1
 };
 
 struct KCfg {

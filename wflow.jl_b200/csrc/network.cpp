@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <utility>
 
 namespace wfb {
 namespace {
@@ -327,16 +328,35 @@ bool build_artifacts(Network& nw, int nthreads, int min_sto, const int64_t* so_o
   return true;
 }
 
-void build_chunks(Network& nw, int64_t target) {
+void build_chunks(Network& nw, int64_t cap) {
   const int64_t n = nw.n;
-  if (target < 1) target = 1;
-  // bottom-up accumulation of the not-yet-cut upstream tree size
+  if (cap < 1) cap = 1;
+  // Bottom-up (upstream first): acc[v] = size of the not-yet-cut upstream tree of v. A chunk
+  // may hold at most `cap` nodes (one node per thread of the CTA that walks it), so when the
+  // tree rooted at v would exceed the cap its largest uncut children are cut off (each becomes
+  // a chunk of its own) until it fits. Every pit closes a chunk.
   std::vector<int64_t> acc(n, 1);
   std::vector<uint8_t> cut(n, 0);
+  std::vector<std::pair<int64_t, int64_t>> kids;
   for (int64_t k = 0; k < n; ++k) {
-    const int64_t v = nw.order[k] - 1, d = nw.down[v];
-    if (d == 0 || acc[v] >= target) cut[v] = 1;
-    else acc[d - 1] += acc[v];
+    const int64_t v = nw.order[k] - 1;
+    int64_t total = 1;
+    for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e) total += acc[nw.in_idx[e] - 1];
+    if (total > cap) {
+      kids.clear();
+      for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e)
+        kids.emplace_back(acc[nw.in_idx[e] - 1], nw.in_idx[e] - 1);
+      std::sort(kids.begin(), kids.end(), [](const auto& a, const auto& b) {
+        return a.first != b.first ? a.first > b.first : a.second < b.second;
+      });
+      for (const auto& kd : kids) {
+        if (total <= cap) break;
+        cut[kd.second] = 1;
+        total -= kd.first;
+      }
+    }
+    acc[v] = total;
+    if (nw.down[v] == 0) cut[v] = 1;
   }
   // chunk outlets in execution order: ascending outlet level, then node id. A producer's outlet
   // is exactly one level above its consumer's receiving node, so this is a topological order

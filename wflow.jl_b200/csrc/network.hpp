@@ -56,8 +56,9 @@ bool build_graph(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, co
 // order, stream order (unless `streamorder_override` given), upstream CSR, partition, wavefront.
 bool build_artifacts(Network& nw, int nthreads, int min_streamorder,
                      const int64_t* streamorder_override, std::string& err);
-// Partition into chunks of about `target` nodes (bottom-up: a node whose not-yet-cut upstream
-// tree reaches `target` nodes, and every pit, closes a chunk) and derive the device slot order.
-void build_chunks(Network& nw, int64_t target);
+// Partition into chunks of at most `cap` nodes (bottom-up: when the not-yet-cut upstream tree
+// of a node would exceed the cap its largest children are cut off; every pit closes a chunk)
+// and derive the device slot order.
+void build_chunks(Network& nw, int64_t cap);
 
 }  // namespace wfb
