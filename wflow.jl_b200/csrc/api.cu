@@ -299,13 +299,43 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
   w.dt = dt;
   w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
   w.smem = smem;
+  w.prof = nullptr;
+  const char* prof_env = getenv("WFB_WAVE_PROF");  // developer aid: dump per-chunk timing
+  const bool prof = prof_env && atoi(prof_env) == kind + 1;
+  const size_t prof_words = 8 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1);
+  if (prof) {
+    CUDA_TRY(h, cudaMalloc((void**)&w.prof, sizeof(long long) * prof_words));
+    CUDA_TRY(h, cudaMemset(w.prof, 0, sizeof(long long) * prof_words));
+  }
   int32_t rc = check_launch(h, launch(w), what);
   if (rc) return rc;
+  if (prof) {
+    std::vector<long long> hp(prof_words);
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(hp.data(), w.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(w.prof);
+    FILE* fp = fopen("gpurun_out/wave_prof.csv", "w");
+    if (fp) {
+      fprintf(fp, "chunk,start_ns,end_ns,stages,nodes,bar_cyc,smid,inlets,fetch_cyc,l0,l1\n");
+      long long t0 = hp[0];
+      for (int64_t c = 0; c < d.nw.n_chunks; ++c) t0 = std::min(t0, hp[8 * c]);
+      for (int64_t c = 0; c < d.nw.n_chunks; ++c)
+        fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", (long long)c,
+                hp[8 * c] - t0, hp[8 * c + 1] - t0, hp[8 * c + 2], hp[8 * c + 3], hp[8 * c + 4],
+                hp[8 * c + 5], hp[8 * c + 6], hp[8 * c + 7], (long long)d.nw.chunk_l0[c],
+                (long long)d.nw.chunk_l1[c]);
+      fclose(fp);
+    }
+  }
   substeps = S;
   return WFLOWB200_OK;
 }
 
 }  // namespace
+
+#ifdef WFB_NEWTON_HIST
+namespace wfb { void dump_newton_hist(); }
+#endif
 
 extern "C" {
 
@@ -716,6 +746,9 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
   if (!h || !out) return WFLOWB200_ERR_ARG;
   RoutingStats rs{};
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+#ifdef WFB_NEWTON_HIST
+  wfb::dump_newton_hist();
+#endif
   CUDA_TRY(h, cudaMemcpy(&rs, h->d_stats, sizeof(rs), cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
   out->newton_calls_land = (int64_t)rs.newton_calls_land;

@@ -30,6 +30,9 @@ struct WaveLaunch {
   double dt;                  // model time step (for the averages)
   int grid;
   size_t smem;                // dynamic shared memory of the kernel (wave_smem)
+  long long* prof;            // developer aid (WFB_WAVE_PROF): 8 x n_chunks int64 written by
+                              // each chunk: start ns, end ns, stages, nodes, barrier-wait cycles
+                              // of thread 0, SM id, inlets, busy cycles of the fetch warp
 };
 
 // kind: 0 overland, 1 river, 2 subsurface
