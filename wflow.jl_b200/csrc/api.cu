@@ -32,7 +32,7 @@ std::string g_create_error;
 struct DomainDev {
   Network nw;
   int32_t* node_of_slot = nullptr;  // device, 0-based node id per slot
-  std::vector<int32_t*> dev_arrays; // everything uploaded for DevNet (freed together)
+  std::vector<void*> dev_arrays;    // everything uploaded for DevNet (freed together)
   unsigned long long* q_out = nullptr;  // per chunk x S x NV published outlet values
   size_t q_out_words = 0;
   DevNet dev{};
@@ -169,60 +169,65 @@ cudaError_t upload_i32(const std::vector<T>& src, int32_t** dst, int64_t offset)
   return cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
 }
 
+template <class T>
+cudaError_t upload_raw(const std::vector<T>& src, const T** dst, std::vector<void*>& owned) {
+  T* ptr = nullptr;
+  cudaError_t e = cudaMalloc((void**)&ptr, std::max<size_t>(src.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  owned.push_back(ptr);
+  *dst = ptr;
+  return cudaMemcpy(ptr, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
 // Device copies of the wavefront artefacts of one domain.
 int32_t upload_domain(WflowB200* h, DomainDev& d) {
   const Network& nw = d.nw;
   const int64_t n = nw.n;
   CUDA_TRY(h, upload_i32(nw.perm, &d.node_of_slot, -1));
-  std::vector<int64_t> level_local(n), up_ptr(n + 1, 0), up_src, chunk_nlev(nw.n_chunks),
-      chunk_feeds(nw.n_chunks);
-  std::vector<int64_t> inl_ptr(nw.n_chunks + 1, 0), inl_level, inl_src;
-  up_src.reserve(nw.in_idx.size());
+  std::vector<int4> meta(nw.n_chunks);
+  std::vector<unsigned long long> node_edges(n, ~0ull);
+  std::vector<uint8_t> node_level(n), inl_level;
+  std::vector<int32_t> inl_src;
   int64_t max_inlets = 0;
   for (int64_t c = 0; c < nw.n_chunks; ++c) {
-    const int64_t p0 = nw.chunk_ptr[c];
-    if (nw.chunk_ptr[c + 1] - p0 > WFB_CHUNK_NODES)
+    const int64_t p0 = nw.chunk_ptr[c], nn = nw.chunk_ptr[c + 1] - p0;
+    const int64_t nlev = nw.chunk_l1[c] - nw.chunk_l0[c] + 1;
+    if (nn > WFB_CHUNK_NODES || nlev > WFB_CHUNK_NODES)
       return fail(h, WFLOWB200_ERR_STATE, "chunk exceeds WFB_CHUNK_NODES");
+    const int64_t i0 = (int64_t)inl_src.size();
     int64_t k = 0;  // inlet number inside the chunk
-    for (int64_t p = p0; p < nw.chunk_ptr[c + 1]; ++p) {
+    for (int64_t p = p0; p < p0 + nn; ++p) {
       const int64_t v = nw.perm[p] - 1;  // in-neighbours are already ascending by node id
-      level_local[p] = nw.node_level[v] - nw.chunk_l0[c];
-      for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e) {
-        const int64_t u = nw.in_idx[e] - 1;
+      node_level[p] = (uint8_t)(nw.node_level[v] - nw.chunk_l0[c]);
+      const int64_t deg = nw.in_ptr[v + 1] - nw.in_ptr[v];
+      if (deg > 8) return fail(h, WFLOWB200_ERR_GRAPH, "node with more than 8 upstream nodes");
+      unsigned long long code = ~0ull;
+      for (int64_t e = 0; e < deg; ++e) {
+        const int64_t u = nw.in_idx[nw.in_ptr[v] + e] - 1;
         const int64_t cu = nw.chunk_of_node[u];
+        unsigned long long b;
         if (cu != c) {
-          up_src.push_back(WFB_CHUNK_NODES + k++);
-          inl_level.push_back(level_local[p]);
-          inl_src.push_back(cu);
+          if (WFB_CHUNK_NODES + k >= (int64_t)WFB_NO_EDGE)
+            return fail(h, WFLOWB200_ERR_STATE, "too many inlet edges in one chunk");
+          b = (unsigned long long)(WFB_CHUNK_NODES + k++);
+          inl_level.push_back(node_level[p]);
+          inl_src.push_back((int32_t)cu);
         } else {
-          up_src.push_back(nw.slot_of[u] - p0);
+          b = (unsigned long long)(nw.slot_of[u] - p0);
         }
+        code = (code & ~(0xffull << (8 * e))) | (b << (8 * e));
       }
-      up_ptr[p + 1] = (int64_t)up_src.size();
+      node_edges[p] = code;
     }
-    inl_ptr[c + 1] = (int64_t)inl_src.size();
     max_inlets = std::max(max_inlets, k);
-    chunk_nlev[c] = nw.chunk_l1[c] - nw.chunk_l0[c] + 1;
-    chunk_feeds[c] = nw.down[nw.chunk_outlet[c] - 1] ? 1 : 0;
+    const int feeds = nw.down[nw.chunk_outlet[c] - 1] ? 1 : 0;
+    meta[c] = make_int4((int)p0, (int)(nn | (nlev << 8) | (feeds << 16)), (int)i0, (int)k);
   }
-  if (WFB_CHUNK_NODES + max_inlets > 65535)
-    return fail(h, WFLOWB200_ERR_STATE, "too many inlet edges in one chunk");
-  auto up = [&](const std::vector<int64_t>& src, const int32_t** dst) -> cudaError_t {
-    int32_t* ptr = nullptr;
-    cudaError_t e = upload_i32(src, &ptr, 0);
-    d.dev_arrays.push_back(ptr);
-    *dst = ptr;
-    return e;
-  };
-  CUDA_TRY(h, up(nw.chunk_ptr, &d.dev.chunk_ptr));
-  CUDA_TRY(h, up(chunk_nlev, &d.dev.chunk_nlev));
-  CUDA_TRY(h, up(chunk_feeds, &d.dev.chunk_feeds));
-  CUDA_TRY(h, up(level_local, &d.dev.level_local));
-  CUDA_TRY(h, up(up_ptr, &d.dev.up_ptr));
-  CUDA_TRY(h, up(up_src, &d.dev.up_src));
-  CUDA_TRY(h, up(inl_ptr, &d.dev.chunk_inl_ptr));
-  CUDA_TRY(h, up(inl_level, &d.dev.inl_level));
-  CUDA_TRY(h, up(inl_src, &d.dev.inl_src));
+  CUDA_TRY(h, upload_raw(meta, &d.dev.chunk_meta, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(node_edges, &d.dev.node_edges, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(node_level, &d.dev.node_level, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(inl_src, &d.dev.inl_src, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(inl_level, &d.dev.inl_level, d.dev_arrays));
   d.dev.n = (int32_t)n;
   d.dev.n_levels = (int32_t)nw.n_wave_levels;
   d.dev.n_chunks = (int32_t)nw.n_chunks;
@@ -232,7 +237,7 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
 
 void free_domain(DomainDev& d) {
   cudaFree(d.node_of_slot);
-  for (int32_t* p : d.dev_arrays) cudaFree(p);
+  for (void* p : d.dev_arrays) cudaFree(p);
   cudaFree(d.q_out);
 }
 
@@ -316,9 +321,10 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
     cudaFree(w.prof);
     FILE* fp = fopen("gpurun_out/wave_prof.csv", "w");
     if (fp) {
-      fprintf(fp, "chunk,start_ns,end_ns,stages,nodes,bar_cyc,smid,inlets,fetch_cyc,l0,l1\n");
+      fprintf(fp, "chunk,start_ns,end_ns,stages,nodes,wait_cyc,smid,inlets,loaded_ns,l0,l1\n");
       long long t0 = hp[0];
       for (int64_t c = 0; c < d.nw.n_chunks; ++c) t0 = std::min(t0, hp[8 * c]);
+      for (int64_t c = 0; c < d.nw.n_chunks; ++c) hp[8 * c + 7] -= t0;
       for (int64_t c = 0; c < d.nw.n_chunks; ++c)
         fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", (long long)c,
                 hp[8 * c] - t0, hp[8 * c + 1] - t0, hp[8 * c + 2], hp[8 * c + 3], hp[8 * c + 4],

@@ -24,25 +24,26 @@ struct DevFields {
 
 // One routing domain (land or river) as the wavefront kernels see it. Slots are ordered by
 // (chunk, level, node id); a chunk is a connected piece of the drainage forest with ONE outlet
-// node (its last slot) and at most WFB_CHUNK_NODES nodes: one CTA walks it, one thread per node.
-#define WFB_CHUNK_NODES 256
+// node (its last slot) and at most WFB_CHUNK_NODES = 32 nodes: one WARP walks it, one lane per
+// node.
+#define WFB_CHUNK_NODES 32
+#define WFB_NO_EDGE 0xffu
 struct DevNet {
   int32_t n;                    // nodes
   int32_t n_levels;             // wavefront levels of the whole domain
   int32_t n_chunks;
   int32_t max_inlets;           // largest number of inlet edges of any chunk
-  const int32_t* chunk_ptr;     // n_chunks + 1 slot offsets
-  const int32_t* chunk_nlev;    // number of levels a chunk spans
-  const int32_t* chunk_feeds;   // 1 if the chunk's outlet drains into another chunk
-  const int32_t* level_local;   // slot -> level inside its chunk (0 = the chunk's first level)
-  const int32_t* up_ptr;        // slot -> CSR offsets of its upstream edges (n + 1)
-  const int32_t* up_src;        // per edge, ordered by ascending upstream NODE ID (the
-                                // reference's left-fold order, utils.jl:472-477): index of the
-                                // source inside the chunk (< WFB_CHUNK_NODES), or
-                                // WFB_CHUNK_NODES + k for the chunk's k-th inlet edge
-  const int32_t* chunk_inl_ptr; // n_chunks + 1 offsets into the inlet lists
-  const int32_t* inl_level;     // local level of the receiving node of an inlet edge
-  const int32_t* inl_src;       // producer chunk of an inlet edge
+  const int4* chunk_meta;       // per chunk: x = first slot, y = nodes | levels << 8 | feeds << 16
+                                // (feeds: the outlet drains into another chunk), z = offset of
+                                // its inlet list, w = number of inlet edges
+  const unsigned long long* node_edges;  // per slot: up to 8 upstream sources, one byte each,
+                                // ordered by ascending upstream NODE ID (the reference's
+                                // left-fold order, utils.jl:472-477): lane of the source inside
+                                // the chunk (< 32), 32 + k for the chunk's k-th inlet edge, or
+                                // WFB_NO_EDGE
+  const uint8_t* node_level;    // per slot: level inside its chunk (0 = the chunk's first level)
+  const int32_t* inl_src;       // per inlet edge: producer chunk
+  const uint8_t* inl_level;     // per inlet edge: level (inside the chunk) of the receiving node
 };
 
 struct KCfg {
