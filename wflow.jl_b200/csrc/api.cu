@@ -128,6 +128,8 @@ struct WflowB200 {
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
   unsigned* d_queue = nullptr;
+  int32_t* d_heavy_list = nullptr;   // cells left to the second pass of the vertical kernel
+  unsigned* d_heavy_count = nullptr;
   RoutingStats* d_stats = nullptr;
   unsigned long long* d_count = nullptr;
   double* d_min = nullptr;
@@ -342,6 +344,9 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
 #ifdef WFB_NEWTON_HIST
 namespace wfb { void dump_newton_hist(); }
 #endif
+#ifdef WFB_UNSAT_HIST
+namespace wfb { void dump_unsat_hist(); }
+#endif
 
 extern "C" {
 
@@ -475,6 +480,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_forcing, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMallocHost((void**)&h->h_pinned, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_heavy_list, (size_t)h->n * sizeof(int32_t)));
+  TRY_CREATE(cudaMalloc((void**)&h->d_heavy_count, sizeof(unsigned)));
   TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
   TRY_CREATE(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
@@ -511,6 +518,7 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
+  cudaFree(h->d_heavy_list); cudaFree(h->d_heavy_count);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
   free_domain(h->land); free_domain(h->river);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
@@ -618,12 +626,16 @@ int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
   if (h->nriv > 0) {  // river h -> land grid (runoff.jl:77-79)
     if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
   }
-  return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->stream),
+  return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->d_heavy_list, h->d_heavy_count, h->stream),
                       "update_land_hydrology_model");
 }
 
 int32_t wflowb200_exchange_recharge(WflowB200* h) {
   if (!h) return WFLOWB200_ERR_ARG;
+#ifdef WFB_UNSAT_HIST
+  cudaStreamSynchronize(h->stream);
+  wfb::dump_unsat_hist();
+#endif
   return check_launch(h, launch_exchange_recharge(h->f, h->kc, h->stream), "exchange_recharge");
 }
 
@@ -690,7 +702,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
     if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
   }
   mark(1);
-  if ((rc = check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->stream),
+  if ((rc = check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->d_heavy_list, h->d_heavy_count, h->stream),
                          "update_land_hydrology_model"))) return rc;
   mark(2);
   if ((rc = wflowb200_exchange_recharge(h))) return rc;

@@ -7,8 +7,9 @@
 namespace wfb {
 
 int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s);
+// heavy_list: n int32 (device), heavy_count: one unsigned (device); see vertical.cu
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          cudaStream_t s);
+                          int32_t* heavy_list, unsigned* heavy_count, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_soil_water_storage(const DevFields& f, const KCfg& c, int n_layers, cudaStream_t s);
 int launch_total_water_storage(const DevFields& f, const KCfg& c, const int32_t* riv_of_land,

@@ -10,6 +10,7 @@
 // (template N) between sub-processes. Arithmetic order follows the reference expression by
 // expression (no FMA contraction: -fmad=false) so results match the Julia code to the last
 // bits that libm differences allow. All reference paths are under /root/reference/Wflow/src.
+#include <cstdio>
 #include "device_math.cuh"
 #include "kernels.cuh"
 #include "model.cuh"
@@ -28,23 +29,107 @@ __device__ __forceinline__ double kv_at_depth(int profile, double kvfac, double 
 }
 
 // unsatzone_flow_layer                                           soil/soil_process.jl:51-92
-__device__ __forceinline__ void unsatzone_flow_layer(double& usd, double& flow, double kv_z,
-                                                     double l_sat, double c, double dt) {
-  if (usd <= 0.0) { usd = 0.0; flow = 0.0; return; }
+// split in two: the part every cell executes once per layer (`setup`: the transfer of water
+// above saturation and the number `its` of explicit sub-iterations), and the sub-iteration
+// loop itself, whose trip count is data dependent (0 for a dry layer, > 100 for a wet one).
+#ifdef WFB_UNSAT_HIST
+__device__ unsigned long long g_unsat_hist[40];
+#endif
+struct UnsatTask {
+  double usd, sum_ast, kv_it, l_sat, c;
+  int its;
+};
+__device__ __forceinline__ UnsatTask unsatzone_flow_setup(double usd, double kv_z, double l_sat,
+                                                          double c, double dt) {
+  UnsatTask t;
+  t.l_sat = l_sat; t.c = c; t.kv_it = 0.0; t.its = 0;
+  if (usd <= 0.0) { t.usd = 0.0; t.sum_ast = 0.0; return t; }
   const double st_sat = jmax(0.0, usd - l_sat);
-  double st = kv_z * bounded_power(usd / l_sat, c);
-  double sum_ast = jmin(st, st_sat / dt);
+  const double st = kv_z * bounded_power(usd / l_sat, c);
+  const double sum_ast = jmin(st, st_sat / dt);
   usd -= sum_ast * dt;
   const double remainder = jmin((st - sum_ast) * dt, usd);
   const int its = (int)jcld(remainder, 2e-4);
-  const double kv_it = kv_z / (double)its;
-  for (int k = 0; k < its; ++k) {
-    st = kv_it * bounded_power(usd / l_sat, c);
+  t.usd = usd; t.sum_ast = sum_ast; t.its = its;
+  t.kv_it = kv_z / (double)its;
+#ifdef WFB_UNSAT_HIST
+  { int b = 0; while ((1 << b) <= its && b < 30) ++b; atomicAdd(&g_unsat_hist[b], 1ull); atomicAdd(&g_unsat_hist[32], (unsigned long long)its); }
+#endif
+  return t;
+}
+__device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt) {
+  double usd = t.usd, sum_ast = t.sum_ast;
+  for (int k = 0; k < t.its; ++k) {
+    const double st = t.kv_it * bounded_power(usd / t.l_sat, t.c);
     const double st_max = usd / dt;
     if (st < st_max) { usd -= st * dt; sum_ast += st; }
     else { usd = 0.0; sum_ast += st_max; break; }
   }
-  flow = sum_ast;
+  t.usd = usd; t.sum_ast = sum_ast;
+}
+
+// The sub-iteration loops of the 256 cells of a CTA, re-balanced: with one cell per lane a warp
+// runs as long as its wettest cell while most lanes idle (measured: 2.7 of 32 lanes active in
+// this loop, 80 % of the kernel's time). The CTA therefore counting-sorts its 256 tasks by
+// trip count in shared memory and lane r executes the task of rank r, so the lanes of a warp
+// run loops of nearly equal length; results travel back through shared memory. Every thread
+// of the CTA must call this (it synchronises), also those without a task (its = 0).
+constexpr int kVertBlock = 256;
+struct UnsatShared {
+  double usd[kVertBlock], sum_ast[kVertBlock], kv_it[kVertBlock], l_sat[kVertBlock], c[kVertBlock];
+  int its[kVertBlock];
+  int bin[kVertBlock];          // histogram / running offsets of the trip counts (clamped)
+  unsigned short owner[kVertBlock];
+  int warp_sum[kVertBlock / 32];
+  int cta_max;
+};
+__device__ __forceinline__ void unsatzone_flow_balanced(UnsatTask& t, double dt, UnsatShared& sh) {
+  const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // cheap uniform exit: nothing to balance when every loop is short
+  const int wmax = __reduce_max_sync(0xffffffffu, t.its);
+  if (tid == 0) sh.cta_max = 0;
+  __syncthreads();
+  if (lane == 0 && wmax > 0) atomicMax(&sh.cta_max, wmax);
+  sh.bin[tid] = 0;
+  __syncthreads();
+  if (sh.cta_max <= 2) {  // same decision in every thread
+    unsatzone_flow_iterate(t, dt);
+    return;
+  }
+  const int key = t.its < kVertBlock - 1 ? t.its : kVertBlock - 1;
+  atomicAdd(&sh.bin[key], 1);
+  sh.usd[tid] = t.usd; sh.sum_ast[tid] = t.sum_ast; sh.kv_it[tid] = t.kv_it;
+  sh.l_sat[tid] = t.l_sat; sh.c[tid] = t.c; sh.its[tid] = t.its;
+  __syncthreads();
+  // exclusive scan of the 256 bins (descending key order: longest loops first)
+  const int cnt = sh.bin[kVertBlock - 1 - tid];
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) sh.warp_sum[wid] = incl;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < kVertBlock / 32; ++w2)
+    if (w2 < wid) base += sh.warp_sum[w2];
+  __syncthreads();
+  sh.bin[kVertBlock - 1 - tid] = base + incl - cnt;
+  __syncthreads();
+  const int rank = atomicAdd(&sh.bin[key], 1);
+  sh.owner[rank] = (unsigned short)tid;
+  __syncthreads();
+  const int j = sh.owner[tid];
+  UnsatTask u;
+  u.usd = sh.usd[j]; u.sum_ast = sh.sum_ast[j]; u.kv_it = sh.kv_it[j]; u.l_sat = sh.l_sat[j];
+  u.c = sh.c[j]; u.its = sh.its[j];
+  unsatzone_flow_iterate(u, dt);
+  sh.usd[j] = u.usd; sh.sum_ast[j] = u.sum_ast;
+  __syncthreads();
+  t.usd = sh.usd[tid]; t.sum_ast = sh.sum_ast[tid];
+  __syncthreads();  // the arrays are reused by the next layer
 }
 
 // rwu_reduction_feddes                                         soil/soil_process.jl:183-200
@@ -62,12 +147,35 @@ __device__ __forceinline__ double rwu_reduction_feddes(double h, double h1, doub
 
 }  // namespace
 
-template <int N>
-__global__ void __launch_bounds__(256)
-land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.n) return;
+// Two passes of the same code. LIGHT (HEAVY = false): one thread per land slot; a cell whose
+// Brooks-Corey loop needs more than kLightIters sub-iterations in some layer is appended to
+// `heavy_list` and left untouched (its read-modify-write states are stored only after the
+// unsaturated-zone section; the pure outputs it has written by then are rewritten with the
+// same values later). HEAVY: one thread per entry of the list, loops re-balanced over the CTA
+// (unsatzone_flow_balanced). With per-cell independent forcing ~1 task in 40 runs 16-250
+// sub-iterations while 9 in 10 run one; a single pass leaves 2.7 of 32 lanes busy in the loop.
+constexpr int kLightIters = 3;
+template <int N, bool HEAVY>
+__global__ void __launch_bounds__(kVertBlock)
+land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t* heavy_list,
+                      unsigned* heavy_count) {
+  __shared__ UnsatShared sh;
+  const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  int i;
+  bool tail = false;
+  if (HEAVY) {
+    // the threads past the end of the list compute a copy of its last cell (they take part in
+    // the CTA-wide re-balancing) and store nothing
+    const int count = (int)*heavy_count;
+    if ((int)(blockIdx.x * blockDim.x) >= count) return;
+    tail = i_raw >= count;
+    i = heavy_list[tail ? count - 1 : i_raw];
+  } else {
+    if (i_raw >= c.n) return;
+    i = i_raw;
+  }
   const int ns = c.ns;
+  double st_canopy = 0.0, st_snoww = 0.0, st_gstore = 0.0, st_snow = 0.0, st_tsoil = 0.0;
 
   // ---- forcing ---------------------------------------------------------------------------
   const double P = __ldg(f.precipitation + i);
@@ -80,8 +188,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     const double lai = __ldg(f.leaf_area_index + i);
     cmax = __ldg(f.storage_specific_leaf + i) * lai + __ldg(f.storage_wood + i);
     gap = exp(-__ldg(f.light_extinction_coefficient + i) * lai);
-    f.maximum_canopy_storage[i] = cmax;
-    f.canopy_gap_fraction[i] = gap;
+    if (!tail) f.maximum_canopy_storage[i] = cmax;
+    if (!tail) f.canopy_gap_fraction[i] = gap;
   } else {
     cmax = __ldg(f.maximum_canopy_storage + i);
     gap = __ldg(f.canopy_gap_fraction + i);
@@ -96,7 +204,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
       const double ewet = canopyfraction * PET * kc;
       const double thr = 1e-4 * (1e-3 * (1.0 / dt));  // to_SI(1e-4, MM_PER_DT; dt)
       e_r = P > 0.0 ? jmin(0.25, ewet / jmax(thr, canopyfraction * P)) : 0.0;
-      f.evaporation_to_precipitation_ratio[i] = e_r;
+      if (!tail) f.evaporation_to_precipitation_ratio[i] = e_r;
     } else {
       e_r = __ldg(f.evaporation_to_precipitation_ratio + i);
     }
@@ -148,12 +256,12 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     if (canopy_potevap > max_evap) { interception = max_evap; cs = 0.0; }
     else { interception = canopy_potevap; cs -= interception * dt; }
     if (cs > cmax) { const double d = cs - cmax; cs = cmax; throughfall += d / dt; }
-    f.canopy_storage[i] = cs;
+    st_canopy = cs;
   }
-  f.canopy_potevap[i] = canopy_potevap;
-  f.throughfall[i] = throughfall;
-  f.interception_rate[i] = interception;
-  f.stemflow[i] = stemflow;
+  if (!tail) f.canopy_potevap[i] = canopy_potevap;
+  if (!tail) f.throughfall[i] = throughfall;
+  if (!tail) f.interception_rate[i] = interception;
+  if (!tail) f.stemflow[i] = stemflow;
 
   // ---- snow (snow.jl:123-177, snow_process.jl:26-116) and glacier (glacier_process.jl:27-62)
   double water_flux_surface;
@@ -194,13 +302,13 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     double snow_runoff;
     if (snoww > maxw) { snow_runoff = (snoww - maxw) / dt; snoww = maxw; }
     else snow_runoff = 0.0;
-    f.effective_precip[i] = eff;
-    f.snow_precip[i] = snow_precip;
-    f.liquid_precip[i] = liquid_precip;
-    f.snow_water[i] = snoww;
-    f.snow_water_equivalent[i] = snoww + snow;
-    f.snow_melt[i] = snow_melt;
-    f.snow_runoff[i] = snow_runoff;
+    if (!tail) f.effective_precip[i] = eff;
+    if (!tail) f.snow_precip[i] = snow_precip;
+    if (!tail) f.liquid_precip[i] = liquid_precip;
+    st_snoww = snoww;
+    if (!tail) f.snow_water_equivalent[i] = snoww + snow;
+    if (!tail) f.snow_melt[i] = snow_melt;
+    if (!tail) f.snow_runoff[i] = snow_runoff;
     double gmelt = 0.0;
     if (glac) {
       gfrac = __ldg(f.glacier_fraction + i);
@@ -214,40 +322,40 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
       const double pot = T > gttm ? __ldg(f.glacier_degree_day_factor + i) * (T - gttm) : 0.0;
       gmelt = snow < 1e-2 ? jmin(pot, gstore / dt) : 0.0;
       gstore -= gmelt * dt;
-      f.glacier_store[i] = gstore;
-      f.glacier_melt[i] = gmelt;
+      st_gstore = gstore;
+      if (!tail) f.glacier_melt[i] = gmelt;
     }
-    f.snow_storage[i] = snow;
+    st_snow = snow;
     water_flux_surface = snow_runoff + gmelt * gfrac;  // runoff.jl:48-58
   } else {
     water_flux_surface = throughfall + stemflow;       // runoff.jl:37-46
   }
-  f.runoff_water_flux_surface[i] = water_flux_surface;
+  if (!tail) f.runoff_water_flux_surface[i] = water_flux_surface;
 
   // ---- open-water runoff (runoff.jl:61-111) ------------------------------------------------
   const double rf = __ldg(f.river_fraction + i), wf = __ldg(f.water_fraction + i);
   const double h_land = __ldg(f.olf_h + i);
   const double h_river = __ldg(f.waterdepth_river + i);  // refreshed by scatter_river_depth_kernel
-  f.waterdepth_land[i] = h_land;
+  if (!tail) f.waterdepth_land[i] = h_land;
   const double runoff_river = jmin(1.0, rf) * water_flux_surface;
   const double runoff_land = jmin(1.0, wf) * water_flux_surface;
   const double aeow_river = rf * jmin(h_river / dt, PET);
   const double aeow_land = wf * jmin(h_land / dt, PET);
-  f.runoff_river[i] = runoff_river;
-  f.runoff_land[i] = runoff_land;
-  f.actual_open_water_evaporation_river[i] = aeow_river;
-  f.actual_open_water_evaporation_land[i] = aeow_land;
-  f.net_runoff_river[i] = runoff_river - aeow_river;
+  if (!tail) f.runoff_river[i] = runoff_river;
+  if (!tail) f.runoff_land[i] = runoff_land;
+  if (!tail) f.actual_open_water_evaporation_river[i] = aeow_river;
+  if (!tail) f.actual_open_water_evaporation_land[i] = aeow_land;
+  if (!tail) f.net_runoff_river[i] = runoff_river - aeow_river;
 
   // ---- soil boundary conditions (soil.jl:643-682) ------------------------------------------
   const double soil_fraction = jmax(gap - wf - rf - gfrac, 0.0);
   const double pot_transp = jmax(0.0, canopy_potevap - interception);
   const double pot_soilevap0 = soil_fraction * PET;
   const double wfs = jmax(water_flux_surface - runoff_river - runoff_land, 0.0);
-  f.soil_fraction[i] = soil_fraction;
-  f.potential_transpiration[i] = pot_transp;
-  f.potential_soilevaporation[i] = pot_soilevap0;
-  f.soil_water_flux_surface[i] = wfs;
+  if (!tail) f.soil_fraction[i] = soil_fraction;
+  if (!tail) f.potential_transpiration[i] = pot_transp;
+  if (!tail) f.potential_soilevaporation[i] = pot_soilevap0;
+  if (!tail) f.soil_water_flux_surface[i] = wfs;
 
   // ---- state -> diagnostics (soil.jl:1400-1436) --------------------------------------------
   const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
@@ -281,25 +389,25 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     else if (zi - cld[k] > 0.0) t = zi - cld[k];
     ult[k] = t;
     n_unsat -= (t != t) ? 1 : 0;
-    f.unsaturated_layer_thickness[k * ns + i] = t;
+    if (!tail) f.unsaturated_layer_thickness[k * ns + i] = t;
   }
-  f.water_table_depth[i] = zi;
-  f.n_unsatlayers[i] = n_unsat;
-  f.total_soil_water_storage[i] = satwd + ustore_depth;
+  if (!tail) f.water_table_depth[i] = zi;
+  if (!tail) f.n_unsatlayers[i] = n_unsat;
+  if (!tail) f.total_soil_water_storage[i] = satwd + ustore_depth;
 
   // ---- soil temperature, infiltration (soil.jl:685-755, soil_process.jl:16-41,229-244) -------
   double f_red = 1.0;
   if (c.snow) {
     double tsoil = f.soil_surface_temperature[i];
     tsoil = tsoil + __ldg(f.w_soil + i) * (T - tsoil);
-    f.soil_surface_temperature[i] = tsoil;
+    st_tsoil = tsoil;
     if (c.soil_infiltration_reduction) {
       const double cf = __ldg(f.cf_soil + i);
       const double bb = 1.0 / (1.0 - cf);
       f_red = scurve(tsoil, 0.0 + 273.15, bb, 8.0) + cf;
     }
   }
-  f.f_infiltration_reduction[i] = f_red;
+  if (!tail) f.f_infiltration_reduction[i] = f_red;
   const double pathfrac = __ldg(f.compacted_soil_area_fraction + i);
   const double cap_soil = __ldg(f.infiltration_capacity_soil + i);
   const double cap_path = __ldg(f.infiltration_capacity_compacted_soil + i);
@@ -309,8 +417,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
   const double max_infiltpath = jmin(cap_path * f_red, pathinf);
   const double infiltration = jmin(max_infiltpath + max_infiltsoil, jmax(0.0, ustore_cap / dt));
   const double infiltration_excess = (soilinf - max_infiltsoil) + (pathinf - max_infiltpath);
-  f.infiltration[i] = infiltration;
-  f.infiltration_excess[i] = infiltration_excess;
+  if (!tail) f.infiltration[i] = infiltration;
+  if (!tail) f.infiltration_excess[i] = infiltration_excess;
 
   // ---- unsaturated zone flow, Brooks-Corey (soil.jl:764-804) -------------------------------
   const double kv_0 = __ldg(f.kv_0 + i);
@@ -325,20 +433,49 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
   double transfer = 0.0;
   {
     double z = 0.0, flow = 0.0;
+    bool heavy = false;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      if (k < n_unsat) {
+      UnsatTask t;
+      t.usd = 0.0; t.sum_ast = 0.0; t.kv_it = 0.0; t.l_sat = 1.0; t.c = 1.0; t.its = 0;
+      const bool in_layer = k < n_unsat && !heavy;
+      if (in_layer) {
         z = (k == 0) ? ult[0] : z + ult[k];
         const double l_sat = ult[k] * theta_e;
         const double kv_z = kv_at_depth(c.kv_profile, kvfac[k], kv_0, fpar, z_exp, z);
-        double usd = (k == 0) ? uld[k] + infiltration * dt : uld[k] + flow * dt;
-        unsatzone_flow_layer(usd, flow, kv_z, l_sat, bc[k], dt);
-        uld[k] = usd;
+        const double usd = (k == 0) ? uld[k] + infiltration * dt : uld[k] + flow * dt;
+        t = unsatzone_flow_setup(usd, kv_z, l_sat, bc[k], dt);
+        if (tail) t.its = 0;
       }
+      if (HEAVY) {
+        unsatzone_flow_balanced(t, dt, sh);
+      } else if (t.its > kLightIters) {
+        heavy = true;
+      } else {
+        unsatzone_flow_iterate(t, dt);
+      }
+      if (in_layer) {
+        uld[k] = t.usd;
+        flow = t.sum_ast;
+      }
+    }
+    if (!HEAVY && heavy) {  // left to the second pass
+      heavy_list[atomicAdd(heavy_count, 1u)] = i;
+      return;
     }
     if (n_unsat > 0) transfer = flow;
   }
-  f.transfer[i] = transfer;
+  // the read-modify-write states of the sections above
+  if (!tail) {
+    if (!c.gash) f.canopy_storage[i] = st_canopy;
+    if (c.snow) {
+      f.snow_water[i] = st_snoww;
+      f.snow_storage[i] = st_snow;
+      f.soil_surface_temperature[i] = st_tsoil;
+      if (c.glacier) f.glacier_store[i] = st_gstore;
+    }
+  }
+  if (!tail) f.transfer[i] = transfer;
 
   // ---- soil evaporation (soil.jl:814-856, soil_process.jl:247-294) --------------------------
   double soilevap_sat, soil_evaporation;
@@ -360,8 +497,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     soil_evaporation = evu + soilevap_sat;
     drainable -= soilevap_sat * dt;
   }
-  f.soil_evaporation_saturated_zone[i] = soilevap_sat;
-  f.soil_evaporation[i] = soil_evaporation;
+  if (!tail) f.soil_evaporation_saturated_zone[i] = soilevap_sat;
+  if (!tail) f.soil_evaporation[i] = soil_evaporation;
 
   // ---- transpiration (soil.jl:865-975) -----------------------------------------------------
   const double rd = __ldg(f.rooting_depth + i);
@@ -376,7 +513,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     else if (tpot_daily < 5.0) h3 = h3_low + (h3_high - h3_low) * (tpot_daily - 1.0) / (5.0 - 1.0);
     else h3 = h3_high;
   }
-  f.h3[i] = h3;
+  if (!tail) f.h3[i] = h3;
   double rootf[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) rootf[k] = __ldg(f.rootfraction + k * ns + i);
@@ -419,9 +556,9 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
   const double ae_sat = jmin(restpottrans * wetroots * alpha_sat, drainable / dt);
   drainable -= ae_sat * dt;
   const double transpiration = actevapustore + ae_sat;
-  f.actual_evaporation_unsaturated_store[i] = actevapustore;
-  f.actual_evaporation_saturated_zone[i] = ae_sat;
-  f.transpiration[i] = transpiration;
+  if (!tail) f.actual_evaporation_unsaturated_store[i] = actevapustore;
+  if (!tail) f.actual_evaporation_saturated_zone[i] = ae_sat;
+  if (!tail) f.transpiration[i] = transpiration;
 
   // ---- actual infiltration and excess water (soil.jl:987-1043, 1178-1192) -------------------
   double excess = 0.0;
@@ -434,8 +571,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
     }
   }
   const double actual_infiltration = infiltration - excess / dt;
-  f.actual_infiltration[i] = actual_infiltration;
-  f.saturation_excess_water[i] = (wfs - actual_infiltration) - infiltration_excess;
+  if (!tail) f.actual_infiltration[i] = actual_infiltration;
+  if (!tail) f.saturation_excess_water[i] = (wfs - actual_infiltration) - infiltration_excess;
   double actinf_soil, actinf_path;
   if (actual_infiltration > 0.0) {  // soil_process.jl:297-323
     actinf_soil = actual_infiltration * max_infiltsoil / (max_infiltpath + max_infiltsoil);
@@ -443,10 +580,10 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
   } else {
     actinf_soil = 0.0; actinf_path = 0.0;
   }
-  f.actual_infiltration_soil[i] = actinf_soil;
-  f.actual_infiltration_compacted_soil[i] = actinf_path;
-  f.excess_water_soil[i] = jmax(wfs * (1.0 - pathfrac) - actinf_soil, 0.0);
-  f.excess_water_compacted_soil[i] = jmax(wfs * pathfrac - actinf_path, 0.0);
+  if (!tail) f.actual_infiltration_soil[i] = actinf_soil;
+  if (!tail) f.actual_infiltration_compacted_soil[i] = actinf_path;
+  if (!tail) f.excess_water_soil[i] = jmax(wfs * (1.0 - pathfrac) - actinf_soil, 0.0);
+  if (!tail) f.excess_water_compacted_soil[i] = jmax(wfs * pathfrac - actinf_path, 0.0);
 
   // ---- recompute stores, capillary flux, leakage, recharge (soil.jl:1194-1209) --------------
   ustore_depth = 0.0;
@@ -454,8 +591,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
   for (int k = 0; k < N; ++k)
     if (k < nlayers) ustore_depth += uld[k];
   ustore_cap = swc - satwd - ustore_depth;
-  f.unsaturated_store_depth[i] = ustore_depth;
-  f.unsaturated_store_capacity[i] = ustore_cap;
+  if (!tail) f.unsaturated_store_depth[i] = ustore_depth;
+  if (!tail) f.unsaturated_store_capacity[i] = ustore_cap;
   double act_capflux = 0.0;
   if (n_unsat > 0) {  // capillary_flux! soil.jl:1050-1111
     double kvfac_nu = kvfac[0];
@@ -483,7 +620,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
       }
     }
   }
-  f.actual_capillary_flux[i] = act_capflux;
+  if (!tail) f.actual_capillary_flux[i] = act_capflux;
   double kvfac_nl = kvfac[0];
 #pragma unroll
   for (int k = 1; k < N; ++k)
@@ -491,15 +628,16 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt) {
   const double deepksat = kv_at_depth(c.kv_profile, kvfac_nl, kv_0, fpar, z_exp, d_soil);
   const double deeptransfer = jmin(drainable / dt, deepksat);
   const double leakage = jmax(0.0, jmin(__ldg(f.maximum_leakage + i), deeptransfer));
-  f.actual_leakage[i] = leakage;
-  f.recharge[i] = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
+  if (!tail) f.actual_leakage[i] = leakage;
+  if (!tail) f.recharge[i] = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
   // total AET (soil.jl:1206-1209) + interception (sbm.jl:130)
   double aet = soil_evaporation + transpiration + aeow_river + aeow_land + 0.0;
   aet += interception;
-  f.actual_evapotranspiration[i] = aet;
-  f.drainable_water_depth[i] = drainable;
+  if (!tail) f.actual_evapotranspiration[i] = aet;
+  if (!tail) f.drainable_water_depth[i] = drainable;
 #pragma unroll
-  for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = uld[k];
+  for (int k = 0; k < N; ++k)
+    if (!tail) f.unsaturated_layer_depth[k * ns + i] = uld[k];
 }
 
 // update_bc_open_water_runoff_model!: river h -> land grid                 runoff.jl:77-79
@@ -613,11 +751,27 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
   return 1;
 }
 
+#ifdef WFB_UNSAT_HIST
+void dump_unsat_hist() {
+  unsigned long long h[40];
+  cudaMemcpyFromSymbol(h, g_unsat_hist, sizeof(h));
+  unsigned long long z[40] = {0};
+  cudaMemcpyToSymbol(g_unsat_hist, z, sizeof(z));
+  fprintf(stderr, "unsat sub-iteration histogram (sum its %llu):", h[32]);
+  for (int b = 0; b < 31; ++b) if (h[b]) fprintf(stderr, " [<%d]=%llu", 1 << b, h[b]);
+  fprintf(stderr, "\n");
+}
+#endif
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          cudaStream_t s) {
-  const int grid = (c.n + 255) / 256;
-  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<grid, 256, 0, s>>>(f, c, dt)));
-  return 1;
+                          int32_t* heavy_list, unsigned* heavy_count, cudaStream_t s) {
+  const int grid = (c.n + kVertBlock - 1) / kVertBlock;
+  cudaMemsetAsync(heavy_count, 0, sizeof(unsigned), s);
+  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N, false><<<grid, kVertBlock, 0, s>>>(
+                               f, c, dt, heavy_list, heavy_count)));
+  // second pass over the listed cells; CTAs beyond the end of the list exit at once
+  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N, true><<<grid, kVertBlock, 0, s>>>(
+                               f, c, dt, heavy_list, heavy_count)));
+  return 2;
 }
 
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s) {
