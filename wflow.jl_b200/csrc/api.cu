@@ -128,8 +128,9 @@ struct WflowB200 {
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
   unsigned* d_queue = nullptr;
-  int32_t* d_heavy_list = nullptr;   // cells left to the second pass of the vertical kernel
-  unsigned* d_heavy_count = nullptr;
+  UnsatWork unsat{};                 // scratch of the unsaturated-zone engine (vertical.cu)
+  double* d_unsat_pool = nullptr;
+  int engine_grid = 0;
   RoutingStats* d_stats = nullptr;
   unsigned long long* d_count = nullptr;
   double* d_min = nullptr;
@@ -480,8 +481,22 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_forcing, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMallocHost((void**)&h->h_pinned, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
-  TRY_CREATE(cudaMalloc((void**)&h->d_heavy_list, (size_t)h->n * sizeof(int32_t)));
-  TRY_CREATE(cudaMalloc((void**)&h->d_heavy_count, sizeof(unsigned)));
+  {
+    const size_t ns = (size_t)h->ns;
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_pool, 5 * ns * sizeof(double)));
+    UnsatWork& u = h->unsat;
+    u.usd = h->d_unsat_pool; u.sum_ast = u.usd + ns; u.kv_it = u.sum_ast + ns;
+    u.l_sat = u.kv_it + ns; u.c = u.l_sat + ns;
+    TRY_CREATE(cudaMalloc((void**)&u.its_layer, ns * sizeof(int32_t)));
+    TRY_CREATE(cudaMalloc((void**)&u.list, 2 * WFB_UNSAT_BUCKETS * ns * sizeof(int32_t)));
+    TRY_CREATE(cudaMalloc((void**)&u.count, 2 * WFB_UNSAT_BUCKETS * sizeof(unsigned)));
+    u.cap = h->ns;
+    const char* ii = getenv("WFB_INLINE_ITERS");  // tunable for experiments
+    u.inline_iters = ii ? atoi(ii) : 8;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    h->engine_grid = std::max(1, sms) * 8;
+  }
   TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
   TRY_CREATE(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
@@ -518,7 +533,8 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
-  cudaFree(h->d_heavy_list); cudaFree(h->d_heavy_count);
+  cudaFree(h->d_unsat_pool); cudaFree(h->unsat.its_layer); cudaFree(h->unsat.list);
+  cudaFree(h->unsat.count);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
   free_domain(h->land); free_domain(h->river);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
@@ -626,7 +642,7 @@ int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
   if (h->nriv > 0) {  // river h -> land grid (runoff.jl:77-79)
     if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
   }
-  return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->d_heavy_list, h->d_heavy_count, h->stream),
+  return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->engine_grid, h->stream),
                       "update_land_hydrology_model");
 }
 
@@ -702,7 +718,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
     if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
   }
   mark(1);
-  if ((rc = check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->d_heavy_list, h->d_heavy_count, h->stream),
+  if ((rc = check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->engine_grid, h->stream),
                          "update_land_hydrology_model"))) return rc;
   mark(2);
   if ((rc = wflowb200_exchange_recharge(h))) return rc;

@@ -7,9 +7,21 @@
 namespace wfb {
 
 int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s);
-// heavy_list: n int32 (device), heavy_count: one unsigned (device); see vertical.cu
+// Device scratch of the unsaturated-zone engine (vertical.cu): the operands of the suspended
+// Brooks-Corey loops (one record per cell) and the lists of suspended cells, bucketed by
+// log2(trip count), double-buffered over the engine's rounds.
+#define WFB_UNSAT_BUCKETS 6
+struct UnsatWork {
+  double *usd, *sum_ast, *kv_it, *l_sat, *c;  // ns doubles each
+  int32_t* its_layer;                         // ns: trip count | layer << 24
+  int32_t* list;                              // [2][WFB_UNSAT_BUCKETS][cap] cell slots
+  unsigned* count;                            // [2][WFB_UNSAT_BUCKETS]
+  int32_t cap;                                // capacity of one list (= ns)
+  int32_t inline_iters;                       // loops up to this many trips run in line
+};
+// engine_grid: CTAs of the persistent engine kernels (a few per SM)
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          int32_t* heavy_list, unsigned* heavy_count, cudaStream_t s);
+                          const UnsatWork& w, int engine_grid, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_soil_water_storage(const DevFields& f, const KCfg& c, int n_layers, cudaStream_t s);
 int launch_total_water_storage(const DevFields& f, const KCfg& c, const int32_t* riv_of_land,

@@ -1,15 +1,36 @@
 // vertical.cu -- the SBM vertical land-surface update as fused sm_100a elementwise kernels.
 //
-// One thread per land slot; every input array is read once and every reference-visible output
-// array is written once (the ~30 sweeps of the reference collapse into three kernels):
-//   land_hydrology_kernel    update_land_hydrology_model!     sbm.jl:82-132
-//   soil_water_storage_kernel update_soil_water_storage!      soil/soil.jl:1294-1392
-//   total_water_storage_kernel update_total_water_storage!    sbm.jl:143-182
+// One thread per land slot; the ~30 sweeps of the reference collapse into
+//   land_surface_kernel       update_land_hydrology_model!, first half     sbm.jl:82-132
+//                             (interception, snow, glacier, open water, soil boundary
+//                             conditions, diagnostics, infiltration, unsaturated-zone flow)
+//   unsat_loop_kernel /       the long Brooks-Corey sub-iteration loops of unsatzone_flow_layer
+//   unsat_resume_kernel       (soil_process.jl:51-92), see "the unsaturated-zone engine" below
+//   soil_column_kernel        update_land_hydrology_model!, second half (soil evaporation,
+//                             transpiration, actual infiltration, capillary flux, leakage,
+//                             recharge, AET)                           soil/soil.jl:814-1209
+//   soil_water_storage_kernel update_soil_water_storage!               soil/soil.jl:1294-1392
+//   total_water_storage_kernel update_total_water_storage!             sbm.jl:143-182
 // HBM-bound: consecutive threads touch consecutive doubles of every SoA array, so each warp
 // load/store is a fully used 256-byte transaction; the layered state lives in registers
 // (template N) between sub-processes. Arithmetic order follows the reference expression by
 // expression (no FMA contraction: -fmad=false) so results match the Julia code to the last
 // bits that libm differences allow. All reference paths are under /root/reference/Wflow/src.
+//
+// The unsaturated-zone engine. unsatzone_flow_layer runs `its = cld(remainder, 2e-4 m)` explicit
+// sub-iterations, each a dependent div -> log -> exp chain. After a few wet days the trip count
+// is 1 for 80 % of the (cell, layer) calls and 64-250 for 1.5 % of them -- and those 1.5 % hold
+// 40 % of all iterations. With one cell per lane a warp runs as long as its wettest cell, and a
+// CTA as long as its wettest warp. The engine therefore takes the long loops OUT of the
+// per-cell kernels: land_surface_kernel runs loops of up to `inline_iters` trips in line and
+// SUSPENDS a cell at the first longer one (the loop's operands go to a per-cell scratch record,
+// the cell id to a list bucketed by log2(its)); unsat_loop_kernel runs all suspended loops of
+// the whole domain at once, one lane per loop, 32 loops of the same bucket per warp, longest
+// buckets first, so the lanes of a warp finish together and every long loop of the domain is in
+// flight at the same time (the sweep lasts as long as ONE longest loop, not one per CTA wave);
+// unsat_resume_kernel continues the suspended cells with their next layer (and may suspend
+// them again: at most N rounds). soil_column_kernel then finishes every cell from arrays that
+// are reference-visible outputs anyway (nothing is recomputed, no second pass over inputs).
 #include <cstdio>
 #include "device_math.cuh"
 #include "kernels.cuh"
@@ -32,149 +53,138 @@ __device__ __forceinline__ double kv_at_depth(int profile, double kvfac, double 
 // split in two: the part every cell executes once per layer (`setup`: the transfer of water
 // above saturation and the number `its` of explicit sub-iterations), and the sub-iteration
 // loop itself, whose trip count is data dependent (0 for a dry layer, > 100 for a wet one).
-#ifdef WFB_UNSAT_HIST
-__device__ unsigned long long g_unsat_hist[40];
-#endif
 struct UnsatTask {
   double usd, sum_ast, kv_it, l_sat, c;
   int its;
 };
 __device__ __forceinline__ UnsatTask unsatzone_flow_setup(double usd, double kv_z, double l_sat,
-                                                          double c, double dt) {
+                                                          double c, double dt, const Divisor& ddt) {
   UnsatTask t;
   t.l_sat = l_sat; t.c = c; t.kv_it = 0.0; t.its = 0;
   if (usd <= 0.0) { t.usd = 0.0; t.sum_ast = 0.0; return t; }
   const double st_sat = jmax(0.0, usd - l_sat);
-  const double st = kv_z * bounded_power(usd / l_sat, c);
-  const double sum_ast = jmin(st, st_sat / dt);
+  const double st = kv_z * bounded_power(fdiv(usd, l_sat), c);
+  const double sum_ast = jmin(st, st_sat / ddt);
   usd -= sum_ast * dt;
   const double remainder = jmin((st - sum_ast) * dt, usd);
-  const int its = (int)jcld(remainder, 2e-4);
+  const int its = (int)jcld_pos(remainder, 2e-4);
   t.usd = usd; t.sum_ast = sum_ast; t.its = its;
-  t.kv_it = kv_z / (double)its;
-#ifdef WFB_UNSAT_HIST
-  { int b = 0; while ((1 << b) <= its && b < 30) ++b; atomicAdd(&g_unsat_hist[b], 1ull); atomicAdd(&g_unsat_hist[32], (unsigned long long)its); }
-#endif
+  t.kv_it = its > 0 ? fdiv(kv_z, (double)its) : 0.0;
   return t;
 }
-__device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt) {
+__device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt, const Divisor& ddt) {
   double usd = t.usd, sum_ast = t.sum_ast;
+  const Divisor dl(t.l_sat);
   for (int k = 0; k < t.its; ++k) {
-    const double st = t.kv_it * bounded_power(usd / t.l_sat, t.c);
-    const double st_max = usd / dt;
+    const double st = t.kv_it * bounded_power(usd / dl, t.c);
+    const double st_max = usd / ddt;
     if (st < st_max) { usd -= st * dt; sum_ast += st; }
     else { usd = 0.0; sum_ast += st_max; break; }
   }
   t.usd = usd; t.sum_ast = sum_ast;
 }
 
-// The sub-iteration loops of the 256 cells of a CTA, re-balanced: with one cell per lane a warp
-// runs as long as its wettest cell while most lanes idle (measured: 2.7 of 32 lanes active in
-// this loop, 80 % of the kernel's time). The CTA therefore counting-sorts its 256 tasks by
-// trip count in shared memory and lane r executes the task of rank r, so the lanes of a warp
-// run loops of nearly equal length; results travel back through shared memory. Every thread
-// of the CTA must call this (it synchronises), also those without a task (its = 0).
-constexpr int kVertBlock = 256;
-struct UnsatShared {
-  double usd[kVertBlock], sum_ast[kVertBlock], kv_it[kVertBlock], l_sat[kVertBlock], c[kVertBlock];
-  int its[kVertBlock];
-  int bin[kVertBlock];          // histogram / running offsets of the trip counts (clamped)
-  unsigned short owner[kVertBlock];
-  int warp_sum[kVertBlock / 32];
-  int cta_max;
-};
-__device__ __forceinline__ void unsatzone_flow_balanced(UnsatTask& t, double dt, UnsatShared& sh) {
-  const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // cheap uniform exit: nothing to balance when every loop is short
-  const int wmax = __reduce_max_sync(0xffffffffu, t.its);
-  if (tid == 0) sh.cta_max = 0;
-  __syncthreads();
-  if (lane == 0 && wmax > 0) atomicMax(&sh.cta_max, wmax);
-  sh.bin[tid] = 0;
-  __syncthreads();
-  if (sh.cta_max <= 2) {  // same decision in every thread
-    unsatzone_flow_iterate(t, dt);
-    return;
+// ---- the unsaturated-zone engine: suspended loops ------------------------------------------
+constexpr int kBuckets = WFB_UNSAT_BUCKETS;
+__device__ __forceinline__ int bucket_of(int its) {  // (8,16] -> 0 ... by log2, clamped
+  const int b = 28 - __clz(its - 1);                 // its in (2^(b+3), 2^(b+4)]
+  return b < 0 ? 0 : (b >= kBuckets ? kBuckets - 1 : b);
+}
+// record the loop of cell i (layer k) and append the cell to the list of its bucket
+// (warp-aggregated: one atomic per warp and bucket)
+__device__ __forceinline__ void suspend_cell(const UnsatWork& w, int parity, int i, int k,
+                                             const UnsatTask& t, bool suspend) {
+  const unsigned active = __ballot_sync(0xffffffffu, suspend);
+  if (!suspend) return;
+  w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast; w.kv_it[i] = t.kv_it; w.l_sat[i] = t.l_sat;
+  w.c[i] = t.c;
+  w.its_layer[i] = t.its | (k << 24);
+  const int b = bucket_of(t.its);
+  const unsigned peers = __match_any_sync(active, b);
+  const int lane = (int)threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(w.count + parity * kBuckets + b, (unsigned)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const unsigned pos = base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+  w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + pos] = i;
+}
+
+// warp tile j of the concatenated bucket lists, longest bucket first -> (bucket, first entry)
+__device__ __forceinline__ bool tile_of(const unsigned* cnt, int j, int& b, int& first, int& n) {
+  for (b = kBuckets - 1; b >= 0; --b) {
+    const int tiles = ((int)cnt[b] + 31) >> 5;
+    if (j < tiles) { first = j << 5; n = (int)cnt[b]; return true; }
+    j -= tiles;
   }
-  const int key = t.its < kVertBlock - 1 ? t.its : kVertBlock - 1;
-  atomicAdd(&sh.bin[key], 1);
-  sh.usd[tid] = t.usd; sh.sum_ast[tid] = t.sum_ast; sh.kv_it[tid] = t.kv_it;
-  sh.l_sat[tid] = t.l_sat; sh.c[tid] = t.c; sh.its[tid] = t.its;
-  __syncthreads();
-  // exclusive scan of the 256 bins (descending key order: longest loops first)
-  const int cnt = sh.bin[kVertBlock - 1 - tid];
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) sh.warp_sum[wid] = incl;
-  __syncthreads();
-  int base = 0;
-#pragma unroll
-  for (int w2 = 0; w2 < kVertBlock / 32; ++w2)
-    if (w2 < wid) base += sh.warp_sum[w2];
-  __syncthreads();
-  sh.bin[kVertBlock - 1 - tid] = base + incl - cnt;
-  __syncthreads();
-  const int rank = atomicAdd(&sh.bin[key], 1);
-  sh.owner[rank] = (unsigned short)tid;
-  __syncthreads();
-  const int j = sh.owner[tid];
-  UnsatTask u;
-  u.usd = sh.usd[j]; u.sum_ast = sh.sum_ast[j]; u.kv_it = sh.kv_it[j]; u.l_sat = sh.l_sat[j];
-  u.c = sh.c[j]; u.its = sh.its[j];
-  unsatzone_flow_iterate(u, dt);
-  sh.usd[j] = u.usd; sh.sum_ast[j] = u.sum_ast;
-  __syncthreads();
-  t.usd = sh.usd[tid]; t.sum_ast = sh.sum_ast[tid];
-  __syncthreads();  // the arrays are reused by the next layer
+  return false;
 }
 
 // rwu_reduction_feddes                                         soil/soil_process.jl:183-200
 __device__ __forceinline__ double rwu_reduction_feddes(double h, double h1, double h2, double h3,
                                                        double h4, double alpha_h1) {
   if (h < h4) return 0.0;
-  if (h < h3) return (h - h4) / (h3 - h4);
+  if (h < h3) return fdiv(h - h4, h3 - h4);
   if (alpha_h1 == 0.0) {
     if (h < h2) return 1.0;
-    if (h < h1) return (h1 - h) / (h1 - h2);
+    if (h < h1) return fdiv(h1 - h, h1 - h2);
     return 0.0;
   }
   return 1.0;
 }
 
+// The unsaturated-zone layers k0.. of one cell (soil.jl:764-804): `flow` enters layer k0, z is
+// the depth of the bottom of layer k0 - 1. Returns true when the cell finished all its layers
+// (uld[] and transfer are then final); false when it was suspended at a long loop.
+template <int N>
+__device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, const UnsatWork& w,
+                                             int parity, int i, int k0, int n_unsat, double z,
+                                             double flow, double first_inflow,
+                                             double (&uld)[N], const double (&ult)[N],
+                                             const double (&bc)[N], const double (&kvfac)[N],
+                                             double kv_0, double fpar, double z_exp, double theta_e,
+                                             double dt, const Divisor& ddt, bool live,
+                                             double& transfer) {
+  bool suspended = false;
+  int k_susp = 0;
+  UnsatTask t_susp;
+  t_susp.usd = t_susp.sum_ast = t_susp.kv_it = 0.0; t_susp.l_sat = 1.0; t_susp.c = 1.0; t_susp.its = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (k >= k0 && k < n_unsat && !suspended) {
+      z = (k == 0) ? ult[0] : z + ult[k];
+      const double l_sat = ult[k] * theta_e;
+      const double kv_z = kv_at_depth(c.kv_profile, kvfac[k], kv_0, fpar, z_exp, z);
+      const double usd = (k == 0) ? uld[k] + first_inflow * dt : uld[k] + flow * dt;
+      UnsatTask t = unsatzone_flow_setup(usd, kv_z, l_sat, bc[k], dt, ddt);
+      if (!live) t.its = 0;
+      if (t.its > w.inline_iters) {
+        suspended = true; k_susp = k; t_susp = t;
+      } else {
+        unsatzone_flow_iterate(t, dt, ddt);
+        uld[k] = t.usd;
+        flow = t.sum_ast;
+      }
+    }
+  }
+  suspend_cell(w, parity, i, k_susp, t_susp, suspended);
+  transfer = n_unsat > 0 ? flow : 0.0;
+  return !suspended;
+}
+
 }  // namespace
 
-// Two passes of the same code. LIGHT (HEAVY = false): one thread per land slot; a cell whose
-// Brooks-Corey loop needs more than kLightIters sub-iterations in some layer is appended to
-// `heavy_list` and left untouched (its read-modify-write states are stored only after the
-// unsaturated-zone section; the pure outputs it has written by then are rewritten with the
-// same values later). HEAVY: one thread per entry of the list, loops re-balanced over the CTA
-// (unsatzone_flow_balanced). With per-cell independent forcing ~1 task in 40 runs 16-250
-// sub-iterations while 9 in 10 run one; a single pass leaves 2.7 of 32 lanes busy in the loop.
-constexpr int kLightIters = 3;
-template <int N, bool HEAVY>
-__global__ void __launch_bounds__(kVertBlock)
-land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t* heavy_list,
-                      unsigned* heavy_count) {
-  __shared__ UnsatShared sh;
-  const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
-  int i;
-  bool tail = false;
-  if (HEAVY) {
-    // the threads past the end of the list compute a copy of its last cell (they take part in
-    // the CTA-wide re-balancing) and store nothing
-    const int count = (int)*heavy_count;
-    if ((int)(blockIdx.x * blockDim.x) >= count) return;
-    tail = i_raw >= count;
-    i = heavy_list[tail ? count - 1 : i_raw];
-  } else {
-    if (i_raw >= c.n) return;
-    i = i_raw;
-  }
+// update_land_hydrology_model!, first half                                 sbm.jl:82-132
+template <int N>
+__global__ void __launch_bounds__(256)
+land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.ns) return;     // whole warps (ns is a multiple of 32)
+  // lanes of the padding slots [n, ns) run along on the padding values (they must take part in
+  // the warp-aggregated suspension) and never suspend; their stores land in the padding
+  const bool live = i < c.n;
   const int ns = c.ns;
+  const Divisor ddt(dt);
   double st_canopy = 0.0, st_snoww = 0.0, st_gstore = 0.0, st_snow = 0.0, st_tsoil = 0.0;
 
   // ---- forcing ---------------------------------------------------------------------------
@@ -188,8 +198,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     const double lai = __ldg(f.leaf_area_index + i);
     cmax = __ldg(f.storage_specific_leaf + i) * lai + __ldg(f.storage_wood + i);
     gap = exp(-__ldg(f.light_extinction_coefficient + i) * lai);
-    if (!tail) f.maximum_canopy_storage[i] = cmax;
-    if (!tail) f.canopy_gap_fraction[i] = gap;
+    f.maximum_canopy_storage[i] = cmax;
+    f.canopy_gap_fraction[i] = gap;
   } else {
     cmax = __ldg(f.maximum_canopy_storage + i);
     gap = __ldg(f.canopy_gap_fraction + i);
@@ -202,9 +212,9 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     if (c.has_lai) {
       const double canopyfraction = 1.0 - gap;
       const double ewet = canopyfraction * PET * kc;
-      const double thr = 1e-4 * (1e-3 * (1.0 / dt));  // to_SI(1e-4, MM_PER_DT; dt)
-      e_r = P > 0.0 ? jmin(0.25, ewet / jmax(thr, canopyfraction * P)) : 0.0;
-      if (!tail) f.evaporation_to_precipitation_ratio[i] = e_r;
+      const double thr = 1e-4 * (1e-3 * (1.0 / ddt));  // to_SI(1e-4, MM_PER_DT; dt)
+      e_r = P > 0.0 ? jmin(0.25, fdiv(ewet, jmax(thr, canopyfraction * P))) : 0.0;
+      f.evaporation_to_precipitation_ratio[i] = e_r;
     } else {
       e_r = __ldg(f.evaporation_to_precipitation_ratio + i);
     }
@@ -214,16 +224,16 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
         frac_stem = 0.1 * gap;
         frac_int = 1.0 - 1.1 * gap;
         // e_r == 0 gives -Inf * 0 = NaN here, and `P > NaN` is false: kept on purpose
-        p_sat = e_r > frac_int ? 0.0 : -cmax / (e_r * dt) * log(1.0 - e_r / frac_int);
+        p_sat = e_r > frac_int ? 0.0 : -cmax / (e_r * dt) * log(1.0 - fdiv(e_r, frac_int));
       } else {
         frac_stem = 1.0 - gap;
         frac_int = 0.0;
         p_sat = 0.0;
       }
       if (P > p_sat) {
-        const double iwet = frac_int * p_sat - cmax / dt;
+        const double iwet = frac_int * p_sat - cmax / ddt;
         const double isat = e_r * (P - p_sat);
-        const double idry = cmax / dt;
+        const double idry = cmax / ddt;
         interception = iwet + isat + idry;
       } else {
         interception = frac_int * P;
@@ -250,18 +260,18 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     }
     stemflow = frac_stem * P;
     throughfall = gap * P;
-    if (cs > cmax) { const double d = cs - cmax; cs = cmax; throughfall += d / dt; }
+    if (cs > cmax) { const double d = cs - cmax; cs = cmax; throughfall += d / ddt; }
     cs += p_canopy * dt;
-    const double max_evap = cs / dt;
+    const double max_evap = cs / ddt;
     if (canopy_potevap > max_evap) { interception = max_evap; cs = 0.0; }
     else { interception = canopy_potevap; cs -= interception * dt; }
-    if (cs > cmax) { const double d = cs - cmax; cs = cmax; throughfall += d / dt; }
+    if (cs > cmax) { const double d = cs - cmax; cs = cmax; throughfall += d / ddt; }
     st_canopy = cs;
   }
-  if (!tail) f.canopy_potevap[i] = canopy_potevap;
-  if (!tail) f.throughfall[i] = throughfall;
-  if (!tail) f.interception_rate[i] = interception;
-  if (!tail) f.stemflow[i] = stemflow;
+  f.canopy_potevap[i] = canopy_potevap;
+  f.throughfall[i] = throughfall;
+  f.interception_rate[i] = interception;
+  f.stemflow[i] = stemflow;
 
   // ---- snow (snow.jl:123-177, snow_process.jl:26-116) and glacier (glacier_process.jl:27-62)
   double water_flux_surface;
@@ -273,7 +283,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     const double tt = __ldg(f.temperature_threshold_snowfall + i);
     double rainfrac;
     if (tti == 0.0) rainfrac = T > tt ? 1.0 : 0.0;
-    else rainfrac = jclamp((T - (tt - tti / 2.0)) / tti, 0.0, 1.0);
+    else rainfrac = jclamp(fdiv(T - (tt - tti / 2.0), tti), 0.0, 1.0);
     const double snowfrac = 1.0 - rainfrac;
     const double snow_precip = snowfrac * 1.0 * eff;
     const double liquid_precip = rainfrac * 1.0 * eff;
@@ -284,7 +294,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     double snow_melt;
     if (T > ttm) {
       const double pot = cfmax * (T - ttm);
-      snow_melt = jmin(pot, snow / dt);
+      snow_melt = jmin(pot, snow / ddt);
       snow -= snow_melt * dt;
       snoww += snow_melt * dt;
     } else {
@@ -300,15 +310,15 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     snoww += liquid_precip * dt;
     const double maxw = snow * whc;
     double snow_runoff;
-    if (snoww > maxw) { snow_runoff = (snoww - maxw) / dt; snoww = maxw; }
+    if (snoww > maxw) { snow_runoff = (snoww - maxw) / ddt; snoww = maxw; }
     else snow_runoff = 0.0;
-    if (!tail) f.effective_precip[i] = eff;
-    if (!tail) f.snow_precip[i] = snow_precip;
-    if (!tail) f.liquid_precip[i] = liquid_precip;
+    f.effective_precip[i] = eff;
+    f.snow_precip[i] = snow_precip;
+    f.liquid_precip[i] = liquid_precip;
     st_snoww = snoww;
-    if (!tail) f.snow_water_equivalent[i] = snoww + snow;
-    if (!tail) f.snow_melt[i] = snow_melt;
-    if (!tail) f.snow_runoff[i] = snow_runoff;
+    f.snow_water_equivalent[i] = snoww + snow;
+    f.snow_melt[i] = snow_melt;
+    f.snow_runoff[i] = snow_runoff;
     double gmelt = 0.0;
     if (glac) {
       gfrac = __ldg(f.glacier_fraction + i);
@@ -320,42 +330,42 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
       gstore += s2g * dt;
       const double gttm = __ldg(f.glacier_temperature_threshold_melt + i);
       const double pot = T > gttm ? __ldg(f.glacier_degree_day_factor + i) * (T - gttm) : 0.0;
-      gmelt = snow < 1e-2 ? jmin(pot, gstore / dt) : 0.0;
+      gmelt = snow < 1e-2 ? jmin(pot, gstore / ddt) : 0.0;
       gstore -= gmelt * dt;
       st_gstore = gstore;
-      if (!tail) f.glacier_melt[i] = gmelt;
+      f.glacier_melt[i] = gmelt;
     }
     st_snow = snow;
     water_flux_surface = snow_runoff + gmelt * gfrac;  // runoff.jl:48-58
   } else {
     water_flux_surface = throughfall + stemflow;       // runoff.jl:37-46
   }
-  if (!tail) f.runoff_water_flux_surface[i] = water_flux_surface;
+  f.runoff_water_flux_surface[i] = water_flux_surface;
 
   // ---- open-water runoff (runoff.jl:61-111) ------------------------------------------------
   const double rf = __ldg(f.river_fraction + i), wf = __ldg(f.water_fraction + i);
   const double h_land = __ldg(f.olf_h + i);
   const double h_river = __ldg(f.waterdepth_river + i);  // refreshed by scatter_river_depth_kernel
-  if (!tail) f.waterdepth_land[i] = h_land;
+  f.waterdepth_land[i] = h_land;
   const double runoff_river = jmin(1.0, rf) * water_flux_surface;
   const double runoff_land = jmin(1.0, wf) * water_flux_surface;
-  const double aeow_river = rf * jmin(h_river / dt, PET);
-  const double aeow_land = wf * jmin(h_land / dt, PET);
-  if (!tail) f.runoff_river[i] = runoff_river;
-  if (!tail) f.runoff_land[i] = runoff_land;
-  if (!tail) f.actual_open_water_evaporation_river[i] = aeow_river;
-  if (!tail) f.actual_open_water_evaporation_land[i] = aeow_land;
-  if (!tail) f.net_runoff_river[i] = runoff_river - aeow_river;
+  const double aeow_river = rf * jmin(h_river / ddt, PET);
+  const double aeow_land = wf * jmin(h_land / ddt, PET);
+  f.runoff_river[i] = runoff_river;
+  f.runoff_land[i] = runoff_land;
+  f.actual_open_water_evaporation_river[i] = aeow_river;
+  f.actual_open_water_evaporation_land[i] = aeow_land;
+  f.net_runoff_river[i] = runoff_river - aeow_river;
 
   // ---- soil boundary conditions (soil.jl:643-682) ------------------------------------------
   const double soil_fraction = jmax(gap - wf - rf - gfrac, 0.0);
   const double pot_transp = jmax(0.0, canopy_potevap - interception);
   const double pot_soilevap0 = soil_fraction * PET;
   const double wfs = jmax(water_flux_surface - runoff_river - runoff_land, 0.0);
-  if (!tail) f.soil_fraction[i] = soil_fraction;
-  if (!tail) f.potential_transpiration[i] = pot_transp;
-  if (!tail) f.potential_soilevaporation[i] = pot_soilevap0;
-  if (!tail) f.soil_water_flux_surface[i] = wfs;
+  f.soil_fraction[i] = soil_fraction;
+  f.potential_transpiration[i] = pot_transp;
+  f.potential_soilevaporation[i] = pot_soilevap0;
+  f.soil_water_flux_surface[i] = wfs;
 
   // ---- state -> diagnostics (soil.jl:1400-1436) --------------------------------------------
   const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
@@ -377,7 +387,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
 #pragma unroll
   for (int k = 0; k < N; ++k)
     if (k < nlayers) ustore_depth += uld[k];
-  const double zi = jmax(0.0, d_soil - satwd / theta_e);
+  const double zi = jmax(0.0, d_soil - fdiv(satwd, theta_e));
   const double theta_d = jmax(theta_s - theta_fc, 0.02);  // lower_bound_drainable_porosity
   double drainable = (d_soil - zi) * theta_d;
   double ustore_cap = swc - satwd - ustore_depth;
@@ -389,11 +399,11 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     else if (zi - cld[k] > 0.0) t = zi - cld[k];
     ult[k] = t;
     n_unsat -= (t != t) ? 1 : 0;
-    if (!tail) f.unsaturated_layer_thickness[k * ns + i] = t;
+    f.unsaturated_layer_thickness[k * ns + i] = t;
   }
-  if (!tail) f.water_table_depth[i] = zi;
-  if (!tail) f.n_unsatlayers[i] = n_unsat;
-  if (!tail) f.total_soil_water_storage[i] = satwd + ustore_depth;
+  f.water_table_depth[i] = zi;
+  f.n_unsatlayers[i] = n_unsat;
+  f.total_soil_water_storage[i] = satwd + ustore_depth;
 
   // ---- soil temperature, infiltration (soil.jl:685-755, soil_process.jl:16-41,229-244) -------
   double f_red = 1.0;
@@ -403,11 +413,11 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     st_tsoil = tsoil;
     if (c.soil_infiltration_reduction) {
       const double cf = __ldg(f.cf_soil + i);
-      const double bb = 1.0 / (1.0 - cf);
+      const double bb = fdiv(1.0, 1.0 - cf);
       f_red = scurve(tsoil, 0.0 + 273.15, bb, 8.0) + cf;
     }
   }
-  if (!tail) f.f_infiltration_reduction[i] = f_red;
+  f.f_infiltration_reduction[i] = f_red;
   const double pathfrac = __ldg(f.compacted_soil_area_fraction + i);
   const double cap_soil = __ldg(f.infiltration_capacity_soil + i);
   const double cap_path = __ldg(f.infiltration_capacity_compacted_soil + i);
@@ -415,10 +425,10 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
   const double pathinf = wfs * pathfrac;
   const double max_infiltsoil = jmin(cap_soil * f_red, soilinf);
   const double max_infiltpath = jmin(cap_path * f_red, pathinf);
-  const double infiltration = jmin(max_infiltpath + max_infiltsoil, jmax(0.0, ustore_cap / dt));
+  const double infiltration = jmin(max_infiltpath + max_infiltsoil, jmax(0.0, ustore_cap / ddt));
   const double infiltration_excess = (soilinf - max_infiltsoil) + (pathinf - max_infiltpath);
-  if (!tail) f.infiltration[i] = infiltration;
-  if (!tail) f.infiltration_excess[i] = infiltration_excess;
+  f.infiltration[i] = infiltration;
+  f.infiltration_excess[i] = infiltration_excess;
 
   // ---- unsaturated zone flow, Brooks-Corey (soil.jl:764-804) -------------------------------
   const double kv_0 = __ldg(f.kv_0 + i);
@@ -430,52 +440,153 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
     kvfac[k] = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
   }
-  double transfer = 0.0;
-  {
-    double z = 0.0, flow = 0.0;
-    bool heavy = false;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      UnsatTask t;
-      t.usd = 0.0; t.sum_ast = 0.0; t.kv_it = 0.0; t.l_sat = 1.0; t.c = 1.0; t.its = 0;
-      const bool in_layer = k < n_unsat && !heavy;
-      if (in_layer) {
-        z = (k == 0) ? ult[0] : z + ult[k];
-        const double l_sat = ult[k] * theta_e;
-        const double kv_z = kv_at_depth(c.kv_profile, kvfac[k], kv_0, fpar, z_exp, z);
-        const double usd = (k == 0) ? uld[k] + infiltration * dt : uld[k] + flow * dt;
-        t = unsatzone_flow_setup(usd, kv_z, l_sat, bc[k], dt);
-        if (tail) t.its = 0;
-      }
-      if (HEAVY) {
-        unsatzone_flow_balanced(t, dt, sh);
-      } else if (t.its > kLightIters) {
-        heavy = true;
-      } else {
-        unsatzone_flow_iterate(t, dt);
-      }
-      if (in_layer) {
-        uld[k] = t.usd;
-        flow = t.sum_ast;
-      }
-    }
-    if (!HEAVY && heavy) {  // left to the second pass
-      heavy_list[atomicAdd(heavy_count, 1u)] = i;
-      return;
-    }
-    if (n_unsat > 0) transfer = flow;
-  }
+  double transfer;
+  const bool done = unsat_layers<N>(f, c, w, 0, i, 0, n_unsat, 0.0, 0.0, infiltration, uld, ult, bc,
+                                    kvfac, kv_0, fpar, z_exp, theta_e, dt, ddt, live, transfer);
   // the read-modify-write states of the sections above
-  if (!tail) {
-    if (!c.gash) f.canopy_storage[i] = st_canopy;
-    if (c.snow) {
-      f.snow_water[i] = st_snoww;
-      f.snow_storage[i] = st_snow;
-      f.soil_surface_temperature[i] = st_tsoil;
-      if (c.glacier) f.glacier_store[i] = st_gstore;
+  if (!c.gash) f.canopy_storage[i] = st_canopy;
+  if (c.snow) {
+    f.snow_water[i] = st_snoww;
+    f.snow_storage[i] = st_snow;
+    f.soil_surface_temperature[i] = st_tsoil;
+    if (c.glacier) f.glacier_store[i] = st_gstore;
+  }
+  // layers above a suspended one are final, the others are written by unsat_resume_kernel
+#pragma unroll
+  for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = uld[k];
+  if (done) f.transfer[i] = transfer;
+}
+
+// All suspended loops of the domain, one lane per loop, 32 loops of one bucket per warp.
+__global__ void __launch_bounds__(128)
+unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
+  const unsigned* cnt = w.count + parity * kBuckets;
+  const int lane = (int)threadIdx.x & 31;
+  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+  // consecutive tiles (the longest loops) go to different SMs
+  const int gw = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
+  const Divisor ddt(dt);
+  for (int j = gw;; j += n_warps) {
+    int b, first, n;
+    if (!tile_of(cnt, j, b, first, n)) break;
+    const int e = first + lane;
+    if (e < n) {
+      const int i = w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + e];
+      UnsatTask t;
+      t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
+      t.c = w.c[i]; t.its = w.its_layer[i] & 0xffffff;
+      unsatzone_flow_iterate(t, dt, ddt);
+      w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast;
     }
   }
-  if (!tail) f.transfer[i] = transfer;
+}
+
+// The suspended cells continue with the layer below the finished loop.
+template <int N>
+__global__ void __launch_bounds__(128)
+unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const int parity,
+                    const double dt) {
+  const unsigned* cnt = w.count + parity * kBuckets;
+  const int lane = (int)threadIdx.x & 31;
+  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+  const int gw = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5);
+  const int ns = c.ns;
+  const Divisor ddt(dt);
+  for (int j = gw;; j += n_warps) {
+    int b, first, n;
+    if (!tile_of(cnt, j, b, first, n)) break;
+    const int e = first + lane;
+    const bool live = e < n;
+    bool resume = false;
+    int i = 0, k0 = 0, n_unsat = 0;
+    double uld[N], ult[N], bc[N], kvfac[N];
+    double kv_0 = 0.0, fpar = 0.0, z_exp = 0.0, theta_e = 1.0, z = 0.0, flow = 0.0, transfer = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { uld[k] = 0.0; ult[k] = 1.0; bc[k] = 1.0; kvfac[k] = 1.0; }
+    if (live) {
+      i = w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + e];
+      const int kl = w.its_layer[i] >> 24;   // the layer whose loop has just been run
+      flow = w.sum_ast[i];
+      n_unsat = f.n_unsatlayers[i];
+      f.unsaturated_layer_depth[kl * ns + i] = w.usd[i];
+      k0 = kl + 1;
+      resume = true;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        ult[k] = f.unsaturated_layer_thickness[k * ns + i];
+        if (k >= k0) uld[k] = f.unsaturated_layer_depth[k * ns + i];
+        bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
+        kvfac[k] = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
+        if (k < k0) z = (k == 0) ? ult[0] : z + ult[k];  // same left-to-right sum as the first pass
+      }
+      kv_0 = __ldg(f.kv_0 + i);
+      fpar = __ldg(f.hydraulic_conductivity_scale_parameter + i);
+      z_exp = c.kv_profile == 1 ? __ldg(f.z_exp + i) : 0.0;
+      theta_e = __ldg(f.theta_s + i) - __ldg(f.theta_r + i);
+    }
+    // every lane of the warp calls unsat_layers (it aggregates the suspensions of the warp)
+    const bool done = unsat_layers<N>(f, c, w, parity ^ 1, i, resume ? k0 : N, resume ? n_unsat : 0,
+                                      z, flow, 0.0, uld, ult, bc, kvfac, kv_0, fpar, z_exp, theta_e,
+                                      dt, ddt, live, transfer);
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        if (k >= k0 && k < n_unsat) f.unsaturated_layer_depth[k * ns + i] = uld[k];
+      if (done) f.transfer[i] = transfer;
+    }
+  }
+}
+
+// update_land_hydrology_model!, second half: every quantity it needs from the first half is a
+// reference-visible output array (or an input), re-read here.
+template <int N>
+__global__ void __launch_bounds__(256)
+soil_column_kernel(const DevFields f, const KCfg c, const double dt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const int ns = c.ns;
+  const Divisor ddt(dt);
+  const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
+  const double theta_e = theta_s - theta_r;
+  const double theta_d = jmax(theta_s - __ldg(f.theta_fc + i), 0.02);
+  const double d_soil = __ldg(f.soil_thickness + i);
+  const double swc = __ldg(f.soil_water_capacity + i);
+  const double satwd = f.saturated_water_depth[i];
+  const double zi = f.water_table_depth[i];
+  const int nlayers = f.number_of_layers[i];
+  const int n_unsat = f.n_unsatlayers[i];
+  double drainable = (d_soil - zi) * theta_d;
+  double uld[N], ult[N], alt[N], cld[N + 1], bc[N], kvfac[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    uld[k] = f.unsaturated_layer_depth[k * ns + i];
+    ult[k] = f.unsaturated_layer_thickness[k * ns + i];
+    alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
+    cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
+    bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
+    kvfac[k] = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
+  }
+  cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
+  const double kv_0 = __ldg(f.kv_0 + i);
+  const double fpar = __ldg(f.hydraulic_conductivity_scale_parameter + i);
+  const double z_exp = c.kv_profile == 1 ? __ldg(f.z_exp + i) : 0.0;
+  const double pot_soilevap0 = f.potential_soilevaporation[i];
+  const double pot_transp = f.potential_transpiration[i];
+  const double infiltration = f.infiltration[i];
+  const double infiltration_excess = f.infiltration_excess[i];
+  const double wfs = f.soil_water_flux_surface[i];
+  const double f_red = f.f_infiltration_reduction[i];
+  const double pathfrac = __ldg(f.compacted_soil_area_fraction + i);
+  // infiltration! soil_process.jl:16-41, the same expressions as in land_surface_kernel
+  const double max_infiltsoil = jmin(__ldg(f.infiltration_capacity_soil + i) * f_red,
+                                     wfs * (1.0 - pathfrac));
+  const double max_infiltpath = jmin(__ldg(f.infiltration_capacity_compacted_soil + i) * f_red,
+                                     wfs * pathfrac);
+  const double transfer = f.transfer[i];
+  const double aeow_river = f.actual_open_water_evaporation_river[i];
+  const double aeow_land = f.actual_open_water_evaporation_land[i];
+  const double interception = f.interception_rate[i];
+  double ustore_depth, ustore_cap;
 
   // ---- soil evaporation (soil.jl:814-856, soil_process.jl:247-294) --------------------------
   double soilevap_sat, soil_evaporation;
@@ -483,22 +594,22 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     double pot = pot_soilevap0;
     double evu;
     if (n_unsat == 0) evu = 0.0;
-    else if (n_unsat == 1) evu = pot * jmin(1.0, uld[0] / (zi * theta_e));
-    else evu = pot * jmin(1.0, uld[0] / (ult[0] * theta_e));
-    evu = jmin(evu, uld[0] / dt);
+    else if (n_unsat == 1) evu = pot * jmin(1.0, fdiv(uld[0], zi * theta_e));
+    else evu = pot * jmin(1.0, fdiv(uld[0], ult[0] * theta_e));
+    evu = jmin(evu, uld[0] / ddt);
     pot -= evu;
     uld[0] = uld[0] - evu * dt;
     if (n_unsat == 0 || n_unsat == 1) {
-      const double e = pot * jmin(1.0, (alt[0] - zi) / alt[0]);
-      soilevap_sat = jmin(e, (alt[0] - zi) * theta_d / dt);  // deliberately not clamped at 0
+      const double e = pot * jmin(1.0, fdiv(alt[0] - zi, alt[0]));
+      soilevap_sat = jmin(e, (alt[0] - zi) * theta_d / ddt);  // deliberately not clamped at 0
     } else {
       soilevap_sat = 0.0;
     }
     soil_evaporation = evu + soilevap_sat;
     drainable -= soilevap_sat * dt;
   }
-  if (!tail) f.soil_evaporation_saturated_zone[i] = soilevap_sat;
-  if (!tail) f.soil_evaporation[i] = soil_evaporation;
+  f.soil_evaporation_saturated_zone[i] = soilevap_sat;
+  f.soil_evaporation[i] = soil_evaporation;
 
   // ---- transpiration (soil.jl:865-975) -----------------------------------------------------
   const double rd = __ldg(f.rooting_depth + i);
@@ -507,13 +618,13 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
   const double hb = __ldg(f.air_entry_pressure + i);
   double h3;
   {
-    const double tpot_daily = pot_transp / WFB_MM_PER_DAY;  // feddes_h3 soil_process.jl:166-176
+    const double tpot_daily = fdiv(pot_transp, WFB_MM_PER_DAY);  // feddes_h3 soil_process.jl:166-176
     const double h3_high = __ldg(f.h3_high + i), h3_low = __ldg(f.h3_low + i);
     if (tpot_daily <= 1.0) h3 = h3_low;
     else if (tpot_daily < 5.0) h3 = h3_low + (h3_high - h3_low) * (tpot_daily - 1.0) / (5.0 - 1.0);
     else h3 = h3_high;
   }
-  if (!tail) f.h3[i] = h3;
+  f.h3[i] = h3;
   double rootf[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) rootf[k] = __ldg(f.rootfraction + k * ns + i);
@@ -524,7 +635,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
       double rfu;
       if (k == n_unsat - 1 && zi < rd) {
         const double rootlength = jmin(alt[k], rd - cld[k]);
-        rfu = rootf[k] * (ult[k] / rootlength);
+        rfu = rootf[k] * fdiv(ult[k], rootlength);
       } else {
         rfu = rootf[k];
       }
@@ -538,13 +649,13 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
     if (k < n_unsat) {
       const double rfu = (k < n_unsat - 1) ? rootf[k] : rf_lowest;
       const double rfs = rd > 0.0 ? jmax(1.0 / sum_rf, 1.0) * rfu : 0.0;
-      const double vwc = jmax(uld[k] / ult[k], 1e-7);
+      const double vwc = jmax(fdiv(uld[k], ult[k]), 1e-7);
       // head_brooks_corey soil_process.jl:113-130
       const double par_lambda = 2.0 / (bc[k] - 3.0);
-      const double head = par_lambda > 0.0 ? hb / jpow(vwc / theta_e, 1.0 / par_lambda) : hb;
+      const double head = par_lambda > 0.0 ? hb / jpow(fdiv(vwc, theta_e), 1.0 / par_lambda) : hb;
       const double alpha = rwu_reduction_feddes(head, h1, h2, h3, h4, alpha_h1);
-      const double availcap = jmin(1.0, jmax(0.0, (rd - cld[k]) / ult[k]));
-      const double maxextr = uld[k] * availcap / dt;
+      const double availcap = jmin(1.0, jmax(0.0, fdiv(rd - cld[k], ult[k])));
+      const double maxextr = uld[k] * availcap / ddt;
       const double layer = jmin(alpha * rfs * pot_transp, maxextr);
       uld[k] = uld[k] - layer * dt;
       actevapustore += layer;
@@ -553,12 +664,12 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
   const double wetroots = scurve(zi, rd, 1.0, __ldg(f.wet_root_distribution_parameter + i));
   const double alpha_sat = rwu_reduction_feddes(0.0, h1, h2, h3, h4, alpha_h1);
   const double restpottrans = pot_transp - actevapustore;
-  const double ae_sat = jmin(restpottrans * wetroots * alpha_sat, drainable / dt);
+  const double ae_sat = jmin(restpottrans * wetroots * alpha_sat, drainable / ddt);
   drainable -= ae_sat * dt;
   const double transpiration = actevapustore + ae_sat;
-  if (!tail) f.actual_evaporation_unsaturated_store[i] = actevapustore;
-  if (!tail) f.actual_evaporation_saturated_zone[i] = ae_sat;
-  if (!tail) f.transpiration[i] = transpiration;
+  f.actual_evaporation_unsaturated_store[i] = actevapustore;
+  f.actual_evaporation_saturated_zone[i] = ae_sat;
+  f.transpiration[i] = transpiration;
 
   // ---- actual infiltration and excess water (soil.jl:987-1043, 1178-1192) -------------------
   double excess = 0.0;
@@ -570,20 +681,21 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
       if (k > 0) uld[k - 1] = uld[k - 1] + excess;
     }
   }
-  const double actual_infiltration = infiltration - excess / dt;
-  if (!tail) f.actual_infiltration[i] = actual_infiltration;
-  if (!tail) f.saturation_excess_water[i] = (wfs - actual_infiltration) - infiltration_excess;
+  const double actual_infiltration = infiltration - excess / ddt;
+  f.actual_infiltration[i] = actual_infiltration;
+  f.saturation_excess_water[i] = (wfs - actual_infiltration) - infiltration_excess;
   double actinf_soil, actinf_path;
   if (actual_infiltration > 0.0) {  // soil_process.jl:297-323
-    actinf_soil = actual_infiltration * max_infiltsoil / (max_infiltpath + max_infiltsoil);
-    actinf_path = actual_infiltration * max_infiltpath / (max_infiltpath + max_infiltsoil);
+    const Divisor dsum(max_infiltpath + max_infiltsoil);
+    actinf_soil = actual_infiltration * max_infiltsoil / dsum;
+    actinf_path = actual_infiltration * max_infiltpath / dsum;
   } else {
     actinf_soil = 0.0; actinf_path = 0.0;
   }
-  if (!tail) f.actual_infiltration_soil[i] = actinf_soil;
-  if (!tail) f.actual_infiltration_compacted_soil[i] = actinf_path;
-  if (!tail) f.excess_water_soil[i] = jmax(wfs * (1.0 - pathfrac) - actinf_soil, 0.0);
-  if (!tail) f.excess_water_compacted_soil[i] = jmax(wfs * pathfrac - actinf_path, 0.0);
+  f.actual_infiltration_soil[i] = actinf_soil;
+  f.actual_infiltration_compacted_soil[i] = actinf_path;
+  f.excess_water_soil[i] = jmax(wfs * (1.0 - pathfrac) - actinf_soil, 0.0);
+  f.excess_water_compacted_soil[i] = jmax(wfs * pathfrac - actinf_path, 0.0);
 
   // ---- recompute stores, capillary flux, leakage, recharge (soil.jl:1194-1209) --------------
   ustore_depth = 0.0;
@@ -591,8 +703,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
   for (int k = 0; k < N; ++k)
     if (k < nlayers) ustore_depth += uld[k];
   ustore_cap = swc - satwd - ustore_depth;
-  if (!tail) f.unsaturated_store_depth[i] = ustore_depth;
-  if (!tail) f.unsaturated_store_capacity[i] = ustore_cap;
+  f.unsaturated_store_depth[i] = ustore_depth;
+  f.unsaturated_store_capacity[i] = ustore_cap;
   double act_capflux = 0.0;
   if (n_unsat > 0) {  // capillary_flux! soil.jl:1050-1111
     double kvfac_nu = kvfac[0];
@@ -601,43 +713,43 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const double dt, int32_t*
       if (k == n_unsat - 1) kvfac_nu = kvfac[k];
     const double ksat = kv_at_depth(c.kv_profile, kvfac_nu, kv_0, fpar, z_exp, zi);
     double mc = jmin(ksat, actevapustore);
-    mc = jmin(mc, ustore_cap / dt);
-    mc = jmin(mc, drainable / dt);
+    mc = jmin(mc, ustore_cap / ddt);
+    mc = jmin(mc, drainable / ddt);
     const double maxcapflux = jmax(0.0, mc);
     double capflux = 0.0;
     if (zi > rd) {
       const double hmax = __ldg(f.cap_hmax + i);
-      capflux = maxcapflux * jpow(1.0 - jmin(zi, hmax) / hmax, __ldg(f.cap_n + i));
+      capflux = maxcapflux * jpow(1.0 - fdiv(jmin(zi, hmax), hmax), __ldg(f.cap_n + i));
     }
     double net = capflux;
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
       if (k < n_unsat) {
-        const double toadd = jmin(net, jmax((ult[k] * theta_e - uld[k]) / dt, 0.0));
+        const double toadd = jmin(net, jmax((ult[k] * theta_e - uld[k]) / ddt, 0.0));
         uld[k] = uld[k] + toadd * dt;
         net -= toadd;
         act_capflux += toadd;
       }
     }
   }
-  if (!tail) f.actual_capillary_flux[i] = act_capflux;
+  f.actual_capillary_flux[i] = act_capflux;
   double kvfac_nl = kvfac[0];
 #pragma unroll
   for (int k = 1; k < N; ++k)
     if (k == nlayers - 1) kvfac_nl = kvfac[k];
   const double deepksat = kv_at_depth(c.kv_profile, kvfac_nl, kv_0, fpar, z_exp, d_soil);
-  const double deeptransfer = jmin(drainable / dt, deepksat);
+  const double deeptransfer = jmin(drainable / ddt, deepksat);
   const double leakage = jmax(0.0, jmin(__ldg(f.maximum_leakage + i), deeptransfer));
-  if (!tail) f.actual_leakage[i] = leakage;
-  if (!tail) f.recharge[i] = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
+  f.actual_leakage[i] = leakage;
+  f.recharge[i] = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
   // total AET (soil.jl:1206-1209) + interception (sbm.jl:130)
   double aet = soil_evaporation + transpiration + aeow_river + aeow_land + 0.0;
   aet += interception;
-  if (!tail) f.actual_evapotranspiration[i] = aet;
-  if (!tail) f.drainable_water_depth[i] = drainable;
+  f.actual_evapotranspiration[i] = aet;
+  f.drainable_water_depth[i] = drainable;
 #pragma unroll
   for (int k = 0; k < N; ++k)
-    if (!tail) f.unsaturated_layer_depth[k * ns + i] = uld[k];
+    f.unsaturated_layer_depth[k * ns + i] = uld[k];
 }
 
 // update_bc_open_water_runoff_model!: river h -> land grid                 runoff.jl:77-79
@@ -751,27 +863,23 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
   return 1;
 }
 
-#ifdef WFB_UNSAT_HIST
-void dump_unsat_hist() {
-  unsigned long long h[40];
-  cudaMemcpyFromSymbol(h, g_unsat_hist, sizeof(h));
-  unsigned long long z[40] = {0};
-  cudaMemcpyToSymbol(g_unsat_hist, z, sizeof(z));
-  fprintf(stderr, "unsat sub-iteration histogram (sum its %llu):", h[32]);
-  for (int b = 0; b < 31; ++b) if (h[b]) fprintf(stderr, " [<%d]=%llu", 1 << b, h[b]);
-  fprintf(stderr, "\n");
-}
-#endif
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          int32_t* heavy_list, unsigned* heavy_count, cudaStream_t s) {
-  const int grid = (c.n + kVertBlock - 1) / kVertBlock;
-  cudaMemsetAsync(heavy_count, 0, sizeof(unsigned), s);
-  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N, false><<<grid, kVertBlock, 0, s>>>(
-                               f, c, dt, heavy_list, heavy_count)));
-  // second pass over the listed cells; CTAs beyond the end of the list exit at once
-  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N, true><<<grid, kVertBlock, 0, s>>>(
-                               f, c, dt, heavy_list, heavy_count)));
-  return 2;
+                          const UnsatWork& w, int engine_grid, cudaStream_t s) {
+  int launches = 0;
+  cudaMemsetAsync(w.count, 0, 2 * kBuckets * sizeof(unsigned), s);
+  const int grid = (c.ns + 255) / 256;
+  WFB_DISPATCH_N(n_layers, (land_surface_kernel<N><<<grid, 256, 0, s>>>(f, c, w, dt)));
+  ++launches;
+  // the suspended loops, then the layers below them: a cell can be suspended once per layer
+  for (int r = 0; r < n_layers; ++r) {
+    const int parity = r & 1;
+    unsat_loop_kernel<<<engine_grid, 128, 0, s>>>(w, parity, dt);
+    if (r > 0) cudaMemsetAsync(w.count + (parity ^ 1) * kBuckets, 0, kBuckets * sizeof(unsigned), s);
+    WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, s>>>(f, c, w, parity, dt)));
+    launches += 2;
+  }
+  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<grid, 256, 0, s>>>(f, c, dt)));
+  return launches + 1;
 }
 
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s) {
