@@ -1,17 +1,18 @@
 #!/bin/bash
-# GPU box session: parity tests, bench line, ncu launch list, ncu full capture of the vertical kernel.
+# GPU box session: parity tests, bench line, ncu launch list, ncu full capture of the vertical kernels.
 TAG=${1:-r1b}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi_$TAG.txt 2>&1
 nproc >> gpurun_out/smi_$TAG.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_$TAG.log 2>&1
 tail -5 gpurun_out/gputests_$TAG.log
-timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 600 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -c 3000 gpurun_out/bench_$TAG.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:land_hydrology -s 6 -c 4 \
-    -o gpurun_out/prof_v1_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
+timeout 600 ncu --set full --clock-control none --import-source on \
+    -k regex:'land_surface|soil_column|unsat_loop|unsat_resume' -s 36 -c 6 \
+    -o gpurun_out/prof_v1_$TAG python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu2_$TAG.log 2>&1
 ls -la gpurun_out
