@@ -95,6 +95,14 @@ typedef struct {
 #define WFLOWB200_A_WAVE_NODE_LEVEL 12 /* level of every node (0-based), by node id            */
 #define WFLOWB200_A_WAVE_CHUNK_PTR 13  /* slot offsets of the chunks (0-based, n_chunks + 1)   */
 #define WFLOWB200_A_WAVE_CHUNK_OUTLET 14 /* outlet node id of every chunk                      */
+/* single-sub-step wavefront (subsurface flow): bundles of WFLOWB200_BAND_DEPTH rows x 32 lanes  */
+#define WFLOWB200_BAND_DEPTH 4
+#define WFLOWB200_A_BAND_NODE 15       /* n_bundles x depth x 32: node id (1-based) or 0        */
+#define WFLOWB200_A_BAND_SRC 16        /* 8 per entry: lane in the previous row, 32768 + k for the
+                                          bundle's k-th inlet, 65535 = none (ascending node id)  */
+#define WFLOWB200_A_BAND_OUT 17        /* per entry: outlet number (0-based) or -1              */
+#define WFLOWB200_A_BAND_INLET_PTR 18  /* n_bundles + 1 offsets into BAND_INLET_OUT             */
+#define WFLOWB200_A_BAND_INLET_OUT 19  /* producer outlet number of every inlet                 */
 
 #define WFLOWB200_DOMAIN_LAND 0
 #define WFLOWB200_DOMAIN_RIVER 1

@@ -30,6 +30,15 @@ def test_update_model_matches_oracle(pkg, d1, d2, steps):
     _close(gpu)
 
 
+def test_band_kernel_matches_oracle(pkg, monkeypatch):
+    """The experimental single-sub-step subsurface kernel over bands (WFB_SSF_BANDS=1, read at
+    create) gives the same fields as the chunk walk and the oracle."""
+    monkeypatch.setenv("WFB_SSF_BANDS", "1")
+    gpu, ora, cfg = parity.run_pair(pkg, 97, 131, steps=4, seed=21)
+    parity.compare_models(gpu, ora)
+    _close(gpu)
+
+
 def test_fine_grained_entry_points_match_oracle(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 40, 50, steps=2, seed=3, fine_grained=True)
     parity.compare_models(gpu, ora)

@@ -42,7 +42,8 @@ class Stats(C.Structure):
 ARTIFACTS = dict(order=0, streamorder=1, upstream_ptr=2, upstream_idx=3, subdomain_level_ptr=4,
                  subdomain_level_idx=5, subdomain_ptr=6, subdomain_order=7, subdomain_indices=8,
                  ldd=9, wave_level_ptr=10, wave_perm=11, wave_node_level=12, wave_chunk_ptr=13,
-                 wave_chunk_outlet=14)
+                 wave_chunk_outlet=14, band_node=15, band_src=16, band_out=17, band_inlet_ptr=18,
+                 band_inlet_out=19)
 
 
 def header_symbols():
@@ -70,7 +71,7 @@ def lib():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
             "(wflow.jl_b200 has no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("WFB_LIB", LIB_PATH))  # WFB_LIB: developer aid (kernel variants)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     L.wflowb200_create.argtypes = [C.POINTER(Config), C.POINTER(Domain), C.POINTER(vp)]
     L.wflowb200_destroy.argtypes = [vp]

@@ -36,6 +36,8 @@ struct DomainDev {
   unsigned long long* q_out = nullptr;  // per chunk x S x NV published outlet values
   size_t q_out_words = 0;
   DevNet dev{};
+  DevBands bands{};                     // land only: single-sub-step subsurface flow
+  unsigned long long* band_q_out = nullptr;
 };
 
 // NetworkLand + NetworkRiver artefacts (network.jl:87-133,214-278; domain.jl:80-125).
@@ -71,6 +73,7 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
   const char* cr = getenv("WFB_CHUNK_RIVER");
   build_chunks(land, std::min<int64_t>(cl ? atoll(cl) : WFB_CHUNK_NODES, WFB_CHUNK_NODES));
   build_chunks(river, std::min<int64_t>(cr ? atoll(cr) : WFB_CHUNK_NODES, WFB_CHUNK_NODES));
+  build_bands(land, WFB_BAND_DEPTH);
   return WFLOWB200_OK;
 }
 
@@ -94,6 +97,15 @@ int32_t copy_artifact(const Network& nw, int32_t id, int64_t* dst, int64_t capac
     case WFLOWB200_A_WAVE_NODE_LEVEL: src = &nw.node_level; break;
     case WFLOWB200_A_WAVE_CHUNK_PTR: src = &nw.chunk_ptr; break;
     case WFLOWB200_A_WAVE_CHUNK_OUTLET: src = &nw.chunk_outlet; break;
+    case WFLOWB200_A_BAND_NODE:
+      tmp.resize(nw.bundle_node.size());
+      for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (int64_t)nw.bundle_node[i] + 1;
+      src = &tmp; break;
+    case WFLOWB200_A_BAND_SRC: tmp.assign(nw.bundle_src.begin(), nw.bundle_src.end()); src = &tmp; break;
+    case WFLOWB200_A_BAND_OUT: tmp.assign(nw.bundle_out.begin(), nw.bundle_out.end()); src = &tmp; break;
+    case WFLOWB200_A_BAND_INLET_PTR: src = &nw.bundle_inl_ptr; break;
+    case WFLOWB200_A_BAND_INLET_OUT:
+      tmp.assign(nw.bundle_inl_out.begin(), nw.bundle_inl_out.end()); src = &tmp; break;
     default: errmsg = "bad artefact id"; return WFLOWB200_ERR_ARG;
   }
   *len_out = (int64_t)src->size();
@@ -135,6 +147,9 @@ struct WflowB200 {
   unsigned long long* d_count = nullptr;
   double* d_min = nullptr;
   int grid_olf = 0, grid_riv = 0, grid_ssf = 0;
+  int grid_band = 0, warps_band = 0;   // single-sub-step subsurface kernel
+  size_t smem_band = 0;
+  bool use_bands = true;
   int64_t launches = 0;
   int64_t sub_land = 0, sub_river = 0, sub_ssf = 0;
   bool timing = false;
@@ -238,7 +253,34 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
   return WFLOWB200_OK;
 }
 
+// Device copies of the band artefacts (land domain).
+int32_t upload_bands(WflowB200* h, DomainDev& d) {
+  const Network& nw = d.nw;
+  std::vector<int32_t> slot(nw.bundle_node.size());
+  for (size_t i = 0; i < slot.size(); ++i)
+    slot[i] = nw.bundle_node[i] < 0 ? -1 : (int32_t)nw.slot_of[nw.bundle_node[i]];
+  std::vector<uint4> src(nw.bundle_node.size());
+  for (size_t i = 0; i < src.size(); ++i) {
+    const uint16_t* c = &nw.bundle_src[8 * i];
+    src[i] = make_uint4((unsigned)c[0] | ((unsigned)c[1] << 16), (unsigned)c[2] | ((unsigned)c[3] << 16),
+                        (unsigned)c[4] | ((unsigned)c[5] << 16), (unsigned)c[6] | ((unsigned)c[7] << 16));
+  }
+  std::vector<int32_t> inl_ptr(nw.bundle_inl_ptr.begin(), nw.bundle_inl_ptr.end());
+  CUDA_TRY(h, upload_raw(slot, &d.bands.slot, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(src, &d.bands.src, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(nw.bundle_out, &d.bands.out, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(inl_ptr, &d.bands.inl_ptr, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(nw.bundle_inl_out, &d.bands.inl_out, d.dev_arrays));
+  d.bands.n_bundles = (int32_t)nw.n_bundles;
+  d.bands.n_outlets = (int32_t)nw.n_band_outlets;
+  d.bands.max_inlets = (int32_t)nw.max_bundle_inlets;
+  CUDA_TRY(h, cudaMalloc((void**)&d.band_q_out,
+                         sizeof(unsigned long long) * 2 * (size_t)std::max<int64_t>(nw.n_band_outlets, 1)));
+  return WFLOWB200_OK;
+}
+
 void free_domain(DomainDev& d) {
+  cudaFree(d.band_q_out);
   cudaFree(d.node_of_slot);
   for (void* p : d.dev_arrays) cudaFree(p);
   cudaFree(d.q_out);
@@ -464,7 +506,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMemset(h->f.number_of_layers, 0, (size_t)h->ns * sizeof(int32_t)));
   TRY_CREATE(cudaMemset(h->f.n_unsatlayers, 0, (size_t)h->ns * sizeof(int32_t)));
 
-  if (upload_domain(h, h->land) || upload_domain(h, h->river)) return bail(WFLOWB200_ERR_CUDA);
+  if (upload_domain(h, h->land) || upload_domain(h, h->river) || upload_bands(h, h->land))
+    return bail(WFLOWB200_ERR_CUDA);
   {
     std::vector<int64_t> riv_land_slot(h->nriv), riv_of_land(h->n, -1);
     for (int p = 0; p < h->nriv; ++p) {
@@ -516,6 +559,22 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->grid_olf = wave_max_grid(0, h->N, h->smem_olf, cfg->device);
   h->grid_riv = wave_max_grid(1, h->N, h->smem_riv, cfg->device);
   h->grid_ssf = wave_max_grid(2, h->N, h->smem_ssf, cfg->device);
+  {
+    const size_t per_warp = band_smem_per_warp(h->N, h->land.bands.max_inlets);
+    h->warps_band = (int)std::min<size_t>(8, (size_t)(220 * 1024) / per_warp);
+    const char* bw = getenv("WFB_BAND_WARPS");  // experiments
+    if (bw && atoi(bw) >= 1) h->warps_band = std::min(h->warps_band, atoi(bw));
+    // The band kernel is kept for experiments (WFB_SSF_BANDS=1): on B200 its inflow-dependent
+    // phase shares the SM with the memory-heavy phases of the sibling warps and the chunk walk
+    // is faster at every size measured so far.
+    const char* ub = getenv("WFB_SSF_BANDS");
+    h->use_bands = ub && atoi(ub) != 0 && h->warps_band >= 1;
+    if (h->use_bands) {
+      h->smem_band = per_warp * h->warps_band;
+      h->grid_band = band_max_grid(h->N, h->warps_band, h->smem_band, cfg->device);
+      if (h->grid_band <= 0) h->use_bands = false;
+    }
+  }
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -658,6 +717,46 @@ int32_t wflowb200_exchange_recharge(WflowB200* h) {
 int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  if (h->use_bands && !getenv("WFB_WAVE_PROF")) {
+    std::vector<double> dts;
+    if (fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1) {  // one sub-step: the band kernel
+      BandLaunch w{};
+      w.queue = h->d_queue + 2 * 32;
+      w.q_out = h->land.band_q_out;
+      w.dt = dts[0];
+      w.warps = h->warps_band;
+      w.smem = h->smem_band;
+      w.grid = (int)std::max<int64_t>(
+          1, std::min<int64_t>(h->grid_band, (h->land.nw.n_bundles + w.warps - 1) / w.warps));
+      h->sub_ssf = 1;
+      const bool prof = getenv("WFB_BAND_PROF") != nullptr;  // developer aid: per-bundle timing
+      const size_t prof_words = 8 * (size_t)std::max<int64_t>(h->land.nw.n_bundles, 1);
+      if (prof) {
+        CUDA_TRY(h, cudaMalloc((void**)&w.prof, sizeof(long long) * prof_words));
+        CUDA_TRY(h, cudaMemset(w.prof, 0, sizeof(long long) * prof_words));
+      }
+      int32_t rc = check_launch(h, launch_subsurface_band(h->f, h->kc, h->land.bands, h->N, w, h->stream),
+                                "update_subsurface_flow_model");
+      if (prof && !rc) {
+        std::vector<long long> hp(prof_words);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(hp.data(), w.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(w.prof);
+        FILE* fp = fopen("gpurun_out/band_prof.csv", "w");
+        if (fp) {
+          fprintf(fp, "bundle,t_start,t_prep,t_inlets,t_solved,t_end,smid,inlets\n");
+          long long t0 = hp[0];
+          for (int64_t b = 0; b < h->land.nw.n_bundles; ++b) t0 = std::min(t0, hp[8 * b]);
+          for (int64_t b = 0; b < h->land.nw.n_bundles; ++b)
+            fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", (long long)b, hp[8 * b] - t0,
+                    hp[8 * b + 1] - t0, hp[8 * b + 2] - t0, hp[8 * b + 3] - t0, hp[8 * b + 4] - t0,
+                    hp[8 * b + 5], hp[8 * b + 6]);
+          fclose(fp);
+        }
+      }
+      return rc;
+    }
+  }
   return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
                   [&](const WaveLaunch& w) {
                     return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);

@@ -58,6 +58,19 @@ int launch_river_wave(const DevFields& f, const KCfg& c, const DevNet& net, cons
                       cudaStream_t s);
 int launch_subsurface_wave(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,
                            const WaveLaunch& w, cudaStream_t s);
+// single-sub-step subsurface flow over bands (routing.cu: subsurface_band_kernel)
+struct BandLaunch {
+  unsigned* queue;            // device: next bundle to hand out (zeroed by the launcher)
+  unsigned long long* q_out;  // device: n_outlets x 2 published values (all-ones = not yet)
+  double dt;                  // the sub-step = the model time step
+  int grid, warps;            // CTAs and warps per CTA
+  size_t smem;
+  long long* prof;            // developer aid (WFB_BAND_PROF): 8 int64 per bundle
+};
+size_t band_smem_per_warp(int n_layers, int max_inlets);
+int band_max_grid(int n_layers, int warps, size_t smem, int device);
+int launch_subsurface_band(const DevFields& f, const KCfg& c, const DevBands& bd, int n_layers,
+                           const BandLaunch& w, cudaStream_t s);
 int launch_lateral_inflow_overland(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_lateral_inflow_river(const DevFields& f, const KCfg& c, cudaStream_t s);
 

@@ -175,8 +175,17 @@ __device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, 
 }  // namespace
 
 // update_land_hydrology_model!, first half                                 sbm.jl:82-132
+#ifndef WFB_V_BLOCK
+#define WFB_V_BLOCK 128
+#endif
+#ifndef WFB_VA_MINBLOCKS
+#define WFB_VA_MINBLOCKS 5
+#endif
+#ifndef WFB_VC_MINBLOCKS
+#define WFB_VC_MINBLOCKS 4
+#endif
 template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(WFB_V_BLOCK, WFB_VA_MINBLOCKS)
 land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.ns) return;     // whole warps (ns is a multiple of 32)
@@ -540,7 +549,7 @@ unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const in
 // update_land_hydrology_model!, second half: every quantity it needs from the first half is a
 // reference-visible output array (or an input), re-read here.
 template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(WFB_V_BLOCK, WFB_VC_MINBLOCKS)
 soil_column_kernel(const DevFields f, const KCfg c, const double dt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -867,8 +876,8 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
                           const UnsatWork& w, int engine_grid, cudaStream_t s) {
   int launches = 0;
   cudaMemsetAsync(w.count, 0, 2 * kBuckets * sizeof(unsigned), s);
-  const int grid = (c.ns + 255) / 256;
-  WFB_DISPATCH_N(n_layers, (land_surface_kernel<N><<<grid, 256, 0, s>>>(f, c, w, dt)));
+  const int grid = (c.ns + WFB_V_BLOCK - 1) / WFB_V_BLOCK;
+  WFB_DISPATCH_N(n_layers, (land_surface_kernel<N><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, w, dt)));
   ++launches;
   // the suspended loops, then the layers below them: a cell can be suspended once per layer
   for (int r = 0; r < n_layers; ++r) {
@@ -878,7 +887,7 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
     WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, s>>>(f, c, w, parity, dt)));
     launches += 2;
   }
-  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<grid, 256, 0, s>>>(f, c, dt)));
+  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, dt)));
   return launches + 1;
 }
 
