@@ -39,6 +39,24 @@ def test_band_kernel_matches_oracle(pkg, monkeypatch):
     _close(gpu)
 
 
+@pytest.mark.parametrize("dt", [86400.0, 3600.0])
+def test_adaptive_internal_time_steps_match_oracle(pkg, dt):
+    """kinematic_wave__adaptive_time_step_flag = true: the sub-step lengths come from the
+    type-7 quantile (surface, surface_kinwave.jl:674-704) / the minimum (subsurface,
+    lateral_subsurface_flow.jl:314-344) of the per-node Courant steps, evaluated on the device
+    after every sub-step; same number of sub-steps and same fields as the oracle."""
+    gpu, ora, cfg = parity.run_pair(pkg, 40, 56, steps=5 if dt > 4000.0 else 3, seed=13,
+                                    adaptive=True, dt=dt, snow=dt > 4000.0)
+    parity.compare_models(gpu, ora)
+    st, o = gpu.stats(), ora.newton_stats()
+    for k in ("substeps_land", "substeps_river", "substeps_ssf"):
+        assert st[k] == o[k], (k, st[k], o[k])
+    print({k: st[k] for k in st if k.startswith("substeps")})
+    if dt > 4000.0:  # the daily step needs several river / subsurface sub-steps
+        assert st["substeps_land"] + st["substeps_river"] + st["substeps_ssf"] > 3
+    _close(gpu)
+
+
 def test_fine_grained_entry_points_match_oracle(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 40, 50, steps=2, seed=3, fine_grained=True)
     parity.compare_models(gpu, ora)

@@ -146,6 +146,8 @@ struct WflowB200 {
   RoutingStats* d_stats = nullptr;
   unsigned long long* d_count = nullptr;
   double* d_min = nullptr;
+  double* d_work = nullptr;                 // adaptive sub-stepping: per-node stable time steps
+  unsigned long long* d_qstate = nullptr;   // state of the quantile select
   int grid_olf = 0, grid_riv = 0, grid_ssf = 0;
   int grid_band = 0, warps_band = 0;   // single-sub-step subsurface kernel
   size_t smem_band = 0;
@@ -326,9 +328,12 @@ int32_t check_launch(WflowB200* h, int rc, const char* what) {
 // 2 subsurface; nv = values published per node and sub-step.
 template <class Launch>
 int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kind, int nv,
-                 int max_grid, size_t smem, int64_t& substeps, Launch launch, const char* what) {
+                 int max_grid, size_t smem, int64_t& substeps, Launch launch, const char* what,
+                 double dt_single = 0.0, bool accumulate = false) {
   std::vector<double> dts;
-  const int S = fixed_substeps(dt, dt_fixed, dts);
+  int S;
+  if (dt_single > 0.0) { dts.assign(1, dt_single); S = 1; }  // one adaptive sub-step
+  else S = fixed_substeps(dt, dt_fixed, dts);
   if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
   const size_t need = (size_t)std::max<int64_t>(d.nw.n_chunks, 1) * (size_t)S * (size_t)nv;
   if (need > d.q_out_words) {  // outlet values of every sub-step, per chunk
@@ -347,6 +352,7 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
   w.dt_fixed = dts[0];
   w.dt_last = dts[S - 1];
   w.dt = dt;
+  w.accumulate = accumulate ? 1 : 0;
   w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
   w.smem = smem;
   w.prof = nullptr;
@@ -379,6 +385,60 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
     }
   }
   substeps = S;
+  return WFLOWB200_OK;
+}
+
+// Adaptive internal time stepping (kinematic_wave__adaptive_time_step_flag): the reference's
+// `while t < dt` loop (surface_kinwave.jl:371-379,640-655; lateral_subsurface_flow.jl:289-299).
+// Every sub-step needs a statistic of the whole domain's state after the previous one (a
+// type-7 quantile of the Courant steps for the surface components, their minimum for the
+// subsurface), so sub-steps cannot be pipelined through the levels: one wavefront launch per
+// sub-step, the statistic reduced on the device and read back (8-32 bytes) to drive the loop.
+template <class Launch>
+int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int nv, int max_grid,
+                          size_t smem, int64_t& substeps, Launch launch, const char* what) {
+  double t = 0.0;
+  int64_t count = 0;
+  while (t < dt) {
+    double dt_s;
+    if (kind == 2) {  // stable_timestep(::LateralSSF)  lateral_subsurface_flow.jl:314-344
+      int32_t rc = check_launch(h, launch_stable_timestep_ssf(h->f, h->kc, h->d_min, h->d_count, h->stream), what);
+      if (rc) return rc;
+      double mn = 0.0;
+      unsigned long long k = 0;
+      CUDA_TRY(h, cudaMemcpyAsync(&mn, h->d_min, 8, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(&k, h->d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      dt_s = (k == 0 ? 0.5 : mn) * h->cfg.ssf_alpha_coefficient;
+    } else {          // stable_timestep (surface)       surface_kinwave.jl:674-704
+      const bool riv = kind == 1;
+      const int n = riv ? h->nriv : h->n;
+      int32_t rc = check_launch(h, launch_stable_timesteps_surface(
+                                       riv ? h->f.riv_q : h->f.olf_q, riv ? h->f.riv_alpha : h->f.olf_alpha,
+                                       riv ? h->f.riv_flow_length : h->f.flow_length, n, h->d_work,
+                                       h->d_count, h->stream), what);
+      if (rc) return rc;
+      rc = check_launch(h, launch_quantile7(h->d_work, h->d_count, n, riv ? 0.05 : 0.02, h->d_qstate,
+                                            h->stream), what);
+      if (rc) return rc;
+      unsigned long long st[4];
+      CUDA_TRY(h, cudaMemcpyAsync(st, h->d_qstate, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      double a, b, g;
+      memcpy(&a, &st[1], 8); memcpy(&b, &st[2], 8); memcpy(&g, &st[3], 8);
+      if (st[0] == 0) dt_s = 600.0;
+      else if (st[0] == 1) dt_s = a;
+      else dt_s = (std::isfinite(a) && std::isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
+    }
+    if (!(dt_s > 0.0)) return fail(h, WFLOWB200_ERR_STATE, std::string(what) + ": stable time step is not positive");
+    if (t + dt_s > dt) dt_s = dt - t;  // check_timestepsize  routing/timestepping.jl:11-16
+    int64_t one = 0;
+    int32_t rc = run_wave(h, d, dt, 0.0, kind, nv, max_grid, smem, one, launch, what, dt_s, count > 0);
+    if (rc) return rc;
+    t += dt_s;
+    if (++count > kMaxSub) return fail(h, WFLOWB200_ERR_STATE, std::string(what) + ": too many adaptive sub-steps");
+  }
+  substeps = count;
   return WFLOWB200_OK;
 }
 
@@ -544,6 +604,10 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
   TRY_CREATE(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
   TRY_CREATE(cudaMalloc((void**)&h->d_min, sizeof(double)));
+  if (cfg->adaptive) {
+    TRY_CREATE(cudaMalloc((void**)&h->d_work, (size_t)h->ns * sizeof(double)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_qstate, WFB_QUANTILE_STATE_WORDS * sizeof(unsigned long long)));
+  }
 
   h->kc.n = h->n; h->kc.nriv = h->nriv; h->kc.ns = h->ns; h->kc.nrs = h->nrs;
   h->kc.gash = cfg->gash; h->kc.has_lai = cfg->has_lai; h->kc.snow = cfg->snow;
@@ -595,6 +659,7 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->d_unsat_pool); cudaFree(h->unsat.its_layer); cudaFree(h->unsat.list);
   cudaFree(h->unsat.count);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
+  cudaFree(h->d_work); cudaFree(h->d_qstate);
   free_domain(h->land); free_domain(h->river);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
   if (h->forcing_consumed) cudaEventDestroy(h->forcing_consumed);
@@ -716,7 +781,11 @@ int32_t wflowb200_exchange_recharge(WflowB200* h) {
 
 int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
-  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  if (h->cfg.adaptive)
+    return run_wave_adaptive(h, h->land, dt, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
+                             [&](const WaveLaunch& w) {
+                               return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
+                             }, "update_subsurface_flow_model");
   if (h->use_bands && !getenv("WFB_WAVE_PROF")) {
     std::vector<double> dts;
     if (fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1) {  // one sub-step: the band kernel
@@ -778,7 +847,11 @@ int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h) {
 
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
-  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  if (h->cfg.adaptive)
+    return run_wave_adaptive(h, h->land, dt, 0, 2, h->grid_olf, h->smem_olf, h->sub_land,
+                             [&](const WaveLaunch& w) {
+                               return launch_overland_wave(h->f, h->kc, h->land.dev, w, h->stream);
+                             }, "update_overland_flow_model");
   return run_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, h->grid_olf, h->smem_olf, h->sub_land,
                   [&](const WaveLaunch& w) {
                     return launch_overland_wave(h->f, h->kc, h->land.dev, w, h->stream);
@@ -794,7 +867,11 @@ int32_t wflowb200_update_lateral_inflow_river(WflowB200* h) {
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
   if (!h) return WFLOWB200_ERR_ARG;
   if (h->nriv == 0) return WFLOWB200_OK;
-  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_STATE, "adaptive sub-stepping: use update_model");
+  if (h->cfg.adaptive)
+    return run_wave_adaptive(h, h->river, dt, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
+                             [&](const WaveLaunch& w) {
+                               return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
+                             }, "update_river_flow_model");
   return run_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
                   [&](const WaveLaunch& w) {
                     return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);

@@ -41,6 +41,8 @@ struct WaveLaunch {
   int S;                      // number of sub-steps pipelined through the wavefront
   double dt_fixed, dt_last;   // sub-step lengths: S - 1 times dt_fixed, then dt_last
   double dt;                  // model time step (for the averages)
+  int accumulate;             // adaptive sub-stepping, one launch per sub-step: this launch
+                              // continues the cumulative fluxes of the previous ones
   int grid;
   size_t smem;                // dynamic shared memory of the kernel (wave_smem)
   long long* prof;            // developer aid (WFB_WAVE_PROF): 8 x n_chunks int64 written by
@@ -80,6 +82,14 @@ int launch_stable_timesteps_surface(const double* q, const double* alpha, const 
                                     double* work, unsigned long long* count, cudaStream_t s);
 int launch_stable_timestep_ssf(const DevFields& f, const KCfg& c, double* out_min,
                                unsigned long long* count, cudaStream_t s);
+// Statistics.quantile! (type 7) of the `*count` positive values in `work` (Statistics 1.11.1,
+// call site surface_kinwave.jl:698): radix select of the two order statistics it interpolates
+// between. `state` holds QUANTILE_STATE_WORDS 64-bit words (device); after the launches
+// state[0] = k, state[1] = bits of v[j], state[2] = bits of v[j+1] (sorted, 1-based j),
+// state[3] = bits of gamma.
+#define WFB_QUANTILE_STATE_WORDS (16 + 256)
+int launch_quantile7(const double* work, const unsigned long long* count, int n_max, double p,
+                     unsigned long long* state, cudaStream_t s);
 
 // host<->device layout conversion through the slot permutation
 int launch_gather_field(double* dst, const double* staged, const int32_t* node_of_slot, int n,
