@@ -136,8 +136,10 @@ int32_t wflowb200_set_field_i64(WflowB200* h, int32_t which, const int64_t* src)
 int32_t wflowb200_get_field_i64(WflowB200* h, int32_t which, int64_t* dst);
 
 /* update_forcing! hand-off (io.jl:108-160 -> AtmosphericForcing forcing.jl:2-10): three host
- * vectors [m s-1, m s-1, K]; copied H2D asynchronously on the library's copy stream through
- * pinned staging; the next update_* call waits for it on the device. */
+ * vectors [m s-1, m s-1, K]; copied H2D on the library's copy stream -- straight from the
+ * caller's arrays when they are page-locked (cudaHostRegister / cudaMallocHost), else through
+ * the library's pinned staging buffer. The arrays may be reused as soon as the call returns;
+ * the next update_* call waits for the copy on the device. */
 int32_t wflowb200_set_forcing(WflowB200* h, const double* precipitation,
                               const double* potential_evaporation, const double* temperature);
 

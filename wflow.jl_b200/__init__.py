@@ -5,7 +5,7 @@ The directory name is not a valid dotted module name; load it by path:
 `__graft_entry__.load_pkg()` registers it as module `wflow_jl_b200` (tests/conftest.py and
 bench.py use that helper).
 """
-from . import _lib, synthetic  # noqa: F401
+from . import _lib, partition, synthetic  # noqa: F401
 from ._lib import build, header_symbols  # noqa: F401
 from .model import SbmModel, WflowB200Error  # noqa: F401
 from .network import build_network_artifacts  # noqa: F401

@@ -749,6 +749,24 @@ int32_t wflowb200_set_forcing(WflowB200* h, const double* P, const double* PET, 
   // the previous forcing must have been consumed before the staging buffers are reused
   CUDA_TRY(h, cudaEventSynchronize(h->forcing_consumed));
   const size_t nb = (size_t)h->n * sizeof(double);
+  // Page-locked caller arrays (cudaHostRegister / cudaMallocHost) are copied straight to the
+  // device; the call returns when the copy has left them, so the caller may reuse them at once
+  // (same contract as the staged path). Pageable arrays go through the pinned staging buffer.
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  if (pinned(P) && pinned(PET) && pinned(T)) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_forcing, P, nb, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_forcing + h->n, PET, nb, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_forcing + 2 * (size_t)h->n, T, nb, cudaMemcpyHostToDevice,
+                                h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->forcing_ready, h->copy_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    h->forcing_pending = true;
+    return WFLOWB200_OK;
+  }
   memcpy(h->h_pinned, P, nb);
   memcpy(h->h_pinned + h->n, PET, nb);
   memcpy(h->h_pinned + 2 * (size_t)h->n, T, nb);
