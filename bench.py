@@ -158,7 +158,8 @@ def run_cpu(pkg, cfg, dom, fields, steps: int, warmup: int, seed: int, first_ste
     ora = parity.make_oracle(cfg, dom, fields)
     dt = cfg["dt"]
     gid = dom["gid"]
-    cores = len(os.sched_getaffinity(0))
+    # all the host threads the process may use (torchrun exports OMP_NUM_THREADS=1)
+    cores = ora._L.wfo_set_num_threads(len(os.sched_getaffinity(0)))
 
     def one(step):
         p, e, t = pkg.synthetic.make_forcing(seed, step, gid, dt)

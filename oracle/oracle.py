@@ -69,6 +69,8 @@ def lib():
             getattr(L, f).restype = None
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.wfo_get_stats.restype = None
+        L.wfo_set_num_threads.argtypes = [C.c_int]
+        L.wfo_set_num_threads.restype = C.c_int
         L.wfo_sweep.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.wfo_sweep.restype = C.c_int
         d = C.c_double

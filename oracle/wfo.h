@@ -172,6 +172,9 @@ void wfo_update_model(wfo_model*, double dt);                  /* sbm_model.jl:6
 void wfo_update_diagnostic_vars(wfo_model*);                   /* soil.jl:1400-1436 */
 int  wfo_sweep(wfo_model*, const char* name, double dt);                   /* test hook */
 void wfo_get_stats(wfo_model*, int64_t out[9]);
+/* OpenMP team size of the sweeps (a launcher such as torchrun exports OMP_NUM_THREADS=1);
+ * returns the value in effect. n <= 0 only queries. */
+int wfo_set_num_threads(int n);
 
 /* scalar kernels exported for the known-answer tests */
 void wfo_rainfall_interception_gash(double cmax, double e_r, double gap, double p, double cs,

@@ -76,37 +76,46 @@ def test_masked_raster_artifacts_and_pit_fixup(pkg):
     assert np.array_equal(art["land"]["order"], land["order"])
 
 
-def test_wavefront_levels_and_chunks_are_a_valid_schedule(pkg):
+@pytest.mark.parametrize("piece_land,piece_river", [(None, None), ("0", "0"), ("6", "4")])
+def test_wavefront_levels_and_chunks_are_a_valid_schedule(pkg, monkeypatch, piece_land, piece_river):
     """Every drainage edge spans exactly one wavefront level (the invariant the skewed
-    wavefront relies on); chunks are connected pieces with one outlet; slots are ordered
-    (chunk, level, node id); chunk order is a topological order of the chunk DAG."""
+    wavefront relies on); a chunk holds at most 32 nodes in at most 32 levels, made of connected
+    pieces with one root each; slots are ordered (chunk, level, node id); every edge that leaves
+    a chunk leads to a LATER chunk (queue order = topological order of the chunk DAG)."""
+    if piece_land is not None:
+        monkeypatch.setenv("WFB_PIECE_LAND", piece_land)
+        monkeypatch.setenv("WFB_PIECE_RIVER", piece_river)
     cfg, dom, _ = pkg.synthetic.make_basin(90, 140, seed=5)
-    a = pkg.build_network_artifacts(cfg, dom)["land"]
-    perm, level, cp, outlet = a["wave_perm"], a["wave_node_level"], a["wave_chunk_ptr"], a["wave_chunk_outlet"]
-    n = cfg["n"]
-    assert sorted(perm.tolist()) == list(range(1, n + 1))
-    down = dom["down"]
-    has = down > 0
-    assert np.all(level[down[has] - 1] == level[has] + 1)
-    assert np.all(level[~has] == level.max())
-    assert np.array_equal(np.bincount(level), np.diff(a["wave_level_ptr"]))
-    chunk = np.zeros(n, dtype=np.int64)
-    for c in range(len(cp) - 1):
-        seg = perm[cp[c]:cp[c + 1]]
-        chunk[seg - 1] = c
-        key = level[seg - 1] * (n + 1) + seg
-        assert np.all(np.diff(key) > 0)                      # (level, node id) ascending
-        assert seg[-1] == outlet[c] or level[outlet[c] - 1] == level[seg - 1].max()
-        inside = has[seg - 1] & (chunk[down[seg - 1] - 1] == c)
-        # exactly one node of the chunk leaves it (its outlet)
-    for c in range(len(cp) - 1):
-        seg = perm[cp[c]:cp[c + 1]]
-        leaving = [v for v in seg if down[v - 1] == 0 or chunk[down[v - 1] - 1] != c]
-        assert leaving == [outlet[c]]
-        d = down[outlet[c] - 1]
-        if d:
-            assert chunk[d - 1] > c                          # producers come first in the queue
-    assert len(cp) - 1 >= 2
+    art = pkg.build_network_artifacts(cfg, dom)
+    rl = dom["river_land_indices"]
+    # river forest: downstream river node (1-based river id) of every river node
+    riv_of_land = np.zeros(cfg["n"] + 1, dtype=np.int64)
+    riv_of_land[rl] = np.arange(1, len(rl) + 1)
+    down_land = dom["down"]
+    down_riv = riv_of_land[down_land[rl - 1]]
+    for name, down in (("land", down_land), ("river", down_riv)):
+        a = art[name]
+        perm, level, cp, roots = (a["wave_perm"], a["wave_node_level"], a["wave_chunk_ptr"],
+                                  a["wave_chunk_outlet"])
+        n = len(perm)
+        assert sorted(perm.tolist()) == list(range(1, n + 1))
+        has = down > 0
+        assert np.all(level[down[has] - 1] == level[has] + 1)
+        assert np.all(level[~has] == level.max())
+        assert np.array_equal(np.bincount(level), np.diff(a["wave_level_ptr"]))
+        chunk = np.zeros(n, dtype=np.int64)
+        for c in range(len(cp) - 1):
+            seg = perm[cp[c]:cp[c + 1]]
+            chunk[seg - 1] = c
+            assert 1 <= len(seg) <= 32
+            assert level[seg - 1].max() - level[seg - 1].min() < 32
+            key = level[seg - 1] * (n + 1) + seg
+            assert np.all(np.diff(key) > 0)                  # (level, node id) ascending
+        leaving = (~has) | (chunk[np.maximum(down, 1) - 1] != chunk)
+        assert sorted((np.nonzero(leaving)[0] + 1).tolist()) == sorted(roots.tolist())
+        out = has & leaving
+        assert np.all(chunk[down[out] - 1] > chunk[out])     # producers come first in the queue
+        assert len(cp) - 1 >= 2
 
 
 @pytest.mark.parametrize("d1,d2,seed", [(90, 140, 5), (33, 61, 9), (7, 300, 2)])

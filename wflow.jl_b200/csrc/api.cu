@@ -71,8 +71,21 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
   // chunk sizes of the block-local wavefront (nodes per CTA work item); tunable for experiments
   const char* cl = getenv("WFB_CHUNK_LAND");
   const char* cr = getenv("WFB_CHUNK_RIVER");
-  build_chunks(land, std::min<int64_t>(cl ? atoll(cl) : WFB_CHUNK_NODES, WFB_CHUNK_NODES));
-  build_chunks(river, std::min<int64_t>(cr ? atoll(cr) : WFB_CHUNK_NODES, WFB_CHUNK_NODES));
+  // piece depth (levels) of the chunks; 0 = one connected piece per chunk. Tunable for experiments
+  const char* pl = getenv("WFB_PIECE_LAND");
+  const char* pr = getenv("WFB_PIECE_RIVER");
+  // Shallow multi-piece chunks cut the warp-stages of a sweep (24 sub-steps: -31 % at depth 4,
+  // one sub-step: -72 %) but add chunk-to-chunk hand-offs to the dependent chain of the sweep.
+  // Measured on B200: a loss on a latency-bound domain (1000^2: 1000 nodes per level, +16 % step
+  // time at depth 6), a gain on a throughput-bound one (3536^2: -8 %), so the depth follows the
+  // mean level width.
+  int64_t depth_land = WFB_PIECE_DEPTH_LAND;
+  if (land.n_wave_levels > 0 && land.n / land.n_wave_levels >= WFB_PIECE_WIDE_LEVEL)
+    depth_land = WFB_PIECE_DEPTH_LAND_WIDE;
+  build_chunks(land, std::min<int64_t>(cl ? atoll(cl) : WFB_CHUNK_NODES, WFB_CHUNK_NODES),
+               pl ? atoll(pl) : depth_land);
+  build_chunks(river, std::min<int64_t>(cr ? atoll(cr) : WFB_CHUNK_NODES, WFB_CHUNK_NODES),
+               pr ? atoll(pr) : WFB_PIECE_DEPTH_RIVER);
   build_bands(land, WFB_BAND_DEPTH);
   return WFLOWB200_OK;
 }
@@ -207,7 +220,7 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
   std::vector<int4> meta(nw.n_chunks);
   std::vector<unsigned long long> node_edges(n, ~0ull);
   std::vector<uint8_t> node_level(n), inl_level;
-  std::vector<int32_t> inl_src;
+  std::vector<int32_t> inl_src, node_out(n, -1);
   int64_t max_inlets = 0;
   for (int64_t c = 0; c < nw.n_chunks; ++c) {
     const int64_t p0 = nw.chunk_ptr[c], nn = nw.chunk_ptr[c + 1] - p0;
@@ -219,6 +232,7 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
     for (int64_t p = p0; p < p0 + nn; ++p) {
       const int64_t v = nw.perm[p] - 1;  // in-neighbours are already ascending by node id
       node_level[p] = (uint8_t)(nw.node_level[v] - nw.chunk_l0[c]);
+      node_out[p] = (int32_t)nw.out_of_node[v];
       const int64_t deg = nw.in_ptr[v + 1] - nw.in_ptr[v];
       if (deg > 8) return fail(h, WFLOWB200_ERR_GRAPH, "node with more than 8 upstream nodes");
       unsigned long long code = ~0ull;
@@ -231,7 +245,9 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
             return fail(h, WFLOWB200_ERR_STATE, "too many inlet edges in one chunk");
           b = (unsigned long long)(WFB_CHUNK_NODES + k++);
           inl_level.push_back(node_level[p]);
-          inl_src.push_back((int32_t)cu);
+          if (nw.out_of_node[u] < 0)
+            return fail(h, WFLOWB200_ERR_STATE, "inlet edge from a node that does not publish");
+          inl_src.push_back((int32_t)nw.out_of_node[u]);
         } else {
           b = (unsigned long long)(nw.slot_of[u] - p0);
         }
@@ -240,12 +256,13 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
       node_edges[p] = code;
     }
     max_inlets = std::max(max_inlets, k);
-    const int feeds = nw.down[nw.chunk_outlet[c] - 1] ? 1 : 0;
-    meta[c] = make_int4((int)p0, (int)(nn | (nlev << 8) | (feeds << 16)), (int)i0, (int)k);
+    meta[c] = make_int4((int)p0, (int)(nn | (nlev << 8)), (int)i0, (int)k);
   }
   CUDA_TRY(h, upload_raw(meta, &d.dev.chunk_meta, d.dev_arrays));
   CUDA_TRY(h, upload_raw(node_edges, &d.dev.node_edges, d.dev_arrays));
   CUDA_TRY(h, upload_raw(node_level, &d.dev.node_level, d.dev_arrays));
+  CUDA_TRY(h, upload_raw(node_out, &d.dev.node_out, d.dev_arrays));
+  d.dev.n_outlets = (int32_t)nw.n_outlets;
   CUDA_TRY(h, upload_raw(inl_src, &d.dev.inl_src, d.dev_arrays));
   CUDA_TRY(h, upload_raw(inl_level, &d.dev.inl_level, d.dev_arrays));
   d.dev.n = (int32_t)n;
@@ -335,8 +352,8 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
   if (dt_single > 0.0) { dts.assign(1, dt_single); S = 1; }  // one adaptive sub-step
   else S = fixed_substeps(dt, dt_fixed, dts);
   if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
-  const size_t need = (size_t)std::max<int64_t>(d.nw.n_chunks, 1) * (size_t)S * (size_t)nv;
-  if (need > d.q_out_words) {  // outlet values of every sub-step, per chunk
+  const size_t need = (size_t)std::max<int64_t>(d.nw.n_outlets, 1) * (size_t)S * (size_t)nv;
+  if (need > d.q_out_words) {  // published values of every sub-step, per outlet
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d.q_out);
     d.q_out = nullptr;

@@ -23,26 +23,34 @@ struct DevFields {
 };
 
 // One routing domain (land or river) as the wavefront kernels see it. Slots are ordered by
-// (chunk, level, node id); a chunk is a connected piece of the drainage forest with ONE outlet
-// node (its last slot) and at most WFB_CHUNK_NODES = 32 nodes: one WARP walks it, one lane per
-// node.
+// (chunk, level, node id); a chunk is a set of connected pieces of the drainage forest (one
+// outlet node each) with at most WFB_CHUNK_NODES = 32 nodes in total: one WARP walks it, one
+// lane per node.
 #define WFB_CHUNK_NODES 32
+// piece depth of the chunks (network.hpp: build_chunks; 0 = one connected piece per chunk):
+// see api.cu: build_networks for the measurements behind these values
+#define WFB_PIECE_DEPTH_LAND 0
+#define WFB_PIECE_DEPTH_LAND_WIDE 6   // land domains with >= WFB_PIECE_WIDE_LEVEL nodes per level
+#define WFB_PIECE_WIDE_LEVEL 2048
+#define WFB_PIECE_DEPTH_RIVER 0
 #define WFB_NO_EDGE 0xffu
 struct DevNet {
   int32_t n;                    // nodes
   int32_t n_levels;             // wavefront levels of the whole domain
   int32_t n_chunks;
   int32_t max_inlets;           // largest number of inlet edges of any chunk
-  const int4* chunk_meta;       // per chunk: x = first slot, y = nodes | levels << 8 | feeds << 16
-                                // (feeds: the outlet drains into another chunk), z = offset of
-                                // its inlet list, w = number of inlet edges
+  int32_t n_outlets;            // publishing piece roots of the whole domain
+  const int4* chunk_meta;       // per chunk: x = first slot, y = nodes | levels << 8, z = offset
+                                // of its inlet list, w = number of inlet edges
+  const int32_t* node_out;      // per slot: outlet number if the node drains into another chunk
+                                // (it publishes its discharge of every sub-step), else -1
   const unsigned long long* node_edges;  // per slot: up to 8 upstream sources, one byte each,
                                 // ordered by ascending upstream NODE ID (the reference's
                                 // left-fold order, utils.jl:472-477): lane of the source inside
                                 // the chunk (< 32), 32 + k for the chunk's k-th inlet edge, or
                                 // WFB_NO_EDGE
   const uint8_t* node_level;    // per slot: level inside its chunk (0 = the chunk's first level)
-  const int32_t* inl_src;       // per inlet edge: producer chunk
+  const int32_t* inl_src;       // per inlet edge: outlet number of the producer
   const uint8_t* inl_level;     // per inlet edge: level (inside the chunk) of the receiving node
 };
 

@@ -328,24 +328,31 @@ bool build_artifacts(Network& nw, int nthreads, int min_sto, const int64_t* so_o
   return true;
 }
 
-void build_chunks(Network& nw, int64_t cap) {
+void build_chunks(Network& nw, int64_t cap, int64_t piece_depth) {
   const int64_t n = nw.n;
   if (cap < 1) cap = 1;
-  // Bottom-up (upstream first): acc[v] = size of the not-yet-cut upstream tree of v. A chunk
-  // may hold at most `cap` nodes (one node per thread of the CTA that walks it), so when the
+  std::vector<int64_t> dist(n, 0);
+  for (int64_t k = n - 1; k >= 0; --k) {
+    const int64_t v = nw.order[k] - 1, d = nw.down[v];
+    dist[v] = d ? dist[d - 1] + 1 : 0;
+  }
+  // Bottom-up (upstream first): acc[v] = size of the not-yet-cut upstream tree of v. A piece
+  // may hold at most `cap` nodes (one node per lane of the warp that walks it), so when the
   // tree rooted at v would exceed the cap its largest uncut children are cut off (each becomes
-  // a chunk of its own) until it fits. Every pit closes a chunk.
+  // the root of a piece of its own) until it fits. Pits and, with piece_depth > 0, the nodes at
+  // a multiple of piece_depth from their outlet are roots as well.
   std::vector<int64_t> acc(n, 1);
   std::vector<uint8_t> cut(n, 0);
   std::vector<std::pair<int64_t, int64_t>> kids;
   for (int64_t k = 0; k < n; ++k) {
     const int64_t v = nw.order[k] - 1;
     int64_t total = 1;
-    for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e) total += acc[nw.in_idx[e] - 1];
+    for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e)
+      if (!cut[nw.in_idx[e] - 1]) total += acc[nw.in_idx[e] - 1];
     if (total > cap) {
       kids.clear();
       for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e)
-        kids.emplace_back(acc[nw.in_idx[e] - 1], nw.in_idx[e] - 1);
+        if (!cut[nw.in_idx[e] - 1]) kids.emplace_back(acc[nw.in_idx[e] - 1], nw.in_idx[e] - 1);
       std::sort(kids.begin(), kids.end(), [](const auto& a, const auto& b) {
         return a.first != b.first ? a.first > b.first : a.second < b.second;
       });
@@ -356,24 +363,35 @@ void build_chunks(Network& nw, int64_t cap) {
       }
     }
     acc[v] = total;
-    if (nw.down[v] == 0) cut[v] = 1;
+    if (nw.down[v] == 0 || (piece_depth > 0 && dist[v] % piece_depth == 0)) cut[v] = 1;
   }
-  // chunk outlets in execution order: ascending outlet level, then node id. A producer's outlet
-  // is exactly one level above its consumer's receiving node, so this is a topological order
-  // of the chunk DAG (dynamic scheduling in this order cannot deadlock).
-  std::vector<int64_t> outlets;
+  // piece roots in execution order: ascending root level, then node id. A producer's root is
+  // exactly one level above the node it feeds, which lies at or above its consumer's root
+  // level, so this is a topological order of the piece DAG and of the chunks packed from it
+  // (dynamic scheduling in this order cannot deadlock).
+  std::vector<int64_t> roots;
   for (int64_t v = 0; v < n; ++v)
-    if (cut[v]) outlets.push_back(v);
-  std::sort(outlets.begin(), outlets.end(), [&](int64_t a, int64_t b) {
+    if (cut[v]) roots.push_back(v);
+  std::sort(roots.begin(), roots.end(), [&](int64_t a, int64_t b) {
     return nw.node_level[a] != nw.node_level[b] ? nw.node_level[a] < nw.node_level[b] : a < b;
   });
-  nw.n_chunks = (int64_t)outlets.size();
+  // pack: consecutive pieces with the same root level share a chunk while they fit
   nw.chunk_of_node.assign(n, -1);
-  nw.chunk_outlet.assign(nw.n_chunks, 0);
-  for (int64_t c = 0; c < nw.n_chunks; ++c) {
-    nw.chunk_of_node[outlets[c]] = c;
-    nw.chunk_outlet[c] = outlets[c] + 1;
+  nw.chunk_outlet.assign(roots.size(), 0);
+  nw.out_of_node.assign(n, -1);
+  nw.n_outlets = 0;
+  int64_t nc = 0, fill = 0, cur_level = -1;
+  for (size_t i = 0; i < roots.size(); ++i) {
+    const int64_t r = roots[i];
+    const bool join = piece_depth > 0 && nc > 0 && nw.node_level[r] == cur_level &&
+                      fill + acc[r] <= cap;
+    if (!join) { ++nc; fill = 0; cur_level = nw.node_level[r]; }
+    fill += acc[r];
+    nw.chunk_of_node[r] = nc - 1;
+    nw.chunk_outlet[i] = r + 1;
+    if (nw.down[r] != 0) nw.out_of_node[r] = nw.n_outlets++;
   }
+  nw.n_chunks = nc;
   for (int64_t k = n - 1; k >= 0; --k) {  // downstream -> upstream
     const int64_t v = nw.order[k] - 1;
     if (!cut[v]) nw.chunk_of_node[v] = nw.chunk_of_node[nw.down[v] - 1];
@@ -397,14 +415,16 @@ void build_chunks(Network& nw, int64_t cap) {
   int64_t p = 0;
   for (int64_t c = 0; c < nw.n_chunks; ++c) {
     nw.chunk_ptr[c] = p;
+    int64_t q = p;
+    while (q < n && nw.chunk_of_node[nodes[q]] == c) ++q;
     const int64_t l0 = nw.node_level[nodes[p]];
-    const int64_t l1 = nw.node_level[outlets[c]];
+    const int64_t l1 = nw.node_level[nodes[q - 1]];  // slots are level-ascending inside a chunk
     nw.chunk_l0[c] = l0;
     nw.chunk_l1[c] = l1;
     nw.chunk_clp_off[c] = (int64_t)nw.clp.size();
     for (int64_t l = l0; l <= l1; ++l) {
       nw.clp.push_back(p);
-      while (p < n && nw.chunk_of_node[nodes[p]] == c && nw.node_level[nodes[p]] == l) ++p;
+      while (p < q && nw.node_level[nodes[p]] == l) ++p;
     }
     nw.clp.push_back(p);
   }

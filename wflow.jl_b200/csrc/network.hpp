@@ -32,8 +32,10 @@ struct Network {
   std::vector<int64_t> up_ptr, up_idx; // upstream_nodes by toposort position
   // sub-domain partition (order_of_subdomains / order_subdomain / subdomain_indices)
   std::vector<int64_t> lvl_ptr, lvl_idx, sub_ptr, sub_order, sub_indices;
-  // B200 wavefront: topological-depth levels, and the partition of the forest into CHUNKS
-  // (connected pieces with one outlet node each) that one CTA walks on its own.
+  // B200 wavefront: topological-depth levels, and the partition of the forest into CHUNKS of
+  // at most 32 nodes that one warp walks on its own. A chunk holds one or more PIECES: connected
+  // parts of the forest with one outlet node (root) each; the roots that drain into another
+  // chunk publish their discharge (outlet numbers, in execution order of the chunks).
   int64_t n_wave_levels = 0;
   std::vector<int64_t> wave_level_ptr; // histogram offsets of the levels (n_wave_levels + 1)
   std::vector<int64_t> node_level;     // node id - 1 -> level
@@ -44,7 +46,9 @@ struct Network {
   std::vector<int64_t> chunk_of_node;  // node id - 1 -> chunk (in execution order)
   std::vector<int64_t> chunk_ptr;      // n_chunks + 1 slot offsets
   std::vector<int64_t> chunk_l0, chunk_l1;  // first / last (= outlet) level of a chunk
-  std::vector<int64_t> chunk_outlet;   // outlet node id (1-based)
+  std::vector<int64_t> chunk_outlet;   // root node ids (1-based) of all pieces, in chunk order
+  std::vector<int64_t> out_of_node;    // node id - 1 -> outlet number, -1 if it does not publish
+  int64_t n_outlets = 0;
   std::vector<int64_t> chunk_clp_off;  // n_chunks + 1 offsets into clp
   std::vector<int64_t> clp;            // per chunk: (l1 - l0 + 2) absolute slot offsets of its levels
   // B200 single-sub-step wavefront (subsurface flow): BANDS of `band_depth` consecutive levels.
@@ -73,10 +77,14 @@ bool build_graph(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, co
 // order, stream order (unless `streamorder_override` given), upstream CSR, partition, wavefront.
 bool build_artifacts(Network& nw, int nthreads, int min_streamorder,
                      const int64_t* streamorder_override, std::string& err);
-// Partition into chunks of at most `cap` nodes (bottom-up: when the not-yet-cut upstream tree
-// of a node would exceed the cap its largest children are cut off; every pit closes a chunk)
-// and derive the device slot order.
-void build_chunks(Network& nw, int64_t cap);
+// Cut the forest into pieces of at most `cap` nodes (bottom-up: when the not-yet-cut upstream
+// tree of a node would exceed the cap its largest children are cut off; every pit closes a
+// piece) and, with piece_depth > 0, of at most piece_depth levels (every node whose distance to
+// its outlet is a multiple of piece_depth closes a piece); pack pieces with the same root level
+// into chunks of at most `cap` nodes (piece_depth == 0: one piece per chunk); derive the device
+// slot order (chunk, level, node id). Shallow chunks keep the lanes of a warp busy: a chunk of
+// L levels walks L - 1 + S stages for S sub-steps.
+void build_chunks(Network& nw, int64_t cap, int64_t piece_depth);
 // Bands / fragments / bundles of the single-sub-step wavefront (see Network).
 void build_bands(Network& nw, int64_t depth);
 
