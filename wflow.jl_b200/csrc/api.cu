@@ -153,9 +153,17 @@ struct WflowB200 {
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
   unsigned* d_queue = nullptr;
-  UnsatWork unsat{};                 // scratch of the unsaturated-zone engine (vertical.cu)
+  std::vector<UnsatWork> unsat;      // scratch of the unsaturated-zone engine, per slice
   double* d_unsat_pool = nullptr;
+  int32_t* d_unsat_its = nullptr;
+  int32_t* d_unsat_list = nullptr;
+  unsigned* d_unsat_count = nullptr;
   int engine_grid = 0;
+  cudaStream_t side_stream[WFB_V_SIDE_STREAMS] = {};  // high priority: the loop engines
+  cudaEvent_t v_ev[32] = {};
+  cudaGraphExec_t v_graph = nullptr;  // the vertical update of one step, captured once per dt
+  double v_graph_dt = 0.0;
+  int v_graph_launches = 0;
   RoutingStats* d_stats = nullptr;
   unsigned long long* d_count = nullptr;
   double* d_min = nullptr;
@@ -461,6 +469,42 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
 
 }  // namespace
 
+// update_land_hydrology_model! as ONE graph launch: the slices, their engine rounds on the side
+// streams and the ordering events (~50 kernel launches and memsets per step) are captured once
+// per time step length; issuing them one by one costs more host time than the GPU needs.
+static int32_t launch_vertical(WflowB200* h, double dt) {
+  if (getenv("WFB_NO_GRAPH")) {  // developer aid
+    return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(),
+                                                 (int)h->unsat.size(), h->engine_grid, h->stream,
+                                                 h->side_stream, h->v_ev),
+                        "update_land_hydrology_model");
+  }
+  if (!h->v_graph || h->v_graph_dt != dt) {
+    if (h->v_graph) { cudaGraphExecDestroy(h->v_graph); h->v_graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
+                                         h->engine_grid, h->stream, h->side_stream, h->v_ev);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc < 0 || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      return fail(h, WFLOWB200_ERR_CUDA, std::string("update_land_hydrology_model: graph capture failed: ") +
+                                             cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&h->v_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      h->v_graph = nullptr;
+      return fail(h, WFLOWB200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    h->v_graph_dt = dt;
+    h->v_graph_launches = rc;
+  }
+  CUDA_TRY(h, cudaGraphLaunch(h->v_graph, h->stream));
+  h->launches += h->v_graph_launches;
+  return WFLOWB200_OK;
+}
+
 #ifdef WFB_NEWTON_HIST
 namespace wfb { void dump_newton_hist(); }
 #endif
@@ -603,19 +647,39 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
   {
     const size_t ns = (size_t)h->ns;
+    // Slices > 1 put the loop engine of a slice on a side stream under the elementwise kernels
+    // of the others (vertical.cu). Measured on B200 (1000^2): 0.610 ms with one slice, 0.583 with
+    // two, 0.60-0.63 with four to eight -- the engine tails do not overlap enough to pay for the
+    // extra launches, so one slice (one stream, no events) is the default.
+    const char* vs = getenv("WFB_V_SLICES");
+    const int n_slices = std::max(1, std::min(16, vs ? atoi(vs) : 1));
+    const size_t per = ((ns + n_slices - 1) / n_slices + 127) / 128 * 128;  // cells per slice
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_pool, 5 * ns * sizeof(double)));
-    UnsatWork& u = h->unsat;
-    u.usd = h->d_unsat_pool; u.sum_ast = u.usd + ns; u.kv_it = u.sum_ast + ns;
-    u.l_sat = u.kv_it + ns; u.c = u.l_sat + ns;
-    TRY_CREATE(cudaMalloc((void**)&u.its_layer, ns * sizeof(int32_t)));
-    TRY_CREATE(cudaMalloc((void**)&u.list, 2 * WFB_UNSAT_BUCKETS * ns * sizeof(int32_t)));
-    TRY_CREATE(cudaMalloc((void**)&u.count, 2 * WFB_UNSAT_BUCKETS * sizeof(unsigned)));
-    u.cap = h->ns;
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_its, ns * sizeof(int32_t)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_list,
+                          (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * per * sizeof(int32_t)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count,
+                          (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * sizeof(unsigned)));
     const char* ii = getenv("WFB_INLINE_ITERS");  // tunable for experiments
-    u.inline_iters = ii ? atoi(ii) : 8;
+    h->unsat.resize(n_slices);
+    for (int k = 0; k < n_slices; ++k) {
+      UnsatWork& u = h->unsat[k];
+      u.usd = h->d_unsat_pool; u.sum_ast = u.usd + ns; u.kv_it = u.sum_ast + ns;
+      u.l_sat = u.kv_it + ns; u.c = u.l_sat + ns;   // per-cell records: shared by the slices
+      u.its_layer = h->d_unsat_its;
+      u.list = h->d_unsat_list + (size_t)k * 2 * WFB_UNSAT_BUCKETS * per;
+      u.count = h->d_unsat_count + (size_t)k * 2 * WFB_UNSAT_BUCKETS;
+      u.cap = (int32_t)per;
+      u.inline_iters = ii ? atoi(ii) : 8;
+    }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     h->engine_grid = std::max(1, sms) * 8;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (auto& st : h->side_stream)
+      TRY_CREATE(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
+    for (auto& e : h->v_ev) TRY_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
@@ -673,8 +737,12 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
-  cudaFree(h->d_unsat_pool); cudaFree(h->unsat.its_layer); cudaFree(h->unsat.list);
-  cudaFree(h->unsat.count);
+  for (auto st : h->side_stream) if (st) cudaStreamSynchronize(st);
+  cudaFree(h->d_unsat_pool); cudaFree(h->d_unsat_its); cudaFree(h->d_unsat_list);
+  cudaFree(h->d_unsat_count);
+  if (h->v_graph) cudaGraphExecDestroy(h->v_graph);
+  for (auto e : h->v_ev) if (e) cudaEventDestroy(e);
+  for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
   cudaFree(h->d_work); cudaFree(h->d_qstate);
   free_domain(h->land); free_domain(h->river);
@@ -801,8 +869,7 @@ int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
   if (h->nriv > 0) {  // river h -> land grid (runoff.jl:77-79)
     if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
   }
-  return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->engine_grid, h->stream),
-                      "update_land_hydrology_model");
+  return launch_vertical(h, dt);
 }
 
 int32_t wflowb200_exchange_recharge(WflowB200* h) {
@@ -929,8 +996,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
     if ((rc = check_launch(h, launch_scatter_river_depth(h->f, h->kc, h->stream), "scatter"))) return rc;
   }
   mark(1);
-  if ((rc = check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->engine_grid, h->stream),
-                         "update_land_hydrology_model"))) return rc;
+  if ((rc = launch_vertical(h, dt))) return rc;
   mark(2);
   if ((rc = wflowb200_exchange_recharge(h))) return rc;
   mark(3);

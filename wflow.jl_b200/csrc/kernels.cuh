@@ -11,6 +11,7 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 // Brooks-Corey loops (one record per cell) and the lists of suspended cells, bucketed by
 // log2(trip count), double-buffered over the engine's rounds.
 #define WFB_UNSAT_BUCKETS 6
+#define WFB_V_SIDE_STREAMS 8
 struct UnsatWork {
   double *usd, *sum_ast, *kv_it, *l_sat, *c;  // ns doubles each
   int32_t* its_layer;                         // ns: trip count | layer << 24
@@ -19,9 +20,13 @@ struct UnsatWork {
   int32_t cap;                                // capacity of one list (= ns)
   int32_t inline_iters;                       // loops up to this many trips run in line
 };
-// engine_grid: CTAs of the persistent engine kernels (a few per SM)
+// engine_grid: CTAs of the persistent engine kernels (a few per SM). The cells are cut into
+// n_slices slices (one UnsatWork each); the loop engine of slice k runs on side[k % WFB_V_SIDE_STREAMS]
+// (high-priority streams) under the elementwise kernels of the next slices on s; ev holds
+// 2 * n_slices events.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork& w, int engine_grid, cudaStream_t s);
+                          const UnsatWork* w, int n_slices, int engine_grid, cudaStream_t s,
+                          cudaStream_t const* side, cudaEvent_t const* ev);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_soil_water_storage(const DevFields& f, const KCfg& c, int n_layers, cudaStream_t s);
 int launch_total_water_storage(const DevFields& f, const KCfg& c, const int32_t* riv_of_land,

@@ -186,9 +186,11 @@ __device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, 
 #endif
 template <int N>
 __global__ void __launch_bounds__(WFB_V_BLOCK, WFB_VA_MINBLOCKS)
-land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.ns) return;     // whole warps (ns is a multiple of 32)
+land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
+                    const int i_begin, const int i_end) {
+  // cells [i_begin, i_end) of one slice; both are multiples of 32 (or i_end = ns)
+  const int i = i_begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= i_end) return;    // whole warps
   // lanes of the padding slots [n, ns) run along on the padding values (they must take part in
   // the warp-aggregated suspension) and never suspend; their stores land in the padding
   const bool live = i < c.n;
@@ -550,9 +552,10 @@ unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const in
 // reference-visible output array (or an input), re-read here.
 template <int N>
 __global__ void __launch_bounds__(WFB_V_BLOCK, WFB_VC_MINBLOCKS)
-soil_column_kernel(const DevFields f, const KCfg c, const double dt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.n) return;
+soil_column_kernel(const DevFields f, const KCfg c, const double dt, const int i_begin,
+                   const int i_end) {
+  const int i = i_begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= i_end || i >= c.n) return;
   const int ns = c.ns;
   const Divisor ddt(dt);
   const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
@@ -872,23 +875,61 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
   return 1;
 }
 
+// The domain is cut into slices. The loop engine of a slice is a latency-bound tail (it lasts
+// as long as the longest Brooks-Corey loop of the slice, with a few hundred busy warps), so it
+// runs on a high-priority side stream UNDER the bandwidth-bound kernels of the next slices:
+//   main:  A0 A1 A2 A3 C0 C1 C2 C3      (A = land_surface_kernel, C = soil_column_kernel)
+//   side:     E0 E1 E2 E3               (E = loop / resume rounds; a cell can be suspended once
+//                                        per layer, hence n_layers rounds)
+// Only the last slice's engine is exposed, and C0 .. C(K-2) run under it.
+// ev[2k] orders E_k after A_k, ev[2k+1] orders C_k after E_k.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork& w, int engine_grid, cudaStream_t s) {
+                          const UnsatWork* w, int n_slices, int engine_grid, cudaStream_t s,
+                          cudaStream_t const* side, cudaEvent_t const* ev) {
   int launches = 0;
-  cudaMemsetAsync(w.count, 0, 2 * kBuckets * sizeof(unsigned), s);
-  const int grid = (c.ns + WFB_V_BLOCK - 1) / WFB_V_BLOCK;
-  WFB_DISPATCH_N(n_layers, (land_surface_kernel<N><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, w, dt)));
-  ++launches;
-  // the suspended loops, then the layers below them: a cell can be suspended once per layer
-  for (int r = 0; r < n_layers; ++r) {
-    const int parity = r & 1;
-    unsat_loop_kernel<<<engine_grid, 128, 0, s>>>(w, parity, dt);
-    if (r > 0) cudaMemsetAsync(w.count + (parity ^ 1) * kBuckets, 0, kBuckets * sizeof(unsigned), s);
-    WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, s>>>(f, c, w, parity, dt)));
-    launches += 2;
+  if (n_slices < 1) n_slices = 1;
+  const int per = ((c.ns + n_slices - 1) / n_slices + 127) / 128 * 128;
+  auto range = [&](int k, int& i0, int& i1) {
+    i0 = k * per;
+    i1 = (k + 1) * per < c.ns ? (k + 1) * per : c.ns;
+    return i0 < i1;
+  };
+  auto second_half = [&](int k) {
+    int i0, i1;
+    if (!range(k, i0, i1)) return;
+    if (n_slices > 1) cudaStreamWaitEvent(s, ev[2 * k + 1], 0);
+    const int grid = (i1 - i0 + WFB_V_BLOCK - 1) / WFB_V_BLOCK;
+    switch (n_layers) {
+#define WFB_CASE(NN) case NN: soil_column_kernel<NN><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, dt, i0, i1); break;
+      WFB_CASE(1) WFB_CASE(2) WFB_CASE(3) WFB_CASE(4) WFB_CASE(5) WFB_CASE(6) WFB_CASE(7) WFB_CASE(8)
+#undef WFB_CASE
+    }
+    ++launches;
+  };
+  for (int k = 0; k < n_slices; ++k) {
+    int i0, i1;
+    if (!range(k, i0, i1)) break;
+    cudaMemsetAsync(w[k].count, 0, 2 * kBuckets * sizeof(unsigned), s);
+    const int grid = (i1 - i0 + WFB_V_BLOCK - 1) / WFB_V_BLOCK;
+    WFB_DISPATCH_N(n_layers, (land_surface_kernel<N><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, w[k], dt, i0, i1)));
+    ++launches;
+    cudaStream_t e = n_slices > 1 ? side[k % WFB_V_SIDE_STREAMS] : s;
+    if (n_slices > 1) {
+      cudaEventRecord(ev[2 * k], s);
+      cudaStreamWaitEvent(e, ev[2 * k], 0);
+    }
+    for (int r = 0; r < n_layers; ++r) {
+      const int parity = r & 1;
+      unsat_loop_kernel<<<engine_grid, 128, 0, e>>>(w[k], parity, dt);
+      if (r > 0)
+        cudaMemsetAsync(w[k].count + (parity ^ 1) * kBuckets, 0, kBuckets * sizeof(unsigned), e);
+      WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], parity, dt)));
+      launches += 2;
+    }
+    if (n_slices > 1) cudaEventRecord(ev[2 * k + 1], e);
   }
-  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, dt)));
-  return launches + 1;
+  for (int k = 0; k < n_slices; ++k) second_half(k);
+  return launches;
 }
 
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s) {
