@@ -30,6 +30,7 @@ from __graft_entry__ import load_pkg  # noqa: E402
 
 METRIC = "cell-timesteps/s (SBM vertical + kinwave)"
 ADAPTIVE = False
+V1_DRAM_BYTES_PER_CELL = 1477  # measured (ncu), see roofline.traffic_source
 UNIT = "cell-timesteps/s"
 
 
@@ -335,7 +336,15 @@ def main():
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_cell": v1_bytes_per_cell(N, cfg),
-                     "ms_per_launch": v1_ms, "traffic": None},
+                     "ms_per_launch": v1_ms,
+                     # DRAM bytes of the same kernels from the ncu --set full captures under
+                     # profiles/ (r1e: land_surface 719 MB + loop engine 71 MB, r1c: soil_column
+                     # 687 MB per 1e6 cells and step), over the live-measured duration
+                     "traffic": (V1_DRAM_BYTES_PER_CELL * n / (v1_ms * 1e-3) / 1e9
+                                 if v1_ms > 0 and N == 4 and cfg["gash"] and cfg["snow"] else None),
+                     "traffic_bytes_per_cell": V1_DRAM_BYTES_PER_CELL,
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                       "profiles/r1e_vertical_ncu.md + r1c_vertical_ncu.md"},
         "stage_ms_per_step": stage_ms,
         "routing": {"newton_calls": st["newton_calls_land"] + st["newton_calls_river"],
                     "newton_iters_booked": st["newton_iters_land"] + st["newton_iters_river"]},
