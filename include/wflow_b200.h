@@ -166,6 +166,13 @@ int32_t wflowb200_update_total_water_storage(WflowB200* h);
 /* update_model!(model::AbstractModel{<:SbmModel}): all of the above, in order, state resident
  * on the device                                                          sbm_model.jl:60-92 */
 int32_t wflowb200_update_model(WflowB200* h, double dt);
+/* Self-test of the device arithmetic the kernels are built on (csrc/device_math.cuh), over n
+ * pseudo-random arguments: out6 = { max ulp distance fexp vs exp, flog vs log, max relative
+ * difference of pow(x, c) = exp(c log x) for x in (0, 1], c in [1, 40], max ulp distance of the
+ * guard-free division vs IEEE `/`, of the branch-free Julia min/max vs their definition, max
+ * |difference| of cld(x, 2e-4) vs Julia's formula }. No handle needed. */
+int32_t wflowb200_selftest_math(int32_t device, int64_t n, double* out6);
+
 /* block until all device work of this handle is done */
 int32_t wflowb200_synchronize(WflowB200* h);
 

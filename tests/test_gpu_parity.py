@@ -57,6 +57,22 @@ def test_adaptive_internal_time_steps_match_oracle(pkg, dt):
     _close(gpu)
 
 
+def test_device_math_selftest(pkg):
+    """device_math.cuh on the device: table-driven exp / log within 2 ulp of libdevice's (each is
+    < 1 ulp from the correctly rounded value), pow(x, c) within 2e-13 relative, the guard-free
+    division bit-identical to IEEE `/`, branch-free min/max identical to Julia's definition
+    (NaN propagation), cld(x, 2e-4) identical to Julia's formula."""
+    import ctypes as C
+    out = (C.c_double * 6)()
+    rc = pkg._lib.lib().wflowb200_selftest_math(0, 1 << 24, out)
+    assert rc == 0
+    w_exp, w_log, w_pow, w_div, w_mm, w_cld = list(out)
+    print("selftest", list(out))
+    assert w_exp <= 2 and w_log <= 2
+    assert w_pow <= 2e-13
+    assert w_div == 0 and w_mm == 0 and w_cld == 0
+
+
 def test_fine_grained_entry_points_match_oracle(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 40, 50, steps=2, seed=3, fine_grained=True)
     parity.compare_models(gpu, ora)

@@ -99,6 +99,7 @@ def lib():
     L.wflowb200_set_timing.argtypes = [vp, i32]
     L.wflowb200_timer_start.argtypes = [vp]
     L.wflowb200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    L.wflowb200_selftest_math.argtypes = [i32, i64, C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -1023,6 +1023,21 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   return WFLOWB200_OK;
 }
 
+int32_t wflowb200_selftest_math(int32_t device, int64_t n, double* out6) {
+  if (!out6 || n <= 0) return WFLOWB200_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess)
+    return fail(nullptr, WFLOWB200_ERR_CUDA, "no CUDA device: libwflow_b200 has no CPU fallback");
+  unsigned long long* d = nullptr;
+  if (cudaMalloc((void**)&d, 6 * sizeof(unsigned long long)) != cudaSuccess)
+    return fail(nullptr, WFLOWB200_ERR_CUDA, "cudaMalloc failed");
+  cudaMemset(d, 0, 6 * sizeof(unsigned long long));
+  launch_selftest_math(n, d, nullptr);
+  const cudaError_t e = cudaMemcpy(out6, d, 6 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(nullptr, WFLOWB200_ERR_CUDA, cudaGetErrorString(e));
+  return WFLOWB200_OK;
+}
+
 int32_t wflowb200_synchronize(WflowB200* h) {
   if (!h) return WFLOWB200_ERR_ARG;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));

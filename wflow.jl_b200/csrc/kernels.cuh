@@ -27,6 +27,8 @@ struct UnsatWork {
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, int engine_grid, cudaStream_t s,
                           cudaStream_t const* side, cudaEvent_t const* ev);
+// self-test of device_math.cuh: out[6] (device, zeroed) receives bit patterns of the maxima
+int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_soil_water_storage(const DevFields& f, const KCfg& c, int n_layers, cudaStream_t s);
 int launch_total_water_storage(const DevFields& f, const KCfg& c, const int32_t* riv_of_land,

@@ -72,11 +72,18 @@ __device__ __forceinline__ UnsatTask unsatzone_flow_setup(double usd, double kv_
   t.kv_it = its > 0 ? fdiv(kv_z, (double)its) : 0.0;
   return t;
 }
+// FAST: table-driven pow (device_math.cuh). Measured in the loop engine on B200: no change
+// (64 + 58 us for the two loop rounds with either pow), so the default keeps one numeric path.
+#ifndef WFB_ENGINE_FAST_POW
+#define WFB_ENGINE_FAST_POW 0
+#endif
+template <bool FAST>
 __device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt, const Divisor& ddt) {
   double usd = t.usd, sum_ast = t.sum_ast;
   const Divisor dl(t.l_sat);
   for (int k = 0; k < t.its; ++k) {
-    const double st = t.kv_it * bounded_power(usd / dl, t.c);
+    const double st = t.kv_it * (FAST ? bounded_power_fast(usd / dl, t.c)
+                                      : bounded_power(usd / dl, t.c));
     const double st_max = usd / ddt;
     if (st < st_max) { usd -= st * dt; sum_ast += st; }
     else { usd = 0.0; sum_ast += st_max; break; }
@@ -161,7 +168,7 @@ __device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, 
       if (t.its > w.inline_iters) {
         suspended = true; k_susp = k; t_susp = t;
       } else {
-        unsatzone_flow_iterate(t, dt, ddt);
+        unsatzone_flow_iterate<false>(t, dt, ddt);
         uld[k] = t.usd;
         flow = t.sum_ast;
       }
@@ -486,7 +493,7 @@ unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
       UnsatTask t;
       t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
       t.c = w.c[i]; t.its = w.its_layer[i] & 0xffffff;
-      unsatzone_flow_iterate(t, dt, ddt);
+      unsatzone_flow_iterate<WFB_ENGINE_FAST_POW != 0>(t, dt, ddt);
       w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast;
     }
   }
@@ -853,6 +860,70 @@ total_water_storage_kernel(const DevFields f, const KCfg c, const int32_t* __res
   const double lateral = f.olf_h[i] * (1.0 - f.river_fraction[i]);
   total += sub_surface + lateral;
   f.total_storage[i] = total;
+}
+
+// ---- self-test of device_math.cuh (wflowb200_selftest_math) ----------------------------------
+// Largest distance, in units in the last place, between flog / fexp and libdevice's log / exp
+// (both are < 1 ulp from the correctly rounded value), the largest relative difference of
+// jpow(x, c) for x in (0, 1], c in [1, 40] against exp(c log x), and checks of fdiv, jmin, jmax
+// and jcld_pos against the plain formulations.
+__device__ __forceinline__ double ulp_dist(double a, double b) {
+  if (a == b || (a != a && b != b)) return 0.0;
+  if (a != a || b != b) return 1e300;
+  const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+  if ((ia < 0) != (ib < 0)) return 1e300;
+  const long long d = ia - ib;
+  return (double)(d < 0 ? -d : d);
+}
+__device__ __forceinline__ double u01_hash(unsigned long long i, unsigned long long salt) {
+  unsigned long long z = (i + 1) * 0x9E3779B97F4A7C15ull + salt * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+__global__ void selftest_math_kernel(long long n, unsigned long long* out) {
+  double w_exp = 0.0, w_log = 0.0, w_pow = 0.0, w_div = 0.0, w_mm = 0.0, w_cld = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double u = u01_hash(i, 1), v = u01_hash(i, 2), t = u01_hash(i, 3);
+    // exp over the whole finite range, log over 600 decades and close to 1
+    const double xe = -745.0 + 1455.0 * u;
+    w_exp = fmax(w_exp, ulp_dist(fexp(xe), exp(xe)));
+    double xl = exp((u - 0.5) * 1380.0);
+    if ((i & 3) == 1) xl = 1.0 + (v - 0.5) * 0.0625 * t;
+    if ((i & 3) == 2) xl = 1.0 - ldexp(v, -(int)(t * 52.0));
+    w_log = fmax(w_log, ulp_dist(flog(xl), log(xl)));
+    const double xp = (i & 1) ? v : 1.0 - v * v * v, cp = 1.0 + 39.0 * t;
+    const double want = exp(cp * log(xp)), got = jpow_fast(xp, cp);
+    if (want > 1e-290) w_pow = fmax(w_pow, fabs(got - want) / want);
+    // fdiv == IEEE division for normal operands; zero numerator gives zero
+    const double a = (i % 7 == 0) ? 0.0 : ldexp(0.5 + u, (int)(v * 600.0) - 300);
+    const double bb = ldexp(0.5 + t, (int)(u * 400.0) - 200);
+    w_div = fmax(w_div, ulp_dist(fdiv(a, bb), a / bb));
+    w_div = fmax(w_div, ulp_dist(a / Divisor(bb), a / bb));
+    // jmin / jmax against the branchy Julia formulation (NaN propagation)
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double ma = (i % 11 == 0) ? nan : u - 0.5, mb = (i % 13 == 0) ? nan : v - 0.5;
+    const double rmin = (ma != ma || mb != mb) ? nan : (ma < mb ? ma : mb);
+    const double rmax = (ma != ma || mb != mb) ? nan : (ma > mb ? ma : mb);
+    w_mm = fmax(w_mm, ulp_dist(jmin(ma, mb), rmin));
+    w_mm = fmax(w_mm, ulp_dist(jmax(ma, mb), rmax));
+    // cld(x, 2e-4) against Julia's round((x - mod(x, -y)) / y)
+    double xc = u * 0.3;
+    if ((i & 7) == 3) xc = 2e-4 * (double)(1 + (int)(v * 1000.0));
+    w_cld = fmax(w_cld, fabs(jcld_pos(xc, 2e-4) - jcld(xc, 2e-4)));
+  }
+  double w[6] = {w_exp, w_log, w_pow, w_div, w_mm, w_cld};
+  for (int q = 0; q < 6; ++q) {
+    for (int o = 16; o > 0; o >>= 1) w[q] = fmax(w[q], __shfl_xor_sync(0xffffffffu, w[q], o));
+    if ((threadIdx.x & 31) == 0)
+      atomicMax(out + q, (unsigned long long)__double_as_longlong(w[q]));  // w >= 0
+  }
+}
+int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s) {
+  selftest_math_kernel<<<148 * 4, 256, 0, s>>>(n, out);
+  return 1;
 }
 
 // ---- launchers ----------------------------------------------------------------------------
