@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
@@ -178,7 +178,7 @@ def run_cpu(pkg, cfg, dom, fields, steps: int, warmup: int, seed: int, first_ste
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1000, help="raster side per GPU")
@@ -249,12 +249,16 @@ def main():
     n, nriv, N, dt = cfg["n"], cfg["nriv"], cfg["N"], cfg["dt"]
     model = pkg.SbmModel(cfg, dom, fields, device=local)
     gid = dom["gid"]
+    if world > 1 or args.no_cpu_baseline:
+        fields = None  # only the cpu_baseline leg needs the host copies again
     # the step's inputs wait in page-locked host memory (the contract's e2e leg copies them from
     # there): the library then copies them straight to the device, without its staging memcpy
     def pin(a):
         return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    # a pool of distinct forcing fields, cycled (bounds the pinned memory of large tiles)
+    n_forcing = min(args.warmup + args.steps, max(4, int(2.0e9 // (24 * max(len(gid), 1)))))
     forcing = [tuple(pin(a) for a in pkg.synthetic.make_forcing(args.seed, s, gid, dt))
-               for s in range(args.warmup + 2 * args.steps)]
+               for s in range(n_forcing)]
 
     def barrier():
         model.synchronize()
@@ -264,7 +268,7 @@ def main():
 
     # warm-up: spin the model up so that soil, overland and river stores are active
     for s in range(args.warmup):
-        model.set_forcing(*forcing[s])
+        model.set_forcing(*forcing[s % len(forcing)])
         model.update_model(dt)
     model.synchronize()
     launches0 = model.stats()["kernel_launches"]
@@ -290,10 +294,15 @@ def main():
     # ---- leg 2: end to end through the public API with HOST buffers ------------------------
     out = None
     barrier()
+    # Double-buffered like a driver that reads step s + 1 while step s runs: the H2D copy of the
+    # NEXT step's forcing is issued right after the step has been enqueued and overlaps its
+    # kernels; every step's inputs are still copied inside the timed region (K copies for K steps).
     t0 = time.perf_counter()
+    model.set_forcing(*forcing[(args.warmup) % len(forcing)])            # H2D, step 0
     for s in range(args.steps):
-        model.set_forcing(*forcing[args.warmup + s])     # H2D of the step's inputs
-        model.update_model(dt)
+        model.update_model(dt)                           # asynchronous
+        if s + 1 < args.steps:
+            model.set_forcing(*forcing[(args.warmup + s + 1) % len(forcing)])  # H2D, step s + 1
         out = model.get("riv_q_average")                 # D2H of the step's result
     model.synchronize()
     e2e_s = time.perf_counter() - t0
