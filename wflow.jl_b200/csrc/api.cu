@@ -998,7 +998,8 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   mark(1);
   if ((rc = launch_vertical(h, dt))) return rc;
   mark(2);
-  if ((rc = wflowb200_exchange_recharge(h))) return rc;
+  // wflowb200_exchange_recharge: soil_column_kernel has already written recharge_rate and the
+  // subsurface water table depth (the separate entry point stays for the fine-grained sequence)
   mark(3);
   if ((rc = wflowb200_update_subsurface_flow_model(h, dt))) return rc;
   mark(4);

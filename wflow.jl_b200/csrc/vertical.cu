@@ -760,7 +760,12 @@ soil_column_kernel(const DevFields f, const KCfg c, const double dt, const int i
   const double deeptransfer = jmin(drainable / ddt, deepksat);
   const double leakage = jmax(0.0, jmin(__ldg(f.maximum_leakage + i), deeptransfer));
   f.actual_leakage[i] = leakage;
-  f.recharge[i] = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
+  const double recharge = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
+  f.recharge[i] = recharge;
+  // the recharge / water-table hand-off to the subsurface flow (sbm_model.jl:74-81), fused:
+  // exchange_recharge_kernel would re-read both arrays
+  f.recharge_rate[i] = recharge;
+  f.ssf_water_table_depth[i] = zi;
   // total AET (soil.jl:1206-1209) + interception (sbm.jl:130)
   double aet = soil_evaporation + transpiration + aeow_river + aeow_land + 0.0;
   aet += interception;
