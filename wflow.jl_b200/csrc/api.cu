@@ -36,6 +36,8 @@ struct DomainDev {
   unsigned long long* q_out = nullptr;  // per chunk x S x NV published outlet values
   size_t q_out_words = 0;
   DevNet dev{};
+  int32_t* chunk_of_slot = nullptr;     // device, land only: slot -> chunk (fused surface kernel)
+  unsigned* chunk_done = nullptr;       // device, land only: per chunk, epoch of its last finalize
   DevBands bands{};                     // land only: single-sub-step subsurface flow
   unsigned long long* band_q_out = nullptr;
 };
@@ -170,6 +172,11 @@ struct WflowB200 {
   double* d_work = nullptr;                 // adaptive sub-stepping: per-node stable time steps
   unsigned long long* d_qstate = nullptr;   // state of the quantile select
   int grid_olf = 0, grid_riv = 0, grid_ssf = 0;
+  int grid_surface = 0;                // overland + river in one kernel
+  size_t smem_surface = 0;
+  unsigned smem_surface_per_warp = 0;
+  bool fuse_surface = true;
+  unsigned surface_epoch = 0;
   int grid_band = 0, warps_band = 0;   // single-sub-step subsurface kernel
   size_t smem_band = 0;
   bool use_bands = true;
@@ -273,6 +280,13 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
   d.dev.n_outlets = (int32_t)nw.n_outlets;
   CUDA_TRY(h, upload_raw(inl_src, &d.dev.inl_src, d.dev_arrays));
   CUDA_TRY(h, upload_raw(inl_level, &d.dev.inl_level, d.dev_arrays));
+  {
+    std::vector<int64_t> cos(n);
+    for (int64_t p = 0; p < n; ++p) cos[p] = nw.chunk_of_node[nw.perm[p] - 1];
+    CUDA_TRY(h, upload_i32(cos, &d.chunk_of_slot, 0));
+    CUDA_TRY(h, cudaMalloc((void**)&d.chunk_done, std::max<size_t>(nw.n_chunks, 1) * sizeof(unsigned)));
+    CUDA_TRY(h, cudaMemset(d.chunk_done, 0, std::max<size_t>(nw.n_chunks, 1) * sizeof(unsigned)));
+  }
   d.dev.n = (int32_t)n;
   d.dev.n_levels = (int32_t)nw.n_wave_levels;
   d.dev.n_chunks = (int32_t)nw.n_chunks;
@@ -308,6 +322,8 @@ int32_t upload_bands(WflowB200* h, DomainDev& d) {
 
 void free_domain(DomainDev& d) {
   cudaFree(d.band_q_out);
+  cudaFree(d.chunk_of_slot);
+  cudaFree(d.chunk_done);
   cudaFree(d.node_of_slot);
   for (void* p : d.dev_arrays) cudaFree(p);
   cudaFree(d.q_out);
@@ -409,6 +425,33 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
       fclose(fp);
     }
   }
+  substeps = S;
+  return WFLOWB200_OK;
+}
+
+// The sub-step plan and buffers of one component, without launching it (fused kernels).
+int32_t prepare_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kind, int nv,
+                     WaveLaunch& w, int64_t& substeps, const char* what) {
+  std::vector<double> dts;
+  const int S = fixed_substeps(dt, dt_fixed, dts);
+  if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, std::string(what) + ": bad internal time step");
+  const size_t need = (size_t)std::max<int64_t>(d.nw.n_outlets, 1) * (size_t)S * (size_t)nv;
+  if (need > d.q_out_words) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d.q_out);
+    d.q_out = nullptr;
+    d.q_out_words = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&d.q_out, need * sizeof(unsigned long long)));
+    d.q_out_words = need;
+  }
+  w = WaveLaunch{};
+  w.queue = h->d_queue + kind * 32;
+  w.q_out = d.q_out;
+  w.stats = h->d_stats;
+  w.S = S;
+  w.dt_fixed = dts[0];
+  w.dt_last = dts[S - 1];
+  w.dt = dt;
   substeps = S;
   return WFLOWB200_OK;
 }
@@ -720,6 +763,13 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       if (h->grid_band <= 0) h->use_bands = false;
     }
   }
+  {
+    h->smem_surface = surface_smem(h->land.dev.max_inlets, h->river.dev.max_inlets,
+                                   &h->smem_surface_per_warp);
+    h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
+    const char* fs = getenv("WFB_FUSE_SURFACE");  // 0: overland and river as separate kernels
+    h->fuse_surface = !(fs && atoi(fs) == 0) && h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive;
+  }
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -980,6 +1030,29 @@ int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
                   }, "update_river_flow_model");
 }
 
+// update_overland_flow_model! + update_lateral_inflow!(river) + update_river_flow_model! in one
+// launch (routing.cu: surface_wave_kernel); same results as the three separate entry points.
+static int32_t update_surface_fused(WflowB200* h, double dt) {
+  WaveLaunch wl{}, wr{};
+  int32_t rc;
+  if ((rc = prepare_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, wl, h->sub_land, "update_overland_flow_model"))) return rc;
+  if ((rc = prepare_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, wr, h->sub_river, "update_river_flow_model"))) return rc;
+  wl.smem = wr.smem = h->smem_surface;
+  wl.smem_per_warp = wr.smem_per_warp = h->smem_surface_per_warp;
+  const int64_t warps_needed = h->land.nw.n_chunks + h->river.nw.n_chunks;
+  wl.grid = wr.grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_surface, (warps_needed + 7) / 8));
+  SurfaceSync sync{};
+  sync.land_done = h->land.chunk_done;
+  sync.epoch = ++h->surface_epoch;
+  sync.land_chunk_of_slot = h->land.chunk_of_slot;
+  const char* rs = getenv("WFB_SURFACE_RIVER_SHARE");  // "share/period", tunable for experiments
+  sync.period = 3; sync.river_share = 1;
+  if (rs) sscanf(rs, "%d/%d", &sync.river_share, &sync.period);
+  if (sync.period < 2 || sync.river_share < 1 || sync.river_share >= sync.period) { sync.period = 3; sync.river_share = 1; }
+  return check_launch(h, launch_surface_wave(h->f, h->kc, h->land.dev, h->river.dev, wl, wr, sync, h->stream),
+                      "update_overland_flow_model + update_river_flow_model");
+}
+
 int32_t wflowb200_update_total_water_storage(WflowB200* h) {
   if (!h) return WFLOWB200_ERR_ARG;
   return check_launch(h, launch_total_water_storage(h->f, h->kc, h->riv_of_land, h->stream),
@@ -1005,11 +1078,17 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   mark(4);
   if ((rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater
   mark(5);
-  if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
-  mark(6);
-  if ((rc = wflowb200_update_lateral_inflow_river(h))) return rc;
-  mark(7);
-  if ((rc = wflowb200_update_river_flow_model(h, dt))) return rc;
+  if (h->fuse_surface) {  // overland and river wavefronts overlapped (timed as "overland")
+    if ((rc = update_surface_fused(h, dt))) return rc;
+    mark(6);
+    mark(7);
+  } else {
+    if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
+    mark(6);
+    if ((rc = wflowb200_update_lateral_inflow_river(h))) return rc;
+    mark(7);
+    if ((rc = wflowb200_update_river_flow_model(h, dt))) return rc;
+  }
   mark(8);
   if ((rc = wflowb200_update_total_water_storage(h))) return rc;
   mark(9);

@@ -52,13 +52,30 @@ struct WaveLaunch {
                               // continues the cumulative fluxes of the previous ones
   int grid;
   size_t smem;                // dynamic shared memory of the kernel (wave_smem)
+  unsigned smem_per_warp;     // bytes of a warp's region (0: the component's own layout);
+                              // set when two components share one kernel
   long long* prof;            // developer aid (WFB_WAVE_PROF): 8 x n_chunks int64 written by
                               // each chunk: start ns, end ns, stages, nodes, barrier-wait cycles
                               // of thread 0, SM id, inlets, busy cycles of the fetch warp
 };
 
+// Overland and river flow in ONE kernel (launch_surface_wave): the warps of the grid are split
+// between the two components; a river chunk starts when the overland flow of its cells' land
+// chunks is final (per-land-chunk flags), so the river wavefront trails the overland wavefront
+// by a few levels instead of starting after it.
+struct SurfaceSync {
+  unsigned* land_done;                 // device: per land chunk, the epoch of its last finalize
+  unsigned epoch;                      // this launch
+  const int32_t* land_chunk_of_slot;   // land slot -> land chunk
+  int period, river_share;             // warp g serves the river if g % period < river_share
+};
 // kind: 0 overland, 1 river, 2 subsurface
 int wave_block();
+size_t surface_smem(int max_inlets_land, int max_inlets_river, unsigned* per_warp);
+int surface_max_grid(size_t smem, int device);
+int launch_surface_wave(const DevFields& f, const KCfg& c, const DevNet& land, const DevNet& river,
+                        const WaveLaunch& wl, const WaveLaunch& wr, const SurfaceSync& sync,
+                        cudaStream_t s);
 size_t wave_smem(int kind, int max_inlets);
 int wave_max_grid(int kind, int n_layers, size_t smem, int device);  // co-resident CTAs
 int launch_overland_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
