@@ -7,6 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/sm
 nproc >> gpurun_out/smi_$TAG.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_$TAG.log 2>&1
 tail -3 gpurun_out/gputests_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 600 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -c 600 gpurun_out/bench_$TAG.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
@@ -20,7 +21,7 @@ WFB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source o
     -o gpurun_out/prof_v1_$TAG python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu2_$TAG.log 2>&1
 WFB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'overland_wave|river_wave|subsurface_wave' -s 30 -c 3 \
+    -k regex:'surface_wave|overland_wave|river_wave|subsurface_wave' -s 20 -c 2 \
     -o gpurun_out/prof_wave_$TAG python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu3_$TAG.log 2>&1
 ls -la gpurun_out | tail -12

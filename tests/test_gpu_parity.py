@@ -73,6 +73,20 @@ def test_device_math_selftest(pkg):
     assert w_div == 0 and w_mm == 0 and w_cld == 0
 
 
+@pytest.mark.parametrize("env", [{"WFB_FUSE_SURFACE": "0"}, {"WFB_FUSE_ROUTING": "1"},
+                                 {"WFB_SSF_S1": "1"}, {"WFB_PIECE_LAND": "6", "WFB_V_SLICES": "4"}])
+def test_alternative_kernel_paths_match_oracle(pkg, monkeypatch, env):
+    """Every kernel organisation behind the same entry point gives the same fields: overland
+    and river as separate kernels (the default fuses them), subsurface + soil storage + overland
+    + river in one kernel, the slim single-sub-step subsurface node, multi-piece chunks with a
+    sliced vertical update (all read at create)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    gpu, ora, cfg = parity.run_pair(pkg, 97, 131, steps=4, seed=29)
+    parity.compare_models(gpu, ora)
+    _close(gpu)
+
+
 def test_fine_grained_entry_points_match_oracle(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 40, 50, steps=2, seed=3, fine_grained=True)
     parity.compare_models(gpu, ora)

@@ -38,6 +38,7 @@ struct DomainDev {
   DevNet dev{};
   int32_t* chunk_of_slot = nullptr;     // device, land only: slot -> chunk (fused surface kernel)
   unsigned* chunk_done = nullptr;       // device, land only: per chunk, epoch of its last finalize
+  unsigned* chunk_ssf_done = nullptr;   // the same for subsurface flow + soil water storage
   DevBands bands{};                     // land only: single-sub-step subsurface flow
   unsigned long long* band_q_out = nullptr;
 };
@@ -176,7 +177,13 @@ struct WflowB200 {
   size_t smem_surface = 0;
   unsigned smem_surface_per_warp = 0;
   bool fuse_surface = true;
+  int grid_ssf_s1 = 0;                 // single-sub-step subsurface kernel with the slim node
+  bool use_ssf_s1 = true;
+  int grid_routing = 0;                // subsurface + soil storage + overland + river in one kernel
+  bool fuse_routing = true;
   unsigned surface_epoch = 0;
+  unsigned long long* ssf_q_out = nullptr;  // outlet values of the subsurface warps (fused routing)
+  size_t ssf_q_out_words = 0;
   int grid_band = 0, warps_band = 0;   // single-sub-step subsurface kernel
   size_t smem_band = 0;
   bool use_bands = true;
@@ -286,6 +293,8 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
     CUDA_TRY(h, upload_i32(cos, &d.chunk_of_slot, 0));
     CUDA_TRY(h, cudaMalloc((void**)&d.chunk_done, std::max<size_t>(nw.n_chunks, 1) * sizeof(unsigned)));
     CUDA_TRY(h, cudaMemset(d.chunk_done, 0, std::max<size_t>(nw.n_chunks, 1) * sizeof(unsigned)));
+    CUDA_TRY(h, cudaMalloc((void**)&d.chunk_ssf_done, std::max<size_t>(nw.n_chunks, 1) * sizeof(unsigned)));
+    CUDA_TRY(h, cudaMemset(d.chunk_ssf_done, 0, std::max<size_t>(nw.n_chunks, 1) * sizeof(unsigned)));
   }
   d.dev.n = (int32_t)n;
   d.dev.n_levels = (int32_t)nw.n_wave_levels;
@@ -324,6 +333,7 @@ void free_domain(DomainDev& d) {
   cudaFree(d.band_q_out);
   cudaFree(d.chunk_of_slot);
   cudaFree(d.chunk_done);
+  cudaFree(d.chunk_ssf_done);
   cudaFree(d.node_of_slot);
   for (void* p : d.dev_arrays) cudaFree(p);
   cudaFree(d.q_out);
@@ -769,6 +779,17 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
     const char* fs = getenv("WFB_FUSE_SURFACE");  // 0: overland and river as separate kernels
     h->fuse_surface = !(fs && atoi(fs) == 0) && h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive;
+    h->grid_ssf_s1 = subsurface_s1_max_grid(h->N, h->smem_ssf, cfg->device);
+    // the slim single-sub-step node halves the registers (2 CTAs per SM) but is twice as slow
+    // on B200 (1000^2: 1.98 vs 0.98 ms, 3536^2: 11.0 vs 4.6 ms): opt-in, kept for the fused kernel
+    const char* s1 = getenv("WFB_SSF_S1");
+    h->use_ssf_s1 = s1 && atoi(s1) != 0 && h->grid_ssf_s1 > 0;
+    h->grid_routing = routing_max_grid(h->N, h->smem_surface, cfg->device);
+    const char* fr = getenv("WFB_FUSE_ROUTING");  // 0: the subsurface flow in a kernel of its own
+    // measured on B200 (1000^2): 2.51 ms for the three components in one kernel at the best warp
+    // split (river 1 / subsurface 3 / overland 4 of 8) against 2.56 ms with the subsurface flow
+    // on its own -- the 2368 resident warps are too few for three wavefronts -- so it is opt-in
+    h->fuse_routing = h->fuse_surface && fr && atoi(fr) != 0 && h->grid_routing > 0;
   }
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
@@ -794,7 +815,7 @@ void wflowb200_destroy(WflowB200* h) {
   for (auto e : h->v_ev) if (e) cudaEventDestroy(e);
   for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
-  cudaFree(h->d_work); cudaFree(h->d_qstate);
+  cudaFree(h->d_work); cudaFree(h->d_qstate); cudaFree(h->ssf_q_out);
   free_domain(h->land); free_domain(h->river);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
   if (h->forcing_consumed) cudaEventDestroy(h->forcing_consumed);
@@ -978,6 +999,14 @@ int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
       return rc;
     }
   }
+  {
+    std::vector<double> dts;
+    if (h->use_ssf_s1 && !getenv("WFB_WAVE_PROF") && fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1)
+      return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf_s1, h->smem_ssf, h->sub_ssf,
+                      [&](const WaveLaunch& w) {
+                        return launch_subsurface_s1(h->f, h->kc, h->land.dev, h->N, w, h->stream);
+                      }, "update_subsurface_flow_model");
+  }
   return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
                   [&](const WaveLaunch& w) {
                     return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
@@ -1053,6 +1082,56 @@ static int32_t update_surface_fused(WflowB200* h, double dt) {
                       "update_overland_flow_model + update_river_flow_model");
 }
 
+// update_subsurface_flow_model! (single sub-step) + update_soil_water_storage! + the overland
+// and river flow in one launch (routing.cu: routing_wave_kernel). Returns 1 (and launches
+// nothing) when the configuration needs the separate kernels.
+static int32_t update_routing_fused(WflowB200* h, double dt, bool* done) {
+  *done = false;
+  std::vector<double> dts;
+  if (!h->fuse_routing || fixed_substeps(dt, h->cfg.dt_ssf, dts) != 1) return WFLOWB200_OK;
+  WaveLaunch ws{}, wl{}, wr{};
+  int32_t rc;
+  // the subsurface and overland flow walk the same land chunks: separate outlet buffers
+  const size_t need_ssf = (size_t)std::max<int64_t>(h->land.nw.n_outlets, 1) * 2;
+  if (need_ssf > h->ssf_q_out_words) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->ssf_q_out);
+    h->ssf_q_out = nullptr;
+    h->ssf_q_out_words = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->ssf_q_out, need_ssf * sizeof(unsigned long long)));
+    h->ssf_q_out_words = need_ssf;
+  }
+  if ((rc = prepare_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, wl, h->sub_land, "update_overland_flow_model"))) return rc;
+  if ((rc = prepare_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, wr, h->sub_river, "update_river_flow_model"))) return rc;
+  ws.queue = h->d_queue + 2 * 32;
+  ws.q_out = h->ssf_q_out;
+  ws.stats = h->d_stats;
+  ws.S = 1;
+  ws.dt_fixed = ws.dt_last = dts[0];
+  ws.dt = dt;
+  h->sub_ssf = 1;
+  ws.smem = wl.smem = wr.smem = h->smem_surface;
+  ws.smem_per_warp = wl.smem_per_warp = wr.smem_per_warp = h->smem_surface_per_warp;
+  SurfaceSync sync{};
+  sync.land_done = h->land.chunk_done;
+  sync.ssf_done = h->land.chunk_ssf_done;
+  sync.epoch = ++h->surface_epoch;
+  sync.land_chunk_of_slot = h->land.chunk_of_slot;
+  sync.period = 8; sync.river_share = 2; sync.ssf_share = 2;
+  const char* rs = getenv("WFB_ROUTING_SHARES");  // "river/ssf/period", tunable for experiments
+  if (rs) sscanf(rs, "%d/%d/%d", &sync.river_share, &sync.ssf_share, &sync.period);
+  if (sync.river_share < 1 || sync.ssf_share < 1 || sync.river_share + sync.ssf_share >= sync.period) {
+    sync.period = 8; sync.river_share = 2; sync.ssf_share = 2;
+  }
+  const int64_t warps_needed = 2 * h->land.nw.n_chunks + h->river.nw.n_chunks;
+  ws.grid = wl.grid = wr.grid =
+      (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_routing, (warps_needed + 7) / 8));
+  rc = check_launch(h, launch_routing_wave(h->f, h->kc, h->land.dev, h->river.dev, h->N, ws, wl, wr, sync, h->stream),
+                    "routing (subsurface + soil storage + overland + river)");
+  *done = rc == WFLOWB200_OK;
+  return rc;
+}
+
 int32_t wflowb200_update_total_water_storage(WflowB200* h) {
   if (!h) return WFLOWB200_ERR_ARG;
   return check_launch(h, launch_total_water_storage(h->f, h->kc, h->riv_of_land, h->stream),
@@ -1074,6 +1153,22 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   // wflowb200_exchange_recharge: soil_column_kernel has already written recharge_rate and the
   // subsurface water table depth (the separate entry point stays for the fine-grained sequence)
   mark(3);
+  bool fused = false;
+  if ((rc = update_routing_fused(h, dt, &fused))) return rc;
+  if (fused) {  // the three wavefronts in one kernel (timed as "subsurface")
+    mark(4); mark(5); mark(6); mark(7); mark(8);
+    if ((rc = wflowb200_update_total_water_storage(h))) return rc;
+    mark(9);
+    if (h->timing) {
+      CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
+      float d[9];
+      for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&d[i], h->ev[i], h->ev[i + 1]);
+      h->ms[0] += d[1]; h->ms[1] += d[3]; h->ms[2] += d[4]; h->ms[3] += d[5]; h->ms[4] += d[7];
+      h->ms[5] += d[8]; h->ms[6] += d[0] + d[2] + d[6];
+      h->timed_steps++;
+    }
+    return WFLOWB200_OK;
+  }
   if ((rc = wflowb200_update_subsurface_flow_model(h, dt))) return rc;
   mark(4);
   if ((rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater

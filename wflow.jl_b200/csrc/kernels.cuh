@@ -65,6 +65,11 @@ struct WaveLaunch {
 // by a few levels instead of starting after it.
 struct SurfaceSync {
   unsigned* land_done;                 // device: per land chunk, the epoch of its last finalize
+  unsigned* ssf_done;                  // device: per land chunk, subsurface flow + soil water
+                                       // storage of its cells are final (nullptr: the
+                                       // subsurface flow ran in a kernel of its own)
+  int ssf_share;                       // warp g serves the subsurface flow if
+                                       // river_share <= g % period < river_share + ssf_share
   unsigned epoch;                      // this launch
   const int32_t* land_chunk_of_slot;   // land slot -> land chunk
   int period, river_share;             // warp g serves the river if g % period < river_share
@@ -76,6 +81,15 @@ int surface_max_grid(size_t smem, int device);
 int launch_surface_wave(const DevFields& f, const KCfg& c, const DevNet& land, const DevNet& river,
                         const WaveLaunch& wl, const WaveLaunch& wr, const SurfaceSync& sync,
                         cudaStream_t s);
+// the single-sub-step subsurface flow with the slim node (about half the registers)
+int subsurface_s1_max_grid(int n_layers, size_t smem, int device);
+int launch_subsurface_s1(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,
+                         const WaveLaunch& w, cudaStream_t s);
+// subsurface flow (single sub-step) + update_soil_water_storage! + overland + river in one kernel
+int routing_max_grid(int n_layers, size_t smem, int device);
+int launch_routing_wave(const DevFields& f, const KCfg& c, const DevNet& land, const DevNet& river,
+                        int n_layers, const WaveLaunch& ws, const WaveLaunch& wl,
+                        const WaveLaunch& wr, const SurfaceSync& sync, cudaStream_t s);
 size_t wave_smem(int kind, int max_inlets);
 int wave_max_grid(int kind, int n_layers, size_t smem, int device);  // co-resident CTAs
 int launch_overland_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
