@@ -48,6 +48,8 @@ struct WaveLaunch {
   int S;                      // number of sub-steps pipelined through the wavefront
   double dt_fixed, dt_last;   // sub-step lengths: S - 1 times dt_fixed, then dt_last
   double dt;                  // model time step (for the averages)
+  int fuse_soil_storage;      // subsurface flow: run update_soil_water_storage! for every cell
+                              // right after its subsurface flow is final (saves a pass over HBM)
   int accumulate;             // adaptive sub-stepping, one launch per sub-step: this launch
                               // continues the cumulative fluxes of the previous ones
   int grid;
