@@ -75,7 +75,8 @@ def test_device_math_selftest(pkg):
 
 @pytest.mark.parametrize("env", [{"WFB_FUSE_SURFACE": "0"}, {"WFB_FUSE_ROUTING": "1"},
                                  {"WFB_SSF_S1": "1"}, {"WFB_PIECE_LAND": "6", "WFB_V_SLICES": "4"},
-                                 {"WFB_FUSE_SOIL_STORAGE": "0"}])
+                                 {"WFB_FUSE_SOIL_STORAGE": "0"}, {"WFB_OVERLAP_SSF": "0"},
+                                 {"WFB_OVERLAP_SSF": "1", "WFB_SSF_OVERLAP_SMS": "40"}])
 def test_alternative_kernel_paths_match_oracle(pkg, monkeypatch, env):
     """Every kernel organisation behind the same entry point gives the same fields: overland
     and river as separate kernels (the default fuses them), subsurface + soil storage + overland

@@ -1101,8 +1101,81 @@ static int32_t update_surface_fused(WflowB200* h, double dt) {
   sync.period = 3; sync.river_share = 1;
   if (rs) sscanf(rs, "%d/%d", &sync.river_share, &sync.period);
   if (sync.period < 2 || sync.river_share < 1 || sync.river_share >= sync.period) { sync.period = 3; sync.river_share = 1; }
-  return check_launch(h, launch_surface_wave(h->f, h->kc, h->land.dev, h->river.dev, wl, wr, sync, h->stream),
+  return check_launch(h, launch_surface_wave(h->f, h->kc, h->land.dev, h->river.dev, wl, wr, sync, false, h->stream),
                       "update_overland_flow_model + update_river_flow_model");
+}
+
+// The subsurface sweep (with update_soil_water_storage! fused into it) and the surface kernel
+// OVERLAPPED: the subsurface kernel runs on part of the SMs and flags every land chunk whose
+// results are final; the surface kernel is launched programmatically dependent (it may start as
+// soon as every CTA of the subsurface grid is resident, so it can only take the SMs that grid
+// leaves free and the subsurface sweep always makes progress: no deadlock), its overland warps
+// wait for their chunk's flag. Three wavefronts then follow each other through the levels.
+static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
+  *done = false;
+  const char* ov = getenv("WFB_OVERLAP_SSF");  // 0 / 1 override
+  const bool wide = h->land.nw.n_wave_levels > 0 &&
+                    h->land.nw.n / h->land.nw.n_wave_levels >= WFB_PIECE_WIDE_LEVEL;
+  const bool want = ov ? atoi(ov) != 0 : !wide;
+  if (!want || !h->fuse_surface || h->cfg.adaptive || h->use_bands || h->use_ssf_s1 ||
+      getenv("WFB_WAVE_PROF"))
+    return WFLOWB200_OK;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+  const char* es = getenv("WFB_SSF_OVERLAP_SMS");  // SMs (= CTAs) of the subsurface sweep
+  int ssf_ctas = es ? atoi(es) : sms / 2;
+  if (ssf_ctas < 1 || ssf_ctas >= sms) ssf_ctas = sms / 2;
+  WaveLaunch ws{}, wl{}, wr{};
+  int32_t rc;
+  if ((rc = prepare_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, wl, h->sub_land, "update_overland_flow_model"))) return rc;
+  if ((rc = prepare_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, wr, h->sub_river, "update_river_flow_model"))) return rc;
+  // the subsurface flow walks the same land chunks as the overland flow: its own outlet buffer
+  std::vector<double> dts;
+  const int S = fixed_substeps(dt, h->cfg.dt_ssf, dts);
+  if (S <= 0) return fail(h, WFLOWB200_ERR_ARG, "update_subsurface_flow_model: bad internal time step");
+  const size_t need_ssf = (size_t)std::max<int64_t>(h->land.nw.n_outlets, 1) * 2 * (size_t)S;
+  if (need_ssf > h->ssf_q_out_words) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->ssf_q_out);
+    h->ssf_q_out = nullptr;
+    h->ssf_q_out_words = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->ssf_q_out, need_ssf * sizeof(unsigned long long)));
+    h->ssf_q_out_words = need_ssf;
+  }
+  ws.queue = h->d_queue + 2 * 32;
+  ws.q_out = h->ssf_q_out;
+  ws.stats = h->d_stats;
+  ws.S = S;
+  ws.dt_fixed = dts[0];
+  ws.dt_last = dts[S - 1];
+  ws.dt = dt;
+  ws.smem = h->smem_ssf;
+  ws.grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ssf_ctas, h->grid_ssf), h->land.nw.n_chunks));
+  ws.fuse_soil_storage = 1;
+  ws.done_flags = h->land.chunk_ssf_done;
+  ws.done_epoch = ++h->surface_epoch;
+  ws.trigger_dependents = 1;
+  h->sub_ssf = S;
+  wl.smem = wr.smem = h->smem_surface;
+  wl.smem_per_warp = wr.smem_per_warp = h->smem_surface_per_warp;
+  const int64_t warps_needed = h->land.nw.n_chunks + h->river.nw.n_chunks;
+  const int64_t room = (int64_t)(sms - ws.grid) * 2;  // two surface CTAs per free SM
+  wl.grid = wr.grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(h->grid_surface, room),
+                                                                 (warps_needed + 7) / 8));
+  SurfaceSync sync{};
+  sync.land_done = h->land.chunk_done;
+  sync.ssf_done = h->land.chunk_ssf_done;
+  sync.epoch = h->surface_epoch;
+  sync.land_chunk_of_slot = h->land.chunk_of_slot;
+  sync.period = 3; sync.river_share = 1;
+  // every reset before the first kernel: nothing may sit between the two launches
+  reset_surface_wave(h->land.dev, h->river.dev, wl, wr, h->stream);
+  if ((rc = check_launch(h, launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, ws, h->stream),
+                         "update_subsurface_flow_model"))) return rc;
+  rc = check_launch(h, launch_surface_wave(h->f, h->kc, h->land.dev, h->river.dev, wl, wr, sync, true, h->stream),
+                    "update_overland_flow_model + update_river_flow_model");
+  *done = rc == WFLOWB200_OK;
+  return rc;
 }
 
 // update_subsurface_flow_model! (single sub-step) + update_soil_water_storage! + the overland
@@ -1178,7 +1251,8 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   mark(3);
   bool fused = false;
   if ((rc = update_routing_fused(h, dt, &fused))) return rc;
-  if (fused) {  // the three wavefronts in one kernel (timed as "subsurface")
+  if (!fused && (rc = update_routing_overlapped(h, dt, &fused))) return rc;
+  if (fused) {  // the three wavefronts overlapped (timed as "subsurface")
     mark(4); mark(5); mark(6); mark(7); mark(8);
     if ((rc = wflowb200_update_total_water_storage(h))) return rc;
     mark(9);

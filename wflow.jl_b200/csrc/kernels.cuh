@@ -48,6 +48,9 @@ struct WaveLaunch {
   int S;                      // number of sub-steps pipelined through the wavefront
   double dt_fixed, dt_last;   // sub-step lengths: S - 1 times dt_fixed, then dt_last
   double dt;                  // model time step (for the averages)
+  unsigned* done_flags;       // subsurface flow overlapped with the surface kernel: per chunk,
+  unsigned done_epoch;        // the epoch stored when the chunk's results are final; the kernel
+  int trigger_dependents;     // then lets the dependent (surface) kernel launch at once
   int fuse_soil_storage;      // subsurface flow: run update_soil_water_storage! for every cell
                               // right after its subsurface flow is final (saves a pass over HBM)
   int accumulate;             // adaptive sub-stepping, one launch per sub-step: this launch
@@ -80,9 +83,14 @@ struct SurfaceSync {
 int wave_block();
 size_t surface_smem(int max_inlets_land, int max_inlets_river, unsigned* per_warp);
 int surface_max_grid(size_t smem, int device);
+// overlap_previous: programmatic dependent launch -- the kernel may start as soon as every CTA
+// of the previous kernel in the stream (the subsurface sweep) has started; it then orders itself
+// after that kernel's results through sync.ssf_done only
 int launch_surface_wave(const DevFields& f, const KCfg& c, const DevNet& land, const DevNet& river,
                         const WaveLaunch& wl, const WaveLaunch& wr, const SurfaceSync& sync,
-                        cudaStream_t s);
+                        bool overlap_previous, cudaStream_t s);
+void reset_surface_wave(const DevNet& land, const DevNet& river, const WaveLaunch& wl,
+                        const WaveLaunch& wr, cudaStream_t s);
 // the single-sub-step subsurface flow with the slim node (about half the registers)
 int subsurface_s1_max_grid(int n_layers, size_t smem, int device);
 int launch_subsurface_s1(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,
