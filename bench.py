@@ -355,6 +355,12 @@ def main():
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, "
                                        "profiles/r1e_vertical_ncu.md + r1c_vertical_ncu.md"},
         "stage_ms_per_step": stage_ms,
+        "stage_note": ("subsurface, soil_storage, overland and river run overlapped (subsurface "
+                       "sweep + surface kernel on disjoint SMs, update_soil_water_storage! inside "
+                       "the sweep): their time is booked under 'subsurface'"
+                       if stage_ms.get("overland", 1.0) < 0.02 else
+                       "overland and river run in one kernel, booked under 'overland'"
+                       if stage_ms.get("river", 1.0) < 0.02 else "stages run back to back"),
         "routing": {"newton_calls": st["newton_calls_land"] + st["newton_calls_river"],
                     "newton_iters_booked": st["newton_iters_land"] + st["newton_iters_river"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * n,

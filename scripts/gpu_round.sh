@@ -21,7 +21,7 @@ WFB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source o
     -o gpurun_out/prof_v1_$TAG python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu2_$TAG.log 2>&1
 WFB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'surface_wave|overland_wave|river_wave|subsurface_wave' -s 20 -c 2 \
+    -k regex:'surface_wave|subsurface_wave' -s 20 -c 2 \
     -o gpurun_out/prof_wave_$TAG python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu3_$TAG.log 2>&1
 ls -la gpurun_out | tail -12
