@@ -1113,9 +1113,12 @@ static int32_t update_surface_fused(WflowB200* h, double dt) {
 // wait for their chunk's flag. Three wavefronts then follow each other through the levels.
 static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   *done = false;
+  // pays while the sweeps are bound by their dependent chains; measured step times with / without
+  // the overlap: 1000^2 2.5 / 3.1 ms, 1500^2 5.03 / 5.21, 2000^2 8.54 / 8.24, 2500^2 12.3 / 12.1,
+  // 3536^2 24.8 / 22.4 -> on below 1750 nodes per level
   const char* ov = getenv("WFB_OVERLAP_SSF");  // 0 / 1 override
   const bool wide = h->land.nw.n_wave_levels > 0 &&
-                    h->land.nw.n / h->land.nw.n_wave_levels >= WFB_PIECE_WIDE_LEVEL;
+                    h->land.nw.n / h->land.nw.n_wave_levels >= WFB_OVERLAP_MAX_LEVEL_WIDTH;
   const bool want = ov ? atoi(ov) != 0 : !wide;
   if (!want || !h->fuse_surface || h->cfg.adaptive || h->use_bands || h->use_ssf_s1 ||
       getenv("WFB_WAVE_PROF"))
@@ -1123,9 +1126,9 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
   const char* es = getenv("WFB_SSF_OVERLAP_SMS");  // SMs (= CTAs) of the subsurface sweep
-  // measured at 1000^2 (routing ms): 44 SMs 2.38, 56: 1.95, 64: 1.91, 74: 2.11, 84: 2.38
-  int ssf_ctas = es ? atoi(es) : (sms * 7) / 16;
-  if (ssf_ctas < 1 || ssf_ctas >= sms) ssf_ctas = (sms * 7) / 16;
+  // measured at 1000^2 (routing ms): 44 SMs 2.38, 52: 1.91, 60: 1.83, 64: 1.89, 74: 2.11, 84: 2.38
+  int ssf_ctas = es ? atoi(es) : (sms * 13) / 32;
+  if (ssf_ctas < 1 || ssf_ctas >= sms) ssf_ctas = (sms * 13) / 32;
   WaveLaunch ws{}, wl{}, wr{};
   int32_t rc;
   if ((rc = prepare_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, wl, h->sub_land, "update_overland_flow_model"))) return rc;

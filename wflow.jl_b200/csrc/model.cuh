@@ -33,6 +33,8 @@ struct DevFields {
 #define WFB_PIECE_DEPTH_LAND_WIDE 6   // land domains with >= WFB_PIECE_WIDE_LEVEL nodes per level
 #define WFB_PIECE_WIDE_LEVEL 2048
 #define WFB_PIECE_DEPTH_RIVER 0
+// the subsurface sweep and the surface kernel run overlapped below this mean level width
+#define WFB_OVERLAP_MAX_LEVEL_WIDTH 1750
 #define WFB_NO_EDGE 0xffu
 struct DevNet {
   int32_t n;                    // nodes
