@@ -9,7 +9,9 @@ echo "host memory ${MEM} GB -> size ${SIZE}"
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1"
 timeout 600 $RUN --master-port 29521 bench.py --gpus $G --steps 20 --warmup 10 > gpurun_out/bench_n${G}.json 2> gpurun_out/bench_n${G}.err
 tail -c 400 gpurun_out/bench_n${G}.json; echo
+if [ -z "$SKIP_BIG" ]; then
 timeout 1200 $RUN --master-port 29522 bench.py --gpus $G --size $SIZE --steps 5 --warmup 6 --no-cpu-baseline > gpurun_out/bench_n${G}_big.json 2> gpurun_out/bench_n${G}_big.err
+fi
 python -c "
 import json
 for f in ('gpurun_out/bench_n${G}.json','gpurun_out/bench_n${G}_big.json'):
