@@ -138,8 +138,38 @@ struct WflowB200Network {
   Network land, river;
 };
 
+// Developer knobs (environment variables, read ONCE at create): kernel organisations that were
+// measured against each other on B200 stay selectable for experiments and for the parity tests.
+struct Tuning {
+  int wave_prof = 0;          // WFB_WAVE_PROF = kind + 1: dump per-chunk timing of that component
+  bool band_prof = false;     // WFB_BAND_PROF: per-bundle timing of the band kernel
+  bool no_graph = false;      // WFB_NO_GRAPH: vertical update launch by launch (for ncu)
+  int fuse_soil_storage = -1; // WFB_FUSE_SOIL_STORAGE: -1 automatic (mean level width)
+  int overlap_ssf = -1;       // WFB_OVERLAP_SSF: -1 automatic (mean level width)
+  int ssf_overlap_sms = 0;    // WFB_SSF_OVERLAP_SMS: 0 = 13/32 of the SMs
+  int river_share = 1, river_period = 3;                  // WFB_SURFACE_RIVER_SHARE "share/period"
+  int r_river = 2, r_ssf = 2, r_period = 8;               // WFB_ROUTING_SHARES "river/ssf/period"
+  void read() {
+    auto geti = [](const char* name, int dflt) {
+      const char* v = getenv(name);
+      return v ? atoi(v) : dflt;
+    };
+    wave_prof = geti("WFB_WAVE_PROF", 0);
+    band_prof = getenv("WFB_BAND_PROF") != nullptr;
+    no_graph = getenv("WFB_NO_GRAPH") != nullptr;
+    fuse_soil_storage = geti("WFB_FUSE_SOIL_STORAGE", -1);
+    overlap_ssf = geti("WFB_OVERLAP_SSF", -1);
+    ssf_overlap_sms = geti("WFB_SSF_OVERLAP_SMS", 0);
+    if (const char* v = getenv("WFB_SURFACE_RIVER_SHARE")) sscanf(v, "%d/%d", &river_share, &river_period);
+    if (river_period < 2 || river_share < 1 || river_share >= river_period) { river_share = 1; river_period = 3; }
+    if (const char* v = getenv("WFB_ROUTING_SHARES")) sscanf(v, "%d/%d/%d", &r_river, &r_ssf, &r_period);
+    if (r_river < 1 || r_ssf < 1 || r_river + r_ssf >= r_period) { r_river = 2; r_ssf = 2; r_period = 8; }
+  }
+};
+
 struct WflowB200 {
   WflowB200Config cfg{};
+  Tuning tune{};
   int n = 0, nriv = 0, N = 0, ns = 0, nrs = 0;
   DomainDev land, river;
   DevFields f{};
@@ -408,8 +438,7 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
   w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
   w.smem = smem;
   w.prof = nullptr;
-  const char* prof_env = getenv("WFB_WAVE_PROF");  // developer aid: dump per-chunk timing
-  const bool prof = prof_env && atoi(prof_env) == kind + 1;
+  const bool prof = h->tune.wave_prof == kind + 1;  // developer aid: dump per-chunk timing
   const size_t prof_words = 8 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1);
   if (prof) {
     CUDA_TRY(h, cudaMalloc((void**)&w.prof, sizeof(long long) * prof_words));
@@ -527,7 +556,7 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
 // streams and the ordering events (~50 kernel launches and memsets per step) are captured once
 // per time step length; issuing them one by one costs more host time than the GPU needs.
 static int32_t launch_vertical(WflowB200* h, double dt) {
-  if (getenv("WFB_NO_GRAPH")) {  // developer aid
+  if (h->tune.no_graph) {  // developer aid
     return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(),
                                                  (int)h->unsat.size(), h->engine_grid, h->stream,
                                                  h->side_stream, h->v_ev),
@@ -601,6 +630,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
 
   WflowB200* h = new WflowB200();
   h->cfg = *cfg;
+  h->tune.read();
   h->n = (int)cfg->n; h->nriv = (int)cfg->nriv; h->N = cfg->n_layers;
   h->ns = (h->n + 31) / 32 * 32;
   h->nrs = (h->nriv + 31) / 32 * 32;
@@ -960,7 +990,7 @@ int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
                              [&](const WaveLaunch& w) {
                                return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
                              }, "update_subsurface_flow_model");
-  if (h->use_bands && !getenv("WFB_WAVE_PROF")) {
+  if (h->use_bands && !h->tune.wave_prof) {
     std::vector<double> dts;
     if (fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1) {  // one sub-step: the band kernel
       BandLaunch w{};
@@ -972,7 +1002,7 @@ int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
       w.grid = (int)std::max<int64_t>(
           1, std::min<int64_t>(h->grid_band, (h->land.nw.n_bundles + w.warps - 1) / w.warps));
       h->sub_ssf = 1;
-      const bool prof = getenv("WFB_BAND_PROF") != nullptr;  // developer aid: per-bundle timing
+      const bool prof = h->tune.band_prof;  // developer aid: per-bundle timing
       const size_t prof_words = 8 * (size_t)std::max<int64_t>(h->land.nw.n_bundles, 1);
       if (prof) {
         CUDA_TRY(h, cudaMalloc((void**)&w.prof, sizeof(long long) * prof_words));
@@ -1002,7 +1032,7 @@ int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
   }
   {
     std::vector<double> dts;
-    if (h->use_ssf_s1 && !getenv("WFB_WAVE_PROF") && fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1)
+    if (h->use_ssf_s1 && !h->tune.wave_prof && fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1)
       return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf_s1, h->smem_ssf, h->sub_ssf,
                       [&](const WaveLaunch& w) {
                         return launch_subsurface_s1(h->f, h->kc, h->land.dev, h->N, w, h->stream);
@@ -1022,11 +1052,10 @@ static int32_t update_subsurface_and_soil_storage(WflowB200* h, double dt, bool*
   // idle (1000^2: -0.05 ms per step); on wide, throughput-bound domains the separate
   // bandwidth-bound kernel is faster (3536^2: +0.8 ms when fused). Same criterion as the piece
   // depth of the chunks: the mean level width.
-  const char* fv = getenv("WFB_FUSE_SOIL_STORAGE");  // 0 / 1 override
   const bool wide = h->land.nw.n_wave_levels > 0 &&
                     h->land.nw.n / h->land.nw.n_wave_levels >= WFB_PIECE_WIDE_LEVEL;
-  const bool want = fv ? atoi(fv) != 0 : !wide;
-  if (h->cfg.adaptive || !want || getenv("WFB_WAVE_PROF") ||
+  const bool want = h->tune.fuse_soil_storage >= 0 ? h->tune.fuse_soil_storage != 0 : !wide;
+  if (h->cfg.adaptive || !want || h->tune.wave_prof ||
       (h->use_bands && h->cfg.dt_ssf >= dt) || h->use_ssf_s1)
     return wflowb200_update_subsurface_flow_model(h, dt);
   *fused = true;
@@ -1097,10 +1126,8 @@ static int32_t update_surface_fused(WflowB200* h, double dt) {
   sync.land_done = h->land.chunk_done;
   sync.epoch = ++h->surface_epoch;
   sync.land_chunk_of_slot = h->land.chunk_of_slot;
-  const char* rs = getenv("WFB_SURFACE_RIVER_SHARE");  // "share/period", tunable for experiments
-  sync.period = 3; sync.river_share = 1;
-  if (rs) sscanf(rs, "%d/%d", &sync.river_share, &sync.period);
-  if (sync.period < 2 || sync.river_share < 1 || sync.river_share >= sync.period) { sync.period = 3; sync.river_share = 1; }
+  sync.period = h->tune.river_period;
+  sync.river_share = h->tune.river_share;
   return check_launch(h, launch_surface_wave(h->f, h->kc, h->land.dev, h->river.dev, wl, wr, sync, false, h->stream),
                       "update_overland_flow_model + update_river_flow_model");
 }
@@ -1116,18 +1143,16 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   // pays while the sweeps are bound by their dependent chains; measured step times with / without
   // the overlap: 1000^2 2.5 / 3.1 ms, 1500^2 5.03 / 5.21, 2000^2 8.54 / 8.24, 2500^2 12.3 / 12.1,
   // 3536^2 24.8 / 22.4 -> on below 1750 nodes per level
-  const char* ov = getenv("WFB_OVERLAP_SSF");  // 0 / 1 override
   const bool wide = h->land.nw.n_wave_levels > 0 &&
                     h->land.nw.n / h->land.nw.n_wave_levels >= WFB_OVERLAP_MAX_LEVEL_WIDTH;
-  const bool want = ov ? atoi(ov) != 0 : !wide;
+  const bool want = h->tune.overlap_ssf >= 0 ? h->tune.overlap_ssf != 0 : !wide;
   if (!want || !h->fuse_surface || h->cfg.adaptive || h->use_bands || h->use_ssf_s1 ||
-      getenv("WFB_WAVE_PROF"))
+      h->tune.wave_prof)
     return WFLOWB200_OK;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-  const char* es = getenv("WFB_SSF_OVERLAP_SMS");  // SMs (= CTAs) of the subsurface sweep
-  // measured at 1000^2 (routing ms): 44 SMs 2.38, 52: 1.91, 60: 1.83, 64: 1.89, 74: 2.11, 84: 2.38
-  int ssf_ctas = es ? atoi(es) : (sms * 13) / 32;
+  // SMs (= CTAs) of the subsurface sweep; measured at 1000^2 (routing ms): 44 SMs 2.38, 52: 1.91, 60: 1.83, 64: 1.89, 74: 2.11, 84: 2.38
+  int ssf_ctas = h->tune.ssf_overlap_sms > 0 ? h->tune.ssf_overlap_sms : (sms * 13) / 32;
   if (ssf_ctas < 1 || ssf_ctas >= sms) ssf_ctas = (sms * 13) / 32;
   WaveLaunch ws{}, wl{}, wr{};
   int32_t rc;
@@ -1171,7 +1196,8 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   sync.ssf_done = h->land.chunk_ssf_done;
   sync.epoch = h->surface_epoch;
   sync.land_chunk_of_slot = h->land.chunk_of_slot;
-  sync.period = 3; sync.river_share = 1;
+  sync.period = h->tune.river_period;
+  sync.river_share = h->tune.river_share;
   // every reset before the first kernel: nothing may sit between the two launches
   reset_surface_wave(h->land.dev, h->river.dev, wl, wr, h->stream);
   if ((rc = check_launch(h, launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, ws, h->stream),
@@ -1217,12 +1243,7 @@ static int32_t update_routing_fused(WflowB200* h, double dt, bool* done) {
   sync.ssf_done = h->land.chunk_ssf_done;
   sync.epoch = ++h->surface_epoch;
   sync.land_chunk_of_slot = h->land.chunk_of_slot;
-  sync.period = 8; sync.river_share = 2; sync.ssf_share = 2;
-  const char* rs = getenv("WFB_ROUTING_SHARES");  // "river/ssf/period", tunable for experiments
-  if (rs) sscanf(rs, "%d/%d/%d", &sync.river_share, &sync.ssf_share, &sync.period);
-  if (sync.river_share < 1 || sync.ssf_share < 1 || sync.river_share + sync.ssf_share >= sync.period) {
-    sync.period = 8; sync.river_share = 2; sync.ssf_share = 2;
-  }
+  sync.period = h->tune.r_period; sync.river_share = h->tune.r_river; sync.ssf_share = h->tune.r_ssf;
   const int64_t warps_needed = 2 * h->land.nw.n_chunks + h->river.nw.n_chunks;
   ws.grid = wl.grid = wr.grid =
       (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_routing, (warps_needed + 7) / 8));
@@ -1236,6 +1257,18 @@ int32_t wflowb200_update_total_water_storage(WflowB200* h) {
   if (!h) return WFLOWB200_ERR_ARG;
   return check_launch(h, launch_total_water_storage(h->f, h->kc, h->riv_of_land, h->stream),
                       "update_total_water_storage");
+}
+
+// stage timing of update_model (set_timing): the ten events bracket the stages
+static int32_t book_stage_times(WflowB200* h) {
+  if (!h->timing) return WFLOWB200_OK;
+  CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
+  float d[9];
+  for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&d[i], h->ev[i], h->ev[i + 1]);
+  h->ms[0] += d[1]; h->ms[1] += d[3]; h->ms[2] += d[4]; h->ms[3] += d[5]; h->ms[4] += d[7];
+  h->ms[5] += d[8]; h->ms[6] += d[0] + d[2] + d[6];
+  h->timed_steps++;
+  return WFLOWB200_OK;
 }
 
 int32_t wflowb200_update_model(WflowB200* h, double dt) {
@@ -1260,15 +1293,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
     mark(4); mark(5); mark(6); mark(7); mark(8);
     if ((rc = wflowb200_update_total_water_storage(h))) return rc;
     mark(9);
-    if (h->timing) {
-      CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
-      float d[9];
-      for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&d[i], h->ev[i], h->ev[i + 1]);
-      h->ms[0] += d[1]; h->ms[1] += d[3]; h->ms[2] += d[4]; h->ms[3] += d[5]; h->ms[4] += d[7];
-      h->ms[5] += d[8]; h->ms[6] += d[0] + d[2] + d[6];
-      h->timed_steps++;
-    }
-    return WFLOWB200_OK;
+    return book_stage_times(h);
   }
   bool soil_fused = false;
   if ((rc = update_subsurface_and_soil_storage(h, dt, &soil_fused))) return rc;
@@ -1289,15 +1314,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   mark(8);
   if ((rc = wflowb200_update_total_water_storage(h))) return rc;
   mark(9);
-  if (h->timing) {
-    CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
-    float d[9];
-    for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&d[i], h->ev[i], h->ev[i + 1]);
-    h->ms[0] += d[1]; h->ms[1] += d[3]; h->ms[2] += d[4]; h->ms[3] += d[5]; h->ms[4] += d[7];
-    h->ms[5] += d[8]; h->ms[6] += d[0] + d[2] + d[6];
-    h->timed_steps++;
-  }
-  return WFLOWB200_OK;
+  return book_stage_times(h);
 }
 
 int32_t wflowb200_selftest_math(int32_t device, int64_t n, double* out6) {
