@@ -190,6 +190,7 @@ struct WflowB200 {
   double* d_unsat_pool = nullptr;
   int32_t* d_unsat_its = nullptr;
   int32_t* d_unsat_list = nullptr;
+  unsigned long long* d_engine_diag = nullptr;
   unsigned* d_unsat_count = nullptr;
   int engine_grid = 0;
   cudaStream_t side_stream[WFB_V_SIDE_STREAMS] = {};  // high priority: the loop engines
@@ -755,6 +756,12 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       u.count = h->d_unsat_count + (size_t)k * 2 * WFB_UNSAT_BUCKETS;
       u.cap = (int32_t)per;
       u.inline_iters = ii ? atoi(ii) : 8;
+      u.diag = nullptr;
+    }
+    if (getenv("WFB_ENGINE_DIAG")) {  // developer aid: printed by wflowb200_get_stats
+      TRY_CREATE(cudaMalloc((void**)&h->d_engine_diag, 3 * sizeof(unsigned long long)));
+      TRY_CREATE(cudaMemset(h->d_engine_diag, 0, 3 * sizeof(unsigned long long)));
+      for (auto& u : h->unsat) u.diag = h->d_engine_diag;
     }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -842,6 +849,7 @@ void wflowb200_destroy(WflowB200* h) {
   for (auto st : h->side_stream) if (st) cudaStreamSynchronize(st);
   cudaFree(h->d_unsat_pool); cudaFree(h->d_unsat_its); cudaFree(h->d_unsat_list);
   cudaFree(h->d_unsat_count);
+  cudaFree(h->d_engine_diag);
   if (h->v_graph) cudaGraphExecDestroy(h->v_graph);
   for (auto e : h->v_ev) if (e) cudaEventDestroy(e);
   for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
@@ -1370,6 +1378,13 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
   wfb::dump_newton_hist();
 #endif
   CUDA_TRY(h, cudaMemcpy(&rs, h->d_stats, sizeof(rs), cudaMemcpyDeviceToHost));
+  if (h->d_engine_diag) {
+    unsigned long long dg[3] = {0, 0, 0};
+    cudaMemcpy(dg, h->d_engine_diag, sizeof(dg), cudaMemcpyDeviceToHost);
+    cudaMemset(h->d_engine_diag, 0, sizeof(dg));
+    fprintf(stderr, "loop engine since the last call: %llu suspended loops, %llu trips, longest %llu\n",
+            dg[0], dg[1], dg[2]);
+  }
   memset(out, 0, sizeof(*out));
   out->newton_calls_land = (int64_t)rs.newton_calls_land;
   out->newton_iters_land = (int64_t)rs.newton_iters_land;

@@ -19,6 +19,7 @@ struct UnsatWork {
   unsigned* count;                            // [2][WFB_UNSAT_BUCKETS]
   int32_t cap;                                // capacity of one list (= ns)
   int32_t inline_iters;                       // loops up to this many trips run in line
+  unsigned long long* diag;                   // developer aid: {loops, trips, longest} or nullptr
 };
 // engine_grid: CTAs of the persistent engine kernels (a few per SM). The cells are cut into
 // n_slices slices (one UnsatWork each); the loop engine of slice k runs on side[k % WFB_V_SIDE_STREAMS]

@@ -494,6 +494,11 @@ unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
       UnsatTask t;
       t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
       t.c = w.c[i]; t.its = w.its_layer[i] & 0xffffff;
+      if (w.diag) {  // developer aid (WFB_ENGINE_DIAG): loops, trips and the longest loop per round
+        atomicAdd(w.diag + 0, 1ull);
+        atomicAdd(w.diag + 1, (unsigned long long)t.its);
+        atomicMax(w.diag + 2, (unsigned long long)t.its);
+      }
       unsatzone_flow_iterate<WFB_ENGINE_FAST_POW != 0>(t, dt, ddt);
       w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast;
     }
