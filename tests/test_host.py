@@ -211,3 +211,25 @@ def test_oracle_water_balance_and_determinism(pkg):
         ora1.update_model(dt)
     for k in ("riv_q", "olf_q", "ssf_q", "water_table_depth", "total_storage"):
         assert np.array_equal(ora1.f[k], f[k]), k
+
+
+def test_create_rejects_bad_arguments_before_touching_the_device(pkg):
+    """Argument validation of wflowb200_create happens before any CUDA call: status
+    WFLOWB200_ERR_ARG (1) and a message, never a crash (the shim turns it into error(...))."""
+    import ctypes as C
+    L = pkg._lib.lib()
+    cfg, dom, _ = pkg.synthetic.make_basin(6, 8, seed=1)
+    idx = np.ascontiguousarray(dom["indices"], dtype=np.int64)
+    ldd = np.ascontiguousarray(dom["ldd"], dtype=np.uint8)
+    rli = np.ascontiguousarray(dom["river_land_indices"], dtype=np.int64)
+    d = pkg._lib.Domain(dom["d1"], dom["d2"], idx.ctypes.data, ldd.ctypes.data, rli.ctypes.data)
+    for bad in (dict(n=0), dict(n_layers=0), dict(n_layers=9), dict(kv_profile=7)):
+        c = pkg._lib.Config()
+        c.n, c.nriv, c.n_layers = cfg["n"], cfg["nriv"], cfg["n_layers"]
+        for k, v in bad.items():
+            setattr(c, k, v)
+        h = C.c_void_p()
+        rc = L.wflowb200_create(C.byref(c), C.byref(d), C.byref(h))
+        assert rc == 1 and not h.value, bad
+        assert L.wflowb200_last_error(None).decode()
+    assert L.wflowb200_create(None, None, None) == 1

@@ -388,7 +388,6 @@ land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
 
   // ---- state -> diagnostics (soil.jl:1400-1436) --------------------------------------------
   const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
-  const double theta_fc = __ldg(f.theta_fc + i);
   const double theta_e = theta_s - theta_r;
   const double d_soil = __ldg(f.soil_thickness + i);
   const double swc = __ldg(f.soil_water_capacity + i);
@@ -407,8 +406,6 @@ land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
   for (int k = 0; k < N; ++k)
     if (k < nlayers) ustore_depth += uld[k];
   const double zi = jmax(0.0, d_soil - fdiv(satwd, theta_e));
-  const double theta_d = jmax(theta_s - theta_fc, 0.02);  // lower_bound_drainable_porosity
-  double drainable = (d_soil - zi) * theta_d;
   double ustore_cap = swc - satwd - ustore_depth;
   int n_unsat = N;
 #pragma unroll
