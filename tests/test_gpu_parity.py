@@ -148,6 +148,19 @@ def test_masked_raster_and_single_column(pkg):
     _close(gpu)
 
 
+def test_degenerate_domains(pkg):
+    """No river cells at all (nriv = 0: the river kernels and the fused surface kernel are
+    skipped), a one-cell domain and a two-cell column."""
+    gpu, ora, cfg = parity.run_pair(pkg, 12, 16, steps=3, seed=3, river_fraction_target=0.0)
+    assert cfg["nriv"] == 0
+    parity.compare_models(gpu, ora)
+    _close(gpu)
+    for d1, d2 in ((1, 1), (2, 1)):
+        gpu, ora, cfg = parity.run_pair(pkg, d1, d2, steps=2, seed=3)
+        parity.compare_models(gpu, ora)
+        _close(gpu)
+
+
 def test_artifacts_bit_exact_on_device_handle(pkg):
     cfg, dom, fields = pkg.synthetic.make_basin(120, 200, seed=1)
     cfg["land_streamorder_min"], cfg["river_streamorder_min"] = 3, 3
