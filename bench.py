@@ -190,6 +190,10 @@ def main():
                          "(strong scaling) instead of one --size tile per rank")
     ap.add_argument("--adaptive", action="store_true",
                     help="adaptive internal routing time steps instead of the fixed defaults")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=INT",
+                    help="wflowb200_set_option (kernel organisation), e.g. vertical_graph=0 for ncu")
+    ap.add_argument("--cfg", action="append", default=[], metavar="NAME=INT",
+                    help="WflowB200Config tuning field, e.g. vertical_slices=1")
     args = ap.parse_args()
     rank, world, local = dist_env()
     global ADAPTIVE
@@ -247,7 +251,13 @@ def main():
     else:
         cfg, dom, fields = build_tile(pkg, args.size, rank, args.seed)
     n, nriv, N, dt = cfg["n"], cfg["nriv"], cfg["N"], cfg["dt"]
+    for kv in args.cfg:
+        k, v = kv.split("=")
+        cfg[k] = int(v)
     model = pkg.SbmModel(cfg, dom, fields, device=local)
+    for kv in args.option:
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
     gid = dom["gid"]
     if world > 1 or args.no_cpu_baseline:
         fields = None  # only the cpu_baseline leg needs the host copies again

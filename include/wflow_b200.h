@@ -42,6 +42,7 @@ enum {
 /* int64 per-cell arrays */
 #define WFLOWB200_I_number_of_layers 0   /* SbmSoilParameters.number_of_layers  soil/soil.jl:91 */
 #define WFLOWB200_I_n_unsatlayers 1      /* SbmSoilVariables.n_unsatlayers      soil/soil.jl:21 */
+#define WFLOWB200_I_nlayers_kv 2         /* KvLayeredExponential.nlayers_kv    soil/soil.jl:236 */
 
 /* The flags of config_structure.jl:62-115 (ModelSection) that change the hot path. */
 typedef struct {
@@ -54,7 +55,8 @@ typedef struct {
   int32_t snow;                /* snow__flag                                                   */
   int32_t glacier;             /* glacier__flag (only with snow, sbm.jl:41-54)                 */
   int32_t soil_infiltration_reduction; /* soil_infiltration_reduction__flag                    */
-  int32_t kv_profile;          /* 0 exponential, 1 exponential_constant                        */
+  int32_t kv_profile;          /* 0 exponential, 1 exponential_constant, 2 layered,
+                                  3 layered_exponential        soil.jl:213-244, utils.jl:727-789 */
   int32_t adaptive;            /* kinematic_wave__adaptive_time_step_flag                      */
   int32_t nthreads;            /* Threads.nthreads() the artefacts should be built for
                                   (subdomains.jl:176: 1 -> single sub-domain)                  */
@@ -66,6 +68,11 @@ typedef struct {
   double ssf_alpha_coefficient;/* subsurface_kinematic_wave__alpha_coefficient                 */
   double kin_wave_min_flow_qroot; /* KIN_WAVE_MIN_FLOW^0.2 as the host evaluates it
                                   (routing/utils.jl:2); 0 -> library uses pow(1e-30, 0.2)      */
+  /* B200 tuning, fixed at create; 0 = automatic (chosen from the shape of the domain) */
+  int32_t wave_piece_depth_land; /* levels per piece of the land chunks; -1: one connected piece */
+  int32_t vertical_slices;       /* slices of the vertical update (loop engine overlap), 1..8   */
+  int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (8)    */
+  int32_t reserved_;
 } WflowB200Config;
 
 /* The drainage network as the Julia model holds it (network.jl:48-81,175-208). */
@@ -95,15 +102,6 @@ typedef struct {
 #define WFLOWB200_A_WAVE_NODE_LEVEL 12 /* level of every node (0-based), by node id            */
 #define WFLOWB200_A_WAVE_CHUNK_PTR 13  /* slot offsets of the chunks (0-based, n_chunks + 1)   */
 #define WFLOWB200_A_WAVE_CHUNK_OUTLET 14 /* outlet node id of every chunk                      */
-/* single-sub-step wavefront (subsurface flow): bundles of WFLOWB200_BAND_DEPTH rows x 32 lanes  */
-#define WFLOWB200_BAND_DEPTH 4
-#define WFLOWB200_A_BAND_NODE 15       /* n_bundles x depth x 32: node id (1-based) or 0        */
-#define WFLOWB200_A_BAND_SRC 16        /* 8 per entry: lane in the previous row, 32768 + k for the
-                                          bundle's k-th inlet, 65535 = none (ascending node id)  */
-#define WFLOWB200_A_BAND_OUT 17        /* per entry: outlet number (0-based) or -1              */
-#define WFLOWB200_A_BAND_INLET_PTR 18  /* n_bundles + 1 offsets into BAND_INLET_OUT             */
-#define WFLOWB200_A_BAND_INLET_OUT 19  /* producer outlet number of every inlet                 */
-
 #define WFLOWB200_DOMAIN_LAND 0
 #define WFLOWB200_DOMAIN_RIVER 1
 
@@ -167,14 +165,31 @@ int32_t wflowb200_update_total_water_storage(WflowB200* h);
  * on the device                                                          sbm_model.jl:60-92 */
 int32_t wflowb200_update_model(WflowB200* h, double dt);
 /* Self-test of the device arithmetic the kernels are built on (csrc/device_math.cuh), over n
- * pseudo-random arguments: out6 = { max ulp distance fexp vs exp, flog vs log, max relative
- * difference of pow(x, c) = exp(c log x) for x in (0, 1], c in [1, 40], max ulp distance of the
- * guard-free division vs IEEE `/`, of the branch-free Julia min/max vs their definition, max
- * |difference| of cld(x, 2e-4) vs Julia's formula }. No handle needed. */
+ * pseudo-random arguments: out6 = { 0, 0, max relative difference of pow(x, c) = exp(c log x)
+ * against libdevice's pow for x in (0, 1], c in [1, 40], max ulp distance of the guard-free
+ * division vs IEEE `/`, of the branch-free Julia min/max vs their definition, max |difference|
+ * of cld(x, 2e-4) vs Julia's formula }. No handle needed. */
 int32_t wflowb200_selftest_math(int32_t device, int64_t n, double* out6);
 
-/* block until all device work of this handle is done */
+/* block until all device work of this handle is done; WFLOWB200_ERR_STATE if a wavefront kernel
+ * gave up a bounded wait (its grid was not co-resident: MPS share, second context, debugger) */
 int32_t wflowb200_synchronize(WflowB200* h);
+
+/* Select between kernel organisations that give identical results (the parity tests run every
+ * one): "fuse_soil_storage", "overlap_subsurface" (-1 automatic, 0, 1), "overlap_subsurface_sms",
+ * "fuse_surface" (0, 1), "surface_river_share", "surface_river_period", "vertical_graph" (0, 1),
+ * "kinwave_root_each_substep" (0, 1: see below). */
+int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value);
+/* "kinwave_root_each_substep" = 1 additionally evaluates u_prev = pow(q_prev, 0.2) before EVERY
+ * kinematic-wave solve like surface_process.jl:33 (default: the fifth root is carried from the
+ * previous solve of the node, within half an ulp of it; one pow per node and model step). */
+
+/* Newton iteration counts of `kinematic_wave` (surface_process.jl:24-70) per node, summed over
+ * the solves since enabling (iteration-count parity against the reference). enable = 1
+ * allocates and zeroes the counters, 0 frees them. dst: n (land) / nriv (river) values in node
+ * order. */
+int32_t wflowb200_newton_trace(WflowB200* h, int32_t enable);
+int32_t wflowb200_get_newton_trace(WflowB200* h, int32_t domain, int64_t* dst);
 
 /* ---- artefacts and statistics --------------------------------------------------------- */
 

@@ -11,7 +11,7 @@
  *   InterceptionVariables canopy.jl:4-16, GashParameters :19-23; SnowHbv* snow/snow.jl:4-45;
  *   Glacier* glacier/glacier.jl:4-60; OpenWaterRunoff* surfacewater/runoff.jl:4-27;
  *   LandParameters domain.jl:2-29; SbmSoilParameters soil/soil.jl:87-150, SbmSoilBC :203-211,
- *   SbmSoilVariables :4-84, Kv* :213-244; LateralSsf* routing/subsurface/
+ *   SbmSoilVariables :4-84, Kv* :213-244 (kv, z_layered: the layered profiles); LateralSsf* routing/subsurface/
  *   lateral_subsurface_flow.jl:2-54, RechargeVariables boundary_conditions.jl:204-213;
  *   OverLandFlowVariables routing/surface/surface_kinwave.jl:154-178, LandFlowBC :181-185;
  *   RiverFlowVariables :5-29, RiverFlowBC routing/surface/surface_flow.jl:9-34.
@@ -46,6 +46,7 @@
   X(cf_soil, 0) X(compacted_soil_area_fraction, 0) X(wet_root_distribution_parameter, 0) \
   X(rootfraction, 1) X(h1, 0) X(h2, 0) X(h3_high, 0) X(h3_low, 0) X(h4, 0) X(alpha_h1, 0) \
   X(soil_fraction, 0) X(kv_0, 0) X(hydraulic_conductivity_scale_parameter, 0) X(z_exp, 0) \
+  X(kv, 1) X(z_layered, 0) \
   X(soil_water_flux_surface, 0) X(potential_transpiration, 0) X(potential_soilevaporation, 0) \
   X(h3, 0) X(unsaturated_store_capacity, 0) X(unsaturated_layer_depth, 1) \
   X(unsaturated_layer_thickness, 1) X(saturated_water_depth, 0) X(drainable_water_depth, 0) \
@@ -61,7 +62,7 @@
   X(relative_volumetric_water_content_root_zone, 0) X(unsaturated_store_depth, 0) \
   X(transfer, 0) X(recharge, 0) X(actual_leakage, 0) X(total_storage, 0) \
   X(total_soil_water_storage, 0) X(soil_surface_temperature, 0) X(f_infiltration_reduction, 0) \
-  X(kh_0, 0) X(ssf_soil_thickness, 0) X(specific_yield, 0) X(ssf_top, 0) \
+  X(kh_0, 0) X(ssf_khfrac, 0) X(ssf_kh, 0) X(ssf_soil_thickness, 0) X(specific_yield, 0) X(ssf_top, 0) \
   X(ssf_water_table_depth, 0) X(ssf_head, 0) X(ssf_exfiltwater_cumulative, 0) \
   X(ssf_exfiltwater_average, 0) X(ssf_q, 0) X(ssf_q_cumulative, 0) X(ssf_q_average, 0) \
   X(ssf_q_in, 0) X(ssf_q_in_cumulative, 0) X(ssf_q_in_average, 0) X(ssf_q_max, 0) \

@@ -14,15 +14,16 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libwfo.so")
-_lib = None
+_ALT_PATH = os.path.join(_HERE, "_build", "libwfo_alt.so")  # noisy-libm variant (wfo_math.h)
+_libs = {}
 
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("wfo_vertical.c", "wfo_routing.c", "wfo.h", "wfo_math.h")]
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    stale = any((not os.path.exists(p)) or any(os.path.getmtime(s) > os.path.getmtime(p)
+                                                for s in srcs) for p in (_LIB_PATH, _ALT_PATH))
     if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"],
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "all"],
                               stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -43,11 +44,11 @@ class _Cfg(C.Structure):
                 ("ssf_alpha_coefficient", C.c_double)]
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(variant: str = ""):
+    """variant "alt": the same oracle on a noisy libm (tolerance calibration)."""
+    if variant not in _libs:
         build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(_ALT_PATH if variant == "alt" else _LIB_PATH)
         L.wfo_field_name.restype = C.c_char_p
         L.wfo_new.restype = C.c_void_p
         L.wfo_cfg.restype = C.POINTER(_Cfg)
@@ -107,8 +108,8 @@ def lib():
                                             C.c_void_p], d)
         sig("wfo_round_sigdigits12", [d], d)
         sig("wfo_cld", [d, d], d)
-        _lib = L
-    return _lib
+        _libs[variant] = L
+    return _libs[variant]
 
 
 def field_table():
@@ -158,8 +159,9 @@ class OracleModel:
     `net_land` / `net_river`: dicts from oracle.network.build_domain_network (1-based).
     """
 
-    def __init__(self, cfg: dict, fields: dict, net_land: dict, net_river: dict):
-        L = lib()
+    def __init__(self, cfg: dict, fields: dict, net_land: dict, net_river: dict,
+                 variant: str = ""):
+        L = lib(variant)
         self._L = L
         self.h = L.wfo_new()
         c = L.wfo_cfg(self.h).contents
@@ -245,6 +247,18 @@ class OracleModel:
                 "newton_calls_river", "newton_maxit_land", "newton_maxit_river",
                 "substeps_land", "substeps_river", "substeps_ssf")
         return dict(zip(keys, list(out)))
+
+    def newton_trace(self, enable: bool):
+        """Per-node Newton iteration totals of the kinematic-wave solves (zeroed on enable)."""
+        for dom, size in (("land", self.cfg["n"]), ("river", self.cfg["nriv"])):
+            a = np.zeros(int(size), dtype=np.int64) if enable else None
+            self._trace = getattr(self, "_trace", {})
+            self._trace[dom] = a
+            self._L.wfo_set_iptr(self.h, ("newton_trace_" + dom).encode(),
+                                 a.ctypes.data if enable else None)
+
+    def newton_trace_get(self, dom: str) -> np.ndarray:
+        return self._trace[dom].copy()
 
     def sweep(self, name, dt=0.0):
         rc = self._L.wfo_sweep(self.h, name.encode(), dt)

@@ -79,7 +79,7 @@
   X(transfer, 0) X(recharge, 0) X(actual_leakage, 0) X(total_storage, 0) \
   X(total_soil_water_storage, 0) X(soil_surface_temperature, 0) X(f_infiltration_reduction, 0) \
   /* lateral subsurface flow (lateral_subsurface_flow.jl:2-54) + recharge BC */ \
-  X(kh_0, 0) X(ssf_soil_thickness, 0) X(specific_yield, 0) X(ssf_top, 0) \
+  X(kh_0, 0) X(ssf_khfrac, 0) X(ssf_kh, 0) X(ssf_soil_thickness, 0) X(specific_yield, 0) X(ssf_top, 0) \
   X(ssf_water_table_depth, 0) X(ssf_head, 0) X(ssf_exfiltwater_cumulative, 0) \
   X(ssf_exfiltwater_average, 0) X(ssf_q, 0) X(ssf_q_cumulative, 0) X(ssf_q_average, 0) \
   X(ssf_q_in, 0) X(ssf_q_in_cumulative, 0) X(ssf_q_in_average, 0) X(ssf_q_max, 0) \
@@ -134,6 +134,8 @@ typedef struct wfo_model {
   int64_t* n_unsatlayers;     /* n */
   int64_t* nlayers_kv;        /* n (layered_exponential only) */
   int64_t* river_land_indices;/* nriv, 0-based land index of each river cell */
+  int64_t* newton_trace_land; /* n / nriv or NULL: Newton iterations of kinematic_wave per node, */
+  int64_t* newton_trace_river;/* summed over the sub-steps (iteration-count parity tests)       */
   wfo_network land, river;
   double* scratch;            /* max(n, nriv) doubles: stable_timesteps */
   /* statistics */

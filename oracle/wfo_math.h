@@ -7,6 +7,28 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifdef WFO_ALT_LIBM
+/* A deliberately NOISY libm (build variant libwfo_alt.so, tests/test_tolerances.py): exp, log
+ * and cbrt results are moved by one unit in the last place for a pseudo-random half of the
+ * arguments. Two runs of the oracle that differ only in this way bracket what any two faithful
+ * (< 1-2 ulp) math libraries -- glibc here, libdevice on the GPU, Julia's own in the reference --
+ * may do to the results; the per-field tolerances of tests/parity.py are calibrated on it. */
+static inline double wfo_alt_noise(double x, double r) {
+  uint64_t b;
+  __builtin_memcpy(&b, &x, 8);
+  b = (b ^ (b >> 29)) * 0xBF58476D1CE4E5B9ull;
+  b ^= b >> 32;
+  if (!isfinite(r) || r == 0.0 || (b & 1)) return r;
+  return nextafter(r, (b & 2) ? INFINITY : -INFINITY);
+}
+static inline double wfo_alt_exp(double x) { return wfo_alt_noise(x, exp(x)); }
+static inline double wfo_alt_log(double x) { return wfo_alt_noise(x, log(x)); }
+static inline double wfo_alt_cbrt(double x) { return wfo_alt_noise(x, cbrt(x)); }
+#define exp(x) wfo_alt_exp(x)
+#define log(x) wfo_alt_log(x)
+#define cbrt(x) wfo_alt_cbrt(x)
+#endif
+
 /* to_SI_factor(MM_PER_DAY) = 86400^-1 * 1e-3 (units.jl:55-68, factors multiplied in field
  * order: d before mm) */
 #define WFO_MM_PER_DAY ((1.0 / 86400.0) * 1e-3)

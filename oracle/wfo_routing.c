@@ -431,6 +431,7 @@ static void kinwave_land_update(wfo_model* m, double dt) {
         wfo_kinematic_wave(m->olf_qin[v], m->olf_q[v], m->olf_qlat[v], m->olf_alpha[v], dt,
                            m->flow_length[v], o, &it);
         it_sum += it; calls += 1; if (it > maxit) maxit = it;
+        if (m->newton_trace_land) m->newton_trace_land[v] += it;
         m->olf_q[v] = o[0];
         if (m->surface_flow_width[v] > 0.0) m->olf_h[v] = o[1] / m->surface_flow_width[v];
         m->olf_storage[v] = m->flow_length[v] * m->surface_flow_width[v] * m->olf_h[v];
@@ -510,6 +511,7 @@ static void kinwave_river_update(wfo_model* m, double dt) {
         wfo_kinematic_wave(m->riv_qin[v], m->riv_q[v], m->riv_qlat[v] + inflow, m->riv_alpha[v], dt,
                            m->riv_flow_length[v], o, &it);
         it_sum += it; calls += 1; if (it > maxit) maxit = it;
+        if (m->newton_trace_river) m->newton_trace_river[v] += it;
         m->riv_q[v] = o[0];
         m->riv_h[v] = o[1] / m->riv_flow_width[v];
         m->riv_storage[v] = m->riv_flow_length[v] * o[1];

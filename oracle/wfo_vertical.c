@@ -40,6 +40,8 @@ int wfo_set_iptr(wfo_model* m, const char* name, int64_t* p) {
   if (!strcmp(name, "number_of_layers")) { m->number_of_layers = p; return 0; }
   if (!strcmp(name, "n_unsatlayers")) { m->n_unsatlayers = p; return 0; }
   if (!strcmp(name, "nlayers_kv")) { m->nlayers_kv = p; return 0; }
+  if (!strcmp(name, "newton_trace_land")) { m->newton_trace_land = p; return 0; }
+  if (!strcmp(name, "newton_trace_river")) { m->newton_trace_river = p; return 0; }
   if (!strcmp(name, "river_land_indices")) { m->river_land_indices = p; return 0; }
   return -1;
 }

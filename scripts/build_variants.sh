@@ -1,5 +1,6 @@
 #!/bin/bash
 # developer aid: build kernel-tuning variants of the library into wflow.jl_b200/csrc/_obj/variants/
+# (select one with WFB_LIB=<path> python bench.py ...)
 set -e
 cd "$(dirname "$0")/../wflow.jl_b200/csrc"
 mkdir -p _obj/variants
@@ -12,8 +13,11 @@ build() { # name, flags
   wait
   $NV -shared -o _obj/variants/lib_$name.so $d/api.o $d/vertical.o $d/routing.o $d/network.o
 }
-build ssf2 -DWFB_SSF_MINBLOCKS=2
-build olf3 -DWFB_OLF_MINBLOCKS=3 -DWFB_RIV_MINBLOCKS=3
-build v128 -DWFB_V_BLOCK=128 -DWFB_VA_MINBLOCKS=5 -DWFB_VC_MINBLOCKS=4
-build v128b -DWFB_V_BLOCK=128 -DWFB_VA_MINBLOCKS=6 -DWFB_VC_MINBLOCKS=5
+for v in "$@"; do
+  case $v in
+    mb3) build mb3 -DWFB_V_MINBLOCKS=3 ;;
+    mb5) build mb5 -DWFB_V_MINBLOCKS=5 ;;
+    *) echo "unknown variant $v"; exit 1 ;;
+  esac
+done
 ls -la _obj/variants/*.so

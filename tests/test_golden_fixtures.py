@@ -47,7 +47,12 @@ def test_cuda_path_matches_golden_fixture(pkg, name):
         gpu.set_forcing(*pkg.synthetic.make_forcing(seed, step, dom["gid"], dt))
         gpu.update_model(dt)
     gpu.synchronize()
-    golden = types.SimpleNamespace(f=_fixture(name))
-    worst = parity.compare_models(gpu, golden, rtol=parity.RTOL)
-    print(f"{name}: worst scaled relative difference {worst:.3e}")
+    fx = _fixture(name)
+    fx["river_land_indices"] = dom["river_land_indices"] - 1
+    st = gpu.stats()
+    golden = types.SimpleNamespace(f=fx, cfg=cfg, newton_stats=lambda: st)
+    rep = parity.compare_models(gpu, golden, rtol=parity.RTOL,
+                                names=[n for n in gpu.field_names() if n in fx])
+    assert len(rep) >= 140
+    print(f"{name}: {rep.summary()}")
     gpu.close()

@@ -1,6 +1,7 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
-the same seeded inputs. Float64 fields within 1e-10 relative (tests/parity.py), integer fields
-and indexing artefacts bit-exact."""
+the same seeded inputs. Float64 fields ELEMENTWISE within 1e-10 relative plus a per-element
+absolute tolerance derived from the operands of the reference expression (tests/parity.py;
+calibrated by tests/test_tolerances.py), integer fields and indexing artefacts bit-exact."""
 import os
 import sys
 
@@ -22,20 +23,57 @@ def _close(*models):
 @pytest.mark.parametrize("d1,d2,steps", [(48, 64, 3), (97, 131, 4)])
 def test_update_model_matches_oracle(pkg, d1, d2, steps):
     gpu, ora, cfg = parity.run_pair(pkg, d1, d2, steps=steps, seed=42)
-    worst = parity.compare_models(gpu, ora)
+    rep = parity.compare_models(gpu, ora)
     st = gpu.stats()
     assert st["kernel_launches"] > 0
     assert st["substeps_land"] == 24 and st["substeps_river"] == 96 and st["substeps_ssf"] == 1
-    print(f"worst scaled rel diff {worst:.3e}")
+    print(rep.summary())
     _close(gpu)
 
 
-def test_band_kernel_matches_oracle(pkg, monkeypatch):
-    """The experimental single-sub-step subsurface kernel over bands (WFB_SSF_BANDS=1, read at
-    create) gives the same fields as the chunk walk and the oracle."""
-    monkeypatch.setenv("WFB_SSF_BANDS", "1")
-    gpu, ora, cfg = parity.run_pair(pkg, 97, 131, steps=4, seed=21)
-    parity.compare_models(gpu, ora)
+def test_benchmark_size_1000x1000_all_defaults(pkg):
+    """BASELINE configs[1], the raster bench.py times: 10^6 cells, 1000 wavefront levels, every
+    default (overlapped subsurface / surface kernels, sliced vertical update with the tile order
+    of the previous step, ~80 000 suspended Brooks-Corey loops per step once the soil is wet)."""
+    gpu, ora, cfg = parity.run_pair(pkg, 1000, 1000, steps=4, seed=42, newton_trace=True)
+    assert cfg["n"] == 1000000
+    rep = parity.compare_models(gpu, ora)
+    print(rep.summary())
+    print("newton parity (nodes, nodes with a differing iteration total, gpu, oracle):",
+          parity.newton_parity(gpu, ora))
+    _close(gpu)
+
+
+def test_wide_raster_takes_the_wide_domain_defaults(pkg):
+    """2304 nodes per wavefront level: multi-piece land chunks (depth 6), no subsurface / surface
+    overlap, update_soil_water_storage! as a kernel of its own -- chosen by the library, no
+    option set."""
+    gpu, ora, cfg = parity.run_pair(pkg, 2304, 64, steps=3, seed=17)
+    a = gpu.artifacts("land")
+    assert cfg["n"] // (len(a["wave_level_ptr"]) - 1) >= 2048
+    rep = parity.compare_models(gpu, ora)
+    print(rep.summary())
+    _close(gpu)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_moselle_shape_dendritic_network(pkg, adaptive):
+    """BASELINE configs[0] shape (test/bmi.jl:108-115: 50 063 land cells, ~5 809 river cells): ONE
+    outlet, all eight LDD codes, node ids unrelated to the drainage order (steepest descent on a
+    smooth random surface), fixed and adaptive internal time steps (test/sbm_config.toml:123)."""
+    gpu, ora, cfg = parity.run_pair(pkg, 264, 291, steps=4, seed=7, network="dendritic",
+                                    n_active=50063, n_river=5809, adaptive=adaptive,
+                                    newton_trace=True)
+    assert cfg["n"] == 50063 and abs(cfg["nriv"] - 5809) < 60
+    ldd = gpu.artifacts("land")["ldd"]
+    assert set(np.unique(ldd)) == set(range(1, 10)) and (ldd == 5).sum() == 1
+    rep = parity.compare_models(gpu, ora)
+    st, o = gpu.stats(), ora.newton_stats()
+    for k in ("substeps_land", "substeps_river", "substeps_ssf"):
+        assert st[k] == o[k], (k, st[k], o[k])
+    print(rep.summary())
+    print("sub-steps", {k: st[k] for k in st if k.startswith("substeps")},
+          "newton parity:", parity.newton_parity(gpu, ora))
     _close(gpu)
 
 
@@ -58,8 +96,8 @@ def test_adaptive_internal_time_steps_match_oracle(pkg, dt):
 
 
 def test_device_math_selftest(pkg):
-    """device_math.cuh on the device: table-driven exp / log within 2 ulp of libdevice's (each is
-    < 1 ulp from the correctly rounded value), pow(x, c) within 2e-13 relative, the guard-free
+    """device_math.cuh on the device: pow(x, c) = exp(c log x) within 2e-13 relative of
+    libdevice's pow, the guard-free
     division bit-identical to IEEE `/`, branch-free min/max identical to Julia's definition
     (NaN propagation), cld(x, 2e-4) identical to Julia's formula."""
     import ctypes as C
@@ -68,23 +106,27 @@ def test_device_math_selftest(pkg):
     assert rc == 0
     w_exp, w_log, w_pow, w_div, w_mm, w_cld = list(out)
     print("selftest", list(out))
-    assert w_exp <= 2 and w_log <= 2
+    assert w_exp == 0 and w_log == 0    # unused slots
     assert w_pow <= 2e-13
     assert w_div == 0 and w_mm == 0 and w_cld == 0
 
 
-@pytest.mark.parametrize("env", [{"WFB_FUSE_SURFACE": "0"}, {"WFB_FUSE_ROUTING": "1"},
-                                 {"WFB_SSF_S1": "1"}, {"WFB_PIECE_LAND": "6", "WFB_V_SLICES": "4"},
-                                 {"WFB_FUSE_SOIL_STORAGE": "0"}, {"WFB_OVERLAP_SSF": "0"},
-                                 {"WFB_OVERLAP_SSF": "1", "WFB_SSF_OVERLAP_SMS": "40"}])
-def test_alternative_kernel_paths_match_oracle(pkg, monkeypatch, env):
+@pytest.mark.parametrize("options,cfg_over", [
+    ({"fuse_surface": 0}, {}),
+    ({}, {"wave_piece_depth_land": 6, "vertical_slices": 4}),
+    ({"fuse_soil_storage": 0}, {"vertical_slices": 2, "unsat_inline_iters": 2}),
+    ({"overlap_subsurface": 0}, {"wave_piece_depth_land": -1}),
+    ({"overlap_subsurface": 1, "overlap_subsurface_sms": 40}, {}),
+    ({"vertical_graph": 0, "surface_river_period": 4, "surface_river_share": 2}, {}),
+])
+def test_alternative_kernel_paths_match_oracle(pkg, options, cfg_over):
     """Every kernel organisation behind the same entry point gives the same fields: overland
-    and river as separate kernels (the default fuses them), subsurface + soil storage + overland
-    + river in one kernel, the slim single-sub-step subsurface node, multi-piece chunks with a
-    sliced vertical update (all read at create)."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    gpu, ora, cfg = parity.run_pair(pkg, 97, 131, steps=4, seed=29)
+    and river as separate kernels (the default fuses them), multi-piece chunks, a sliced vertical
+    update with a short in-line loop limit (more suspended cells), the subsurface sweep with /
+    without the fused soil-water storage and the overlapped surface kernel, the vertical update
+    launch by launch instead of as a CUDA graph."""
+    gpu, ora, cfg = parity.run_pair(pkg, 97, 131, steps=4, seed=29, cfg_over=cfg_over,
+                                    options=options)
     parity.compare_models(gpu, ora)
     _close(gpu)
 
@@ -95,20 +137,26 @@ def test_fine_grained_entry_points_match_oracle(pkg):
     _close(gpu)
 
 
-def test_newton_iteration_counts_match(pkg):
-    gpu, ora, cfg = parity.run_pair(pkg, 64, 96, steps=3, seed=11)
-    st = gpu.stats()
-    L = ora._L
-    import ctypes as C
-    # oracle counters live in the C struct; exposed through the model's python mirror
-    o = ora.newton_stats()
+@pytest.mark.parametrize("root_each", [0, 1])
+def test_newton_iteration_counts(pkg, root_each):
+    """`kinematic_wave` (surface_process.jl:24-70): the number of solves is equal, and the Newton
+    iteration totals are compared NODE BY NODE (exact integers, no tolerance on the totals). An
+    iterate whose residual lies within a few ulp of the 1e-12 threshold may stop one iteration
+    earlier or later under a different (faithful) libm -- the oracle against itself on a +-1 ulp
+    noisy libm differs in ~2e-5 of the iterations (tests/test_tolerances.py) -- so a small number
+    of nodes may differ; it is printed and bounded. root_each = 1: the fifth root of the previous
+    discharge is evaluated before every solve like the reference does, instead of carried."""
+    gpu, ora, cfg = parity.run_pair(pkg, 64, 96, steps=3, seed=11, newton_trace=True,
+                                    options={"kinwave_root_each_substep": root_each})
+    st, o = gpu.stats(), ora.newton_stats()
     assert st["newton_calls_land"] == o["newton_calls_land"]
     assert st["newton_calls_river"] == o["newton_calls_river"]
-    # same number of Newton iterations (north_star); libm last-bit differences may move an
-    # iterate across the 1e-12 residual threshold for a handful of nodes
-    for k in ("land", "river"):
-        a, b = st[f"newton_iters_{k}"], o[f"newton_iters_{k}"]
-        assert abs(a - b) <= 1e-4 * max(b, 1), (k, a, b)
+    np_ = parity.newton_parity(gpu, ora)
+    print("newton parity (nodes, nodes with a differing iteration total, gpu total, oracle total):", np_)
+    for dom, (nodes, differ, gsum, osum) in np_.items():
+        assert differ <= max(2, nodes // 200), (dom, nodes, differ)
+        assert abs(gsum - osum) <= max(8, differ * 8), (dom, gsum, osum)
+    parity.compare_models(gpu, ora)
     _close(gpu)
 
 

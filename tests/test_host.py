@@ -118,57 +118,6 @@ def test_wavefront_levels_and_chunks_are_a_valid_schedule(pkg, monkeypatch, piec
         assert len(cp) - 1 >= 2
 
 
-@pytest.mark.parametrize("d1,d2,seed", [(90, 140, 5), (33, 61, 9), (7, 300, 2)])
-def test_bands_are_a_valid_single_substep_schedule(pkg, d1, d2, seed):
-    """Bands / fragments / bundles of the single-sub-step subsurface kernel: every node sits in
-    exactly one (bundle, row, lane); a node's sources are its in-neighbours in ascending node id
-    (the reference's left-fold order, utils.jl:472-477); sources inside the bundle sit in the
-    previous row; every other source is an inlet whose producer is a fragment root of an
-    EARLIER bundle (queue order = topological order of the bundle DAG)."""
-    cfg, dom, _ = pkg.synthetic.make_basin(d1, d2, seed=seed)
-    a = pkg.build_network_artifacts(cfg, dom)["land"]
-    n, D = cfg["n"], 4
-    node = a["band_node"].reshape(-1, D, 32)
-    src = a["band_src"].reshape(-1, D, 32, 8)
-    out = a["band_out"].reshape(-1, D, 32)
-    iptr, iout = a["band_inlet_ptr"], a["band_inlet_out"]
-    nb = node.shape[0]
-    assert len(iptr) == nb + 1 and iptr[-1] == len(iout)
-    ids = node[node > 0]
-    assert sorted(ids.tolist()) == list(range(1, n + 1))
-    where = {}
-    for b, r, l in zip(*np.nonzero(node)):
-        where[int(node[b, r, l])] = (int(b), int(r), int(l))
-    down = dom["down"]
-    ups = [[] for _ in range(n + 1)]
-    for v in range(1, n + 1):
-        if down[v - 1]:
-            ups[down[v - 1]].append(v)
-    outlet_owner = {}
-    for b, r, l in zip(*np.nonzero(out >= 0)):
-        outlet_owner[int(out[b, r, l])] = int(node[b, r, l])
-    assert sorted(outlet_owner) == list(range(len(outlet_owner)))
-    for v in range(1, n + 1):
-        b, r, l = where[v]
-        codes = [int(c) for c in src[b, r, l] if c != 0xffff]
-        assert len(codes) == len(ups[v])
-        assert list(src[b, r, l][len(codes):]) == [0xffff] * (8 - len(codes))
-        for u, code in zip(sorted(ups[v]), codes):
-            bu, ru, lu = where[u]
-            if code & 0x8000:
-                k = code & 0x7fff
-                assert bu < b                                  # producer bundle runs earlier
-                assert 0 <= k < iptr[b + 1] - iptr[b]
-                assert outlet_owner[int(iout[iptr[b] + k])] == u
-            else:
-                assert (bu, ru, lu) == (b, r - 1, code)
-        leaves = down[v - 1] == 0 or where[int(down[v - 1])][0] != b
-        assert (out[b, r, l] >= 0) == (down[v - 1] != 0 and leaves)
-    # lanes of a row are filled from lane 0 without holes
-    filled = node > 0
-    assert np.all(filled[:, :, 1:] <= filled[:, :, :-1])
-
-
 def test_cycle_is_rejected(pkg):
     # two cells pointing at each other: 6 (east, +1 in d1) and 4 (west)
     cfg = dict(n_layers=4, nthreads=1)

@@ -21,7 +21,9 @@ class Config(C.Structure):
                 ("adaptive", C.c_int32), ("nthreads", C.c_int32),
                 ("land_streamorder_min", C.c_int32), ("river_streamorder_min", C.c_int32),
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
-                ("ssf_alpha_coefficient", C.c_double), ("kin_wave_min_flow_qroot", C.c_double)]
+                ("ssf_alpha_coefficient", C.c_double), ("kin_wave_min_flow_qroot", C.c_double),
+                ("wave_piece_depth_land", C.c_int32), ("vertical_slices", C.c_int32),
+                ("unsat_inline_iters", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Domain(C.Structure):
@@ -42,8 +44,7 @@ class Stats(C.Structure):
 ARTIFACTS = dict(order=0, streamorder=1, upstream_ptr=2, upstream_idx=3, subdomain_level_ptr=4,
                  subdomain_level_idx=5, subdomain_ptr=6, subdomain_order=7, subdomain_indices=8,
                  ldd=9, wave_level_ptr=10, wave_perm=11, wave_node_level=12, wave_chunk_ptr=13,
-                 wave_chunk_outlet=14, band_node=15, band_src=16, band_out=17, band_inlet_ptr=18,
-                 band_inlet_out=19)
+                 wave_chunk_outlet=14)
 
 
 def header_symbols():
@@ -71,7 +72,7 @@ def lib():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
             "(wflow.jl_b200 has no CPU fallback)")
-    L = C.CDLL(os.environ.get("WFB_LIB", LIB_PATH))  # WFB_LIB: developer aid (kernel variants)
+    L = C.CDLL(os.environ.get("WFB_LIB", LIB_PATH))  # WFB_LIB: a build variant (scripts/build_variants.sh)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     L.wflowb200_create.argtypes = [C.POINTER(Config), C.POINTER(Domain), C.POINTER(vp)]
     L.wflowb200_destroy.argtypes = [vp]
@@ -99,6 +100,9 @@ def lib():
     L.wflowb200_set_timing.argtypes = [vp, i32]
     L.wflowb200_timer_start.argtypes = [vp]
     L.wflowb200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    L.wflowb200_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.wflowb200_newton_trace.argtypes = [vp, i32]
+    L.wflowb200_get_newton_trace.argtypes = [vp, i32, vp]
     L.wflowb200_selftest_math.argtypes = [i32, i64, C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -39,8 +39,6 @@ struct DomainDev {
   int32_t* chunk_of_slot = nullptr;     // device, land only: slot -> chunk (fused surface kernel)
   unsigned* chunk_done = nullptr;       // device, land only: per chunk, epoch of its last finalize
   unsigned* chunk_ssf_done = nullptr;   // the same for subsurface flow + soil water storage
-  DevBands bands{};                     // land only: single-sub-step subsurface flow
-  unsigned long long* band_q_out = nullptr;
 };
 
 // NetworkLand + NetworkRiver artefacts (network.jl:87-133,214-278; domain.jl:80-125).
@@ -71,12 +69,6 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
     errmsg = "river network: " + err;
     return WFLOWB200_ERR_GRAPH;
   }
-  // chunk sizes of the block-local wavefront (nodes per CTA work item); tunable for experiments
-  const char* cl = getenv("WFB_CHUNK_LAND");
-  const char* cr = getenv("WFB_CHUNK_RIVER");
-  // piece depth (levels) of the chunks; 0 = one connected piece per chunk. Tunable for experiments
-  const char* pl = getenv("WFB_PIECE_LAND");
-  const char* pr = getenv("WFB_PIECE_RIVER");
   // Shallow multi-piece chunks cut the warp-stages of a sweep (24 sub-steps: -31 % at depth 4,
   // one sub-step: -72 %) but add chunk-to-chunk hand-offs to the dependent chain of the sweep.
   // Measured on B200: a loss on a latency-bound domain (1000^2: 1000 nodes per level, +16 % step
@@ -85,11 +77,10 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
   int64_t depth_land = WFB_PIECE_DEPTH_LAND;
   if (land.n_wave_levels > 0 && land.n / land.n_wave_levels >= WFB_PIECE_WIDE_LEVEL)
     depth_land = WFB_PIECE_DEPTH_LAND_WIDE;
-  build_chunks(land, std::min<int64_t>(cl ? atoll(cl) : WFB_CHUNK_NODES, WFB_CHUNK_NODES),
-               pl ? atoll(pl) : depth_land);
-  build_chunks(river, std::min<int64_t>(cr ? atoll(cr) : WFB_CHUNK_NODES, WFB_CHUNK_NODES),
-               pr ? atoll(pr) : WFB_PIECE_DEPTH_RIVER);
-  build_bands(land, WFB_BAND_DEPTH);
+  if (cfg->wave_piece_depth_land > 0) depth_land = cfg->wave_piece_depth_land;
+  else if (cfg->wave_piece_depth_land < 0) depth_land = 0;
+  build_chunks(land, WFB_CHUNK_NODES, depth_land);
+  build_chunks(river, WFB_CHUNK_NODES, WFB_PIECE_DEPTH_RIVER);
   return WFLOWB200_OK;
 }
 
@@ -113,15 +104,6 @@ int32_t copy_artifact(const Network& nw, int32_t id, int64_t* dst, int64_t capac
     case WFLOWB200_A_WAVE_NODE_LEVEL: src = &nw.node_level; break;
     case WFLOWB200_A_WAVE_CHUNK_PTR: src = &nw.chunk_ptr; break;
     case WFLOWB200_A_WAVE_CHUNK_OUTLET: src = &nw.chunk_outlet; break;
-    case WFLOWB200_A_BAND_NODE:
-      tmp.resize(nw.bundle_node.size());
-      for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (int64_t)nw.bundle_node[i] + 1;
-      src = &tmp; break;
-    case WFLOWB200_A_BAND_SRC: tmp.assign(nw.bundle_src.begin(), nw.bundle_src.end()); src = &tmp; break;
-    case WFLOWB200_A_BAND_OUT: tmp.assign(nw.bundle_out.begin(), nw.bundle_out.end()); src = &tmp; break;
-    case WFLOWB200_A_BAND_INLET_PTR: src = &nw.bundle_inl_ptr; break;
-    case WFLOWB200_A_BAND_INLET_OUT:
-      tmp.assign(nw.bundle_inl_out.begin(), nw.bundle_inl_out.end()); src = &tmp; break;
     default: errmsg = "bad artefact id"; return WFLOWB200_ERR_ARG;
   }
   *len_out = (int64_t)src->size();
@@ -138,33 +120,15 @@ struct WflowB200Network {
   Network land, river;
 };
 
-// Developer knobs (environment variables, read ONCE at create): kernel organisations that were
-// measured against each other on B200 stay selectable for experiments and for the parity tests.
+// Kernel organisations that are chosen from the shape of the domain (mean level width) and can be
+// overridden per handle through wflowb200_set_option (the parity tests exercise every one).
 struct Tuning {
-  int wave_prof = 0;          // WFB_WAVE_PROF = kind + 1: dump per-chunk timing of that component
-  bool band_prof = false;     // WFB_BAND_PROF: per-bundle timing of the band kernel
-  bool no_graph = false;      // WFB_NO_GRAPH: vertical update launch by launch (for ncu)
-  int fuse_soil_storage = -1; // WFB_FUSE_SOIL_STORAGE: -1 automatic (mean level width)
-  int overlap_ssf = -1;       // WFB_OVERLAP_SSF: -1 automatic (mean level width)
-  int ssf_overlap_sms = 0;    // WFB_SSF_OVERLAP_SMS: 0 = 13/32 of the SMs
-  int river_share = 1, river_period = 3;                  // WFB_SURFACE_RIVER_SHARE "share/period"
-  int r_river = 2, r_ssf = 2, r_period = 8;               // WFB_ROUTING_SHARES "river/ssf/period"
-  void read() {
-    auto geti = [](const char* name, int dflt) {
-      const char* v = getenv(name);
-      return v ? atoi(v) : dflt;
-    };
-    wave_prof = geti("WFB_WAVE_PROF", 0);
-    band_prof = getenv("WFB_BAND_PROF") != nullptr;
-    no_graph = getenv("WFB_NO_GRAPH") != nullptr;
-    fuse_soil_storage = geti("WFB_FUSE_SOIL_STORAGE", -1);
-    overlap_ssf = geti("WFB_OVERLAP_SSF", -1);
-    ssf_overlap_sms = geti("WFB_SSF_OVERLAP_SMS", 0);
-    if (const char* v = getenv("WFB_SURFACE_RIVER_SHARE")) sscanf(v, "%d/%d", &river_share, &river_period);
-    if (river_period < 2 || river_share < 1 || river_share >= river_period) { river_share = 1; river_period = 3; }
-    if (const char* v = getenv("WFB_ROUTING_SHARES")) sscanf(v, "%d/%d/%d", &r_river, &r_ssf, &r_period);
-    if (r_river < 1 || r_ssf < 1 || r_river + r_ssf >= r_period) { r_river = 2; r_ssf = 2; r_period = 8; }
-  }
+  int fuse_soil_storage = -1; // -1 automatic: update_soil_water_storage! inside the subsurface sweep
+  int overlap_ssf = -1;       // -1 automatic: subsurface sweep and surface kernel overlapped
+  int ssf_overlap_sms = 0;    // 0 = 13/32 of the SMs
+  int fuse_surface = 1;       // overland + river in one kernel
+  int river_share = 1, river_period = 3;  // warps of the surface kernel serving the river
+  int use_graph = 1;          // vertical update as one CUDA graph launch
 };
 
 struct WflowB200 {
@@ -190,11 +154,14 @@ struct WflowB200 {
   double* d_unsat_pool = nullptr;
   int32_t* d_unsat_its = nullptr;
   int32_t* d_unsat_list = nullptr;
-  unsigned long long* d_engine_diag = nullptr;
+  unsigned* d_tile_prio = nullptr;   // per tile: longest suspended loop of the current step
+  int32_t* d_tile_order = nullptr;   // tiles, longest loops of the previous step first
+  std::vector<int> slice_tile_begin; // n_slices + 1
+  unsigned* d_err = nullptr;         // device error word (bounded waits of the wavefront kernels)
   unsigned* d_unsat_count = nullptr;
   int engine_grid = 0;
   cudaStream_t side_stream[WFB_V_SIDE_STREAMS] = {};  // high priority: the loop engines
-  cudaEvent_t v_ev[32] = {};
+  cudaEvent_t v_ev[2 * WFB_V_MAX_SLICES] = {};
   cudaGraphExec_t v_graph = nullptr;  // the vertical update of one step, captured once per dt
   double v_graph_dt = 0.0;
   int v_graph_launches = 0;
@@ -208,16 +175,9 @@ struct WflowB200 {
   size_t smem_surface = 0;
   unsigned smem_surface_per_warp = 0;
   bool fuse_surface = true;
-  int grid_ssf_s1 = 0;                 // single-sub-step subsurface kernel with the slim node
-  bool use_ssf_s1 = true;
-  int grid_routing = 0;                // subsurface + soil storage + overland + river in one kernel
-  bool fuse_routing = true;
   unsigned surface_epoch = 0;
   unsigned long long* ssf_q_out = nullptr;  // outlet values of the subsurface warps (fused routing)
   size_t ssf_q_out_words = 0;
-  int grid_band = 0, warps_band = 0;   // single-sub-step subsurface kernel
-  size_t smem_band = 0;
-  bool use_bands = true;
   int64_t launches = 0;
   int64_t sub_land = 0, sub_river = 0, sub_ssf = 0;
   bool timing = false;
@@ -243,6 +203,35 @@ int32_t fail(WflowB200* h, int32_t code, const std::string& msg) {
     if (e_ != cudaSuccess)                                                             \
       return fail(h, WFLOWB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+// Every entry point runs on the handle's device whatever the caller's current device is (a Julia
+// task may migrate between threads, each with its own current device), and restores it.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define WFB_ENTER(h)                     \
+  if (!(h)) return WFLOWB200_ERR_ARG;    \
+  DeviceGuard device_guard_((h)->cfg.device)
+
+// The wavefront kernels raise the error word when one of their bounded waits expired
+// (routing.cu: spin_expired): the grid was not co-resident and the step's results are invalid.
+int32_t check_device_error(WflowB200* h) {
+  unsigned e = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&e, h->d_err, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (e != 0)
+    return fail(h, WFLOWB200_ERR_STATE,
+                "a wavefront wait timed out: the routing grid was not co-resident on the device "
+                "(MPS share, second context or debugger?); the results of this step are invalid");
+  return WFLOWB200_OK;
+}
 
 int layers_of(const WflowB200* h, int kind) { return kind == 1 ? h->N : kind == 2 ? h->N + 1 : 1; }
 
@@ -334,34 +323,7 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
   return WFLOWB200_OK;
 }
 
-// Device copies of the band artefacts (land domain).
-int32_t upload_bands(WflowB200* h, DomainDev& d) {
-  const Network& nw = d.nw;
-  std::vector<int32_t> slot(nw.bundle_node.size());
-  for (size_t i = 0; i < slot.size(); ++i)
-    slot[i] = nw.bundle_node[i] < 0 ? -1 : (int32_t)nw.slot_of[nw.bundle_node[i]];
-  std::vector<uint4> src(nw.bundle_node.size());
-  for (size_t i = 0; i < src.size(); ++i) {
-    const uint16_t* c = &nw.bundle_src[8 * i];
-    src[i] = make_uint4((unsigned)c[0] | ((unsigned)c[1] << 16), (unsigned)c[2] | ((unsigned)c[3] << 16),
-                        (unsigned)c[4] | ((unsigned)c[5] << 16), (unsigned)c[6] | ((unsigned)c[7] << 16));
-  }
-  std::vector<int32_t> inl_ptr(nw.bundle_inl_ptr.begin(), nw.bundle_inl_ptr.end());
-  CUDA_TRY(h, upload_raw(slot, &d.bands.slot, d.dev_arrays));
-  CUDA_TRY(h, upload_raw(src, &d.bands.src, d.dev_arrays));
-  CUDA_TRY(h, upload_raw(nw.bundle_out, &d.bands.out, d.dev_arrays));
-  CUDA_TRY(h, upload_raw(inl_ptr, &d.bands.inl_ptr, d.dev_arrays));
-  CUDA_TRY(h, upload_raw(nw.bundle_inl_out, &d.bands.inl_out, d.dev_arrays));
-  d.bands.n_bundles = (int32_t)nw.n_bundles;
-  d.bands.n_outlets = (int32_t)nw.n_band_outlets;
-  d.bands.max_inlets = (int32_t)nw.max_bundle_inlets;
-  CUDA_TRY(h, cudaMalloc((void**)&d.band_q_out,
-                         sizeof(unsigned long long) * 2 * (size_t)std::max<int64_t>(nw.n_band_outlets, 1)));
-  return WFLOWB200_OK;
-}
-
 void free_domain(DomainDev& d) {
-  cudaFree(d.band_q_out);
   cudaFree(d.chunk_of_slot);
   cudaFree(d.chunk_done);
   cudaFree(d.chunk_ssf_done);
@@ -438,34 +400,9 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
   w.fuse_soil_storage = fuse_soil_storage ? 1 : 0;
   w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
   w.smem = smem;
-  w.prof = nullptr;
-  const bool prof = h->tune.wave_prof == kind + 1;  // developer aid: dump per-chunk timing
-  const size_t prof_words = 8 * (size_t)std::max<int64_t>(d.nw.n_chunks, 1);
-  if (prof) {
-    CUDA_TRY(h, cudaMalloc((void**)&w.prof, sizeof(long long) * prof_words));
-    CUDA_TRY(h, cudaMemset(w.prof, 0, sizeof(long long) * prof_words));
-  }
+  w.err = h->d_err;
   int32_t rc = check_launch(h, launch(w), what);
   if (rc) return rc;
-  if (prof) {
-    std::vector<long long> hp(prof_words);
-    cudaStreamSynchronize(h->stream);
-    cudaMemcpy(hp.data(), w.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(w.prof);
-    FILE* fp = fopen("gpurun_out/wave_prof.csv", "w");
-    if (fp) {
-      fprintf(fp, "chunk,start_ns,end_ns,stages,nodes,wait_cyc,smid,inlets,loaded_ns,l0,l1\n");
-      long long t0 = hp[0];
-      for (int64_t c = 0; c < d.nw.n_chunks; ++c) t0 = std::min(t0, hp[8 * c]);
-      for (int64_t c = 0; c < d.nw.n_chunks; ++c) hp[8 * c + 7] -= t0;
-      for (int64_t c = 0; c < d.nw.n_chunks; ++c)
-        fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", (long long)c,
-                hp[8 * c] - t0, hp[8 * c + 1] - t0, hp[8 * c + 2], hp[8 * c + 3], hp[8 * c + 4],
-                hp[8 * c + 5], hp[8 * c + 6], hp[8 * c + 7], (long long)d.nw.chunk_l0[c],
-                (long long)d.nw.chunk_l1[c]);
-      fclose(fp);
-    }
-  }
   substeps = S;
   return WFLOWB200_OK;
 }
@@ -493,6 +430,7 @@ int32_t prepare_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int
   w.dt_fixed = dts[0];
   w.dt_last = dts[S - 1];
   w.dt = dt;
+  w.err = h->d_err;
   substeps = S;
   return WFLOWB200_OK;
 }
@@ -557,18 +495,17 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
 // streams and the ordering events (~50 kernel launches and memsets per step) are captured once
 // per time step length; issuing them one by one costs more host time than the GPU needs.
 static int32_t launch_vertical(WflowB200* h, double dt) {
-  if (h->tune.no_graph) {  // developer aid
-    return check_launch(h, launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(),
-                                                 (int)h->unsat.size(), h->engine_grid, h->stream,
-                                                 h->side_stream, h->v_ev),
-                        "update_land_hydrology_model");
-  }
+  auto issue = [&]() {
+    return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
+                                 h->slice_tile_begin.data(), h->d_tile_prio, h->d_tile_order,
+                                 h->engine_grid, h->stream, h->side_stream, h->v_ev);
+  };
+  if (!h->tune.use_graph) return check_launch(h, issue(), "update_land_hydrology_model");
   if (!h->v_graph || h->v_graph_dt != dt) {
     if (h->v_graph) { cudaGraphExecDestroy(h->v_graph); h->v_graph = nullptr; }
     cudaGraph_t g = nullptr;
     CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
-                                         h->engine_grid, h->stream, h->side_stream, h->v_ev);
+    const int rc = issue();
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     if (rc < 0 || e != cudaSuccess || !g) {
       if (g) cudaGraphDestroy(g);
@@ -588,13 +525,6 @@ static int32_t launch_vertical(WflowB200* h, double dt) {
   h->launches += h->v_graph_launches;
   return WFLOWB200_OK;
 }
-
-#ifdef WFB_NEWTON_HIST
-namespace wfb { void dump_newton_hist(); }
-#endif
-#ifdef WFB_UNSAT_HIST
-namespace wfb { void dump_unsat_hist(); }
-#endif
 
 extern "C" {
 
@@ -620,18 +550,17 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   if (cfg->n <= 0 || cfg->nriv < 0 || cfg->n_layers < 1 || cfg->n_layers > 8)
     return fail(nullptr, WFLOWB200_ERR_ARG, "n > 0, nriv >= 0, 1 <= n_layers <= 8 required");
   if (cfg->n > 0x7fffff00LL) return fail(nullptr, WFLOWB200_ERR_ARG, "n exceeds int32 slots");
-  if (cfg->kv_profile != 0 && cfg->kv_profile != 1)
-    return fail(nullptr, WFLOWB200_ERR_ARG,
-                "only exponential / exponential_constant conductivity profiles are implemented");
+  if (cfg->kv_profile < 0 || cfg->kv_profile > 3)
+    return fail(nullptr, WFLOWB200_ERR_ARG, "kv_profile must be 0 .. 3");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, WFLOWB200_ERR_CUDA, "no CUDA device: libwflow_b200 has no CPU fallback");
-  if (cudaSetDevice(cfg->device) != cudaSuccess)
-    return fail(nullptr, WFLOWB200_ERR_CUDA, "cudaSetDevice failed");
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, WFLOWB200_ERR_CUDA, "no such CUDA device");
+  DeviceGuard device_guard_(cfg->device);
 
   WflowB200* h = new WflowB200();
   h->cfg = *cfg;
-  h->tune.read();
   h->n = (int)cfg->n; h->nriv = (int)cfg->nriv; h->N = cfg->n_layers;
   h->ns = (h->n + 31) / 32 * 32;
   h->nrs = (h->nriv + 31) / 32 * 32;
@@ -709,10 +638,12 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   }
   TRY_CREATE(cudaMalloc((void**)&h->f.number_of_layers, (size_t)h->ns * sizeof(int32_t)));
   TRY_CREATE(cudaMalloc((void**)&h->f.n_unsatlayers, (size_t)h->ns * sizeof(int32_t)));
+  TRY_CREATE(cudaMalloc((void**)&h->f.nlayers_kv, (size_t)h->ns * sizeof(int32_t)));
+  TRY_CREATE(cudaMemset(h->f.nlayers_kv, 0, (size_t)h->ns * sizeof(int32_t)));
   TRY_CREATE(cudaMemset(h->f.number_of_layers, 0, (size_t)h->ns * sizeof(int32_t)));
   TRY_CREATE(cudaMemset(h->f.n_unsatlayers, 0, (size_t)h->ns * sizeof(int32_t)));
 
-  if (upload_domain(h, h->land) || upload_domain(h, h->river) || upload_bands(h, h->land))
+  if (upload_domain(h, h->land) || upload_domain(h, h->river))
     return bail(WFLOWB200_ERR_CUDA);
   {
     std::vector<int64_t> riv_land_slot(h->nriv), riv_of_land(h->n, -1);
@@ -732,20 +663,25 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
   {
     const size_t ns = (size_t)h->ns;
-    // Slices > 1 put the loop engine of a slice on a side stream under the elementwise kernels
-    // of the others (vertical.cu). Measured on B200 (1000^2): 0.610 ms with one slice, 0.583 with
-    // two, 0.60-0.63 with four to eight -- the engine tails do not overlap enough to pay for the
-    // extra launches, so one slice (one stream, no events) is the default.
-    const char* vs = getenv("WFB_V_SLICES");
-    const int n_slices = std::max(1, std::min(16, vs ? atoi(vs) : 1));
-    const size_t per = ((ns + n_slices - 1) / n_slices + 127) / 128 * 128;  // cells per slice
+    // The tiles (128 slots), ordered by the longest Brooks-Corey loop they held in the previous
+    // step, are cut into slices; the loop engine of a slice runs on a side stream under
+    // land_hydrology_kernel of the next slices (vertical.cu). Small domains: one slice.
+    const int n_tiles = (int)((ns + WFB_V_TILE - 1) / WFB_V_TILE);
+    int n_slices = cfg->vertical_slices > 0 ? cfg->vertical_slices : (n_tiles >= 2048 ? 4 : 1);
+    n_slices = std::max(1, std::min(std::min(n_slices, WFB_V_MAX_SLICES), n_tiles));
+    h->slice_tile_begin.resize(n_slices + 1);
+    for (int k = 0; k <= n_slices; ++k)
+      h->slice_tile_begin[k] = (int)((int64_t)n_tiles * k / n_slices);
+    const size_t per = ((size_t)(n_tiles + n_slices - 1) / n_slices + 1) * WFB_V_TILE;  // cells per slice
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_pool, 5 * ns * sizeof(double)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_its, ns * sizeof(int32_t)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_list,
                           (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * per * sizeof(int32_t)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count,
                           (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * sizeof(unsigned)));
-    const char* ii = getenv("WFB_INLINE_ITERS");  // tunable for experiments
+    TRY_CREATE(cudaMalloc((void**)&h->d_tile_prio, (size_t)n_tiles * sizeof(unsigned)));
+    TRY_CREATE(cudaMemset(h->d_tile_prio, 0, (size_t)n_tiles * sizeof(unsigned)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_tile_order, (size_t)n_tiles * sizeof(int32_t)));
     h->unsat.resize(n_slices);
     for (int k = 0; k < n_slices; ++k) {
       UnsatWork& u = h->unsat[k];
@@ -754,14 +690,9 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       u.its_layer = h->d_unsat_its;
       u.list = h->d_unsat_list + (size_t)k * 2 * WFB_UNSAT_BUCKETS * per;
       u.count = h->d_unsat_count + (size_t)k * 2 * WFB_UNSAT_BUCKETS;
+      u.tile_prio = h->d_tile_prio;
       u.cap = (int32_t)per;
-      u.inline_iters = ii ? atoi(ii) : 8;
-      u.diag = nullptr;
-    }
-    if (getenv("WFB_ENGINE_DIAG")) {  // developer aid: printed by wflowb200_get_stats
-      TRY_CREATE(cudaMalloc((void**)&h->d_engine_diag, 3 * sizeof(unsigned long long)));
-      TRY_CREATE(cudaMemset(h->d_engine_diag, 0, 3 * sizeof(unsigned long long)));
-      for (auto& u : h->unsat) u.diag = h->d_engine_diag;
+      u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 8;
     }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -772,6 +703,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       TRY_CREATE(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
     for (auto& e : h->v_ev) TRY_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
+  TRY_CREATE(cudaMalloc((void**)&h->d_err, sizeof(unsigned)));
+  TRY_CREATE(cudaMemset(h->d_err, 0, sizeof(unsigned)));
   TRY_CREATE(cudaMalloc((void**)&h->d_stats, sizeof(RoutingStats)));
   TRY_CREATE(cudaMemset(h->d_stats, 0, sizeof(RoutingStats)));
   TRY_CREATE(cudaMalloc((void**)&h->d_count, sizeof(unsigned long long)));
@@ -795,40 +728,10 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->grid_olf = wave_max_grid(0, h->N, h->smem_olf, cfg->device);
   h->grid_riv = wave_max_grid(1, h->N, h->smem_riv, cfg->device);
   h->grid_ssf = wave_max_grid(2, h->N, h->smem_ssf, cfg->device);
-  {
-    const size_t per_warp = band_smem_per_warp(h->N, h->land.bands.max_inlets);
-    h->warps_band = (int)std::min<size_t>(8, (size_t)(220 * 1024) / per_warp);
-    const char* bw = getenv("WFB_BAND_WARPS");  // experiments
-    if (bw && atoi(bw) >= 1) h->warps_band = std::min(h->warps_band, atoi(bw));
-    // The band kernel is kept for experiments (WFB_SSF_BANDS=1): on B200 its inflow-dependent
-    // phase shares the SM with the memory-heavy phases of the sibling warps and the chunk walk
-    // is faster at every size measured so far.
-    const char* ub = getenv("WFB_SSF_BANDS");
-    h->use_bands = ub && atoi(ub) != 0 && h->warps_band >= 1;
-    if (h->use_bands) {
-      h->smem_band = per_warp * h->warps_band;
-      h->grid_band = band_max_grid(h->N, h->warps_band, h->smem_band, cfg->device);
-      if (h->grid_band <= 0) h->use_bands = false;
-    }
-  }
-  {
-    h->smem_surface = surface_smem(h->land.dev.max_inlets, h->river.dev.max_inlets,
-                                   &h->smem_surface_per_warp);
-    h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
-    const char* fs = getenv("WFB_FUSE_SURFACE");  // 0: overland and river as separate kernels
-    h->fuse_surface = !(fs && atoi(fs) == 0) && h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive;
-    h->grid_ssf_s1 = subsurface_s1_max_grid(h->N, h->smem_ssf, cfg->device);
-    // the slim single-sub-step node halves the registers (2 CTAs per SM) but is twice as slow
-    // on B200 (1000^2: 1.98 vs 0.98 ms, 3536^2: 11.0 vs 4.6 ms): opt-in, kept for the fused kernel
-    const char* s1 = getenv("WFB_SSF_S1");
-    h->use_ssf_s1 = s1 && atoi(s1) != 0 && h->grid_ssf_s1 > 0;
-    h->grid_routing = routing_max_grid(h->N, h->smem_surface, cfg->device);
-    const char* fr = getenv("WFB_FUSE_ROUTING");  // 0: the subsurface flow in a kernel of its own
-    // measured on B200 (1000^2): 2.51 ms for the three components in one kernel at the best warp
-    // split (river 1 / subsurface 3 / overland 4 of 8) against 2.56 ms with the subsurface flow
-    // on its own -- the 2368 resident warps are too few for three wavefronts -- so it is opt-in
-    h->fuse_routing = h->fuse_surface && fr && atoi(fr) != 0 && h->grid_routing > 0;
-  }
+  h->smem_surface = surface_smem(h->land.dev.max_inlets, h->river.dev.max_inlets,
+                                 &h->smem_surface_per_warp);
+  h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
+  h->fuse_surface = h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive;
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -841,15 +744,17 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
 
 void wflowb200_destroy(WflowB200* h) {
   if (!h) return;
+  DeviceGuard device_guard_(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
+  cudaFree(h->f.nlayers_kv); cudaFree(h->f.olf_newton_trace); cudaFree(h->f.riv_newton_trace);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
   for (auto st : h->side_stream) if (st) cudaStreamSynchronize(st);
   cudaFree(h->d_unsat_pool); cudaFree(h->d_unsat_its); cudaFree(h->d_unsat_list);
   cudaFree(h->d_unsat_count);
-  cudaFree(h->d_engine_diag);
+  cudaFree(h->d_tile_prio); cudaFree(h->d_tile_order); cudaFree(h->d_err);
   if (h->v_graph) cudaGraphExecDestroy(h->v_graph);
   for (auto e : h->v_ev) if (e) cudaEventDestroy(e);
   for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
@@ -867,7 +772,6 @@ void wflowb200_destroy(WflowB200* h) {
 
 static int32_t field_common(WflowB200* h, int32_t id, int64_t sc, int64_t sl, int& kind,
                             int& layers, int& count, size_t& extent) {
-  if (!h) return WFLOWB200_ERR_ARG;
   if (id < 0 || id >= WFLOWB200_NUM_FIELDS) return fail(h, WFLOWB200_ERR_ARG, "bad field id");
   kind = kFieldKinds[id];
   layers = layers_of(h, kind);
@@ -884,6 +788,7 @@ static int32_t field_common(WflowB200* h, int32_t id, int64_t sc, int64_t sl, in
 }
 
 int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t sc, int64_t sl) {
+  WFB_ENTER(h);
   int kind, layers, count; size_t extent;
   int32_t rc = field_common(h, id, sc, sl, kind, layers, count, extent);
   if (rc) return rc;
@@ -899,6 +804,7 @@ int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t
 }
 
 int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, int64_t sl) {
+  WFB_ENTER(h);
   int kind, layers, count; size_t extent;
   int32_t rc = field_common(h, id, sc, sl, kind, layers, count, extent);
   if (rc) return rc;
@@ -911,16 +817,16 @@ int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, i
                                       kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_stage, extent * sizeof(double), cudaMemcpyDeviceToHost,
                               h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return WFLOWB200_OK;
+  return check_device_error(h);
 }
 
 int32_t wflowb200_set_field_i64(WflowB200* h, int32_t which, const int64_t* src) {
-  if (!h || !src) return WFLOWB200_ERR_ARG;
-  if (which != 0 && which != 1) return fail(h, WFLOWB200_ERR_ARG, "bad int field");
+  WFB_ENTER(h);
+  if (!src) return WFLOWB200_ERR_ARG;
+  if (which < 0 || which > 2) return fail(h, WFLOWB200_ERR_ARG, "bad int field");
   std::vector<int32_t> tmp(h->n);
   for (int p = 0; p < h->n; ++p) tmp[p] = (int32_t)src[h->land.nw.perm[p] - 1];
-  int32_t* dst = which == 0 ? h->f.number_of_layers : h->f.n_unsatlayers;
+  int32_t* dst = which == 0 ? h->f.number_of_layers : which == 1 ? h->f.n_unsatlayers : h->f.nlayers_kv;
   CUDA_TRY(h, cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(int32_t),
                               cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -928,10 +834,11 @@ int32_t wflowb200_set_field_i64(WflowB200* h, int32_t which, const int64_t* src)
 }
 
 int32_t wflowb200_get_field_i64(WflowB200* h, int32_t which, int64_t* dst) {
-  if (!h || !dst) return WFLOWB200_ERR_ARG;
-  if (which != 0 && which != 1) return fail(h, WFLOWB200_ERR_ARG, "bad int field");
+  WFB_ENTER(h);
+  if (!dst) return WFLOWB200_ERR_ARG;
+  if (which < 0 || which > 2) return fail(h, WFLOWB200_ERR_ARG, "bad int field");
   std::vector<int32_t> tmp(h->n);
-  const int32_t* src = which == 0 ? h->f.number_of_layers : h->f.n_unsatlayers;
+  const int32_t* src = which == 0 ? h->f.number_of_layers : which == 1 ? h->f.n_unsatlayers : h->f.nlayers_kv;
   CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(int32_t),
                               cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -940,7 +847,8 @@ int32_t wflowb200_get_field_i64(WflowB200* h, int32_t which, int64_t* dst) {
 }
 
 int32_t wflowb200_set_forcing(WflowB200* h, const double* P, const double* PET, const double* T) {
-  if (!h || !P || !PET || !T) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
+  if (!P || !PET || !T) return WFLOWB200_ERR_ARG;
   // the previous forcing must have been consumed before the staging buffers are reused
   CUDA_TRY(h, cudaEventSynchronize(h->forcing_consumed));
   const size_t nb = (size_t)h->n * sizeof(double);
@@ -973,7 +881,7 @@ int32_t wflowb200_set_forcing(WflowB200* h, const double* P, const double* PET, 
 }
 
 int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   int32_t rc = wait_forcing(h);
   if (rc) return rc;
   if (h->nriv > 0) {  // river h -> land grid (runoff.jl:77-79)
@@ -983,69 +891,17 @@ int32_t wflowb200_update_land_hydrology_model(WflowB200* h, double dt) {
 }
 
 int32_t wflowb200_exchange_recharge(WflowB200* h) {
-  if (!h) return WFLOWB200_ERR_ARG;
-#ifdef WFB_UNSAT_HIST
-  cudaStreamSynchronize(h->stream);
-  wfb::dump_unsat_hist();
-#endif
+  WFB_ENTER(h);
   return check_launch(h, launch_exchange_recharge(h->f, h->kc, h->stream), "exchange_recharge");
 }
 
 int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   if (h->cfg.adaptive)
     return run_wave_adaptive(h, h->land, dt, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
                              [&](const WaveLaunch& w) {
                                return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
                              }, "update_subsurface_flow_model");
-  if (h->use_bands && !h->tune.wave_prof) {
-    std::vector<double> dts;
-    if (fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1) {  // one sub-step: the band kernel
-      BandLaunch w{};
-      w.queue = h->d_queue + 2 * 32;
-      w.q_out = h->land.band_q_out;
-      w.dt = dts[0];
-      w.warps = h->warps_band;
-      w.smem = h->smem_band;
-      w.grid = (int)std::max<int64_t>(
-          1, std::min<int64_t>(h->grid_band, (h->land.nw.n_bundles + w.warps - 1) / w.warps));
-      h->sub_ssf = 1;
-      const bool prof = h->tune.band_prof;  // developer aid: per-bundle timing
-      const size_t prof_words = 8 * (size_t)std::max<int64_t>(h->land.nw.n_bundles, 1);
-      if (prof) {
-        CUDA_TRY(h, cudaMalloc((void**)&w.prof, sizeof(long long) * prof_words));
-        CUDA_TRY(h, cudaMemset(w.prof, 0, sizeof(long long) * prof_words));
-      }
-      int32_t rc = check_launch(h, launch_subsurface_band(h->f, h->kc, h->land.bands, h->N, w, h->stream),
-                                "update_subsurface_flow_model");
-      if (prof && !rc) {
-        std::vector<long long> hp(prof_words);
-        cudaStreamSynchronize(h->stream);
-        cudaMemcpy(hp.data(), w.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        cudaFree(w.prof);
-        FILE* fp = fopen("gpurun_out/band_prof.csv", "w");
-        if (fp) {
-          fprintf(fp, "bundle,t_start,t_prep,t_inlets,t_solved,t_end,smid,inlets\n");
-          long long t0 = hp[0];
-          for (int64_t b = 0; b < h->land.nw.n_bundles; ++b) t0 = std::min(t0, hp[8 * b]);
-          for (int64_t b = 0; b < h->land.nw.n_bundles; ++b)
-            fprintf(fp, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", (long long)b, hp[8 * b] - t0,
-                    hp[8 * b + 1] - t0, hp[8 * b + 2] - t0, hp[8 * b + 3] - t0, hp[8 * b + 4] - t0,
-                    hp[8 * b + 5], hp[8 * b + 6]);
-          fclose(fp);
-        }
-      }
-      return rc;
-    }
-  }
-  {
-    std::vector<double> dts;
-    if (h->use_ssf_s1 && !h->tune.wave_prof && fixed_substeps(dt, h->cfg.dt_ssf, dts) == 1)
-      return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf_s1, h->smem_ssf, h->sub_ssf,
-                      [&](const WaveLaunch& w) {
-                        return launch_subsurface_s1(h->f, h->kc, h->land.dev, h->N, w, h->stream);
-                      }, "update_subsurface_flow_model");
-  }
   return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
                   [&](const WaveLaunch& w) {
                     return launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, w, h->stream);
@@ -1063,8 +919,7 @@ static int32_t update_subsurface_and_soil_storage(WflowB200* h, double dt, bool*
   const bool wide = h->land.nw.n_wave_levels > 0 &&
                     h->land.nw.n / h->land.nw.n_wave_levels >= WFB_PIECE_WIDE_LEVEL;
   const bool want = h->tune.fuse_soil_storage >= 0 ? h->tune.fuse_soil_storage != 0 : !wide;
-  if (h->cfg.adaptive || !want || h->tune.wave_prof ||
-      (h->use_bands && h->cfg.dt_ssf >= dt) || h->use_ssf_s1)
+  if (h->cfg.adaptive || !want)
     return wflowb200_update_subsurface_flow_model(h, dt);
   *fused = true;
   return run_wave(h, h->land, dt, h->cfg.dt_ssf, 2, 2, h->grid_ssf, h->smem_ssf, h->sub_ssf,
@@ -1074,20 +929,20 @@ static int32_t update_subsurface_and_soil_storage(WflowB200* h, double dt, bool*
 }
 
 int32_t wflowb200_update_soil_water_storage(WflowB200* h, double dt) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   (void)dt;
   return check_launch(h, launch_soil_water_storage(h->f, h->kc, h->N, h->stream),
                       "update_soil_water_storage");
 }
 
 int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   return check_launch(h, launch_lateral_inflow_overland(h->f, h->kc, h->stream),
                       "update_lateral_inflow(overland)");
 }
 
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   if (h->cfg.adaptive)
     return run_wave_adaptive(h, h->land, dt, 0, 2, h->grid_olf, h->smem_olf, h->sub_land,
                              [&](const WaveLaunch& w) {
@@ -1100,13 +955,13 @@ int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
 }
 
 int32_t wflowb200_update_lateral_inflow_river(WflowB200* h) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   return check_launch(h, launch_lateral_inflow_river(h->f, h->kc, h->stream),
                       "update_lateral_inflow(river)");
 }
 
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   if (h->nriv == 0) return WFLOWB200_OK;
   if (h->cfg.adaptive)
     return run_wave_adaptive(h, h->river, dt, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
@@ -1136,6 +991,7 @@ static int32_t update_surface_fused(WflowB200* h, double dt) {
   sync.land_chunk_of_slot = h->land.chunk_of_slot;
   sync.period = h->tune.river_period;
   sync.river_share = h->tune.river_share;
+  sync.err = h->d_err;
   return check_launch(h, launch_surface_wave(h->f, h->kc, h->land.dev, h->river.dev, wl, wr, sync, false, h->stream),
                       "update_overland_flow_model + update_river_flow_model");
 }
@@ -1154,9 +1010,7 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   const bool wide = h->land.nw.n_wave_levels > 0 &&
                     h->land.nw.n / h->land.nw.n_wave_levels >= WFB_OVERLAP_MAX_LEVEL_WIDTH;
   const bool want = h->tune.overlap_ssf >= 0 ? h->tune.overlap_ssf != 0 : !wide;
-  if (!want || !h->fuse_surface || h->cfg.adaptive || h->use_bands || h->use_ssf_s1 ||
-      h->tune.wave_prof)
-    return WFLOWB200_OK;
+  if (!want || !h->fuse_surface || !h->tune.fuse_surface || h->cfg.adaptive) return WFLOWB200_OK;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
   // SMs (= CTAs) of the subsurface sweep; measured at 1000^2 (routing ms): 44 SMs 2.38, 52: 1.91, 60: 1.83, 64: 1.89, 74: 2.11, 84: 2.38
@@ -1187,6 +1041,7 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   ws.dt_last = dts[S - 1];
   ws.dt = dt;
   ws.smem = h->smem_ssf;
+  ws.err = h->d_err;
   ws.grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ssf_ctas, h->grid_ssf), h->land.nw.n_chunks));
   ws.fuse_soil_storage = 1;
   ws.done_flags = h->land.chunk_ssf_done;
@@ -1206,6 +1061,7 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   sync.land_chunk_of_slot = h->land.chunk_of_slot;
   sync.period = h->tune.river_period;
   sync.river_share = h->tune.river_share;
+  sync.err = h->d_err;
   // every reset before the first kernel: nothing may sit between the two launches
   reset_surface_wave(h->land.dev, h->river.dev, wl, wr, h->stream);
   if ((rc = check_launch(h, launch_subsurface_wave(h->f, h->kc, h->land.dev, h->N, ws, h->stream),
@@ -1216,53 +1072,8 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   return rc;
 }
 
-// update_subsurface_flow_model! (single sub-step) + update_soil_water_storage! + the overland
-// and river flow in one launch (routing.cu: routing_wave_kernel). Returns 1 (and launches
-// nothing) when the configuration needs the separate kernels.
-static int32_t update_routing_fused(WflowB200* h, double dt, bool* done) {
-  *done = false;
-  std::vector<double> dts;
-  if (!h->fuse_routing || fixed_substeps(dt, h->cfg.dt_ssf, dts) != 1) return WFLOWB200_OK;
-  WaveLaunch ws{}, wl{}, wr{};
-  int32_t rc;
-  // the subsurface and overland flow walk the same land chunks: separate outlet buffers
-  const size_t need_ssf = (size_t)std::max<int64_t>(h->land.nw.n_outlets, 1) * 2;
-  if (need_ssf > h->ssf_q_out_words) {
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->ssf_q_out);
-    h->ssf_q_out = nullptr;
-    h->ssf_q_out_words = 0;
-    CUDA_TRY(h, cudaMalloc((void**)&h->ssf_q_out, need_ssf * sizeof(unsigned long long)));
-    h->ssf_q_out_words = need_ssf;
-  }
-  if ((rc = prepare_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, wl, h->sub_land, "update_overland_flow_model"))) return rc;
-  if ((rc = prepare_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, wr, h->sub_river, "update_river_flow_model"))) return rc;
-  ws.queue = h->d_queue + 2 * 32;
-  ws.q_out = h->ssf_q_out;
-  ws.stats = h->d_stats;
-  ws.S = 1;
-  ws.dt_fixed = ws.dt_last = dts[0];
-  ws.dt = dt;
-  h->sub_ssf = 1;
-  ws.smem = wl.smem = wr.smem = h->smem_surface;
-  ws.smem_per_warp = wl.smem_per_warp = wr.smem_per_warp = h->smem_surface_per_warp;
-  SurfaceSync sync{};
-  sync.land_done = h->land.chunk_done;
-  sync.ssf_done = h->land.chunk_ssf_done;
-  sync.epoch = ++h->surface_epoch;
-  sync.land_chunk_of_slot = h->land.chunk_of_slot;
-  sync.period = h->tune.r_period; sync.river_share = h->tune.r_river; sync.ssf_share = h->tune.r_ssf;
-  const int64_t warps_needed = 2 * h->land.nw.n_chunks + h->river.nw.n_chunks;
-  ws.grid = wl.grid = wr.grid =
-      (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_routing, (warps_needed + 7) / 8));
-  rc = check_launch(h, launch_routing_wave(h->f, h->kc, h->land.dev, h->river.dev, h->N, ws, wl, wr, sync, h->stream),
-                    "routing (subsurface + soil storage + overland + river)");
-  *done = rc == WFLOWB200_OK;
-  return rc;
-}
-
 int32_t wflowb200_update_total_water_storage(WflowB200* h) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   return check_launch(h, launch_total_water_storage(h->f, h->kc, h->riv_of_land, h->stream),
                       "update_total_water_storage");
 }
@@ -1280,7 +1091,7 @@ static int32_t book_stage_times(WflowB200* h) {
 }
 
 int32_t wflowb200_update_model(WflowB200* h, double dt) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   int32_t rc;
   auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->ev[i], h->stream); };
   mark(0);
@@ -1295,8 +1106,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   // subsurface water table depth (the separate entry point stays for the fine-grained sequence)
   mark(3);
   bool fused = false;
-  if ((rc = update_routing_fused(h, dt, &fused))) return rc;
-  if (!fused && (rc = update_routing_overlapped(h, dt, &fused))) return rc;
+  if ((rc = update_routing_overlapped(h, dt, &fused))) return rc;
   if (fused) {  // the three wavefronts overlapped (timed as "subsurface")
     mark(4); mark(5); mark(6); mark(7); mark(8);
     if ((rc = wflowb200_update_total_water_storage(h))) return rc;
@@ -1308,7 +1118,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
   mark(4);
   if (!soil_fused && (rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater
   mark(5);
-  if (h->fuse_surface) {  // overland and river wavefronts overlapped (timed as "overland")
+  if (h->fuse_surface && h->tune.fuse_surface) {  // overland and river wavefronts overlapped (timed as "overland")
     if ((rc = update_surface_fused(h, dt))) return rc;
     mark(6);
     mark(7);
@@ -1341,14 +1151,60 @@ int32_t wflowb200_selftest_math(int32_t device, int64_t n, double* out6) {
 }
 
 int32_t wflowb200_synchronize(WflowB200* h) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
+  return check_device_error(h);
+}
+
+int32_t wflowb200_newton_trace(WflowB200* h, int32_t enable) {
+  WFB_ENTER(h);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->f.olf_newton_trace); cudaFree(h->f.riv_newton_trace);
+  h->f.olf_newton_trace = h->f.riv_newton_trace = nullptr;
+  if (enable) {
+    CUDA_TRY(h, cudaMalloc((void**)&h->f.olf_newton_trace, (size_t)h->ns * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->f.riv_newton_trace, (size_t)std::max(h->nrs, 32) * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMemset(h->f.olf_newton_trace, 0, (size_t)h->ns * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMemset(h->f.riv_newton_trace, 0, (size_t)std::max(h->nrs, 32) * sizeof(int32_t)));
+  }
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_get_newton_trace(WflowB200* h, int32_t domain, int64_t* dst) {
+  WFB_ENTER(h);
+  if (!dst) return WFLOWB200_ERR_ARG;
+  const bool riv = domain == WFLOWB200_DOMAIN_RIVER;
+  const int32_t* src = riv ? h->f.riv_newton_trace : h->f.olf_newton_trace;
+  if (!src) return fail(h, WFLOWB200_ERR_STATE, "newton trace is not enabled");
+  const DomainDev& d = riv ? h->river : h->land;
+  const int n = riv ? h->nriv : h->n;
+  std::vector<int32_t> tmp(n);
+  CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < n; ++p) dst[d.nw.perm[p] - 1] = tmp[p];
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value) {
+  WFB_ENTER(h);
+  if (!name) return WFLOWB200_ERR_ARG;
+  Tuning& t = h->tune;
+  const std::string k(name);
+  if (k == "fuse_soil_storage") t.fuse_soil_storage = value;
+  else if (k == "overlap_subsurface") t.overlap_ssf = value;
+  else if (k == "overlap_subsurface_sms") t.ssf_overlap_sms = value;
+  else if (k == "fuse_surface") t.fuse_surface = value != 0;
+  else if (k == "surface_river_share") { if (value >= 1 && value < t.river_period) t.river_share = value; }
+  else if (k == "surface_river_period") { if (value >= 2 && value > t.river_share) t.river_period = value; }
+  else if (k == "vertical_graph") t.use_graph = value != 0;
+  else if (k == "kinwave_root_each_substep") h->kc.kw_root_each_substep = value != 0;
+  else return fail(h, WFLOWB200_ERR_ARG, "unknown option: " + k);
   return WFLOWB200_OK;
 }
 
 int32_t wflowb200_get_artifact(WflowB200* h, int32_t domain, int32_t id, int64_t* dst,
                                int64_t capacity, int64_t* len_out) {
-  if (!h || !len_out) return WFLOWB200_ERR_ARG;
+  if (!h || !len_out) return WFLOWB200_ERR_ARG;  // host data only: no device guard
   const Network& nw = domain == WFLOWB200_DOMAIN_RIVER ? h->river.nw : h->land.nw;
   return copy_artifact(nw, id, dst, capacity, len_out, h->err);
 }
@@ -1371,20 +1227,11 @@ int32_t wflowb200_network_get(const WflowB200Network* net, int32_t domain, int32
 void wflowb200_network_destroy(WflowB200Network* net) { delete net; }
 
 int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
-  if (!h || !out) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
+  if (!out) return WFLOWB200_ERR_ARG;
   RoutingStats rs{};
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-#ifdef WFB_NEWTON_HIST
-  wfb::dump_newton_hist();
-#endif
+  { int32_t rc = check_device_error(h); if (rc) return rc; }
   CUDA_TRY(h, cudaMemcpy(&rs, h->d_stats, sizeof(rs), cudaMemcpyDeviceToHost));
-  if (h->d_engine_diag) {
-    unsigned long long dg[3] = {0, 0, 0};
-    cudaMemcpy(dg, h->d_engine_diag, sizeof(dg), cudaMemcpyDeviceToHost);
-    cudaMemset(h->d_engine_diag, 0, sizeof(dg));
-    fprintf(stderr, "loop engine since the last call: %llu suspended loops, %llu trips, longest %llu\n",
-            dg[0], dg[1], dg[2]);
-  }
   memset(out, 0, sizeof(*out));
   out->newton_calls_land = (int64_t)rs.newton_calls_land;
   out->newton_iters_land = (int64_t)rs.newton_iters_land;
@@ -1405,7 +1252,7 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
 }
 
 int32_t wflowb200_set_timing(WflowB200* h, int32_t enabled) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   h->timing = enabled != 0;
   for (auto& m : h->ms) m = 0.0;
   h->timed_steps = 0;
@@ -1413,12 +1260,13 @@ int32_t wflowb200_set_timing(WflowB200* h, int32_t enabled) {
 }
 
 int32_t wflowb200_timer_start(WflowB200* h) {
-  if (!h) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
   CUDA_TRY(h, cudaEventRecord(h->tm[0], h->stream));
   return WFLOWB200_OK;
 }
 int32_t wflowb200_timer_stop(WflowB200* h, double* elapsed_ms) {
-  if (!h || !elapsed_ms) return WFLOWB200_ERR_ARG;
+  WFB_ENTER(h);
+  if (!elapsed_ms) return WFLOWB200_ERR_ARG;
   CUDA_TRY(h, cudaEventRecord(h->tm[1], h->stream));
   CUDA_TRY(h, cudaEventSynchronize(h->tm[1]));
   float ms = 0.f;

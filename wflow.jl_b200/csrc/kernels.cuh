@@ -11,23 +11,27 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 // Brooks-Corey loops (one record per cell) and the lists of suspended cells, bucketed by
 // log2(trip count), double-buffered over the engine's rounds.
 #define WFB_UNSAT_BUCKETS 6
-#define WFB_V_SIDE_STREAMS 8
+#define WFB_V_SIDE_STREAMS 4
+#define WFB_V_MAX_SLICES 8
+#define WFB_V_TILE 128                        // cells per tile (= CTA of land_hydrology_kernel)
 struct UnsatWork {
   double *usd, *sum_ast, *kv_it, *l_sat, *c;  // ns doubles each
   int32_t* its_layer;                         // ns: trip count | layer << 24
   int32_t* list;                              // [2][WFB_UNSAT_BUCKETS][cap] cell slots
   unsigned* count;                            // [2][WFB_UNSAT_BUCKETS]
-  int32_t cap;                                // capacity of one list (= ns)
+  unsigned* tile_prio;                        // per tile: longest suspended loop of this step
+  int32_t cap;                                // capacity of one list (cells of the slice)
   int32_t inline_iters;                       // loops up to this many trips run in line
-  unsigned long long* diag;                   // developer aid: {loops, trips, longest} or nullptr
 };
-// engine_grid: CTAs of the persistent engine kernels (a few per SM). The cells are cut into
-// n_slices slices (one UnsatWork each); the loop engine of slice k runs on side[k % WFB_V_SIDE_STREAMS]
-// (high-priority streams) under the elementwise kernels of the next slices on s; ev holds
-// 2 * n_slices events.
+// engine_grid: CTAs of the engine kernels (a few per SM). The tiles, in the order written by
+// tile_order_kernel into tile_order, are cut into n_slices slices (slice k = ordered tiles
+// [slice_tile_begin[k], slice_tile_begin[k+1]); one UnsatWork each); the loop engine of slice k
+// runs on side[k % WFB_V_SIDE_STREAMS] (high-priority streams) under land_hydrology_kernel of the
+// next slices on s; ev holds 2 * n_slices events.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork* w, int n_slices, int engine_grid, cudaStream_t s,
-                          cudaStream_t const* side, cudaEvent_t const* ev);
+                          const UnsatWork* w, int n_slices, const int* slice_tile_begin,
+                          unsigned* tile_prio, int32_t* tile_order, int engine_grid,
+                          cudaStream_t s, cudaStream_t const* side, cudaEvent_t const* ev);
 // self-test of device_math.cuh: out[6] (device, zeroed) receives bit patterns of the maxima
 int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
@@ -60,9 +64,7 @@ struct WaveLaunch {
   size_t smem;                // dynamic shared memory of the kernel (wave_smem)
   unsigned smem_per_warp;     // bytes of a warp's region (0: the component's own layout);
                               // set when two components share one kernel
-  long long* prof;            // developer aid (WFB_WAVE_PROF): 8 x n_chunks int64 written by
-                              // each chunk: start ns, end ns, stages, nodes, barrier-wait cycles
-                              // of thread 0, SM id, inlets, busy cycles of the fetch warp
+  unsigned* err;              // device: the handle's error word (bounded waits, routing.cu)
 };
 
 // Overland and river flow in ONE kernel (launch_surface_wave): the warps of the grid are split
@@ -74,11 +76,10 @@ struct SurfaceSync {
   unsigned* ssf_done;                  // device: per land chunk, subsurface flow + soil water
                                        // storage of its cells are final (nullptr: the
                                        // subsurface flow ran in a kernel of its own)
-  int ssf_share;                       // warp g serves the subsurface flow if
-                                       // river_share <= g % period < river_share + ssf_share
   unsigned epoch;                      // this launch
   const int32_t* land_chunk_of_slot;   // land slot -> land chunk
   int period, river_share;             // warp g serves the river if g % period < river_share
+  unsigned* err;                       // device: the handle's error word (bounded waits)
 };
 // kind: 0 overland, 1 river, 2 subsurface
 int wave_block();
@@ -92,15 +93,6 @@ int launch_surface_wave(const DevFields& f, const KCfg& c, const DevNet& land, c
                         bool overlap_previous, cudaStream_t s);
 void reset_surface_wave(const DevNet& land, const DevNet& river, const WaveLaunch& wl,
                         const WaveLaunch& wr, cudaStream_t s);
-// the single-sub-step subsurface flow with the slim node (about half the registers)
-int subsurface_s1_max_grid(int n_layers, size_t smem, int device);
-int launch_subsurface_s1(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,
-                         const WaveLaunch& w, cudaStream_t s);
-// subsurface flow (single sub-step) + update_soil_water_storage! + overland + river in one kernel
-int routing_max_grid(int n_layers, size_t smem, int device);
-int launch_routing_wave(const DevFields& f, const KCfg& c, const DevNet& land, const DevNet& river,
-                        int n_layers, const WaveLaunch& ws, const WaveLaunch& wl,
-                        const WaveLaunch& wr, const SurfaceSync& sync, cudaStream_t s);
 size_t wave_smem(int kind, int max_inlets);
 int wave_max_grid(int kind, int n_layers, size_t smem, int device);  // co-resident CTAs
 int launch_overland_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
@@ -109,19 +101,6 @@ int launch_river_wave(const DevFields& f, const KCfg& c, const DevNet& net, cons
                       cudaStream_t s);
 int launch_subsurface_wave(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,
                            const WaveLaunch& w, cudaStream_t s);
-// single-sub-step subsurface flow over bands (routing.cu: subsurface_band_kernel)
-struct BandLaunch {
-  unsigned* queue;            // device: next bundle to hand out (zeroed by the launcher)
-  unsigned long long* q_out;  // device: n_outlets x 2 published values (all-ones = not yet)
-  double dt;                  // the sub-step = the model time step
-  int grid, warps;            // CTAs and warps per CTA
-  size_t smem;
-  long long* prof;            // developer aid (WFB_BAND_PROF): 8 int64 per bundle
-};
-size_t band_smem_per_warp(int n_layers, int max_inlets);
-int band_max_grid(int n_layers, int warps, size_t smem, int device);
-int launch_subsurface_band(const DevFields& f, const KCfg& c, const DevBands& bd, int n_layers,
-                           const BandLaunch& w, cudaStream_t s);
 int launch_lateral_inflow_overland(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_lateral_inflow_river(const DevFields& f, const KCfg& c, cudaStream_t s);
 

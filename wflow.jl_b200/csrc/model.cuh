@@ -20,6 +20,9 @@ struct DevFields {
   int32_t* number_of_layers;   // land
   int32_t* n_unsatlayers;      // land
   int32_t* riv_land_slot;      // river slot -> land slot
+  int32_t* nlayers_kv;         // land (KvLayeredExponential only)
+  int32_t* olf_newton_trace;   // land / river, or nullptr: Newton iterations of kinematic_wave
+  int32_t* riv_newton_trace;   // per node since wflowb200_newton_trace(h, 1)
 };
 
 // One routing domain (land or river) as the wavefront kernels see it. Slots are ordered by
@@ -56,24 +59,12 @@ struct DevNet {
   const uint8_t* inl_level;     // per inlet edge: level (inside the chunk) of the receiving node
 };
 
-// The land domain as the single-sub-step subsurface kernel sees it (network.hpp: bands,
-// fragments, bundles): one warp walks a bundle row by row, one lane per node of the row.
-#define WFB_BAND_DEPTH 4
-struct DevBands {
-  int32_t n_bundles, n_outlets, max_inlets;
-  const int32_t* slot;     // n_bundles * WFB_BAND_DEPTH * 32: land slot or -1
-  const uint4* src;        // per entry: 8 x 16-bit upstream sources in ascending node id: lane in
-                           // the previous row (< 32), 0x8000 | k for the bundle's k-th inlet,
-                           // 0xffff none
-  const int32_t* out;      // per entry: outlet number if the node feeds another bundle, else -1
-  const int32_t* inl_ptr;  // n_bundles + 1
-  const int32_t* inl_out;  // per inlet: outlet number of the producer
-};
-
 struct KCfg {
   int32_t n, nriv, ns, nrs;
   int32_t gash, has_lai, snow, glacier, soil_infiltration_reduction, kv_profile;
   double qroot;                // KIN_WAVE_MIN_FLOW^0.2
+  int32_t kw_root_each_substep; // 1: u_prev = pow(q_prev, 0.2) before every solve, like the
+                               // reference (default 0: carried, see routing.cu: KwState)
 };
 
 }  // namespace wfb

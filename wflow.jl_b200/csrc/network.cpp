@@ -432,155 +432,4 @@ void build_chunks(Network& nw, int64_t cap, int64_t piece_depth) {
   nw.chunk_clp_off[nw.n_chunks] = (int64_t)nw.clp.size();
 }
 
-// Bands, fragments and bundles of the single-sub-step wavefront. Rows are aligned on the
-// distance to the outlet: a node with dist % depth == 0 (pits included) is a fragment root and
-// sits in the last row of its band, so inside a band every edge goes from row r to row r + 1
-// and a fragment has exactly one outlet (its root). A fragment that would put more than 32
-// nodes into one row is split at its root (the upstream neighbours of the root become roots);
-// such a producer fragment gets a smaller class than its consumer, bundles hold fragments of
-// one (band, class) only and are executed in ascending (band, class): a topological order of
-// the bundle DAG.
-void build_bands(Network& nw, int64_t depth) {
-  const int64_t n = nw.n, D = std::max<int64_t>(1, depth);
-  nw.band_depth = D;
-  std::vector<int64_t> dist(n, 0);
-  int64_t dmax = 0;
-  for (int64_t k = n - 1; k >= 0; --k) {
-    const int64_t v = nw.order[k] - 1, d = nw.down[v];
-    dist[v] = d ? dist[d - 1] + 1 : 0;
-    dmax = std::max(dmax, dist[v]);
-  }
-  auto row_of = [&](int64_t v) { return (D - 1) - (dist[v] % D); };
-  auto band_of = [&](int64_t v) { return dist[v] / D; };  // larger = further upstream
-  std::vector<uint8_t> forced(n, 0);
-  std::vector<int64_t> fid(n, -1), root_of_frag;
-  std::vector<int32_t> cnt;  // per fragment and row
-  for (;;) {
-    root_of_frag.clear();
-    for (int64_t k = n - 1; k >= 0; --k) {  // downstream first
-      const int64_t v = nw.order[k] - 1;
-      if (nw.down[v] == 0 || dist[v] % D == 0 || forced[v]) {
-        fid[v] = (int64_t)root_of_frag.size();
-        root_of_frag.push_back(v);
-      } else {
-        fid[v] = fid[nw.down[v] - 1];
-      }
-    }
-    cnt.assign(root_of_frag.size() * (size_t)D, 0);
-    for (int64_t v = 0; v < n; ++v) cnt[fid[v] * D + row_of(v)]++;
-    bool again = false;
-    for (size_t f = 0; f < root_of_frag.size(); ++f) {
-      bool wide = false;
-      for (int64_t r = 0; r < D; ++r) wide |= cnt[f * D + r] > 32;
-      if (!wide) continue;
-      const int64_t v = root_of_frag[f];
-      for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1]; ++e) {
-        const int64_t u = nw.in_idx[e] - 1;
-        if (fid[u] == (int64_t)f) { forced[u] = 1; again = true; }
-      }
-    }
-    if (!again) break;
-  }
-  const int64_t nf = (int64_t)root_of_frag.size();
-  // class of a fragment inside its band (0 unless fragments were split)
-  std::vector<int64_t> cls(nf, 0);
-  for (int64_t k = 0; k < n; ++k) {  // upstream first: cls of a producer is final at its root
-    const int64_t v = nw.order[k] - 1;
-    if (root_of_frag[fid[v]] != v || nw.down[v] == 0) continue;
-    const int64_t dn = nw.down[v] - 1;
-    if (band_of(dn) == band_of(v)) cls[fid[dn]] = std::max(cls[fid[dn]], cls[fid[v]] + 1);
-  }
-  // execution order of the fragments: upstream bands first, then class, then root id
-  std::vector<int64_t> frags(nf);
-  for (int64_t f = 0; f < nf; ++f) frags[f] = f;
-  std::sort(frags.begin(), frags.end(), [&](int64_t a, int64_t b) {
-    const int64_t ba = band_of(root_of_frag[a]), bb = band_of(root_of_frag[b]);
-    if (ba != bb) return ba > bb;
-    if (cls[a] != cls[b]) return cls[a] < cls[b];
-    return root_of_frag[a] < root_of_frag[b];
-  });
-  // next-fit packing of the fragments of one (band, class) into bundles
-  std::vector<int64_t> bundle_of_frag(nf, -1);
-  std::vector<int32_t> fill(D, 0);
-  int64_t nb = 0, cur_band = -1, cur_cls = -1;
-  bool open = false;
-  for (int64_t f : frags) {
-    const int64_t b = band_of(root_of_frag[f]);
-    bool fits = open && b == cur_band && cls[f] == cur_cls;
-    for (int64_t r = 0; fits && r < D; ++r) fits = fill[r] + cnt[f * D + r] <= 32;
-    if (!fits) {
-      ++nb;
-      std::fill(fill.begin(), fill.end(), 0);
-      cur_band = b; cur_cls = cls[f]; open = true;
-    }
-    for (int64_t r = 0; r < D; ++r) fill[r] += cnt[f * D + r];
-    bundle_of_frag[f] = nb - 1;
-  }
-  nw.n_bundles = nb;
-  // lanes: per bundle and row, nodes in ascending (fragment order, node id) = ascending node id
-  // inside a fragment; a simple counting pass in node-id order per fragment keeps it O(n log n)
-  nw.bundle_node.assign((size_t)nb * D * 32, -1);
-  std::vector<int64_t> lane_of(n, -1), bundle_of(n, -1);
-  {
-    std::vector<int64_t> nodes(n);
-    for (int64_t v = 0; v < n; ++v) { nodes[v] = v; bundle_of[v] = bundle_of_frag[fid[v]]; }
-    std::vector<int64_t> frag_rank(nf);
-    for (int64_t i = 0; i < nf; ++i) frag_rank[frags[i]] = i;
-    std::sort(nodes.begin(), nodes.end(), [&](int64_t a, int64_t b) {
-      if (bundle_of[a] != bundle_of[b]) return bundle_of[a] < bundle_of[b];
-      const int64_t ra = row_of(a), rb = row_of(b);
-      if (ra != rb) return ra < rb;
-      if (fid[a] != fid[b]) return frag_rank[fid[a]] < frag_rank[fid[b]];
-      return a < b;
-    });
-    int64_t pb = -1, pr = -1, lane = 0;
-    for (int64_t v : nodes) {
-      const int64_t b = bundle_of[v], r = row_of(v);
-      if (b != pb || r != pr) { pb = b; pr = r; lane = 0; }
-      lane_of[v] = lane;
-      nw.bundle_node[((size_t)b * D + r) * 32 + lane] = (int32_t)v;
-      ++lane;
-    }
-  }
-  // edges, outlets, inlets
-  nw.bundle_src.assign((size_t)nb * D * 32 * 8, 0xffff);
-  nw.bundle_out.assign((size_t)nb * D * 32, -1);
-  nw.bundle_inl_ptr.assign(nb + 1, 0);
-  nw.bundle_inl_out.clear();
-  std::vector<int32_t> out_id(n, -1);
-  int64_t n_out = 0;
-  for (int64_t v = 0; v < n; ++v) {
-    if (root_of_frag[fid[v]] == v && nw.down[v] != 0) {
-      out_id[v] = (int32_t)n_out++;
-      nw.bundle_out[((size_t)bundle_of[v] * D + row_of(v)) * 32 + lane_of[v]] = out_id[v];
-    }
-  }
-  nw.n_band_outlets = n_out;
-  nw.max_bundle_inlets = 0;
-  for (int64_t b = 0; b < nb; ++b) {
-    int64_t k = 0;
-    for (int64_t r = 0; r < D; ++r) {
-      for (int64_t l = 0; l < 32; ++l) {
-        const size_t e0 = ((size_t)b * D + r) * 32 + l;
-        const int64_t v = nw.bundle_node[e0];
-        if (v < 0) continue;
-        int64_t j = 0;
-        for (int64_t e = nw.in_ptr[v]; e < nw.in_ptr[v + 1] && j < 8; ++e, ++j) {
-          const int64_t u = nw.in_idx[e] - 1;
-          uint16_t code;
-          if (bundle_of[u] == b) {
-            code = (uint16_t)lane_of[u];  // row r - 1 of the same bundle
-          } else {
-            code = (uint16_t)(0x8000 | k++);
-            nw.bundle_inl_out.push_back(out_id[u]);
-          }
-          nw.bundle_src[e0 * 8 + j] = code;
-        }
-      }
-    }
-    nw.bundle_inl_ptr[b + 1] = (int64_t)nw.bundle_inl_out.size();
-    nw.max_bundle_inlets = std::max(nw.max_bundle_inlets, k);
-  }
-}
-
 }  // namespace wfb

@@ -51,23 +51,6 @@ struct Network {
   int64_t n_outlets = 0;
   std::vector<int64_t> chunk_clp_off;  // n_chunks + 1 offsets into clp
   std::vector<int64_t> clp;            // per chunk: (l1 - l0 + 2) absolute slot offsets of its levels
-  // B200 single-sub-step wavefront (subsurface flow): BANDS of `band_depth` consecutive levels.
-  // A FRAGMENT is the part of the forest that drains, inside one band, to one root (a node
-  // whose distance to its outlet is a multiple of band_depth, or a pit); a BUNDLE packs
-  // fragments of one band so that every row (level inside the band) holds at most 32 nodes:
-  // one warp walks a bundle row by row, one lane per node of the row.
-  int64_t band_depth = 0;
-  int64_t n_bundles = 0;               // in execution order (upstream bands first)
-  std::vector<int32_t> bundle_node;    // n_bundles * band_depth * 32: node id - 1, or -1
-  std::vector<uint16_t> bundle_src;    // 8 per entry: upstream sources in ascending node id:
-                                       // lane in the previous row (< 32), 0x8000 | k for the
-                                       // bundle's k-th inlet, 0xffff none
-  std::vector<int32_t> bundle_out;     // per entry: outlet number if the node feeds another
-                                       // bundle, else -1
-  std::vector<int64_t> bundle_inl_ptr; // n_bundles + 1
-  std::vector<int32_t> bundle_inl_out; // per inlet: outlet number of the producer
-  int64_t n_band_outlets = 0;
-  int64_t max_bundle_inlets = 0;
 };
 
 // Build `down` from a gridded LDD (flowgraph). `indices` holds 2n CartesianIndex pairs.
@@ -85,7 +68,5 @@ bool build_artifacts(Network& nw, int nthreads, int min_streamorder,
 // slot order (chunk, level, node id). Shallow chunks keep the lanes of a warp busy: a chunk of
 // L levels walks L - 1 + S stages for S sub-steps.
 void build_chunks(Network& nw, int64_t cap, int64_t piece_depth);
-// Bands / fragments / bundles of the single-sub-step wavefront (see Network).
-void build_bands(Network& nw, int64_t depth);
 
 }  // namespace wfb

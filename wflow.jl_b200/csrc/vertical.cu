@@ -1,19 +1,22 @@
 // vertical.cu -- the SBM vertical land-surface update as fused sm_100a elementwise kernels.
 //
 // One thread per land slot; the ~30 sweeps of the reference collapse into
-//   land_surface_kernel       update_land_hydrology_model!, first half     sbm.jl:82-132
-//                             (interception, snow, glacier, open water, soil boundary
-//                             conditions, diagnostics, infiltration, unsaturated-zone flow)
-//   unsat_loop_kernel /       the long Brooks-Corey sub-iteration loops of unsatzone_flow_layer
-//   unsat_resume_kernel       (soil_process.jl:51-92), see "the unsaturated-zone engine" below
-//   soil_column_kernel        update_land_hydrology_model!, second half (soil evaporation,
+//   land_hydrology_kernel     update_land_hydrology_model! (sbm.jl:82-132): interception, snow,
+//                             glacier, open water, soil boundary conditions, diagnostics,
+//                             infiltration, unsaturated-zone flow AND -- for every cell whose
+//                             Brooks-Corey loops are short -- the second half (soil evaporation,
 //                             transpiration, actual infiltration, capillary flux, leakage,
-//                             recharge, AET)                           soil/soil.jl:814-1209
+//                             recharge, AET; soil/soil.jl:814-1209) straight from registers
+//   unsat_loop_kernel /       the long Brooks-Corey sub-iteration loops of unsatzone_flow_layer
+//   unsat_resume_kernel       (soil_process.jl:51-92) of the few cells that have them, see "the
+//                             unsaturated-zone engine" below; a resumed cell is FINISHED there
+//                             (its second half included)
 //   soil_water_storage_kernel update_soil_water_storage!               soil/soil.jl:1294-1392
 //   total_water_storage_kernel update_total_water_storage!             sbm.jl:143-182
 // HBM-bound: consecutive threads touch consecutive doubles of every SoA array, so each warp
 // load/store is a fully used 256-byte transaction; the layered state lives in registers
-// (template N) between sub-processes. Arithmetic order follows the reference expression by
+// (template N) between sub-processes; every input array is read once and every output array
+// written once per cell and step. Arithmetic order follows the reference expression by
 // expression (no FMA contraction: -fmad=false) so results match the Julia code to the last
 // bits that libm differences allow. All reference paths are under /root/reference/Wflow/src.
 //
@@ -22,15 +25,20 @@
 // is 1 for 80 % of the (cell, layer) calls and 64-250 for 1.5 % of them -- and those 1.5 % hold
 // 40 % of all iterations. With one cell per lane a warp runs as long as its wettest cell, and a
 // CTA as long as its wettest warp. The engine therefore takes the long loops OUT of the
-// per-cell kernels: land_surface_kernel runs loops of up to `inline_iters` trips in line and
+// per-cell kernel: land_hydrology_kernel runs loops of up to `inline_iters` trips in line and
 // SUSPENDS a cell at the first longer one (the loop's operands go to a per-cell scratch record,
 // the cell id to a list bucketed by log2(its)); unsat_loop_kernel runs all suspended loops of
-// the whole domain at once, one lane per loop, 32 loops of the same bucket per warp, longest
-// buckets first, so the lanes of a warp finish together and every long loop of the domain is in
-// flight at the same time (the sweep lasts as long as ONE longest loop, not one per CTA wave);
-// unsat_resume_kernel continues the suspended cells with their next layer (and may suspend
-// them again: at most N rounds). soil_column_kernel then finishes every cell from arrays that
-// are reference-visible outputs anyway (nothing is recomputed, no second pass over inputs).
+// a slice at once, one lane per loop, 32 loops of the same bucket per warp, longest buckets
+// first, so the lanes of a warp finish together; unsat_resume_kernel continues the suspended
+// cells with their next layer (and may suspend them again: at most N rounds) and finishes them.
+//
+// Hiding the engine. A loop round lasts as long as its LONGEST loop (a dependent chain of up to
+// ~250 trips x ~600 cycles), with a few hundred busy warps: latency, not throughput. The cells
+// are therefore processed in TILES of 128 in an order that puts the tiles with the longest loops
+// of the PREVIOUS model step first (wet cells stay wet: tile_order_kernel, a counting sort of
+// the tiles by last step's longest loop), the ordered tiles are cut into slices, and the engine
+// rounds of slice k run on a high-priority side stream UNDER land_hydrology_kernel of the slices
+// after it. Only the engine of the last slice -- the tiles with the shortest loops -- is exposed.
 #include <cstdio>
 #include "device_math.cuh"
 #include "kernels.cuh"
@@ -41,13 +49,52 @@ namespace wfb {
 
 namespace {
 
+constexpr int kTile = WFB_V_TILE;  // cells per tile = threads per CTA of land_hydrology_kernel
+
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-// hydraulic_conductivity_at_depth, KvExponential / KvExponentialConstant   utils.jl:727-760
-__device__ __forceinline__ double kv_at_depth(int profile, double kvfac, double kv_0, double f,
-                                              double z_exp, double z) {
-  if (profile == 1 && !(z < z_exp)) return kvfac * kv_0 * exp(-f * z_exp);
-  return kvfac * kv_0 * exp(-f * z);
+// v[n] for a run-time n without local memory (the arrays live in registers)
+template <int N>
+__device__ __forceinline__ double pick(const double (&v)[N], int n) {
+  double r = v[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k)
+    if (k == n) r = v[k];
+  return r;
+}
+
+// The vertical conductivity profile of one cell (soil.jl:213-244). k[n] is the layer's
+// vertical_hydraulic_conductivity_factor, for the layered profiles already multiplied with the
+// layer's kv (the reference only ever uses the product, in this order).
+template <int N>
+struct KvCol {
+  double k[N];
+  double kv_0, f, zx;  // zx: z_exp (exponential_constant) or z_layered (layered_exponential)
+  int nk;              // nlayers_kv - 1 (layered_exponential)
+};
+template <int N>
+__device__ __forceinline__ KvCol<N> load_kvcol(const DevFields& f, const KCfg& c, int i) {
+  KvCol<N> kv;
+  const int ns = c.ns, prof = c.kv_profile;
+  kv.kv_0 = prof < 2 ? __ldg(f.kv_0 + i) : 0.0;
+  kv.f = prof != 2 ? __ldg(f.hydraulic_conductivity_scale_parameter + i) : 0.0;
+  kv.zx = prof == 1 ? __ldg(f.z_exp + i) : (prof == 3 ? __ldg(f.z_layered + i) : 0.0);
+  kv.nk = prof == 3 ? f.nlayers_kv[i] - 1 : 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double fac = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
+    kv.k[k] = prof >= 2 ? fac * __ldg(f.kv + k * ns + i) : fac;
+  }
+  return kv;
+}
+// hydraulic_conductivity_at_depth for layer n (0-based), all four profiles   utils.jl:727-789
+template <int N>
+__device__ __forceinline__ double kv_at_depth(int profile, const KvCol<N>& kv, double kn, double z) {
+  if (profile == 0) return kn * kv.kv_0 * exp(-kv.f * z);
+  if (profile == 1) return kn * kv.kv_0 * exp(-kv.f * (z < kv.zx ? z : kv.zx));
+  if (profile == 2) return kn;
+  if (z < kv.zx) return kn;
+  return pick<N>(kv.k, kv.nk) * exp(-kv.f * (z - kv.zx));
 }
 
 // unsatzone_flow_layer                                           soil/soil_process.jl:51-92
@@ -73,18 +120,11 @@ __device__ __forceinline__ UnsatTask unsatzone_flow_setup(double usd, double kv_
   t.kv_it = its > 0 ? fdiv(kv_z, (double)its) : 0.0;
   return t;
 }
-// FAST: table-driven pow (device_math.cuh). Measured in the loop engine on B200: no change
-// (64 + 58 us for the two loop rounds with either pow), so the default keeps one numeric path.
-#ifndef WFB_ENGINE_FAST_POW
-#define WFB_ENGINE_FAST_POW 0
-#endif
-template <bool FAST>
 __device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt, const Divisor& ddt) {
   double usd = t.usd, sum_ast = t.sum_ast;
   const Divisor dl(t.l_sat);
   for (int k = 0; k < t.its; ++k) {
-    const double st = t.kv_it * (FAST ? bounded_power_fast(usd / dl, t.c)
-                                      : bounded_power(usd / dl, t.c));
+    const double st = t.kv_it * bounded_power(usd / dl, t.c);
     const double st_max = usd / ddt;
     if (st < st_max) { usd -= st * dt; sum_ast += st; }
     else { usd = 0.0; sum_ast += st_max; break; }
@@ -107,6 +147,7 @@ __device__ __forceinline__ void suspend_cell(const UnsatWork& w, int parity, int
   w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast; w.kv_it[i] = t.kv_it; w.l_sat[i] = t.l_sat;
   w.c[i] = t.c;
   w.its_layer[i] = t.its | (k << 24);
+  atomicMax(w.tile_prio + i / kTile, (unsigned)t.its);  // tile_order_kernel of the next step
   const int b = bucket_of(t.its);
   const unsigned peers = __match_any_sync(active, b);
   const int lane = (int)threadIdx.x & 31;
@@ -145,14 +186,12 @@ __device__ __forceinline__ double rwu_reduction_feddes(double h, double h1, doub
 // the depth of the bottom of layer k0 - 1. Returns true when the cell finished all its layers
 // (uld[] and transfer are then final); false when it was suspended at a long loop.
 template <int N>
-__device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, const UnsatWork& w,
-                                             int parity, int i, int k0, int n_unsat, double z,
-                                             double flow, double first_inflow,
-                                             double (&uld)[N], const double (&ult)[N],
-                                             const double (&bc)[N], const double (&kvfac)[N],
-                                             double kv_0, double fpar, double z_exp, double theta_e,
-                                             double dt, const Divisor& ddt, bool live,
-                                             double& transfer) {
+__device__ __forceinline__ bool unsat_layers(const KCfg& c, const UnsatWork& w, int parity, int i,
+                                             int k0, int n_unsat, double z, double flow,
+                                             double first_inflow, double (&uld)[N],
+                                             const double (&ult)[N], const double (&bc)[N],
+                                             const KvCol<N>& kv, double theta_e, double dt,
+                                             const Divisor& ddt, bool live, double& transfer) {
   bool suspended = false;
   int k_susp = 0;
   UnsatTask t_susp;
@@ -162,14 +201,14 @@ __device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, 
     if (k >= k0 && k < n_unsat && !suspended) {
       z = (k == 0) ? ult[0] : z + ult[k];
       const double l_sat = ult[k] * theta_e;
-      const double kv_z = kv_at_depth(c.kv_profile, kvfac[k], kv_0, fpar, z_exp, z);
+      const double kv_z = kv_at_depth<N>(c.kv_profile, kv, kv.k[k], z);
       const double usd = (k == 0) ? uld[k] + first_inflow * dt : uld[k] + flow * dt;
       UnsatTask t = unsatzone_flow_setup(usd, kv_z, l_sat, bc[k], dt, ddt);
       if (!live) t.its = 0;
       if (t.its > w.inline_iters) {
         suspended = true; k_susp = k; t_susp = t;
       } else {
-        unsatzone_flow_iterate<false>(t, dt, ddt);
+        unsatzone_flow_iterate(t, dt, ddt);
         uld[k] = t.usd;
         flow = t.sum_ast;
       }
@@ -180,31 +219,291 @@ __device__ __forceinline__ bool unsat_layers(const DevFields& f, const KCfg& c, 
   return !suspended;
 }
 
+// What the second half of update_land_hydrology_model! needs from the first half: registers in
+// land_hydrology_kernel, re-read from the (reference-visible) arrays in unsat_resume_kernel.
+template <int N>
+struct SoilColumn {
+  double theta_s, theta_e, d_soil, swc, satwd, zi;
+  int nlayers, n_unsat;
+  double uld[N], ult[N], alt[N], cld[N + 1], bc[N];
+  KvCol<N> kv;
+  double pot_soilevap, pot_transp, infiltration, infiltration_excess, wfs, max_infiltsoil,
+      max_infiltpath, pathfrac, transfer, aeow_river, aeow_land, interception;
+};
+
+// kh_layered_profile!                                                      utils.jl:792-895
+// equivalent horizontal conductivity of the saturated part of the column (layered profiles)
+template <int N>
+__device__ __forceinline__ double kh_layered(int profile, const SoilColumn<N>& s, const double (&kvl)[N],
+                                             double fpar, double z_layered, int nlayers_kv,
+                                             double khfrac) {
+  const int m = s.nlayers;  // 1-based count
+  if (!(s.d_soil > s.zi)) return pick<N>(kvl, m - 1) * khfrac;  // (both profiles: kv[i][m] * ratio)
+  double transmissivity = 0.0;
+  int n = s.n_unsat > 1 ? s.n_unsat : 1;  // 1-based layer
+  if (profile == 2) {
+    transmissivity += (pick<N + 1>(s.cld, n) - s.zi) * pick<N>(kvl, n - 1);
+    n += 1;
+    for (; n <= m; ++n) transmissivity += pick<N>(s.alt, n - 1) * pick<N>(kvl, n - 1);
+  } else {
+    const double zt = s.d_soil - z_layered;
+    const double kvj = pick<N>(kvl, nlayers_kv - 1);
+    if (s.zi >= z_layered) {
+      transmissivity += kvj / fpar * (exp(-fpar * (s.zi - z_layered)) - exp(-fpar * zt));
+      n = m;
+    } else {
+      transmissivity += (pick<N + 1>(s.cld, n) - s.zi) * pick<N>(kvl, n - 1);
+    }
+    n += 1;
+    while (n <= m) {
+      if (n > nlayers_kv) {
+        transmissivity += kvj / fpar * (1.0 - exp(-fpar * zt));
+        n = m;
+      } else {
+        transmissivity += pick<N>(s.alt, n - 1) * pick<N>(kvl, n - 1);
+      }
+      n += 1;
+    }
+  }
+  return (transmissivity / (s.d_soil - s.zi)) * khfrac;
+}
+
+// update_land_hydrology_model!, second half, for one cell: soil evaporation, transpiration,
+// actual infiltration, capillary flux, leakage, recharge, AET      soil/soil.jl:814-1209
+template <int N>
+__device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg& c, const int i,
+                                                 const double dt, const Divisor& ddt,
+                                                 SoilColumn<N>& s) {
+  const int ns = c.ns;
+  const double theta_e = s.theta_e;
+  const double theta_d = jmax(s.theta_s - __ldg(f.theta_fc + i), 0.02);
+  const double zi = s.zi;
+  const int n_unsat = s.n_unsat, nlayers = s.nlayers;
+  double (&uld)[N] = s.uld;
+  const double (&ult)[N] = s.ult;
+  const double (&alt)[N] = s.alt;
+  const double (&cld)[N + 1] = s.cld;
+  double drainable = (s.d_soil - zi) * theta_d;
+
+  // ---- soil evaporation (soil.jl:814-856, soil_process.jl:247-294) --------------------------
+  double soilevap_sat, soil_evaporation;
+  {
+    double pot = s.pot_soilevap;
+    double evu;
+    if (n_unsat == 0) evu = 0.0;
+    else if (n_unsat == 1) evu = pot * jmin(1.0, fdiv(uld[0], zi * theta_e));
+    else evu = pot * jmin(1.0, fdiv(uld[0], ult[0] * theta_e));
+    evu = jmin(evu, uld[0] / ddt);
+    pot -= evu;
+    uld[0] = uld[0] - evu * dt;
+    if (n_unsat == 0 || n_unsat == 1) {
+      const double e = pot * jmin(1.0, fdiv(alt[0] - zi, alt[0]));
+      soilevap_sat = jmin(e, (alt[0] - zi) * theta_d / ddt);  // deliberately not clamped at 0
+    } else {
+      soilevap_sat = 0.0;
+    }
+    soil_evaporation = evu + soilevap_sat;
+    drainable -= soilevap_sat * dt;
+  }
+  f.soil_evaporation_saturated_zone[i] = soilevap_sat;
+  f.soil_evaporation[i] = soil_evaporation;
+
+  // ---- transpiration (soil.jl:865-975) -----------------------------------------------------
+  const double pot_transp = s.pot_transp;
+  const double rd = __ldg(f.rooting_depth + i);
+  const double h1 = __ldg(f.h1 + i), h2 = __ldg(f.h2 + i), h4 = __ldg(f.h4 + i);
+  const double alpha_h1 = __ldg(f.alpha_h1 + i);
+  const double hb = __ldg(f.air_entry_pressure + i);
+  double h3;
+  {
+    const double tpot_daily = fdiv(pot_transp, WFB_MM_PER_DAY);  // feddes_h3 soil_process.jl:166-176
+    const double h3_high = __ldg(f.h3_high + i), h3_low = __ldg(f.h3_low + i);
+    if (tpot_daily <= 1.0) h3 = h3_low;
+    else if (tpot_daily < 5.0) h3 = h3_low + (h3_high - h3_low) * (tpot_daily - 1.0) / (5.0 - 1.0);
+    else h3 = h3_high;
+  }
+  f.h3[i] = h3;
+  double rootf[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) rootf[k] = __ldg(f.rootfraction + k * ns + i);
+  // root fraction of the lowest unsaturated layer, rescaled to its unsaturated part; the layer
+  // is selected with pick() -- indexing the register arrays with n_unsat - 1 would move them
+  // to local memory
+  double sum_rf = 0.0, rf_lowest = 0.0;
+  if (n_unsat > 0) {
+    const int kl = n_unsat - 1;
+    rf_lowest = pick<N>(rootf, kl);
+    if (zi < rd) {
+      const double rootlength = jmin(pick<N>(alt, kl), rd - pick<N + 1>(cld, kl));
+      rf_lowest = rf_lowest * fdiv(pick<N>(ult, kl), rootlength);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (k < n_unsat - 1) sum_rf += rootf[k];  // the same left fold: upper layers, then the lowest
+  if (n_unsat > 0) sum_rf += rf_lowest;
+  double actevapustore = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (k < n_unsat) {
+      const double rfu = (k < n_unsat - 1) ? rootf[k] : rf_lowest;
+      const double rfs = rd > 0.0 ? jmax(1.0 / sum_rf, 1.0) * rfu : 0.0;
+      const double vwc = jmax(fdiv(uld[k], ult[k]), 1e-7);
+      // head_brooks_corey soil_process.jl:113-130
+      const double par_lambda = 2.0 / (s.bc[k] - 3.0);
+      const double head = par_lambda > 0.0 ? hb / jpow(fdiv(vwc, theta_e), 1.0 / par_lambda) : hb;
+      const double alpha = rwu_reduction_feddes(head, h1, h2, h3, h4, alpha_h1);
+      const double availcap = jmin(1.0, jmax(0.0, fdiv(rd - cld[k], ult[k])));
+      const double maxextr = uld[k] * availcap / ddt;
+      const double layer = jmin(alpha * rfs * pot_transp, maxextr);
+      uld[k] = uld[k] - layer * dt;
+      actevapustore += layer;
+    }
+  }
+  const double wetroots = scurve(zi, rd, 1.0, __ldg(f.wet_root_distribution_parameter + i));
+  const double alpha_sat = rwu_reduction_feddes(0.0, h1, h2, h3, h4, alpha_h1);
+  const double restpottrans = pot_transp - actevapustore;
+  const double ae_sat = jmin(restpottrans * wetroots * alpha_sat, drainable / ddt);
+  drainable -= ae_sat * dt;
+  const double transpiration = actevapustore + ae_sat;
+  f.actual_evaporation_unsaturated_store[i] = actevapustore;
+  f.actual_evaporation_saturated_zone[i] = ae_sat;
+  f.transpiration[i] = transpiration;
+
+  // ---- actual infiltration and excess water (soil.jl:987-1043, 1178-1192) -------------------
+  double excess = 0.0;
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    if (k < n_unsat) {
+      excess = jmax(0.0, uld[k] - ult[k] * theta_e);
+      uld[k] = uld[k] - excess;
+      if (k > 0) uld[k - 1] = uld[k - 1] + excess;
+    }
+  }
+  const double wfs = s.wfs, pathfrac = s.pathfrac;
+  const double actual_infiltration = s.infiltration - excess / ddt;
+  f.actual_infiltration[i] = actual_infiltration;
+  f.saturation_excess_water[i] = (wfs - actual_infiltration) - s.infiltration_excess;
+  double actinf_soil, actinf_path;
+  if (actual_infiltration > 0.0) {  // soil_process.jl:297-323
+    const Divisor dsum(s.max_infiltpath + s.max_infiltsoil);
+    actinf_soil = actual_infiltration * s.max_infiltsoil / dsum;
+    actinf_path = actual_infiltration * s.max_infiltpath / dsum;
+  } else {
+    actinf_soil = 0.0; actinf_path = 0.0;
+  }
+  f.actual_infiltration_soil[i] = actinf_soil;
+  f.actual_infiltration_compacted_soil[i] = actinf_path;
+  f.excess_water_soil[i] = jmax(wfs * (1.0 - pathfrac) - actinf_soil, 0.0);
+  f.excess_water_compacted_soil[i] = jmax(wfs * pathfrac - actinf_path, 0.0);
+
+  // ---- recompute stores, capillary flux, leakage, recharge (soil.jl:1194-1209) --------------
+  double ustore_depth = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (k < nlayers) ustore_depth += uld[k];
+  const double ustore_cap = s.swc - s.satwd - ustore_depth;
+  f.unsaturated_store_depth[i] = ustore_depth;
+  f.unsaturated_store_capacity[i] = ustore_cap;
+  double act_capflux = 0.0;
+  if (n_unsat > 0) {  // capillary_flux! soil.jl:1050-1111
+    const double ksat = kv_at_depth<N>(c.kv_profile, s.kv, pick<N>(s.kv.k, n_unsat - 1), zi);
+    double mc = jmin(ksat, actevapustore);
+    mc = jmin(mc, ustore_cap / ddt);
+    mc = jmin(mc, drainable / ddt);
+    const double maxcapflux = jmax(0.0, mc);
+    double capflux = 0.0;
+    if (zi > rd) {
+      const double hmax = __ldg(f.cap_hmax + i);
+      capflux = maxcapflux * jpow(1.0 - fdiv(jmin(zi, hmax), hmax), __ldg(f.cap_n + i));
+    }
+    double net = capflux;
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+      if (k < n_unsat) {
+        const double toadd = jmin(net, jmax((ult[k] * theta_e - uld[k]) / ddt, 0.0));
+        uld[k] = uld[k] + toadd * dt;
+        net -= toadd;
+        act_capflux += toadd;
+      }
+    }
+  }
+  f.actual_capillary_flux[i] = act_capflux;
+  const double deepksat = kv_at_depth<N>(c.kv_profile, s.kv, pick<N>(s.kv.k, nlayers - 1), s.d_soil);
+  const double deeptransfer = jmin(drainable / ddt, deepksat);
+  const double leakage = jmax(0.0, jmin(__ldg(f.maximum_leakage + i), deeptransfer));
+  f.actual_leakage[i] = leakage;
+  const double recharge = (s.transfer - act_capflux - leakage - ae_sat - soilevap_sat);
+  f.recharge[i] = recharge;
+  // the recharge / water-table hand-off to the subsurface flow (sbm_model.jl:74-81), fused:
+  // exchange_recharge_kernel would re-read both arrays
+  f.recharge_rate[i] = recharge;
+  f.ssf_water_table_depth[i] = zi;
+  // total AET (soil.jl:1206-1209) + interception (sbm.jl:130)
+  double aet = soil_evaporation + transpiration + s.aeow_river + s.aeow_land + 0.0;
+  aet += s.interception;
+  f.actual_evapotranspiration[i] = aet;
+  f.drainable_water_depth[i] = drainable;
+#pragma unroll
+  for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = uld[k];
+  // kh_layered_profile! (sbm_model.jl:84): the layered profiles' equivalent horizontal
+  // conductivity of this step, from the water table and layers of the diagnostics above
+#ifndef WFB_NO_KH
+  if (c.kv_profile >= 2) {
+    double kvl[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) kvl[k] = __ldg(f.kv + k * ns + i);
+    f.ssf_kh[i] = kh_layered<N>(c.kv_profile, s, kvl, s.kv.f, s.kv.zx, s.kv.nk + 1,
+                                __ldg(f.ssf_khfrac + i));
+  }
+#endif
+}
+
 }  // namespace
 
-// update_land_hydrology_model!, first half                                 sbm.jl:82-132
-#ifndef WFB_V_BLOCK
-#define WFB_V_BLOCK 128
+#ifndef WFB_V_MINBLOCKS
+#define WFB_V_MINBLOCKS 4
 #endif
-#ifndef WFB_VA_MINBLOCKS
-#define WFB_VA_MINBLOCKS 5
-#endif
-#ifndef WFB_VC_MINBLOCKS
-#define WFB_VC_MINBLOCKS 4
-#endif
+// Counting sort of the tiles by the longest Brooks-Corey loop they held in the PREVIOUS model
+// step (tile_prio, raised by suspend_cell), longest first; ties keep no particular order. One
+// CTA: a domain of 10^7 cells has 10^5 tiles.
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(unsigned* __restrict__ prio, int32_t* __restrict__ order, const int n_tiles) {
+  __shared__ unsigned hist[64], base[64];
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int t = (int)threadIdx.x; t < n_tiles; t += (int)blockDim.x) {
+    const unsigned b = 63u - min(prio[t] >> 2, 63u);
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int b = 0; b < 64; ++b) { base[b] = acc; acc += hist[b]; }
+  }
+  __syncthreads();
+  for (int t = (int)threadIdx.x; t < n_tiles; t += (int)blockDim.x) {
+    const unsigned b = 63u - min(prio[t] >> 2, 63u);
+    order[atomicAdd(&base[b], 1u)] = t;
+    prio[t] = 0u;
+  }
+}
+
+// update_land_hydrology_model!                                                sbm.jl:82-132
 template <int N>
-__global__ void __launch_bounds__(WFB_V_BLOCK, WFB_VA_MINBLOCKS)
-land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
-                    const int i_begin, const int i_end) {
-  // cells [i_begin, i_end) of one slice; both are multiples of 32 (or i_end = ns)
-  const int i = i_begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (i >= i_end) return;    // whole warps
+__global__ void __launch_bounds__(WFB_V_TILE, WFB_V_MINBLOCKS)
+land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
+                      const int32_t* __restrict__ order, const int tile_begin) {
+  // one tile of 128 consecutive slots per CTA, in the order of tile_order_kernel
+  const int i = __ldg(order + tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
+  if (i >= c.ns) return;    // whole warps (ns is a multiple of 32)
   // lanes of the padding slots [n, ns) run along on the padding values (they must take part in
   // the warp-aggregated suspension) and never suspend; their stores land in the padding
   const bool live = i < c.n;
   const int ns = c.ns;
   const Divisor ddt(dt);
   double st_canopy = 0.0, st_snoww = 0.0, st_gstore = 0.0, st_snow = 0.0, st_tsoil = 0.0;
+  SoilColumn<N> s;
 
   // ---- forcing ---------------------------------------------------------------------------
   const double P = __ldg(f.precipitation + i);
@@ -387,39 +686,41 @@ land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
   f.soil_water_flux_surface[i] = wfs;
 
   // ---- state -> diagnostics (soil.jl:1400-1436) --------------------------------------------
-  const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
-  const double theta_e = theta_s - theta_r;
-  const double d_soil = __ldg(f.soil_thickness + i);
-  const double swc = __ldg(f.soil_water_capacity + i);
-  const double satwd = f.saturated_water_depth[i];
-  const int nlayers = f.number_of_layers[i];
-  double uld[N], ult[N], alt[N], cld[N + 1];
+  s.theta_s = __ldg(f.theta_s + i);
+  s.theta_e = s.theta_s - __ldg(f.theta_r + i);
+  const double theta_e = s.theta_e;
+  s.d_soil = __ldg(f.soil_thickness + i);
+  s.swc = __ldg(f.soil_water_capacity + i);
+  s.satwd = f.saturated_water_depth[i];
+  s.nlayers = f.number_of_layers[i];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    uld[k] = f.unsaturated_layer_depth[k * ns + i];
-    alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
-    cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
+    s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
+    s.alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
+    s.cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
   }
-  cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
+  s.cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
   double ustore_depth = 0.0;
 #pragma unroll
   for (int k = 0; k < N; ++k)
-    if (k < nlayers) ustore_depth += uld[k];
-  const double zi = jmax(0.0, d_soil - fdiv(satwd, theta_e));
-  double ustore_cap = swc - satwd - ustore_depth;
+    if (k < s.nlayers) ustore_depth += s.uld[k];
+  const double zi = jmax(0.0, s.d_soil - fdiv(s.satwd, theta_e));
+  s.zi = zi;
+  const double ustore_cap = s.swc - s.satwd - ustore_depth;
   int n_unsat = N;
 #pragma unroll
   for (int k = 0; k < N; ++k) {  // set_layerthickness utils.jl:390-404
     double t = qnan();
-    if (zi > cld[k + 1]) t = alt[k];
-    else if (zi - cld[k] > 0.0) t = zi - cld[k];
-    ult[k] = t;
+    if (zi > s.cld[k + 1]) t = s.alt[k];
+    else if (zi - s.cld[k] > 0.0) t = zi - s.cld[k];
+    s.ult[k] = t;
     n_unsat -= (t != t) ? 1 : 0;
     f.unsaturated_layer_thickness[k * ns + i] = t;
   }
+  s.n_unsat = n_unsat;
   f.water_table_depth[i] = zi;
   f.n_unsatlayers[i] = n_unsat;
-  f.total_soil_water_storage[i] = satwd + ustore_depth;
+  f.total_soil_water_storage[i] = s.satwd + ustore_depth;
 
   // ---- soil temperature, infiltration (soil.jl:685-755, soil_process.jl:16-41,229-244) -------
   double f_red = 1.0;
@@ -447,18 +748,12 @@ land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
   f.infiltration_excess[i] = infiltration_excess;
 
   // ---- unsaturated zone flow, Brooks-Corey (soil.jl:764-804) -------------------------------
-  const double kv_0 = __ldg(f.kv_0 + i);
-  const double fpar = __ldg(f.hydraulic_conductivity_scale_parameter + i);
-  const double z_exp = c.kv_profile == 1 ? __ldg(f.z_exp + i) : 0.0;
-  double bc[N], kvfac[N];
+  s.kv = load_kvcol<N>(f, c, i);
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
-    kvfac[k] = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
-  }
+  for (int k = 0; k < N; ++k) s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
   double transfer;
-  const bool done = unsat_layers<N>(f, c, w, 0, i, 0, n_unsat, 0.0, 0.0, infiltration, uld, ult, bc,
-                                    kvfac, kv_0, fpar, z_exp, theta_e, dt, ddt, live, transfer);
+  const bool done = unsat_layers<N>(c, w, 0, i, 0, n_unsat, 0.0, 0.0, infiltration, s.uld, s.ult,
+                                    s.bc, s.kv, theta_e, dt, ddt, live, transfer);
   // the read-modify-write states of the sections above
   if (!c.gash) f.canopy_storage[i] = st_canopy;
   if (c.snow) {
@@ -467,13 +762,22 @@ land_surface_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
     f.soil_surface_temperature[i] = st_tsoil;
     if (c.glacier) f.glacier_store[i] = st_gstore;
   }
-  // layers above a suspended one are final, the others are written by unsat_resume_kernel
+  if (done) {
+    // the second half straight from registers: nothing of the first half is read back
+    f.transfer[i] = transfer;
+    s.pot_soilevap = pot_soilevap0; s.pot_transp = pot_transp; s.infiltration = infiltration;
+    s.infiltration_excess = infiltration_excess; s.wfs = wfs; s.max_infiltsoil = max_infiltsoil;
+    s.max_infiltpath = max_infiltpath; s.pathfrac = pathfrac; s.transfer = transfer;
+    s.aeow_river = aeow_river; s.aeow_land = aeow_land; s.interception = interception;
+    soil_column_cell<N>(f, c, i, dt, ddt, s);
+  } else {
+    // layers above the suspended one are final, the others are written by unsat_resume_kernel
 #pragma unroll
-  for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = uld[k];
-  if (done) f.transfer[i] = transfer;
+    for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
+  }
 }
 
-// All suspended loops of the domain, one lane per loop, 32 loops of one bucket per warp.
+// All suspended loops of a slice, one lane per loop, 32 loops of one bucket per warp.
 __global__ void __launch_bounds__(128)
 unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
   const unsigned* cnt = w.count + parity * kBuckets;
@@ -491,18 +795,15 @@ unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
       UnsatTask t;
       t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
       t.c = w.c[i]; t.its = w.its_layer[i] & 0xffffff;
-      if (w.diag) {  // developer aid (WFB_ENGINE_DIAG): loops, trips and the longest loop per round
-        atomicAdd(w.diag + 0, 1ull);
-        atomicAdd(w.diag + 1, (unsigned long long)t.its);
-        atomicMax(w.diag + 2, (unsigned long long)t.its);
-      }
-      unsatzone_flow_iterate<WFB_ENGINE_FAST_POW != 0>(t, dt, ddt);
+      unsatzone_flow_iterate(t, dt, ddt);
       w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast;
     }
   }
 }
 
-// The suspended cells continue with the layer below the finished loop.
+// The suspended cells continue with the layer below the finished loop; a cell that gets through
+// its remaining layers is finished here (second half of update_land_hydrology_model!), from the
+// reference-visible arrays land_hydrology_kernel wrote for it.
 template <int N>
 __global__ void __launch_bounds__(128)
 unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const int parity,
@@ -518,265 +819,71 @@ unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const in
     if (!tile_of(cnt, j, b, first, n)) break;
     const int e = first + lane;
     const bool live = e < n;
-    bool resume = false;
-    int i = 0, k0 = 0, n_unsat = 0;
-    double uld[N], ult[N], bc[N], kvfac[N];
-    double kv_0 = 0.0, fpar = 0.0, z_exp = 0.0, theta_e = 1.0, z = 0.0, flow = 0.0, transfer = 0.0;
+    int i = 0, k0 = N;
+    double z = 0.0, flow = 0.0, transfer = 0.0;
+    SoilColumn<N> s;
+    s.n_unsat = 0; s.theta_e = 1.0;
+    s.kv.kv_0 = s.kv.f = s.kv.zx = 0.0; s.kv.nk = 0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) { uld[k] = 0.0; ult[k] = 1.0; bc[k] = 1.0; kvfac[k] = 1.0; }
+    for (int k = 0; k < N; ++k) { s.uld[k] = 0.0; s.ult[k] = 1.0; s.bc[k] = 1.0; s.kv.k[k] = 1.0; }
     if (live) {
       i = w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + e];
       const int kl = w.its_layer[i] >> 24;   // the layer whose loop has just been run
       flow = w.sum_ast[i];
-      n_unsat = f.n_unsatlayers[i];
-      f.unsaturated_layer_depth[kl * ns + i] = w.usd[i];
+      s.n_unsat = f.n_unsatlayers[i];
       k0 = kl + 1;
-      resume = true;
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        ult[k] = f.unsaturated_layer_thickness[k * ns + i];
-        if (k >= k0) uld[k] = f.unsaturated_layer_depth[k * ns + i];
-        bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
-        kvfac[k] = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
-        if (k < k0) z = (k == 0) ? ult[0] : z + ult[k];  // same left-to-right sum as the first pass
+        s.ult[k] = f.unsaturated_layer_thickness[k * ns + i];
+        s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
+        s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
+        if (k < k0) z = (k == 0) ? s.ult[0] : z + s.ult[k];  // same left-to-right sum as the first pass
       }
-      kv_0 = __ldg(f.kv_0 + i);
-      fpar = __ldg(f.hydraulic_conductivity_scale_parameter + i);
-      z_exp = c.kv_profile == 1 ? __ldg(f.z_exp + i) : 0.0;
-      theta_e = __ldg(f.theta_s + i) - __ldg(f.theta_r + i);
-    }
-    // every lane of the warp calls unsat_layers (it aggregates the suspensions of the warp)
-    const bool done = unsat_layers<N>(f, c, w, parity ^ 1, i, resume ? k0 : N, resume ? n_unsat : 0,
-                                      z, flow, 0.0, uld, ult, bc, kvfac, kv_0, fpar, z_exp, theta_e,
-                                      dt, ddt, live, transfer);
-    if (live) {
 #pragma unroll
       for (int k = 0; k < N; ++k)
-        if (k >= k0 && k < n_unsat) f.unsaturated_layer_depth[k * ns + i] = uld[k];
-      if (done) f.transfer[i] = transfer;
+        if (k == kl) s.uld[k] = w.usd[i];
+      s.kv = load_kvcol<N>(f, c, i);
+      s.theta_s = __ldg(f.theta_s + i);
+      s.theta_e = s.theta_s - __ldg(f.theta_r + i);
     }
-  }
-}
-
-// update_land_hydrology_model!, second half: every quantity it needs from the first half is a
-// reference-visible output array (or an input), re-read here.
-template <int N>
-__global__ void __launch_bounds__(WFB_V_BLOCK, WFB_VC_MINBLOCKS)
-soil_column_kernel(const DevFields f, const KCfg c, const double dt, const int i_begin,
-                   const int i_end) {
-  const int i = i_begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (i >= i_end || i >= c.n) return;
-  const int ns = c.ns;
-  const Divisor ddt(dt);
-  const double theta_s = __ldg(f.theta_s + i), theta_r = __ldg(f.theta_r + i);
-  const double theta_e = theta_s - theta_r;
-  const double theta_d = jmax(theta_s - __ldg(f.theta_fc + i), 0.02);
-  const double d_soil = __ldg(f.soil_thickness + i);
-  const double swc = __ldg(f.soil_water_capacity + i);
-  const double satwd = f.saturated_water_depth[i];
-  const double zi = f.water_table_depth[i];
-  const int nlayers = f.number_of_layers[i];
-  const int n_unsat = f.n_unsatlayers[i];
-  double drainable = (d_soil - zi) * theta_d;
-  double uld[N], ult[N], alt[N], cld[N + 1], bc[N], kvfac[N];
+    // every lane of the warp calls unsat_layers (it aggregates the suspensions of the warp)
+    const bool done = unsat_layers<N>(c, w, parity ^ 1, i, k0, s.n_unsat, z, flow, 0.0, s.uld, s.ult,
+                                      s.bc, s.kv, s.theta_e, dt, ddt, live, transfer);
+    if (!live) continue;
+    if (!done) {
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    uld[k] = f.unsaturated_layer_depth[k * ns + i];
-    ult[k] = f.unsaturated_layer_thickness[k * ns + i];
-    alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
-    cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
-    bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
-    kvfac[k] = __ldg(f.vertical_hydraulic_conductivity_factor + k * ns + i);
-  }
-  cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
-  const double kv_0 = __ldg(f.kv_0 + i);
-  const double fpar = __ldg(f.hydraulic_conductivity_scale_parameter + i);
-  const double z_exp = c.kv_profile == 1 ? __ldg(f.z_exp + i) : 0.0;
-  const double pot_soilevap0 = f.potential_soilevaporation[i];
-  const double pot_transp = f.potential_transpiration[i];
-  const double infiltration = f.infiltration[i];
-  const double infiltration_excess = f.infiltration_excess[i];
-  const double wfs = f.soil_water_flux_surface[i];
-  const double f_red = f.f_infiltration_reduction[i];
-  const double pathfrac = __ldg(f.compacted_soil_area_fraction + i);
-  // infiltration! soil_process.jl:16-41, the same expressions as in land_surface_kernel
-  const double max_infiltsoil = jmin(__ldg(f.infiltration_capacity_soil + i) * f_red,
-                                     wfs * (1.0 - pathfrac));
-  const double max_infiltpath = jmin(__ldg(f.infiltration_capacity_compacted_soil + i) * f_red,
-                                     wfs * pathfrac);
-  const double transfer = f.transfer[i];
-  const double aeow_river = f.actual_open_water_evaporation_river[i];
-  const double aeow_land = f.actual_open_water_evaporation_land[i];
-  const double interception = f.interception_rate[i];
-  double ustore_depth, ustore_cap;
-
-  // ---- soil evaporation (soil.jl:814-856, soil_process.jl:247-294) --------------------------
-  double soilevap_sat, soil_evaporation;
-  {
-    double pot = pot_soilevap0;
-    double evu;
-    if (n_unsat == 0) evu = 0.0;
-    else if (n_unsat == 1) evu = pot * jmin(1.0, fdiv(uld[0], zi * theta_e));
-    else evu = pot * jmin(1.0, fdiv(uld[0], ult[0] * theta_e));
-    evu = jmin(evu, uld[0] / ddt);
-    pot -= evu;
-    uld[0] = uld[0] - evu * dt;
-    if (n_unsat == 0 || n_unsat == 1) {
-      const double e = pot * jmin(1.0, fdiv(alt[0] - zi, alt[0]));
-      soilevap_sat = jmin(e, (alt[0] - zi) * theta_d / ddt);  // deliberately not clamped at 0
-    } else {
-      soilevap_sat = 0.0;
+      for (int k = 0; k < N; ++k)
+        if (k >= k0 - 1 && k < s.n_unsat) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
+      continue;
     }
-    soil_evaporation = evu + soilevap_sat;
-    drainable -= soilevap_sat * dt;
-  }
-  f.soil_evaporation_saturated_zone[i] = soilevap_sat;
-  f.soil_evaporation[i] = soil_evaporation;
-
-  // ---- transpiration (soil.jl:865-975) -----------------------------------------------------
-  const double rd = __ldg(f.rooting_depth + i);
-  const double h1 = __ldg(f.h1 + i), h2 = __ldg(f.h2 + i), h4 = __ldg(f.h4 + i);
-  const double alpha_h1 = __ldg(f.alpha_h1 + i);
-  const double hb = __ldg(f.air_entry_pressure + i);
-  double h3;
-  {
-    const double tpot_daily = fdiv(pot_transp, WFB_MM_PER_DAY);  // feddes_h3 soil_process.jl:166-176
-    const double h3_high = __ldg(f.h3_high + i), h3_low = __ldg(f.h3_low + i);
-    if (tpot_daily <= 1.0) h3 = h3_low;
-    else if (tpot_daily < 5.0) h3 = h3_low + (h3_high - h3_low) * (tpot_daily - 1.0) / (5.0 - 1.0);
-    else h3 = h3_high;
-  }
-  f.h3[i] = h3;
-  double rootf[N];
+    f.transfer[i] = transfer;
+    s.transfer = transfer;
+    s.d_soil = __ldg(f.soil_thickness + i);
+    s.swc = __ldg(f.soil_water_capacity + i);
+    s.satwd = f.saturated_water_depth[i];
+    s.zi = f.water_table_depth[i];
+    s.nlayers = f.number_of_layers[i];
 #pragma unroll
-  for (int k = 0; k < N; ++k) rootf[k] = __ldg(f.rootfraction + k * ns + i);
-  double sum_rf = 0.0, rf_lowest = 0.0;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    if (k < n_unsat) {
-      double rfu;
-      if (k == n_unsat - 1 && zi < rd) {
-        const double rootlength = jmin(alt[k], rd - cld[k]);
-        rfu = rootf[k] * fdiv(ult[k], rootlength);
-      } else {
-        rfu = rootf[k];
-      }
-      sum_rf += rfu;
-      rf_lowest = rfu;
+    for (int k = 0; k < N; ++k) {
+      s.alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
+      s.cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
     }
+    s.cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
+    s.pot_soilevap = f.potential_soilevaporation[i];
+    s.pot_transp = f.potential_transpiration[i];
+    s.infiltration = f.infiltration[i];
+    s.infiltration_excess = f.infiltration_excess[i];
+    s.wfs = f.soil_water_flux_surface[i];
+    const double f_red = f.f_infiltration_reduction[i];
+    s.pathfrac = __ldg(f.compacted_soil_area_fraction + i);
+    // infiltration! soil_process.jl:16-41, the same expressions as in land_hydrology_kernel
+    s.max_infiltsoil = jmin(__ldg(f.infiltration_capacity_soil + i) * f_red, s.wfs * (1.0 - s.pathfrac));
+    s.max_infiltpath = jmin(__ldg(f.infiltration_capacity_compacted_soil + i) * f_red, s.wfs * s.pathfrac);
+    s.aeow_river = f.actual_open_water_evaporation_river[i];
+    s.aeow_land = f.actual_open_water_evaporation_land[i];
+    s.interception = f.interception_rate[i];
+    soil_column_cell<N>(f, c, i, dt, ddt, s);
   }
-  double actevapustore = 0.0;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    if (k < n_unsat) {
-      const double rfu = (k < n_unsat - 1) ? rootf[k] : rf_lowest;
-      const double rfs = rd > 0.0 ? jmax(1.0 / sum_rf, 1.0) * rfu : 0.0;
-      const double vwc = jmax(fdiv(uld[k], ult[k]), 1e-7);
-      // head_brooks_corey soil_process.jl:113-130
-      const double par_lambda = 2.0 / (bc[k] - 3.0);
-      const double head = par_lambda > 0.0 ? hb / jpow(fdiv(vwc, theta_e), 1.0 / par_lambda) : hb;
-      const double alpha = rwu_reduction_feddes(head, h1, h2, h3, h4, alpha_h1);
-      const double availcap = jmin(1.0, jmax(0.0, fdiv(rd - cld[k], ult[k])));
-      const double maxextr = uld[k] * availcap / ddt;
-      const double layer = jmin(alpha * rfs * pot_transp, maxextr);
-      uld[k] = uld[k] - layer * dt;
-      actevapustore += layer;
-    }
-  }
-  const double wetroots = scurve(zi, rd, 1.0, __ldg(f.wet_root_distribution_parameter + i));
-  const double alpha_sat = rwu_reduction_feddes(0.0, h1, h2, h3, h4, alpha_h1);
-  const double restpottrans = pot_transp - actevapustore;
-  const double ae_sat = jmin(restpottrans * wetroots * alpha_sat, drainable / ddt);
-  drainable -= ae_sat * dt;
-  const double transpiration = actevapustore + ae_sat;
-  f.actual_evaporation_unsaturated_store[i] = actevapustore;
-  f.actual_evaporation_saturated_zone[i] = ae_sat;
-  f.transpiration[i] = transpiration;
-
-  // ---- actual infiltration and excess water (soil.jl:987-1043, 1178-1192) -------------------
-  double excess = 0.0;
-#pragma unroll
-  for (int k = N - 1; k >= 0; --k) {
-    if (k < n_unsat) {
-      excess = jmax(0.0, uld[k] - ult[k] * theta_e);
-      uld[k] = uld[k] - excess;
-      if (k > 0) uld[k - 1] = uld[k - 1] + excess;
-    }
-  }
-  const double actual_infiltration = infiltration - excess / ddt;
-  f.actual_infiltration[i] = actual_infiltration;
-  f.saturation_excess_water[i] = (wfs - actual_infiltration) - infiltration_excess;
-  double actinf_soil, actinf_path;
-  if (actual_infiltration > 0.0) {  // soil_process.jl:297-323
-    const Divisor dsum(max_infiltpath + max_infiltsoil);
-    actinf_soil = actual_infiltration * max_infiltsoil / dsum;
-    actinf_path = actual_infiltration * max_infiltpath / dsum;
-  } else {
-    actinf_soil = 0.0; actinf_path = 0.0;
-  }
-  f.actual_infiltration_soil[i] = actinf_soil;
-  f.actual_infiltration_compacted_soil[i] = actinf_path;
-  f.excess_water_soil[i] = jmax(wfs * (1.0 - pathfrac) - actinf_soil, 0.0);
-  f.excess_water_compacted_soil[i] = jmax(wfs * pathfrac - actinf_path, 0.0);
-
-  // ---- recompute stores, capillary flux, leakage, recharge (soil.jl:1194-1209) --------------
-  ustore_depth = 0.0;
-#pragma unroll
-  for (int k = 0; k < N; ++k)
-    if (k < nlayers) ustore_depth += uld[k];
-  ustore_cap = swc - satwd - ustore_depth;
-  f.unsaturated_store_depth[i] = ustore_depth;
-  f.unsaturated_store_capacity[i] = ustore_cap;
-  double act_capflux = 0.0;
-  if (n_unsat > 0) {  // capillary_flux! soil.jl:1050-1111
-    double kvfac_nu = kvfac[0];
-#pragma unroll
-    for (int k = 1; k < N; ++k)
-      if (k == n_unsat - 1) kvfac_nu = kvfac[k];
-    const double ksat = kv_at_depth(c.kv_profile, kvfac_nu, kv_0, fpar, z_exp, zi);
-    double mc = jmin(ksat, actevapustore);
-    mc = jmin(mc, ustore_cap / ddt);
-    mc = jmin(mc, drainable / ddt);
-    const double maxcapflux = jmax(0.0, mc);
-    double capflux = 0.0;
-    if (zi > rd) {
-      const double hmax = __ldg(f.cap_hmax + i);
-      capflux = maxcapflux * jpow(1.0 - fdiv(jmin(zi, hmax), hmax), __ldg(f.cap_n + i));
-    }
-    double net = capflux;
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-      if (k < n_unsat) {
-        const double toadd = jmin(net, jmax((ult[k] * theta_e - uld[k]) / ddt, 0.0));
-        uld[k] = uld[k] + toadd * dt;
-        net -= toadd;
-        act_capflux += toadd;
-      }
-    }
-  }
-  f.actual_capillary_flux[i] = act_capflux;
-  double kvfac_nl = kvfac[0];
-#pragma unroll
-  for (int k = 1; k < N; ++k)
-    if (k == nlayers - 1) kvfac_nl = kvfac[k];
-  const double deepksat = kv_at_depth(c.kv_profile, kvfac_nl, kv_0, fpar, z_exp, d_soil);
-  const double deeptransfer = jmin(drainable / ddt, deepksat);
-  const double leakage = jmax(0.0, jmin(__ldg(f.maximum_leakage + i), deeptransfer));
-  f.actual_leakage[i] = leakage;
-  const double recharge = (transfer - act_capflux - leakage - ae_sat - soilevap_sat);
-  f.recharge[i] = recharge;
-  // the recharge / water-table hand-off to the subsurface flow (sbm_model.jl:74-81), fused:
-  // exchange_recharge_kernel would re-read both arrays
-  f.recharge_rate[i] = recharge;
-  f.ssf_water_table_depth[i] = zi;
-  // total AET (soil.jl:1206-1209) + interception (sbm.jl:130)
-  double aet = soil_evaporation + transpiration + aeow_river + aeow_land + 0.0;
-  aet += interception;
-  f.actual_evapotranspiration[i] = aet;
-  f.drainable_water_depth[i] = drainable;
-#pragma unroll
-  for (int k = 0; k < N; ++k)
-    f.unsaturated_layer_depth[k * ns + i] = uld[k];
 }
 
 // update_bc_open_water_runoff_model!: river h -> land grid                 runoff.jl:77-79
@@ -825,10 +932,9 @@ total_water_storage_kernel(const DevFields f, const KCfg c, const int32_t* __res
 }
 
 // ---- self-test of device_math.cuh (wflowb200_selftest_math) ----------------------------------
-// Largest distance, in units in the last place, between flog / fexp and libdevice's log / exp
-// (both are < 1 ulp from the correctly rounded value), the largest relative difference of
-// jpow(x, c) for x in (0, 1], c in [1, 40] against exp(c log x), and checks of fdiv, jmin, jmax
-// and jcld_pos against the plain formulations.
+// The largest relative difference of jpow(x, c) = exp(c log x) for x in (0, 1], c in [1, 40]
+// against libdevice's pow, and checks of fdiv, jmin, jmax and jcld_pos against the plain
+// formulations (out[0], out[1] are unused and stay 0).
 __device__ __forceinline__ double ulp_dist(double a, double b) {
   if (a == b || (a != a && b != b)) return 0.0;
   if (a != a || b != b) return 1e300;
@@ -849,15 +955,9 @@ __global__ void selftest_math_kernel(long long n, unsigned long long* out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const double u = u01_hash(i, 1), v = u01_hash(i, 2), t = u01_hash(i, 3);
-    // exp over the whole finite range, log over 600 decades and close to 1
-    const double xe = -745.0 + 1455.0 * u;
-    w_exp = fmax(w_exp, ulp_dist(fexp(xe), exp(xe)));
-    double xl = exp((u - 0.5) * 1380.0);
-    if ((i & 3) == 1) xl = 1.0 + (v - 0.5) * 0.0625 * t;
-    if ((i & 3) == 2) xl = 1.0 - ldexp(v, -(int)(t * 52.0));
-    w_log = fmax(w_log, ulp_dist(flog(xl), log(xl)));
+    // jpow(x, c) = exp(c log x) against libdevice's pow (different algorithm, both < 1 ulp-ish)
     const double xp = (i & 1) ? v : 1.0 - v * v * v, cp = 1.0 + 39.0 * t;
-    const double want = exp(cp * log(xp)), got = jpow_fast(xp, cp);
+    const double want = pow(xp, cp), got = jpow(xp, cp);
     if (want > 1e-290) w_pow = fmax(w_pow, fabs(got - want) / want);
     // fdiv == IEEE division for normal operands; zero numerator gives zero
     const double a = (i % 7 == 0) ? 0.0 : ldexp(0.5 + u, (int)(v * 600.0) - 300);
@@ -908,43 +1008,28 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
   return 1;
 }
 
-// The domain is cut into slices. The loop engine of a slice is a latency-bound tail (it lasts
-// as long as the longest Brooks-Corey loop of the slice, with a few hundred busy warps), so it
-// runs on a high-priority side stream UNDER the bandwidth-bound kernels of the next slices:
-//   main:  A0 A1 A2 A3 C0 C1 C2 C3      (A = land_surface_kernel, C = soil_column_kernel)
-//   side:     E0 E1 E2 E3               (E = loop / resume rounds; a cell can be suspended once
-//                                        per layer, hence n_layers rounds)
-// Only the last slice's engine is exposed, and C0 .. C(K-2) run under it.
-// ev[2k] orders E_k after A_k, ev[2k+1] orders C_k after E_k.
+// The ordered tiles are cut into slices. The loop engine of a slice is a latency-bound tail (it
+// lasts as long as the longest Brooks-Corey loop of the slice, with a few hundred busy warps), so
+// it runs on a high-priority side stream UNDER land_hydrology_kernel of the next slices:
+//   main:  O A0 A1 A2 A3             (O = tile_order_kernel, A = land_hydrology_kernel)
+//   side:       E0 E1 E2 E3          (E = loop / resume rounds; a cell can be suspended once
+//                                     per layer, hence n_layers rounds)
+// Slice 0 holds the tiles with the longest loops of the previous step; only the engine of the
+// last slice is exposed. ev[2k] orders E_k after A_k, ev[2k+1] joins E_k into the main stream.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork* w, int n_slices, int engine_grid, cudaStream_t s,
-                          cudaStream_t const* side, cudaEvent_t const* ev) {
+                          const UnsatWork* w, int n_slices, const int* slice_tile_begin,
+                          unsigned* tile_prio, int32_t* tile_order, int engine_grid,
+                          cudaStream_t s, cudaStream_t const* side, cudaEvent_t const* ev) {
   int launches = 0;
-  if (n_slices < 1) n_slices = 1;
-  const int per = ((c.ns + n_slices - 1) / n_slices + 127) / 128 * 128;
-  auto range = [&](int k, int& i0, int& i1) {
-    i0 = k * per;
-    i1 = (k + 1) * per < c.ns ? (k + 1) * per : c.ns;
-    return i0 < i1;
-  };
-  auto second_half = [&](int k) {
-    int i0, i1;
-    if (!range(k, i0, i1)) return;
-    if (n_slices > 1) cudaStreamWaitEvent(s, ev[2 * k + 1], 0);
-    const int grid = (i1 - i0 + WFB_V_BLOCK - 1) / WFB_V_BLOCK;
-    switch (n_layers) {
-#define WFB_CASE(NN) case NN: soil_column_kernel<NN><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, dt, i0, i1); break;
-      WFB_CASE(1) WFB_CASE(2) WFB_CASE(3) WFB_CASE(4) WFB_CASE(5) WFB_CASE(6) WFB_CASE(7) WFB_CASE(8)
-#undef WFB_CASE
-    }
-    ++launches;
-  };
+  const int n_tiles = (c.ns + kTile - 1) / kTile;
+  tile_order_kernel<<<1, 1024, 0, s>>>(tile_prio, tile_order, n_tiles);
+  ++launches;
   for (int k = 0; k < n_slices; ++k) {
-    int i0, i1;
-    if (!range(k, i0, i1)) break;
+    const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
+    if (t0 >= t1) continue;
     cudaMemsetAsync(w[k].count, 0, 2 * kBuckets * sizeof(unsigned), s);
-    const int grid = (i1 - i0 + WFB_V_BLOCK - 1) / WFB_V_BLOCK;
-    WFB_DISPATCH_N(n_layers, (land_surface_kernel<N><<<grid, WFB_V_BLOCK, 0, s>>>(f, c, w[k], dt, i0, i1)));
+    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<t1 - t0, kTile, 0, s>>>(
+                                 f, c, w[k], dt, tile_order, t0)));
     ++launches;
     cudaStream_t e = n_slices > 1 ? side[k % WFB_V_SIDE_STREAMS] : s;
     if (n_slices > 1) {
@@ -961,7 +1046,9 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
     }
     if (n_slices > 1) cudaEventRecord(ev[2 * k + 1], e);
   }
-  for (int k = 0; k < n_slices; ++k) second_half(k);
+  if (n_slices > 1)
+    for (int k = 0; k < n_slices; ++k)
+      if (slice_tile_begin[k] < slice_tile_begin[k + 1]) cudaStreamWaitEvent(s, ev[2 * k + 1], 0);
   return launches;
 }
 

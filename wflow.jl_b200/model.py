@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 
-INT_FIELDS = {"number_of_layers": 0, "n_unsatlayers": 1}
+INT_FIELDS = {"number_of_layers": 0, "n_unsatlayers": 1, "nlayers_kv": 2}
 
 
 class WflowB200Error(RuntimeError):
@@ -51,6 +51,8 @@ class SbmModel:
         c.dt_ssf = float(cfg.get("dt_ssf", 86400.0))
         c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
         c.kin_wave_min_flow_qroot = float(cfg.get("kin_wave_min_flow_qroot", 1e-30 ** 0.2))
+        for k in ("wave_piece_depth_land", "vertical_slices", "unsat_inline_iters"):  # 0 = automatic
+            setattr(c, k, int(cfg.get(k, 0)))
         d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
                         rli.ctypes.data)
         rc = self._L.wflowb200_create(C.byref(c), C.byref(d), C.byref(self._h))
@@ -165,6 +167,19 @@ class SbmModel:
 
     def synchronize(self):
         self._check(self._L.wflowb200_synchronize(self._h))
+
+    def set_option(self, name: str, value: int):
+        """Select between kernel organisations with identical results (wflow_b200.h)."""
+        self._check(self._L.wflowb200_set_option(self._h, name.encode(), int(value)))
+
+    def newton_trace(self, enable: bool):
+        self._check(self._L.wflowb200_newton_trace(self._h, int(enable)))
+
+    def newton_trace_get(self, domain: str) -> np.ndarray:
+        dom = {"land": 0, "river": 1}[domain]
+        a = np.zeros(self.n if dom == 0 else self.nriv, dtype=np.int64)
+        self._check(self._L.wflowb200_get_newton_trace(self._h, dom, a.ctypes.data))
+        return a
 
     # ---- artefacts / statistics ----------------------------------------------------------
     def artifact(self, domain: str, name: str) -> np.ndarray:

@@ -68,20 +68,79 @@ def scheidegger_ldd(d1: int, d2: int, seed: int, mask: np.ndarray | None = None)
     return indices, ldd, down, lin
 
 
+# PCRaster LDD code of the CartesianIndex offset (di, dj)   (utils.jl:2-12)
+_LDD_OF = {(-1, -1): 1, (0, -1): 2, (1, -1): 3, (-1, 0): 4, (1, 0): 6, (-1, 1): 7, (0, 1): 8,
+           (1, 1): 9}
+
+
+def dendritic_ldd(d1: int, d2: int, seed: int, n_active: int | None = None):
+    """A single-outlet dendritic D8 network with all eight drain directions: priority-flood
+    (Barnes et al. 2014) from one outlet on the raster edge over a smooth random surface (a
+    tilted plane + a few low-frequency waves + white noise): every cell drains to the neighbour
+    it was flooded from, i.e. along the steepest-descent path of the pit-filled surface. With
+    `n_active` the basin is the first n_active cells reached (a connected, basin-shaped mask).
+    Cell ids are the column-major ranks of the active cells, so they are unrelated to the
+    drainage order. Same return values as scheidegger_ldd."""
+    import heapq
+    ii, jj = np.meshgrid(np.arange(d1, dtype=np.float64), np.arange(d2, dtype=np.float64),
+                         indexing="ij")
+    lin_all = (jj * d1 + ii).astype(np.int64)
+    ph = u01(seed, 70, np.arange(16))
+    z = 0.9 * (d2 - 1 - jj) / max(d2 - 1, 1) + 0.25 * np.abs(ii / max(d1 - 1, 1) - 0.5)
+    for k in range(4):
+        fx, fy = 1.0 + 2.0 * ph[4 * k], 1.0 + 2.0 * ph[4 * k + 1]
+        z += 0.08 / (k + 1) * np.sin(2 * np.pi * (fx * ii / d1 + ph[4 * k + 2])) \
+            * np.cos(2 * np.pi * (fy * jj / d2 + ph[4 * k + 3]))
+    z += 0.02 * u01(seed, 71, lin_all.ravel()).reshape(d1, d2)
+    want = d1 * d2 if n_active is None else int(n_active)
+    oi, oj = d1 // 2, d2 - 1                        # the outlet: middle of the last column
+    closed = np.zeros((d1, d2), dtype=bool)
+    down_ij = np.full((d1, d2, 2), -1, dtype=np.int64)
+    heap = [(float(z[oi, oj]), oi, oj)]
+    closed[oi, oj] = True
+    count = 1
+    nbrs = [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]
+    while heap and count < want:
+        zc, ci, cj = heapq.heappop(heap)
+        for di, dj in nbrs:
+            ni, nj = ci + di, cj + dj
+            if 0 <= ni < d1 and 0 <= nj < d2 and not closed[ni, nj]:
+                closed[ni, nj] = True
+                down_ij[ni, nj] = (ci, cj)
+                heapq.heappush(heap, (max(float(z[ni, nj]), zc), ni, nj))
+                count += 1
+                if count >= want:
+                    break
+    lin = np.nonzero(closed.ravel(order="F"))[0].astype(np.int64)
+    i = lin % d1
+    j = lin // d1
+    rank = np.full(d1 * d2, -1, dtype=np.int64)
+    rank[lin] = np.arange(len(lin))
+    di = down_ij[i, j, 0] - i
+    dj = down_ij[i, j, 1] - j
+    pit = down_ij[i, j, 0] < 0
+    code = np.array([[_LDD_OF.get((a, b), 5) for b in (-1, 0, 1)] for a in (-1, 0, 1)], dtype=np.uint8)
+    ldd = np.where(pit, 5, code[np.clip(di, -1, 1) + 1, np.clip(dj, -1, 1) + 1]).astype(np.uint8)
+    down = np.where(pit, 0, rank[np.where(pit, 0, down_ij[i, j, 1] * d1 + down_ij[i, j, 0])] + 1)
+    indices = np.stack([i + 1, j + 1], axis=1).astype(np.int64)
+    return indices, ldd, down.astype(np.int64), lin
+
+
 def upstream_cells(indices: np.ndarray, down: np.ndarray) -> np.ndarray:
-    """Number of cells draining through each cell (itself included); rows are processed in
-    increasing j because every edge goes from row j to row j + 1."""
+    """Number of cells draining through each cell (itself included): Kahn's algorithm, one
+    vectorised sweep per topological level."""
     n = len(down)
     acc = np.ones(n, dtype=np.int64)
-    j = indices[:, 1]
-    order = np.argsort(j, kind="stable")
-    js = j[order]
-    bounds = np.searchsorted(js, np.arange(js.min(), js.max() + 2))
-    for a, b in zip(bounds[:-1], bounds[1:]):
-        nodes = order[a:b]
-        d = down[nodes]
+    indeg = np.bincount(down[down > 0] - 1, minlength=n)
+    front = np.nonzero(indeg == 0)[0]
+    while len(front):
+        d = down[front]
         m = d > 0
-        np.add.at(acc, d[m] - 1, acc[nodes[m]])
+        tgt = d[m] - 1
+        np.add.at(acc, tgt, acc[front[m]])
+        np.subtract.at(indeg, tgt, 1)
+        cand = np.unique(tgt)
+        front = cand[indeg[cand] == 0]
     return acc
 
 
@@ -105,16 +164,25 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                cell_length: float = 1000.0, snow: bool = True, glacier: bool = False,
                kv_profile: int = 0, nthreads: int = 8, adaptive: bool = False,
                soil_infiltration_reduction: bool = False, id_offset: int = 0,
-               external_inflow: bool = False):
+               external_inflow: bool = False, network: str = "scheidegger",
+               n_active: int | None = None, n_river: int | None = None):
     """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
-    the reference's field names; layered arrays are cell-major (n, N)."""
-    indices, ldd, down, lin = scheidegger_ldd(d1, d2, seed, mask)
+    the reference's field names; layered arrays are cell-major (n, N). network: "scheidegger"
+    (a forest of many small basins, codes 5/7/8/9) or "dendritic" (one outlet, all eight
+    directions; n_active cells, n_river river cells by upstream area)."""
+    if network == "dendritic":
+        indices, ldd, down, lin = dendritic_ldd(d1, d2, seed, n_active)
+    else:
+        indices, ldd, down, lin = scheidegger_ldd(d1, d2, seed, mask)
     gid = lin + np.int64(id_offset)
     n = len(ldd)
     N = len(soil_layer_thickness_mm) + 1
     acc = upstream_cells(indices, down)
     # river mask: largest upstream areas, fraction ~ Moselle's 5809 / 50063
-    if river_fraction_target > 0:
+    if n_river:
+        thr = np.sort(acc)[::-1][min(int(n_river), n) - 1]
+        river = acc >= max(thr, 2)
+    elif river_fraction_target > 0:
         thr = np.quantile(acc, 1.0 - river_fraction_target)
         river = acc >= max(thr, 2)
     else:
@@ -205,7 +273,7 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     # ---- shared land parameters (domain.jl:218-261, utils.jl:418-466) ------------------------
     xl = yl = cell_length
     area = np.full(n, xl * yl)
-    diag = ~np.isin(ldd, (2, 8, 4, 6))  # our LDD only has 5, 7, 8, 9
+    diag = ~np.isin(ldd, (2, 8, 4, 6))
     F["area"] = area
     F["flow_length"] = np.where(diag, np.hypot(xl, yl), yl)
     F["flow_width"] = np.where(diag, (xl * yl) / np.hypot(xl, yl), xl)
