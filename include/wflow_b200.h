@@ -72,7 +72,8 @@ typedef struct {
   int32_t wave_piece_depth_land; /* levels per piece of the land chunks; -1: one connected piece */
   int32_t vertical_slices;       /* slices of the vertical update (loop engine overlap), 1..8   */
   int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (8)    */
-  int32_t reserved_;
+  int32_t snow_gravitational_transport; /* snow_gravitational_transport__flag: lateral snow
+                                  transport between snow and glacier model     sbm.jl:98-100 */
 } WflowB200Config;
 
 /* The drainage network as the Julia model holds it (network.jl:48-81,175-208). */
@@ -82,6 +83,13 @@ typedef struct {
                                         ascending (utils.jl:85-99)                             */
   const uint8_t* ldd;                /* n: land local_drain_direction (PCRaster 1..9)          */
   const int64_t* river_land_indices; /* nriv: NetworkRiver.land_indices, 1-based, ascending    */
+  /* reservoir__flag (domain.jl:96-109): the river node of every reservoir outlet, i.e. the
+   * positions of the non-zero entries of NetworkRiver.reservoir_indices, reservoir 1 first.
+   * Reservoir outlets are dropped from the upstream lists of the land and river kinematic
+   * waves; their outflow becomes the inflow of the downstream river node
+   * (surface_kinwave.jl:441-489). nres = 0 / NULL: no reservoirs. */
+  int64_t nres;
+  const int64_t* reservoir_river_indices; /* nres, 1-based river node ids                      */
 } WflowB200Domain;
 
 /* artefact ids for wflowb200_get_artifact (all returned as 1-based int64, reference layout) */
@@ -141,6 +149,27 @@ int32_t wflowb200_get_field_i64(WflowB200* h, int32_t which, int64_t* dst);
 int32_t wflowb200_set_forcing(WflowB200* h, const double* precipitation,
                               const double* potential_evaporation, const double* temperature);
 
+/* Staging ring for the forcing of the coming steps (the reader thread of io.jl:108-160 runs
+ * ahead of the model): `depth` slabs of (P, PET, T) in HBM. put() starts the H2D copy of one slab
+ * on the copy stream and returns at once when the arrays are page-locked (it waits, on the
+ * device, until the step that last used the slot has consumed it); use() makes the next
+ * update_* call take its forcing from that slab instead of wflowb200_set_forcing's. */
+int32_t wflowb200_forcing_ring_create(WflowB200* h, int32_t depth);
+int32_t wflowb200_forcing_ring_put(WflowB200* h, int32_t slot, const double* precipitation,
+                                   const double* potential_evaporation, const double* temperature);
+int32_t wflowb200_forcing_ring_use(WflowB200* h, int32_t slot);
+
+/* Cyclic leaf_area_index (update_cyclic!, io.jl:187-227): all n_slabs slabs (12 monthly or 366
+ * daily, [slab][cell] in node order) are staged in HBM once; use() copies one slab into the
+ * model's leaf_area_index on the device when the month / day changes -- no host traffic. */
+int32_t wflowb200_set_cyclic_lai(WflowB200* h, const double* table, int32_t n_slabs);
+int32_t wflowb200_use_cyclic_lai(WflowB200* h, int32_t slab);
+
+/* Output gather (write_output io.jl:815-899 reads a handful of model vectors per step): the
+ * listed fields, concatenated in this order (node order, layered fields cell-major), with ONE
+ * device-to-host copy through page-locked memory. dst holds the sum of the fields' sizes. */
+int32_t wflowb200_get_fields(WflowB200* h, const int32_t* field_ids, int32_t n_ids, double* dst);
+
 /* ---- the hot path --------------------------------------------------------------------- */
 
 /* update_land_hydrology_model!(land, routing, domain, config, dt)            sbm.jl:82-132 */
@@ -157,7 +186,12 @@ int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h);
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt);
 /* update_lateral_inflow!(river, ...)                                  surface_kinwave.jl:710-734 */
 int32_t wflowb200_update_lateral_inflow_river(WflowB200* h);
-/* update_river_flow_model!(river, domain, clock, dt)                  surface_kinwave.jl:613-662 */
+/* update_inflow!(reservoir, river_flow, (; overland_flow, subsurface_flow), network): overland
+ * and subsurface flow into the reservoirs                             surface_kinwave.jl:772-805 */
+int32_t wflowb200_update_inflow_reservoir(WflowB200* h);
+/* update_river_flow_model!(river, domain, clock, dt), incl. the reservoirs on the river
+ * (update_reservoir_model! reservoir.jl:585-634: simple, modified_puls, free_weir without a
+ * linked lower reservoir, observed outflow; linear storage curve)    surface_kinwave.jl:613-662 */
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt);
 /* update_total_water_storage!(land, domain, routing)                          sbm.jl:143-182 */
 int32_t wflowb200_update_total_water_storage(WflowB200* h);

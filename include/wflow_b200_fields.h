@@ -2,7 +2,7 @@
  * wflow_b200_fields.h -- the Float64 arrays of the Julia model structs that live on the device.
  *
  * X(name, kind): kind 0 = land scalar (n), 1 = land layered (n x N), 2 = land layered+1
- * (n x (N+1)), 3 = river scalar (nriv). Names are the reference's struct field names; a
+ * (n x (N+1)), 3 = river scalar (nriv), 4 = reservoir scalar (nres). Names are the reference's struct field names; a
  * component prefix is added where two structs share a name (snow_/glacier_/ssf_/olf_/riv_/
  * recharge_/runoff_/soil_).
  *
@@ -14,7 +14,10 @@
  *   SbmSoilVariables :4-84, Kv* :213-244 (kv, z_layered: the layered profiles); LateralSsf* routing/subsurface/
  *   lateral_subsurface_flow.jl:2-54, RechargeVariables boundary_conditions.jl:204-213;
  *   OverLandFlowVariables routing/surface/surface_kinwave.jl:154-178, LandFlowBC :181-185;
- *   RiverFlowVariables :5-29, RiverFlowBC routing/surface/surface_flow.jl:9-34.
+ *   RiverFlowVariables :5-29, RiverFlowBC routing/surface/surface_flow.jl:9-34;
+ *   ReservoirParameters routing/surface/reservoir.jl:5-44, ReservoirVariables :200-217,
+ *   ReservoirBC :251-272 (res_outflow_curve_type holds ReservoirOutflowType as a number:
+ *   2 free_weir, 3 modified_puls, 4 simple).
  */
 #ifndef WFLOW_B200_FIELDS_H
 #define WFLOW_B200_FIELDS_H
@@ -30,6 +33,7 @@
   X(temperature_threshold_melt, 0) X(degree_day_factor, 0) X(water_holding_capacity, 0) \
   X(snow_storage, 0) X(snow_water, 0) X(snow_water_equivalent, 0) X(snow_melt, 0) \
   X(snow_runoff, 0) X(effective_precip, 0) X(snow_precip, 0) X(liquid_precip, 0) \
+  X(snow_in, 0) X(snow_out, 0) \
   X(glacier_temperature_threshold_melt, 0) X(glacier_degree_day_factor, 0) \
   X(glacier_snow_to_ice_fraction, 0) X(glacier_fraction, 0) X(glacier_store, 0) \
   X(glacier_melt, 0) \
@@ -77,6 +81,15 @@
   X(riv_abstraction, 3) X(riv_actual_external_abstraction_cumulative, 3) \
   X(riv_actual_external_abstraction_average, 3) X(riv_inwater, 3) X(riv_q, 3) \
   X(riv_qlat, 3) X(riv_qin, 3) X(riv_qin_cumulative, 3) X(riv_qin_average, 3) \
-  X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3)
+  X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3) \
+  X(res_area, 4) X(res_outflow_curve_type, 4) X(res_maximum_storage, 4) X(res_threshold, 4) \
+  X(res_rating_curve_coefficient, 4) X(res_rating_curve_exponent, 4) X(res_maximum_release, 4) \
+  X(res_demand, 4) X(res_target_minimum_fraction, 4) X(res_target_full_fraction, 4) \
+  X(res_inflow_subsurface, 4) X(res_inflow_overland, 4) X(res_inflow_cumulative, 4) \
+  X(res_inflow_average, 4) X(res_external_inflow, 4) \
+  X(res_actual_external_abstraction_cumulative, 4) X(res_actual_external_abstraction_average, 4) \
+  X(res_precipitation, 4) X(res_evaporation, 4) X(res_waterlevel, 4) X(res_storage, 4) \
+  X(res_outflow, 4) X(res_outflow_cumulative, 4) X(res_outflow_average, 4) X(res_outflow_obs, 4) \
+  X(res_actevap_cumulative, 4)
 
 #endif

@@ -330,15 +330,17 @@ def get_flow_fraction_to_river(g: DiGraph1, ldd, inds_river, slope) -> np.ndarra
     return fraction
 
 
-def build_domain_network(ldd, indices, d1, min_sto, nthreads, streamorder=None):
-    """NetworkLand / NetworkRiver construction (network.jl:87-133, 214-278; domain.jl:108-122)
-    without reservoirs. Returns a dict of the reference's artefacts (1-based)."""
+def build_domain_network(ldd, indices, d1, min_sto, nthreads, streamorder=None, pits_mask=None):
+    """NetworkLand / NetworkRiver construction (network.jl:87-133, 214-278; domain.jl:80-125).
+    pits_mask: the reservoir outlet cells of this domain (domain.jl:96-109): they are dropped
+    from the upstream lists AFTER order and sub-domains have been built on the full graph.
+    Returns a dict of the reference's artefacts (1-based)."""
     g, ldd2 = flowgraph(ldd, indices, d1)
     order = topological_sort_by_dfs(g)
     so = stream_order(g, order) if streamorder is None else np.asarray(streamorder)
     pits = np.nonzero(ldd2 == LDD_PIT)[0] + 1
     sub_order, sub_indices, sub_topo = kinwave_set_subdomains(g, order, pits, so, min_sto, nthreads)
-    up_ptr, up_idx = filter_upstream_nodes(g, order)
+    up_ptr, up_idx = filter_upstream_nodes(g, order, pits_mask)
     return dict(graph=g, ldd=ldd2, order=order, streamorder=so, pits=pits,
                 order_of_subdomains=sub_order, subdomain_indices=sub_indices,
                 order_subdomain=sub_topo, up_ptr=up_ptr, up_idx=up_idx)

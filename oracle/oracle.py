@@ -32,14 +32,15 @@ class _Net(C.Structure):
     _fields_ = [("n", C.c_int64), ("up_ptr", C.c_void_p), ("up_idx", C.c_void_p),
                 ("n_levels", C.c_int64), ("level_ptr", C.c_void_p), ("level_sub", C.c_void_p),
                 ("n_sub", C.c_int64), ("sub_ptr", C.c_void_p), ("sub_nodes", C.c_void_p),
-                ("sub_pos", C.c_void_p)]
+                ("sub_pos", C.c_void_p), ("down", C.c_void_p), ("order", C.c_void_p)]
 
 
 class _Cfg(C.Structure):
-    _fields_ = [("n", C.c_int64), ("nriv", C.c_int64), ("N", C.c_int64),
+    _fields_ = [("n", C.c_int64), ("nriv", C.c_int64), ("N", C.c_int64), ("nres", C.c_int64),
                 ("gash", C.c_int32), ("has_lai", C.c_int32), ("snow", C.c_int32),
                 ("glacier", C.c_int32), ("soil_infiltration_reduction", C.c_int32),
-                ("kv_profile", C.c_int32), ("adaptive", C.c_int32), ("nthreads", C.c_int32),
+                ("kv_profile", C.c_int32), ("adaptive", C.c_int32), ("snow_transport", C.c_int32),
+                ("nthreads", C.c_int32),
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
                 ("ssf_alpha_coefficient", C.c_double)]
 
@@ -65,9 +66,11 @@ def lib(variant: str = ""):
             getattr(L, f).restype = None
         for f in ("wfo_exchange_recharge", "wfo_update_total_water_storage",
                   "wfo_update_diagnostic_vars", "wfo_update_lateral_inflow_overland",
-                  "wfo_update_lateral_inflow_river"):
+                  "wfo_update_lateral_inflow_river", "wfo_update_inflow_reservoir"):
             getattr(L, f).argtypes = [C.c_void_p]
             getattr(L, f).restype = None
+        L.wfo_kinwave_river_update.argtypes = [C.c_void_p, C.c_double]
+        L.wfo_kinwave_river_update.restype = None
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.wfo_get_stats.restype = None
         L.wfo_set_num_threads.argtypes = [C.c_int]
@@ -108,6 +111,7 @@ def lib(variant: str = ""):
                                             C.c_void_p], d)
         sig("wfo_round_sigdigits12", [d], d)
         sig("wfo_cld", [d, d], d)
+        sig("wfo_accucapacityflux", [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, d])
         _libs[variant] = L
     return _libs[variant]
 
@@ -121,7 +125,7 @@ def field_table():
 # lateral_subsurface_flow.jl:9-38, boundary_conditions.jl:204-213, surface_kinwave.jl:5-29,
 # 154-185, surface_flow.jl:9-34); every other field starts as MISSING_VALUE (NaN).
 ZERO_DEFAULTS = (
-    "canopy_storage", "waterdepth_river", "unsaturated_store_depth", "total_storage",
+    "snow_in", "snow_out", "canopy_storage", "waterdepth_river", "unsaturated_store_depth", "total_storage",
     "ssf_exfiltwater_cumulative", "ssf_exfiltwater_average", "ssf_q_cumulative", "ssf_q_average",
     "ssf_q_in_cumulative", "ssf_q_in_average", "ssf_to_river_cumulative", "ssf_to_river_average",
     "ssf_q_net_cumulative", "ssf_q_net_average", "recharge_flux", "recharge_flux_cumulative",
@@ -133,7 +137,13 @@ ZERO_DEFAULTS = (
     "riv_q_cumulative", "riv_q_average", "riv_storage", "riv_h")
 VALUE_DEFAULTS = {"f_infiltration_reduction": 1.0, "soil_surface_temperature": 10.0 + 273.15}
 
-INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_indices")
+INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_indices",
+              "reservoir_river_indices")
+# reservoir defaults (reservoir.jl:200-272): cumulative / average variables start at zero
+ZERO_DEFAULTS = ZERO_DEFAULTS + (
+    "res_inflow_cumulative", "res_inflow_average", "res_external_inflow",
+    "res_actual_external_abstraction_cumulative", "res_actual_external_abstraction_average",
+    "res_outflow_cumulative", "res_outflow_average", "res_actevap_cumulative")
 
 
 def call_out(fn_name, nout, *args):
@@ -166,9 +176,10 @@ class OracleModel:
         self.h = L.wfo_new()
         c = L.wfo_cfg(self.h).contents
         n, nriv, N = int(cfg["n"]), int(cfg["nriv"]), int(cfg["N"])
-        c.n, c.nriv, c.N = n, nriv, N
+        nres = int(cfg.get("nres", 0))
+        c.n, c.nriv, c.N, c.nres = n, nriv, N, nres
         for k in ("gash", "has_lai", "snow", "glacier", "soil_infiltration_reduction",
-                  "kv_profile", "adaptive"):
+                  "kv_profile", "adaptive", "snow_transport"):
             setattr(c, k, int(cfg.get(k, 0)))
         c.nthreads = int(cfg.get("nthreads", 0))
         c.dt_land = float(cfg.get("dt_land", 3600.0))
@@ -177,7 +188,7 @@ class OracleModel:
         c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
         self.cfg = dict(cfg)
         self.f = {}
-        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,)}
+        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,), 4: (nres,)}
         for name, kind in field_table():
             if name in fields and fields[name] is not None:
                 a = np.ascontiguousarray(np.array(fields[name], dtype=np.float64, copy=True))
@@ -191,7 +202,7 @@ class OracleModel:
             self.f[name] = a
             L.wfo_set_ptr(self.h, name.encode(), a.ctypes.data)
         for name in INT_FIELDS:
-            size = nriv if name == "river_land_indices" else n
+            size = {"river_land_indices": nriv, "reservoir_river_indices": nres}.get(name, n)
             if name in fields and fields[name] is not None:
                 a = np.ascontiguousarray(np.array(fields[name], dtype=np.int64, copy=True))
             else:
@@ -210,6 +221,11 @@ class OracleModel:
             sp, sn = _csr(net["order_subdomain"])
             _, si = _csr(net["subdomain_indices"])
             arrs["sub_ptr"], arrs["sub_nodes"], arrs["sub_pos"] = sp, sn - 1, si - 1
+            if "graph" in net:   # only the reservoirs need the downstream node
+                arrs["down"] = np.asarray(net["graph"].down, dtype=np.int64) - 1   # 0 (pit) -> -1
+            else:
+                arrs["down"] = np.full(max(int(s.n), 1), -1, dtype=np.int64)
+            arrs["order"] = np.asarray(net["order"], dtype=np.int64) - 1
             s.n_levels = len(net["order_of_subdomains"])
             s.n_sub = len(net["order_subdomain"])
             for k, a in arrs.items():
@@ -233,6 +249,7 @@ class OracleModel:
     def surface_routing(self, dt): self._L.wfo_surface_routing(self.h, dt)
     def update_lateral_inflow_overland(self): self._L.wfo_update_lateral_inflow_overland(self.h)
     def update_lateral_inflow_river(self): self._L.wfo_update_lateral_inflow_river(self.h)
+    def update_inflow_reservoir(self): self._L.wfo_update_inflow_reservoir(self.h)
     def update_overland_flow_model(self, dt): self._L.wfo_update_overland_flow_model(self.h, dt)
     def update_river_flow_model(self, dt): self._L.wfo_update_river_flow_model(self.h, dt)
     def update_total_water_storage(self): self._L.wfo_update_total_water_storage(self.h)

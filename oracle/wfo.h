@@ -24,7 +24,7 @@
 #include <stdint.h>
 
 /* kind: 0 = land scalar (n), 1 = land layered (n*N), 2 = land layered+1 (n*(N+1)),
- *       3 = river scalar (nriv) */
+ *       3 = river scalar (nriv), 4 = reservoir scalar (nres) */
 #define WFO_FIELDS(X) \
   /* forcing (forcing.jl:2-10) */ \
   X(precipitation, 0) X(potential_evaporation, 0) X(temperature, 0) \
@@ -40,6 +40,7 @@
   X(temperature_threshold_melt, 0) X(degree_day_factor, 0) X(water_holding_capacity, 0) \
   X(snow_storage, 0) X(snow_water, 0) X(snow_water_equivalent, 0) X(snow_melt, 0) \
   X(snow_runoff, 0) X(effective_precip, 0) X(snow_precip, 0) X(liquid_precip, 0) \
+  X(snow_in, 0) X(snow_out, 0) \
   /* glacier (glacier.jl) */ \
   X(glacier_temperature_threshold_melt, 0) X(glacier_degree_day_factor, 0) \
   X(glacier_snow_to_ice_fraction, 0) X(glacier_fraction, 0) X(glacier_store, 0) \
@@ -96,7 +97,19 @@
   X(riv_abstraction, 3) X(riv_actual_external_abstraction_cumulative, 3) \
   X(riv_actual_external_abstraction_average, 3) X(riv_inwater, 3) X(riv_q, 3) \
   X(riv_qlat, 3) X(riv_qin, 3) X(riv_qin_cumulative, 3) X(riv_qin_average, 3) \
-  X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3)
+  X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3) \
+  /* reservoirs (routing/surface/reservoir.jl:5-44 parameters, 200-217 variables, 251-272 BC); \
+   * res_outflow_curve_type holds ReservoirOutflowType as a number (2 free_weir, 3 \
+   * modified_puls, 4 simple) */ \
+  X(res_area, 4) X(res_outflow_curve_type, 4) X(res_maximum_storage, 4) X(res_threshold, 4) \
+  X(res_rating_curve_coefficient, 4) X(res_rating_curve_exponent, 4) X(res_maximum_release, 4) \
+  X(res_demand, 4) X(res_target_minimum_fraction, 4) X(res_target_full_fraction, 4) \
+  X(res_inflow_subsurface, 4) X(res_inflow_overland, 4) X(res_inflow_cumulative, 4) \
+  X(res_inflow_average, 4) X(res_external_inflow, 4) \
+  X(res_actual_external_abstraction_cumulative, 4) X(res_actual_external_abstraction_average, 4) \
+  X(res_precipitation, 4) X(res_evaporation, 4) X(res_waterlevel, 4) X(res_storage, 4) \
+  X(res_outflow, 4) X(res_outflow_cumulative, 4) X(res_outflow_average, 4) X(res_outflow_obs, 4) \
+  X(res_actevap_cumulative, 4)
 
 /* Per-domain network artefacts needed to walk the routing in the reference's order
  * (network.jl:48-81): all 0-based here. */
@@ -111,16 +124,20 @@ typedef struct {
   const int64_t* sub_ptr;     /* CSR: per subdomain, its nodes in walk order          */
   const int64_t* sub_nodes;   /* order_subdomain[m]   (node id v)                     */
   const int64_t* sub_pos;     /* subdomain_indices[m] (toposort position n)           */
+  const int64_t* down;        /* outneighbors(graph, v): downstream node or -1 (pit)  */
+  const int64_t* order;       /* network.order (topological_sort_by_dfs), node ids    */
 } wfo_network;
 
 typedef struct {
   int64_t n, nriv, N;         /* land cells, river cells, maximum_number_of_layers    */
+  int64_t nres;               /* reservoirs (reservoir__flag)                         */
   int32_t gash;               /* 1: Gash (dt >= 23 h), 0: modified Rutter  sbm.jl:26  */
   int32_t has_lai;            /* cyclic LAI present (canopy.jl:65,128)                */
   int32_t snow, glacier;      /* snow__flag, glacier__flag                            */
   int32_t soil_infiltration_reduction;
   int32_t kv_profile;         /* 0 exponential, 1 exponential_constant, 2 layered, 3 layered_exponential */
   int32_t adaptive;           /* kinematic_wave__adaptive_time_step_flag              */
+  int32_t snow_transport;     /* snow_gravitational_transport__flag                   */
   int32_t nthreads;           /* OpenMP threads (0 = default)                         */
   double dt_land, dt_river, dt_ssf, ssf_alpha_coefficient;
 } wfo_config;
@@ -134,6 +151,8 @@ typedef struct wfo_model {
   int64_t* n_unsatlayers;     /* n */
   int64_t* nlayers_kv;        /* n (layered_exponential only) */
   int64_t* river_land_indices;/* nriv, 0-based land index of each river cell */
+  int64_t* reservoir_river_indices; /* nres, 0-based river node of each reservoir     */
+  int64_t* riv_reservoir;     /* nriv: NetworkRiver.reservoir_indices - 1 (-1 = none), derived */
   int64_t* newton_trace_land; /* n / nriv or NULL: Newton iterations of kinematic_wave per node, */
   int64_t* newton_trace_river;/* summed over the sub-steps (iteration-count parity tests)       */
   wfo_network land, river;
@@ -161,7 +180,8 @@ wfo_config* wfo_cfg(wfo_model*);
 
 /* model-level sweeps */
 void wfo_update_land_hydrology_model(wfo_model*, double dt);   /* sbm.jl:82-132  */
-void wfo_exchange_recharge(wfo_model*);                        /* sbm_model.jl:74-81 */
+void wfo_exchange_recharge(wfo_model*);                        /* sbm_model.jl:74-84 */
+void wfo_kh_layered_profile(wfo_model*);                       /* utils.jl:792-895   */
 void wfo_update_subsurface_flow_model(wfo_model*, double dt);  /* lateral_subsurface_flow.jl:279-304 */
 void wfo_update_soil_water_storage(wfo_model*, double dt);     /* soil.jl:1294-1392 */
 void wfo_surface_routing(wfo_model*, double dt);               /* surface_routing.jl:7-46 */
@@ -169,6 +189,8 @@ void wfo_update_overland_flow_model(wfo_model*, double dt);
 void wfo_update_river_flow_model(wfo_model*, double dt);
 void wfo_update_lateral_inflow_overland(wfo_model*);
 void wfo_update_lateral_inflow_river(wfo_model*);
+void wfo_update_inflow_reservoir(wfo_model*);                  /* surface_kinwave.jl:772-805 */
+void wfo_kinwave_river_update(wfo_model*, double dt_s);        /* test hook: one sub-step    */
 void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182 */
 void wfo_update_model(wfo_model*, double dt);                  /* sbm_model.jl:60-92 */
 void wfo_update_diagnostic_vars(wfo_model*);                   /* soil.jl:1400-1436 */
@@ -220,6 +242,10 @@ void wfo_water_table_change(wfo_model* m, double net_flux, double sy, int64_t i,
 double wfo_stable_timestep_surface(const double* q, const double* alpha, const double* len,
                                    int64_t n, double p, double* work);
 double wfo_round_sigdigits12(double v);
+/* accucapacityflux!(flux, material, network, capacity, dt)  routing/utils.jl:82-109; `order`
+ * and `down` 0-based (down < 0: pit); material is updated in place */
+void wfo_accucapacityflux(double* flux, double* material, const int64_t* order,
+                          const int64_t* down, int64_t n, const double* capacity, double dt);
 double wfo_cld(double x, double y);
 #ifdef __cplusplus
 }

@@ -195,6 +195,82 @@ static void update_ustorelayerdepth(wfo_model* m, double zi_prev, double zi, int
   m->water_table_depth[i] = zi;
 }
 
+/* kinematic_wave_ssf(..., kh_profile::KhLayered, ...)      subsurface_process.jl:183-228
+ * celerity from the equivalent conductivity kh of the step (ssf_celerity :47-51); no inner
+ * sub-iterations; the excess above the soil column uses the effective specific yield sy_d */
+static void kinematic_wave_ssf_layered(wfo_model* m, double q_in, double q_prev, double zi_prev,
+                                       double q_net_bnds, double slope, double sy, double d,
+                                       double dt, double dx, double dw, double q_max, int64_t i,
+                                       double out[4]) {
+  double q = (q_prev + q_in) / 2.0;
+  const double celerity = (slope * m->ssf_kh[i]) / sy;
+  const double constant_term = (dt / dx) * (q_in + q_net_bnds) + q_prev / celerity;
+  q = wfo_kw_ssf_newton_raphson(q, constant_term, celerity, dt, dx);
+  q = jl_min(q, (q_max * dw));
+  const double net_flux = (q_in + q_net_bnds - q) / (dw * dx);
+  double o[2];
+  wfo_water_table_change(m, net_flux, sy, i, dt, o);
+  const double dh = o[0], exfilt = o[1];
+  double zi = zi_prev - dh;
+  const double sy_d = dh > 0.0 ? (net_flux - exfilt) * dt / dh : sy;
+  if (zi > d) {
+    const double q_excess = (dw * dx) * sy_d * (zi - d) / dt;
+    q = jl_max(q - q_excess, WFO_KIN_WAVE_MIN_FLOW);
+  }
+  zi = jl_clamp(zi, 0.0, d);
+  update_ustorelayerdepth(m, zi_prev, zi, i);
+  out[0] = q; out[1] = zi; out[2] = exfilt; out[3] = net_flux;
+}
+
+/* kh_layered_profile!(soil, subsurface_flow, kv_profile::KvLayered / KvLayeredExponential)
+ * utils.jl:792-895: equivalent horizontal conductivity of the saturated part of the column */
+void wfo_kh_layered_profile(wfo_model* m) {
+  const int prof = m->cfg.kv_profile;
+  if (prof < 2) return;
+  const int64_t N = m->cfg.N;
+  PFOR for (int64_t i = 0; i < m->cfg.n; ++i) {
+    const double* kv = m->kv + i * N;
+    const double* cld = m->cumulative_layer_depth + i * (N + 1);   /* _sumlayers[n] = cld[n] */
+    const double* alt = m->actual_layer_thickness + i * N;
+    const int64_t mm = m->number_of_layers[i];
+    const double d = m->soil_thickness[i], zi = m->water_table_depth[i];
+    const double ratio = m->ssf_khfrac[i];
+    if (d > zi) {
+      double transmissivity = 0.0;
+      int64_t n = m->n_unsatlayers[i] > 1 ? m->n_unsatlayers[i] : 1;
+      if (prof == 2) {
+        transmissivity += (cld[n] - zi) * kv[n - 1];
+        n += 1;
+        while (n <= mm) { transmissivity += alt[n - 1] * kv[n - 1]; n += 1; }
+      } else {
+        const double f = m->hydraulic_conductivity_scale_parameter[i], zl = m->z_layered[i];
+        const int64_t j = m->nlayers_kv[i];
+        if (zi >= zl) {
+          const double zt = d - zl;
+          transmissivity += kv[j - 1] / f * (exp(-f * (zi - zl)) - exp(-f * zt));
+          n = mm;
+        } else {
+          transmissivity += (cld[n] - zi) * kv[n - 1];
+        }
+        n += 1;
+        while (n <= mm) {
+          if (n > j) {
+            const double zt = d - zl;
+            transmissivity += kv[j - 1] / f * (1.0 - exp(-f * zt));
+            n = mm;
+          } else {
+            transmissivity += alt[n - 1] * kv[n - 1];
+          }
+          n += 1;
+        }
+      }
+      m->ssf_kh[i] = (transmissivity / (d - zi)) * ratio;
+    } else {
+      m->ssf_kh[i] = kv[mm - 1] * ratio;
+    }
+  }
+}
+
 /* routing/subsurface/subsurface_process.jl:89-172 (KhExponential / KhExponentialConstant) */
 void wfo_kinematic_wave_ssf(wfo_model* m, double q_in, double q_prev, double zi_prev,
                             double q_net_bnds, double slope, double sy, double d, double dt,
@@ -204,6 +280,11 @@ void wfo_kinematic_wave_ssf(wfo_model* m, double q_in, double q_prev, double zi_
     return;
   }
   const int prof = m->cfg.kv_profile;
+  if (prof >= 2) {
+    kinematic_wave_ssf_layered(m, q_in, q_prev, zi_prev, q_net_bnds, slope, sy, d, dt, dx, dw,
+                               q_max, i, out);
+    return;
+  }
   const double kh_0 = m->kh_0[i], f = m->hydraulic_conductivity_scale_parameter[i];
   const double z_exp = prof == 1 ? m->z_exp[i] : 0.0;
   double q = (q_prev + q_in) / 2.0;
@@ -299,9 +380,11 @@ static double stable_timestep_ssf(wfo_model* m) {
   for (int64_t i = 0; i < m->cfg.n; ++i) {
     if (m->ssf_water_table_depth[i] > 0.0) {
       ++k;
-      double c = wfo_ssf_celerity(m->ssf_water_table_depth[i], m->slope[i], m->specific_yield[i],
-                                  m->kh_0[i], m->hydraulic_conductivity_scale_parameter[i],
-                                  prof == 1 ? m->z_exp[i] : 0.0, prof);
+      double c = prof >= 2 ? (m->slope[i] * m->ssf_kh[i]) / m->specific_yield[i]
+                           : wfo_ssf_celerity(m->ssf_water_table_depth[i], m->slope[i],
+                                              m->specific_yield[i], m->kh_0[i],
+                                              m->hydraulic_conductivity_scale_parameter[i],
+                                              prof == 1 ? m->z_exp[i] : 0.0, prof);
       dt_min = jl_min(dt_min, m->flow_length[i] / c);
     }
   }
@@ -362,6 +445,7 @@ void wfo_exchange_recharge(wfo_model* m) {
     m->recharge_rate[i] = m->recharge[i];
     m->ssf_water_table_depth[i] = m->water_table_depth[i];
   }
+  wfo_kh_layered_profile(m);   /* sbm_model.jl:84, layered conductivity profiles only */
 }
 
 /* lateral_subsurface_flow.jl:279-304 ; groundwater.jl:606-638 ; boundary_conditions.jl:12-21,219-236 */
@@ -482,7 +566,143 @@ void wfo_update_overland_flow_model(wfo_model* m, double dt) {
 /* river flow                                                                               */
 /* ---------------------------------------------------------------------------------------- */
 
-/* surface_kinwave.jl:492-566 (no reservoirs, no floodplain) */
+/* ---------------------------------------------------------------------------------------- */
+/* reservoirs                                                    routing/surface/reservoir.jl */
+/* ---------------------------------------------------------------------------------------- */
+
+/* update_reservoir_simple                                                reservoir.jl:389-421 */
+static void update_reservoir_simple(wfo_model* m, int64_t i, double precipitation,
+                                    double evaporation, double inflow, double dt, double* outflow,
+                                    double* storage_out) {
+  double storage = m->res_storage[i] + (inflow + precipitation - evaporation) * dt;
+  storage = jl_max(storage, 0.0);
+  const double fill_fraction = storage / m->res_maximum_storage[i];
+  const double fac = wfo_scurve(fill_fraction, m->res_target_minimum_fraction[i], 1.0, 30.0);
+  const double demand_release = jl_min(fac * m->res_demand[i], storage / dt);
+  storage -= demand_release * dt;
+  const double release_wanted = jl_max(
+      0.0, (storage - m->res_maximum_storage[i] * m->res_target_full_fraction[i]) / dt);
+  const double overflow_q = jl_max(0.0, (storage - m->res_maximum_storage[i]) / dt);
+  const double release_realized =
+      jl_min(release_wanted, overflow_q + m->res_maximum_release[i] - demand_release);
+  storage -= release_realized * dt;
+  *outflow = release_realized + demand_release;
+  *storage_out = storage;
+}
+
+/* update_reservoir_modified_puls                                         reservoir.jl:427-456 */
+static void update_reservoir_modified_puls(wfo_model* m, int64_t i, double precipitation,
+                                           double evaporation, double inflow, double dt,
+                                           double* outflow_out, double* storage_out) {
+  const double res_factor = m->res_area[i] / (dt * sqrt(m->res_rating_curve_coefficient[i]));
+  const double si_factor = m->res_storage[i] / dt + precipitation - evaporation + inflow;
+  const double si_factor_adj = si_factor - m->res_area[i] * m->res_threshold[i] / dt;
+  double outflow;
+  if (si_factor_adj > 0.0) {
+    const double qs = -res_factor + sqrt((res_factor * res_factor + 4 * si_factor_adj));
+    outflow = qs > 0.0 ? 0.25 * (qs * qs) : 0.0;
+  } else {
+    outflow = 0.0;
+  }
+  outflow = jl_min(outflow, si_factor);
+  *outflow_out = outflow;
+  *storage_out = (si_factor - outflow) * dt;
+}
+
+/* update_reservoir_free_weir without a linked lower reservoir (lower_reservoir_ind = 0:
+ * diff_wl = 0)                                                           reservoir.jl:487-553 */
+static void update_reservoir_free_weir(wfo_model* m, int64_t i, double precipitation,
+                                       double evaporation, double inflow, double dt,
+                                       double* outflow_out, double* storage_out) {
+  const double storage_input =
+      jl_max(m->res_storage[i] / dt + precipitation - evaporation + inflow, 0.0);
+  double outflow;
+  if (m->res_waterlevel[i] > m->res_threshold[i]) {
+    const double dh = m->res_waterlevel[i] - m->res_threshold[i];
+    outflow = m->res_rating_curve_coefficient[i] * jl_pow(dh, m->res_rating_curve_exponent[i]);
+    const double maxflow = dh * m->res_area[i] / dt;
+    outflow = jl_min(outflow, maxflow);
+  } else {
+    outflow = 0.0;
+  }
+  *outflow_out = outflow;
+  *storage_out = (storage_input - outflow) * dt;
+}
+
+/* update_reservoir_outflow_obs                                           reservoir.jl:556-577 */
+static void update_reservoir_outflow_obs(wfo_model* m, int64_t i, double precipitation,
+                                         double evaporation, double inflow, double dt,
+                                         double* outflow_out, double* storage_out) {
+  const double storage_input =
+      jl_max(m->res_storage[i] / dt + precipitation - evaporation + inflow, 0.0);
+  double outflow = jl_min(m->res_outflow_obs[i], storage_input);
+  double storage = (storage_input - outflow) * dt;
+  if (!isnan(m->res_maximum_storage[i])) {
+    const double overflow = jl_max(0.0, (storage - m->res_maximum_storage[i]) / dt);
+    storage -= overflow * dt;
+    outflow += overflow;
+  }
+  *outflow_out = outflow;
+  *storage_out = storage;
+}
+
+/* update_reservoir_model!(reservoir_model, i, inflow, dt)                reservoir.jl:585-634
+ * (linear storage curve; ReservoirOutflowType rating_curve (H-Q tables) is not restated) */
+static void update_reservoir_model_i(wfo_model* m, int64_t i, double inflow, double dt) {
+  const double precipitation = m->res_precipitation[i] * m->res_area[i];
+  const double available_storage = m->res_storage[i] + (inflow + precipitation) * dt;
+  const double potential_evaporation = m->res_evaporation[i] * m->res_area[i];
+  const double evaporation = jl_min(available_storage / dt, potential_evaporation);
+  double outflow = 0.0, storage = m->res_storage[i];
+  const int type = (int)m->res_outflow_curve_type[i];
+  if (!isnan(m->res_outflow_obs[i]))
+    update_reservoir_outflow_obs(m, i, precipitation, evaporation, inflow, dt, &outflow, &storage);
+  else if (type == 2)
+    update_reservoir_free_weir(m, i, precipitation, evaporation, inflow, dt, &outflow, &storage);
+  else if (type == 3)
+    update_reservoir_modified_puls(m, i, precipitation, evaporation, inflow, dt, &outflow, &storage);
+  else if (type == 4)
+    update_reservoir_simple(m, i, precipitation, evaporation, inflow, dt, &outflow, &storage);
+  const double waterlevel = m->res_waterlevel[i] + (storage - m->res_storage[i]) / m->res_area[i];
+  m->res_storage[i] = storage;
+  m->res_waterlevel[i] = waterlevel;
+  m->res_outflow[i] = outflow;
+  m->res_inflow_cumulative[i] += inflow * dt;
+  m->res_outflow_cumulative[i] += outflow * dt;
+  m->res_actevap_cumulative[i] += evaporation / m->res_area[i] * dt;
+}
+
+/* update_reservoir_model!(reservoir, river variables, network, v, dt)  surface_kinwave.jl:441-489 */
+static void update_reservoir_at_node(wfo_model* m, int64_t v, double dt) {
+  const int64_t i = m->riv_reservoir[v];
+  if (i < 0) return;
+  const double inflow_ext = m->res_external_inflow[i];
+  double inflow;
+  if (inflow_ext < 0.0) {
+    const double abstraction = jl_min(-inflow_ext, (m->res_storage[i] / dt) * 0.98);
+    m->res_actual_external_abstraction_cumulative[i] += abstraction * dt;
+    inflow = -abstraction;
+  } else {
+    inflow = inflow_ext;
+  }
+  const double net_inflow =
+      m->riv_q[v] + m->res_inflow_overland[i] + m->res_inflow_subsurface[i] + inflow;
+  update_reservoir_model_i(m, i, net_inflow, dt);
+  const int64_t j = m->river.down[v];   /* a reservoir without a downstream node is an error in
+                                           the reference; the wrapper rejects it */
+  if (j >= 0) m->riv_qin[j] = m->res_outflow[i];
+}
+
+/* update_inflow!(reservoir, river_flow, external_models, network)      surface_kinwave.jl:772-805 */
+void wfo_update_inflow_reservoir(wfo_model* m) {
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {
+    const int64_t li = m->river_land_indices[m->reservoir_river_indices[i]];
+    m->res_inflow_overland[i] = m->olf_q_average[li];
+    m->res_inflow_subsurface[i] = m->ssf_q_average[li];
+  }
+}
+
+/* surface_kinwave.jl:492-566 (no floodplain) */
 static void kinwave_river_update(wfo_model* m, double dt) {
   const wfo_network* nw = &m->river;
   PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) m->riv_qin[i] = 0.0;
@@ -513,6 +733,7 @@ static void kinwave_river_update(wfo_model* m, double dt) {
         it_sum += it; calls += 1; if (it > maxit) maxit = it;
         if (m->newton_trace_river) m->newton_trace_river[v] += it;
         m->riv_q[v] = o[0];
+        if (m->cfg.nres > 0) update_reservoir_at_node(m, v, dt);
         m->riv_h[v] = o[1] / m->riv_flow_width[v];
         m->riv_storage[v] = m->riv_flow_length[v] * o[1];
         m->riv_q_cumulative[v] += m->riv_q[v] * dt;
@@ -523,6 +744,9 @@ static void kinwave_river_update(wfo_model* m, double dt) {
     if (maxit > m->newton_maxit_river) m->newton_maxit_river = maxit;
   }
 }
+
+/* test hook: one kinwave_river_update! with sub-step dt (routing_process.jl:290-383) */
+void wfo_kinwave_river_update(wfo_model* m, double dt) { kinwave_river_update(m, dt); }
 
 /* surface_kinwave.jl:710-734 */
 void wfo_update_lateral_inflow_river(wfo_model* m) {
@@ -542,6 +766,12 @@ void wfo_update_river_flow_model(wfo_model* m, double dt) {
     m->riv_actual_external_abstraction_cumulative[i] = 0.0;
     m->riv_qin_cumulative[i] = 0.0;
   }
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {  /* set_reservoir_vars!  surface_kinwave.jl:227-237 */
+    m->res_inflow_cumulative[i] = 0.0;
+    m->res_actual_external_abstraction_cumulative[i] = 0.0;
+    m->res_outflow_cumulative[i] = 0.0;
+    m->res_actevap_cumulative[i] = 0.0;
+  }
   double t = 0.0;
   m->substeps_river = 0;
   while (t < dt) {
@@ -560,6 +790,12 @@ void wfo_update_river_flow_model(wfo_model* m, double dt) {
         m->riv_actual_external_abstraction_cumulative[i] / dt;
     m->riv_qin_average[i] = m->riv_qin_cumulative[i] / dt;
   }
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {  /* average_reservoir_vars!  surface_kinwave.jl:244-258 */
+    m->res_outflow_average[i] = m->res_outflow_cumulative[i] / dt;
+    m->res_inflow_average[i] = m->res_inflow_cumulative[i] / dt;
+    m->res_actual_external_abstraction_average[i] =
+        m->res_actual_external_abstraction_cumulative[i] / dt;
+  }
 }
 
 /* surface_routing.jl:7-46 */
@@ -567,6 +803,7 @@ void wfo_surface_routing(wfo_model* m, double dt) {
   wfo_update_lateral_inflow_overland(m);
   wfo_update_overland_flow_model(m, dt);
   wfo_update_lateral_inflow_river(m);
+  wfo_update_inflow_reservoir(m);
   wfo_update_river_flow_model(m, dt);
 }
 

@@ -27,7 +27,7 @@ const char* wfo_field_name(int id) { return k_names[id]; }
 int wfo_field_kind(int id) { return k_kinds[id]; }
 wfo_model* wfo_new(void) { return (wfo_model*)calloc(1, sizeof(wfo_model)); }
 void wfo_free(wfo_model* m) {
-  if (m) { free(m->scratch); free(m); }
+  if (m) { free(m->scratch); free(m->riv_reservoir); free(m); }
 }
 wfo_config* wfo_cfg(wfo_model* m) { return &m->cfg; }
 int wfo_set_ptr(wfo_model* m, const char* name, double* p) {
@@ -41,6 +41,14 @@ int wfo_set_iptr(wfo_model* m, const char* name, int64_t* p) {
   if (!strcmp(name, "n_unsatlayers")) { m->n_unsatlayers = p; return 0; }
   if (!strcmp(name, "nlayers_kv")) { m->nlayers_kv = p; return 0; }
   if (!strcmp(name, "newton_trace_land")) { m->newton_trace_land = p; return 0; }
+  if (!strcmp(name, "reservoir_river_indices")) {
+    m->reservoir_river_indices = p;
+    free(m->riv_reservoir);
+    m->riv_reservoir = (int64_t*)malloc(sizeof(int64_t) * (size_t)(m->cfg.nriv > 0 ? m->cfg.nriv : 1));
+    for (int64_t r = 0; r < m->cfg.nriv; ++r) m->riv_reservoir[r] = -1;
+    for (int64_t i = 0; i < m->cfg.nres; ++i) m->riv_reservoir[p[i]] = i;
+    return 0;
+  }
   if (!strcmp(name, "newton_trace_river")) { m->newton_trace_river = p; return 0; }
   if (!strcmp(name, "river_land_indices")) { m->river_land_indices = p; return 0; }
   return -1;
@@ -409,6 +417,48 @@ static void update_snow_model(wfo_model* m, double dt) {
   }
 }
 
+/* accucapacityflux!                                              routing/utils.jl:82-109 */
+void wfo_accucapacityflux(double* flux, double* material, const int64_t* order,
+                          const int64_t* down, int64_t n, const double* capacity, double dt) {
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t v = order[k];
+    const double flux_val = jl_min(material[v] / dt, capacity[v]);
+    const double material_update = flux_val * dt;
+    material[v] -= material_update;
+    flux[v] = flux_val;
+    if (down[v] >= 0) material[down[v]] += material_update;
+  }
+}
+
+/* lateral_snow_transport!(snow, domain, dt)        routing/surface/surface_process.jl:9-19
+ * (serial over the whole land network, like the reference) */
+static void lateral_snow_transport(wfo_model* m, double dt) {
+  if (!m->cfg.snow || !m->cfg.snow_transport) return;
+  const int64_t n = m->cfg.n;
+  const wfo_network* nw = &m->land;
+  double* cap1 = (double*)malloc(sizeof(double) * (size_t)n * 3);
+  double* cap2 = cap1 + n;
+  double* flux2 = cap2 + n;
+  const double snow_storage_max = 10.0, tan80 = 5.67;
+  for (int64_t i = 0; i < n; ++i) {
+    const double snowflux_frac = jl_min(0.5, m->slope[i] / tan80) *
+                                 jl_min(1.0, m->snow_storage[i] / snow_storage_max);
+    cap1[i] = snowflux_frac * m->snow_storage[i] / dt;   /* maxflux */
+    cap2[i] = m->snow_water[i] * snowflux_frac / dt;
+  }
+  wfo_accucapacityflux(m->snow_out, m->snow_storage, nw->order, nw->down, n, cap1, dt);
+  wfo_accucapacityflux(flux2, m->snow_water, nw->order, nw->down, n, cap2, dt);
+  for (int64_t i = 0; i < n; ++i) m->snow_out[i] += flux2[i];
+  /* flux_in!(snow_in, snow_out, network)                         routing/utils.jl:161-167 */
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t v = nw->order[k];
+    double ssum = 0.0;
+    for (int64_t u = nw->up_ptr[k]; u < nw->up_ptr[k + 1]; ++u) ssum += m->snow_out[nw->up_idx[u]];
+    m->snow_in[v] = ssum;
+  }
+  free(cap1);
+}
+
 /* glacier/glacier.jl:122-154 ; only active when snow && glacier (sbm.jl:41-54) */
 static void update_glacier_model(wfo_model* m, double dt) {
   if (!(m->cfg.snow && m->cfg.glacier)) return;
@@ -709,6 +759,7 @@ static void update_soil_water_flow(wfo_model* m, double dt) {
 void wfo_update_land_hydrology_model(wfo_model* m, double dt) {
   update_interception_model(m, dt);
   update_snow_model(m, dt);
+  lateral_snow_transport(m, dt);   /* snow_gravitational_transport__flag, sbm.jl:98-100 */
   update_glacier_model(m, dt);
   update_open_water_runoff(m, dt);
   update_bc_soil_model(m);

@@ -17,6 +17,16 @@ for v in "$@"; do
   case $v in
     mb3) build mb3 -DWFB_V_MINBLOCKS=3 ;;
     mb5) build mb5 -DWFB_V_MINBLOCKS=5 ;;
+    pf0) build pf0 -DWFB_V_PREFETCH=0 ;;
+    pf1) build pf1 -DWFB_V_PREFETCH=1 ;;
+    pf1mb5) build pf1mb5 -DWFB_V_PREFETCH=1 -DWFB_V_MINBLOCKS=5 ;;
+    pf2mb5) build pf2mb5 -DWFB_V_PREFETCH=2 -DWFB_V_MINBLOCKS=5 ;;
+    pf2mb3) build pf2mb3 -DWFB_V_PREFETCH=2 -DWFB_V_MINBLOCKS=3 ;;
+    mb6) build mb6 -DWFB_V_MINBLOCKS=6 ;;
+    mb8) build mb8 -DWFB_V_MINBLOCKS=8 ;;
+    mb5cs) build mb5cs -DWFB_V_MINBLOCKS=5 -DWFB_V_LDCS=1 ;;
+    mb6cs) build mb6cs -DWFB_V_MINBLOCKS=6 -DWFB_V_LDCS=1 ;;
+    mb4cs) build mb4cs -DWFB_V_MINBLOCKS=4 -DWFB_V_LDCS=1 ;;
     *) echo "unknown variant $v"; exit 1 ;;
   esac
 done

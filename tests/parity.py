@@ -38,12 +38,20 @@ ATOL_FLOOR = 1e-18
 
 def oracle_networks(cfg, dom):
     """The oracle builds its OWN artefacts (oracle/network.py), independent of the product."""
-    land = onw.build_domain_network(dom["ldd"], dom["indices"], dom["d1"],
-                                    cfg["land_streamorder_min"], cfg["nthreads"])
     rl = dom["river_land_indices"]
+    pits_land = pits_river = None
+    rr = dom.get("reservoir_river_indices")
+    if rr is not None and len(rr):      # reservoir outlets (domain.jl:96-109)
+        pits_river = np.zeros(len(rl), dtype=bool)
+        pits_river[rr - 1] = True
+        pits_land = np.zeros(len(dom["ldd"]), dtype=bool)
+        pits_land[rl[rr - 1] - 1] = True
+    land = onw.build_domain_network(dom["ldd"], dom["indices"], dom["d1"],
+                                    cfg["land_streamorder_min"], cfg["nthreads"],
+                                    pits_mask=pits_land)
     river = onw.build_domain_network(dom["ldd"][rl - 1], dom["indices"][rl - 1], dom["d1"],
                                      cfg["river_streamorder_min"], cfg["nthreads"],
-                                     streamorder=land["streamorder"][rl - 1])
+                                     streamorder=land["streamorder"][rl - 1], pits_mask=pits_river)
     return land, river
 
 
@@ -51,6 +59,8 @@ def make_oracle(cfg, dom, fields, nets=None, variant=""):
     land, river = nets if nets is not None else oracle_networks(cfg, dom)
     f = dict(fields)
     f["river_land_indices"] = dom["river_land_indices"] - 1
+    if cfg.get("nres", 0):
+        f["reservoir_river_indices"] = dom["reservoir_river_indices"] - 1
     return orc.OracleModel(cfg, f, land, river, variant=variant)
 
 

@@ -176,6 +176,54 @@ def test_glacier_exponential_constant_infiltration_reduction(pkg):
     _close(gpu)
 
 
+@pytest.mark.parametrize("mode", ["update_model", "fine_grained", "adaptive", "separate_kernels"])
+def test_reservoirs_on_the_river(pkg, mode):
+    """reservoir__flag = true (test/sbm_config.toml:126): reservoir outlets are dropped from the
+    upstream lists of the land and river kinematic waves (domain.jl:96-122), the reservoir takes
+    the river, overland and subsurface flow of its outlet cell and hands its outflow to the
+    downstream river node (surface_kinwave.jl:441-489). Simple, modified-Puls, free-weir and
+    observed-outflow reservoirs, with external abstraction / supply (reservoir.jl:389-634)."""
+    kw = dict(reservoirs=6)
+    opts = {}
+    if mode == "adaptive":
+        kw["adaptive"] = True
+    if mode == "separate_kernels":
+        opts = {"fuse_surface": 0}
+    gpu, ora, cfg = parity.run_pair(pkg, 90, 120, steps=4, seed=31, fine_grained=mode == "fine_grained",
+                                    options=opts, **kw)
+    assert cfg["nres"] == 6
+    rep = parity.compare_models(gpu, ora)
+    assert rep["res_outflow"]["rel"] <= parity.RTOL and np.all(ora.f["res_outflow_average"] > 0)
+    print(rep.summary(), "outflow", ora.f["res_outflow_average"])
+    _close(gpu)
+
+
+@pytest.mark.parametrize("kv_profile", [2, 3])
+def test_layered_conductivity_profiles(pkg, kv_profile):
+    """KvLayered / KvLayeredExponential (soil.jl:213-244, utils.jl:763-789) in the unsaturated
+    zone, capillary rise and leakage; kh_layered_profile! (utils.jl:792-895) and
+    kinematic_wave_ssf(::KhLayered) (subsurface_process.jl:47-51,183-228) in the subsurface flow."""
+    gpu, ora, cfg = parity.run_pair(pkg, 60, 84, steps=4, seed=37, kv_profile=kv_profile)
+    rep = parity.compare_models(gpu, ora)
+    assert "ssf_kh" in rep and rep["ssf_kh"]["rel"] <= parity.RTOL
+    print(rep.summary())
+    _close(gpu)
+
+
+@pytest.mark.parametrize("reservoirs", [0, 5])
+def test_lateral_snow_transport(pkg, reservoirs):
+    """snow_gravitational_transport__flag = true (test/sbm_config.toml:124): accucapacityflux of
+    snow storage and snow water over the land network between the snow and the glacier model
+    (sbm.jl:98-100, surface_process.jl:9-19, routing/utils.jl:82-168), also together with
+    reservoirs (whose outlets stay in the transport graph but leave the upstream lists)."""
+    gpu, ora, cfg = parity.run_pair(pkg, 70, 96, steps=4, seed=41, snow_transport=True,
+                                    glacier=True, reservoirs=reservoirs)
+    assert cfg["snow_transport"] == 1 and float(np.max(ora.f["snow_out"])) > 0.0
+    rep = parity.compare_models(gpu, ora)
+    print(rep.summary(), "max snow_out", float(np.max(ora.f["snow_out"])))
+    _close(gpu)
+
+
 def test_five_soil_layers(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 32, 48, steps=2, seed=2,
                                     soil_layer_thickness_mm=(50, 50, 300, 800))
@@ -241,6 +289,40 @@ def test_state_roundtrip_and_set_value(pkg):
     gpu.set("number_of_layers", nl)
     assert np.array_equal(gpu.get("number_of_layers"), nl)
     _close(gpu)
+
+
+def test_forcing_ring_cyclic_lai_and_output_gather(pkg):
+    """The steps either side of the path: forcing slabs staged ahead in an HBM ring,
+    cyclic LAI slabs staged once and switched on the device, several output vectors fetched with
+    one copy -- same results as set_forcing / set / get."""
+    cfg, dom, fields = pkg.synthetic.make_basin(40, 56, seed=9)
+    dt, n = cfg["dt"], cfg["n"]
+    a = pkg.SbmModel(cfg, dom, fields)
+    b = pkg.SbmModel(cfg, dom, fields)
+    rng = np.random.default_rng(1)
+    lai = np.stack([fields["leaf_area_index"] * (0.6 + 0.1 * m) for m in range(12)])
+    b.set_cyclic_lai(lai)
+    b.forcing_ring_create(3)
+    forc = [tuple(np.ascontiguousarray(x) for x in pkg.synthetic.make_forcing(9, s, dom["gid"], dt))
+            for s in range(5)]
+    for s in range(min(3, len(forc))):
+        b.forcing_ring_put(s % 3, *forc[s])
+    names = ["riv_q_average", "riv_h", "snow_storage", "saturated_water_depth",
+             "unsaturated_layer_depth", "total_storage", "olf_q_average", "ssf_water_table_depth"]
+    for s in range(5):
+        month = (s * 5) % 12
+        a.set("leaf_area_index", lai[month])
+        a.set_forcing(*forc[s])
+        a.update_model(dt)
+        b.use_cyclic_lai(month)
+        b.forcing_ring_use(s % 3)
+        b.update_model(dt)
+        if s + 3 < len(forc):
+            b.forcing_ring_put(s % 3, *forc[s + 3])   # refill the slot just consumed
+        got = b.get_fields(names)
+        for nm in names:
+            assert np.array_equal(got[nm], a.get(nm), equal_nan=True), (s, nm)
+    _close(a, b)
 
 
 def test_water_balance_closure(pkg):

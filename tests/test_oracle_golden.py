@@ -407,30 +407,77 @@ def test_kinematic_wave_ssf_routing_process_100_253():
 
 
 def test_kinwave_river_update_routing_process_290_383():
-    """2-node river graph. The reservoir on node 1 is out of scope; its pinned outflow
-    (3.0009999145314317) is injected as qin[2] exactly as update_reservoir_model! does
-    (surface_kinwave.jl:441-489)."""
+    """2-node river graph (1 -> 2) with a SIMPLE RESERVOIR on node 1 that has a negative external
+    inflow (abstraction): stable time step (type-7 quantile), one kinwave_river_update!, river
+    q / h / storage / q_cumulative and the reservoir's water level, storage, outflow and actual
+    evaporation. As in the reference's unit test node 1 stays in node 2's upstream list."""
     L = orc.lib()
     q = np.array([0.5499295110293246, 3.0005238507869465])
     alpha = np.array([2.544585458995107, 2.5507721996678145])
     length = np.array([1059.8125, 951.96875])
-    width = 94.73094177246094
+    width = np.array([94.73094177246094, 94.73094177246094])
     work = np.zeros(2)
     dt = L.wfo_stable_timestep_surface(q.ctypes.data, alpha.ctypes.data, length.ctypes.data, 2,
                                        0.05, work.ctypes.data)
     assert dt == approx(994.6119029285007)
-    out = (C.c_double * 2)()
-    L.wfo_kinematic_wave(0.0, q[0], 0.0, alpha[0], dt, length[0], out, None)
-    q1, a1 = out[0], out[1]
-    assert q1 == approx(0.37903337592185243)
-    assert a1 / width == approx(0.01500830539624011)
-    assert length[0] * a1 == approx(1506.7893805755937)
-    assert q1 * dt == approx(376.9911072990474)
-    L.wfo_kinematic_wave(3.0009999145314317 + q1, q[1], 0.0, alpha[1], dt, length[1], out, None)
-    assert out[0] == approx(3.1969698861305855)
-    assert out[1] / width == approx(0.05407828963124342)
-    assert length[1] * out[1] == approx(4876.828625285123)
-    assert out[0] * dt == approx(3179.744302049454)
+
+    class G:  # outneighbors: 1 -> 2
+        down = np.array([2, 0])
+    river = dict(graph=G, order=np.array([1, 2]), up_ptr=np.array([0, 0, 1]), up_idx=np.array([1]),
+                 order_of_subdomains=[np.array([1])], order_subdomain=[np.array([1, 2])],
+                 subdomain_indices=[np.array([1, 2])])
+
+    class G1:
+        down = np.array([0, 0])
+    land = dict(graph=G1, order=np.array([1, 2]), up_ptr=np.zeros(3, np.int64), up_idx=np.zeros(0, np.int64),
+                order_of_subdomains=[np.array([1, 2])], order_subdomain=[np.array([1]), np.array([2])],
+                subdomain_indices=[np.array([1]), np.array([2])])
+    f = dict(riv_q=q, riv_alpha=alpha, riv_flow_length=length, riv_flow_width=width,
+             riv_qlat=np.zeros(2), riv_qin=np.zeros(2), riv_storage=np.zeros(2), riv_h=np.zeros(2),
+             riv_external_inflow=np.zeros(2), riv_abstraction=np.zeros(2),
+             river_land_indices=np.array([0, 1]), reservoir_river_indices=np.array([0]),
+             res_external_inflow=[-0.1], res_precipitation=[2.0833332436504178e-10],
+             res_evaporation=[5.324074170655674e-9], res_inflow_overland=[0.0],
+             res_inflow_subsurface=[0.02735223635554672], res_area=[1.498462875e6],
+             res_outflow_curve_type=[4.0], res_maximum_release=[24.007999420166016],
+             res_demand=[3.000999927520752], res_target_minimum_fraction=[0.07482631504535675],
+             res_target_full_fraction=[0.7536525130271912], res_maximum_storage=[6.2e7],
+             res_waterlevel=[29.656373296565086], res_storage=[4.443897439204416e7],
+             res_outflow_obs=[np.nan])
+    f = {k: np.asarray(v, dtype=np.int64 if k.endswith("indices") else np.float64)
+         for k, v in f.items()}
+    m = orc.OracleModel(dict(n=2, nriv=2, nres=1, N=1), f, land, river)
+    L.wfo_kinwave_river_update(m.h, dt)
+    assert m.f["riv_q"] == approx(np.array([0.37903337592185243, 3.1969698861305855]))
+    assert m.f["riv_h"] == approx(np.array([0.01500830539624011, 0.05407828963124342]))
+    assert m.f["riv_storage"] == approx(np.array([1506.7893805755937, 4876.828625285123]))
+    assert m.f["riv_q_cumulative"] == approx(np.array([376.9911072990474, 3179.744302049454]))
+    assert m.f["res_waterlevel"][0] == approx(29.654579645252387)
+    assert m.f["res_storage"][0] == approx(4.443628667214138e7)
+    assert m.f["res_outflow"][0] == approx(3.0009999145314317)
+    assert m.f["res_actevap_cumulative"][0] == approx(5.295387542208319e-6)
+
+
+def test_accucapacityflux_routing_process_255_288():
+    """PCRaster accucapacity examples on a 6-node graph (lateral snow transport's engine)."""
+    L = orc.lib()
+    down = np.array([4, 5, 5, 6, 6, 0], dtype=np.int64) - 1
+    order = np.arange(6, dtype=np.int64)
+    dt = 86400.0
+
+    def run(material, capacity):
+        mat = np.array(material, dtype=np.float64)
+        cap = np.array(capacity, dtype=np.float64)
+        flux = np.zeros(6)
+        L.wfo_accucapacityflux(flux.ctypes.data, mat.ctypes.data, order.ctypes.data,
+                               down.ctypes.data, 6, cap.ctypes.data, dt)
+        return flux, mat
+    flux, mat = run(dt * np.array([0.5, 2.0, 2.0, 0.5, 2.0, 0.5]), np.full(6, 1.5))
+    assert np.array_equal(mat, dt * np.array([0.0, 0.5, 0.5, 0.0, 3.5, 1.5]))
+    assert np.array_equal(flux, np.array([0.5, 1.5, 1.5, 1, 1.5, 1.5]))
+    flux, mat = run(dt * np.full(6, 10.0), [2, 30, 30, 2, 30, 2])
+    assert np.array_equal(mat, dt * np.array([8.0, 0.0, 0.0, 10.0, 0.0, 40.0]))
+    assert np.array_equal(flux, np.array([2, 10, 10, 2, 30, 2], dtype=np.float64))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -23,12 +23,13 @@ class Config(C.Structure):
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
                 ("ssf_alpha_coefficient", C.c_double), ("kin_wave_min_flow_qroot", C.c_double),
                 ("wave_piece_depth_land", C.c_int32), ("vertical_slices", C.c_int32),
-                ("unsat_inline_iters", C.c_int32), ("reserved_", C.c_int32)]
+                ("unsat_inline_iters", C.c_int32), ("snow_gravitational_transport", C.c_int32)]
 
 
 class Domain(C.Structure):
     _fields_ = [("d1", C.c_int64), ("d2", C.c_int64), ("indices", C.c_void_p),
-                ("ldd", C.c_void_p), ("river_land_indices", C.c_void_p)]
+                ("ldd", C.c_void_p), ("river_land_indices", C.c_void_p), ("nres", C.c_int64),
+                ("reservoir_river_indices", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -93,13 +94,19 @@ def lib():
               "update_river_flow_model", "update_model"):
         getattr(L, "wflowb200_" + f).argtypes = [vp, dbl]
     for f in ("exchange_recharge", "update_lateral_inflow_overland", "update_lateral_inflow_river",
-              "update_total_water_storage", "synchronize"):
+              "update_inflow_reservoir", "update_total_water_storage", "synchronize"):
         getattr(L, "wflowb200_" + f).argtypes = [vp]
     L.wflowb200_get_artifact.argtypes = [vp, i32, i32, vp, i64, C.POINTER(i64)]
     L.wflowb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.wflowb200_set_timing.argtypes = [vp, i32]
     L.wflowb200_timer_start.argtypes = [vp]
     L.wflowb200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    L.wflowb200_forcing_ring_create.argtypes = [vp, i32]
+    L.wflowb200_forcing_ring_put.argtypes = [vp, i32, vp, vp, vp]
+    L.wflowb200_forcing_ring_use.argtypes = [vp, i32]
+    L.wflowb200_set_cyclic_lai.argtypes = [vp, vp, i32]
+    L.wflowb200_use_cyclic_lai.argtypes = [vp, i32]
+    L.wflowb200_get_fields.argtypes = [vp, vp, i32, vp]
     L.wflowb200_set_option.argtypes = [vp, C.c_char_p, i32]
     L.wflowb200_newton_trace.argtypes = [vp, i32]
     L.wflowb200_get_newton_trace.argtypes = [vp, i32, vp]

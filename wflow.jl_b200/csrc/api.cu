@@ -134,8 +134,13 @@ struct Tuning {
 struct WflowB200 {
   WflowB200Config cfg{};
   Tuning tune{};
-  int n = 0, nriv = 0, N = 0, ns = 0, nrs = 0;
+  int n = 0, nriv = 0, N = 0, ns = 0, nrs = 0, nres = 0, nress = 0;
+  int32_t* res_ident = nullptr;      // identity slot map of the reservoir fields
   DomainDev land, river;
+  DomainDev land_full;               // device arrays only (nw unused): land chunks without the
+  DomainDev* snow_net = nullptr;     // reservoir cut, for lateral snow transport
+  int grid_snow = 0;
+  size_t smem_snow = 0;
   DevFields f{};
   KCfg kc{};
   double* pool = nullptr;  // one HBM allocation holding every Float64 field
@@ -149,6 +154,17 @@ struct WflowB200 {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
+  // staging ring of forcing slabs in HBM (wflowb200_forcing_ring_*): the host uploads the slabs of
+  // the coming steps on the copy stream while the current step computes
+  double* d_ring = nullptr;
+  int ring_depth = 0, ring_use = -1;
+  std::vector<cudaEvent_t> ring_ready;     // per slot: its H2D copy has landed
+  std::vector<cudaEvent_t> ring_consumed;  // per slot: the gather that read it has run
+  // cyclic parameters staged once (io.jl:187-227): leaf_area_index [slabs x n], node order
+  double* d_lai_table = nullptr;
+  int lai_slabs = 0;
+  double* h_out_pinned = nullptr;          // pinned staging of wflowb200_get_fields
+  size_t out_pinned_doubles = 0;
   unsigned* d_queue = nullptr;
   std::vector<UnsatWork> unsat;      // scratch of the unsaturated-zone engine, per slice
   double* d_unsat_pool = nullptr;
@@ -234,6 +250,9 @@ int32_t check_device_error(WflowB200* h) {
 }
 
 int layers_of(const WflowB200* h, int kind) { return kind == 1 ? h->N : kind == 2 ? h->N + 1 : 1; }
+// slots / elements / slot map of a field kind (0-2 land, 3 river, 4 reservoir)
+int slots_of(const WflowB200* h, int kind) { return kind == 3 ? h->nrs : kind == 4 ? h->nress : h->ns; }
+int count_of(const WflowB200* h, int kind) { return kind == 3 ? h->nriv : kind == 4 ? h->nres : h->n; }
 
 template <class T>
 cudaError_t upload_i32(const std::vector<T>& src, int32_t** dst, int64_t offset) {
@@ -255,8 +274,13 @@ cudaError_t upload_raw(const std::vector<T>& src, const T** dst, std::vector<voi
 }
 
 // Device copies of the wavefront artefacts of one domain.
-int32_t upload_domain(WflowB200* h, DomainDev& d) {
-  const Network& nw = d.nw;
+// outlet_res[v] (by node id, may be empty): node v is a reservoir outlet (domain.jl:96-109).
+// cut_outlets: edges leaving an outlet are dropped (the land kinematic waves: filter_upstream_nodes,
+// utils.jl:61-71); otherwise (river) they stay -- they carry the reservoir's outflow -- but
+// move to the END of the receiving node's fold: the reference forms qin[v] = outflow first and
+// then adds sum_at(q, upstream_nodes) (surface_kinwave.jl:481-482,517), and a + b == b + a.
+int32_t upload_domain(WflowB200* h, DomainDev& d, const Network& nw,
+                      const std::vector<uint8_t>& outlet_res, bool cut_outlets) {
   const int64_t n = nw.n;
   CUDA_TRY(h, upload_i32(nw.perm, &d.node_of_slot, -1));
   std::vector<int4> meta(nw.n_chunks);
@@ -278,8 +302,17 @@ int32_t upload_domain(WflowB200* h, DomainDev& d) {
       const int64_t deg = nw.in_ptr[v + 1] - nw.in_ptr[v];
       if (deg > 8) return fail(h, WFLOWB200_ERR_GRAPH, "node with more than 8 upstream nodes");
       unsigned long long code = ~0ull;
-      for (int64_t e = 0; e < deg; ++e) {
-        const int64_t u = nw.in_idx[nw.in_ptr[v] + e] - 1;
+      int64_t srcs[8];
+      int64_t ns_ = 0;
+      for (int pass = 0; pass < 2; ++pass)   // ordinary sources, then reservoir outlets
+        for (int64_t e = 0; e < deg; ++e) {
+          const int64_t u = nw.in_idx[nw.in_ptr[v] + e] - 1;
+          const bool is_res = !outlet_res.empty() && outlet_res[u];
+          if (is_res != (pass == 1) || (is_res && cut_outlets)) continue;
+          srcs[ns_++] = u;
+        }
+      for (int64_t e = 0; e < ns_; ++e) {
+        const int64_t u = srcs[e];
         const int64_t cu = nw.chunk_of_node[u];
         unsigned long long b;
         if (cu != c) {
@@ -349,6 +382,15 @@ int fixed_substeps(double dt, double dt_fixed, std::vector<double>& out) {
 }
 
 int32_t wait_forcing(WflowB200* h) {
+  if (h->ring_use >= 0) {  // a slab of the staging ring
+    const int k = h->ring_use;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ring_ready[k], 0));
+    h->launches += launch_gather_forcing(h->f, h->d_ring + (size_t)k * 3 * h->n,
+                                         h->land.node_of_slot, h->n, h->stream);
+    CUDA_TRY(h, cudaEventRecord(h->ring_consumed[k], h->stream));
+    h->ring_use = -1;
+    h->forcing_pending = false;
+  }
   if (h->forcing_pending) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->forcing_ready, 0));
     h->launches += launch_gather_forcing(h->f, h->d_forcing, h->land.node_of_slot, h->n, h->stream);
@@ -495,11 +537,41 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
 // streams and the ordering events (~50 kernel launches and memsets per step) are captured once
 // per time step length; issuing them one by one costs more host time than the GPU needs.
 static int32_t launch_vertical(WflowB200* h, double dt) {
-  auto issue = [&]() {
+  const bool transport = h->cfg.snow_gravitational_transport != 0;
+  auto issue_phase = [&](int phase) {
     return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
                                  h->slice_tile_begin.data(), h->d_tile_prio, h->d_tile_order,
-                                 h->engine_grid, h->stream, h->side_stream, h->v_ev);
+                                 h->engine_grid, phase, h->stream, h->side_stream, h->v_ev);
   };
+  if (transport) {
+    // interception + snow, lateral_snow_transport! over the land network (sbm.jl:98-100), then
+    // the rest of the update (below: as a graph like the one-phase update)
+    int32_t rc = check_launch(h, issue_phase(1), "update_land_hydrology_model (snow)");
+    if (rc) return rc;
+    int64_t one = 0;
+    DomainDev& sd = *h->snow_net;
+    const size_t need = (size_t)std::max<int64_t>(h->land.nw.n_outlets, 1) * 3;
+    if (need > h->land.q_out_words) {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      cudaFree(h->land.q_out);
+      h->land.q_out = nullptr; h->land.q_out_words = 0;
+      CUDA_TRY(h, cudaMalloc((void**)&h->land.q_out, need * sizeof(unsigned long long)));
+      h->land.q_out_words = need;
+    }
+    WaveLaunch w{};
+    w.queue = h->d_queue + 2 * 32;
+    w.q_out = h->land.q_out;
+    w.stats = h->d_stats;
+    w.S = 1;
+    w.dt_fixed = w.dt_last = w.dt = dt;
+    w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_snow, h->land.nw.n_chunks));
+    w.smem = h->smem_snow;
+    w.err = h->d_err;
+    (void)one;
+    rc = check_launch(h, launch_snow_transport(h->f, h->kc, sd.dev, w, h->stream), "lateral_snow_transport");
+    if (rc) return rc;
+  }
+  auto issue = [&]() { return issue_phase(transport ? 2 : 0); };
   if (!h->tune.use_graph) return check_launch(h, issue(), "update_land_hydrology_model");
   if (!h->v_graph || h->v_graph_dt != dt) {
     if (h->v_graph) { cudaGraphExecDestroy(h->v_graph); h->v_graph = nullptr; }
@@ -552,6 +624,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   if (cfg->n > 0x7fffff00LL) return fail(nullptr, WFLOWB200_ERR_ARG, "n exceeds int32 slots");
   if (cfg->kv_profile < 0 || cfg->kv_profile > 3)
     return fail(nullptr, WFLOWB200_ERR_ARG, "kv_profile must be 0 .. 3");
+  if (cfg->snow_gravitational_transport && !cfg->snow)
+    return fail(nullptr, WFLOWB200_ERR_ARG, "snow_gravitational_transport needs the snow model");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, WFLOWB200_ERR_CUDA, "no CUDA device: libwflow_b200 has no CPU fallback");
@@ -564,6 +638,10 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->n = (int)cfg->n; h->nriv = (int)cfg->nriv; h->N = cfg->n_layers;
   h->ns = (h->n + 31) / 32 * 32;
   h->nrs = (h->nriv + 31) / 32 * 32;
+  h->nres = (int)(dom->reservoir_river_indices ? dom->nres : 0);
+  h->nress = (h->nres + 31) / 32 * 32;
+  if (h->nres < 0 || h->nres > h->nriv)
+    return (delete h, fail(nullptr, WFLOWB200_ERR_ARG, "0 <= nres <= nriv required"));
   if (h->cfg.kin_wave_min_flow_qroot == 0.0) h->cfg.kin_wave_min_flow_qroot = std::pow(1e-30, 0.2);
   auto bail = [&](int32_t code) { g_create_error = h->err; wflowb200_destroy(h); return code; };
 
@@ -579,7 +657,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   for (int i = 0; i < WFLOWB200_NUM_FIELDS; ++i) {
     off[i] = total;
     const int k = kFieldKinds[i];
-    total += k == 3 ? (size_t)h->nrs : (size_t)h->ns * layers_of(h, k);
+    total += (size_t)slots_of(h, k) * layers_of(h, k);
   }
   h->pool_doubles = total;
 #define TRY_CREATE(expr)                                                       \
@@ -608,7 +686,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   // MISSING_VALUE everywhere, then the reference's non-NaN defaults
   launch_fill(h->pool, (long long)total, NAN, h->stream);
   auto fill = [&](double* p, int kind, double v) {
-    launch_fill(p, kind == 3 ? h->nrs : (long long)h->ns * layers_of(h, kind), v, h->stream);
+    launch_fill(p, (long long)slots_of(h, kind) * layers_of(h, kind), v, h->stream);
   };
   fill(h->f.canopy_storage, 0, 0.0);            // canopy.jl:11
   fill(h->f.waterdepth_river, 0, 0.0);          // runoff.jl:26
@@ -635,6 +713,12 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
                            h->f.riv_qin_average, h->f.riv_q_cumulative, h->f.riv_q_average,
                            h->f.riv_storage, h->f.riv_h};
     for (double* p : zeros_riv) fill(p, 3, 0.0);
+    double* zeros_res[] = {h->f.res_inflow_cumulative, h->f.res_inflow_average,   // reservoir.jl:200-272
+                           h->f.res_external_inflow, h->f.res_actual_external_abstraction_cumulative,
+                           h->f.res_actual_external_abstraction_average, h->f.res_outflow_cumulative,
+                           h->f.res_outflow_average, h->f.res_actevap_cumulative};
+    if (h->nres > 0)
+      for (double* p : zeros_res) fill(p, 4, 0.0);
   }
   TRY_CREATE(cudaMalloc((void**)&h->f.number_of_layers, (size_t)h->ns * sizeof(int32_t)));
   TRY_CREATE(cudaMalloc((void**)&h->f.n_unsatlayers, (size_t)h->ns * sizeof(int32_t)));
@@ -643,8 +727,42 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMemset(h->f.number_of_layers, 0, (size_t)h->ns * sizeof(int32_t)));
   TRY_CREATE(cudaMemset(h->f.n_unsatlayers, 0, (size_t)h->ns * sizeof(int32_t)));
 
-  if (upload_domain(h, h->land) || upload_domain(h, h->river))
-    return bail(WFLOWB200_ERR_CUDA);
+  {
+    std::vector<uint8_t> res_land, res_riv;
+    if (h->nres > 0) {
+      res_land.assign(h->n, 0);
+      res_riv.assign(h->nriv, 0);
+      for (int i = 0; i < h->nres; ++i) {
+        const int64_t r = dom->reservoir_river_indices[i];
+        if (r < 1 || r > h->nriv || res_riv[r - 1]) {
+          h->err = "reservoir_river_indices must be distinct 1-based river node ids";
+          return bail(WFLOWB200_ERR_ARG);
+        }
+        if (h->river.nw.down[r - 1] == 0) {   // surface_kinwave.jl:483-488
+          h->err = "a reservoir without a downstream river node is not supported";
+          return bail(WFLOWB200_ERR_GRAPH);
+        }
+        res_riv[r - 1] = 1;
+        res_land[dom->river_land_indices[r - 1] - 1] = 1;
+      }
+    }
+    if (upload_domain(h, h->land, h->land.nw, res_land, true) ||
+        upload_domain(h, h->river, h->river.nw, res_riv, false))
+      return bail(WFLOWB200_ERR_CUDA);
+    h->snow_net = &h->land;
+    if (cfg->snow_gravitational_transport && h->nres > 0) {
+      // accucapacityflux! walks the FULL land graph (routing/utils.jl:82-109): a second set of
+      // chunk edges without the reservoir cut
+      if (upload_domain(h, h->land_full, h->land.nw, std::vector<uint8_t>(), false))
+        return bail(WFLOWB200_ERR_CUDA);
+      h->snow_net = &h->land_full;
+      std::vector<uint8_t> by_slot(h->ns, 0);
+      for (int v = 0; v < h->n; ++v) by_slot[h->land.nw.slot_of[v]] = res_land[v];
+      const uint8_t* dptr = nullptr;
+      if (upload_raw(by_slot, &dptr, h->land_full.dev_arrays) != cudaSuccess) return bail(WFLOWB200_ERR_CUDA);
+      h->f.land_is_res_outlet = const_cast<uint8_t*>(dptr);
+    }
+  }
   {
     std::vector<int64_t> riv_land_slot(h->nriv), riv_of_land(h->n, -1);
     for (int p = 0; p < h->nriv; ++p) {
@@ -655,8 +773,22 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     }
     TRY_CREATE(upload_i32(riv_land_slot, &h->f.riv_land_slot, 0));
     TRY_CREATE(upload_i32(riv_of_land, &h->riv_of_land, 0));
+    if (h->nres > 0) {  // NetworkRiver.reservoir_indices by river slot; the outlet's land slot
+      std::vector<int64_t> riv_res(std::max(h->nrs, 1), -1), res_land(h->nres), ident(h->nres);
+      for (int i = 0; i < h->nres; ++i) {
+        const int64_t rnode = dom->reservoir_river_indices[i] - 1;
+        const int64_t p = h->river.nw.slot_of[rnode];
+        riv_res[p] = i;
+        res_land[i] = riv_land_slot[p];
+        ident[i] = i;
+      }
+      TRY_CREATE(upload_i32(riv_res, &h->f.riv_reservoir, 0));
+      TRY_CREATE(upload_i32(res_land, &h->f.res_land_slot, 0));
+      TRY_CREATE(upload_i32(ident, &h->res_ident, 0));
+    }
   }
-  h->stage_doubles = std::max<size_t>((size_t)h->n * (h->N + 1), (size_t)3 * h->n);
+  h->stage_doubles = std::max<size_t>(std::max<size_t>((size_t)h->n * (h->N + 1), (size_t)3 * h->n),
+                                      (size_t)std::max(h->nriv, h->nres));
   TRY_CREATE(cudaMalloc((void**)&h->d_stage, h->stage_doubles * sizeof(double)));
   TRY_CREATE(cudaMalloc((void**)&h->d_forcing, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMallocHost((void**)&h->h_pinned, (size_t)3 * h->n * sizeof(double)));
@@ -714,7 +846,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     TRY_CREATE(cudaMalloc((void**)&h->d_qstate, WFB_QUANTILE_STATE_WORDS * sizeof(unsigned long long)));
   }
 
-  h->kc.n = h->n; h->kc.nriv = h->nriv; h->kc.ns = h->ns; h->kc.nrs = h->nrs;
+  h->kc.n = h->n; h->kc.nriv = h->nriv; h->kc.ns = h->ns; h->kc.nrs = h->nrs; h->kc.nres = h->nres;
   h->kc.gash = cfg->gash; h->kc.has_lai = cfg->has_lai; h->kc.snow = cfg->snow;
   h->kc.glacier = cfg->glacier;
   h->kc.soil_infiltration_reduction = cfg->soil_infiltration_reduction;
@@ -728,6 +860,11 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->grid_olf = wave_max_grid(0, h->N, h->smem_olf, cfg->device);
   h->grid_riv = wave_max_grid(1, h->N, h->smem_riv, cfg->device);
   h->grid_ssf = wave_max_grid(2, h->N, h->smem_ssf, cfg->device);
+  if (cfg->snow_gravitational_transport) {
+    h->smem_snow = wave_smem(3, std::max(h->land.dev.max_inlets, h->land_full.dev.max_inlets));
+    h->grid_snow = wave_max_grid(3, h->N, h->smem_snow, cfg->device);
+    if (h->grid_snow <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
+  }
   h->smem_surface = surface_smem(h->land.dev.max_inlets, h->river.dev.max_inlets,
                                  &h->smem_surface_per_warp);
   h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
@@ -749,8 +886,12 @@ void wflowb200_destroy(WflowB200* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.nlayers_kv); cudaFree(h->f.olf_newton_trace); cudaFree(h->f.riv_newton_trace);
+  cudaFree(h->f.riv_reservoir); cudaFree(h->f.res_land_slot); cudaFree(h->res_ident);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
+  cudaFree(h->d_ring); cudaFree(h->d_lai_table); cudaFreeHost(h->h_out_pinned);
+  for (auto e : h->ring_ready) if (e) cudaEventDestroy(e);
+  for (auto e : h->ring_consumed) if (e) cudaEventDestroy(e);
   for (auto st : h->side_stream) if (st) cudaStreamSynchronize(st);
   cudaFree(h->d_unsat_pool); cudaFree(h->d_unsat_its); cudaFree(h->d_unsat_list);
   cudaFree(h->d_unsat_count);
@@ -760,7 +901,7 @@ void wflowb200_destroy(WflowB200* h) {
   for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
   cudaFree(h->d_work); cudaFree(h->d_qstate); cudaFree(h->ssf_q_out);
-  free_domain(h->land); free_domain(h->river);
+  free_domain(h->land); free_domain(h->river); free_domain(h->land_full);
   if (h->forcing_ready) cudaEventDestroy(h->forcing_ready);
   if (h->forcing_consumed) cudaEventDestroy(h->forcing_consumed);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -775,7 +916,7 @@ static int32_t field_common(WflowB200* h, int32_t id, int64_t sc, int64_t sl, in
   if (id < 0 || id >= WFLOWB200_NUM_FIELDS) return fail(h, WFLOWB200_ERR_ARG, "bad field id");
   kind = kFieldKinds[id];
   layers = layers_of(h, kind);
-  count = kind == 3 ? h->nriv : h->n;
+  count = count_of(h, kind);
   if (layers == 1) {
     if (sc != 1) return fail(h, WFLOWB200_ERR_ARG, "scalar fields need stride_cell == 1");
   } else if (!((sc == layers && sl == 1) || (sc == 1 && sl == count))) {
@@ -796,9 +937,9 @@ int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t
   if (count == 0) return WFLOWB200_OK;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, src, extent * sizeof(double), cudaMemcpyHostToDevice,
                               h->stream));
-  const DomainDev& d = kind == 3 ? h->river : h->land;
-  h->launches += launch_gather_field(h->field_ptr[id], h->d_stage, d.node_of_slot, count,
-                                     kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
+  const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+  h->launches += launch_gather_field(h->field_ptr[id], h->d_stage, slot_map, count,
+                                     slots_of(h, kind), layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return WFLOWB200_OK;
 }
@@ -812,9 +953,9 @@ int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, i
   if (count == 0) return WFLOWB200_OK;
   rc = wait_forcing(h);
   if (rc) return rc;
-  const DomainDev& d = kind == 3 ? h->river : h->land;
-  h->launches += launch_scatter_field(h->d_stage, h->field_ptr[id], d.node_of_slot, count,
-                                      kind == 3 ? h->nrs : h->ns, layers, sc, sl, h->stream);
+  const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+  h->launches += launch_scatter_field(h->d_stage, h->field_ptr[id], slot_map, count,
+                                      slots_of(h, kind), layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_stage, extent * sizeof(double), cudaMemcpyDeviceToHost,
                               h->stream));
   return check_device_error(h);
@@ -877,6 +1018,117 @@ int32_t wflowb200_set_forcing(WflowB200* h, const double* P, const double* PET, 
                               h->copy_stream));
   CUDA_TRY(h, cudaEventRecord(h->forcing_ready, h->copy_stream));
   h->forcing_pending = true;
+  return WFLOWB200_OK;
+}
+
+// ---- forcing / cyclic-parameter staging and output gather (the steps either side of the path:
+//      io.jl:108-227 update_forcing! / update_cyclic!, io.jl:815-899 write_output) ---------------
+int32_t wflowb200_forcing_ring_create(WflowB200* h, int32_t depth) {
+  WFB_ENTER(h);
+  if (depth < 1 || depth > 1024) return fail(h, WFLOWB200_ERR_ARG, "1 <= depth <= 1024 required");
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+  cudaFree(h->d_ring);
+  h->d_ring = nullptr;
+  for (auto e : h->ring_ready) cudaEventDestroy(e);
+  for (auto e : h->ring_consumed) cudaEventDestroy(e);
+  h->ring_ready.assign(depth, nullptr);
+  h->ring_consumed.assign(depth, nullptr);
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_ring, (size_t)depth * 3 * h->n * sizeof(double)));
+  for (int k = 0; k < depth; ++k) {
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ring_ready[k], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ring_consumed[k], cudaEventDisableTiming));
+  }
+  h->ring_depth = depth;
+  h->ring_use = -1;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_forcing_ring_put(WflowB200* h, int32_t slot, const double* P, const double* PET,
+                                   const double* T) {
+  WFB_ENTER(h);
+  if (!P || !PET || !T) return WFLOWB200_ERR_ARG;
+  if (slot < 0 || slot >= h->ring_depth) return fail(h, WFLOWB200_ERR_ARG, "bad ring slot");
+  // the slab may still be read by the gather of an earlier step
+  CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ring_consumed[slot], 0));
+  const size_t nb = (size_t)h->n * sizeof(double);
+  double* dst = h->d_ring + (size_t)slot * 3 * h->n;
+  // page-locked caller arrays stream straight over; pageable ones are staged by the driver
+  CUDA_TRY(h, cudaMemcpyAsync(dst, P, nb, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst + h->n, PET, nb, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst + 2 * (size_t)h->n, T, nb, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(h, cudaEventRecord(h->ring_ready[slot], h->copy_stream));
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_forcing_ring_use(WflowB200* h, int32_t slot) {
+  WFB_ENTER(h);
+  if (slot < 0 || slot >= h->ring_depth) return fail(h, WFLOWB200_ERR_ARG, "bad ring slot");
+  h->ring_use = slot;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_set_cyclic_lai(WflowB200* h, const double* table, int32_t n_slabs) {
+  WFB_ENTER(h);
+  if (!table || n_slabs < 1) return WFLOWB200_ERR_ARG;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_lai_table);
+  h->d_lai_table = nullptr;
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_lai_table, (size_t)n_slabs * h->n * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpy(h->d_lai_table, table, (size_t)n_slabs * h->n * sizeof(double),
+                         cudaMemcpyHostToDevice));
+  h->lai_slabs = n_slabs;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_use_cyclic_lai(WflowB200* h, int32_t slab) {
+  WFB_ENTER(h);
+  if (slab < 0 || slab >= h->lai_slabs) return fail(h, WFLOWB200_ERR_ARG, "bad LAI slab");
+  h->launches += launch_gather_field(h->f.leaf_area_index, h->d_lai_table + (size_t)slab * h->n,
+                                     h->land.node_of_slot, h->n, h->ns, 1, 1, 1, h->stream);
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_get_fields(WflowB200* h, const int32_t* ids, int32_t n_ids, double* dst) {
+  WFB_ENTER(h);
+  if (!ids || !dst || n_ids < 1) return WFLOWB200_ERR_ARG;
+  size_t total = 0;
+  for (int k = 0; k < n_ids; ++k) {
+    if (ids[k] < 0 || ids[k] >= WFLOWB200_NUM_FIELDS) return fail(h, WFLOWB200_ERR_ARG, "bad field id");
+    const int kind = kFieldKinds[ids[k]];
+    total += (size_t)count_of(h, kind) * layers_of(h, kind);
+  }
+  int32_t rc = wait_forcing(h);
+  if (rc) return rc;
+  if (total > h->stage_doubles) {  // the device staging grows to the largest request
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_stage);
+    h->d_stage = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_stage, total * sizeof(double)));
+    h->stage_doubles = total;
+  }
+  if (total > h->out_pinned_doubles) {
+    cudaFreeHost(h->h_out_pinned);
+    h->h_out_pinned = nullptr;
+    CUDA_TRY(h, cudaMallocHost((void**)&h->h_out_pinned, total * sizeof(double)));
+    h->out_pinned_doubles = total;
+  }
+  size_t off = 0;
+  for (int k = 0; k < n_ids; ++k) {  // node order, layered fields cell-major (Vector{SVector{N}})
+    const int kind = kFieldKinds[ids[k]];
+    const int layers = layers_of(h, kind), count = count_of(h, kind);
+    if (count == 0) continue;
+    const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+    h->launches += launch_scatter_field(h->d_stage + off, h->field_ptr[ids[k]], slot_map, count,
+                                        slots_of(h, kind), layers, layers, 1, h->stream);
+    off += (size_t)count * layers;
+  }
+  // ONE device-to-host copy for the whole set, through page-locked memory
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_out_pinned, h->d_stage, total * sizeof(double),
+                              cudaMemcpyDeviceToHost, h->stream));
+  rc = check_device_error(h);
+  if (rc) return rc;
+  memcpy(dst, h->h_out_pinned, total * sizeof(double));
   return WFLOWB200_OK;
 }
 
@@ -958,6 +1210,12 @@ int32_t wflowb200_update_lateral_inflow_river(WflowB200* h) {
   WFB_ENTER(h);
   return check_launch(h, launch_lateral_inflow_river(h->f, h->kc, h->stream),
                       "update_lateral_inflow(river)");
+}
+
+int32_t wflowb200_update_inflow_reservoir(WflowB200* h) {
+  WFB_ENTER(h);
+  if (h->nres == 0) return WFLOWB200_OK;
+  return check_launch(h, launch_inflow_reservoir(h->f, h->kc, h->stream), "update_inflow(reservoir)");
 }
 
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
@@ -1126,6 +1384,7 @@ int32_t wflowb200_update_model(WflowB200* h, double dt) {
     if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
     mark(6);
     if ((rc = wflowb200_update_lateral_inflow_river(h))) return rc;
+    if ((rc = wflowb200_update_inflow_reservoir(h))) return rc;
     mark(7);
     if ((rc = wflowb200_update_river_flow_model(h, dt))) return rc;
   }

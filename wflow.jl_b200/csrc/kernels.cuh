@@ -30,8 +30,10 @@ struct UnsatWork {
 // next slices on s; ev holds 2 * n_slices events.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, const int* slice_tile_begin,
-                          unsigned* tile_prio, int32_t* tile_order, int engine_grid,
+                          unsigned* tile_prio, int32_t* tile_order, int engine_grid, int phase,
                           cudaStream_t s, cudaStream_t const* side, cudaEvent_t const* ev);
+// phase: 0 the whole update; 1 interception + snow only, 2 the rest (lateral snow transport runs
+// between the two: launch_snow_transport)
 // self-test of device_math.cuh: out[6] (device, zeroed) receives bit patterns of the maxima
 int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);
@@ -101,8 +103,13 @@ int launch_river_wave(const DevFields& f, const KCfg& c, const DevNet& net, cons
                       cudaStream_t s);
 int launch_subsurface_wave(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,
                            const WaveLaunch& w, cudaStream_t s);
+// lateral_snow_transport! (surface_process.jl:9-19): accucapacityflux of snow storage and snow
+// water over the land network + flux_in!; kind 3 of wave_smem / wave_max_grid
+int launch_snow_transport(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
+                          cudaStream_t s);
 int launch_lateral_inflow_overland(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_lateral_inflow_river(const DevFields& f, const KCfg& c, cudaStream_t s);
+int launch_inflow_reservoir(const DevFields& f, const KCfg& c, cudaStream_t s);
 
 // adaptive time step statistics (surface_kinwave.jl:674-704, lateral_subsurface_flow.jl:314-344)
 // `work` holds n doubles; results are written to out[0] (count) / keys in work.

@@ -21,6 +21,9 @@ struct DevFields {
   int32_t* n_unsatlayers;      // land
   int32_t* riv_land_slot;      // river slot -> land slot
   int32_t* nlayers_kv;         // land (KvLayeredExponential only)
+  int32_t* riv_reservoir;      // river slot -> reservoir (0-based) or -1; nullptr without reservoirs
+  int32_t* res_land_slot;      // reservoir -> land slot of its outlet cell
+  uint8_t* land_is_res_outlet; // land slot is a reservoir outlet (nullptr without reservoirs)
   int32_t* olf_newton_trace;   // land / river, or nullptr: Newton iterations of kinematic_wave
   int32_t* riv_newton_trace;   // per node since wflowb200_newton_trace(h, 1)
 };
@@ -60,7 +63,7 @@ struct DevNet {
 };
 
 struct KCfg {
-  int32_t n, nriv, ns, nrs;
+  int32_t n, nriv, ns, nrs, nres;
   int32_t gash, has_lai, snow, glacier, soil_infiltration_reduction, kv_profile;
   double qroot;                // KIN_WAVE_MIN_FLOW^0.2
   int32_t kw_root_each_substep; // 1: u_prev = pow(q_prev, 0.2) before every solve, like the

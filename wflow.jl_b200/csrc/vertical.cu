@@ -45,6 +45,11 @@
 #include "model.cuh"
 #include "soil_storage.cuh"
 
+// one-touch streaming loads of the vertical update (build variant: evict-first in L1 / L2)
+#if defined(WFB_V_LDCS) && WFB_V_LDCS
+#define __ldg(p) __ldcs(p)
+#endif
+
 namespace wfb {
 
 namespace {
@@ -489,11 +494,62 @@ tile_order_kernel(unsigned* __restrict__ prio, int32_t* __restrict__ order, cons
   }
 }
 
+// Every input array of the cell is requested at the top of the kernel, long before its first use:
+// the loads proper sit next to their first use (registers), and with 16 warps per SM that spend
+// most of their time in FP64 dependency chains only a few of them would be in flight at any time.
+#ifndef WFB_V_PREFETCH
+#define WFB_V_PREFETCH 2   // 0 off, 1 into L1, 2 into L2
+#endif
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if WFB_V_PREFETCH == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif WFB_V_PREFETCH == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+template <int N>
+__device__ __forceinline__ void prefetch_inputs(const DevFields& f, const KCfg& c, const int i) {
+#if WFB_V_PREFETCH
+  const int ns = c.ns;
+  const double* const scalars[] = {
+      f.river_fraction, f.water_fraction, f.olf_h, f.waterdepth_river, f.theta_s, f.theta_r,
+      f.soil_thickness, f.soil_water_capacity, f.saturated_water_depth,
+      f.compacted_soil_area_fraction, f.infiltration_capacity_soil,
+      f.infiltration_capacity_compacted_soil, f.kv_0, f.hydraulic_conductivity_scale_parameter,
+      f.theta_fc, f.rooting_depth, f.h1, f.h2, f.h4, f.alpha_h1, f.air_entry_pressure, f.h3_high,
+      f.h3_low, f.wet_root_distribution_parameter, f.cap_hmax, f.cap_n, f.maximum_leakage};
+#pragma unroll
+  for (int a = 0; a < (int)(sizeof(scalars) / sizeof(scalars[0])); ++a) prefetch_line(scalars[a] + i);
+  if (c.snow) {
+    const double* const snow[] = {f.temperature_interval_snowfall, f.temperature_threshold_snowfall,
+                                  f.snow_storage, f.snow_water, f.temperature_threshold_melt,
+                                  f.degree_day_factor, f.water_holding_capacity,
+                                  f.soil_surface_temperature, f.w_soil};
+#pragma unroll
+    for (int a = 0; a < 9; ++a) prefetch_line(snow[a] + i);
+  }
+  prefetch_line(f.number_of_layers + i);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    prefetch_line(f.unsaturated_layer_depth + k * ns + i);
+    prefetch_line(f.actual_layer_thickness + k * ns + i);
+    prefetch_line(f.cumulative_layer_depth + k * ns + i);
+    prefetch_line(f.brooks_corey_exponent + k * ns + i);
+    prefetch_line(f.vertical_hydraulic_conductivity_factor + k * ns + i);
+    prefetch_line(f.rootfraction + k * ns + i);
+  }
+  prefetch_line(f.cumulative_layer_depth + N * ns + i);
+#endif
+}
+
 // update_land_hydrology_model!                                                sbm.jl:82-132
 template <int N>
 __global__ void __launch_bounds__(WFB_V_TILE, WFB_V_MINBLOCKS)
 land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
-                      const int32_t* __restrict__ order, const int tile_begin) {
+                      const int32_t* __restrict__ order, const int tile_begin, const int phase) {
+  // phase 0: the whole update. With lateral snow transport (snow_gravitational_transport__flag,
+  // sbm.jl:98-100) a pass over the drainage network sits between the snow and the glacier
+  // model: phase 1 = interception + snow, phase 2 = everything after the transport.
   // one tile of 128 consecutive slots per CTA, in the order of tile_order_kernel
   const int i = __ldg(order + tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
   if (i >= c.ns) return;    // whole warps (ns is a multiple of 32)
@@ -501,6 +557,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   // the warp-aggregated suspension) and never suspend; their stores land in the padding
   const bool live = i < c.n;
   const int ns = c.ns;
+  prefetch_inputs<N>(f, c, i);
   const Divisor ddt(dt);
   double st_canopy = 0.0, st_snoww = 0.0, st_gstore = 0.0, st_snow = 0.0, st_tsoil = 0.0;
   SoilColumn<N> s;
@@ -512,6 +569,15 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
 
   // ---- interception (canopy.jl:54-163, rainfall_interception.jl:9-130) ----------------------
   double cmax, gap;
+  double canopy_potevap, throughfall = 0.0, interception, stemflow = 0.0;
+  double snow = 0.0, snow_runoff = 0.0;
+  if (phase == 2) {  // results of phase 1, from their (reference-visible) arrays
+    gap = f.canopy_gap_fraction[i];
+    canopy_potevap = f.canopy_potevap[i];
+    interception = f.interception_rate[i];
+    snow_runoff = f.snow_runoff[i];
+    snow = f.snow_storage[i];       // after lateral_snow_transport!
+  } else {
   if (c.has_lai) {
     const double lai = __ldg(f.leaf_area_index + i);
     cmax = __ldg(f.storage_specific_leaf + i) * lai + __ldg(f.storage_wood + i);
@@ -523,8 +589,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     gap = __ldg(f.canopy_gap_fraction + i);
   }
   const double kc = __ldg(f.crop_coefficient + i);
-  const double canopy_potevap = kc * PET * (1.0 - gap);
-  double throughfall, interception, stemflow;
+  canopy_potevap = kc * PET * (1.0 - gap);
   if (c.gash) {
     double e_r;
     if (c.has_lai) {
@@ -591,10 +656,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   f.interception_rate[i] = interception;
   f.stemflow[i] = stemflow;
 
-  // ---- snow (snow.jl:123-177, snow_process.jl:26-116) and glacier (glacier_process.jl:27-62)
-  double water_flux_surface;
-  double gfrac = 0.0;
-  const bool glac = c.snow && c.glacier;
+  // ---- snow (snow.jl:123-177, snow_process.jl:26-116) ---------------------------------------
   if (c.snow) {
     const double eff = throughfall + stemflow;
     const double tti = __ldg(f.temperature_interval_snowfall + i);
@@ -605,7 +667,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     const double snowfrac = 1.0 - rainfrac;
     const double snow_precip = snowfrac * 1.0 * eff;
     const double liquid_precip = rainfrac * 1.0 * eff;
-    double snow = f.snow_storage[i], snoww = f.snow_water[i];
+    snow = f.snow_storage[i];
+    double snoww = f.snow_water[i];
     const double ttm = __ldg(f.temperature_threshold_melt + i);
     const double cfmax = __ldg(f.degree_day_factor + i);
     const double whc = __ldg(f.water_holding_capacity + i);
@@ -627,7 +690,6 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     snow += snow_precip * dt;
     snoww += liquid_precip * dt;
     const double maxw = snow * whc;
-    double snow_runoff;
     if (snoww > maxw) { snow_runoff = (snoww - maxw) / ddt; snoww = maxw; }
     else snow_runoff = 0.0;
     f.effective_precip[i] = eff;
@@ -637,6 +699,19 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     f.snow_water_equivalent[i] = snoww + snow;
     f.snow_melt[i] = snow_melt;
     f.snow_runoff[i] = snow_runoff;
+  }
+  if (phase == 1) {  // the states lateral_snow_transport! works on; the rest follows in phase 2
+    if (!c.gash) f.canopy_storage[i] = st_canopy;
+    if (c.snow) { f.snow_water[i] = st_snoww; f.snow_storage[i] = snow; }
+    return;
+  }
+  }  // phase != 2
+
+  // ---- glacier (glacier.jl:122-154, glacier_process.jl:27-62) and the surface water flux ------
+  double water_flux_surface;
+  double gfrac = 0.0;
+  const bool glac = c.snow && c.glacier;
+  if (c.snow) {
     double gmelt = 0.0;
     if (glac) {
       gfrac = __ldg(f.glacier_fraction + i);
@@ -754,11 +829,12 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   double transfer;
   const bool done = unsat_layers<N>(c, w, 0, i, 0, n_unsat, 0.0, 0.0, infiltration, s.uld, s.ult,
                                     s.bc, s.kv, theta_e, dt, ddt, live, transfer);
-  // the read-modify-write states of the sections above
-  if (!c.gash) f.canopy_storage[i] = st_canopy;
+  // the read-modify-write states of the sections above (phase 2: canopy and snow water were
+  // written by phase 1)
+  if (!c.gash && phase == 0) f.canopy_storage[i] = st_canopy;
   if (c.snow) {
-    f.snow_water[i] = st_snoww;
-    f.snow_storage[i] = st_snow;
+    if (phase == 0) f.snow_water[i] = st_snoww;
+    if (phase == 0 || c.glacier) f.snow_storage[i] = st_snow;
     f.soil_surface_temperature[i] = st_tsoil;
     if (c.glacier) f.glacier_store[i] = st_gstore;
   }
@@ -1018,18 +1094,25 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 // last slice is exposed. ev[2k] orders E_k after A_k, ev[2k+1] joins E_k into the main stream.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, const int* slice_tile_begin,
-                          unsigned* tile_prio, int32_t* tile_order, int engine_grid,
+                          unsigned* tile_prio, int32_t* tile_order, int engine_grid, int phase,
                           cudaStream_t s, cudaStream_t const* side, cudaEvent_t const* ev) {
   int launches = 0;
   const int n_tiles = (c.ns + kTile - 1) / kTile;
-  tile_order_kernel<<<1, 1024, 0, s>>>(tile_prio, tile_order, n_tiles);
-  ++launches;
+  if (phase != 2) {  // (phase 2 reuses the order of phase 1)
+    tile_order_kernel<<<1, 1024, 0, s>>>(tile_prio, tile_order, n_tiles);
+    ++launches;
+  }
+  if (phase == 1) {  // interception + snow of every cell: no loops, no engine
+    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(
+                                 f, c, w[0], dt, tile_order, 0, 1)));
+    return launches + 1;
+  }
   for (int k = 0; k < n_slices; ++k) {
     const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
     if (t0 >= t1) continue;
     cudaMemsetAsync(w[k].count, 0, 2 * kBuckets * sizeof(unsigned), s);
     WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<t1 - t0, kTile, 0, s>>>(
-                                 f, c, w[k], dt, tile_order, t0)));
+                                 f, c, w[k], dt, tile_order, t0, phase)));
     ++launches;
     cudaStream_t e = n_slices > 1 ? side[k % WFB_V_SIDE_STREAMS] : s;
     if (n_slices > 1) {

@@ -37,7 +37,8 @@ class SbmModel:
         idx = np.ascontiguousarray(domain["indices"], dtype=np.int64)
         ldd = np.ascontiguousarray(domain["ldd"], dtype=np.uint8)
         rli = np.ascontiguousarray(domain["river_land_indices"], dtype=np.int64)
-        self.n, self.nriv, self.N = len(ldd), len(rli), int(cfg["n_layers"])
+        rri = np.ascontiguousarray(domain.get("reservoir_river_indices", np.zeros(0)), dtype=np.int64)
+        self.n, self.nriv, self.N, self.nres = len(ldd), len(rli), int(cfg["n_layers"]), len(rri)
         c = _lib.Config()
         c.n, c.nriv, c.n_layers, c.device = self.n, self.nriv, self.N, device
         for k in ("gash", "has_lai", "snow", "glacier", "soil_infiltration_reduction",
@@ -51,10 +52,11 @@ class SbmModel:
         c.dt_ssf = float(cfg.get("dt_ssf", 86400.0))
         c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
         c.kin_wave_min_flow_qroot = float(cfg.get("kin_wave_min_flow_qroot", 1e-30 ** 0.2))
+        c.snow_gravitational_transport = int(cfg.get("snow_transport", 0))
         for k in ("wave_piece_depth_land", "vertical_slices", "unsat_inline_iters"):  # 0 = automatic
             setattr(c, k, int(cfg.get(k, 0)))
         d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
-                        rli.ctypes.data)
+                        rli.ctypes.data, len(rri), rri.ctypes.data if len(rri) else None)
         rc = self._L.wflowb200_create(C.byref(c), C.byref(d), C.byref(self._h))
         if rc != 0:
             msg = self._L.wflowb200_last_error(None).decode()
@@ -86,7 +88,8 @@ class SbmModel:
     # ---- state transfer ----------------------------------------------------------------
     def _shape(self, name):
         k = self._kinds[name]
-        return {0: (self.n,), 1: (self.n, self.N), 2: (self.n, self.N + 1), 3: (self.nriv,)}[k]
+        return {0: (self.n,), 1: (self.n, self.N), 2: (self.n, self.N + 1), 3: (self.nriv,),
+                4: (self.nres,)}[k]
 
     def set(self, name: str, a) -> None:
         if name in INT_FIELDS:
@@ -126,6 +129,40 @@ class SbmModel:
         self._check(self._L.wflowb200_set_forcing(self._h, p.ctypes.data, e.ctypes.data,
                                                   t.ctypes.data))
 
+    # ---- staging either side of the path (io.jl:108-227, 815-899) ------------------------
+    def forcing_ring_create(self, depth: int):
+        self._check(self._L.wflowb200_forcing_ring_create(self._h, int(depth)))
+
+    def forcing_ring_put(self, slot: int, p, e, t):
+        """The arrays must stay alive (and unchanged) until the slab has been used."""
+        for a in (p, e, t):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n,)
+        self._check(self._L.wflowb200_forcing_ring_put(self._h, int(slot), p.ctypes.data,
+                                                       e.ctypes.data, t.ctypes.data))
+
+    def forcing_ring_use(self, slot: int):
+        self._check(self._L.wflowb200_forcing_ring_use(self._h, int(slot)))
+
+    def set_cyclic_lai(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.ndim == 2 and t.shape[1] == self.n
+        self._check(self._L.wflowb200_set_cyclic_lai(self._h, t.ctypes.data, t.shape[0]))
+
+    def use_cyclic_lai(self, slab: int):
+        self._check(self._L.wflowb200_use_cyclic_lai(self._h, int(slab)))
+
+    def get_fields(self, names) -> dict:
+        """Several output vectors with one device-to-host copy (write_output, io.jl:815-899)."""
+        ids = np.array([self._ids[n] for n in names], dtype=np.int32)
+        sizes = [int(np.prod(self._shape(n))) for n in names]
+        buf = np.empty(sum(sizes), dtype=np.float64)
+        self._check(self._L.wflowb200_get_fields(self._h, ids.ctypes.data, len(ids), buf.ctypes.data))
+        out, off = {}, 0
+        for n, sz in zip(names, sizes):
+            out[n] = buf[off:off + sz].reshape(self._shape(n))
+            off += sz
+        return out
+
     # ---- the hot path (names of the reference functions) ---------------------------------
     def update_land_hydrology_model(self, dt):
         self._check(self._L.wflowb200_update_land_hydrology_model(self._h, dt))
@@ -148,6 +185,9 @@ class SbmModel:
     def update_lateral_inflow_river(self):
         self._check(self._L.wflowb200_update_lateral_inflow_river(self._h))
 
+    def update_inflow_reservoir(self):
+        self._check(self._L.wflowb200_update_inflow_reservoir(self._h))
+
     def update_river_flow_model(self, dt):
         self._check(self._L.wflowb200_update_river_flow_model(self._h, dt))
 
@@ -156,6 +196,7 @@ class SbmModel:
         self.update_lateral_inflow_overland()
         self.update_overland_flow_model(dt)
         self.update_lateral_inflow_river()
+        self.update_inflow_reservoir()
         self.update_river_flow_model(dt)
 
     def update_total_water_storage(self):

@@ -28,7 +28,7 @@ def build_network_artifacts(cfg: dict, domain: dict) -> dict:
     c.land_streamorder_min = int(cfg.get("land_streamorder_min", 5))
     c.river_streamorder_min = int(cfg.get("river_streamorder_min", 6))
     d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
-                    rli.ctypes.data)
+                    rli.ctypes.data, 0, None)
     net = C.c_void_p()
     rc = L.wflowb200_network_build(C.byref(c), C.byref(d), C.byref(net))
     if rc != 0:

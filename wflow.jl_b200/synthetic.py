@@ -159,13 +159,48 @@ def set_layerthickness(ref_depth, cum_depth, thickness):
     return out
 
 
+def _kh_layered(profile, F, nlayers, zi, N):
+    """kh_layered_profile! (utils.jl:792-895) for the cold state: n_unsatlayers from zi."""
+    n = len(zi)
+    kv, cld, alt = F["kv"], F["cumulative_layer_depth"], F["actual_layer_thickness"]
+    d, ratio = F["soil_thickness"], F["ssf_khfrac"]
+    ult = set_layerthickness(zi, cld, alt)
+    nunsat = N - np.isnan(ult).sum(axis=1)
+    kh = np.zeros(n)
+    for i in range(n):
+        m = int(nlayers[i])
+        if d[i] > zi[i]:
+            t = 0.0
+            k = max(int(nunsat[i]), 1)
+            if profile == 3 and zi[i] >= F["z_layered"][i]:
+                f, zl, j = F["hydraulic_conductivity_scale_parameter"][i], F["z_layered"][i], int(F["nlayers_kv"][i])
+                t += kv[i, j - 1] / f * (np.exp(-f * (zi[i] - zl)) - np.exp(-f * (d[i] - zl)))
+                k = m
+            else:
+                t += (cld[i, k] - zi[i]) * kv[i, k - 1]
+            k += 1
+            while k <= m:
+                if profile == 3 and k > F["nlayers_kv"][i]:
+                    f, zl, j = F["hydraulic_conductivity_scale_parameter"][i], F["z_layered"][i], int(F["nlayers_kv"][i])
+                    t += kv[i, j - 1] / f * (1.0 - np.exp(-f * (d[i] - zl)))
+                    k = m
+                else:
+                    t += alt[i, k - 1] * kv[i, k - 1]
+                k += 1
+            kh[i] = (t / (d[i] - zi[i])) * ratio[i]
+        else:
+            kh[i] = kv[i, m - 1] * ratio[i]
+    return kh
+
+
 def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                soil_layer_thickness_mm=(100, 300, 800), mask=None, river_fraction_target=0.116,
                cell_length: float = 1000.0, snow: bool = True, glacier: bool = False,
                kv_profile: int = 0, nthreads: int = 8, adaptive: bool = False,
                soil_infiltration_reduction: bool = False, id_offset: int = 0,
                external_inflow: bool = False, network: str = "scheidegger",
-               n_active: int | None = None, n_river: int | None = None):
+               n_active: int | None = None, n_river: int | None = None, reservoirs: int = 0,
+               snow_transport: bool = False):
     """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
     the reference's field names; layered arrays are cell-major (n, N). network: "scheidegger"
     (a forest of many small basins, codes 5/7/8/9) or "dendritic" (one outlet, all eight
@@ -210,6 +245,10 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     F["water_holding_capacity"] = np.full(n, 0.1)
     F["snow_storage"] = np.zeros(n)
     F["snow_water"] = np.zeros(n)
+    if snow_transport:   # a snow pack to move: up to 1.5 m on a third of the cells
+        pack = u01(seed, 18, gid) < 0.33
+        F["snow_storage"] = np.where(pack, 1.5 * u01(seed, 19, gid), 0.0)
+        F["snow_water"] = 0.08 * F["snow_storage"]
     if glacier:
         F["glacier_temperature_threshold_melt"] = np.full(n, 273.15)
         F["glacier_degree_day_factor"] = r(16, 3.0e-3 / 86400.0)
@@ -248,6 +287,23 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     F["hydraulic_conductivity_scale_parameter"] = r(43, 3.304)
     if kv_profile == 1:
         F["z_exp"] = r(44, 0.6)
+    if kv_profile >= 2:   # layered profiles (soil.jl:272-316): kv per layer, decreasing with depth
+        dec = np.array([1.0, 0.55, 0.3, 0.18, 0.12, 0.08, 0.05, 0.03])[:N]
+        F["kv"] = np.stack([r(90 + k, 4.846e-6 * dec[k]) for k in range(N)], axis=1)
+        F["infiltration_capacity_soil"] = F["kv"][:, 0] * F["vertical_hydraulic_conductivity_factor"][:, 0]
+    if kv_profile == 3:   # KvLayeredExponential: z_layered snapped to a layer boundary
+        cld_ = F["cumulative_layer_depth"]
+        zl = np.full(n, 0.4)
+        nk = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            layers = cld_[i, 1:nlayers[i]]        # cumulative_layer_depth[i][2:number_of_layers[i]]
+            if len(layers) == 0:                  # a single layer: keep the first boundary
+                layers = cld_[i, 1:2]
+            k = int(np.argmin(np.abs(zl[i] - layers)))
+            nk[i] = k + 1
+            zl[i] = layers[k]
+        F["z_layered"] = zl
+        F["nlayers_kv"] = nk
     F["maximum_leakage"] = np.zeros(n)
     F["cap_hmax"], F["cap_n"] = np.full(n, 2.0), np.full(n, 2.0)
     F["wet_root_distribution_parameter"] = np.full(n, -5.0e5)
@@ -306,7 +362,24 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     F["specific_yield"] = np.maximum(theta_s - theta_fc, 0.02)
     F["ssf_top"] = 100.0 + 50.0 * u01(seed, 54, gid)
     fpar = F["hydraulic_conductivity_scale_parameter"]
-    if kv_profile == 0:
+    if kv_profile >= 2:   # initialize_lateral_ssf_model!(..., ::KvLayered / ::KvLayeredExponential)
+        F["ssf_khfrac"] = khfrac                                        # utils.jl:988-1050
+        F["ssf_kh"] = _kh_layered(kv_profile, F, nlayers, zi, N)
+        F["ssf_q"] = F["ssf_kh"] * (soil_thickness - zi) * F["slope"] * F["flow_width"]
+        kh_max = np.zeros(n)
+        for i in range(n):
+            acc_ = 0.0
+            for j in range(1, nlayers[i] + 1):
+                if kv_profile == 2 or j <= F["nlayers_kv"][i]:
+                    acc_ += F["kv"][i, j - 1] * alt[i, j - 1]
+                else:
+                    zt = soil_thickness[i] - F["z_layered"][i]
+                    k = max(j - 1, 1)
+                    acc_ += F["kv"][i, k - 1] / fpar[i] * (1.0 - np.exp(-fpar[i] * zt))
+                    break
+            kh_max[i] = acc_ * khfrac[i]
+        F["ssf_q_max"] = kh_max * F["slope"]
+    elif kv_profile == 0:
         F["ssf_q_max"] = ((F["kh_0"] * F["slope"]) / fpar) * (1.0 - np.exp(-fpar * soil_thickness))
         F["ssf_q"] = (((F["kh_0"] * F["slope"]) / fpar)
                       * (np.exp(-fpar * zi) - np.exp(-fpar * soil_thickness)) * F["flow_width"])
@@ -339,15 +412,57 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     for k in ("riv_q", "riv_h", "riv_storage", "riv_qin", "riv_qlat", "riv_inwater"):
         F[k] = np.zeros(nriv)
 
-    cfg = dict(n=n, nriv=nriv, n_layers=N, N=N, gash=int(dt >= 23 * 3600.0), has_lai=1,
+    # ---- reservoirs on the river (reservoir.jl; Moselle has two, test/sbm_config.toml:126) -----
+    reservoir_river_indices = np.zeros(0, dtype=np.int64)
+    nres = 0
+    if reservoirs and nriv:
+        racc = acc[ridx]
+        has_down_river = river[np.maximum(down[ridx], 1) - 1] & (down[ridx] > 0)
+        # mid-sized river nodes with a downstream river node, one per downstream node
+        cand = np.nonzero(has_down_river & (racc >= np.quantile(racc, 0.5)))[0]
+        pick, used = [], set()
+        for c in cand[np.argsort(u01(seed, 80, rg[cand]))]:
+            if int(down[ridx][c]) not in used:
+                pick.append(int(c))
+                used.add(int(down[ridx][c]))
+            if len(pick) == reservoirs:
+                break
+        reservoir_river_indices = np.sort(np.array(pick, dtype=np.int64)) + 1
+        nres = len(reservoir_river_indices)
+        k = np.arange(nres)
+        rid = rg[reservoir_river_indices - 1]
+        F["res_area"] = 1.0e6 * (0.5 + u01(seed, 81, rid))
+        # outflow types cycle: simple, modified_puls, free_weir, simple + observed outflow
+        typ = np.array([4.0, 3.0, 2.0, 4.0])[k % 4]
+        F["res_outflow_curve_type"] = typ
+        F["res_maximum_storage"] = F["res_area"] * 40.0
+        F["res_threshold"] = np.where(typ == 2.0, 9.5, 0.0)
+        F["res_rating_curve_coefficient"] = np.where(typ == 3.0, 8.0, 12.0) * (0.8 + 0.4 * u01(seed, 82, rid))
+        F["res_rating_curve_exponent"] = np.full(nres, 1.5)
+        F["res_maximum_release"] = np.full(nres, 24.0)
+        F["res_demand"] = 0.5 + u01(seed, 83, rid)
+        F["res_target_minimum_fraction"] = np.full(nres, 0.075)
+        F["res_target_full_fraction"] = np.full(nres, 0.75)
+        F["res_waterlevel"] = np.where(typ == 4.0, 30.0, 10.0)
+        F["res_storage"] = F["res_area"] * F["res_waterlevel"]   # initialize_storage, linear
+        F["res_outflow_obs"] = np.where(k % 4 == 3, 0.8, np.nan)
+        F["res_external_inflow"] = np.where(k % 2 == 0, -0.1, 0.05)
+        F["res_precipitation"] = np.full(nres, 2.0e-8)
+        F["res_evaporation"] = np.full(nres, 1.0e-8)
+        for name in ("res_inflow_overland", "res_inflow_subsurface", "res_outflow"):
+            F[name] = np.zeros(nres)
+
+    cfg = dict(n=n, nriv=nriv, nres=nres, n_layers=N, N=N, gash=int(dt >= 23 * 3600.0), has_lai=1,
                snow=int(snow), glacier=int(glacier),
                soil_infiltration_reduction=int(soil_infiltration_reduction),
                kv_profile=kv_profile, adaptive=int(adaptive), nthreads=nthreads,
+               snow_transport=int(snow_transport),
                land_streamorder_min=5, river_streamorder_min=6, dt_land=3600.0, dt_river=900.0,
                dt_ssf=86400.0, ssf_alpha_coefficient=1.0, dt=dt,
                kin_wave_min_flow_qroot=1e-30 ** 0.2)
     domain = dict(d1=d1, d2=d2, indices=indices, ldd=ldd, river_land_indices=river_land_indices,
-                  down=down, gid=gid, upstream_cells=acc)
+                  down=down, gid=gid, upstream_cells=acc,
+                  reservoir_river_indices=reservoir_river_indices)
     return cfg, domain, F
 
 
