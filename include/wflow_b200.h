@@ -74,6 +74,15 @@ typedef struct {
   int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (8)    */
   int32_t snow_gravitational_transport; /* snow_gravitational_transport__flag: lateral snow
                                   transport between snow and glacier model     sbm.jl:98-100 */
+  /* river_routing = "local_inertial" (config_structure.jl; surface_staggered_scheme.jl): the
+   * river flow of update_river_flow_model! on the staggered grid instead of the kinematic wave */
+  int32_t river_routing;       /* 0 kinematic_wave, 1 local_inertial                           */
+  int32_t li_froude_limit;     /* river_water_flow__froude_limit_flag                          */
+  int32_t li_ghost_nodes;      /* 1: every pit drains to a ghost node (the model), 0: it has no
+                                  leaving edge (the reference's unit tests)                    */
+  int32_t reserved_;
+  double li_alpha;             /* river_local_inertial_flow__alpha_coefficient (0.7)           */
+  double li_h_thresh;          /* river_water_flow_threshold__depth (1e-3 m)                   */
 } WflowB200Config;
 
 /* The drainage network as the Julia model holds it (network.jl:48-81,175-208). */
@@ -191,7 +200,11 @@ int32_t wflowb200_update_lateral_inflow_river(WflowB200* h);
 int32_t wflowb200_update_inflow_reservoir(WflowB200* h);
 /* update_river_flow_model!(river, domain, clock, dt), incl. the reservoirs on the river
  * (update_reservoir_model! reservoir.jl:585-634: simple, modified_puls, free_weir without a
- * linked lower reservoir, observed outflow; linear storage curve)    surface_kinwave.jl:613-662 */
+ * linked lower reservoir, observed outflow; linear storage curve)    surface_kinwave.jl:613-662
+ * river_routing = 1: update_river_flow_model!(::RiverFlowModel{<:LocalInertial}) -- adaptive
+ * sub-steps dt_s = alpha min(L / sqrt(g h)), edge flow, reservoirs, node depth and storage, all
+ * sub-steps of the model step inside ONE persistent kernel   surface_staggered_scheme.jl:326-383,
+ * 627-661, 723-759, 800-838, 1004-1020; surface_process.jl:88-115 */
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt);
 /* update_total_water_storage!(land, domain, routing)                          sbm.jl:143-182 */
 int32_t wflowb200_update_total_water_storage(WflowB200* h);
@@ -199,7 +212,9 @@ int32_t wflowb200_update_total_water_storage(WflowB200* h);
  * on the device                                                          sbm_model.jl:60-92 */
 int32_t wflowb200_update_model(WflowB200* h, double dt);
 /* Self-test of the device arithmetic the kernels are built on (csrc/device_math.cuh), over n
- * pseudo-random arguments: out6 = { 0, 0, max relative difference of pow(x, c) = exp(c log x)
+ * pseudo-random arguments: out6 = { max relative difference of the remaining store and of the
+ * summed flux between the loop engine's tracked-power trips and the reference loop
+ * (soil_process.jl:74-90), max relative difference of pow(x, c) = exp(c log x)
  * against libdevice's pow for x in (0, 1], c in [1, 40], max ulp distance of the guard-free
  * division vs IEEE `/`, of the branch-free Julia min/max vs their definition, max |difference|
  * of cld(x, 2e-4) vs Julia's formula }. No handle needed. */

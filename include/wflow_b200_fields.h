@@ -15,6 +15,10 @@
  *   lateral_subsurface_flow.jl:2-54, RechargeVariables boundary_conditions.jl:204-213;
  *   OverLandFlowVariables routing/surface/surface_kinwave.jl:154-178, LandFlowBC :181-185;
  *   RiverFlowVariables :5-29, RiverFlowBC routing/surface/surface_flow.jl:9-34;
+ *   RiverFlowStaggeredParameters / Variables routing/surface/surface_staggered_scheme.jl:1-40,
+ *   157-186 (li_*: local-inertial river flow; edge i is the edge leaving node i, so the edge
+ *   arrays are river-sized and riv_q holds the edge discharge; li_ghost_h: water depth of the
+ *   ghost node downstream of a pit, riverdepth_bc);
  *   ReservoirParameters routing/surface/reservoir.jl:5-44, ReservoirVariables :200-217,
  *   ReservoirBC :251-272 (res_outflow_curve_type holds ReservoirOutflowType as a number:
  *   2 free_weir, 3 modified_puls, 4 simple).
@@ -82,6 +86,9 @@
   X(riv_actual_external_abstraction_average, 3) X(riv_inwater, 3) X(riv_q, 3) \
   X(riv_qlat, 3) X(riv_qin, 3) X(riv_qin_cumulative, 3) X(riv_qin_average, 3) \
   X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3) \
+  X(li_zb, 3) X(li_zb_at_edge, 3) X(li_mannings_n_sq_at_edge, 3) X(li_flow_length_at_edge, 3) \
+  X(li_flow_width_at_edge, 3) X(li_ghost_h, 3) X(li_error, 3) X(li_zs_at_edge, 3) \
+  X(li_water_depth_at_edge, 3) \
   X(res_area, 4) X(res_outflow_curve_type, 4) X(res_maximum_storage, 4) X(res_threshold, 4) \
   X(res_rating_curve_coefficient, 4) X(res_rating_curve_exponent, 4) X(res_maximum_release, 4) \
   X(res_demand, 4) X(res_target_minimum_fraction, 4) X(res_target_full_fraction, 4) \

@@ -32,7 +32,8 @@ class _Net(C.Structure):
     _fields_ = [("n", C.c_int64), ("up_ptr", C.c_void_p), ("up_idx", C.c_void_p),
                 ("n_levels", C.c_int64), ("level_ptr", C.c_void_p), ("level_sub", C.c_void_p),
                 ("n_sub", C.c_int64), ("sub_ptr", C.c_void_p), ("sub_nodes", C.c_void_p),
-                ("sub_pos", C.c_void_p), ("down", C.c_void_p), ("order", C.c_void_p)]
+                ("sub_pos", C.c_void_p), ("down", C.c_void_p), ("order", C.c_void_p),
+                ("in_ptr", C.c_void_p), ("in_idx", C.c_void_p)]
 
 
 class _Cfg(C.Structure):
@@ -40,6 +41,8 @@ class _Cfg(C.Structure):
                 ("gash", C.c_int32), ("has_lai", C.c_int32), ("snow", C.c_int32),
                 ("glacier", C.c_int32), ("soil_infiltration_reduction", C.c_int32),
                 ("kv_profile", C.c_int32), ("adaptive", C.c_int32), ("snow_transport", C.c_int32),
+                ("river_routing", C.c_int32), ("li_froude_limit", C.c_int32),
+                ("li_ghost_nodes", C.c_int32), ("li_alpha", C.c_double), ("li_h_thresh", C.c_double),
                 ("nthreads", C.c_int32),
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
                 ("ssf_alpha_coefficient", C.c_double)]
@@ -71,6 +74,12 @@ def lib(variant: str = ""):
             getattr(L, f).restype = None
         L.wfo_kinwave_river_update.argtypes = [C.c_void_p, C.c_double]
         L.wfo_kinwave_river_update.restype = None
+        L.wfo_li_stable_timestep.argtypes = [C.c_void_p]
+        L.wfo_li_stable_timestep.restype = C.c_double
+        for f in ("wfo_li_update_river_channel_flow", "wfo_li_update_bc_reservoir_model",
+                  "wfo_li_update_water_depth_and_storage"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_double]
+            getattr(L, f).restype = None
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.wfo_get_stats.restype = None
         L.wfo_set_num_threads.argtypes = [C.c_int]
@@ -125,7 +134,7 @@ def field_table():
 # lateral_subsurface_flow.jl:9-38, boundary_conditions.jl:204-213, surface_kinwave.jl:5-29,
 # 154-185, surface_flow.jl:9-34); every other field starts as MISSING_VALUE (NaN).
 ZERO_DEFAULTS = (
-    "snow_in", "snow_out", "canopy_storage", "waterdepth_river", "unsaturated_store_depth", "total_storage",
+    "li_error", "li_zs_at_edge", "li_water_depth_at_edge", "snow_in", "snow_out", "canopy_storage", "waterdepth_river", "unsaturated_store_depth", "total_storage",
     "ssf_exfiltwater_cumulative", "ssf_exfiltwater_average", "ssf_q_cumulative", "ssf_q_average",
     "ssf_q_in_cumulative", "ssf_q_in_average", "ssf_to_river_cumulative", "ssf_to_river_average",
     "ssf_q_net_cumulative", "ssf_q_net_average", "recharge_flux", "recharge_flux_cumulative",
@@ -179,8 +188,11 @@ class OracleModel:
         nres = int(cfg.get("nres", 0))
         c.n, c.nriv, c.N, c.nres = n, nriv, N, nres
         for k in ("gash", "has_lai", "snow", "glacier", "soil_infiltration_reduction",
-                  "kv_profile", "adaptive", "snow_transport"):
+                  "kv_profile", "adaptive", "snow_transport", "river_routing", "li_froude_limit",
+                  "li_ghost_nodes"):
             setattr(c, k, int(cfg.get(k, 0)))
+        c.li_alpha = float(cfg.get("li_alpha", 0.7))
+        c.li_h_thresh = float(cfg.get("li_h_thresh", 1.0e-3))
         c.nthreads = int(cfg.get("nthreads", 0))
         c.dt_land = float(cfg.get("dt_land", 3600.0))
         c.dt_river = float(cfg.get("dt_river", 900.0))
@@ -226,6 +238,11 @@ class OracleModel:
             else:
                 arrs["down"] = np.full(max(int(s.n), 1), -1, dtype=np.int64)
             arrs["order"] = np.asarray(net["order"], dtype=np.int64) - 1
+            dn = arrs["down"][:int(s.n)]            # in-neighbours by node id (full graph)
+            src = np.nonzero(dn >= 0)[0]
+            o = np.argsort(dn[src], kind="stable")
+            arrs["in_ptr"] = np.concatenate([[0], np.cumsum(np.bincount(dn[src], minlength=int(s.n)))])
+            arrs["in_idx"] = src[o]
             s.n_levels = len(net["order_of_subdomains"])
             s.n_sub = len(net["order_subdomain"])
             for k, a in arrs.items():

@@ -98,6 +98,13 @@
   X(riv_actual_external_abstraction_average, 3) X(riv_inwater, 3) X(riv_q, 3) \
   X(riv_qlat, 3) X(riv_qin, 3) X(riv_qin_cumulative, 3) X(riv_qin_average, 3) \
   X(riv_q_cumulative, 3) X(riv_q_average, 3) X(riv_storage, 3) X(riv_h, 3) \
+  /* local-inertial river flow on the staggered grid (surface_staggered_scheme.jl:1-40,157-186): \
+   * edge i is the edge leaving node i (init_staggered_river_flow :225-233), so the edge \
+   * arrays are river-sized; riv_q / riv_q_cumulative / riv_q_average hold the edge discharge; \
+   * li_ghost_h: water depth of the ghost node downstream of a pit (riverdepth_bc) */ \
+  X(li_zb, 3) X(li_zb_at_edge, 3) X(li_mannings_n_sq_at_edge, 3) X(li_flow_length_at_edge, 3) \
+  X(li_flow_width_at_edge, 3) X(li_ghost_h, 3) X(li_error, 3) X(li_zs_at_edge, 3) \
+  X(li_water_depth_at_edge, 3) \
   /* reservoirs (routing/surface/reservoir.jl:5-44 parameters, 200-217 variables, 251-272 BC); \
    * res_outflow_curve_type holds ReservoirOutflowType as a number (2 free_weir, 3 \
    * modified_puls, 4 simple) */ \
@@ -126,6 +133,8 @@ typedef struct {
   const int64_t* sub_pos;     /* subdomain_indices[m] (toposort position n)           */
   const int64_t* down;        /* outneighbors(graph, v): downstream node or -1 (pit)  */
   const int64_t* order;       /* network.order (topological_sort_by_dfs), node ids    */
+  const int64_t* in_ptr;      /* inneighbors(graph, v) by NODE id, CSR (n+1), ascending */
+  const int64_t* in_idx;
 } wfo_network;
 
 typedef struct {
@@ -138,6 +147,10 @@ typedef struct {
   int32_t kv_profile;         /* 0 exponential, 1 exponential_constant, 2 layered, 3 layered_exponential */
   int32_t adaptive;           /* kinematic_wave__adaptive_time_step_flag              */
   int32_t snow_transport;     /* snow_gravitational_transport__flag                   */
+  int32_t river_routing;      /* 0 kinematic_wave, 1 local_inertial                   */
+  int32_t li_froude_limit;    /* river_water_flow__froude_limit_flag                  */
+  int32_t li_ghost_nodes;     /* pits drain to a ghost node (the model; 0: unit tests) */
+  double li_alpha, li_h_thresh; /* river_local_inertial_flow__alpha_coefficient, river_water_flow_threshold__depth */
   int32_t nthreads;           /* OpenMP threads (0 = default)                         */
   double dt_land, dt_river, dt_ssf, ssf_alpha_coefficient;
 } wfo_config;
@@ -191,6 +204,12 @@ void wfo_update_lateral_inflow_overland(wfo_model*);
 void wfo_update_lateral_inflow_river(wfo_model*);
 void wfo_update_inflow_reservoir(wfo_model*);                  /* surface_kinwave.jl:772-805 */
 void wfo_kinwave_river_update(wfo_model*, double dt_s);        /* test hook: one sub-step    */
+/* local-inertial river flow: stable_timestep (:1004-1020), update_river_channel_flow! (:326-383),
+ * update_bc_reservoir_model! (:627-661), update_water_depth_and_storage! (:723-759) */
+double wfo_li_stable_timestep(wfo_model*);
+void wfo_li_update_river_channel_flow(wfo_model*, double dt_s);
+void wfo_li_update_bc_reservoir_model(wfo_model*, double dt_s);
+void wfo_li_update_water_depth_and_storage(wfo_model*, double dt_s);
 void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182 */
 void wfo_update_model(wfo_model*, double dt);                  /* sbm_model.jl:60-92 */
 void wfo_update_diagnostic_vars(wfo_model*);                   /* soil.jl:1400-1436 */

@@ -699,6 +699,10 @@ void wfo_update_inflow_reservoir(wfo_model* m) {
     const int64_t li = m->river_land_indices[m->reservoir_river_indices[i]];
     m->res_inflow_overland[i] = m->olf_q_average[li];
     m->res_inflow_subsurface[i] = m->ssf_q_average[li];
+    if (m->cfg.river_routing == 1) {  /* staggered schemes: to_river is included  :303-321 */
+      m->res_inflow_overland[i] = m->olf_q_average[li] + m->olf_to_river_average[li];
+      m->res_inflow_subsurface[i] = m->ssf_q_average[li] + m->ssf_to_river_average[li];
+    }
   }
 }
 
@@ -757,8 +761,11 @@ void wfo_update_lateral_inflow_river(wfo_model* m) {
   }
 }
 
+static void li_update_river_flow_model(wfo_model* m, double dt);
+
 /* surface_kinwave.jl:613-662 */
 void wfo_update_river_flow_model(wfo_model* m, double dt) {
+  if (m->cfg.river_routing == 1) { li_update_river_flow_model(m, dt); return; }
   const int64_t n = m->cfg.nriv;
   PFOR for (int64_t i = 0; i < n; ++i) {
     m->riv_qlat[i] = m->riv_inwater[i] / m->riv_flow_length[i];
@@ -791,6 +798,155 @@ void wfo_update_river_flow_model(wfo_model* m, double dt) {
     m->riv_qin_average[i] = m->riv_qin_cumulative[i] / dt;
   }
   for (int64_t i = 0; i < m->cfg.nres; ++i) {  /* average_reservoir_vars!  surface_kinwave.jl:244-258 */
+    m->res_outflow_average[i] = m->res_outflow_cumulative[i] / dt;
+    m->res_inflow_average[i] = m->res_inflow_cumulative[i] / dt;
+    m->res_actual_external_abstraction_average[i] =
+        m->res_actual_external_abstraction_cumulative[i] / dt;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* local-inertial river flow (no floodplain)        routing/surface/surface_staggered_scheme.jl */
+/* ---------------------------------------------------------------------------------------- */
+#define WFO_G 9.80665 /* GRAVITATIONAL_ACCELERATION  Wflow.jl:77 */
+
+/* local_inertial_flow                                           surface_process.jl:88-115 */
+static double local_inertial_flow(double q0, double zs0, double zs1, double hf, double A, double R,
+                                  double length, double mannings_n_sq, int froude_limit, double dt) {
+  const double slope = (zs1 - zs0) / length;
+  const double pow_R = cbrt(R * R * R * R);
+  double q = ((q0 - WFO_G * A * dt * slope) /
+              (1.0 + WFO_G * dt * mannings_n_sq * fabs(q0) / (pow_R * A)));
+  const double fr = ((q / A) / sqrt(WFO_G * hf)) * (double)froude_limit;
+  if ((fabs(fr) > 1.0) && (q > 0.0)) q = sqrt(WFO_G * hf) * A;
+  if ((fabs(fr) > 1.0) && (q < 0.0)) q = -sqrt(WFO_G * hf) * A;
+  return q;
+}
+
+/* node the edge leaving node i ends in: a river node, -1 (no edge), or -2 (ghost node of a pit) */
+static int64_t li_dst(const wfo_model* m, int64_t i) {
+  const int64_t d = m->river.down[i];
+  if (d >= 0) return d;
+  return m->cfg.li_ghost_nodes ? -2 : -1;
+}
+
+/* stable_timestep(::RiverFlowModel{<:LocalInertial})   surface_staggered_scheme.jl:1004-1020 */
+double wfo_li_stable_timestep(wfo_model* m) {
+  double dt_min = INFINITY;
+  for (int64_t i = 0; i < m->cfg.nriv; ++i) {
+    const double dt = m->cfg.li_alpha * m->riv_flow_length[i] / sqrt(WFO_G * m->riv_h[i]);
+    dt_min = dt < dt_min ? dt : dt_min;
+  }
+  return isinf(dt_min) ? 60.0 : dt_min;
+}
+
+/* update_river_channel_flow!(::RiverFlowModel{<:LocalInertial})            :326-383 */
+void wfo_li_update_river_channel_flow(wfo_model* m, double dt) {
+  PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) {
+    const int64_t d = li_dst(m, i);
+    if (d == -1) continue;                                   /* no edge leaves this node */
+    if (m->cfg.nres > 0 && m->riv_reservoir[i] >= 0) continue; /* not in active_e          */
+    const double q_previous = m->riv_q[i];
+    const double zs_src = m->li_zb[i] + m->riv_h[i];
+    const double h_dst = d == -2 ? m->li_ghost_h[i] : m->riv_h[d];
+    const double zs_dst = (d == -2 ? m->li_zb[i] : m->li_zb[d]) + h_dst;
+    const double zs_at_edge = jl_max(zs_src, zs_dst);
+    const double hf = zs_at_edge - m->li_zb_at_edge[i];
+    m->li_zs_at_edge[i] = zs_at_edge;
+    m->li_water_depth_at_edge[i] = hf;
+    const double w = m->li_flow_width_at_edge[i];
+    const double A = w * hf;
+    const double R = A / (2.0 * hf + w);
+    double q = hf > m->cfg.li_h_thresh
+                   ? local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R,
+                                         m->li_flow_length_at_edge[i],
+                                         m->li_mannings_n_sq_at_edge[i], m->cfg.li_froude_limit, dt)
+                   : 0.0;
+    if (m->riv_h[i] <= 0.0) q = jl_min(q, 0.0);
+    if (h_dst <= 0.0) q = jl_max(q, 0.0);
+    m->riv_q[i] = q;
+    m->riv_q_cumulative[i] += q * dt;
+  }
+}
+
+/* update_bc_reservoir_model!                                                :627-661 */
+void wfo_li_update_bc_reservoir_model(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->river;
+  for (int64_t v = 0; v < m->cfg.nres; ++v) {
+    const int64_t i = m->reservoir_river_indices[v];
+    double q_in = 0.0;  /* sum_at(q, edges_at_node.src[i]): edges entering the reservoir node */
+    for (int64_t u = nw->in_ptr[i]; u < nw->in_ptr[i + 1]; ++u) q_in += m->riv_q[nw->in_idx[u]];
+    double inflow;
+    if (m->res_external_inflow[v] < 0.0) {
+      const double abstraction = jl_min(-m->res_external_inflow[v], (m->res_storage[v] / dt) * 0.98);
+      m->res_actual_external_abstraction_cumulative[v] += abstraction * dt;
+      inflow = -abstraction;
+    } else {
+      inflow = m->res_external_inflow[v];
+    }
+    const double net_inflow = q_in + m->res_inflow_overland[v] + m->res_inflow_subsurface[v] + inflow;
+    update_reservoir_model_i(m, v, net_inflow, dt);
+    m->riv_q[i] = m->res_outflow[v];
+    m->riv_q_cumulative[i] += m->riv_q[i] * dt;
+  }
+}
+
+/* update_water_depth_and_storage!(river_flow_model, domain, dt)            :723-759 */
+void wfo_li_update_water_depth_and_storage(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->river;
+  PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) {
+    if (m->cfg.nres > 0 && m->riv_reservoir[i] >= 0) continue;  /* not in active_n */
+    double q_src = 0.0;
+    for (int64_t u = nw->in_ptr[i]; u < nw->in_ptr[i + 1]; ++u) q_src += m->riv_q[nw->in_idx[u]];
+    const double q_dst = li_dst(m, i) == -1 ? 0.0 : 0.0 + m->riv_q[i];
+    m->riv_storage[i] += (q_src - q_dst + m->riv_inwater[i] - m->riv_abstraction[i]) * dt;
+    if (m->riv_storage[i] < 0.0) {
+      m->li_error[i] = m->li_error[i] + fabs(m->riv_storage[i]);
+      m->riv_storage[i] = 0.0;
+    }
+    double inflow;
+    if (m->riv_external_inflow[i] < 0.0) {
+      const double abstraction = jl_min(-m->riv_external_inflow[i], m->riv_storage[i] / dt * 0.80);
+      m->riv_actual_external_abstraction_cumulative[i] += abstraction * dt;
+      inflow = -abstraction;
+    } else {
+      inflow = m->riv_external_inflow[i];
+    }
+    m->riv_storage[i] += inflow * dt;
+    m->riv_h[i] = m->riv_storage[i] / (m->riv_flow_length[i] * m->riv_flow_width[i]);
+  }
+}
+
+/* update_river_flow_model!(::RiverFlowModel{<:AbstractStaggeredRoutingMethod})   :800-838 */
+static void li_update_river_flow_model(wfo_model* m, double dt) {
+  const int64_t n = m->cfg.nriv;
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {
+    m->res_inflow_cumulative[i] = 0.0;
+    m->res_actual_external_abstraction_cumulative[i] = 0.0;
+    m->res_outflow_cumulative[i] = 0.0;
+    m->res_actevap_cumulative[i] = 0.0;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->riv_q_cumulative[i] = 0.0;
+    m->riv_actual_external_abstraction_cumulative[i] = 0.0;
+  }
+  double t = 0.0;
+  m->substeps_river = 0;
+  while (t < dt) {
+    double dt_s = wfo_li_stable_timestep(m);
+    dt_s = check_timestepsize(dt_s, t, dt);
+    wfo_li_update_river_channel_flow(m, dt_s);
+    wfo_li_update_bc_reservoir_model(m, dt_s);
+    wfo_li_update_water_depth_and_storage(m, dt_s);
+    t += dt_s;
+    m->substeps_river++;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    m->riv_q_average[i] = m->riv_q_cumulative[i] / dt;
+    m->riv_actual_external_abstraction_average[i] =
+        m->riv_actual_external_abstraction_cumulative[i] / dt;
+  }
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {
     m->res_outflow_average[i] = m->res_outflow_cumulative[i] / dt;
     m->res_inflow_average[i] = m->res_inflow_cumulative[i] / dt;
     m->res_actual_external_abstraction_average[i] =

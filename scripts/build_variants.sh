@@ -8,15 +8,21 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 build() { # name, flags
   name=$1; shift
   d=_obj/variants/$name; mkdir -p $d
-  for f in api vertical routing; do $NV "$@" -c $f.cu -o $d/$f.o & done
+  for f in api vertical routing local_inertial; do $NV "$@" -c $f.cu -o $d/$f.o & done
   $NV -x cu -c network.cpp -o $d/network.o &
   wait
-  $NV -shared -o _obj/variants/lib_$name.so $d/api.o $d/vertical.o $d/routing.o $d/network.o
+  $NV -shared -o _obj/variants/lib_$name.so $d/api.o $d/vertical.o $d/routing.o $d/local_inertial.o $d/network.o
 }
 for v in "$@"; do
   case $v in
     mb3) build mb3 -DWFB_V_MINBLOCKS=3 ;;
     mb5) build mb5 -DWFB_V_MINBLOCKS=5 ;;
+    fused) build fused -DWFB_V_FUSED=1 ;;
+    slowtrips) build slowtrips -DWFB_ENGINE_FAST_TRIPS=0 ;;
+    a6) build a6 -DWFB_V_MINBLOCKS=6 ;;
+    a4) build a4 -DWFB_V_MINBLOCKS=4 ;;
+    c5) build c5 -DWFB_VC_MINBLOCKS=5 ;;
+    c3) build c3 -DWFB_VC_MINBLOCKS=3 ;;
     pf0) build pf0 -DWFB_V_PREFETCH=0 ;;
     pf1) build pf1 -DWFB_V_PREFETCH=1 ;;
     pf1mb5) build pf1mb5 -DWFB_V_PREFETCH=1 -DWFB_V_MINBLOCKS=5 ;;

@@ -458,6 +458,70 @@ def test_kinwave_river_update_routing_process_290_383():
     assert m.f["res_actevap_cumulative"][0] == approx(5.295387542208319e-6)
 
 
+def test_local_inertial_river_with_reservoir_routing_process_385_528():
+    """3-node graph 1 -> 2 -> 3, a simple reservoir on node 2: stable time step, channel flow at
+    the edges, reservoir boundary condition, water depth and storage -- each sub-step of the
+    local-inertial update as the reference's unit test checks it."""
+    L = orc.lib()
+
+    class G:
+        down = np.array([2, 3, 0])
+    river = dict(graph=G, order=np.array([1, 2, 3]), up_ptr=np.array([0, 0, 1, 2]),
+                 up_idx=np.array([1, 2]), order_of_subdomains=[np.array([1])],
+                 order_subdomain=[np.array([1, 2, 3])], subdomain_indices=[np.array([1, 2, 3])])
+
+    class G1:
+        down = np.array([0, 0, 0])
+    land = dict(graph=G1, order=np.array([1, 2, 3]), up_ptr=np.zeros(4, np.int64),
+                up_idx=np.zeros(0, np.int64), order_of_subdomains=[np.array([1])],
+                order_subdomain=[np.array([1, 2, 3])], subdomain_indices=[np.array([1, 2, 3])])
+    w = 94.73094177246094
+    f = dict(riv_inwater=[0.012816561479797707, 0.01544689027914484, -0.0004760637654763434],
+             riv_external_inflow=np.zeros(3), riv_abstraction=np.zeros(3),
+             li_zb=[315.1000061035156, 314.3999938964844, 278.8000183105469],
+             li_zb_at_edge=[315.1000061035156, 314.3999938964844, 0.0],
+             li_mannings_n_sq_at_edge=[0.0008999999597668652, 0.0008999999597668652, 0.0],
+             li_flow_length_at_edge=[831.578125, 1005.890625, 1.0],
+             li_flow_width_at_edge=[w, w, w], li_ghost_h=np.zeros(3),
+             riv_flow_width=[w, w, w], riv_flow_length=[603.34375, 1059.8125, 951.96875],
+             riv_h=[0.04484241735240722, 0.0, 0.07939389691400389],
+             riv_storage=[2562.9827873416416, 0.0, 7159.812778536053],
+             riv_q=[0.534560186001325, 0.0, 0.0],
+             river_land_indices=np.array([0, 1, 2]), reservoir_river_indices=np.array([1]),
+             res_external_inflow=[0.0], res_inflow_overland=[0.0],
+             res_inflow_subsurface=[0.04279912663469156],
+             res_precipitation=[2.0833332436504186e-10], res_evaporation=[5.324074170655674e-9],
+             res_area=[1.498462875e6], res_outflow_curve_type=[4.0],
+             res_maximum_release=[24.007999420166016], res_demand=[3.000999927520752],
+             res_target_minimum_fraction=[0.07482631504535675],
+             res_target_full_fraction=[0.7536525130271912], res_maximum_storage=[6.2e7],
+             res_waterlevel=[29.6558203236325], res_storage=[4.443814578263413e7],
+             res_outflow_obs=[np.nan])
+    f = {k: np.asarray(v, dtype=np.int64 if k.endswith("indices") else np.float64)
+         for k, v in f.items()}
+    m = orc.OracleModel(dict(n=3, nriv=3, nres=1, N=1, river_routing=1, li_froude_limit=1,
+                             li_ghost_nodes=0, li_alpha=1.0, li_h_thresh=0.001), f, land, river)
+    dt = L.wfo_li_stable_timestep(m.h)
+    assert dt == approx(909.829412320351)
+    L.wfo_li_update_river_channel_flow(m.h, dt)
+    assert m.f["li_zs_at_edge"][0] == approx(315.14484852086804)
+    assert m.f["li_water_depth_at_edge"][0] == approx(0.04484241735241312)
+    assert m.f["riv_q"][:2] == approx(np.array([0.534558444239785, 0.0]))
+    assert m.f["riv_q_cumulative"][:2] == approx(np.array([486.35699517356477, 0.0]))
+    L.wfo_li_update_bc_reservoir_model(m.h, dt)
+    assert m.f["riv_q"][1] == approx(3.0009999145276134)
+    assert m.f["riv_q"][1] == m.f["res_outflow"][0]
+    assert m.f["riv_q_cumulative"][1] == approx(2730.397988608082)
+    assert m.f["riv_q_cumulative"][1] == m.f["res_outflow_cumulative"][0]
+    assert m.f["res_storage"][0] == approx(4.443593370702217e7)
+    assert m.f["res_waterlevel"][0] == approx(29.654344093791327)
+    assert m.f["res_inflow_cumulative"][0] == approx(525.2968994074305)
+    assert m.f["res_actevap_cumulative"][0] == approx(4.843999273837613e-6)
+    L.wfo_li_update_water_depth_and_storage(m.h, dt)
+    assert m.f["riv_storage"] == approx(np.array([2088.286676767209, 0.0, 9889.777630328164]))
+    assert m.f["riv_h"] == approx(np.array([0.03653704705843743, 0.0, 0.10966599406601261]))
+
+
 def test_accucapacityflux_routing_process_255_288():
     """PCRaster accucapacity examples on a 6-node graph (lateral snow transport's engine)."""
     L = orc.lib()

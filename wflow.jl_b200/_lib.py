@@ -23,7 +23,10 @@ class Config(C.Structure):
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
                 ("ssf_alpha_coefficient", C.c_double), ("kin_wave_min_flow_qroot", C.c_double),
                 ("wave_piece_depth_land", C.c_int32), ("vertical_slices", C.c_int32),
-                ("unsat_inline_iters", C.c_int32), ("snow_gravitational_transport", C.c_int32)]
+                ("unsat_inline_iters", C.c_int32), ("snow_gravitational_transport", C.c_int32),
+                ("river_routing", C.c_int32), ("li_froude_limit", C.c_int32),
+                ("li_ghost_nodes", C.c_int32), ("reserved_", C.c_int32),
+                ("li_alpha", C.c_double), ("li_h_thresh", C.c_double)]
 
 
 class Domain(C.Structure):

@@ -129,6 +129,7 @@ struct Tuning {
   int fuse_surface = 1;       // overland + river in one kernel
   int river_share = 1, river_period = 3;  // warps of the surface kernel serving the river
   int use_graph = 1;          // vertical update as one CUDA graph launch
+  int run_engine = 1;         // 0: skip the loop engine (timing experiments; results invalid)
 };
 
 struct WflowB200 {
@@ -141,6 +142,10 @@ struct WflowB200 {
   DomainDev* snow_net = nullptr;     // reservoir cut, for lateral snow transport
   int grid_snow = 0;
   size_t smem_snow = 0;
+  int grid_li = 0;                   // local-inertial river flow: co-resident CTAs
+  unsigned* d_li_barrier = nullptr;  // {arrivals, generation}
+  unsigned long long* d_li_dt = nullptr;
+  int* d_li_substeps = nullptr;
   DevFields f{};
   KCfg kc{};
   double* pool = nullptr;  // one HBM allocation holding every Float64 field
@@ -541,7 +546,8 @@ static int32_t launch_vertical(WflowB200* h, double dt) {
   auto issue_phase = [&](int phase) {
     return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
                                  h->slice_tile_begin.data(), h->d_tile_prio, h->d_tile_order,
-                                 h->engine_grid, phase, h->stream, h->side_stream, h->v_ev);
+                                 h->engine_grid, phase, h->tune.run_engine != 0, h->stream,
+                                 h->side_stream, h->v_ev);
   };
   if (transport) {
     // interception + snow, lateral_snow_transport! over the land network (sbm.jl:98-100), then
@@ -689,6 +695,11 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     launch_fill(p, (long long)slots_of(h, kind) * layers_of(h, kind), v, h->stream);
   };
   fill(h->f.canopy_storage, 0, 0.0);            // canopy.jl:11
+  fill(h->f.snow_in, 0, 0.0);                   // snow.jl:17-19
+  fill(h->f.snow_out, 0, 0.0);
+  fill(h->f.li_error, 3, 0.0);                  // surface_staggered_scheme.jl:181-185
+  fill(h->f.li_zs_at_edge, 3, 0.0);
+  fill(h->f.li_water_depth_at_edge, 3, 0.0);
   fill(h->f.waterdepth_river, 0, 0.0);          // runoff.jl:26
   fill(h->f.unsaturated_store_depth, 0, 0.0);   // soil.jl:71
   fill(h->f.total_storage, 0, 0.0);             // soil.jl:77
@@ -784,6 +795,12 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       }
       TRY_CREATE(upload_i32(riv_res, &h->f.riv_reservoir, 0));
       TRY_CREATE(upload_i32(res_land, &h->f.res_land_slot, 0));
+      {
+        std::vector<int64_t> res_riv_slot(h->nres);
+        for (int i = 0; i < h->nres; ++i)
+          res_riv_slot[i] = h->river.nw.slot_of[dom->reservoir_river_indices[i] - 1];
+        TRY_CREATE(upload_i32(res_riv_slot, &h->f.res_river_slot, 0));
+      }
       TRY_CREATE(upload_i32(ident, &h->res_ident, 0));
     }
   }
@@ -852,6 +869,28 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->kc.soil_infiltration_reduction = cfg->soil_infiltration_reduction;
   h->kc.kv_profile = cfg->kv_profile;
   h->kc.qroot = h->cfg.kin_wave_min_flow_qroot;
+  h->kc.river_routing = cfg->river_routing;
+  if (cfg->river_routing == 1) {   // the staggered grid by river slot (network.jl:281-293)
+    const Network& rn = h->river.nw;
+    std::vector<int64_t> dst(std::max(h->nrs, 1), -1), in_ptr(h->nriv + 1, 0), in_idx;
+    for (int p = 0; p < h->nriv; ++p) {
+      const int64_t v = rn.perm[p] - 1;
+      dst[p] = rn.down[v] > 0 ? rn.slot_of[rn.down[v] - 1] : (cfg->li_ghost_nodes ? -2 : -1);
+      for (int64_t e = rn.in_ptr[v]; e < rn.in_ptr[v + 1]; ++e)   // ascending source node id
+        in_idx.push_back(rn.slot_of[rn.in_idx[e] - 1]);
+      in_ptr[p + 1] = (int64_t)in_idx.size();
+    }
+    TRY_CREATE(upload_i32(dst, &h->f.li_dst_slot, 0));
+    TRY_CREATE(upload_i32(in_ptr, &h->f.li_in_ptr, 0));
+    TRY_CREATE(upload_i32(in_idx, &h->f.li_in_idx, 0));
+    TRY_CREATE(cudaMalloc((void**)&h->d_li_barrier, 2 * sizeof(unsigned)));
+    TRY_CREATE(cudaMemset(h->d_li_barrier, 0, 2 * sizeof(unsigned)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_li_dt, 2 * sizeof(unsigned long long)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_li_substeps, sizeof(int)));
+    TRY_CREATE(cudaMemset(h->d_li_substeps, 0, sizeof(int)));
+    h->grid_li = li_max_grid(cfg->device);
+    if (h->grid_li <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
+  }
 
   // persistent cooperative grids: as many co-resident CTAs as the device holds
   h->smem_olf = wave_smem(0, h->land.dev.max_inlets);
@@ -868,7 +907,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->smem_surface = surface_smem(h->land.dev.max_inlets, h->river.dev.max_inlets,
                                  &h->smem_surface_per_warp);
   h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
-  h->fuse_surface = h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive;
+  h->fuse_surface = h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive && cfg->river_routing == 0;
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -887,6 +926,8 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.nlayers_kv); cudaFree(h->f.olf_newton_trace); cudaFree(h->f.riv_newton_trace);
   cudaFree(h->f.riv_reservoir); cudaFree(h->f.res_land_slot); cudaFree(h->res_ident);
+  cudaFree(h->f.res_river_slot); cudaFree(h->f.li_dst_slot); cudaFree(h->f.li_in_ptr);
+  cudaFree(h->f.li_in_idx); cudaFree(h->d_li_barrier); cudaFree(h->d_li_dt); cudaFree(h->d_li_substeps);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
   cudaFree(h->d_ring); cudaFree(h->d_lai_table); cudaFreeHost(h->h_out_pinned);
@@ -1221,6 +1262,20 @@ int32_t wflowb200_update_inflow_reservoir(WflowB200* h) {
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
   WFB_ENTER(h);
   if (h->nriv == 0) return WFLOWB200_OK;
+  if (h->cfg.river_routing == 1) {  // local-inertial river flow: the whole model step in one kernel
+    LiLaunch w{};
+    w.dt = dt;
+    w.alpha = h->cfg.li_alpha > 0.0 ? h->cfg.li_alpha : 0.7;
+    w.h_thresh = h->cfg.li_h_thresh;
+    w.froude_limit = h->cfg.li_froude_limit;
+    w.barrier = h->d_li_barrier;
+    w.dt_bits = h->d_li_dt;
+    w.err = h->d_err;
+    w.substeps = h->d_li_substeps;
+    w.grid = std::max(1, std::min(h->grid_li, (h->nriv + 255) / 256));
+    return check_launch(h, launch_local_inertial_river(h->f, h->kc, w, h->stream),
+                        "update_river_flow_model (local inertial)");
+  }
   if (h->cfg.adaptive)
     return run_wave_adaptive(h, h->river, dt, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
                              [&](const WaveLaunch& w) {
@@ -1456,6 +1511,10 @@ int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value) {
   else if (k == "surface_river_share") { if (value >= 1 && value < t.river_period) t.river_share = value; }
   else if (k == "surface_river_period") { if (value >= 2 && value > t.river_share) t.river_period = value; }
   else if (k == "vertical_graph") t.use_graph = value != 0;
+  else if (k == "vertical_engine") {   // timing experiments only: 0 leaves suspended cells unfinished
+    t.run_engine = value != 0;
+    if (h->v_graph) { cudaGraphExecDestroy(h->v_graph); h->v_graph = nullptr; }
+  }
   else if (k == "kinwave_root_each_substep") h->kc.kw_root_each_substep = value != 0;
   else return fail(h, WFLOWB200_ERR_ARG, "unknown option: " + k);
   return WFLOWB200_OK;
@@ -1498,6 +1557,11 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
   out->newton_calls_river = (int64_t)rs.newton_calls_river;
   out->newton_iters_river = (int64_t)rs.newton_iters_river;
   out->newton_maxit_river = (int64_t)rs.newton_maxit_river;
+  if (h->d_li_substeps) {
+    int cnt = 0;
+    cudaMemcpy(&cnt, h->d_li_substeps, sizeof(int), cudaMemcpyDeviceToHost);
+    h->sub_river = cnt;
+  }
   out->substeps_land = h->sub_land; out->substeps_river = h->sub_river;
   out->substeps_ssf = h->sub_ssf;
   out->wave_levels_land = h->land.nw.n_wave_levels;

@@ -31,7 +31,9 @@ struct UnsatWork {
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, const int* slice_tile_begin,
                           unsigned* tile_prio, int32_t* tile_order, int engine_grid, int phase,
-                          cudaStream_t s, cudaStream_t const* side, cudaEvent_t const* ev);
+                          bool run_engine, cudaStream_t s, cudaStream_t const* side,
+                          cudaEvent_t const* ev);
+// run_engine = false leaves the suspended cells unfinished: timing experiments only
 // phase: 0 the whole update; 1 interception + snow only, 2 the rest (lateral snow transport runs
 // between the two: launch_snow_transport)
 // self-test of device_math.cuh: out[6] (device, zeroed) receives bit patterns of the maxima
@@ -107,6 +109,20 @@ int launch_subsurface_wave(const DevFields& f, const KCfg& c, const DevNet& net,
 // water over the land network + flux_in!; kind 3 of wave_smem / wave_max_grid
 int launch_snow_transport(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
                           cudaStream_t s);
+// Local-inertial river flow (local_inertial.cu): all sub-steps of a model step in one persistent
+// kernel with grid barriers.
+struct LiLaunch {
+  double dt;                    // model time step
+  double alpha, h_thresh;       // stability coefficient, depth threshold for flow at an edge
+  int froude_limit;
+  unsigned* barrier;            // device: {arrivals, generation}
+  unsigned long long* dt_bits;  // device: 2 slots for the minimum Courant step (bit patterns)
+  unsigned* err;                // device: the handle's error word (bounded barrier waits)
+  int* substeps;                // device: number of sub-steps of the model step (out)
+  int grid;                     // co-resident CTAs
+};
+int li_max_grid(int device);
+int launch_local_inertial_river(const DevFields& f, const KCfg& c, const LiLaunch& w, cudaStream_t s);
 int launch_lateral_inflow_overland(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_lateral_inflow_river(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_inflow_reservoir(const DevFields& f, const KCfg& c, cudaStream_t s);

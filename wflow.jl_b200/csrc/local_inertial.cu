@@ -1,0 +1,244 @@
+// local_inertial.cu -- local-inertial river flow on the staggered grid (sm_100a), the river part
+// of BASELINE config #4: update_river_flow_model!(::RiverFlowModel{<:LocalInertial})
+// (routing/surface/surface_staggered_scheme.jl:800-838) with
+//   stable_timestep                     :1004-1020   dt_s = alpha min_i L_i / sqrt(g h_i)
+//   update_river_channel_flow!          :326-383     edge flow, local_inertial_flow
+//                                                     (surface_process.jl:88-115)
+//   update_bc_reservoir_model!          :627-661     reservoirs (their node leaves the active
+//                                                     set, the edge carries the outflow)
+//   update_water_depth_and_storage!     :723-759     node storage and depth
+// All reference paths are under /root/reference/Wflow/src.
+//
+// The scheme is explicit: every sub-step is edge-parallel, then node-parallel, and needs ONE
+// global number first (the minimum Courant step of all nodes) -- a few hundred sub-steps per
+// model day with a few microseconds of work each. Launching three kernels and reading the time
+// step back per sub-step would cost more than the arithmetic, so the WHOLE model step runs in
+// one persistent kernel: the grid is co-resident, phases are separated by a grid barrier, the
+// minimum is an atomicMin on the bit pattern (positive doubles order like integers), and every
+// thread evaluates the `while t < dt` loop (surface_staggered_scheme.jl:816-821) identically.
+// River state is a few MB and stays in L2; values written by other CTAs are read past the L1.
+//
+// Edge i is the edge leaving node i (init_staggered_river_flow, :225-233), so edge arrays are
+// river-sized; a pit drains into a ghost node whose depth is the boundary condition
+// li_ghost_h and whose bed level equals the pit's (get_river_parameters :62-72).
+#include <algorithm>
+#include "device_math.cuh"
+#include "kernels.cuh"
+#include "model.cuh"
+#include "reservoir.cuh"
+
+namespace wfb {
+
+namespace {
+
+constexpr double kG = 9.80665;  // GRAVITATIONAL_ACCELERATION  Wflow.jl:77
+constexpr int kLiBlock = 256;
+
+__device__ __forceinline__ unsigned li_ld_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid barrier (all CTAs are resident). bar[0]: arrivals, bar[1]: generation. Bounded: a grid that
+// is not co-resident raises the handle's error word instead of hanging (api.cu: check_device_error).
+__device__ __forceinline__ bool li_grid_barrier(unsigned* bar, unsigned n_blocks, unsigned& gen,
+                                                unsigned* err) {
+  __shared__ int ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ok = 1;
+    __threadfence();
+    if (atomicAdd(&bar[0], 1u) == n_blocks - 1u) {
+      atomicExch(&bar[0], 0u);
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      unsigned polls = 0;
+      while (li_ld_u32(&bar[1]) == gen) {
+        if ((++polls & 1023u) == 0u) {
+          if (polls >= (1u << 24)) { atomicOr(err, 2u); ok = 0; break; }
+          if (li_ld_u32(err) != 0u) { ok = 0; break; }
+        }
+      }
+    }
+    __threadfence();
+  }
+  ++gen;
+  __syncthreads();
+  return ok != 0;
+}
+
+// local_inertial_flow                                             surface_process.jl:88-115
+__device__ __forceinline__ double local_inertial_flow(double q0, double zs0, double zs1, double hf,
+                                                      double A, double R, double length,
+                                                      double mannings_n_sq, int froude_limit,
+                                                      double dt) {
+  const double slope = (zs1 - zs0) / length;
+  const double pow_R = cbrt(R * R * R * R);
+  double q = ((q0 - kG * A * dt * slope) / (1.0 + kG * dt * mannings_n_sq * fabs(q0) / (pow_R * A)));
+  const double fr = ((q / A) / sqrt(kG * hf)) * (double)froude_limit;
+  if ((fabs(fr) > 1.0) && (q > 0.0)) q = sqrt(kG * hf) * A;
+  if ((fabs(fr) > 1.0) && (q < 0.0)) q = -sqrt(kG * hf) * A;
+  return q;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kLiBlock, 2)
+local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
+  const int n = c.nriv;
+  const int stride = (int)(gridDim.x * blockDim.x);
+  const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const unsigned n_blocks = gridDim.x;
+  unsigned gen = li_ld_u32(&w.barrier[1]);
+  __shared__ unsigned long long s_min;
+  const double dt = w.dt;
+  const unsigned long long inf_bits = 0x7ff0000000000000ull;
+
+  // set_reservoir_vars! / set_flow_vars!                          surface_kinwave.jl:227-237,269-275
+  for (int p = tid; p < n; p += stride) {
+    f.riv_q_cumulative[p] = 0.0;
+    f.riv_actual_external_abstraction_cumulative[p] = 0.0;
+  }
+  for (int i = tid; i < c.nres; i += stride) {
+    f.res_inflow_cumulative[i] = 0.0;
+    f.res_actual_external_abstraction_cumulative[i] = 0.0;
+    f.res_outflow_cumulative[i] = 0.0;
+    f.res_actevap_cumulative[i] = 0.0;
+  }
+
+  double t = 0.0;
+  int count = 0;
+  bool alive = true;
+  while (t < dt && alive) {
+    // ---- stable_timestep: alpha L / sqrt(g h), minimum over the nodes ------------------------
+    if (threadIdx.x == 0) s_min = inf_bits;
+    __syncthreads();
+    double mine = __longlong_as_double((long long)inf_bits);
+    for (int p = tid; p < n; p += stride) {
+      const double h = __ldcg(f.riv_h + p);
+      const double d = w.alpha * __ldg(f.riv_flow_length + p) / sqrt(kG * h);
+      mine = d < mine ? d : mine;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, mine, o);
+      mine = other < mine ? other : mine;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_min, (unsigned long long)__double_as_longlong(mine));
+    __syncthreads();
+    unsigned long long* slot = w.dt_bits + (count & 1);
+    if (threadIdx.x == 0 && s_min != inf_bits) atomicMin(slot, s_min);
+    alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
+    if (!alive) break;
+    const unsigned long long mb = __ldcg(slot);
+    if (tid == 0) w.dt_bits[(count + 1) & 1] = inf_bits;  // the slot of the next sub-step
+    double dt_s = mb == inf_bits ? 60.0 : __longlong_as_double((long long)mb);
+    if (t + dt_s > dt) dt_s = dt - t;  // check_timestepsize  routing/timestepping.jl:11-16
+
+    // ---- update_river_channel_flow!: the edge leaving every active node ------------------------
+    for (int p = tid; p < n; p += stride) {
+      const int d = f.li_dst_slot[p];
+      if (d == -1) continue;
+      if (f.riv_reservoir && f.riv_reservoir[p] >= 0) continue;  // not in active_e
+      const double q_previous = f.riv_q[p];
+      const double h_src = __ldcg(f.riv_h + p);
+      const double zb = __ldg(f.li_zb + p);
+      const double zs_src = zb + h_src;
+      const double h_dst = d == -2 ? __ldg(f.li_ghost_h + p) : __ldcg(f.riv_h + d);
+      const double zs_dst = (d == -2 ? zb : __ldg(f.li_zb + d)) + h_dst;
+      const double zs_at_edge = jmax(zs_src, zs_dst);
+      const double hf = zs_at_edge - __ldg(f.li_zb_at_edge + p);
+      f.li_zs_at_edge[p] = zs_at_edge;
+      f.li_water_depth_at_edge[p] = hf;
+      const double width = __ldg(f.li_flow_width_at_edge + p);
+      const double A = width * hf;
+      const double R = A / (2.0 * hf + width);
+      double q = hf > w.h_thresh
+                     ? local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R,
+                                           __ldg(f.li_flow_length_at_edge + p),
+                                           __ldg(f.li_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
+                     : 0.0;
+      if (h_src <= 0.0) q = jmin(q, 0.0);
+      if (h_dst <= 0.0) q = jmax(q, 0.0);
+      f.riv_q[p] = q;
+      f.riv_q_cumulative[p] += q * dt_s;
+    }
+    alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
+    if (!alive) break;
+
+    // ---- update_bc_reservoir_model!: one thread per reservoir ----------------------------------
+    if (c.nres > 0) {
+      for (int v = tid; v < c.nres; v += stride) {
+        const int p = f.res_river_slot[v];
+        double q_in = 0.0;  // sum_at(q, edges_at_node.src[i])
+        for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_in += __ldcg(f.riv_q + f.li_in_idx[e]);
+        const double outflow = reservoir_step(f, v, q_in, dt_s);
+        f.riv_q[p] = outflow;
+        f.riv_q_cumulative[p] += outflow * dt_s;
+      }
+      alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
+      if (!alive) break;
+    }
+
+    // ---- update_water_depth_and_storage! --------------------------------------------------------
+    for (int p = tid; p < n; p += stride) {
+      if (f.riv_reservoir && f.riv_reservoir[p] >= 0) continue;  // not in active_n
+      double q_src = 0.0;
+      for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_src += __ldcg(f.riv_q + f.li_in_idx[e]);
+      const double q_dst = f.li_dst_slot[p] == -1 ? 0.0 : 0.0 + f.riv_q[p];
+      double storage = f.riv_storage[p];
+      storage += (q_src - q_dst + f.riv_inwater[p] - __ldg(f.riv_abstraction + p)) * dt_s;
+      if (storage < 0.0) {
+        f.li_error[p] = f.li_error[p] + fabs(storage);
+        storage = 0.0;
+      }
+      const double ext = __ldg(f.riv_external_inflow + p);
+      double inflow;
+      if (ext < 0.0) {
+        const double abstraction = jmin(-ext, storage / dt_s * 0.80);
+        f.riv_actual_external_abstraction_cumulative[p] += abstraction * dt_s;
+        inflow = -abstraction;
+      } else {
+        inflow = ext;
+      }
+      storage += inflow * dt_s;
+      f.riv_storage[p] = storage;
+      f.riv_h[p] = storage / (__ldg(f.riv_flow_length + p) * __ldg(f.riv_flow_width + p));
+    }
+    t += dt_s;
+    ++count;
+    // (no barrier here: the next sub-step's minimum reads only this thread's own depths, and its
+    // edge phase comes after the barrier that follows the minimum)
+  }
+  // average_flow_vars! / average_reservoir_vars!                   surface_kinwave.jl:244-258,283-290
+  for (int p = tid; p < n; p += stride) {
+    f.riv_q_average[p] = f.riv_q_cumulative[p] / dt;
+    f.riv_actual_external_abstraction_average[p] = f.riv_actual_external_abstraction_cumulative[p] / dt;
+  }
+  for (int i = tid; i < c.nres; i += stride) {
+    f.res_outflow_average[i] = f.res_outflow_cumulative[i] / dt;
+    f.res_inflow_average[i] = f.res_inflow_cumulative[i] / dt;
+    f.res_actual_external_abstraction_average[i] = f.res_actual_external_abstraction_cumulative[i] / dt;
+  }
+  if (tid == 0) *w.substeps = count;
+}
+
+int li_max_grid(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, local_inertial_river_kernel, kLiBlock, 0) !=
+      cudaSuccess)
+    return -1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return per_sm * sms;
+}
+
+int launch_local_inertial_river(const DevFields& f, const KCfg& c, const LiLaunch& w, cudaStream_t s) {
+  static const unsigned long long inf2[2] = {0x7ff0000000000000ull, 0x7ff0000000000000ull};
+  cudaMemcpyAsync(w.dt_bits, inf2, sizeof(inf2), cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(w.barrier, 0, sizeof(unsigned), s);  // arrivals; the generation keeps counting
+  local_inertial_river_kernel<<<w.grid, kLiBlock, 0, s>>>(f, c, w);
+  return 1;
+}
+
+}  // namespace wfb

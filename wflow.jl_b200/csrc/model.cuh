@@ -23,6 +23,11 @@ struct DevFields {
   int32_t* nlayers_kv;         // land (KvLayeredExponential only)
   int32_t* riv_reservoir;      // river slot -> reservoir (0-based) or -1; nullptr without reservoirs
   int32_t* res_land_slot;      // reservoir -> land slot of its outlet cell
+  int32_t* res_river_slot;     // reservoir -> river slot of its node
+  // local-inertial river flow: the staggered grid by river slot
+  int32_t* li_dst_slot;        // slot of the node the leaving edge ends in, -1 none, -2 ghost
+  int32_t* li_in_ptr;          // edges entering a node (= their source slots), CSR by slot,
+  int32_t* li_in_idx;          // ascending source NODE id (sum_at order)
   uint8_t* land_is_res_outlet; // land slot is a reservoir outlet (nullptr without reservoirs)
   int32_t* olf_newton_trace;   // land / river, or nullptr: Newton iterations of kinematic_wave
   int32_t* riv_newton_trace;   // per node since wflowb200_newton_trace(h, 1)
@@ -66,6 +71,7 @@ struct KCfg {
   int32_t n, nriv, ns, nrs, nres;
   int32_t gash, has_lai, snow, glacier, soil_infiltration_reduction, kv_profile;
   double qroot;                // KIN_WAVE_MIN_FLOW^0.2
+  int32_t river_routing;       // 0 kinematic wave, 1 local inertial
   int32_t kw_root_each_substep; // 1: u_prev = pow(q_prev, 0.2) before every solve, like the
                                // reference (default 0: carried, see routing.cu: KwState)
 };

@@ -137,6 +137,69 @@ __device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt, 
   t.usd = usd; t.sum_ast = sum_ast;
 }
 
+// The same loop with a short dependency chain, for the LONG loops of the engine (a loop round
+// lasts as long as its longest loop: ~250 trips x ~620 cycles of div -> log -> exp with
+// libdevice). A trip drains the fraction eps = st dt / usd of the layer, so with x = usd / l_sat
+// and r = x^(c-1):  x' = x (1 - eps),  eps = (kv_it dt / l_sat) r,  r' = r exp((c-1) log(1 - eps)).
+// For eps <= 1/64 (always, a few trips into a long loop) log(1 - eps) and the exp of the small
+// product are short polynomials (explicit FMAs, Estrin form: ~13 dependent operations instead of
+// ~70), st = kv_it r x. r is re-evaluated with the reference expression every kResync trips, so
+// the tracked value stays within ~1e-14 of it (each update adds ~2 ulp); usd itself is always
+// updated with the reference's own expression usd -= st dt. Trips with a large eps, an
+// oversaturated layer (x > 1, bounded_power = 1) or an underflowing power take the reference
+// path. wflowb200_selftest_math compares both loops.
+constexpr int kResync = 16;
+__device__ __forceinline__ double log1m_small(double e) {  // log(1 - e), 0 <= e <= 1/64
+  // -(e + e^2/2 + ... + e^10/10); the first neglected term is 5e-18 relative
+  const double e2 = e * e, e4 = e2 * e2, e8 = e4 * e4;
+  const double a0 = fma(e, 1.0 / 2.0, 1.0), a1 = fma(e, 1.0 / 4.0, 1.0 / 3.0);
+  const double a2 = fma(e, 1.0 / 6.0, 1.0 / 5.0), a3 = fma(e, 1.0 / 8.0, 1.0 / 7.0);
+  const double a4 = fma(e, 1.0 / 10.0, 1.0 / 9.0);
+  const double b0 = fma(e2, a1, a0), b1 = fma(e2, a3, a2);
+  const double p = fma(e8, a4, fma(e4, b1, b0));
+  return -(e * p);
+}
+__device__ __forceinline__ double exp_small(double z) {  // exp(z), |z| <= 0.175
+  // 1 + z + ... + z^11/11!; the first neglected term is 2e-18
+  const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+  const double d0 = 1.0 + z, d1 = fma(z, 1.0 / 6.0, 0.5);
+  const double d2 = fma(z, 1.0 / 120.0, 1.0 / 24.0), d3 = fma(z, 1.0 / 5040.0, 1.0 / 720.0);
+  const double d4 = fma(z, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double d5 = fma(z, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double e0 = fma(z2, d1, d0), e1 = fma(z2, d3, d2), e2 = fma(z2, d5, d4);
+  return fma(z8, e2, fma(z4, e1, e0));
+}
+__device__ __forceinline__ void unsatzone_flow_iterate_fast(UnsatTask& t, double dt,
+                                                            const Divisor& ddt) {
+  double usd = t.usd, sum_ast = t.sum_ast;
+  const Divisor dl(t.l_sat);
+  const double a = t.kv_it * dt / dl;
+  const double cm1 = t.c - 1.0;
+  double r = 0.0;
+  int fresh = 0;  // trips for which the tracked r may still be used
+  for (int k = 0; k < t.its; ++k) {
+    const double x = usd / dl;
+    double p;
+    if (fresh > 0) {
+      p = r * x;
+    } else {
+      p = bounded_power(x, t.c);  // the reference expression
+      if (x <= 1.0 && p > 1.0e-280) { r = p / x; fresh = kResync; }
+    }
+    const double st = t.kv_it * p;
+    const double st_max = usd / ddt;
+    if (st < st_max) { usd -= st * dt; sum_ast += st; }
+    else { usd = 0.0; sum_ast += st_max; break; }
+    if (fresh > 0) {
+      const double eps = a * r;
+      const double z = cm1 * log1m_small(eps);
+      if (eps <= 1.0 / 64.0 && z >= -0.175) { r *= exp_small(z); --fresh; }
+      else fresh = 0;
+    }
+  }
+  t.usd = usd; t.sum_ast = sum_ast;
+}
+
 // ---- the unsaturated-zone engine: suspended loops ------------------------------------------
 constexpr int kBuckets = WFB_UNSAT_BUCKETS;
 __device__ __forceinline__ int bucket_of(int its) {  // (8,16] -> 0 ... by log2, clamped
@@ -466,8 +529,21 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
 
 }  // namespace
 
+// WFB_V_FUSED = 1: land_hydrology_kernel also finishes every never-suspended cell from registers
+// (no re-read of the first half's outputs). Measured on B200 (1000^2): slower than the split
+// organisation -- the fused kernel needs 128 registers with spills, runs 4 CTAs per SM and takes
+// 436 us against 172 + 142 us for the two halves as kernels of their own, both latency-bound in
+// FP64 dependency chains, not by DRAM (29 % of peak) -- see DESIGN.md section 5.1.
+#ifndef WFB_V_FUSED
+#define WFB_V_FUSED 0
+#endif
+// the loop engine's trips with the tracked power (unsatzone_flow_iterate_fast); 0: every trip
+// with the reference expression
+#ifndef WFB_ENGINE_FAST_TRIPS
+#define WFB_ENGINE_FAST_TRIPS 1
+#endif
 #ifndef WFB_V_MINBLOCKS
-#define WFB_V_MINBLOCKS 4
+#define WFB_V_MINBLOCKS (WFB_V_FUSED ? 4 : 5)
 #endif
 // Counting sort of the tiles by the longest Brooks-Corey loop they held in the PREVIOUS model
 // step (tile_prio, raised by suspend_cell), longest first; ties keep no particular order. One
@@ -838,6 +914,15 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     f.soil_surface_temperature[i] = st_tsoil;
     if (c.glacier) f.glacier_store[i] = st_gstore;
   }
+#if !WFB_V_FUSED
+  // split organisation (default): the second half runs in soil_column_kernel for every cell that
+  // was not suspended (state 0) and in unsat_resume_kernel for the others
+  if (done) { f.transfer[i] = transfer; w.its_layer[i] = 0; }
+#pragma unroll
+  for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
+  (void)pot_soilevap0; (void)infiltration_excess; (void)max_infiltsoil; (void)max_infiltpath;
+  (void)aeow_river; (void)aeow_land;
+#else
   if (done) {
     // the second half straight from registers: nothing of the first half is read back
     f.transfer[i] = transfer;
@@ -851,6 +936,70 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
 #pragma unroll
     for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
   }
+#endif
+}
+
+// What soil_column_cell needs, re-read from the reference-visible arrays the first half wrote
+// (s.uld, s.ult, s.bc, s.kv, s.theta_s, s.theta_e, s.n_unsat may already be loaded).
+template <int N>
+__device__ __forceinline__ void load_column_rest(const DevFields& f, const KCfg& c, const int i,
+                                                 SoilColumn<N>& s) {
+  const int ns = c.ns;
+  s.d_soil = __ldg(f.soil_thickness + i);
+  s.swc = __ldg(f.soil_water_capacity + i);
+  s.satwd = f.saturated_water_depth[i];
+  s.zi = f.water_table_depth[i];
+  s.nlayers = f.number_of_layers[i];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    s.alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
+    s.cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
+  }
+  s.cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
+  s.pot_soilevap = f.potential_soilevaporation[i];
+  s.pot_transp = f.potential_transpiration[i];
+  s.infiltration = f.infiltration[i];
+  s.infiltration_excess = f.infiltration_excess[i];
+  s.wfs = f.soil_water_flux_surface[i];
+  const double f_red = f.f_infiltration_reduction[i];
+  s.pathfrac = __ldg(f.compacted_soil_area_fraction + i);
+  // infiltration! soil_process.jl:16-41, the same expressions as in land_hydrology_kernel
+  s.max_infiltsoil = jmin(__ldg(f.infiltration_capacity_soil + i) * f_red, s.wfs * (1.0 - s.pathfrac));
+  s.max_infiltpath = jmin(__ldg(f.infiltration_capacity_compacted_soil + i) * f_red, s.wfs * s.pathfrac);
+  s.aeow_river = f.actual_open_water_evaporation_river[i];
+  s.aeow_land = f.actual_open_water_evaporation_land[i];
+  s.interception = f.interception_rate[i];
+}
+
+// update_land_hydrology_model!, second half, for every cell whose Brooks-Corey loops were short
+// (split organisation): the suspended ones (state != 0) are finished by unsat_resume_kernel,
+// which runs at the same time on a side stream.
+#ifndef WFB_VC_MINBLOCKS
+#define WFB_VC_MINBLOCKS 4
+#endif
+template <int N>
+__global__ void __launch_bounds__(WFB_V_TILE, WFB_VC_MINBLOCKS)
+soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
+                   const int32_t* __restrict__ order, const int tile_begin) {
+  const int i = __ldg(order + tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
+  if (i >= c.n) return;
+  if (w.its_layer[i] != 0) return;  // suspended: not this kernel's cell
+  const int ns = c.ns;
+  const Divisor ddt(dt);
+  SoilColumn<N> s;
+  s.theta_s = __ldg(f.theta_s + i);
+  s.theta_e = s.theta_s - __ldg(f.theta_r + i);
+  s.n_unsat = f.n_unsatlayers[i];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
+    s.ult[k] = f.unsaturated_layer_thickness[k * ns + i];
+    s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
+  }
+  s.kv = load_kvcol<N>(f, c, i);
+  s.transfer = f.transfer[i];
+  load_column_rest<N>(f, c, i, s);
+  soil_column_cell<N>(f, c, i, dt, ddt, s);
 }
 
 // All suspended loops of a slice, one lane per loop, 32 loops of one bucket per warp.
@@ -871,7 +1020,11 @@ unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
       UnsatTask t;
       t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
       t.c = w.c[i]; t.its = w.its_layer[i] & 0xffffff;
+#if WFB_ENGINE_FAST_TRIPS
+      unsatzone_flow_iterate_fast(t, dt, ddt);
+#else
       unsatzone_flow_iterate(t, dt, ddt);
+#endif
       w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast;
     }
   }
@@ -934,30 +1087,7 @@ unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const in
     }
     f.transfer[i] = transfer;
     s.transfer = transfer;
-    s.d_soil = __ldg(f.soil_thickness + i);
-    s.swc = __ldg(f.soil_water_capacity + i);
-    s.satwd = f.saturated_water_depth[i];
-    s.zi = f.water_table_depth[i];
-    s.nlayers = f.number_of_layers[i];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      s.alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
-      s.cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
-    }
-    s.cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
-    s.pot_soilevap = f.potential_soilevaporation[i];
-    s.pot_transp = f.potential_transpiration[i];
-    s.infiltration = f.infiltration[i];
-    s.infiltration_excess = f.infiltration_excess[i];
-    s.wfs = f.soil_water_flux_surface[i];
-    const double f_red = f.f_infiltration_reduction[i];
-    s.pathfrac = __ldg(f.compacted_soil_area_fraction + i);
-    // infiltration! soil_process.jl:16-41, the same expressions as in land_hydrology_kernel
-    s.max_infiltsoil = jmin(__ldg(f.infiltration_capacity_soil + i) * f_red, s.wfs * (1.0 - s.pathfrac));
-    s.max_infiltpath = jmin(__ldg(f.infiltration_capacity_compacted_soil + i) * f_red, s.wfs * s.pathfrac);
-    s.aeow_river = f.actual_open_water_evaporation_river[i];
-    s.aeow_land = f.actual_open_water_evaporation_land[i];
-    s.interception = f.interception_rate[i];
+    load_column_rest<N>(f, c, i, s);
     soil_column_cell<N>(f, c, i, dt, ddt, s);
   }
 }
@@ -1010,7 +1140,8 @@ total_water_storage_kernel(const DevFields f, const KCfg c, const int32_t* __res
 // ---- self-test of device_math.cuh (wflowb200_selftest_math) ----------------------------------
 // The largest relative difference of jpow(x, c) = exp(c log x) for x in (0, 1], c in [1, 40]
 // against libdevice's pow, and checks of fdiv, jmin, jmax and jcld_pos against the plain
-// formulations (out[0], out[1] are unused and stay 0).
+// formulations; out[0], out[1]: largest relative difference of the remaining store / the summed
+// flux between the loop engine's fast trips and the reference loop.
 __device__ __forceinline__ double ulp_dist(double a, double b) {
   if (a == b || (a != a && b != b)) return 0.0;
   if (a != a || b != b) return 1e300;
@@ -1031,6 +1162,24 @@ __global__ void selftest_math_kernel(long long n, unsigned long long* out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const double u = u01_hash(i, 1), v = u01_hash(i, 2), t = u01_hash(i, 3);
+    // the loop engine's fast trips against the reference loop, on tasks shaped like the model's
+    {
+      UnsatTask ta;
+      ta.l_sat = 0.02 + 0.28 * u;
+      ta.c = 8.0 + 4.0 * v;
+      const double dtl = 86400.0;
+      const Divisor ddl(dtl);
+      const double usd0 = ta.l_sat * (0.3 + 0.7 * t);
+      const double kv_z = (0.001 + 0.3 * u01_hash(i, 4)) / dtl;
+      ta = unsatzone_flow_setup(usd0, kv_z, ta.l_sat, ta.c, dtl, ddl);
+      if (ta.its > 0 && ta.its < 400) {
+        UnsatTask tb = ta;
+        unsatzone_flow_iterate(ta, dtl, ddl);
+        unsatzone_flow_iterate_fast(tb, dtl, ddl);
+        if (ta.usd > 1e-12) w_exp = fmax(w_exp, fabs(tb.usd - ta.usd) / ta.usd);
+        w_log = fmax(w_log, fabs(tb.sum_ast - ta.sum_ast) / ta.sum_ast);
+      }
+    }
     // jpow(x, c) = exp(c log x) against libdevice's pow (different algorithm, both < 1 ulp-ish)
     const double xp = (i & 1) ? v : 1.0 - v * v * v, cp = 1.0 + 39.0 * t;
     const double want = pow(xp, cp), got = jpow(xp, cp);
@@ -1095,7 +1244,8 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, const int* slice_tile_begin,
                           unsigned* tile_prio, int32_t* tile_order, int engine_grid, int phase,
-                          cudaStream_t s, cudaStream_t const* side, cudaEvent_t const* ev) {
+                          bool run_engine, cudaStream_t s, cudaStream_t const* side,
+                          cudaEvent_t const* ev) {
   int launches = 0;
   const int n_tiles = (c.ns + kTile - 1) / kTile;
   if (phase != 2) {  // (phase 2 reuses the order of phase 1)
@@ -1114,12 +1264,13 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
     WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<t1 - t0, kTile, 0, s>>>(
                                  f, c, w[k], dt, tile_order, t0, phase)));
     ++launches;
-    cudaStream_t e = n_slices > 1 ? side[k % WFB_V_SIDE_STREAMS] : s;
-    if (n_slices > 1) {
+    // the engine always runs on a side stream: with one slice it overlaps soil_column_kernel
+    cudaStream_t e = (n_slices > 1 || !WFB_V_FUSED) ? side[k % WFB_V_SIDE_STREAMS] : s;
+    if (e != s) {
       cudaEventRecord(ev[2 * k], s);
       cudaStreamWaitEvent(e, ev[2 * k], 0);
     }
-    for (int r = 0; r < n_layers; ++r) {
+    for (int r = 0; r < (run_engine ? n_layers : 0); ++r) {
       const int parity = r & 1;
       unsat_loop_kernel<<<engine_grid, 128, 0, e>>>(w[k], parity, dt);
       if (r > 0)
@@ -1127,11 +1278,20 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
       WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], parity, dt)));
       launches += 2;
     }
-    if (n_slices > 1) cudaEventRecord(ev[2 * k + 1], e);
+    cudaEventRecord(ev[2 * k + 1], e);
   }
-  if (n_slices > 1)
-    for (int k = 0; k < n_slices; ++k)
-      if (slice_tile_begin[k] < slice_tile_begin[k + 1]) cudaStreamWaitEvent(s, ev[2 * k + 1], 0);
+#if !WFB_V_FUSED
+  // second half of the never-suspended cells, under the engines of the side streams
+  for (int k = 0; k < n_slices; ++k) {
+    const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
+    if (t0 >= t1) continue;
+    WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<t1 - t0, kTile, 0, s>>>(f, c, w[k], dt,
+                                                                              tile_order, t0)));
+    ++launches;
+  }
+#endif
+  for (int k = 0; k < n_slices; ++k)
+    if (slice_tile_begin[k] < slice_tile_begin[k + 1]) cudaStreamWaitEvent(s, ev[2 * k + 1], 0);
   return launches;
 }
 

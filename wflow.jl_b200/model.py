@@ -53,6 +53,11 @@ class SbmModel:
         c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
         c.kin_wave_min_flow_qroot = float(cfg.get("kin_wave_min_flow_qroot", 1e-30 ** 0.2))
         c.snow_gravitational_transport = int(cfg.get("snow_transport", 0))
+        c.river_routing = int(cfg.get("river_routing", 0))
+        c.li_froude_limit = int(cfg.get("li_froude_limit", 1))
+        c.li_ghost_nodes = int(cfg.get("li_ghost_nodes", 1))
+        c.li_alpha = float(cfg.get("li_alpha", 0.7))
+        c.li_h_thresh = float(cfg.get("li_h_thresh", 1.0e-3))
         for k in ("wave_piece_depth_land", "vertical_slices", "unsat_inline_iters"):  # 0 = automatic
             setattr(c, k, int(cfg.get(k, 0)))
         d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,

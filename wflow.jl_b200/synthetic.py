@@ -200,7 +200,7 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                soil_infiltration_reduction: bool = False, id_offset: int = 0,
                external_inflow: bool = False, network: str = "scheidegger",
                n_active: int | None = None, n_river: int | None = None, reservoirs: int = 0,
-               snow_transport: bool = False):
+               snow_transport: bool = False, river_routing: int = 0):
     """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
     the reference's field names; layered arrays are cell-major (n, N). network: "scheidegger"
     (a forest of many small basins, codes 5/7/8/9) or "dendritic" (one outlet, all eight
@@ -412,6 +412,29 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     for k in ("riv_q", "riv_h", "riv_storage", "riv_qin", "riv_qlat", "riv_inwater"):
         F[k] = np.zeros(nriv)
 
+    # ---- local-inertial river flow: the staggered grid (surface_staggered_scheme.jl:36-156) ------
+    if river_routing == 1 and nriv:
+        rdown = np.zeros(nriv, dtype=np.int64)          # downstream river node (1-based, 0 = pit)
+        riv_of_land = np.zeros(n, dtype=np.int64)
+        riv_of_land[ridx] = np.arange(1, nriv + 1)
+        dl = down[ridx]
+        rdown[dl > 0] = riv_of_land[dl[dl > 0] - 1]
+        L, W = F["riv_flow_length"], F["riv_flow_width"]
+        # bed level: falls along the network with the river slope, 10 m at the pits
+        zb = np.full(nriv, 10.0)
+        order = np.argsort(-acc[ridx], kind="stable")   # downstream nodes first
+        for r in order:
+            if rdown[r] > 0:
+                zb[r] = zb[rdown[r] - 1] + riv_slope[r] * L[r]
+        d = np.where(rdown > 0, rdown - 1, np.arange(nriv))   # ghost node copies the pit
+        F["li_zb"] = zb
+        F["li_zb_at_edge"] = np.maximum(zb, zb[d])
+        F["li_flow_width_at_edge"] = np.minimum(W, W[d])
+        F["li_flow_length_at_edge"] = (L + L[d]) / 2.0          # Statistics.mean of the pair
+        n_at_edge = (riv_n[d] * L[d] + riv_n * L) / (L[d] + L)
+        F["li_mannings_n_sq_at_edge"] = n_at_edge * n_at_edge
+        F["li_ghost_h"] = np.zeros(nriv)                        # riverdepth_bc
+        F["li_error"] = np.zeros(nriv)
     # ---- reservoirs on the river (reservoir.jl; Moselle has two, test/sbm_config.toml:126) -----
     reservoir_river_indices = np.zeros(0, dtype=np.int64)
     nres = 0
@@ -456,7 +479,8 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                snow=int(snow), glacier=int(glacier),
                soil_infiltration_reduction=int(soil_infiltration_reduction),
                kv_profile=kv_profile, adaptive=int(adaptive), nthreads=nthreads,
-               snow_transport=int(snow_transport),
+               snow_transport=int(snow_transport), river_routing=int(river_routing),
+               li_froude_limit=1, li_ghost_nodes=1, li_alpha=0.7, li_h_thresh=1.0e-3,
                land_streamorder_min=5, river_streamorder_min=6, dt_land=3600.0, dt_river=900.0,
                dt_ssf=86400.0, ssf_alpha_coefficient=1.0, dt=dt,
                kin_wave_min_flow_qroot=1e-30 ** 0.2)
