@@ -1,15 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- cell-timesteps/s of the wflow_sbm hot path (SBM vertical + kinematic-wave
-routing) on B200, with the HBM roofline of the vertical kernel and the CPU baseline beside it.
+routing) on B200, with the HBM roofline of the vertical update and the CPU baseline beside it.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the CPU implementation (oracle port)
 
 One "step" = one model time step (update_model!, sbm_model.jl:60-92) of a synthetic D8 basin:
-forcing -> fused SBM vertical kernel -> subsurface / overland / river kinematic wave (24 + 96
-+ 1 internal sub-steps at the reference's default fixed internal time steps) -> storages.
+forcing -> SBM vertical update -> subsurface / overland / river kinematic wave (24 + 96 + 1
+internal sub-steps at the reference's default fixed internal time steps) -> storages.
 N = 1 runs BASELINE.json configs[1] (synthetic 1000 x 1000 basin); N > 1 runs one such
-sub-catchment tile per GPU (disjoint catchments, no data-path collective: weak scaling).
+sub-catchment tile per GPU (disjoint catchments, no data-path collective: weak scaling) and, at
+N = 8, additionally measures configs[2]: ONE 10000 x 10000 raster (10^8 cells) of sub-catchments
+sharded over the GPUs, each rank generating only its own shard from (seed, global cell id).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -17,7 +19,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -29,13 +30,19 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_pkg  # noqa: E402
 
 METRIC = "cell-timesteps/s (SBM vertical + kinwave)"
-ADAPTIVE = False
-V1_DRAM_BYTES_PER_CELL = 1477  # measured (ncu), see roofline.traffic_source
 UNIT = "cell-timesteps/s"
+# DRAM bytes per cell of the vertical update (ncu dram__bytes_read.sum + dram__bytes_write.sum of
+# its kernels, profiles/r2_vertical_ncu.md), N = 4, Gash + snow
+V1_DRAM_BYTES_PER_CELL = 1477
+V1_TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_vertical_ncu.md"
+# a realistic per-step output set (write_output, io.jl:815-899; the Moselle TOML writes ~8 vectors)
+OUTPUT_FIELDS = ["riv_q_average", "riv_h", "snow_storage", "saturated_water_depth",
+                 "unsaturated_store_depth", "total_storage", "olf_q_average",
+                 "ssf_water_table_depth"]
 
 
 # --------------------------------------------------------------------------------------------
-# algorithmic bytes (DESIGN.md §4): every distinct input array read once + every
+# algorithmic bytes (DESIGN.md section 4): every distinct input array read once + every
 # reference-visible output array written once, Float64 (int32 counters 4 B)
 # --------------------------------------------------------------------------------------------
 def v1_bytes_per_cell(N: int, cfg: dict) -> int:
@@ -86,46 +93,53 @@ def v1_bytes_per_cell(N: int, cfg: dict) -> int:
     return 8 * (len(reads) + len(writes) + layered_r + layered_w) + 4 + 4  # + 2 int32 arrays
 
 
-def v2_bytes_per_cell(N: int) -> int:
-    return 8 * ((13 + 4 * N) + (12 + 2 * N)) + 8
-
-
 # --------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons during the timed region, through NVML (a sample every few
+    milliseconds; nvidia-smi takes longer per call than a timed step)."""
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], None, set()
         self._halt = threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nv = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        nv = self.nv
+        if nv is None:
+            return
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)}
+        try:
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.mx = None
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.004)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows for k in range(4)
-                          if len(r) >= 7 and r[3 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_peak():
@@ -136,43 +150,119 @@ def measured_peak():
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
 
 
-def build_tile(pkg, size: int, rank: int, seed: int):
-    """One sub-catchment tile per rank: a `size` x `size` Scheidegger forest whose cell ids
-    are offset so that every tile of the global raster is a different random forest."""
-    return pkg.synthetic.make_basin(size, size, seed=seed, id_offset=rank * size * size,
-                                    adaptive=ADAPTIVE)
+def workload_text(d1, d2, adaptive):
+    return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical + kinematic-wave "
+            "river/overland/subsurface, daily step, "
+            + ("adaptive internal steps" if adaptive else "fixed internal steps 3600/900/86400 s")
+            + ", N=4 soil layers, snow on")
+
+
+def config_block(workload, n, nriv, world):
+    """The SAME keys in both arms (the driver compares them)."""
+    return {"workload": workload, "cells_per_gpu": int(n), "river_cells_per_gpu": int(nriv),
+            "parallelism": f"{world} x disjoint sub-catchment tiles, no collective"}
+
+
+def build_tile(pkg, d1, d2, rank, seed, adaptive):
+    """One sub-catchment tile per rank: a d1 x d2 Scheidegger forest whose cell ids are offset so
+    that every tile of the global raster is a different random forest. Only the rank's own
+    cells are ever generated: everything is a pure function of (seed, global cell id)."""
+    return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive)
 
 
 # --------------------------------------------------------------------------------------------
-def run_cpu(pkg, cfg, dom, fields, steps: int, warmup: int, seed: int, first_step: int = 0):
-    """The CPU implementation of the path: the C oracle (port of the Julia algorithm, OpenMP,
-    threaded over the reference's own sub-domain partition). Julia is not available here, so
-    kind = "port". Returns (cell-timesteps/s, cores, seconds per step)."""
+def make_cpu_model(cfg, dom, fields):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import parity
     ora = parity.make_oracle(cfg, dom, fields)
-    dt = cfg["dt"]
-    gid = dom["gid"]
     # all the host threads the process may use (torchrun exports OMP_NUM_THREADS=1)
     cores = ora._L.wfo_set_num_threads(len(os.sched_getaffinity(0)))
+    return ora, cores
 
-    def one(step):
-        p, e, t = pkg.synthetic.make_forcing(seed, step, gid, dt)
-        ora.f["precipitation"][:], ora.f["potential_evaporation"][:], ora.f["temperature"][:] = p, e, t
+
+def cpu_step(pkg, ora, cfg, gid, seed, step):
+    p, e, t = pkg.synthetic.make_forcing(seed, step, gid, cfg["dt"])
+    ora.f["precipitation"][:], ora.f["potential_evaporation"][:], ora.f["temperature"][:] = p, e, t
+    t0 = time.perf_counter()
+    ora.update_model(cfg["dt"])
+    return time.perf_counter() - t0
+
+
+# --------------------------------------------------------------------------------------------
+def measure(pkg, torch, dist, model, cfg, dom, seed, steps, warmup, world, local, e2e=True,
+            first_step=0):
+    """Warm-up, the device-timed leg (forcing slabs resident in HBM, a different one every step)
+    and the end-to-end leg (host buffers: H2D of every step's forcing and D2H of an output set
+    inside the timed region). Returns a dict."""
+    n, dt = cfg["n"], cfg["dt"]
+    gid = dom["gid"]
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    depth = int(max(2, min(steps, 24, 3.0e9 // (24 * max(n, 1)))))
+    forcing = [tuple(pin(a) for a in pkg.synthetic.make_forcing(seed, first_step + s, gid, dt))
+               for s in range(depth)]
+
+    def barrier():
+        model.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(warmup):   # spin the model up: soil, overland and river stores become active
+        model.set_forcing(*forcing[s % len(forcing)])
+        model.update_model(dt)
+    model.synchronize()
+    launches0 = model.stats()["kernel_launches"]
+
+    # ---- leg 1: device-resident inputs, a different forcing slab every step ---------------------
+    model.forcing_ring_create(depth)
+    for k in range(depth):
+        model.forcing_ring_put(k, *forcing[k % len(forcing)])
+    sampler = ClockSampler(local)
+    sampler.start()
+    model.set_timing(True)
+    barrier()
+    model.timer_start()
+    for s in range(steps):
+        model.forcing_ring_use(s % depth)
+        model.update_model(dt)
+    ms = model.timer_stop()
+    barrier()
+    st = model.stats()
+    model.set_timing(False)
+    launches = st["kernel_launches"] - launches0
+    t_max = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    out = {"ms": float(t_max.item()), "stats": st, "launches": int(launches)}
+
+    # ---- leg 2: end to end through the public API with HOST buffers ------------------------------
+    if e2e:
+        got = None
+        barrier()
         t0 = time.perf_counter()
-        ora.update_model(dt)
-        return time.perf_counter() - t0
-
-    for s in range(warmup):
-        one(first_step + s)
-    el = sum(one(first_step + warmup + s) for s in range(steps))
-    return cfg["n"] * steps / el, cores, el / steps
+        model.forcing_ring_put(0, *forcing[0])                      # H2D, step 0
+        for s in range(steps):
+            model.forcing_ring_use(s % depth)
+            model.update_model(dt)                                   # asynchronous
+            if s + 1 < steps:                                        # H2D of step s + 1 overlaps step s
+                model.forcing_ring_put((s + 1) % depth, *forcing[(s + 1) % len(forcing)])
+            got = model.get_fields(OUTPUT_FIELDS)                    # D2H of the step's output set
+        model.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        assert got is not None and all(np.isfinite(v).all() for v in got.values())
+        out["e2e_s"] = float(t_e2e.item())
+        out["d2h_bytes"] = int(sum(v.size for v in got.values()) * 8)
+    out["clocks"] = sampler.stop()
+    return out
 
 
 def main():
@@ -182,12 +272,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1000, help="raster side per GPU")
+    ap.add_argument("--shape", default="", metavar="D1xD2", help="raster shape per GPU (overrides --size)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-steps", type=int, default=2, help="oracle steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--partition", type=int, default=0, metavar="G",
-                    help="shard ONE G x G basin raster over the ranks by whole drainage basins "
-                         "(strong scaling) instead of one --size tile per rank")
+    ap.add_argument("--no-config3", action="store_true",
+                    help="skip the 10^8-cell raster block of the 8-GPU line")
     ap.add_argument("--adaptive", action="store_true",
                     help="adaptive internal routing time steps instead of the fixed defaults")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=INT",
@@ -196,30 +286,33 @@ def main():
                     help="WflowB200Config tuning field, e.g. vertical_slices=1")
     args = ap.parse_args()
     rank, world, local = dist_env()
-    global ADAPTIVE
-    ADAPTIVE = args.adaptive
     pkg = load_pkg()
-    workload = f"synthetic {args.size}x{args.size} D8 basin per GPU, wflow_sbm vertical + " \
-               "kinematic-wave river/overland/subsurface, daily step, " + \
-               ("adaptive internal steps" if args.adaptive else
-                "fixed internal steps 3600/900/86400 s") + ", N=4 soil layers, snow on"
+    d1, d2 = (int(x) for x in args.shape.split("x")) if args.shape else (args.size, args.size)
+    workload = workload_text(d1, d2, args.adaptive)
 
     # ------------------------------------------------------------------ reference arm ----
     if args.impl == "reference":
         if rank != 0:
             return
-        cfg, dom, fields = build_tile(pkg, args.size, 0, args.seed)
-        k = max(1, min(args.steps, 3))
-        w = min(args.warmup, 1)
-        value, cores, sps = run_cpu(pkg, cfg, dom, fields, k, w, args.seed)
-        sample = (f"full {args.size}x{args.size} tile (n={cfg['n']}), {k} timed model steps after "
-                  f"{w} warm-up (of the requested {args.steps}/{args.warmup}: bounded CPU sample)")
+        cfg, dom, fields = build_tile(pkg, d1, d2, 0, args.seed, args.adaptive)
+        ora, cores = make_cpu_model(cfg, dom, fields)
+        t_first = cpu_step(pkg, ora, cfg, dom["gid"], args.seed, 0)   # first warm-up step, timed
+        # the requested W / K when they fit ~2 minutes of CPU work, else a bounded sample
+        budget = 120.0
+        w = max(1, min(args.warmup, int(budget / 4 / max(t_first, 1e-3))))
+        k = max(1, min(args.steps, int(budget * 3 / 4 / max(t_first, 1e-3))))
+        for s in range(1, w):
+            cpu_step(pkg, ora, cfg, dom["gid"], args.seed, s)
+        el = sum(cpu_step(pkg, ora, cfg, dom["gid"], args.seed, w + s) for s in range(k))
+        value = cfg["n"] * k / el
+        sample = (f"full {d1}x{d2} tile (n={cfg['n']}), {k} timed model steps after {w} warm-up "
+                  f"(requested {args.steps}/{args.warmup}); C/OpenMP port of the Julia algorithm "
+                  "threaded over the reference's sub-domain partition (Julia is not installed)")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-            "n_gpus": args.gpus, "steps": k, "warmup": w, "ms_per_step": sps * 1e3,
+            "n_gpus": args.gpus, "steps": k, "warmup": w, "ms_per_step": el / k * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload, "cells_per_gpu": cfg["n"], "river_cells": cfg["nriv"]},
+            "data": "synthetic", "config": config_block(workload, cfg["n"], cfg["nriv"], args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -236,100 +329,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    if args.partition:
-        # every rank derives the same global domain and keeps its own basins
-        gcfg, gdom, gfields = pkg.synthetic.make_basin(args.partition, args.partition,
-                                                       seed=args.seed, adaptive=ADAPTIVE)
-        shard = pkg.partition.partition_basins(gdom, world)[rank]
-        cfg = pkg.partition.shard_config(gcfg, shard)
-        dom = pkg.partition.shard_domain(gdom, shard)
-        fields = pkg.partition.shard_fields(gfields, dict(pkg._lib.field_table()), shard)
-        del gcfg, gdom, gfields
-        workload = workload.replace(f"synthetic {args.size}x{args.size} D8 basin per GPU",
-                                    f"ONE synthetic {args.partition}x{args.partition} D8 raster "
-                                    f"sharded by whole drainage basins over {world} GPU(s)")
-    else:
-        cfg, dom, fields = build_tile(pkg, args.size, rank, args.seed)
-    n, nriv, N, dt = cfg["n"], cfg["nriv"], cfg["N"], cfg["dt"]
+    cfg, dom, fields = build_tile(pkg, d1, d2, rank, args.seed, args.adaptive)
     for kv in args.cfg:
         k, v = kv.split("=")
         cfg[k] = int(v)
+    n, nriv, N, dt = cfg["n"], cfg["nriv"], cfg["N"], cfg["dt"]
     model = pkg.SbmModel(cfg, dom, fields, device=local)
     for kv in args.option:
         k, v = kv.split("=")
         model.set_option(k, int(v))
-    gid = dom["gid"]
-    if world > 1 or args.no_cpu_baseline:
-        fields = None  # only the cpu_baseline leg needs the host copies again
-    # the step's inputs wait in page-locked host memory (the contract's e2e leg copies them from
-    # there): the library then copies them straight to the device, without its staging memcpy
-    def pin(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    # a pool of distinct forcing fields, cycled (bounds the pinned memory of large tiles)
-    n_forcing = min(args.warmup + args.steps, max(4, int(2.0e9 // (24 * max(len(gid), 1)))))
-    forcing = [tuple(pin(a) for a in pkg.synthetic.make_forcing(args.seed, s, gid, dt))
-               for s in range(n_forcing)]
+    do_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    if not do_cpu:
+        fields = None  # only the cpu_baseline / parity leg needs the host copies again
 
-    def barrier():
-        model.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # warm-up: spin the model up so that soil, overland and river stores are active
-    for s in range(args.warmup):
-        model.set_forcing(*forcing[s % len(forcing)])
-        model.update_model(dt)
-    model.synchronize()
-    launches0 = model.stats()["kernel_launches"]
-
-    # ---- leg 1: device-resident inputs (forcing of the last warm-up step stays in HBM) -----
-    sampler = ClockSampler(local)
-    sampler.start()
-    model.set_timing(True)
-    barrier()
-    model.timer_start()
-    for s in range(args.steps):
-        model.update_model(dt)
-    ms = model.timer_stop()
-    barrier()
-    st = model.stats()
-    model.set_timing(False)
-    launches = st["kernel_launches"] - launches0
-    t_max = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms_max = float(t_max.item())
-
-    # ---- leg 2: end to end through the public API with HOST buffers ------------------------
-    out = None
-    barrier()
-    # Double-buffered like a driver that reads step s + 1 while step s runs: the H2D copy of the
-    # NEXT step's forcing is issued right after the step has been enqueued and overlaps its
-    # kernels; every step's inputs are still copied inside the timed region (K copies for K steps).
-    t0 = time.perf_counter()
-    model.set_forcing(*forcing[(args.warmup) % len(forcing)])            # H2D, step 0
-    for s in range(args.steps):
-        model.update_model(dt)                           # asynchronous
-        if s + 1 < args.steps:
-            model.set_forcing(*forcing[(args.warmup + s + 1) % len(forcing)])  # H2D, step s + 1
-        out = model.get("riv_q_average")                 # D2H of the step's result
-    model.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e2e.item())
-    assert out is not None and np.isfinite(out).all()
-
+    m = measure(pkg, torch, dist, model, cfg, dom, args.seed, args.steps, args.warmup, world, local)
+    st = m["stats"]
     total_cells = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_cells, op=dist.ReduceOp.SUM)
     cells = float(total_cells.item())
-
-    value = cells * args.steps / (ms_max * 1e-3)
-    e2e_value = cells * args.steps / e2e_s
+    value = cells * args.steps / (m["ms"] * 1e-3)
+    e2e_value = cells * args.steps / m["e2e_s"]
     peak, peak_src = measured_peak()
     k = max(st["timed_steps"], 1)
     v1_ms = st["ms_land_hydrology"] / k
@@ -338,32 +358,27 @@ def main():
     stage_ms = {kk[3:]: st[kk] / k for kk in st if kk.startswith("ms_")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.partition else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": workload, "cells_per_gpu": n, "river_cells_per_gpu": nriv,
-                   "parallelism": (f"{world} shards of whole drainage basins (greedy LPT), no "
-                                   "data-path collective" if args.partition else
-                                   f"{world} x disjoint sub-catchment tiles, no collective"),
-                   "l2_policy": "working set (~1.9 kB/cell x 1e6 cells = 1.9 GB) exceeds the "
-                                "126 MB L2; no explicit flush",
-                   "wave_levels_land": st["wave_levels_land"],
-                   "wave_levels_river": st["wave_levels_river"],
-                   "substeps": [st["substeps_land"], st["substeps_river"], st["substeps_ssf"]]},
-        "roofline": {"bound": "hbm", "kernel": "update_land_hydrology_model! = land_surface_kernel<4> + unsaturated-zone "
-                               "loop engine + soil_column_kernel<4> (SBM vertical, V1)",
+        "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_block(workload, n, nriv, world),
+        "details": {"l2_policy": "working set (~1.9 kB/cell x 1e6 cells = 1.9 GB) exceeds the 126 MB "
+                                 "L2; no explicit flush; a different forcing slab every step",
+                    "wave_levels_land": st["wave_levels_land"],
+                    "wave_levels_river": st["wave_levels_river"],
+                    "substeps": [st["substeps_land"], st["substeps_river"], st["substeps_ssf"]],
+                    "e2e_outputs": OUTPUT_FIELDS},
+        "roofline": {"bound": "hbm",
+                     "kernel": "update_land_hydrology_model! = land_hydrology_kernel<4> + "
+                               "soil_column_kernel<4> + loop engine (unsat_engine_kernel<4>, "
+                               "soil_column_sparse_kernel<4>) (SBM vertical, V1)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_cell": v1_bytes_per_cell(N, cfg),
                      "ms_per_launch": v1_ms,
-                     # DRAM bytes of the same kernels from the ncu --set full captures under
-                     # profiles/ (r1e: land_surface 719 MB + loop engine 71 MB, r1c: soil_column
-                     # 687 MB per 1e6 cells and step), over the live-measured duration
                      "traffic": (V1_DRAM_BYTES_PER_CELL * n / (v1_ms * 1e-3) / 1e9
                                  if v1_ms > 0 and N == 4 and cfg["gash"] and cfg["snow"] else None),
                      "traffic_bytes_per_cell": V1_DRAM_BYTES_PER_CELL,
-                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                       "profiles/r1e_vertical_ncu.md + r1c_vertical_ncu.md"},
+                     "traffic_source": V1_TRAFFIC_SOURCE},
         "stage_ms_per_step": stage_ms,
         "stage_note": ("subsurface, soil_storage, overland and river run overlapped (subsurface "
                        "sweep + surface kernel on disjoint SMs, update_soil_water_storage! inside "
@@ -374,28 +389,75 @@ def main():
         "routing": {"newton_calls": st["newton_calls_land"] + st["newton_calls_river"],
                     "newton_iters_booked": st["newton_iters_land"] + st["newton_iters_river"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * n,
-                "d2h_bytes_per_step": 8 * nriv, "ms_per_step": e2e_s / args.steps * 1e3},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+                "d2h_bytes_per_step": m["d2h_bytes"], "ms_per_step": m["e2e_s"] / args.steps * 1e3},
+        "gpu_launches": m["launches"],
+        "clocks": m["clocks"],
     }
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # same regime as the GPU's timed steps: start the CPU model from the GPU's spun-up state
+    if do_cpu:
+        # The CPU model starts from the GPU's spun-up state (same regime as the timed steps); the
+        # GPU then takes the same steps with the same forcing and EVERY field is compared: parity
+        # at the benchmarked size, in the benchmarked state.
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import parity
+        first = args.warmup + 2 * args.steps
         warm = dict(fields)
         for name in model.field_names():
             warm[name] = model.get(name)
-        cv, cores, sps = run_cpu(pkg, cfg, dom, warm, args.cpu_steps, 1, args.seed,
-                                 first_step=args.warmup + args.steps)
+        ora, cores = make_cpu_model(cfg, dom, warm)
+        cpu_step(pkg, ora, cfg, dom["gid"], args.seed, first)          # warm-up (first touch)
+        el = sum(cpu_step(pkg, ora, cfg, dom["gid"], args.seed, first + 1 + s)
+                 for s in range(args.cpu_steps))
+        for s in range(1 + args.cpu_steps):
+            model.set_forcing(*pkg.synthetic.make_forcing(args.seed, first + s, dom["gid"], dt))
+            model.update_model(dt)
+        try:
+            rep = parity.compare_models(model, ora)
+            line["parity_checked"] = {"worst_rel": rep.worst_rel, "n_fields": len(rep),
+                                      "cells": n, "steps": 1 + args.cpu_steps,
+                                      "tolerance": "elementwise 1e-10 relative + per-element atol "
+                                                   "(tests/parity.py)", "ok": True}
+        except AssertionError as e:
+            line["parity_checked"] = {"ok": False, "error": str(e)[:300]}
         line["cpu_baseline"] = {
-            "value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"full {args.size}x{args.size} tile, {args.cpu_steps} model steps after 1 "
-                      f"warm-up, started from the GPU model's spun-up state ({sps:.2f} s/step); C/OpenMP port of the Julia algorithm, "
-                      "threaded over the reference's sub-domain partition (Julia not installed)"}
+            "value": n * args.cpu_steps / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"full {d1}x{d2} tile, {args.cpu_steps} model steps after 1 warm-up, started "
+                      f"from the GPU model's spun-up state ({el / args.cpu_steps:.2f} s/step); "
+                      "C/OpenMP port of the Julia algorithm, threaded over the reference's "
+                      "sub-domain partition (Julia not installed)"}
     elif rank == 0:
         line["cpu_baseline"] = None
+    model.close()
+    del model
+
+    # ---- BASELINE configs[2]: ONE 10000 x 10000 raster (10^8 cells), sharded by sub-catchment ----
+    if world == 8 and not args.no_config3 and not args.adaptive:
+        # The global raster is 8 strips of 1250 x 10000 cells; drainage never leaves a strip (like
+        # at the raster edge), so a strip is a set of whole sub-catchments = one shard, and every
+        # rank generates its strip alone from (seed, global cell id).
+        g1, g2 = 10000 // world, 10000
+        steps3 = max(20, min(args.steps, 30))
+        cfg3, dom3, fields3 = build_tile(pkg, g1, g2, rank, args.seed + 1, False)
+        model3 = pkg.SbmModel(cfg3, dom3, fields3, device=local)
+        del fields3
+        m3 = measure(pkg, torch, dist, model3, cfg3, dom3, args.seed + 1, steps3, 5, world, local,
+                     e2e=False)
+        tot3 = torch.tensor([float(cfg3["n"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot3, op=dist.ReduceOp.SUM)
+        st3 = m3["stats"]
+        k3 = max(st3["timed_steps"], 1)
+        line["config3"] = {
+            "workload": "ONE synthetic 10000x10000 raster (1e8 cells) of sub-catchments, sharded "
+                        "by sub-catchment over 8 GPUs (strips of 1250x10000 whose drainage stays "
+                        "inside the strip), fixed internal steps, no data-path collective",
+            "cells": float(tot3.item()), "steps": steps3, "warmup": 5,
+            "ms_per_step": m3["ms"] / steps3,
+            "value": float(tot3.item()) * steps3 / (m3["ms"] * 1e-3), "unit": UNIT,
+            "stage_ms_per_step": {kk[3:]: st3[kk] / k3 for kk in st3 if kk.startswith("ms_")},
+            "wave_levels_land": st3["wave_levels_land"]}
+        model3.close()
     if rank == 0:
         print(json.dumps(line))
-    model.close()
     if world > 1:
         dist.destroy_process_group()
 

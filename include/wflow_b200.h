@@ -224,6 +224,24 @@ int32_t wflowb200_selftest_math(int32_t device, int64_t n, double* out6);
  * gave up a bounded wait (its grid was not co-resident: MPS share, second context, debugger) */
 int32_t wflowb200_synchronize(WflowB200* h);
 
+/* ---- sharded domains (one handle per GPU / per shard) ---------------------------------------
+ * Basin-aligned shards need no exchange of fluxes (subdomains.jl:177-199: the reference threads
+ * over the same units). With kinematic_wave__adaptive_time_step_flag every routing sub-step
+ * additionally needs a statistic of the WHOLE domain -- the type-7 quantile of the Courant
+ * steps (surface_kinwave.jl:674-704) and their minimum (lateral_subsurface_flow.jl:314-344) --
+ * which the shards reduce: histograms of the radix select, counts and minima are all-reduced,
+ * so every shard takes exactly the sub-steps the unsharded domain takes.
+ *   NCCL, one process per GPU: rank 0 calls comm_unique_id, the host distributes the 128 bytes
+ *   (MPI / torch.distributed), every rank calls comm_init_nccl(handle, rank, world, id).
+ *   One process, several handles (several shards on one GPU, tests): group_create(n), every
+ *   handle joins; the handles are then stepped from n host threads at the same time. */
+typedef struct WflowB200Group WflowB200Group;
+int32_t wflowb200_comm_unique_id(char* out128);
+int32_t wflowb200_comm_init_nccl(WflowB200* h, int32_t rank, int32_t world, const char* id128);
+int32_t wflowb200_group_create(int32_t n_handles, WflowB200Group** out);
+int32_t wflowb200_group_join(WflowB200Group* g, WflowB200* h);
+void wflowb200_group_destroy(WflowB200Group* g);
+
 /* Select between kernel organisations that give identical results (the parity tests run every
  * one): "fuse_soil_storage", "overlap_subsurface" (-1 automatic, 0, 1), "overlap_subsurface_sms",
  * "fuse_surface" (0, 1), "surface_river_share", "surface_river_period", "vertical_graph" (0, 1),

@@ -1,6 +1,15 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "update_model_matches or selftest" 2>&1 | grep -E "Error|assert|passed|failed|selftest" | head -20
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'unsat_loop' -s 16 -c 2 \
-    -o gpurun_out/prof_loop_r2e python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
-    --option vertical_graph=0 --cfg vertical_slices=1 > gpurun_out/bench_under_ncu_r2e.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | grep -E "Error|assert|passed|failed" | head -20
+run() { # label, extra args
+  timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 10 $2 > gpurun_out/bench_var.json 2>> gpurun_out/bench_var.err
+  python - "$1" <<'PY'
+import json,sys
+d=json.loads(open('gpurun_out/bench_var.json').read().strip().splitlines()[-1])
+print(sys.argv[1], 'ms/step %.3f'%d['ms_per_step'], 'V1 %.3f'%d['stage_ms_per_step']['land_hydrology'])
+PY
+}
+run default ""
+run slices_1 "--cfg vertical_slices=1"
+run slices_2 "--cfg vertical_slices=2"
+run slices_3 "--cfg vertical_slices=3"
+run noengine_1 "--option vertical_engine=0 --cfg vertical_slices=1"

@@ -276,7 +276,9 @@ class Report(dict):
     def summary(self):
         k = max(self, key=lambda n: self[n]["rel"]) if self else ""
         n_atol = sum(v["need_atol"] for v in self.values())
-        return (f"{len(self)} fields: worst elementwise rel diff {self.worst_rel:.3e} ({k}); "
+        n_outl = sum(v.get("outliers", 0) for v in self.values())
+        extra = f"; {n_outl} threshold outliers" if n_outl else ""
+        return (f"{len(self)} fields: worst elementwise rel diff {self.worst_rel:.3e} ({k}){extra}; "
                 f"{n_atol} elements inside their absolute tolerance only; worst normwise "
                 f"{max((v['norm'] for v in self.values()), default=0.0):.3e}")
 
@@ -285,10 +287,15 @@ def _getter(m):
     return m.get if hasattr(m, "field_names") else (lambda name: m.f[name])
 
 
-def compare_models(gpu, ora, rtol=RTOL, skip=(), verbose=False, names=None):
+def compare_models(gpu, ora, rtol=RTOL, skip=(), verbose=False, names=None, outliers=None):
     """Every Float64 field and the integer fields. NaN (MISSING_VALUE) must match NaN, +-Inf must
     match exactly, integers must be equal; Float64: |g - o| <= rtol |o| + atol_f (module
-    docstring). `gpu` may be a second oracle (tolerance calibration). Returns a Report."""
+    docstring). `gpu` may be a second oracle (tolerance calibration). Returns a Report.
+    outliers = (fraction, rtol_out): at most that fraction of a field's elements may miss the test
+    as long as they pass it with rtol_out -- only for schemes whose own thresholds turn a last-bit
+    difference into a visible one (the local-inertial river flow switches an edge's discharge on
+    where the depth crosses h_thresh exactly, surface_staggered_scheme.jl:359-377); the number of
+    such elements is reported in Report[...]["outliers"]."""
     gget, oget = _getter(gpu), _getter(ora)
     cfg = dict(ora.cfg)
     st = ora.newton_stats()   # sub-steps of the last model step (fixed or adaptive)
@@ -319,12 +326,21 @@ def compare_models(gpu, ora, rtol=RTOL, skip=(), verbose=False, names=None):
         diff = np.abs(np.where(fin, g - o, 0.0))
         mag = np.abs(np.where(fin, o, 0.0))
         bad = diff > rtol * mag + atol
+        n_out = 0
+        if outliers is not None and bad.any():
+            frac, rtol_out = outliers
+            really_bad = diff > rtol_out * mag + atol * (rtol_out / rtol)
+            n_out = int((bad & ~really_bad).sum())
+            if n_out <= frac * max(int(fin.sum()), 1):
+                bad = really_bad
         above = fin & (diff > atol)          # judged by the relative term
         with np.errstate(divide="ignore", invalid="ignore"):
             rel = np.where(above & (mag > 0), diff / np.where(mag > 0, mag, 1.0), 0.0)
         need = fin & (diff > rtol * mag) & ~bad
         scale = float(mag.max())
-        rep[name] = dict(rel=float(rel.max()), need_atol=int(need.sum()),
+        if n_out:
+            rel = np.where(bad | ~(diff > rtol * mag + atol), rel, 0.0)  # outliers reported apart
+        rep[name] = dict(rel=float(rel.max()), need_atol=int(need.sum()), outliers=n_out,
                          norm=float(diff.max() / scale) if scale > 0 else float(diff.max()))
         if verbose:
             print(f"{name:48s} rel {rep[name]['rel']:.3e}  atol-only {rep[name]['need_atol']:8d}  "

@@ -232,7 +232,12 @@ def test_local_inertial_river_flow(pkg, reservoirs):
     of a model step run inside one persistent kernel. Same number of sub-steps as the oracle."""
     gpu, ora, cfg = parity.run_pair(pkg, 70, 110, steps=4, seed=43, river_routing=1,
                                     reservoirs=reservoirs)
-    rep = parity.compare_models(gpu, ora)
+    # The explicit scheme with its wet/dry thresholds (h_thresh, h <= 0 limiters, Froude limit)
+    # amplifies last-bit differences: the oracle against ITSELF on a +-1 ulp noisy libm differs by
+    # up to 8e-3 while the dry channels fill and by ~1e-6 after four days, in nearly every river
+    # element (tests/test_tolerances.py::test_local_inertial_amplifies_last_bit_noise). So river
+    # fields are held to 1e-5 here; everything the river does not touch stays at 1e-10.
+    rep = parity.compare_models(gpu, ora, outliers=(1.0, 1e-5))
     st, o = gpu.stats(), ora.newton_stats()
     assert abs(st["substeps_river"] - o["substeps_river"]) <= 1 and o["substeps_river"] > 20
     assert float(np.max(ora.f["riv_q_average"])) > 0.0
@@ -305,6 +310,56 @@ def test_state_roundtrip_and_set_value(pkg):
     gpu.set("number_of_layers", nl)
     assert np.array_equal(gpu.get("number_of_layers"), nl)
     _close(gpu)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_two_shards_equal_one_handle_bit_for_bit(pkg, adaptive):
+    """The N > 1 PRODUCT path: one domain cut into two shards of whole drainage basins
+    (partition.py), each shard its own handle, against the single-handle run -- bit for bit, with
+    fixed internal time steps (no exchange at all) and with adaptive ones, where the type-7
+    quantile and the minimum of the Courant steps are reduced over the shards (histograms of the
+    radix select, counts, minima: the same reductions run over NCCL with one process per GPU)."""
+    cfg, dom, fields = pkg.synthetic.make_basin(60, 90, seed=27, adaptive=adaptive)
+    dt = cfg["dt"]
+    one = pkg.SbmModel(cfg, dom, fields)
+    shards = pkg.partition.partition_basins(dom, 2)
+    table = dict(pkg._lib.field_table())
+    parts = []
+    for sh in shards:
+        ldom = pkg.partition.shard_domain(dom, sh)
+        lcfg = pkg.partition.shard_config(cfg, sh)
+        lfields = pkg.partition.shard_fields(fields, table, sh)
+        lfields.pop("nlayers_kv", None)
+        parts.append(pkg.SbmModel(lcfg, ldom, lfields))
+    if adaptive:   # a shard refuses to run alone
+        with pytest.raises(pkg.WflowB200Error):
+            parts[0].update_model(dt)
+    group = pkg.ShardGroup(parts)
+    for step in range(3):
+        p, e, t = pkg.synthetic.make_forcing(27, step, dom["gid"], dt)
+        one.set_forcing(p, e, t)
+        one.update_model(dt)
+        for m, sh in zip(parts, shards):
+            m.set_forcing(np.ascontiguousarray(p[sh.cells]), np.ascontiguousarray(e[sh.cells]),
+                          np.ascontiguousarray(t[sh.cells]))
+        group.step_all(dt)
+    st = one.stats()
+    for m in parts:
+        sm = m.stats()
+        for k in ("substeps_land", "substeps_river", "substeps_ssf"):
+            assert sm[k] == st[k], (k, sm[k], st[k])
+    for name in one.field_names():
+        kind = table.get(name, 0)
+        if kind == 4:
+            continue
+        want = one.get(name)
+        got = np.empty_like(want)
+        for m, sh in zip(parts, shards):
+            got[sh.river_cells if kind == 3 else sh.cells] = m.get(name)
+        assert np.array_equal(got, want, equal_nan=True), name
+    print("sub-steps", {k: st[k] for k in st if k.startswith("substeps")})
+    group.close()
+    _close(one, *parts)
 
 
 def test_forcing_ring_cyclic_lai_and_output_gather(pkg):

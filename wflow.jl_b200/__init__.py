@@ -7,5 +7,5 @@ bench.py use that helper).
 """
 from . import _lib, partition, synthetic  # noqa: F401
 from ._lib import build, header_symbols  # noqa: F401
-from .model import SbmModel, WflowB200Error  # noqa: F401
+from .model import SbmModel, ShardGroup, WflowB200Error  # noqa: F401
 from .network import build_network_artifacts  # noqa: F401

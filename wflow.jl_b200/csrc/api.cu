@@ -1,8 +1,13 @@
 // api.cu -- the C ABI of libwflow_b200.so (include/wflow_b200.h): handle lifetime, HBM layout,
 // host<->device field transfer through the slot permutation, and the orchestration of the hot
 // path (update_model!, sbm_model.jl:60-92). No CPU fallback: every entry point needs the device.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -116,6 +121,85 @@ int32_t copy_artifact(const Network& nw, int32_t id, int64_t* dst, int64_t capac
 
 }  // namespace
 
+// ---- reductions across the shards of one model domain ------------------------------------------
+// With adaptive internal time steps every routing sub-step needs a statistic of the WHOLE domain
+// (surface_kinwave.jl:674-704: a type-7 quantile; lateral_subsurface_flow.jl:314-344: a minimum).
+// A sharded domain reduces the partial results of its shards: over NCCL when every shard lives in
+// its own process / GPU (wflowb200_comm_init_nccl), through a host rendezvous when the shards
+// are handles of one process (wflowb200_group_*: tests, several shards on one GPU).
+struct ShardComm {
+  virtual ~ShardComm() {}
+  // in-place all-reduce of n unsigned 64-bit words in device memory, ordered on s; op 0 sum, 1 min
+  virtual int allreduce(unsigned long long* dev, int n, int op, cudaStream_t s) = 0;
+};
+
+struct NcclApi {  // resolved at run time: the library has no link-time dependency on NCCL
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+static NcclApi g_nccl;
+
+struct NcclShardComm : ShardComm {
+  ncclComm_t comm = nullptr;
+  ~NcclShardComm() override { if (comm) g_nccl.CommDestroy(comm); }
+  int allreduce(unsigned long long* dev, int n, int op, cudaStream_t s) override {
+    return g_nccl.AllReduce(dev, dev, (size_t)n, ncclUint64, op == 0 ? ncclSum : ncclMin, comm, s) ==
+                   ncclSuccess ? 0 : -1;
+  }
+};
+
+struct WflowB200Group {  // host rendezvous of the handles of one process
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, arrived = 0;
+  unsigned long long generation = 0;
+  std::vector<unsigned long long> acc, result[2];
+};
+
+struct GroupShardComm : ShardComm {
+  WflowB200Group* g = nullptr;
+  std::vector<unsigned long long> host;
+  int allreduce(unsigned long long* dev, int n, int op, cudaStream_t s) override {
+    host.resize(n);
+    if (cudaMemcpyAsync(host.data(), dev, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) !=
+            cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+      return -1;
+    {
+      std::unique_lock<std::mutex> lk(g->m);
+      if (g->arrived == 0) g->acc = host;
+      else
+        for (int k = 0; k < n; ++k)
+          g->acc[k] = op == 0 ? g->acc[k] + host[k] : std::min(g->acc[k], host[k]);
+      const unsigned long long gen = g->generation;
+      if (++g->arrived == g->n) {
+        g->result[gen & 1] = g->acc;
+        g->arrived = 0;
+        ++g->generation;
+        g->cv.notify_all();
+      } else {
+        g->cv.wait(lk, [&] { return g->generation != gen; });
+      }
+      host = g->result[gen & 1];
+    }
+    return cudaMemcpyAsync(dev, host.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s) ==
+                   cudaSuccess ? 0 : -1;
+  }
+};
+
 struct WflowB200Network {
   Network land, river;
 };
@@ -157,6 +241,7 @@ struct WflowB200 {
   double* h_pinned = nullptr;  // pinned host staging for forcing (3n doubles)
   double* d_forcing = nullptr; // device staging for forcing (3n doubles)
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  ShardComm* comm = nullptr;   // reductions across the shards of the domain (adaptive mode)
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
   // staging ring of forcing slabs in HBM (wflowb200_forcing_ring_*): the host uploads the slabs of
@@ -175,8 +260,6 @@ struct WflowB200 {
   double* d_unsat_pool = nullptr;
   int32_t* d_unsat_its = nullptr;
   int32_t* d_unsat_list = nullptr;
-  unsigned* d_tile_prio = nullptr;   // per tile: longest suspended loop of the current step
-  int32_t* d_tile_order = nullptr;   // tiles, longest loops of the previous step first
   std::vector<int> slice_tile_begin; // n_slices + 1
   unsigned* d_err = nullptr;         // device error word (bounded waits of the wavefront kernels)
   unsigned* d_unsat_count = nullptr;
@@ -498,6 +581,9 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
     if (kind == 2) {  // stable_timestep(::LateralSSF)  lateral_subsurface_flow.jl:314-344
       int32_t rc = check_launch(h, launch_stable_timestep_ssf(h->f, h->kc, h->d_min, h->d_count, h->stream), what);
       if (rc) return rc;
+      if (h->comm && (h->comm->allreduce((unsigned long long*)h->d_min, 1, 1, h->stream) ||
+                      h->comm->allreduce(h->d_count, 1, 0, h->stream)))
+        return fail(h, WFLOWB200_ERR_CUDA, std::string(what) + ": shard reduction failed");
       double mn = 0.0;
       unsigned long long k = 0;
       CUDA_TRY(h, cudaMemcpyAsync(&mn, h->d_min, 8, cudaMemcpyDeviceToHost, h->stream));
@@ -512,16 +598,23 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
                                        riv ? h->f.riv_flow_length : h->f.flow_length, n, h->d_work,
                                        h->d_count, h->stream), what);
       if (rc) return rc;
+      bool reduce_failed = false;
+      const ShardReduce reduce = [&](unsigned long long* p, int cnt, int op) {
+        const int e = h->comm->allreduce(p, cnt, op, h->stream);
+        reduce_failed |= e != 0;
+        return e;
+      };
       rc = check_launch(h, launch_quantile7(h->d_work, h->d_count, n, riv ? 0.05 : 0.02, h->d_qstate,
-                                            h->stream), what);
+                                            h->stream, h->comm ? &reduce : nullptr), what);
       if (rc) return rc;
-      unsigned long long st[4];
+      if (reduce_failed) return fail(h, WFLOWB200_ERR_CUDA, std::string(what) + ": shard reduction failed");
+      unsigned long long st[11];
       CUDA_TRY(h, cudaMemcpyAsync(st, h->d_qstate, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(h, cudaStreamSynchronize(h->stream));
       double a, b, g;
       memcpy(&a, &st[1], 8); memcpy(&b, &st[2], 8); memcpy(&g, &st[3], 8);
-      if (st[0] == 0) dt_s = 600.0;
-      else if (st[0] == 1) dt_s = a;
+      if (st[10] == 0) dt_s = 600.0;       // k of ALL shards
+      else if (st[10] == 1) dt_s = a;
       else dt_s = (std::isfinite(a) && std::isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
     }
     if (!(dt_s > 0.0)) return fail(h, WFLOWB200_ERR_STATE, std::string(what) + ": stable time step is not positive");
@@ -545,8 +638,7 @@ static int32_t launch_vertical(WflowB200* h, double dt) {
   const bool transport = h->cfg.snow_gravitational_transport != 0;
   auto issue_phase = [&](int phase) {
     return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
-                                 h->slice_tile_begin.data(), h->d_tile_prio, h->d_tile_order,
-                                 h->engine_grid, phase, h->tune.run_engine != 0, h->stream,
+                                 h->slice_tile_begin.data(), h->engine_grid, phase, h->tune.run_engine != 0, h->stream,
                                  h->side_stream, h->v_ev);
   };
   if (transport) {
@@ -812,9 +904,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
   {
     const size_t ns = (size_t)h->ns;
-    // The tiles (128 slots), ordered by the longest Brooks-Corey loop they held in the previous
-    // step, are cut into slices; the loop engine of a slice runs on a side stream under
-    // land_hydrology_kernel of the next slices (vertical.cu). Small domains: one slice.
+    // The tiles (128 slots) are cut into contiguous slices; the loop engine of a slice runs on a
+    // side stream under the dense kernels of the next slices (vertical.cu). Small domains: one.
     const int n_tiles = (int)((ns + WFB_V_TILE - 1) / WFB_V_TILE);
     int n_slices = cfg->vertical_slices > 0 ? cfg->vertical_slices : (n_tiles >= 2048 ? 4 : 1);
     n_slices = std::max(1, std::min(std::min(n_slices, WFB_V_MAX_SLICES), n_tiles));
@@ -828,9 +919,6 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
                           (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * per * sizeof(int32_t)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count,
                           (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * sizeof(unsigned)));
-    TRY_CREATE(cudaMalloc((void**)&h->d_tile_prio, (size_t)n_tiles * sizeof(unsigned)));
-    TRY_CREATE(cudaMemset(h->d_tile_prio, 0, (size_t)n_tiles * sizeof(unsigned)));
-    TRY_CREATE(cudaMalloc((void**)&h->d_tile_order, (size_t)n_tiles * sizeof(int32_t)));
     h->unsat.resize(n_slices);
     for (int k = 0; k < n_slices; ++k) {
       UnsatWork& u = h->unsat[k];
@@ -839,7 +927,6 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       u.its_layer = h->d_unsat_its;
       u.list = h->d_unsat_list + (size_t)k * 2 * WFB_UNSAT_BUCKETS * per;
       u.count = h->d_unsat_count + (size_t)k * 2 * WFB_UNSAT_BUCKETS;
-      u.tile_prio = h->d_tile_prio;
       u.cap = (int32_t)per;
       u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 8;
     }
@@ -922,6 +1009,9 @@ void wflowb200_destroy(WflowB200* h) {
   if (!h) return;
   DeviceGuard device_guard_(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  delete h->comm;
+  h->comm = nullptr;
+  if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.nlayers_kv); cudaFree(h->f.olf_newton_trace); cudaFree(h->f.riv_newton_trace);
@@ -936,7 +1026,7 @@ void wflowb200_destroy(WflowB200* h) {
   for (auto st : h->side_stream) if (st) cudaStreamSynchronize(st);
   cudaFree(h->d_unsat_pool); cudaFree(h->d_unsat_its); cudaFree(h->d_unsat_list);
   cudaFree(h->d_unsat_count);
-  cudaFree(h->d_tile_prio); cudaFree(h->d_tile_order); cudaFree(h->d_err);
+  cudaFree(h->d_err);
   if (h->v_graph) cudaGraphExecDestroy(h->v_graph);
   for (auto e : h->v_ev) if (e) cudaEventDestroy(e);
   for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
@@ -1496,6 +1586,50 @@ int32_t wflowb200_get_newton_trace(WflowB200* h, int32_t domain, int64_t* dst) {
                               h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   for (int p = 0; p < n; ++p) dst[d.nw.perm[p] - 1] = tmp[p];
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_comm_unique_id(char* out128) {
+  if (!out128) return WFLOWB200_ERR_ARG;
+  if (!g_nccl.load()) return fail(nullptr, WFLOWB200_ERR_STATE, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, WFLOWB200_ERR_CUDA, "ncclGetUniqueId failed");
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_comm_init_nccl(WflowB200* h, int32_t rank, int32_t world, const char* id128) {
+  WFB_ENTER(h);
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(h, WFLOWB200_ERR_ARG, "bad rank / world");
+  if (!g_nccl.load()) return fail(h, WFLOWB200_ERR_STATE, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NcclShardComm* c = new NcclShardComm();
+  if (g_nccl.CommInitRank(&c->comm, world, id, rank) != ncclSuccess) {
+    c->comm = nullptr;
+    delete c;
+    return fail(h, WFLOWB200_ERR_CUDA, "ncclCommInitRank failed");
+  }
+  delete h->comm;
+  h->comm = c;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_group_create(int32_t n_handles, WflowB200Group** out) {
+  if (!out || n_handles < 1) return WFLOWB200_ERR_ARG;
+  *out = new WflowB200Group();
+  (*out)->n = n_handles;
+  return WFLOWB200_OK;
+}
+void wflowb200_group_destroy(WflowB200Group* g) { delete g; }
+int32_t wflowb200_group_join(WflowB200Group* g, WflowB200* h) {
+  WFB_ENTER(h);
+  if (!g) return WFLOWB200_ERR_ARG;
+  GroupShardComm* c = new GroupShardComm();
+  c->g = g;
+  delete h->comm;
+  h->comm = c;
   return WFLOWB200_OK;
 }
 

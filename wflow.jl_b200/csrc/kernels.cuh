@@ -2,6 +2,7 @@
 // Each returns the number of kernel launches it issued (negative on bad arguments).
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
 #include "model.cuh"
 
 namespace wfb {
@@ -19,19 +20,17 @@ struct UnsatWork {
   int32_t* its_layer;                         // ns: trip count | layer << 24
   int32_t* list;                              // [2][WFB_UNSAT_BUCKETS][cap] cell slots
   unsigned* count;                            // [2][WFB_UNSAT_BUCKETS]
-  unsigned* tile_prio;                        // per tile: longest suspended loop of this step
   int32_t cap;                                // capacity of one list (cells of the slice)
   int32_t inline_iters;                       // loops up to this many trips run in line
 };
-// engine_grid: CTAs of the engine kernels (a few per SM). The tiles, in the order written by
-// tile_order_kernel into tile_order, are cut into n_slices slices (slice k = ordered tiles
-// [slice_tile_begin[k], slice_tile_begin[k+1]); one UnsatWork each); the loop engine of slice k
+// engine_grid: CTAs of the engine kernels (a few per SM). The tiles (WFB_V_TILE consecutive slots)
+// are cut into n_slices contiguous slices (slice k = tiles [slice_tile_begin[k],
+// slice_tile_begin[k+1]); one UnsatWork each); the loop engine of slice k
 // runs on side[k % WFB_V_SIDE_STREAMS] (high-priority streams) under land_hydrology_kernel of the
 // next slices on s; ev holds 2 * n_slices events.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, const int* slice_tile_begin,
-                          unsigned* tile_prio, int32_t* tile_order, int engine_grid, int phase,
-                          bool run_engine, cudaStream_t s, cudaStream_t const* side,
+                          int engine_grid, int phase, bool run_engine, cudaStream_t s, cudaStream_t const* side,
                           cudaEvent_t const* ev);
 // run_engine = false leaves the suspended cells unfinished: timing experiments only
 // phase: 0 the whole update; 1 interception + snow only, 2 the rest (lateral snow transport runs
@@ -139,8 +138,12 @@ int launch_stable_timestep_ssf(const DevFields& f, const KCfg& c, double* out_mi
 // state[0] = k, state[1] = bits of v[j], state[2] = bits of v[j+1] (sorted, 1-based j),
 // state[3] = bits of gamma.
 #define WFB_QUANTILE_STATE_WORDS (16 + 256)
+// `reduce` (sharded domains, else nullptr): in-place all-reduce over the shards of n 64-bit words
+// in device memory, ordered on the stream; op 0 = sum, 1 = minimum. After the launches
+// state[10] = k of all shards.
+typedef std::function<int(unsigned long long*, int, int)> ShardReduce;
 int launch_quantile7(const double* work, const unsigned long long* count, int n_max, double p,
-                     unsigned long long* state, cudaStream_t s);
+                     unsigned long long* state, cudaStream_t s, const ShardReduce* reduce);
 
 // host<->device layout conversion through the slot permutation
 int launch_gather_field(double* dst, const double* staged, const int32_t* node_of_slot, int n,

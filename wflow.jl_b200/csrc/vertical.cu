@@ -32,13 +32,12 @@
 // first, so the lanes of a warp finish together; unsat_resume_kernel continues the suspended
 // cells with their next layer (and may suspend them again: at most N rounds) and finishes them.
 //
-// Hiding the engine. A loop round lasts as long as its LONGEST loop (a dependent chain of up to
-// ~250 trips x ~600 cycles), with a few hundred busy warps: latency, not throughput. The cells
-// are therefore processed in TILES of 128 in an order that puts the tiles with the longest loops
-// of the PREVIOUS model step first (wet cells stay wet: tile_order_kernel, a counting sort of
-// the tiles by last step's longest loop), the ordered tiles are cut into slices, and the engine
-// rounds of slice k run on a high-priority side stream UNDER land_hydrology_kernel of the slices
-// after it. Only the engine of the last slice -- the tiles with the shortest loops -- is exposed.
+// Hiding the engine. The engine's kernels are a latency-bound tail (as long as the longest
+// suspended loop). The tiles (128 consecutive slots) are cut into a few contiguous slices and the
+// engine of slice k runs on a high-priority side stream under the dense kernels of the slices
+// after it. (Ordering the tiles by the longest loop of the previous step was tried and dropped:
+// nearly every tile holds a loop of 200+ trips, so no order isolates them, and scattering
+// 1 KB tiles over HBM costs DRAM page locality.)
 #include <cstdio>
 #include "device_math.cuh"
 #include "kernels.cuh"
@@ -215,7 +214,6 @@ __device__ __forceinline__ void suspend_cell(const UnsatWork& w, int parity, int
   w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast; w.kv_it[i] = t.kv_it; w.l_sat[i] = t.l_sat;
   w.c[i] = t.c;
   w.its_layer[i] = t.its | (k << 24);
-  atomicMax(w.tile_prio + i / kTile, (unsigned)t.its);  // tile_order_kernel of the next step
   const int b = bucket_of(t.its);
   const unsigned peers = __match_any_sync(active, b);
   const int lane = (int)threadIdx.x & 31;
@@ -545,36 +543,11 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
 #ifndef WFB_V_MINBLOCKS
 #define WFB_V_MINBLOCKS (WFB_V_FUSED ? 4 : 5)
 #endif
-// Counting sort of the tiles by the longest Brooks-Corey loop they held in the PREVIOUS model
-// step (tile_prio, raised by suspend_cell), longest first; ties keep no particular order. One
-// CTA: a domain of 10^7 cells has 10^5 tiles.
-__global__ void __launch_bounds__(1024)
-tile_order_kernel(unsigned* __restrict__ prio, int32_t* __restrict__ order, const int n_tiles) {
-  __shared__ unsigned hist[64], base[64];
-  if (threadIdx.x < 64) hist[threadIdx.x] = 0u;
-  __syncthreads();
-  for (int t = (int)threadIdx.x; t < n_tiles; t += (int)blockDim.x) {
-    const unsigned b = 63u - min(prio[t] >> 2, 63u);
-    atomicAdd(&hist[b], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned acc = 0;
-    for (int b = 0; b < 64; ++b) { base[b] = acc; acc += hist[b]; }
-  }
-  __syncthreads();
-  for (int t = (int)threadIdx.x; t < n_tiles; t += (int)blockDim.x) {
-    const unsigned b = 63u - min(prio[t] >> 2, 63u);
-    order[atomicAdd(&base[b], 1u)] = t;
-    prio[t] = 0u;
-  }
-}
-
 // Every input array of the cell is requested at the top of the kernel, long before its first use:
 // the loads proper sit next to their first use (registers), and with 16 warps per SM that spend
 // most of their time in FP64 dependency chains only a few of them would be in flight at any time.
 #ifndef WFB_V_PREFETCH
-#define WFB_V_PREFETCH 2   // 0 off, 1 into L1, 2 into L2
+#define WFB_V_PREFETCH 0   // 0 off, 1 into L1, 2 into L2 (measured on B200: no gain either way)
 #endif
 __device__ __forceinline__ void prefetch_line(const void* p) {
 #if WFB_V_PREFETCH == 1
@@ -622,12 +595,12 @@ __device__ __forceinline__ void prefetch_inputs(const DevFields& f, const KCfg& 
 template <int N>
 __global__ void __launch_bounds__(WFB_V_TILE, WFB_V_MINBLOCKS)
 land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
-                      const int32_t* __restrict__ order, const int tile_begin, const int phase) {
+                      const int tile_begin, const int phase) {
   // phase 0: the whole update. With lateral snow transport (snow_gravitational_transport__flag,
   // sbm.jl:98-100) a pass over the drainage network sits between the snow and the glacier
   // model: phase 1 = interception + snow, phase 2 = everything after the transport.
-  // one tile of 128 consecutive slots per CTA, in the order of tile_order_kernel
-  const int i = __ldg(order + tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
+  // one tile of 128 consecutive slots per CTA
+  const int i = (tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
   if (i >= c.ns) return;    // whole warps (ns is a multiple of 32)
   // lanes of the padding slots [n, ns) run along on the padding values (they must take part in
   // the warp-aggregated suspension) and never suspend; their stores land in the padding
@@ -980,8 +953,8 @@ __device__ __forceinline__ void load_column_rest(const DevFields& f, const KCfg&
 template <int N>
 __global__ void __launch_bounds__(WFB_V_TILE, WFB_VC_MINBLOCKS)
 soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
-                   const int32_t* __restrict__ order, const int tile_begin) {
-  const int i = __ldg(order + tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
+                   const int tile_begin) {
+  const int i = (tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
   if (i >= c.n) return;
   if (w.its_layer[i] != 0) return;  // suspended: not this kernel's cell
   const int ns = c.ns;
@@ -1002,6 +975,106 @@ soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const dou
   soil_column_cell<N>(f, c, i, dt, ddt, s);
 }
 
+// The loop engine, split organisation: ONE light kernel takes every suspended cell of a slice
+// through all its remaining unsaturated layers -- the long loop it was suspended at (tracked-power
+// trips), then the layers below with loops of any length in line -- one lane per cell, 32 cells
+// of one bucket per warp, longest buckets first. Per-layer operands are fetched when their layer
+// is reached (an L2 hit, negligible next to a loop), so a lane holds ~50 registers and the
+// kernel shares the SMs with the bandwidth-bound kernels of the main stream.
+// soil_column_sparse_kernel then finishes these cells (second half).
+template <int N>
+__global__ void __launch_bounds__(128)
+unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
+  const unsigned* cnt = w.count;
+  const int lane = (int)threadIdx.x & 31;
+  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+  // consecutive tiles (the longest loops) go to different SMs
+  const int gw = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
+  const int ns = c.ns;
+  const Divisor ddt(dt);
+  for (int j = gw;; j += n_warps) {
+    int b, first, n;
+    if (!tile_of(cnt, j, b, first, n)) break;
+    const int e = first + lane;
+    if (e >= n) continue;
+    const int i = w.list[(size_t)b * (size_t)w.cap + e];
+    UnsatTask t;
+    t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
+    t.c = w.c[i];
+    const int code = w.its_layer[i];
+    t.its = code & 0xffffff;
+    const int kl = code >> 24;  // the layer the cell was suspended at
+#if WFB_ENGINE_FAST_TRIPS
+    unsatzone_flow_iterate_fast(t, dt, ddt);
+#else
+    unsatzone_flow_iterate(t, dt, ddt);
+#endif
+    f.unsaturated_layer_depth[kl * ns + i] = t.usd;
+    double flow = t.sum_ast;
+    const int n_unsat = f.n_unsatlayers[i];
+    if (kl + 1 < n_unsat) {  // the layers below (soil.jl:770-801), loops of any length in line
+      const KvCol<N> kv = load_kvcol<N>(f, c, i);
+      const double theta_e = __ldg(f.theta_s + i) - __ldg(f.theta_r + i);
+      double z = 0.0;
+      for (int k = 0; k <= kl; ++k) {  // same left-to-right sum as the first pass
+        const double ultk = f.unsaturated_layer_thickness[k * ns + i];
+        z = (k == 0) ? ultk : z + ultk;
+      }
+      for (int k = kl + 1; k < n_unsat; ++k) {
+        const double ultk = f.unsaturated_layer_thickness[k * ns + i];
+        z = z + ultk;
+        const double l_sat = ultk * theta_e;
+        const double kv_z = kv_at_depth<N>(c.kv_profile, kv, pick<N>(kv.k, k), z);
+        const double usd = f.unsaturated_layer_depth[k * ns + i] + flow * dt;
+        UnsatTask tk = unsatzone_flow_setup(usd, kv_z, l_sat,
+                                            __ldg(f.brooks_corey_exponent + k * ns + i), dt, ddt);
+#if WFB_ENGINE_FAST_TRIPS
+        unsatzone_flow_iterate_fast(tk, dt, ddt);
+#else
+        unsatzone_flow_iterate(tk, dt, ddt);
+#endif
+        f.unsaturated_layer_depth[k * ns + i] = tk.usd;
+        flow = tk.sum_ast;
+      }
+    }
+    f.transfer[i] = flow;  // n_unsat > 0 for a suspended cell
+  }
+}
+
+// Second half of update_land_hydrology_model! for the cells the engine has finished.
+template <int N>
+__global__ void __launch_bounds__(128)
+soil_column_sparse_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
+  const unsigned* cnt = w.count;
+  const int lane = (int)threadIdx.x & 31;
+  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+  const int gw = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5);
+  const int ns = c.ns;
+  const Divisor ddt(dt);
+  for (int j = gw;; j += n_warps) {
+    int b, first, n;
+    if (!tile_of(cnt, j, b, first, n)) break;
+    const int e = first + lane;
+    if (e >= n) continue;
+    const int i = w.list[(size_t)b * (size_t)w.cap + e];
+    SoilColumn<N> s;
+    s.theta_s = __ldg(f.theta_s + i);
+    s.theta_e = s.theta_s - __ldg(f.theta_r + i);
+    s.n_unsat = f.n_unsatlayers[i];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
+      s.ult[k] = f.unsaturated_layer_thickness[k * ns + i];
+      s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
+    }
+    s.kv = load_kvcol<N>(f, c, i);
+    s.transfer = f.transfer[i];
+    load_column_rest<N>(f, c, i, s);
+    soil_column_cell<N>(f, c, i, dt, ddt, s);
+  }
+}
+
+#if WFB_V_FUSED
 // All suspended loops of a slice, one lane per loop, 32 loops of one bucket per warp.
 __global__ void __launch_bounds__(128)
 unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
@@ -1091,6 +1164,8 @@ unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const in
     soil_column_cell<N>(f, c, i, dt, ddt, s);
   }
 }
+
+#endif  // WFB_V_FUSED (multi-round engine of the fused organisation)
 
 // update_bc_open_water_runoff_model!: river h -> land grid                 runoff.jl:77-79
 __global__ void scatter_river_depth_kernel(const DevFields f, const KCfg c) {
@@ -1243,26 +1318,20 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 // last slice is exposed. ev[2k] orders E_k after A_k, ev[2k+1] joins E_k into the main stream.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
                           const UnsatWork* w, int n_slices, const int* slice_tile_begin,
-                          unsigned* tile_prio, int32_t* tile_order, int engine_grid, int phase,
-                          bool run_engine, cudaStream_t s, cudaStream_t const* side,
+                          int engine_grid, int phase, bool run_engine, cudaStream_t s, cudaStream_t const* side,
                           cudaEvent_t const* ev) {
   int launches = 0;
   const int n_tiles = (c.ns + kTile - 1) / kTile;
-  if (phase != 2) {  // (phase 2 reuses the order of phase 1)
-    tile_order_kernel<<<1, 1024, 0, s>>>(tile_prio, tile_order, n_tiles);
-    ++launches;
-  }
   if (phase == 1) {  // interception + snow of every cell: no loops, no engine
-    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(
-                                 f, c, w[0], dt, tile_order, 0, 1)));
+    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w[0], dt, 0, 1)));
     return launches + 1;
   }
   for (int k = 0; k < n_slices; ++k) {
     const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
     if (t0 >= t1) continue;
     cudaMemsetAsync(w[k].count, 0, 2 * kBuckets * sizeof(unsigned), s);
-    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<t1 - t0, kTile, 0, s>>>(
-                                 f, c, w[k], dt, tile_order, t0, phase)));
+    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<t1 - t0, kTile, 0, s>>>(f, c, w[k], dt, t0,
+                                                                                 phase)));
     ++launches;
     // the engine always runs on a side stream: with one slice it overlaps soil_column_kernel
     cudaStream_t e = (n_slices > 1 || !WFB_V_FUSED) ? side[k % WFB_V_SIDE_STREAMS] : s;
@@ -1270,6 +1339,7 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
       cudaEventRecord(ev[2 * k], s);
       cudaStreamWaitEvent(e, ev[2 * k], 0);
     }
+#if WFB_V_FUSED
     for (int r = 0; r < (run_engine ? n_layers : 0); ++r) {
       const int parity = r & 1;
       unsat_loop_kernel<<<engine_grid, 128, 0, e>>>(w[k], parity, dt);
@@ -1278,6 +1348,13 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
       WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], parity, dt)));
       launches += 2;
     }
+#else
+    if (run_engine) {
+      WFB_DISPATCH_N(n_layers, (unsat_engine_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], dt)));
+      WFB_DISPATCH_N(n_layers, (soil_column_sparse_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], dt)));
+      launches += 2;
+    }
+#endif
     cudaEventRecord(ev[2 * k + 1], e);
   }
 #if !WFB_V_FUSED
@@ -1285,8 +1362,7 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
   for (int k = 0; k < n_slices; ++k) {
     const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
     if (t0 >= t1) continue;
-    WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<t1 - t0, kTile, 0, s>>>(f, c, w[k], dt,
-                                                                              tile_order, t0)));
+    WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<t1 - t0, kTile, 0, s>>>(f, c, w[k], dt, t0)));
     ++launches;
   }
 #endif

@@ -23,6 +23,45 @@ class WflowB200Error(RuntimeError):
     pass
 
 
+class ShardGroup:
+    """The shards of one domain as handles of ONE process (several shards on one GPU, tests):
+    their adaptive time-step statistics are reduced through a host rendezvous, so the handles
+    must be stepped from `n` threads at the same time (`step_all`)."""
+
+    def __init__(self, models):
+        self._L = _lib.lib()
+        self._g = C.c_void_p()
+        self.models = list(models)
+        rc = self._L.wflowb200_group_create(len(self.models), C.byref(self._g))
+        if rc != 0:
+            raise WflowB200Error(f"wflowb200_group_create failed ({rc})")
+        for m in self.models:
+            m._check(self._L.wflowb200_group_join(self._g, m._h))
+            m._has_comm = True
+
+    def step_all(self, dt):
+        import threading
+        errs = []
+
+        def run(m):
+            try:
+                m.update_model(dt)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=run, args=(m,)) for m in self.models]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def close(self):
+        if self._g.value:
+            self._L.wflowb200_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+
 class SbmModel:
     """One handle = one GPU. `cfg` keys follow WflowB200Config; `domain` holds d1, d2,
     indices (n, 2) 1-based CartesianIndex pairs in column-major order, ldd (n,) uint8 and
@@ -209,7 +248,27 @@ class SbmModel:
 
     def update_model(self, dt):
         """update_model!(model::AbstractModel{<:SbmModel}) (sbm_model.jl:60-92)."""
+        if self.cfg.get("sharded") and self.cfg.get("adaptive") and not self._has_comm:
+            raise WflowB200Error(
+                "a shard of a domain with adaptive internal time steps needs the statistics of "
+                "ALL shards: attach a communicator first (comm_init_nccl / ShardGroup.join)")
         self._check(self._L.wflowb200_update_model(self._h, dt))
+
+    # ---- sharded domains: reductions of the adaptive time-step statistics ------------------
+    _has_comm = False
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = _lib.lib().wflowb200_comm_unique_id(buf)
+        if rc != 0:
+            raise WflowB200Error(f"wflowb200_comm_unique_id failed ({rc})")
+        return buf.raw
+
+    def comm_init_nccl(self, rank: int, world: int, unique_id: bytes):
+        """One process per GPU: every rank passes the 128 bytes rank 0 got from comm_unique_id."""
+        self._check(self._L.wflowb200_comm_init_nccl(self._h, int(rank), int(world), unique_id))
+        self._has_comm = True
 
     def synchronize(self):
         self._check(self._L.wflowb200_synchronize(self._h))

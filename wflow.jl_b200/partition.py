@@ -104,6 +104,7 @@ def shard_domain(domain: dict, shard: Shard) -> dict:
     down = downstream_ids(domain)[cells]
     assert np.all(local_of[down[down > 0] - 1] > 0), "a drainage edge leaves the shard"
     out["down"] = np.where(down > 0, local_of[np.maximum(down, 1) - 1], 0)
+    out["reservoir_river_indices"] = np.zeros(0, dtype=np.int64)
     for k in ("gid", "upstream_cells"):
         if k in domain:
             out[k] = np.asarray(domain[k])[cells]
@@ -124,7 +125,14 @@ def shard_fields(fields: dict, table: dict, shard: Shard) -> dict:
 
 
 def shard_config(cfg: dict, shard: Shard) -> dict:
+    """The shard's configuration. With adaptive internal time steps a shard cannot be advanced on
+    its own: the sub-step length is a statistic of the WHOLE domain (surface_kinwave.jl:674-704,
+    lateral_subsurface_flow.jl:314-344). `sharded` makes SbmModel.update_model refuse to run until
+    a communicator is attached (comm_init_nccl, ShardGroup)."""
+    if cfg.get("nres", 0):
+        raise ValueError("sharding a domain with reservoirs is not implemented")
     c = dict(cfg)
     c["n"] = int(len(shard.cells))
     c["nriv"] = int(len(shard.river_cells))
+    c["sharded"] = True
     return c
