@@ -70,7 +70,7 @@ typedef struct {
                                   (routing/utils.jl:2); 0 -> library uses pow(1e-30, 0.2)      */
   /* B200 tuning, fixed at create; 0 = automatic (chosen from the shape of the domain) */
   int32_t wave_piece_depth_land; /* levels per piece of the land chunks; -1: one connected piece */
-  int32_t vertical_slices;       /* slices of the vertical update (loop engine overlap), 1..8   */
+  int32_t vertical_slices;       /* unused (kept for ABI stability)                             */
   int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (8)    */
   int32_t snow_gravitational_transport; /* snow_gravitational_transport__flag: lateral snow
                                   transport between snow and glacier model     sbm.jl:98-100 */
@@ -178,6 +178,13 @@ int32_t wflowb200_use_cyclic_lai(WflowB200* h, int32_t slab);
  * listed fields, concatenated in this order (node order, layered fields cell-major), with ONE
  * device-to-host copy through page-locked memory. dst holds the sum of the fields' sizes. */
 int32_t wflowb200_get_fields(WflowB200* h, const int32_t* field_ids, int32_t n_ids, double* dst);
+/* The same without blocking: dst must be page-locked (cudaHostRegister / cudaMallocHost); the
+ * fields are packed on the compute stream, copied on the copy stream, and the next update_* call
+ * may be issued at once (the output writer of step s runs while step s + 1 computes).
+ * wait_outputs blocks until every pending copy has landed. */
+int32_t wflowb200_get_fields_async(WflowB200* h, const int32_t* field_ids, int32_t n_ids,
+                                   double* dst_pinned);
+int32_t wflowb200_wait_outputs(WflowB200* h);
 
 /* ---- the hot path --------------------------------------------------------------------- */
 
@@ -247,6 +254,10 @@ void wflowb200_group_destroy(WflowB200Group* g);
  * "fuse_surface" (0, 1), "surface_river_share", "surface_river_period", "vertical_graph" (0, 1),
  * "kinwave_root_each_substep" (0, 1: see below). */
 int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value);
+/* Developer aid: with the options "vertical_timeline" = 1 and "vertical_graph" = 0, the completion
+ * times [ms since the start of the last vertical update] of its kernels: [0] = 0,
+ * [1] land_hydrology_kernel, [2] unsat_engine_kernel, [3] soil_column_kernel. capacity >= 4. */
+int32_t wflowb200_get_vertical_timeline(WflowB200* h, double* out_ms, int32_t capacity);
 /* "kinwave_root_each_substep" = 1 additionally evaluates u_prev = pow(q_prev, 0.2) before EVERY
  * kinematic-wave solve like surface_process.jl:33 (default: the fifth root is carried from the
  * previous solve of the node, within half an ulp of it; one pow per node and model step). */

@@ -20,6 +20,10 @@ for v in "$@"; do
     fused) build fused -DWFB_V_FUSED=1 ;;
     slowtrips) build slowtrips -DWFB_ENGINE_FAST_TRIPS=0 ;;
     a6) build a6 -DWFB_V_MINBLOCKS=6 ;;
+    a8) build a8 -DWFB_V_MINBLOCKS=8 ;;
+    c6) build c6 -DWFB_VC_MINBLOCKS=6 ;;
+    c8) build c8 -DWFB_VC_MINBLOCKS=8 ;;
+    a6c6) build a6c6 -DWFB_V_MINBLOCKS=6 -DWFB_VC_MINBLOCKS=6 ;;
     a4) build a4 -DWFB_V_MINBLOCKS=4 ;;
     c5) build c5 -DWFB_VC_MINBLOCKS=5 ;;
     c3) build c3 -DWFB_VC_MINBLOCKS=3 ;;

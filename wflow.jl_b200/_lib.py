@@ -110,6 +110,8 @@ def lib():
     L.wflowb200_set_cyclic_lai.argtypes = [vp, vp, i32]
     L.wflowb200_use_cyclic_lai.argtypes = [vp, i32]
     L.wflowb200_get_fields.argtypes = [vp, vp, i32, vp]
+    L.wflowb200_get_fields_async.argtypes = [vp, vp, i32, vp]
+    L.wflowb200_wait_outputs.argtypes = [vp]
     L.wflowb200_comm_unique_id.argtypes = [C.c_char_p]
     L.wflowb200_comm_init_nccl.argtypes = [vp, i32, i32, C.c_char_p]
     L.wflowb200_group_create.argtypes = [i32, C.POINTER(vp)]
@@ -117,6 +119,7 @@ def lib():
     L.wflowb200_group_destroy.argtypes = [vp]
     L.wflowb200_group_destroy.restype = None
     L.wflowb200_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.wflowb200_get_vertical_timeline.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.wflowb200_newton_trace.argtypes = [vp, i32]
     L.wflowb200_get_newton_trace.argtypes = [vp, i32, vp]
     L.wflowb200_selftest_math.argtypes = [i32, i64, C.POINTER(C.c_double)]

@@ -214,6 +214,7 @@ struct Tuning {
   int river_share = 1, river_period = 3;  // warps of the surface kernel serving the river
   int use_graph = 1;          // vertical update as one CUDA graph launch
   int run_engine = 1;         // 0: skip the loop engine (timing experiments; results invalid)
+  int timeline = 0;           // record completion events of the vertical kernels (graph off)
 };
 
 struct WflowB200 {
@@ -255,17 +256,19 @@ struct WflowB200 {
   int lai_slabs = 0;
   double* h_out_pinned = nullptr;          // pinned staging of wflowb200_get_fields
   size_t out_pinned_doubles = 0;
+  double* d_out[2] = {nullptr, nullptr};   // device staging of the asynchronous output gather
+  size_t out_doubles[2] = {0, 0};
+  int out_parity = 0;
+  cudaEvent_t out_gathered = nullptr, out_copied[2] = {nullptr, nullptr};
   unsigned* d_queue = nullptr;
-  std::vector<UnsatWork> unsat;      // scratch of the unsaturated-zone engine, per slice
+  UnsatWork unsat{};                 // scratch of the unsaturated-zone engine
   double* d_unsat_pool = nullptr;
   int32_t* d_unsat_its = nullptr;
   int32_t* d_unsat_list = nullptr;
-  std::vector<int> slice_tile_begin; // n_slices + 1
   unsigned* d_err = nullptr;         // device error word (bounded waits of the wavefront kernels)
   unsigned* d_unsat_count = nullptr;
   int engine_grid = 0;
-  cudaStream_t side_stream[WFB_V_SIDE_STREAMS] = {};  // high priority: the loop engines
-  cudaEvent_t v_ev[2 * WFB_V_MAX_SLICES] = {};
+  cudaEvent_t tl_ev[4] = {};         // timeline of the vertical kernels (developer aid)
   cudaGraphExec_t v_graph = nullptr;  // the vertical update of one step, captured once per dt
   double v_graph_dt = 0.0;
   int v_graph_launches = 0;
@@ -631,15 +634,14 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
 
 }  // namespace
 
-// update_land_hydrology_model! as ONE graph launch: the slices, their engine rounds on the side
-// streams and the ordering events (~50 kernel launches and memsets per step) are captured once
-// per time step length; issuing them one by one costs more host time than the GPU needs.
+// update_land_hydrology_model! as ONE graph launch (a memset and three kernels), captured once
+// per time step length.
 static int32_t launch_vertical(WflowB200* h, double dt) {
   const bool transport = h->cfg.snow_gravitational_transport != 0;
   auto issue_phase = [&](int phase) {
-    return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat.data(), (int)h->unsat.size(),
-                                 h->slice_tile_begin.data(), h->engine_grid, phase, h->tune.run_engine != 0, h->stream,
-                                 h->side_stream, h->v_ev);
+    return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->engine_grid, phase,
+                                 h->tune.run_engine != 0, h->stream,
+                                 (h->tune.timeline && !h->tune.use_graph) ? h->tl_ev : nullptr);
   };
   if (transport) {
     // interception + snow, lateral_snow_transport! over the land network (sbm.jl:98-100), then
@@ -904,40 +906,21 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   TRY_CREATE(cudaMalloc((void**)&h->d_queue, 3 * 32 * sizeof(unsigned)));
   {
     const size_t ns = (size_t)h->ns;
-    // The tiles (128 slots) are cut into contiguous slices; the loop engine of a slice runs on a
-    // side stream under the dense kernels of the next slices (vertical.cu). Small domains: one.
-    const int n_tiles = (int)((ns + WFB_V_TILE - 1) / WFB_V_TILE);
-    int n_slices = cfg->vertical_slices > 0 ? cfg->vertical_slices : (n_tiles >= 2048 ? 4 : 1);
-    n_slices = std::max(1, std::min(std::min(n_slices, WFB_V_MAX_SLICES), n_tiles));
-    h->slice_tile_begin.resize(n_slices + 1);
-    for (int k = 0; k <= n_slices; ++k)
-      h->slice_tile_begin[k] = (int)((int64_t)n_tiles * k / n_slices);
-    const size_t per = ((size_t)(n_tiles + n_slices - 1) / n_slices + 1) * WFB_V_TILE;  // cells per slice
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_pool, 5 * ns * sizeof(double)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_its, ns * sizeof(int32_t)));
-    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_list,
-                          (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * per * sizeof(int32_t)));
-    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count,
-                          (size_t)n_slices * 2 * WFB_UNSAT_BUCKETS * sizeof(unsigned)));
-    h->unsat.resize(n_slices);
-    for (int k = 0; k < n_slices; ++k) {
-      UnsatWork& u = h->unsat[k];
-      u.usd = h->d_unsat_pool; u.sum_ast = u.usd + ns; u.kv_it = u.sum_ast + ns;
-      u.l_sat = u.kv_it + ns; u.c = u.l_sat + ns;   // per-cell records: shared by the slices
-      u.its_layer = h->d_unsat_its;
-      u.list = h->d_unsat_list + (size_t)k * 2 * WFB_UNSAT_BUCKETS * per;
-      u.count = h->d_unsat_count + (size_t)k * 2 * WFB_UNSAT_BUCKETS;
-      u.cap = (int32_t)per;
-      u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 8;
-    }
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_list, (size_t)WFB_UNSAT_BUCKETS * ns * sizeof(int32_t)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count, WFB_UNSAT_BUCKETS * sizeof(unsigned)));
+    UnsatWork& u = h->unsat;
+    u.usd = h->d_unsat_pool; u.sum_ast = u.usd + ns; u.kv_it = u.sum_ast + ns;
+    u.l_sat = u.kv_it + ns; u.c = u.l_sat + ns;
+    u.its_layer = h->d_unsat_its;
+    u.list = h->d_unsat_list;
+    u.count = h->d_unsat_count;
+    u.cap = (int32_t)ns;
+    u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 8;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     h->engine_grid = std::max(1, sms) * 8;
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    for (auto& st : h->side_stream)
-      TRY_CREATE(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
-    for (auto& e : h->v_ev) TRY_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   TRY_CREATE(cudaMalloc((void**)&h->d_err, sizeof(unsigned)));
   TRY_CREATE(cudaMemset(h->d_err, 0, sizeof(unsigned)));
@@ -1021,15 +1004,16 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
   cudaFree(h->d_ring); cudaFree(h->d_lai_table); cudaFreeHost(h->h_out_pinned);
+  cudaFree(h->d_out[0]); cudaFree(h->d_out[1]);
+  if (h->out_gathered) cudaEventDestroy(h->out_gathered);
+  for (auto e : h->out_copied) if (e) cudaEventDestroy(e);
   for (auto e : h->ring_ready) if (e) cudaEventDestroy(e);
   for (auto e : h->ring_consumed) if (e) cudaEventDestroy(e);
-  for (auto st : h->side_stream) if (st) cudaStreamSynchronize(st);
   cudaFree(h->d_unsat_pool); cudaFree(h->d_unsat_its); cudaFree(h->d_unsat_list);
   cudaFree(h->d_unsat_count);
   cudaFree(h->d_err);
   if (h->v_graph) cudaGraphExecDestroy(h->v_graph);
-  for (auto e : h->v_ev) if (e) cudaEventDestroy(e);
-  for (auto st : h->side_stream) if (st) cudaStreamDestroy(st);
+  for (auto e : h->tl_ev) if (e) cudaEventDestroy(e);
   cudaFree(h->d_stats); cudaFree(h->d_count); cudaFree(h->d_min);
   cudaFree(h->d_work); cudaFree(h->d_qstate); cudaFree(h->ssf_q_out);
   free_domain(h->land); free_domain(h->river); free_domain(h->land_full);
@@ -1260,6 +1244,65 @@ int32_t wflowb200_get_fields(WflowB200* h, const int32_t* ids, int32_t n_ids, do
   rc = check_device_error(h);
   if (rc) return rc;
   memcpy(dst, h->h_out_pinned, total * sizeof(double));
+  return WFLOWB200_OK;
+}
+
+// The same gather without blocking the compute stream: the fields are packed on the compute
+// stream into one of two device staging buffers, the device-to-host copy runs on the copy stream
+// (dst must be page-locked), and the next update_* calls may be enqueued at once.
+// wflowb200_wait_outputs blocks until every pending copy has landed in its dst.
+int32_t wflowb200_get_fields_async(WflowB200* h, const int32_t* ids, int32_t n_ids, double* dst) {
+  WFB_ENTER(h);
+  if (!ids || !dst || n_ids < 1) return WFLOWB200_ERR_ARG;
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, dst) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    return fail(h, WFLOWB200_ERR_ARG, "get_fields_async needs a page-locked destination");
+  }
+  size_t total = 0;
+  for (int k = 0; k < n_ids; ++k) {
+    if (ids[k] < 0 || ids[k] >= WFLOWB200_NUM_FIELDS) return fail(h, WFLOWB200_ERR_ARG, "bad field id");
+    const int kind = kFieldKinds[ids[k]];
+    total += (size_t)count_of(h, kind) * layers_of(h, kind);
+  }
+  int32_t rc = wait_forcing(h);
+  if (rc) return rc;
+  if (!h->out_gathered) {
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->out_gathered, cudaEventDisableTiming));
+    for (auto& e : h->out_copied) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int b = h->out_parity;
+  h->out_parity ^= 1;
+  if (total > h->out_doubles[b]) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    cudaFree(h->d_out[b]);
+    h->d_out[b] = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_out[b], total * sizeof(double)));
+    h->out_doubles[b] = total;
+  }
+  // the copy that last used this staging buffer must have left it
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->out_copied[b], 0));
+  size_t off = 0;
+  for (int k = 0; k < n_ids; ++k) {
+    const int kind = kFieldKinds[ids[k]];
+    const int layers = layers_of(h, kind), count = count_of(h, kind);
+    if (count == 0) continue;
+    const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+    h->launches += launch_scatter_field(h->d_out[b] + off, h->field_ptr[ids[k]], slot_map, count,
+                                        slots_of(h, kind), layers, layers, 1, h->stream);
+    off += (size_t)count * layers;
+  }
+  CUDA_TRY(h, cudaEventRecord(h->out_gathered, h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->out_gathered, 0));
+  CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_out[b], total * sizeof(double), cudaMemcpyDeviceToHost,
+                              h->copy_stream));
+  CUDA_TRY(h, cudaEventRecord(h->out_copied[b], h->copy_stream));
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_wait_outputs(WflowB200* h) {
+  WFB_ENTER(h);
+  CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
   return WFLOWB200_OK;
 }
 
@@ -1633,6 +1676,21 @@ int32_t wflowb200_group_join(WflowB200Group* g, WflowB200* h) {
   return WFLOWB200_OK;
 }
 
+int32_t wflowb200_get_vertical_timeline(WflowB200* h, double* out_ms, int32_t capacity) {
+  WFB_ENTER(h);
+  const int n = 4;
+  if (!out_ms || capacity < n) return fail(h, WFLOWB200_ERR_ARG, "timeline buffer too small");
+  if (!h->tune.timeline || h->tune.use_graph || !h->tl_ev[0])
+    return fail(h, WFLOWB200_ERR_STATE, "set vertical_timeline = 1 and vertical_graph = 0 first");
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < n; ++k) {
+    float ms = 0.f;
+    out_ms[k] = cudaEventElapsedTime(&ms, h->tl_ev[0], h->tl_ev[k]) == cudaSuccess ? ms : -1.0;
+  }
+  cudaGetLastError();
+  return WFLOWB200_OK;
+}
+
 int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value) {
   WFB_ENTER(h);
   if (!name) return WFLOWB200_ERR_ARG;
@@ -1645,6 +1703,11 @@ int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value) {
   else if (k == "surface_river_share") { if (value >= 1 && value < t.river_period) t.river_share = value; }
   else if (k == "surface_river_period") { if (value >= 2 && value > t.river_share) t.river_period = value; }
   else if (k == "vertical_graph") t.use_graph = value != 0;
+  else if (k == "vertical_timeline") {
+    t.timeline = value != 0;
+    for (auto& e : h->tl_ev)
+      if (!e && t.timeline) CUDA_TRY(h, cudaEventCreate(&e));
+  }
   else if (k == "vertical_engine") {   // timing experiments only: 0 leaves suspended cells unfinished
     t.run_engine = value != 0;
     if (h->v_graph) { cudaGraphExecDestroy(h->v_graph); h->v_graph = nullptr; }

@@ -10,31 +10,24 @@ namespace wfb {
 int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s);
 // Device scratch of the unsaturated-zone engine (vertical.cu): the operands of the suspended
 // Brooks-Corey loops (one record per cell) and the lists of suspended cells, bucketed by
-// log2(trip count), double-buffered over the engine's rounds.
+// log2(trip count).
 #define WFB_UNSAT_BUCKETS 6
-#define WFB_V_SIDE_STREAMS 4
-#define WFB_V_MAX_SLICES 8
 #define WFB_V_TILE 128                        // cells per tile (= CTA of land_hydrology_kernel)
 struct UnsatWork {
   double *usd, *sum_ast, *kv_it, *l_sat, *c;  // ns doubles each
   int32_t* its_layer;                         // ns: trip count | layer << 24
-  int32_t* list;                              // [2][WFB_UNSAT_BUCKETS][cap] cell slots
-  unsigned* count;                            // [2][WFB_UNSAT_BUCKETS]
+  int32_t* list;                              // [WFB_UNSAT_BUCKETS][cap] cell slots
+  unsigned* count;                            // [WFB_UNSAT_BUCKETS]
   int32_t cap;                                // capacity of one list (cells of the slice)
   int32_t inline_iters;                       // loops up to this many trips run in line
 };
-// engine_grid: CTAs of the engine kernels (a few per SM). The tiles (WFB_V_TILE consecutive slots)
-// are cut into n_slices contiguous slices (slice k = tiles [slice_tile_begin[k],
-// slice_tile_begin[k+1]); one UnsatWork each); the loop engine of slice k
-// runs on side[k % WFB_V_SIDE_STREAMS] (high-priority streams) under land_hydrology_kernel of the
-// next slices on s; ev holds 2 * n_slices events.
+// engine_grid: CTAs of the engine kernel (a few per SM). phase: 0 the whole update; 1 interception
+// + snow only, 2 the rest (lateral snow transport runs between the two: launch_snow_transport).
+// run_engine = false leaves the suspended cells unfinished (timing experiments only). tl: optional
+// timing events of the kernels' completion (wflowb200_get_vertical_timeline).
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork* w, int n_slices, const int* slice_tile_begin,
-                          int engine_grid, int phase, bool run_engine, cudaStream_t s, cudaStream_t const* side,
-                          cudaEvent_t const* ev);
-// run_engine = false leaves the suspended cells unfinished: timing experiments only
-// phase: 0 the whole update; 1 interception + snow only, 2 the rest (lateral snow transport runs
-// between the two: launch_snow_transport)
+                          const UnsatWork& w, int engine_grid, int phase, bool run_engine,
+                          cudaStream_t s, cudaEvent_t const* tl = nullptr);
 // self-test of device_math.cuh: out[6] (device, zeroed) receives bit patterns of the maxima
 int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);

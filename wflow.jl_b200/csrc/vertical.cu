@@ -1,43 +1,34 @@
-// vertical.cu -- the SBM vertical land-surface update as fused sm_100a elementwise kernels.
+// vertical.cu -- the SBM vertical land-surface update as sm_100a elementwise kernels.
 //
 // One thread per land slot; the ~30 sweeps of the reference collapse into
-//   land_hydrology_kernel     update_land_hydrology_model! (sbm.jl:82-132): interception, snow,
-//                             glacier, open water, soil boundary conditions, diagnostics,
-//                             infiltration, unsaturated-zone flow AND -- for every cell whose
-//                             Brooks-Corey loops are short -- the second half (soil evaporation,
-//                             transpiration, actual infiltration, capillary flux, leakage,
-//                             recharge, AET; soil/soil.jl:814-1209) straight from registers
-//   unsat_loop_kernel /       the long Brooks-Corey sub-iteration loops of unsatzone_flow_layer
-//   unsat_resume_kernel       (soil_process.jl:51-92) of the few cells that have them, see "the
-//                             unsaturated-zone engine" below; a resumed cell is FINISHED there
-//                             (its second half included)
+//   land_hydrology_kernel     update_land_hydrology_model!, first half (sbm.jl:82-132):
+//                             interception, snow, glacier, open water, soil boundary conditions,
+//                             diagnostics, infiltration, unsaturated-zone flow
+//   unsat_engine_kernel       the long Brooks-Corey sub-iteration loops of unsatzone_flow_layer
+//                             (soil_process.jl:51-92) of the cells that have them, see "the
+//                             unsaturated-zone engine" below
+//   soil_column_kernel        second half: soil evaporation, transpiration, actual infiltration,
+//                             capillary flux, leakage, recharge, AET   soil/soil.jl:814-1209
 //   soil_water_storage_kernel update_soil_water_storage!               soil/soil.jl:1294-1392
 //   total_water_storage_kernel update_total_water_storage!             sbm.jl:143-182
-// HBM-bound: consecutive threads touch consecutive doubles of every SoA array, so each warp
-// load/store is a fully used 256-byte transaction; the layered state lives in registers
-// (template N) between sub-processes; every input array is read once and every output array
-// written once per cell and step. Arithmetic order follows the reference expression by
-// expression (no FMA contraction: -fmad=false) so results match the Julia code to the last
-// bits that libm differences allow. All reference paths are under /root/reference/Wflow/src.
+// Consecutive threads touch consecutive doubles of every SoA array, so each warp load/store is a
+// fully used 256-byte transaction; the layered state lives in registers (template N) between
+// sub-processes. Arithmetic order follows the reference expression by expression (no FMA
+// contraction: -fmad=false) so results match the Julia code to the last bits that libm
+// differences allow. All reference paths are under /root/reference/Wflow/src.
 //
 // The unsaturated-zone engine. unsatzone_flow_layer runs `its = cld(remainder, 2e-4 m)` explicit
 // sub-iterations, each a dependent div -> log -> exp chain. After a few wet days the trip count
-// is 1 for 80 % of the (cell, layer) calls and 64-250 for 1.5 % of them -- and those 1.5 % hold
+// is 1 for 80 % of the (cell, layer) calls and 64-400 for 1.5 % of them -- and those 1.5 % hold
 // 40 % of all iterations. With one cell per lane a warp runs as long as its wettest cell, and a
 // CTA as long as its wettest warp. The engine therefore takes the long loops OUT of the
 // per-cell kernel: land_hydrology_kernel runs loops of up to `inline_iters` trips in line and
 // SUSPENDS a cell at the first longer one (the loop's operands go to a per-cell scratch record,
-// the cell id to a list bucketed by log2(its)); unsat_loop_kernel runs all suspended loops of
-// a slice at once, one lane per loop, 32 loops of the same bucket per warp, longest buckets
-// first, so the lanes of a warp finish together; unsat_resume_kernel continues the suspended
-// cells with their next layer (and may suspend them again: at most N rounds) and finishes them.
-//
-// Hiding the engine. The engine's kernels are a latency-bound tail (as long as the longest
-// suspended loop). The tiles (128 consecutive slots) are cut into a few contiguous slices and the
-// engine of slice k runs on a high-priority side stream under the dense kernels of the slices
-// after it. (Ordering the tiles by the longest loop of the previous step was tried and dropped:
-// nearly every tile holds a loop of 200+ trips, so no order isolates them, and scattering
-// 1 KB tiles over HBM costs DRAM page locality.)
+// the cell id to a list bucketed by log2(its)); unsat_engine_kernel takes every suspended cell
+// through its remaining layers, one lane per cell, 32 cells of the same bucket per warp, longest
+// buckets first, with trips that track the power instead of re-evaluating log and exp
+// (unsatzone_flow_iterate_fast); soil_column_kernel then finishes every cell from arrays that
+// are reference-visible outputs anyway.
 #include <cstdio>
 #include "device_math.cuh"
 #include "kernels.cuh"
@@ -136,52 +127,38 @@ __device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt, 
   t.usd = usd; t.sum_ast = sum_ast;
 }
 
-// The same loop with a short dependency chain, for the LONG loops of the engine (a loop round
-// lasts as long as its longest loop: ~250 trips x ~620 cycles of div -> log -> exp with
+// The same loop with a short dependency chain, for the LONG loops of the engine (the engine lasts
+// as long as the longest cell's loops: ~1000 trips x ~600 cycles of div -> log -> exp with
 // libdevice). A trip drains the fraction eps = st dt / usd of the layer, so with x = usd / l_sat
-// and r = x^(c-1):  x' = x (1 - eps),  eps = (kv_it dt / l_sat) r,  r' = r exp((c-1) log(1 - eps)).
-// For eps <= 1/64 (always, a few trips into a long loop) log(1 - eps) and the exp of the small
-// product are short polynomials (explicit FMAs, Estrin form: ~13 dependent operations instead of
-// ~70), st = kv_it r x. r is re-evaluated with the reference expression every kResync trips, so
-// the tracked value stays within ~1e-14 of it (each update adds ~2 ulp); usd itself is always
-// updated with the reference's own expression usd -= st dt. Trips with a large eps, an
-// oversaturated layer (x > 1, bounded_power = 1) or an underflowing power take the reference
-// path. wflowb200_selftest_math compares both loops.
-constexpr int kResync = 16;
-__device__ __forceinline__ double log1m_small(double e) {  // log(1 - e), 0 <= e <= 1/64
-  // -(e + e^2/2 + ... + e^10/10); the first neglected term is 5e-18 relative
-  const double e2 = e * e, e4 = e2 * e2, e8 = e4 * e4;
-  const double a0 = fma(e, 1.0 / 2.0, 1.0), a1 = fma(e, 1.0 / 4.0, 1.0 / 3.0);
-  const double a2 = fma(e, 1.0 / 6.0, 1.0 / 5.0), a3 = fma(e, 1.0 / 8.0, 1.0 / 7.0);
-  const double a4 = fma(e, 1.0 / 10.0, 1.0 / 9.0);
-  const double b0 = fma(e2, a1, a0), b1 = fma(e2, a3, a2);
-  const double p = fma(e8, a4, fma(e4, b1, b0));
-  return -(e * p);
-}
-__device__ __forceinline__ double exp_small(double z) {  // exp(z), |z| <= 0.175
-  // 1 + z + ... + z^11/11!; the first neglected term is 2e-18
-  const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-  const double d0 = 1.0 + z, d1 = fma(z, 1.0 / 6.0, 0.5);
-  const double d2 = fma(z, 1.0 / 120.0, 1.0 / 24.0), d3 = fma(z, 1.0 / 5040.0, 1.0 / 720.0);
-  const double d4 = fma(z, 1.0 / 362880.0, 1.0 / 40320.0);
-  const double d5 = fma(z, 1.0 / 39916800.0, 1.0 / 3628800.0);
-  const double e0 = fma(z2, d1, d0), e1 = fma(z2, d3, d2), e2 = fma(z2, d5, d4);
-  return fma(z8, e2, fma(z4, e1, e0));
-}
+// and r = x^(c-1):   x' = x (1 - eps),   eps = (kv_it dt / l_sat) r,   r' = r (1 - eps)^(c-1).
+// For eps <= 1/64 (always, a few trips into a long loop) the power is its binomial series in eps
+// with coefficients that depend on c only -- twelve terms, evaluated in Estrin form with explicit
+// FMAs: 6 dependent operations per trip instead of ~70 -- and st = kv_it r x. r is re-evaluated
+// with the reference expression every kResync trips, so the tracked value stays within ~1e-14 of
+// it (each update adds ~1 ulp); usd itself is always updated with the reference's own expression
+// usd -= st dt. Trips with a large eps, an oversaturated layer (x > 1: bounded_power = 1) or an
+// underflowing power take the reference path. Largest difference to the reference loop over
+// random tasks: 7e-16 (store), 6e-15 (flux); wflowb200_selftest_math measures it on the device.
+constexpr int kResync = 64;
 __device__ __forceinline__ void unsatzone_flow_iterate_fast(UnsatTask& t, double dt,
                                                             const Divisor& ddt) {
   double usd = t.usd, sum_ast = t.sum_ast;
   const Divisor dl(t.l_sat);
   const double a = t.kv_it * dt / dl;
-  const double cm1 = t.c - 1.0;
+  const double m = t.c - 1.0;
+  // (1 - e)^m = sum_j b_j e^j,  b_0 = 1,  b_j = -b_{j-1} (m - j + 1) / j
+  double b[12];
+  b[0] = 1.0;
+#pragma unroll
+  for (int j = 1; j < 12; ++j) b[j] = b[j - 1] * (-(m - (double)(j - 1)) / (double)j);
   double r = 0.0;
   int fresh = 0;  // trips for which the tracked r may still be used
   for (int k = 0; k < t.its; ++k) {
-    const double x = usd / dl;
     double p;
     if (fresh > 0) {
-      p = r * x;
+      p = r * (usd * dl.r);   // x = usd / l_sat to within an ulp: r itself is tracked
     } else {
+      const double x = usd / dl;
       p = bounded_power(x, t.c);  // the reference expression
       if (x <= 1.0 && p > 1.0e-280) { r = p / x; fresh = kResync; }
     }
@@ -190,10 +167,17 @@ __device__ __forceinline__ void unsatzone_flow_iterate_fast(UnsatTask& t, double
     if (st < st_max) { usd -= st * dt; sum_ast += st; }
     else { usd = 0.0; sum_ast += st_max; break; }
     if (fresh > 0) {
-      const double eps = a * r;
-      const double z = cm1 * log1m_small(eps);
-      if (eps <= 1.0 / 64.0 && z >= -0.175) { r *= exp_small(z); --fresh; }
-      else fresh = 0;
+      const double e = a * r;
+      if (e <= 1.0 / 64.0 && m * e <= 0.175) {
+        const double e2 = e * e, e4 = e2 * e2, e8 = e4 * e4;
+        const double p0 = fma(e, b[1], b[0]), p1 = fma(e, b[3], b[2]), p2 = fma(e, b[5], b[4]);
+        const double p3 = fma(e, b[7], b[6]), p4 = fma(e, b[9], b[8]), p5 = fma(e, b[11], b[10]);
+        const double q0 = fma(e2, p1, p0), q1 = fma(e2, p3, p2), q2 = fma(e2, p5, p4);
+        r *= fma(e8, q2, fma(e4, q1, q0));
+        --fresh;
+      } else {
+        fresh = 0;
+      }
     }
   }
   t.usd = usd; t.sum_ast = sum_ast;
@@ -207,7 +191,7 @@ __device__ __forceinline__ int bucket_of(int its) {  // (8,16] -> 0 ... by log2,
 }
 // record the loop of cell i (layer k) and append the cell to the list of its bucket
 // (warp-aggregated: one atomic per warp and bucket)
-__device__ __forceinline__ void suspend_cell(const UnsatWork& w, int parity, int i, int k,
+__device__ __forceinline__ void suspend_cell(const UnsatWork& w, int i, int k,
                                              const UnsatTask& t, bool suspend) {
   const unsigned active = __ballot_sync(0xffffffffu, suspend);
   if (!suspend) return;
@@ -219,10 +203,10 @@ __device__ __forceinline__ void suspend_cell(const UnsatWork& w, int parity, int
   const int lane = (int)threadIdx.x & 31;
   const int leader = __ffs(peers) - 1;
   unsigned base = 0;
-  if (lane == leader) base = atomicAdd(w.count + parity * kBuckets + b, (unsigned)__popc(peers));
+  if (lane == leader) base = atomicAdd(w.count + b, (unsigned)__popc(peers));
   base = __shfl_sync(peers, base, leader);
   const unsigned pos = base + (unsigned)__popc(peers & ((1u << lane) - 1u));
-  w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + pos] = i;
+  w.list[((size_t)b) * (size_t)w.cap + pos] = i;
 }
 
 // warp tile j of the concatenated bucket lists, longest bucket first -> (bucket, first entry)
@@ -252,7 +236,7 @@ __device__ __forceinline__ double rwu_reduction_feddes(double h, double h1, doub
 // the depth of the bottom of layer k0 - 1. Returns true when the cell finished all its layers
 // (uld[] and transfer are then final); false when it was suspended at a long loop.
 template <int N>
-__device__ __forceinline__ bool unsat_layers(const KCfg& c, const UnsatWork& w, int parity, int i,
+__device__ __forceinline__ bool unsat_layers(const KCfg& c, const UnsatWork& w, int i,
                                              int k0, int n_unsat, double z, double flow,
                                              double first_inflow, double (&uld)[N],
                                              const double (&ult)[N], const double (&bc)[N],
@@ -280,13 +264,13 @@ __device__ __forceinline__ bool unsat_layers(const KCfg& c, const UnsatWork& w, 
       }
     }
   }
-  suspend_cell(w, parity, i, k_susp, t_susp, suspended);
+  suspend_cell(w, i, k_susp, t_susp, suspended);
   transfer = n_unsat > 0 ? flow : 0.0;
   return !suspended;
 }
 
 // What the second half of update_land_hydrology_model! needs from the first half: registers in
-// land_hydrology_kernel, re-read from the (reference-visible) arrays in unsat_resume_kernel.
+// soil_column_kernel re-reads it from the (reference-visible) arrays the first half wrote.
 template <int N>
 struct SoilColumn {
   double theta_s, theta_e, d_soil, swc, satwd, zi;
@@ -527,21 +511,16 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
 
 }  // namespace
 
-// WFB_V_FUSED = 1: land_hydrology_kernel also finishes every never-suspended cell from registers
-// (no re-read of the first half's outputs). Measured on B200 (1000^2): slower than the split
-// organisation -- the fused kernel needs 128 registers with spills, runs 4 CTAs per SM and takes
-// 436 us against 172 + 142 us for the two halves as kernels of their own, both latency-bound in
-// FP64 dependency chains, not by DRAM (29 % of peak) -- see DESIGN.md section 5.1.
-#ifndef WFB_V_FUSED
-#define WFB_V_FUSED 0
-#endif
+// (Finishing every never-suspended cell inside land_hydrology_kernel, straight from registers,
+// was built and measured: 128 registers with spills, 4 CTAs per SM, 436 us against 203 + 190 us
+// for the two halves as kernels of their own -- see DESIGN.md section 5.1.)
 // the loop engine's trips with the tracked power (unsatzone_flow_iterate_fast); 0: every trip
 // with the reference expression
 #ifndef WFB_ENGINE_FAST_TRIPS
 #define WFB_ENGINE_FAST_TRIPS 1
 #endif
 #ifndef WFB_V_MINBLOCKS
-#define WFB_V_MINBLOCKS (WFB_V_FUSED ? 4 : 5)
+#define WFB_V_MINBLOCKS 5
 #endif
 // Every input array of the cell is requested at the top of the kernel, long before its first use:
 // the loads proper sit next to their first use (registers), and with 16 warps per SM that spend
@@ -876,7 +855,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
 #pragma unroll
   for (int k = 0; k < N; ++k) s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
   double transfer;
-  const bool done = unsat_layers<N>(c, w, 0, i, 0, n_unsat, 0.0, 0.0, infiltration, s.uld, s.ult,
+  const bool done = unsat_layers<N>(c, w, i, 0, n_unsat, 0.0, 0.0, infiltration, s.uld, s.ult,
                                     s.bc, s.kv, theta_e, dt, ddt, live, transfer);
   // the read-modify-write states of the sections above (phase 2: canopy and snow water were
   // written by phase 1)
@@ -887,29 +866,13 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     f.soil_surface_temperature[i] = st_tsoil;
     if (c.glacier) f.glacier_store[i] = st_gstore;
   }
-#if !WFB_V_FUSED
-  // split organisation (default): the second half runs in soil_column_kernel for every cell that
-  // was not suspended (state 0) and in unsat_resume_kernel for the others
-  if (done) { f.transfer[i] = transfer; w.its_layer[i] = 0; }
+  // the second half runs in soil_column_kernel, after the loop engine has finished the
+  // suspended cells' layers (nothing below is needed from registers: it is all in arrays)
+  if (done) f.transfer[i] = transfer;
 #pragma unroll
   for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
   (void)pot_soilevap0; (void)infiltration_excess; (void)max_infiltsoil; (void)max_infiltpath;
   (void)aeow_river; (void)aeow_land;
-#else
-  if (done) {
-    // the second half straight from registers: nothing of the first half is read back
-    f.transfer[i] = transfer;
-    s.pot_soilevap = pot_soilevap0; s.pot_transp = pot_transp; s.infiltration = infiltration;
-    s.infiltration_excess = infiltration_excess; s.wfs = wfs; s.max_infiltsoil = max_infiltsoil;
-    s.max_infiltpath = max_infiltpath; s.pathfrac = pathfrac; s.transfer = transfer;
-    s.aeow_river = aeow_river; s.aeow_land = aeow_land; s.interception = interception;
-    soil_column_cell<N>(f, c, i, dt, ddt, s);
-  } else {
-    // layers above the suspended one are final, the others are written by unsat_resume_kernel
-#pragma unroll
-    for (int k = 0; k < N; ++k) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
-  }
-#endif
 }
 
 // What soil_column_cell needs, re-read from the reference-visible arrays the first half wrote
@@ -944,9 +907,8 @@ __device__ __forceinline__ void load_column_rest(const DevFields& f, const KCfg&
   s.interception = f.interception_rate[i];
 }
 
-// update_land_hydrology_model!, second half, for every cell whose Brooks-Corey loops were short
-// (split organisation): the suspended ones (state != 0) are finished by unsat_resume_kernel,
-// which runs at the same time on a side stream.
+// update_land_hydrology_model!, second half (soil evaporation ... recharge, AET), every cell:
+// everything it needs from the first half is a reference-visible output array (or an input).
 #ifndef WFB_VC_MINBLOCKS
 #define WFB_VC_MINBLOCKS 4
 #endif
@@ -956,7 +918,6 @@ soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const dou
                    const int tile_begin) {
   const int i = (tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
   if (i >= c.n) return;
-  if (w.its_layer[i] != 0) return;  // suspended: not this kernel's cell
   const int ns = c.ns;
   const Divisor ddt(dt);
   SoilColumn<N> s;
@@ -980,8 +941,7 @@ soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const dou
 // trips), then the layers below with loops of any length in line -- one lane per cell, 32 cells
 // of one bucket per warp, longest buckets first. Per-layer operands are fetched when their layer
 // is reached (an L2 hit, negligible next to a loop), so a lane holds ~50 registers and the
-// kernel shares the SMs with the bandwidth-bound kernels of the main stream.
-// soil_column_sparse_kernel then finishes these cells (second half).
+// kernel is light; soil_column_kernel then runs the second half of every cell.
 template <int N>
 __global__ void __launch_bounds__(128)
 unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
@@ -1040,132 +1000,6 @@ unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
     f.transfer[i] = flow;  // n_unsat > 0 for a suspended cell
   }
 }
-
-// Second half of update_land_hydrology_model! for the cells the engine has finished.
-template <int N>
-__global__ void __launch_bounds__(128)
-soil_column_sparse_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
-  const unsigned* cnt = w.count;
-  const int lane = (int)threadIdx.x & 31;
-  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
-  const int gw = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5);
-  const int ns = c.ns;
-  const Divisor ddt(dt);
-  for (int j = gw;; j += n_warps) {
-    int b, first, n;
-    if (!tile_of(cnt, j, b, first, n)) break;
-    const int e = first + lane;
-    if (e >= n) continue;
-    const int i = w.list[(size_t)b * (size_t)w.cap + e];
-    SoilColumn<N> s;
-    s.theta_s = __ldg(f.theta_s + i);
-    s.theta_e = s.theta_s - __ldg(f.theta_r + i);
-    s.n_unsat = f.n_unsatlayers[i];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
-      s.ult[k] = f.unsaturated_layer_thickness[k * ns + i];
-      s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
-    }
-    s.kv = load_kvcol<N>(f, c, i);
-    s.transfer = f.transfer[i];
-    load_column_rest<N>(f, c, i, s);
-    soil_column_cell<N>(f, c, i, dt, ddt, s);
-  }
-}
-
-#if WFB_V_FUSED
-// All suspended loops of a slice, one lane per loop, 32 loops of one bucket per warp.
-__global__ void __launch_bounds__(128)
-unsat_loop_kernel(const UnsatWork w, const int parity, const double dt) {
-  const unsigned* cnt = w.count + parity * kBuckets;
-  const int lane = (int)threadIdx.x & 31;
-  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
-  // consecutive tiles (the longest loops) go to different SMs
-  const int gw = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
-  const Divisor ddt(dt);
-  for (int j = gw;; j += n_warps) {
-    int b, first, n;
-    if (!tile_of(cnt, j, b, first, n)) break;
-    const int e = first + lane;
-    if (e < n) {
-      const int i = w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + e];
-      UnsatTask t;
-      t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
-      t.c = w.c[i]; t.its = w.its_layer[i] & 0xffffff;
-#if WFB_ENGINE_FAST_TRIPS
-      unsatzone_flow_iterate_fast(t, dt, ddt);
-#else
-      unsatzone_flow_iterate(t, dt, ddt);
-#endif
-      w.usd[i] = t.usd; w.sum_ast[i] = t.sum_ast;
-    }
-  }
-}
-
-// The suspended cells continue with the layer below the finished loop; a cell that gets through
-// its remaining layers is finished here (second half of update_land_hydrology_model!), from the
-// reference-visible arrays land_hydrology_kernel wrote for it.
-template <int N>
-__global__ void __launch_bounds__(128)
-unsat_resume_kernel(const DevFields f, const KCfg c, const UnsatWork w, const int parity,
-                    const double dt) {
-  const unsigned* cnt = w.count + parity * kBuckets;
-  const int lane = (int)threadIdx.x & 31;
-  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
-  const int gw = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5);
-  const int ns = c.ns;
-  const Divisor ddt(dt);
-  for (int j = gw;; j += n_warps) {
-    int b, first, n;
-    if (!tile_of(cnt, j, b, first, n)) break;
-    const int e = first + lane;
-    const bool live = e < n;
-    int i = 0, k0 = N;
-    double z = 0.0, flow = 0.0, transfer = 0.0;
-    SoilColumn<N> s;
-    s.n_unsat = 0; s.theta_e = 1.0;
-    s.kv.kv_0 = s.kv.f = s.kv.zx = 0.0; s.kv.nk = 0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) { s.uld[k] = 0.0; s.ult[k] = 1.0; s.bc[k] = 1.0; s.kv.k[k] = 1.0; }
-    if (live) {
-      i = w.list[((size_t)parity * kBuckets + b) * (size_t)w.cap + e];
-      const int kl = w.its_layer[i] >> 24;   // the layer whose loop has just been run
-      flow = w.sum_ast[i];
-      s.n_unsat = f.n_unsatlayers[i];
-      k0 = kl + 1;
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        s.ult[k] = f.unsaturated_layer_thickness[k * ns + i];
-        s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
-        s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
-        if (k < k0) z = (k == 0) ? s.ult[0] : z + s.ult[k];  // same left-to-right sum as the first pass
-      }
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-        if (k == kl) s.uld[k] = w.usd[i];
-      s.kv = load_kvcol<N>(f, c, i);
-      s.theta_s = __ldg(f.theta_s + i);
-      s.theta_e = s.theta_s - __ldg(f.theta_r + i);
-    }
-    // every lane of the warp calls unsat_layers (it aggregates the suspensions of the warp)
-    const bool done = unsat_layers<N>(c, w, parity ^ 1, i, k0, s.n_unsat, z, flow, 0.0, s.uld, s.ult,
-                                      s.bc, s.kv, s.theta_e, dt, ddt, live, transfer);
-    if (!live) continue;
-    if (!done) {
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-        if (k >= k0 - 1 && k < s.n_unsat) f.unsaturated_layer_depth[k * ns + i] = s.uld[k];
-      continue;
-    }
-    f.transfer[i] = transfer;
-    s.transfer = transfer;
-    load_column_rest<N>(f, c, i, s);
-    soil_column_cell<N>(f, c, i, dt, ddt, s);
-  }
-}
-
-#endif  // WFB_V_FUSED (multi-round engine of the fused organisation)
 
 // update_bc_open_water_runoff_model!: river h -> land grid                 runoff.jl:77-79
 __global__ void scatter_river_depth_kernel(const DevFields f, const KCfg c) {
@@ -1308,67 +1142,32 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
   return 1;
 }
 
-// The ordered tiles are cut into slices. The loop engine of a slice is a latency-bound tail (it
-// lasts as long as the longest Brooks-Corey loop of the slice, with a few hundred busy warps), so
-// it runs on a high-priority side stream UNDER land_hydrology_kernel of the next slices:
-//   main:  O A0 A1 A2 A3             (O = tile_order_kernel, A = land_hydrology_kernel)
-//   side:       E0 E1 E2 E3          (E = loop / resume rounds; a cell can be suspended once
-//                                     per layer, hence n_layers rounds)
-// Slice 0 holds the tiles with the longest loops of the previous step; only the engine of the
-// last slice is exposed. ev[2k] orders E_k after A_k, ev[2k+1] joins E_k into the main stream.
+// land_hydrology_kernel (dense) -> unsat_engine_kernel (the suspended cells' loops) ->
+// soil_column_kernel (dense), one stream. Measured on B200 (1000^2, scripts/vertical_timeline.py):
+// running the engine on a side stream UNDER the dense kernels, in 1 to 8 slices, is slower than
+// this plain sequence -- soil_column_kernel takes 400 instead of 190 us and the engine 200
+// instead of 70 us when they share the SMs (all three are bound by FP64 dependency chains, not
+// by DRAM), so nothing is hidden. tl (optional timing events): [0] start, [1] land_hydrology,
+// [2] unsat_engine, [3] soil_column done.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork* w, int n_slices, const int* slice_tile_begin,
-                          int engine_grid, int phase, bool run_engine, cudaStream_t s, cudaStream_t const* side,
-                          cudaEvent_t const* ev) {
+                          const UnsatWork& w, int engine_grid, int phase, bool run_engine,
+                          cudaStream_t s, cudaEvent_t const* tl) {
   int launches = 0;
   const int n_tiles = (c.ns + kTile - 1) / kTile;
+  if (tl) cudaEventRecord(tl[0], s);
   if (phase == 1) {  // interception + snow of every cell: no loops, no engine
-    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w[0], dt, 0, 1)));
+    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w, dt, 0, 1)));
     return launches + 1;
   }
-  for (int k = 0; k < n_slices; ++k) {
-    const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
-    if (t0 >= t1) continue;
-    cudaMemsetAsync(w[k].count, 0, 2 * kBuckets * sizeof(unsigned), s);
-    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<t1 - t0, kTile, 0, s>>>(f, c, w[k], dt, t0,
-                                                                                 phase)));
-    ++launches;
-    // the engine always runs on a side stream: with one slice it overlaps soil_column_kernel
-    cudaStream_t e = (n_slices > 1 || !WFB_V_FUSED) ? side[k % WFB_V_SIDE_STREAMS] : s;
-    if (e != s) {
-      cudaEventRecord(ev[2 * k], s);
-      cudaStreamWaitEvent(e, ev[2 * k], 0);
-    }
-#if WFB_V_FUSED
-    for (int r = 0; r < (run_engine ? n_layers : 0); ++r) {
-      const int parity = r & 1;
-      unsat_loop_kernel<<<engine_grid, 128, 0, e>>>(w[k], parity, dt);
-      if (r > 0)
-        cudaMemsetAsync(w[k].count + (parity ^ 1) * kBuckets, 0, kBuckets * sizeof(unsigned), e);
-      WFB_DISPATCH_N(n_layers, (unsat_resume_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], parity, dt)));
-      launches += 2;
-    }
-#else
-    if (run_engine) {
-      WFB_DISPATCH_N(n_layers, (unsat_engine_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], dt)));
-      WFB_DISPATCH_N(n_layers, (soil_column_sparse_kernel<N><<<engine_grid, 128, 0, e>>>(f, c, w[k], dt)));
-      launches += 2;
-    }
-#endif
-    cudaEventRecord(ev[2 * k + 1], e);
-  }
-#if !WFB_V_FUSED
-  // second half of the never-suspended cells, under the engines of the side streams
-  for (int k = 0; k < n_slices; ++k) {
-    const int t0 = slice_tile_begin[k], t1 = slice_tile_begin[k + 1];
-    if (t0 >= t1) continue;
-    WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<t1 - t0, kTile, 0, s>>>(f, c, w[k], dt, t0)));
-    ++launches;
-  }
-#endif
-  for (int k = 0; k < n_slices; ++k)
-    if (slice_tile_begin[k] < slice_tile_begin[k + 1]) cudaStreamWaitEvent(s, ev[2 * k + 1], 0);
-  return launches;
+  cudaMemsetAsync(w.count, 0, kBuckets * sizeof(unsigned), s);
+  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w, dt, 0, phase)));
+  if (tl) cudaEventRecord(tl[1], s);
+  if (run_engine)
+    WFB_DISPATCH_N(n_layers, (unsat_engine_kernel<N><<<engine_grid, 128, 0, s>>>(f, c, w, dt)));
+  if (tl) cudaEventRecord(tl[2], s);
+  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w, dt, 0)));
+  if (tl) cudaEventRecord(tl[3], s);
+  return launches + 3;
 }
 
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s) {

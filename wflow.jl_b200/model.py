@@ -207,6 +207,19 @@ class SbmModel:
             off += sz
         return out
 
+    def output_size(self, names) -> int:
+        return int(sum(np.prod(self._shape(n)) for n in names))
+
+    def get_fields_async(self, names, out_pinned: np.ndarray):
+        """Non-blocking get_fields into a page-locked float64 buffer of output_size(names)."""
+        ids = np.array([self._ids[n] for n in names], dtype=np.int32)
+        assert out_pinned.dtype == np.float64 and out_pinned.size >= self.output_size(names)
+        self._check(self._L.wflowb200_get_fields_async(self._h, ids.ctypes.data, len(ids),
+                                                       out_pinned.ctypes.data))
+
+    def wait_outputs(self):
+        self._check(self._L.wflowb200_wait_outputs(self._h))
+
     # ---- the hot path (names of the reference functions) ---------------------------------
     def update_land_hydrology_model(self, dt):
         self._check(self._L.wflowb200_update_land_hydrology_model(self._h, dt))
@@ -276,6 +289,11 @@ class SbmModel:
     def set_option(self, name: str, value: int):
         """Select between kernel organisations with identical results (wflow_b200.h)."""
         self._check(self._L.wflowb200_set_option(self._h, name.encode(), int(value)))
+
+    def vertical_timeline(self):
+        buf = (C.c_double * 4)()
+        self._check(self._L.wflowb200_get_vertical_timeline(self._h, buf, 4))
+        return list(buf)
 
     def newton_trace(self, enable: bool):
         self._check(self._L.wflowb200_newton_trace(self._h, int(enable)))
