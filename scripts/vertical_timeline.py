@@ -7,6 +7,9 @@ cfg, dom, fields = pkg.synthetic.make_basin(1000, 1000, seed=42)
 m = pkg.SbmModel(cfg, dom, fields)
 m.set_option("vertical_graph", 0)
 m.set_option("vertical_timeline", 1)
+for kv in sys.argv[1:]:   # e.g. vertical_engine_rounds=4
+    k, v = kv.split("=")
+    m.set_option(k, int(v))
 dt = cfg["dt"]
 for s in range(12):
     m.set_forcing(*pkg.synthetic.make_forcing(42, s, dom["gid"], dt))

@@ -267,6 +267,7 @@ struct WflowB200 {
   int32_t* d_unsat_list = nullptr;
   unsigned* d_err = nullptr;         // device error word (bounded waits of the wavefront kernels)
   unsigned* d_unsat_count = nullptr;
+  VerticalStage v_stage{};           // input staging lists of the dense vertical kernels
   int engine_grid = 0;
   cudaEvent_t tl_ev[4] = {};         // timeline of the vertical kernels (developer aid)
   cudaGraphExec_t v_graph = nullptr;  // the vertical update of one step, captured once per dt
@@ -639,7 +640,7 @@ int32_t run_wave_adaptive(WflowB200* h, DomainDev& d, double dt, int kind, int n
 static int32_t launch_vertical(WflowB200* h, double dt) {
   const bool transport = h->cfg.snow_gravitational_transport != 0;
   auto issue_phase = [&](int phase) {
-    return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->engine_grid, phase,
+    return launch_land_hydrology(h->f, h->kc, h->N, dt, h->unsat, h->v_stage, h->engine_grid, phase,
                                  h->tune.run_engine != 0, h->stream,
                                  (h->tune.timeline && !h->tune.use_graph) ? h->tl_ev : nullptr);
   };
@@ -939,6 +940,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->kc.soil_infiltration_reduction = cfg->soil_infiltration_reduction;
   h->kc.kv_profile = cfg->kv_profile;
   h->kc.qroot = h->cfg.kin_wave_min_flow_qroot;
+  build_vertical_stage(h->f, h->kc, h->N, h->v_stage);
   h->kc.river_routing = cfg->river_routing;
   if (cfg->river_routing == 1) {   // the staggered grid by river slot (network.jl:281-293)
     const Network& rn = h->river.nw;

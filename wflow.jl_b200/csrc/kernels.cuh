@@ -21,13 +21,28 @@ struct UnsatWork {
   int32_t cap;                                // capacity of one list (cells of the slice)
   int32_t inline_iters;                       // loops up to this many trips run in line
 };
+// Lane-private input staging of the two dense kernels. A warp of a register-limited kernel keeps
+// only a few loads in flight, so a cell's ~50 input loads become ~12 serialised round trips to
+// DRAM. Instead every lane asks for ALL its inputs at kernel entry with cp.async (no register is
+// tied up): row r of the CTA's shared memory receives the tile's 128 values of array p[r], lane t
+// reads back only its own word (no barrier, cp.async.wait_all only).
+constexpr int kMaxStage = 80;
+struct StageList {
+  const double* p[kMaxStage];  // array (layer slab) staged in row r, nullptr: row not in use
+  int32_t rows;                // rows to stage; dynamic shared memory = rows * 128 * 8 bytes
+};
+struct VerticalStage {
+  StageList first[3];          // land_hydrology_kernel by phase
+  StageList second;            // soil_column_kernel
+};
+void build_vertical_stage(const DevFields& f, const KCfg& c, int n_layers, VerticalStage& vs);
 // engine_grid: CTAs of the engine kernel (a few per SM). phase: 0 the whole update; 1 interception
 // + snow only, 2 the rest (lateral snow transport runs between the two: launch_snow_transport).
 // run_engine = false leaves the suspended cells unfinished (timing experiments only). tl: optional
 // timing events of the kernels' completion (wflowb200_get_vertical_timeline).
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork& w, int engine_grid, int phase, bool run_engine,
-                          cudaStream_t s, cudaEvent_t const* tl = nullptr);
+                          const UnsatWork& w, const VerticalStage& vs, int engine_grid, int phase,
+                          bool run_engine, cudaStream_t s, cudaEvent_t const* tl = nullptr);
 // self-test of device_math.cuh: out[6] (device, zeroed) receives bit patterns of the maxima
 int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s);
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s);

@@ -13,7 +13,9 @@
 //   total_water_storage_kernel update_total_water_storage!             sbm.jl:143-182
 // Consecutive threads touch consecutive doubles of every SoA array, so each warp load/store is a
 // fully used 256-byte transaction; the layered state lives in registers (template N) between
-// sub-processes. Arithmetic order follows the reference expression by expression (no FMA
+// sub-processes. The two dense kernels ask for ALL their inputs at kernel entry (cp.async into
+// lane-private shared-memory rows, "input staging" below): at 4-5 register-limited CTAs per SM a
+// warp keeps too few ordinary loads in flight, and a cell's ~50 loads cost ~12 DRAM round trips. Arithmetic order follows the reference expression by expression (no FMA
 // contraction: -fmad=false) so results match the Julia code to the last bits that libm
 // differences allow. All reference paths are under /root/reference/Wflow/src.
 //
@@ -34,11 +36,6 @@
 #include "kernels.cuh"
 #include "model.cuh"
 #include "soil_storage.cuh"
-
-// one-touch streaming loads of the vertical update (build variant: evict-first in L1 / L2)
-#if defined(WFB_V_LDCS) && WFB_V_LDCS
-#define __ldg(p) __ldcs(p)
-#endif
 
 namespace wfb {
 
@@ -127,57 +124,61 @@ __device__ __forceinline__ void unsatzone_flow_iterate(UnsatTask& t, double dt, 
   t.usd = usd; t.sum_ast = sum_ast;
 }
 
-// The same loop with a short dependency chain, for the LONG loops of the engine (the engine lasts
-// as long as the longest cell's loops: ~1000 trips x ~600 cycles of div -> log -> exp with
-// libdevice). A trip drains the fraction eps = st dt / usd of the layer, so with x = usd / l_sat
-// and r = x^(c-1):   x' = x (1 - eps),   eps = (kv_it dt / l_sat) r,   r' = r (1 - eps)^(c-1).
-// For eps <= 1/64 (always, a few trips into a long loop) the power is its binomial series in eps
-// with coefficients that depend on c only -- twelve terms, evaluated in Estrin form with explicit
-// FMAs: 6 dependent operations per trip instead of ~70 -- and st = kv_it r x. r is re-evaluated
-// with the reference expression every kResync trips, so the tracked value stays within ~1e-14 of
-// it (each update adds ~1 ulp); usd itself is always updated with the reference's own expression
-// usd -= st dt. Trips with a large eps, an oversaturated layer (x > 1: bounded_power = 1) or an
-// underflowing power take the reference path. Largest difference to the reference loop over
-// random tasks: 7e-16 (store), 6e-15 (flux); wflowb200_selftest_math measures it on the device.
+// The same loop with a short dependency chain, for the LONG loops of the engine. The engine lasts
+// as long as the trips of its wettest cell, one after the other: ~1600 trips x (div -> log -> exp
+// with libdevice: ~600 cycles; with a tracked power but the reference's comparisons as branches
+// on the chain: ~150 cycles). A trip drains the fraction e = st dt / usd of the layer. With
+// x = usd / l_sat and r = x^(c-1):   e = (kv_it dt / l_sat) r,   x' = x (1 - e),
+// r' = r (1 - e)^(c-1), hence   e' = e (1 - e)^(c-1).
+// For e <= 1/64 the power is its binomial series in e with coefficients that depend on c only
+// (twelve terms, Estrin form, explicit FMAs), so e itself is tracked from trip to trip: five
+// dependent operations and no branch. usd' = usd - usd e and st = usd e / dt follow beside the
+// chain. c > 1 makes e fall from trip to trip, so e <= 1/64 (which also implies the reference's
+// st < usd / dt) needs testing only when tracking starts. Tracking starts from the reference
+// expression (bounded_power) and restarts from it every kResync trips, so e stays within ~1e-14 of
+// the reference's value; an oversaturated layer (x > 1), an underflowing power or a large e take
+// the reference path trip by trip. Largest difference to the reference loop over random tasks:
+// wflowb200_selftest_math measures it on the device (tests/test_gpu_parity.py).
 constexpr int kResync = 64;
 __device__ __forceinline__ void unsatzone_flow_iterate_fast(UnsatTask& t, double dt,
                                                             const Divisor& ddt) {
   double usd = t.usd, sum_ast = t.sum_ast;
   const Divisor dl(t.l_sat);
   const double a = t.kv_it * dt / dl;
+  const double inv_dt = 1.0 / ddt;
   const double m = t.c - 1.0;
   // (1 - e)^m = sum_j b_j e^j,  b_0 = 1,  b_j = -b_{j-1} (m - j + 1) / j
   double b[12];
   b[0] = 1.0;
 #pragma unroll
   for (int j = 1; j < 12; ++j) b[j] = b[j - 1] * (-(m - (double)(j - 1)) / (double)j);
-  double r = 0.0;
-  int fresh = 0;  // trips for which the tracked r may still be used
-  for (int k = 0; k < t.its; ++k) {
-    double p;
+  const double e_max = m > 0.0 ? jmin(1.0 / 64.0, 0.175 / m) : -1.0;  // twelve terms suffice
+  double e = 0.0;
+  int fresh = 0;  // trips for which the tracked e may still be used
+  for (int k = 0; k < t.its; ++k) {   // ONE flat loop: the lanes of a warp are at different trips
     if (fresh > 0) {
-      p = r * (usd * dl.r);   // x = usd / l_sat to within an ulp: r itself is tracked
+      const double sd = usd * e;
+      sum_ast += usd * (e * inv_dt);
+      usd -= sd;
+      --fresh;
     } else {
       const double x = usd / dl;
-      p = bounded_power(x, t.c);  // the reference expression
-      if (x <= 1.0 && p > 1.0e-280) { r = p / x; fresh = kResync; }
-    }
-    const double st = t.kv_it * p;
-    const double st_max = usd / ddt;
-    if (st < st_max) { usd -= st * dt; sum_ast += st; }
-    else { usd = 0.0; sum_ast += st_max; break; }
-    if (fresh > 0) {
-      const double e = a * r;
-      if (e <= 1.0 / 64.0 && m * e <= 0.175) {
-        const double e2 = e * e, e4 = e2 * e2, e8 = e4 * e4;
-        const double p0 = fma(e, b[1], b[0]), p1 = fma(e, b[3], b[2]), p2 = fma(e, b[5], b[4]);
-        const double p3 = fma(e, b[7], b[6]), p4 = fma(e, b[9], b[8]), p5 = fma(e, b[11], b[10]);
-        const double q0 = fma(e2, p1, p0), q1 = fma(e2, p3, p2), q2 = fma(e2, p5, p4);
-        r *= fma(e8, q2, fma(e4, q1, q0));
-        --fresh;
-      } else {
-        fresh = 0;
+      const double p = bounded_power(x, t.c);  // the reference expression
+      const double st = t.kv_it * p;
+      const double st_max = usd / ddt;
+      if (st < st_max) { usd -= st * dt; sum_ast += st; }
+      else { usd = 0.0; sum_ast += st_max; break; }
+      if (x <= 1.0 && p > 1.0e-280) {
+        e = a * (p / x);
+        if (e <= e_max) fresh = kResync;
       }
+    }
+    if (fresh > 0) {  // e of the next trip
+      const double e2 = e * e, e4 = e2 * e2, e8 = e4 * e4;
+      const double p0 = fma(e, b[1], b[0]), p1 = fma(e, b[3], b[2]), p2 = fma(e, b[5], b[4]);
+      const double p3 = fma(e, b[7], b[6]), p4 = fma(e, b[9], b[8]), p5 = fma(e, b[11], b[10]);
+      const double q0 = fma(e2, p1, p0), q1 = fma(e2, p3, p2), q2 = fma(e2, p5, p4);
+      e *= fma(e8, q2, fma(e4, q1, q0));
     }
   }
   t.usd = usd; t.sum_ast = sum_ast;
@@ -269,8 +270,76 @@ __device__ __forceinline__ bool unsat_layers(const KCfg& c, const UnsatWork& w, 
   return !suspended;
 }
 
-// What the second half of update_land_hydrology_model! needs from the first half: registers in
-// soil_column_kernel re-reads it from the (reference-visible) arrays the first half wrote.
+// ---- lane-private input staging (kernels.cuh: StageList) -------------------------------------
+// Rows of the two dense kernels. The rows every configuration reads come first, the rows only
+// some configurations read last, so that the default configurations allocate no row they do
+// not use (N = 4: 43 rows = 5 CTAs per SM for the first half, 48 rows = 4 for the second).
+extern __shared__ double stage_rows[];
+namespace st1 {  // land_hydrology_kernel
+enum : int { snow_storage, snow_water, ttm, cfmax, whc, tsoil, w_soil, cf_soil, rf, wf, olf_h,
+             h_river, theta_s, theta_r, d_soil, swc, satwd, pathfrac, cap_soil, cap_path, kv_0,
+             kv_f, layered };
+template <int N> struct Rows {
+  static constexpr int kvfac = layered, uld = kvfac + N, alt = uld + N, bc = alt + N, cld = bc + N,
+                       core = cld + N + 1,
+                       canopy_storage = core, cmax = core + 1, gap = core + 2, e_r = core + 3,
+                       kv_zx = core + 4, kvlay = core + 5, all = kvlay + N;
+};
+}  // namespace st1
+namespace st2 {  // soil_column_kernel
+enum : int { d_soil, swc, satwd, zi, pot_soilevap, pot_transp, infiltration, infiltration_excess,
+             wfs, f_red, pathfrac, cap_soil, cap_path, aeow_river, aeow_land, interception,
+             theta_fc, rooting_depth, h1, h2, h4, alpha_h1, air_entry, h3_high, h3_low, wet_root,
+             cap_hmax, cap_n, max_leakage, kv_0, kv_f, layered };
+template <int N> struct Rows {
+  static constexpr int kvfac = layered, alt = kvfac + N, cld = alt + N, rootf = cld + N + 1,
+                       core = rootf + N,
+                       kv_zx = core, khfrac = core + 1, kvlay = core + 2, all = kvlay + N;
+};
+}  // namespace st2
+static_assert(st1::Rows<8>::all <= kMaxStage && st2::Rows<8>::all <= kMaxStage, "kMaxStage");
+
+// A lane copies 16 bytes: lanes 0-15 bring the warp's 32 values of row r, lanes 16-31 those of
+// row r + 1 (half the requests of an 8-byte copy per lane, and they bypass the L1).
+__device__ __forceinline__ void stage_issue(const StageList& sl, const int tile) {
+  const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
+  const int half = lane >> 4, first = warp * 32 + (lane & 15) * 2;  // first of this lane's 2 cells
+  const size_t src = (size_t)tile * kTile + first;
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(stage_rows) + (unsigned)first * 8u;
+#pragma unroll 4
+  for (int r = half; r < sl.rows; r += 2) {
+    const double* const p = sl.p[r];
+    if (p)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)r * (kTile * 8u)),
+                   "l"(p + src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// (whole warps must get here: a lane reads what other lanes of its warp asked for)
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+}
+// this lane's value of row r
+__device__ __forceinline__ double staged(const int r) { return stage_rows[r * kTile + (int)threadIdx.x]; }
+
+template <int N, class Rows>
+__device__ __forceinline__ KvCol<N> staged_kvcol(const DevFields& f, const KCfg& c, const int i,
+                                                 const int kv_0, const int kv_f) {
+  KvCol<N> kv;
+  const int prof = c.kv_profile;
+  kv.kv_0 = prof < 2 ? staged(kv_0) : 0.0;
+  kv.f = prof != 2 ? staged(kv_f) : 0.0;
+  kv.zx = (prof == 1 || prof == 3) ? staged(Rows::kv_zx) : 0.0;
+  kv.nk = prof == 3 ? f.nlayers_kv[i] - 1 : 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double fac = staged(Rows::kvfac + k);
+    kv.k[k] = prof >= 2 ? fac * staged(Rows::kvlay + k) : fac;
+  }
+  return kv;
+}
+
 template <int N>
 struct SoilColumn {
   double theta_s, theta_e, d_soil, swc, satwd, zi;
@@ -326,7 +395,7 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
                                                  SoilColumn<N>& s) {
   const int ns = c.ns;
   const double theta_e = s.theta_e;
-  const double theta_d = jmax(s.theta_s - __ldg(f.theta_fc + i), 0.02);
+  const double theta_d = jmax(s.theta_s - staged(st2::theta_fc), 0.02);
   const double zi = s.zi;
   const int n_unsat = s.n_unsat, nlayers = s.nlayers;
   double (&uld)[N] = s.uld;
@@ -360,14 +429,14 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
 
   // ---- transpiration (soil.jl:865-975) -----------------------------------------------------
   const double pot_transp = s.pot_transp;
-  const double rd = __ldg(f.rooting_depth + i);
-  const double h1 = __ldg(f.h1 + i), h2 = __ldg(f.h2 + i), h4 = __ldg(f.h4 + i);
-  const double alpha_h1 = __ldg(f.alpha_h1 + i);
-  const double hb = __ldg(f.air_entry_pressure + i);
+  const double rd = staged(st2::rooting_depth);
+  const double h1 = staged(st2::h1), h2 = staged(st2::h2), h4 = staged(st2::h4);
+  const double alpha_h1 = staged(st2::alpha_h1);
+  const double hb = staged(st2::air_entry);
   double h3;
   {
     const double tpot_daily = fdiv(pot_transp, WFB_MM_PER_DAY);  // feddes_h3 soil_process.jl:166-176
-    const double h3_high = __ldg(f.h3_high + i), h3_low = __ldg(f.h3_low + i);
+    const double h3_high = staged(st2::h3_high), h3_low = staged(st2::h3_low);
     if (tpot_daily <= 1.0) h3 = h3_low;
     else if (tpot_daily < 5.0) h3 = h3_low + (h3_high - h3_low) * (tpot_daily - 1.0) / (5.0 - 1.0);
     else h3 = h3_high;
@@ -375,7 +444,7 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
   f.h3[i] = h3;
   double rootf[N];
 #pragma unroll
-  for (int k = 0; k < N; ++k) rootf[k] = __ldg(f.rootfraction + k * ns + i);
+  for (int k = 0; k < N; ++k) rootf[k] = staged(st2::Rows<N>::rootf + k);
   // root fraction of the lowest unsaturated layer, rescaled to its unsaturated part; the layer
   // is selected with pick() -- indexing the register arrays with n_unsat - 1 would move them
   // to local memory
@@ -410,7 +479,7 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
       actevapustore += layer;
     }
   }
-  const double wetroots = scurve(zi, rd, 1.0, __ldg(f.wet_root_distribution_parameter + i));
+  const double wetroots = scurve(zi, rd, 1.0, staged(st2::wet_root));
   const double alpha_sat = rwu_reduction_feddes(0.0, h1, h2, h3, h4, alpha_h1);
   const double restpottrans = pot_transp - actevapustore;
   const double ae_sat = jmin(restpottrans * wetroots * alpha_sat, drainable / ddt);
@@ -464,8 +533,8 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
     const double maxcapflux = jmax(0.0, mc);
     double capflux = 0.0;
     if (zi > rd) {
-      const double hmax = __ldg(f.cap_hmax + i);
-      capflux = maxcapflux * jpow(1.0 - fdiv(jmin(zi, hmax), hmax), __ldg(f.cap_n + i));
+      const double hmax = staged(st2::cap_hmax);
+      capflux = maxcapflux * jpow(1.0 - fdiv(jmin(zi, hmax), hmax), staged(st2::cap_n));
     }
     double net = capflux;
 #pragma unroll
@@ -481,7 +550,7 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
   f.actual_capillary_flux[i] = act_capflux;
   const double deepksat = kv_at_depth<N>(c.kv_profile, s.kv, pick<N>(s.kv.k, nlayers - 1), s.d_soil);
   const double deeptransfer = jmin(drainable / ddt, deepksat);
-  const double leakage = jmax(0.0, jmin(__ldg(f.maximum_leakage + i), deeptransfer));
+  const double leakage = jmax(0.0, jmin(staged(st2::max_leakage), deeptransfer));
   f.actual_leakage[i] = leakage;
   const double recharge = (s.transfer - act_capflux - leakage - ae_sat - soilevap_sat);
   f.recharge[i] = recharge;
@@ -502,9 +571,9 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
   if (c.kv_profile >= 2) {
     double kvl[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) kvl[k] = __ldg(f.kv + k * ns + i);
+    for (int k = 0; k < N; ++k) kvl[k] = staged(st2::Rows<N>::kvlay + k);
     f.ssf_kh[i] = kh_layered<N>(c.kv_profile, s, kvl, s.kv.f, s.kv.zx, s.kv.nk + 1,
-                                __ldg(f.ssf_khfrac + i));
+                                staged(st2::Rows<N>::khfrac));
   }
 #endif
 }
@@ -522,59 +591,11 @@ __device__ __forceinline__ void soil_column_cell(const DevFields& f, const KCfg&
 #ifndef WFB_V_MINBLOCKS
 #define WFB_V_MINBLOCKS 5
 #endif
-// Every input array of the cell is requested at the top of the kernel, long before its first use:
-// the loads proper sit next to their first use (registers), and with 16 warps per SM that spend
-// most of their time in FP64 dependency chains only a few of them would be in flight at any time.
-#ifndef WFB_V_PREFETCH
-#define WFB_V_PREFETCH 0   // 0 off, 1 into L1, 2 into L2 (measured on B200: no gain either way)
-#endif
-__device__ __forceinline__ void prefetch_line(const void* p) {
-#if WFB_V_PREFETCH == 1
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#elif WFB_V_PREFETCH == 2
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
-template <int N>
-__device__ __forceinline__ void prefetch_inputs(const DevFields& f, const KCfg& c, const int i) {
-#if WFB_V_PREFETCH
-  const int ns = c.ns;
-  const double* const scalars[] = {
-      f.river_fraction, f.water_fraction, f.olf_h, f.waterdepth_river, f.theta_s, f.theta_r,
-      f.soil_thickness, f.soil_water_capacity, f.saturated_water_depth,
-      f.compacted_soil_area_fraction, f.infiltration_capacity_soil,
-      f.infiltration_capacity_compacted_soil, f.kv_0, f.hydraulic_conductivity_scale_parameter,
-      f.theta_fc, f.rooting_depth, f.h1, f.h2, f.h4, f.alpha_h1, f.air_entry_pressure, f.h3_high,
-      f.h3_low, f.wet_root_distribution_parameter, f.cap_hmax, f.cap_n, f.maximum_leakage};
-#pragma unroll
-  for (int a = 0; a < (int)(sizeof(scalars) / sizeof(scalars[0])); ++a) prefetch_line(scalars[a] + i);
-  if (c.snow) {
-    const double* const snow[] = {f.temperature_interval_snowfall, f.temperature_threshold_snowfall,
-                                  f.snow_storage, f.snow_water, f.temperature_threshold_melt,
-                                  f.degree_day_factor, f.water_holding_capacity,
-                                  f.soil_surface_temperature, f.w_soil};
-#pragma unroll
-    for (int a = 0; a < 9; ++a) prefetch_line(snow[a] + i);
-  }
-  prefetch_line(f.number_of_layers + i);
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    prefetch_line(f.unsaturated_layer_depth + k * ns + i);
-    prefetch_line(f.actual_layer_thickness + k * ns + i);
-    prefetch_line(f.cumulative_layer_depth + k * ns + i);
-    prefetch_line(f.brooks_corey_exponent + k * ns + i);
-    prefetch_line(f.vertical_hydraulic_conductivity_factor + k * ns + i);
-    prefetch_line(f.rootfraction + k * ns + i);
-  }
-  prefetch_line(f.cumulative_layer_depth + N * ns + i);
-#endif
-}
-
 // update_land_hydrology_model!                                                sbm.jl:82-132
 template <int N>
 __global__ void __launch_bounds__(WFB_V_TILE, WFB_V_MINBLOCKS)
-land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
-                      const int tile_begin, const int phase) {
+land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const StageList sl,
+                      const double dt, const int tile_begin, const int phase) {
   // phase 0: the whole update. With lateral snow transport (snow_gravitational_transport__flag,
   // sbm.jl:98-100) a pass over the drainage network sits between the snow and the glacier
   // model: phase 1 = interception + snow, phase 2 = everything after the transport.
@@ -585,16 +606,27 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   // the warp-aggregated suspension) and never suspend; their stores land in the padding
   const bool live = i < c.n;
   const int ns = c.ns;
-  prefetch_inputs<N>(f, c, i);
+  using R = st1::Rows<N>;
+  // the few inputs that are not staged are asked for first, then everything else at once
+  const double P = __ldg(f.precipitation + i);
+  const double PET = __ldg(f.potential_evaporation + i);
+  const double T = __ldg(f.temperature + i);
+  const bool first_part = phase != 2;
+  const bool with_lai = first_part && c.has_lai, with_snow = first_part && c.snow;
+  const double lai = with_lai ? __ldg(f.leaf_area_index + i) : 0.0;
+  const double sl_leaf = with_lai ? __ldg(f.storage_specific_leaf + i) : 0.0;
+  const double s_wood = with_lai ? __ldg(f.storage_wood + i) : 0.0;
+  const double k_ext = with_lai ? __ldg(f.light_extinction_coefficient + i) : 0.0;
+  const double kc = first_part ? __ldg(f.crop_coefficient + i) : 0.0;
+  const double tti = with_snow ? __ldg(f.temperature_interval_snowfall + i) : 0.0;
+  const double tt = with_snow ? __ldg(f.temperature_threshold_snowfall + i) : 0.0;
+  const int nlayers = phase != 1 ? f.number_of_layers[i] : 0;
+  stage_issue(sl, tile_begin + (int)blockIdx.x);
   const Divisor ddt(dt);
   double st_canopy = 0.0, st_snoww = 0.0, st_gstore = 0.0, st_snow = 0.0, st_tsoil = 0.0;
   SoilColumn<N> s;
 
   // ---- forcing ---------------------------------------------------------------------------
-  const double P = __ldg(f.precipitation + i);
-  const double PET = __ldg(f.potential_evaporation + i);
-  const double T = __ldg(f.temperature + i);
-
   // ---- interception (canopy.jl:54-163, rainfall_interception.jl:9-130) ----------------------
   double cmax, gap;
   double canopy_potevap, throughfall = 0.0, interception, stemflow = 0.0;
@@ -607,16 +639,15 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     snow = f.snow_storage[i];       // after lateral_snow_transport!
   } else {
   if (c.has_lai) {
-    const double lai = __ldg(f.leaf_area_index + i);
-    cmax = __ldg(f.storage_specific_leaf + i) * lai + __ldg(f.storage_wood + i);
-    gap = exp(-__ldg(f.light_extinction_coefficient + i) * lai);
+    cmax = sl_leaf * lai + s_wood;
+    gap = exp(-k_ext * lai);
     f.maximum_canopy_storage[i] = cmax;
     f.canopy_gap_fraction[i] = gap;
   } else {
-    cmax = __ldg(f.maximum_canopy_storage + i);
-    gap = __ldg(f.canopy_gap_fraction + i);
+    stage_wait();
+    cmax = staged(R::cmax);
+    gap = staged(R::gap);
   }
-  const double kc = __ldg(f.crop_coefficient + i);
   canopy_potevap = kc * PET * (1.0 - gap);
   if (c.gash) {
     double e_r;
@@ -627,7 +658,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
       e_r = P > 0.0 ? jmin(0.25, fdiv(ewet, jmax(thr, canopyfraction * P))) : 0.0;
       f.evaporation_to_precipitation_ratio[i] = e_r;
     } else {
-      e_r = __ldg(f.evaporation_to_precipitation_ratio + i);
+      e_r = staged(R::e_r);
     }
     if (cmax > 0.0) {
       double frac_stem, frac_int, p_sat;
@@ -660,7 +691,8 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
       throughfall = P; interception = 0.0; stemflow = 0.0;
     }
   } else {
-    double cs = f.canopy_storage[i];
+    stage_wait();
+    double cs = staged(R::canopy_storage);
     double frac_stem, p_canopy;
     if (gap < 1.0 / 1.1) {
       frac_stem = 0.1 * gap;
@@ -687,19 +719,18 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   // ---- snow (snow.jl:123-177, snow_process.jl:26-116) ---------------------------------------
   if (c.snow) {
     const double eff = throughfall + stemflow;
-    const double tti = __ldg(f.temperature_interval_snowfall + i);
-    const double tt = __ldg(f.temperature_threshold_snowfall + i);
     double rainfrac;
     if (tti == 0.0) rainfrac = T > tt ? 1.0 : 0.0;
     else rainfrac = jclamp(fdiv(T - (tt - tti / 2.0), tti), 0.0, 1.0);
     const double snowfrac = 1.0 - rainfrac;
     const double snow_precip = snowfrac * 1.0 * eff;
     const double liquid_precip = rainfrac * 1.0 * eff;
-    snow = f.snow_storage[i];
-    double snoww = f.snow_water[i];
-    const double ttm = __ldg(f.temperature_threshold_melt + i);
-    const double cfmax = __ldg(f.degree_day_factor + i);
-    const double whc = __ldg(f.water_holding_capacity + i);
+    stage_wait();
+    snow = staged(st1::snow_storage);
+    double snoww = staged(st1::snow_water);
+    const double ttm = staged(st1::ttm);
+    const double cfmax = staged(st1::cfmax);
+    const double whc = staged(st1::whc);
     double snow_melt;
     if (T > ttm) {
       const double pot = cfmax * (T - ttm);
@@ -729,6 +760,7 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
     f.snow_runoff[i] = snow_runoff;
   }
   if (phase == 1) {  // the states lateral_snow_transport! works on; the rest follows in phase 2
+    stage_wait();
     if (!c.gash) f.canopy_storage[i] = st_canopy;
     if (c.snow) { f.snow_water[i] = st_snoww; f.snow_storage[i] = snow; }
     return;
@@ -764,9 +796,10 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   f.runoff_water_flux_surface[i] = water_flux_surface;
 
   // ---- open-water runoff (runoff.jl:61-111) ------------------------------------------------
-  const double rf = __ldg(f.river_fraction + i), wf = __ldg(f.water_fraction + i);
-  const double h_land = __ldg(f.olf_h + i);
-  const double h_river = __ldg(f.waterdepth_river + i);  // refreshed by scatter_river_depth_kernel
+  stage_wait();
+  const double rf = staged(st1::rf), wf = staged(st1::wf);
+  const double h_land = staged(st1::olf_h);
+  const double h_river = staged(st1::h_river);  // refreshed by scatter_river_depth_kernel
   f.waterdepth_land[i] = h_land;
   const double runoff_river = jmin(1.0, rf) * water_flux_surface;
   const double runoff_land = jmin(1.0, wf) * water_flux_surface;
@@ -789,20 +822,20 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   f.soil_water_flux_surface[i] = wfs;
 
   // ---- state -> diagnostics (soil.jl:1400-1436) --------------------------------------------
-  s.theta_s = __ldg(f.theta_s + i);
-  s.theta_e = s.theta_s - __ldg(f.theta_r + i);
+  s.theta_s = staged(st1::theta_s);
+  s.theta_e = s.theta_s - staged(st1::theta_r);
   const double theta_e = s.theta_e;
-  s.d_soil = __ldg(f.soil_thickness + i);
-  s.swc = __ldg(f.soil_water_capacity + i);
-  s.satwd = f.saturated_water_depth[i];
-  s.nlayers = f.number_of_layers[i];
+  s.d_soil = staged(st1::d_soil);
+  s.swc = staged(st1::swc);
+  s.satwd = staged(st1::satwd);
+  s.nlayers = nlayers;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    s.uld[k] = f.unsaturated_layer_depth[k * ns + i];
-    s.alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
-    s.cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
+    s.uld[k] = staged(R::uld + k);
+    s.alt[k] = staged(R::alt + k);
+    s.cld[k] = staged(R::cld + k);
   }
-  s.cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
+  s.cld[N] = staged(R::cld + N);
   double ustore_depth = 0.0;
 #pragma unroll
   for (int k = 0; k < N; ++k)
@@ -828,19 +861,19 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   // ---- soil temperature, infiltration (soil.jl:685-755, soil_process.jl:16-41,229-244) -------
   double f_red = 1.0;
   if (c.snow) {
-    double tsoil = f.soil_surface_temperature[i];
-    tsoil = tsoil + __ldg(f.w_soil + i) * (T - tsoil);
+    double tsoil = staged(st1::tsoil);
+    tsoil = tsoil + staged(st1::w_soil) * (T - tsoil);
     st_tsoil = tsoil;
     if (c.soil_infiltration_reduction) {
-      const double cf = __ldg(f.cf_soil + i);
+      const double cf = staged(st1::cf_soil);
       const double bb = fdiv(1.0, 1.0 - cf);
       f_red = scurve(tsoil, 0.0 + 273.15, bb, 8.0) + cf;
     }
   }
   f.f_infiltration_reduction[i] = f_red;
-  const double pathfrac = __ldg(f.compacted_soil_area_fraction + i);
-  const double cap_soil = __ldg(f.infiltration_capacity_soil + i);
-  const double cap_path = __ldg(f.infiltration_capacity_compacted_soil + i);
+  const double pathfrac = staged(st1::pathfrac);
+  const double cap_soil = staged(st1::cap_soil);
+  const double cap_path = staged(st1::cap_path);
   const double soilinf = wfs * (1.0 - pathfrac);
   const double pathinf = wfs * pathfrac;
   const double max_infiltsoil = jmin(cap_soil * f_red, soilinf);
@@ -851,9 +884,9 @@ land_hydrology_kernel(const DevFields f, const KCfg c, const UnsatWork w, const 
   f.infiltration_excess[i] = infiltration_excess;
 
   // ---- unsaturated zone flow, Brooks-Corey (soil.jl:764-804) -------------------------------
-  s.kv = load_kvcol<N>(f, c, i);
+  s.kv = staged_kvcol<N, R>(f, c, i, st1::kv_0, st1::kv_f);
 #pragma unroll
-  for (int k = 0; k < N; ++k) s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
+  for (int k = 0; k < N; ++k) s.bc[k] = staged(R::bc + k);
   double transfer;
   const bool done = unsat_layers<N>(c, w, i, 0, n_unsat, 0.0, 0.0, infiltration, s.uld, s.ult,
                                     s.bc, s.kv, theta_e, dt, ddt, live, transfer);
@@ -881,30 +914,30 @@ template <int N>
 __device__ __forceinline__ void load_column_rest(const DevFields& f, const KCfg& c, const int i,
                                                  SoilColumn<N>& s) {
   const int ns = c.ns;
-  s.d_soil = __ldg(f.soil_thickness + i);
-  s.swc = __ldg(f.soil_water_capacity + i);
-  s.satwd = f.saturated_water_depth[i];
-  s.zi = f.water_table_depth[i];
-  s.nlayers = f.number_of_layers[i];
+  using R = st2::Rows<N>;
+  s.d_soil = staged(st2::d_soil);
+  s.swc = staged(st2::swc);
+  s.satwd = staged(st2::satwd);
+  s.zi = staged(st2::zi);
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    s.alt[k] = __ldg(f.actual_layer_thickness + k * ns + i);
-    s.cld[k] = __ldg(f.cumulative_layer_depth + k * ns + i);
+    s.alt[k] = staged(R::alt + k);
+    s.cld[k] = staged(R::cld + k);
   }
-  s.cld[N] = __ldg(f.cumulative_layer_depth + N * ns + i);
-  s.pot_soilevap = f.potential_soilevaporation[i];
-  s.pot_transp = f.potential_transpiration[i];
-  s.infiltration = f.infiltration[i];
-  s.infiltration_excess = f.infiltration_excess[i];
-  s.wfs = f.soil_water_flux_surface[i];
-  const double f_red = f.f_infiltration_reduction[i];
-  s.pathfrac = __ldg(f.compacted_soil_area_fraction + i);
+  s.cld[N] = staged(R::cld + N);
+  s.pot_soilevap = staged(st2::pot_soilevap);
+  s.pot_transp = staged(st2::pot_transp);
+  s.infiltration = staged(st2::infiltration);
+  s.infiltration_excess = staged(st2::infiltration_excess);
+  s.wfs = staged(st2::wfs);
+  const double f_red = staged(st2::f_red);
+  s.pathfrac = staged(st2::pathfrac);
   // infiltration! soil_process.jl:16-41, the same expressions as in land_hydrology_kernel
-  s.max_infiltsoil = jmin(__ldg(f.infiltration_capacity_soil + i) * f_red, s.wfs * (1.0 - s.pathfrac));
-  s.max_infiltpath = jmin(__ldg(f.infiltration_capacity_compacted_soil + i) * f_red, s.wfs * s.pathfrac);
-  s.aeow_river = f.actual_open_water_evaporation_river[i];
-  s.aeow_land = f.actual_open_water_evaporation_land[i];
-  s.interception = f.interception_rate[i];
+  s.max_infiltsoil = jmin(staged(st2::cap_soil) * f_red, s.wfs * (1.0 - s.pathfrac));
+  s.max_infiltpath = jmin(staged(st2::cap_path) * f_red, s.wfs * s.pathfrac);
+  s.aeow_river = staged(st2::aeow_river);
+  s.aeow_land = staged(st2::aeow_land);
+  s.interception = staged(st2::interception);
 }
 
 // update_land_hydrology_model!, second half (soil evaporation ... recharge, AET), every cell:
@@ -914,11 +947,12 @@ __device__ __forceinline__ void load_column_rest(const DevFields& f, const KCfg&
 #endif
 template <int N>
 __global__ void __launch_bounds__(WFB_V_TILE, WFB_VC_MINBLOCKS)
-soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt,
-                   const int tile_begin) {
+soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const StageList sl,
+                   const double dt, const int tile_begin) {
   const int i = (tile_begin + (int)blockIdx.x) * kTile + (int)threadIdx.x;
-  if (i >= c.n) return;
+  if (i >= c.ns) return;   // whole warps take part in the staging
   const int ns = c.ns;
+  stage_issue(sl, tile_begin + (int)blockIdx.x);
   const Divisor ddt(dt);
   SoilColumn<N> s;
   s.theta_s = __ldg(f.theta_s + i);
@@ -930,22 +964,27 @@ soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const dou
     s.ult[k] = f.unsaturated_layer_thickness[k * ns + i];
     s.bc[k] = __ldg(f.brooks_corey_exponent + k * ns + i);
   }
-  s.kv = load_kvcol<N>(f, c, i);
   s.transfer = f.transfer[i];
+  s.nlayers = f.number_of_layers[i];
+  stage_wait();
+  if (i >= c.n) return;
+  s.kv = staged_kvcol<N, st2::Rows<N>>(f, c, i, st2::kv_0, st2::kv_f);
   load_column_rest<N>(f, c, i, s);
   soil_column_cell<N>(f, c, i, dt, ddt, s);
 }
 
-// The loop engine, split organisation: ONE light kernel takes every suspended cell of a slice
-// through all its remaining unsaturated layers -- the long loop it was suspended at (tracked-power
-// trips), then the layers below with loops of any length in line -- one lane per cell, 32 cells
-// of one bucket per warp, longest buckets first. Per-layer operands are fetched when their layer
-// is reached (an L2 hit, negligible next to a loop), so a lane holds ~50 registers and the
-// kernel is light; soil_column_kernel then runs the second half of every cell.
+// The loop engine: one lane per suspended cell, 32 cells of one bucket (trip counts within a factor
+// of two) per warp, longest buckets first. A lane runs the long loop its cell was suspended at
+// (tracked trips), then the layers below with loops of any length in line. Per-layer operands are
+// fetched when their layer is reached. The kernel lasts as long as the trips of the wettest cell
+// (~4000 on the benchmark basin, ~55 cycles each): sending the later long loops of a cell to a
+// further launch, regrouped by trip count, was built and measured -- no gain, the lanes' idling
+// is not what bounds it.
 template <int N>
 __global__ void __launch_bounds__(128)
 unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
   const unsigned* cnt = w.count;
+  const int32_t* list = w.list;
   const int lane = (int)threadIdx.x & 31;
   const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
   // consecutive tiles (the longest loops) go to different SMs
@@ -957,7 +996,7 @@ unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
     if (!tile_of(cnt, j, b, first, n)) break;
     const int e = first + lane;
     if (e >= n) continue;
-    const int i = w.list[(size_t)b * (size_t)w.cap + e];
+    const int i = list[(size_t)b * (size_t)w.cap + e];
     UnsatTask t;
     t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
     t.c = w.c[i];
@@ -972,7 +1011,7 @@ unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
     f.unsaturated_layer_depth[kl * ns + i] = t.usd;
     double flow = t.sum_ast;
     const int n_unsat = f.n_unsatlayers[i];
-    if (kl + 1 < n_unsat) {  // the layers below (soil.jl:770-801), loops of any length in line
+    if (kl + 1 < n_unsat) {  // the layers below (soil.jl:770-801)
       const KvCol<N> kv = load_kvcol<N>(f, c, i);
       const double theta_e = __ldg(f.theta_s + i) - __ldg(f.theta_r + i);
       double z = 0.0;
@@ -1136,6 +1175,128 @@ int launch_selftest_math(long long n, unsigned long long* out, cudaStream_t s) {
     default: return -1;                               \
   }
 
+// The staging lists of the two dense kernels for this configuration (see the row enums above).
+template <int N>
+static void build_vertical_stage_n(const DevFields& f, const KCfg& c, VerticalStage& vs) {
+  const size_t ns = (size_t)c.ns;
+  auto put = [](StageList& l, int row, const double* p) {
+    l.p[row] = p;
+    if (row + 1 > l.rows) l.rows = row + 1;
+  };
+  auto layered = [&](StageList& l, int row0, const double* p, int layers) {
+    for (int k = 0; k < layers; ++k) put(l, row0 + k, p + (size_t)k * ns);
+  };
+  vs = VerticalStage{};
+  using R1 = st1::Rows<N>;
+  for (int phase = 0; phase < 3; ++phase) {
+    StageList& l = vs.first[phase];
+    if (phase != 2) {  // interception and snow
+      if (!c.has_lai) {
+        put(l, R1::cmax, f.maximum_canopy_storage);
+        put(l, R1::gap, f.canopy_gap_fraction);
+        if (c.gash) put(l, R1::e_r, f.evaporation_to_precipitation_ratio);
+      }
+      if (!c.gash) put(l, R1::canopy_storage, f.canopy_storage);
+      if (c.snow) {
+        put(l, st1::snow_storage, f.snow_storage);
+        put(l, st1::snow_water, f.snow_water);
+        put(l, st1::ttm, f.temperature_threshold_melt);
+        put(l, st1::cfmax, f.degree_day_factor);
+        put(l, st1::whc, f.water_holding_capacity);
+      }
+    }
+    if (phase == 1) continue;
+    if (c.snow) {
+      put(l, st1::tsoil, f.soil_surface_temperature);
+      put(l, st1::w_soil, f.w_soil);
+      if (c.soil_infiltration_reduction) put(l, st1::cf_soil, f.cf_soil);
+    }
+    put(l, st1::rf, f.river_fraction);
+    put(l, st1::wf, f.water_fraction);
+    put(l, st1::olf_h, f.olf_h);
+    put(l, st1::h_river, f.waterdepth_river);
+    put(l, st1::theta_s, f.theta_s);
+    put(l, st1::theta_r, f.theta_r);
+    put(l, st1::d_soil, f.soil_thickness);
+    put(l, st1::swc, f.soil_water_capacity);
+    put(l, st1::satwd, f.saturated_water_depth);
+    put(l, st1::pathfrac, f.compacted_soil_area_fraction);
+    put(l, st1::cap_soil, f.infiltration_capacity_soil);
+    put(l, st1::cap_path, f.infiltration_capacity_compacted_soil);
+    if (c.kv_profile < 2) put(l, st1::kv_0, f.kv_0);
+    if (c.kv_profile != 2) put(l, st1::kv_f, f.hydraulic_conductivity_scale_parameter);
+    if (c.kv_profile == 1) put(l, R1::kv_zx, f.z_exp);
+    if (c.kv_profile == 3) put(l, R1::kv_zx, f.z_layered);
+    layered(l, R1::kvfac, f.vertical_hydraulic_conductivity_factor, N);
+    if (c.kv_profile >= 2) layered(l, R1::kvlay, f.kv, N);
+    layered(l, R1::uld, f.unsaturated_layer_depth, N);
+    layered(l, R1::alt, f.actual_layer_thickness, N);
+    layered(l, R1::bc, f.brooks_corey_exponent, N);
+    layered(l, R1::cld, f.cumulative_layer_depth, N + 1);
+  }
+  using R2 = st2::Rows<N>;
+  StageList& l = vs.second;
+  put(l, st2::d_soil, f.soil_thickness);
+  put(l, st2::swc, f.soil_water_capacity);
+  put(l, st2::satwd, f.saturated_water_depth);
+  put(l, st2::zi, f.water_table_depth);
+  put(l, st2::pot_soilevap, f.potential_soilevaporation);
+  put(l, st2::pot_transp, f.potential_transpiration);
+  put(l, st2::infiltration, f.infiltration);
+  put(l, st2::infiltration_excess, f.infiltration_excess);
+  put(l, st2::wfs, f.soil_water_flux_surface);
+  put(l, st2::f_red, f.f_infiltration_reduction);
+  put(l, st2::pathfrac, f.compacted_soil_area_fraction);
+  put(l, st2::cap_soil, f.infiltration_capacity_soil);
+  put(l, st2::cap_path, f.infiltration_capacity_compacted_soil);
+  put(l, st2::aeow_river, f.actual_open_water_evaporation_river);
+  put(l, st2::aeow_land, f.actual_open_water_evaporation_land);
+  put(l, st2::interception, f.interception_rate);
+  put(l, st2::theta_fc, f.theta_fc);
+  put(l, st2::rooting_depth, f.rooting_depth);
+  put(l, st2::h1, f.h1);
+  put(l, st2::h2, f.h2);
+  put(l, st2::h4, f.h4);
+  put(l, st2::alpha_h1, f.alpha_h1);
+  put(l, st2::air_entry, f.air_entry_pressure);
+  put(l, st2::h3_high, f.h3_high);
+  put(l, st2::h3_low, f.h3_low);
+  put(l, st2::wet_root, f.wet_root_distribution_parameter);
+  put(l, st2::cap_hmax, f.cap_hmax);
+  put(l, st2::cap_n, f.cap_n);
+  put(l, st2::max_leakage, f.maximum_leakage);
+  if (c.kv_profile < 2) put(l, st2::kv_0, f.kv_0);
+  if (c.kv_profile != 2) put(l, st2::kv_f, f.hydraulic_conductivity_scale_parameter);
+  if (c.kv_profile == 1) put(l, R2::kv_zx, f.z_exp);
+  if (c.kv_profile == 3) put(l, R2::kv_zx, f.z_layered);
+  layered(l, R2::kvfac, f.vertical_hydraulic_conductivity_factor, N);
+  layered(l, R2::alt, f.actual_layer_thickness, N);
+  layered(l, R2::cld, f.cumulative_layer_depth, N + 1);
+  layered(l, R2::rootf, f.rootfraction, N);
+  if (c.kv_profile >= 2) {
+    put(l, R2::khfrac, f.ssf_khfrac);
+    layered(l, R2::kvlay, f.kv, N);
+  }
+  // more than 48 KB of dynamic shared memory has to be asked for once per kernel
+  const int most = (int)sizeof(double) * kTile * kMaxStage;
+  cudaFuncSetAttribute(land_hydrology_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+  cudaFuncSetAttribute(soil_column_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+}
+
+void build_vertical_stage(const DevFields& f, const KCfg& c, int n_layers, VerticalStage& vs) {
+  switch (n_layers) {
+    case 1: build_vertical_stage_n<1>(f, c, vs); break;
+    case 2: build_vertical_stage_n<2>(f, c, vs); break;
+    case 3: build_vertical_stage_n<3>(f, c, vs); break;
+    case 4: build_vertical_stage_n<4>(f, c, vs); break;
+    case 5: build_vertical_stage_n<5>(f, c, vs); break;
+    case 6: build_vertical_stage_n<6>(f, c, vs); break;
+    case 7: build_vertical_stage_n<7>(f, c, vs); break;
+    case 8: build_vertical_stage_n<8>(f, c, vs); break;
+    default: vs = VerticalStage{}; break;
+  }
+}
+
 int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s) {
   if (c.nriv == 0) return 0;
   scatter_river_depth_kernel<<<(c.nriv + 255) / 256, 256, 0, s>>>(f, c);
@@ -1150,24 +1311,26 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 // by DRAM), so nothing is hidden. tl (optional timing events): [0] start, [1] land_hydrology,
 // [2] unsat_engine, [3] soil_column done.
 int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, double dt,
-                          const UnsatWork& w, int engine_grid, int phase, bool run_engine,
-                          cudaStream_t s, cudaEvent_t const* tl) {
+                          const UnsatWork& w, const VerticalStage& vs, int engine_grid, int phase,
+                          bool run_engine, cudaStream_t s, cudaEvent_t const* tl) {
   int launches = 0;
   const int n_tiles = (c.ns + kTile - 1) / kTile;
+  const StageList& s1 = vs.first[phase];
+  const size_t row = sizeof(double) * kTile, smem1 = s1.rows * row, smem2 = vs.second.rows * row;
   if (tl) cudaEventRecord(tl[0], s);
   if (phase == 1) {  // interception + snow of every cell: no loops, no engine
-    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w, dt, 0, 1)));
+    WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, smem1, s>>>(f, c, w, s1, dt, 0, 1)));
     return launches + 1;
   }
   cudaMemsetAsync(w.count, 0, kBuckets * sizeof(unsigned), s);
-  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w, dt, 0, phase)));
+  WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, smem1, s>>>(f, c, w, s1, dt, 0, phase)));
   if (tl) cudaEventRecord(tl[1], s);
   if (run_engine)
     WFB_DISPATCH_N(n_layers, (unsat_engine_kernel<N><<<engine_grid, 128, 0, s>>>(f, c, w, dt)));
   if (tl) cudaEventRecord(tl[2], s);
-  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<n_tiles, kTile, 0, s>>>(f, c, w, dt, 0)));
+  WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<n_tiles, kTile, smem2, s>>>(f, c, w, vs.second, dt, 0)));
   if (tl) cudaEventRecord(tl[3], s);
-  return launches + 3;
+  return launches + 2 + (run_engine ? 1 : 0);
 }
 
 int launch_exchange_recharge(const DevFields& f, const KCfg& c, cudaStream_t s) {
