@@ -99,6 +99,25 @@ typedef struct {
    * (surface_kinwave.jl:441-489). nres = 0 / NULL: no reservoirs. */
   int64_t nres;
   const int64_t* reservoir_river_indices; /* nres, 1-based river node ids                      */
+  /* A shard that is PART of a drainage basin, cut at confluences (the reference cuts its basins
+   * the same way into sub-domains for its threads, subdomains.jl:169-255): discharge crosses
+   * the shard's border on CUT EDGES. An IMPORT is a cut edge whose upstream node lives on another
+   * shard; an EXPORT is one whose downstream node does (here the node is a pit of `ldd`).
+   * import_dst: the local node (1-based) the edge ends in; import_pos: the position of the edge
+   * among ALL upstream sources of that node in ascending GLOBAL node id (0-based) -- the
+   * reference sums upstream values in that order (utils.jl:472-477) and the shards must too.
+   * export_src: the local node (1-based) the edge leaves. All zero / NULL: no cut edges.
+   * Values travel through wflowb200_exchange_* below. */
+  int64_t n_land_imports;
+  const int64_t* land_import_dst;
+  const int64_t* land_import_pos;
+  int64_t n_land_exports;
+  const int64_t* land_export_src;
+  int64_t n_river_imports;
+  const int64_t* river_import_dst;
+  const int64_t* river_import_pos;
+  int64_t n_river_exports;
+  const int64_t* river_export_src;
 } WflowB200Domain;
 
 /* artefact ids for wflowb200_get_artifact (all returned as 1-based int64, reference layout) */
@@ -248,6 +267,34 @@ int32_t wflowb200_comm_init_nccl(WflowB200* h, int32_t rank, int32_t world, cons
 int32_t wflowb200_group_create(int32_t n_handles, WflowB200Group** out);
 int32_t wflowb200_group_join(WflowB200Group* g, WflowB200* h);
 void wflowb200_group_destroy(WflowB200Group* g);
+
+/* ---- cut edges: discharge across shards of ONE basin over NVLink peer memory ---------------
+ * (kinematic-wave routing with fixed internal time steps; update_model only.)
+ * Every sub-step value that crosses a cut edge -- subsurface flow (and its share for the river),
+ * overland flow of each of the S_land sub-steps, river discharge of each of the S_river sub-steps --
+ * is ONE 8-byte store of the producing lane straight into the consumer GPU's memory
+ * (st.relaxed.sys through the NVLink mapping), into the slot the consuming lane polls: the same
+ * data-is-flag slots the chunks of one GPU use among themselves, so the wavefronts of the shards
+ * run as ONE skewed wavefront without any collective on the data path. The slots are double
+ * buffered by the parity of the model step; a shard resets the other buffer at the start of a
+ * step, behind a barrier of the communicator (wflowb200_comm_init_nccl / group_join: required).
+ *   1. every shard: exchange_prepare(h, dt) -> its import buffer (device pointer for handles of
+ *      the same process, CUDA IPC handle for other processes) and size;
+ *   2. every producer: exchange_open_peer(h, peer, ...) for each shard it exports to, then
+ *      exchange_bind(h, domain, export, peer, import of that peer) for each export;
+ *   3. update_model as usual, all shards in the same step. */
+int32_t wflowb200_exchange_prepare(WflowB200* h, double dt, uint64_t* device_ptr,
+                                   void* ipc_handle64, int64_t* bytes);
+/* peer: any id >= 0 chosen by the caller (< 64). device_ptr != 0: the peer's buffer is
+ * addressable as is (same process; peer_device = its CUDA device, peer access is enabled);
+ * otherwise ipc_handle64 is opened. n_*_imports: the PEER's import counts (layout of its buffer). */
+int32_t wflowb200_exchange_open_peer(WflowB200* h, int32_t peer, uint64_t device_ptr,
+                                     int32_t peer_device, const void* ipc_handle64,
+                                     int64_t peer_n_land_imports, int64_t peer_n_river_imports);
+/* export `export_index` (0-based, order of *_export_src) of `domain` feeds import
+ * `peer_import_index` (0-based, order of the peer's *_import_dst) of the same domain on `peer` */
+int32_t wflowb200_exchange_bind(WflowB200* h, int32_t domain, int64_t export_index, int32_t peer,
+                                int64_t peer_import_index);
 
 /* Select between kernel organisations that give identical results (the parity tests run every
  * one): "fuse_soil_storage", "overlap_subsurface" (-1 automatic, 0, 1), "overlap_subsurface_sms",

@@ -1,5 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
-    --log-file gpurun_out/launches_r2l.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
-    --option vertical_graph=0 > gpurun_out/bench_under_ncu_r2l.log 2>&1
-wc -l gpurun_out/launches_r2l.csv
+timeout 600 python -m pytest tests/test_gpu_cut_exchange.py -m gpu -x -q -s 2>&1 | tail -30

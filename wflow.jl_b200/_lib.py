@@ -32,7 +32,13 @@ class Config(C.Structure):
 class Domain(C.Structure):
     _fields_ = [("d1", C.c_int64), ("d2", C.c_int64), ("indices", C.c_void_p),
                 ("ldd", C.c_void_p), ("river_land_indices", C.c_void_p), ("nres", C.c_int64),
-                ("reservoir_river_indices", C.c_void_p)]
+                ("reservoir_river_indices", C.c_void_p),
+                # cut edges of a shard that is part of a basin
+                ("n_land_imports", C.c_int64), ("land_import_dst", C.c_void_p),
+                ("land_import_pos", C.c_void_p), ("n_land_exports", C.c_int64),
+                ("land_export_src", C.c_void_p), ("n_river_imports", C.c_int64),
+                ("river_import_dst", C.c_void_p), ("river_import_pos", C.c_void_p),
+                ("n_river_exports", C.c_int64), ("river_export_src", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -116,6 +122,10 @@ def lib():
     L.wflowb200_comm_init_nccl.argtypes = [vp, i32, i32, C.c_char_p]
     L.wflowb200_group_create.argtypes = [i32, C.POINTER(vp)]
     L.wflowb200_group_join.argtypes = [vp, vp]
+    L.wflowb200_exchange_prepare.argtypes = [vp, C.c_double, C.POINTER(C.c_uint64), vp,
+                                             C.POINTER(C.c_int64)]
+    L.wflowb200_exchange_open_peer.argtypes = [vp, i32, C.c_uint64, i32, vp, C.c_int64, C.c_int64]
+    L.wflowb200_exchange_bind.argtypes = [vp, i32, C.c_int64, i32, C.c_int64]
     L.wflowb200_group_destroy.argtypes = [vp]
     L.wflowb200_group_destroy.restype = None
     L.wflowb200_set_option.argtypes = [vp, C.c_char_p, i32]

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,41 @@ const int kFieldKinds[] = {
 #undef X
 };
 std::string g_create_error;
+
+// Cut edges of a shard that is part of a basin (wflowb200_exchange_*). Kinds of values:
+// 0 overland flow (land, 2 values per sub-step), 1 river flow (river, 1), 2 subsurface flow (land, 2).
+struct ExchangeLayout {
+  int64_t n_imp[2] = {0, 0};     // imports of the land / river domain
+  size_t kind_off[3] = {0, 0, 0};
+  size_t words = 0;              // one parity
+  void set(int64_t n_land, int64_t n_river, const int (&S)[3]) {
+    n_imp[0] = n_land; n_imp[1] = n_river;
+    kind_off[0] = 0;
+    kind_off[1] = kind_off[0] + (size_t)n_land * S[0] * 2;
+    kind_off[2] = kind_off[1] + (size_t)n_river * S[1] * 1;
+    words = kind_off[2] + (size_t)n_land * S[2] * 2;
+  }
+};
+struct ExchangePeer {
+  unsigned long long* base = nullptr;
+  bool ipc = false;
+  ExchangeLayout lay;
+};
+struct Exchange {
+  bool prepared = false;         // exchange_prepare was called: the shard takes part in the barrier
+  int64_t n_exp[2] = {0, 0};
+  int S[3] = {0, 0, 0};
+  ExchangeLayout lay;            // of this shard's import buffer
+  unsigned long long* imp = nullptr;            // device: [2 parities][lay.words]
+  std::map<int, ExchangePeer> peers;
+  std::vector<std::pair<int, int64_t>> bound[2];  // per export: (peer, import of the peer), -1 unbound
+  unsigned long long** d_exp[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  bool tables_current = false;
+  uint64_t step = 0;
+  bool in_update_model = false;
+  unsigned long long* d_token = nullptr;  // the barrier's all-reduced word
+  bool active() const { return lay.n_imp[0] + lay.n_imp[1] + n_exp[0] + n_exp[1] > 0; }
+};
 
 struct DomainDev {
   Network nw;
@@ -211,6 +247,8 @@ struct Tuning {
   int overlap_ssf = -1;       // -1 automatic: subsurface sweep and surface kernel overlapped
   int ssf_overlap_sms = 0;    // 0 = 13/32 of the SMs
   int fuse_surface = 1;       // overland + river in one kernel
+  int grid_percent = 100;     // share of the co-resident capacity the wavefront kernels may take
+                              // (several handles with cut edges on ONE GPU must all be resident)
   int river_share = 1, river_period = 3;  // warps of the surface kernel serving the river
   int use_graph = 1;          // vertical update as one CUDA graph launch
   int run_engine = 1;         // 0: skip the loop engine (timing experiments; results invalid)
@@ -243,6 +281,7 @@ struct WflowB200 {
   double* d_forcing = nullptr; // device staging for forcing (3n doubles)
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   ShardComm* comm = nullptr;   // reductions across the shards of the domain (adaptive mode)
+  Exchange xchg;               // cut edges
   cudaEvent_t forcing_ready = nullptr, forcing_consumed = nullptr;
   bool forcing_pending = false;
   // staging ring of forcing slabs in HBM (wflowb200_forcing_ring_*): the host uploads the slabs of
@@ -371,9 +410,23 @@ cudaError_t upload_raw(const std::vector<T>& src, const T** dst, std::vector<voi
 // utils.jl:61-71); otherwise (river) they stay -- they carry the reservoir's outflow -- but
 // move to the END of the receiving node's fold: the reference forms qin[v] = outflow first and
 // then adds sum_at(q, upstream_nodes) (surface_kinwave.jl:481-482,517), and a + b == b + a.
+// imp_dst / imp_pos / exp_src: the shard's cut edges of this domain (WflowB200Domain).
 int32_t upload_domain(WflowB200* h, DomainDev& d, const Network& nw,
-                      const std::vector<uint8_t>& outlet_res, bool cut_outlets) {
+                      const std::vector<uint8_t>& outlet_res, bool cut_outlets,
+                      const std::vector<int64_t>& imp_dst = {}, const std::vector<int64_t>& imp_pos = {},
+                      const std::vector<int64_t>& exp_src = {}) {
   const int64_t n = nw.n;
+  // imports by receiving node, ascending position
+  std::vector<std::vector<std::pair<int64_t, int64_t>>> imports_of;  // node -> (pos, import)
+  if (!imp_dst.empty()) {
+    imports_of.resize(n);
+    for (size_t k = 0; k < imp_dst.size(); ++k) {
+      if (imp_dst[k] < 1 || imp_dst[k] > n || imp_pos[k] < 0 || imp_pos[k] > 7)
+        return fail(h, WFLOWB200_ERR_ARG, "import: bad node or position");
+      imports_of[imp_dst[k] - 1].emplace_back(imp_pos[k], (int64_t)k);
+    }
+    for (auto& l : imports_of) std::sort(l.begin(), l.end());
+  }
   CUDA_TRY(h, upload_i32(nw.perm, &d.node_of_slot, -1));
   std::vector<int4> meta(nw.n_chunks);
   std::vector<unsigned long long> node_edges(n, ~0ull);
@@ -392,9 +445,10 @@ int32_t upload_domain(WflowB200* h, DomainDev& d, const Network& nw,
       node_level[p] = (uint8_t)(nw.node_level[v] - nw.chunk_l0[c]);
       node_out[p] = (int32_t)nw.out_of_node[v];
       const int64_t deg = nw.in_ptr[v + 1] - nw.in_ptr[v];
-      if (deg > 8) return fail(h, WFLOWB200_ERR_GRAPH, "node with more than 8 upstream nodes");
+      const int64_t n_imp_v = imports_of.empty() ? 0 : (int64_t)imports_of[v].size();
+      if (deg + n_imp_v > 8) return fail(h, WFLOWB200_ERR_GRAPH, "node with more than 8 upstream nodes");
       unsigned long long code = ~0ull;
-      int64_t srcs[8];
+      int64_t srcs[8];   // node id, or -(import + 1)
       int64_t ns_ = 0;
       for (int pass = 0; pass < 2; ++pass)   // ordinary sources, then reservoir outlets
         for (int64_t e = 0; e < deg; ++e) {
@@ -403,8 +457,24 @@ int32_t upload_domain(WflowB200* h, DomainDev& d, const Network& nw,
           if (is_res != (pass == 1) || (is_res && cut_outlets)) continue;
           srcs[ns_++] = u;
         }
+      for (int64_t q = 0; q < n_imp_v; ++q) {  // a cut edge takes its place in the global order
+        const int64_t pos = imports_of[v][q].first;
+        if (pos > ns_) return fail(h, WFLOWB200_ERR_ARG, "import: position beyond the node's sources");
+        for (int64_t e = ns_; e > pos; --e) srcs[e] = srcs[e - 1];
+        srcs[pos] = -(imports_of[v][q].second + 1);
+        ++ns_;
+      }
       for (int64_t e = 0; e < ns_; ++e) {
         const int64_t u = srcs[e];
+        if (u < 0) {  // import: an inlet edge fed by another GPU
+          if (WFB_CHUNK_NODES + k >= (int64_t)WFB_NO_EDGE)
+            return fail(h, WFLOWB200_ERR_STATE, "too many inlet edges in one chunk");
+          const unsigned long long b = (unsigned long long)(WFB_CHUNK_NODES + k++);
+          inl_level.push_back(node_level[p]);
+          inl_src.push_back((int32_t)(nw.n_outlets + (-u - 1)));
+          code = (code & ~(0xffull << (8 * e))) | (b << (8 * e));
+          continue;
+        }
         const int64_t cu = nw.chunk_of_node[u];
         unsigned long long b;
         if (cu != c) {
@@ -432,6 +502,17 @@ int32_t upload_domain(WflowB200* h, DomainDev& d, const Network& nw,
   d.dev.n_outlets = (int32_t)nw.n_outlets;
   CUDA_TRY(h, upload_raw(inl_src, &d.dev.inl_src, d.dev_arrays));
   CUDA_TRY(h, upload_raw(inl_level, &d.dev.inl_level, d.dev_arrays));
+  d.dev.node_export = nullptr;
+  if (!exp_src.empty()) {
+    std::vector<int32_t> node_export(n, -1);
+    for (size_t k = 0; k < exp_src.size(); ++k) {
+      const int64_t v = exp_src[k];
+      if (v < 1 || v > n || nw.down[v - 1] != 0 || node_export[nw.slot_of[v - 1]] >= 0)
+        return fail(h, WFLOWB200_ERR_ARG, "export: the node must be a distinct pit of the shard's ldd");
+      node_export[nw.slot_of[v - 1]] = (int32_t)k;
+    }
+    CUDA_TRY(h, upload_raw(node_export, &d.dev.node_export, d.dev_arrays));
+  }
   {
     std::vector<int64_t> cos(n);
     for (int64_t p = 0; p < n; ++p) cos[p] = nw.chunk_of_node[nw.perm[p] - 1];
@@ -502,6 +583,24 @@ int32_t check_launch(WflowB200* h, int rc, const char* what) {
   return WFLOWB200_OK;
 }
 
+// Cut edges: this step's import slots and export targets of one component.
+int32_t bind_exchange(WflowB200* h, int kind, WaveLaunch& w) {
+  w.imports = nullptr;
+  w.exports = nullptr;
+  Exchange& x = h->xchg;
+  if (!x.active()) return WFLOWB200_OK;
+  if (!x.prepared || !x.tables_current || !x.in_update_model)
+    return fail(h, WFLOWB200_ERR_STATE,
+                "a shard with cut edges runs through wflowb200_update_model after "
+                "wflowb200_exchange_prepare / open_peer / bind (every export bound)");
+  if (w.S != x.S[kind])
+    return fail(h, WFLOWB200_ERR_ARG, "cut edges: the time step differs from wflowb200_exchange_prepare");
+  const int par = (int)(x.step & 1);
+  if (x.imp) w.imports = x.imp + (size_t)par * x.lay.words + x.lay.kind_off[kind];
+  w.exports = x.d_exp[kind][par];
+  return WFLOWB200_OK;
+}
+
 // Run one routing component with the fixed-step skewed wavefront. kind: 0 overland, 1 river,
 // 2 subsurface; nv = values published per node and sub-step.
 template <class Launch>
@@ -532,10 +631,12 @@ int32_t run_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int kin
   w.dt = dt;
   w.accumulate = accumulate ? 1 : 0;
   w.fuse_soil_storage = fuse_soil_storage ? 1 : 0;
-  w.grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, d.nw.n_chunks));
+  w.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)max_grid * h->tune.grid_percent / 100, d.nw.n_chunks));
   w.smem = smem;
   w.err = h->d_err;
-  int32_t rc = check_launch(h, launch(w), what);
+  int32_t rc = bind_exchange(h, kind, w);
+  if (rc) return rc;
+  rc = check_launch(h, launch(w), what);
   if (rc) return rc;
   substeps = S;
   return WFLOWB200_OK;
@@ -566,7 +667,7 @@ int32_t prepare_wave(WflowB200* h, DomainDev& d, double dt, double dt_fixed, int
   w.dt = dt;
   w.err = h->d_err;
   substeps = S;
-  return WFLOWB200_OK;
+  return bind_exchange(h, kind, w);
 }
 
 // Adaptive internal time stepping (kinematic_wave__adaptive_time_step_flag): the reference's
@@ -852,9 +953,33 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
         res_land[dom->river_land_indices[r - 1] - 1] = 1;
       }
     }
-    if (upload_domain(h, h->land, h->land.nw, res_land, true) ||
-        upload_domain(h, h->river, h->river.nw, res_riv, false))
-      return bail(WFLOWB200_ERR_CUDA);
+    auto vec = [](const int64_t* p, int64_t k) {
+      return (p && k > 0) ? std::vector<int64_t>(p, p + k) : std::vector<int64_t>();
+    };
+    const int64_t nli = dom->n_land_imports, nle = dom->n_land_exports;
+    const int64_t nri = dom->n_river_imports, nre = dom->n_river_exports;
+    if (nli < 0 || nle < 0 || nri < 0 || nre < 0 || (nli && (!dom->land_import_dst || !dom->land_import_pos)) ||
+        (nle && !dom->land_export_src) || (nri && (!dom->river_import_dst || !dom->river_import_pos)) ||
+        (nre && !dom->river_export_src)) {
+      h->err = "cut edges: counts and arrays do not agree";
+      return bail(WFLOWB200_ERR_ARG);
+    }
+    if (nli + nle + nri + nre > 0 &&
+        (cfg->adaptive || h->nres > 0 || cfg->snow_gravitational_transport || cfg->river_routing != 0)) {
+      h->err = "cut edges are supported for kinematic-wave routing with fixed internal time steps, "
+               "without reservoirs and lateral snow transport";
+      return bail(WFLOWB200_ERR_ARG);
+    }
+    h->xchg.lay.n_imp[0] = nli; h->xchg.lay.n_imp[1] = nri;
+    h->xchg.n_exp[0] = nle; h->xchg.n_exp[1] = nre;
+    h->xchg.bound[0].assign(nle, {-1, -1});
+    h->xchg.bound[1].assign(nre, {-1, -1});
+    if (upload_domain(h, h->land, h->land.nw, res_land, true, vec(dom->land_import_dst, nli),
+                      vec(dom->land_import_pos, nli), vec(dom->land_export_src, nle)) ||
+        upload_domain(h, h->river, h->river.nw, res_riv, false, vec(dom->river_import_dst, nri),
+                      vec(dom->river_import_pos, nri), vec(dom->river_export_src, nre)))
+      return bail(h->err.find("import") != std::string::npos || h->err.find("export") != std::string::npos
+                      ? WFLOWB200_ERR_ARG : WFLOWB200_ERR_CUDA);
     h->snow_net = &h->land;
     if (cfg->snow_gravitational_transport && h->nres > 0) {
       // accucapacityflux! walks the FULL land graph (routing/utils.jl:82-109): a second set of
@@ -990,10 +1115,13 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   return WFLOWB200_OK;
 }
 
+static void free_exchange(WflowB200* h);
+static int32_t exchange_begin_step(WflowB200* h);
 void wflowb200_destroy(WflowB200* h) {
   if (!h) return;
   DeviceGuard device_guard_(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  free_exchange(h);
   delete h->comm;
   h->comm = nullptr;
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1432,7 +1560,8 @@ static int32_t update_surface_fused(WflowB200* h, double dt) {
   wl.smem = wr.smem = h->smem_surface;
   wl.smem_per_warp = wr.smem_per_warp = h->smem_surface_per_warp;
   const int64_t warps_needed = h->land.nw.n_chunks + h->river.nw.n_chunks;
-  wl.grid = wr.grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_surface, (warps_needed + 7) / 8));
+  wl.grid = wr.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->grid_surface * h->tune.grid_percent / 100,
+                                                                 (warps_needed + 7) / 8));
   SurfaceSync sync{};
   sync.land_done = h->land.chunk_done;
   sync.epoch = ++h->surface_epoch;
@@ -1464,6 +1593,10 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   // SMs (= CTAs) of the subsurface sweep; measured at 1000^2 (routing ms): 44 SMs 2.38, 52: 1.91, 60: 1.83, 64: 1.89, 74: 2.11, 84: 2.38
   int ssf_ctas = h->tune.ssf_overlap_sms > 0 ? h->tune.ssf_overlap_sms : (sms * 13) / 32;
   if (ssf_ctas < 1 || ssf_ctas >= sms) ssf_ctas = (sms * 13) / 32;
+  if (h->tune.grid_percent < 100) {  // the handle shares the GPU with other handles
+    sms = std::max(2, sms * h->tune.grid_percent / 100);
+    ssf_ctas = std::max(1, std::min(ssf_ctas * h->tune.grid_percent / 100, sms - 1));
+  }
   WaveLaunch ws{}, wl{}, wr{};
   int32_t rc;
   if ((rc = prepare_wave(h, h->land, dt, h->cfg.dt_land, 0, 2, wl, h->sub_land, "update_overland_flow_model"))) return rc;
@@ -1490,6 +1623,7 @@ static int32_t update_routing_overlapped(WflowB200* h, double dt, bool* done) {
   ws.dt = dt;
   ws.smem = h->smem_ssf;
   ws.err = h->d_err;
+  if ((rc = bind_exchange(h, 2, ws))) return rc;
   ws.grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ssf_ctas, h->grid_ssf), h->land.nw.n_chunks));
   ws.fuse_soil_storage = 1;
   ws.done_flags = h->land.chunk_ssf_done;
@@ -1538,8 +1672,18 @@ static int32_t book_stage_times(WflowB200* h) {
   return WFLOWB200_OK;
 }
 
+static int32_t update_model_step(WflowB200* h, double dt);
 int32_t wflowb200_update_model(WflowB200* h, double dt) {
   WFB_ENTER(h);
+  int32_t rc = exchange_begin_step(h);
+  if (rc) return rc;
+  h->xchg.in_update_model = true;
+  rc = update_model_step(h, dt);
+  h->xchg.in_update_model = false;
+  if (rc == WFLOWB200_OK) h->xchg.step++;
+  return rc;
+}
+static int32_t update_model_step(WflowB200* h, double dt) {
   int32_t rc;
   auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->ev[i], h->stream); };
   mark(0);
@@ -1678,6 +1822,154 @@ int32_t wflowb200_group_join(WflowB200Group* g, WflowB200* h) {
   return WFLOWB200_OK;
 }
 
+// ---- cut edges ------------------------------------------------------------------------------
+static void free_exchange(WflowB200* h) {
+  Exchange& x = h->xchg;
+  for (auto& kv : x.peers)
+    if (kv.second.ipc && kv.second.base) cudaIpcCloseMemHandle(kv.second.base);
+  x.peers.clear();
+  for (auto& k : x.d_exp)
+    for (auto& t : k) { cudaFree(t); t = nullptr; }
+  cudaFree(x.imp); x.imp = nullptr;
+  cudaFree(x.d_token); x.d_token = nullptr;
+}
+
+int32_t wflowb200_exchange_prepare(WflowB200* h, double dt, uint64_t* device_ptr,
+                                   void* ipc_handle64, int64_t* bytes) {
+  WFB_ENTER(h);
+  Exchange& x = h->xchg;
+  if (x.prepared) return fail(h, WFLOWB200_ERR_STATE, "exchange_prepare: called twice");
+  if (h->cfg.adaptive) return fail(h, WFLOWB200_ERR_ARG, "exchange: fixed internal time steps only");
+  std::vector<double> dts;
+  const double fixed[3] = {h->cfg.dt_land, h->cfg.dt_river, h->cfg.dt_ssf};
+  for (int k = 0; k < 3; ++k) {
+    x.S[k] = fixed_substeps(dt, fixed[k], dts);
+    if (x.S[k] <= 0) return fail(h, WFLOWB200_ERR_ARG, "exchange_prepare: bad internal time step");
+  }
+  x.lay.set(x.lay.n_imp[0], x.lay.n_imp[1], x.S);
+  CUDA_TRY(h, cudaMalloc((void**)&x.d_token, sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMemset(x.d_token, 0, sizeof(unsigned long long)));
+  if (x.lay.words > 0) {
+    CUDA_TRY(h, cudaMalloc((void**)&x.imp, 2 * x.lay.words * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemset(x.imp, 0xff, 2 * x.lay.words * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    if (ipc_handle64) {
+      static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+      cudaIpcMemHandle_t ih;
+      CUDA_TRY(h, cudaIpcGetMemHandle(&ih, x.imp));
+      memcpy(ipc_handle64, &ih, 64);
+    }
+  } else if (ipc_handle64) {
+    memset(ipc_handle64, 0, 64);
+  }
+  if (device_ptr) *device_ptr = (uint64_t)(uintptr_t)x.imp;
+  if (bytes) *bytes = (int64_t)(2 * x.lay.words * sizeof(unsigned long long));
+  x.prepared = true;
+  x.tables_current = false;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_exchange_open_peer(WflowB200* h, int32_t peer, uint64_t device_ptr,
+                                     int32_t peer_device, const void* ipc_handle64,
+                                     int64_t peer_n_land_imports, int64_t peer_n_river_imports) {
+  WFB_ENTER(h);
+  Exchange& x = h->xchg;
+  if (!x.prepared) return fail(h, WFLOWB200_ERR_STATE, "exchange_open_peer: exchange_prepare first");
+  if (peer < 0 || peer >= 64 || x.peers.count(peer) || peer_n_land_imports < 0 || peer_n_river_imports < 0)
+    return fail(h, WFLOWB200_ERR_ARG, "exchange_open_peer: bad or repeated peer");
+  ExchangePeer pr;
+  pr.lay.set(peer_n_land_imports, peer_n_river_imports, x.S);
+  if (device_ptr) {
+    if (peer_device != h->cfg.device) {
+      int can = 0;
+      CUDA_TRY(h, cudaDeviceCanAccessPeer(&can, h->cfg.device, peer_device));
+      if (!can) return fail(h, WFLOWB200_ERR_CUDA, "exchange_open_peer: no peer access between the devices");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(h, WFLOWB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    pr.base = (unsigned long long*)(uintptr_t)device_ptr;
+  } else {
+    if (!ipc_handle64) return fail(h, WFLOWB200_ERR_ARG, "exchange_open_peer: no pointer and no IPC handle");
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, ipc_handle64, 64);
+    void* ptr = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    pr.base = (unsigned long long*)ptr;
+    pr.ipc = true;
+  }
+  x.peers[peer] = pr;
+  x.tables_current = false;
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_exchange_bind(WflowB200* h, int32_t domain, int64_t export_index, int32_t peer,
+                                int64_t peer_import_index) {
+  WFB_ENTER(h);
+  Exchange& x = h->xchg;
+  if (domain < 0 || domain > 1 || export_index < 0 || export_index >= x.n_exp[domain])
+    return fail(h, WFLOWB200_ERR_ARG, "exchange_bind: no such export");
+  auto it = x.peers.find(peer);
+  if (it == x.peers.end() || peer_import_index < 0 || peer_import_index >= it->second.lay.n_imp[domain])
+    return fail(h, WFLOWB200_ERR_ARG, "exchange_bind: no such peer or import");
+  x.bound[domain][export_index] = {peer, peer_import_index};
+  x.tables_current = false;
+  return WFLOWB200_OK;
+}
+
+// per (kind, parity): where every export of the kind's domain stores its S x NV values
+static int32_t build_export_tables(WflowB200* h) {
+  Exchange& x = h->xchg;
+  static const int kDomainOfKind[3] = {0, 1, 0}, kNv[3] = {2, 1, 2};
+  for (int kind = 0; kind < 3; ++kind) {
+    const int dom = kDomainOfKind[kind];
+    const int64_t ne = x.n_exp[dom];
+    for (int par = 0; par < 2; ++par) {
+      cudaFree(x.d_exp[kind][par]);
+      x.d_exp[kind][par] = nullptr;
+      if (ne == 0) continue;
+      std::vector<unsigned long long*> tab(ne);
+      for (int64_t e = 0; e < ne; ++e) {
+        const auto& b = x.bound[dom][e];
+        if (b.first < 0) return fail(h, WFLOWB200_ERR_STATE, "exchange: an export is not bound to a peer");
+        const ExchangePeer& pr = x.peers[b.first];
+        tab[e] = pr.base + (size_t)par * pr.lay.words + pr.lay.kind_off[kind] +
+                 (size_t)b.second * x.S[kind] * kNv[kind];
+      }
+      CUDA_TRY(h, cudaMalloc((void**)&x.d_exp[kind][par], ne * sizeof(unsigned long long*)));
+      CUDA_TRY(h, cudaMemcpy(x.d_exp[kind][par], tab.data(), ne * sizeof(unsigned long long*),
+                             cudaMemcpyHostToDevice));
+    }
+  }
+  x.tables_current = true;
+  return WFLOWB200_OK;
+}
+
+// Start of a model step of a shard that takes part in an exchange: every shard has finished the
+// previous step (barrier), then the import slots of the NEXT step are emptied -- the producers
+// write them after the next barrier at the earliest, this step's were emptied a step ago.
+static int32_t exchange_begin_step(WflowB200* h) {
+  Exchange& x = h->xchg;
+  if (!x.prepared) {
+    if (x.active()) return fail(h, WFLOWB200_ERR_STATE, "a shard with cut edges needs wflowb200_exchange_prepare");
+    return WFLOWB200_OK;
+  }
+  if (!h->comm) return fail(h, WFLOWB200_ERR_STATE, "exchange: the shards need a communicator (comm_init_nccl / group_join)");
+  if (!x.tables_current) {
+    const int32_t rc = build_export_tables(h);
+    if (rc) return rc;
+  }
+  if (h->comm->allreduce(x.d_token, 1, 0, h->stream))
+    return fail(h, WFLOWB200_ERR_CUDA, "exchange: barrier failed");
+  if (x.imp) {
+    const int next = (int)((x.step + 1) & 1);
+    CUDA_TRY(h, cudaMemsetAsync(x.imp + (size_t)next * x.lay.words, 0xff,
+                                x.lay.words * sizeof(unsigned long long), h->stream));
+  }
+  return WFLOWB200_OK;
+}
+
 int32_t wflowb200_get_vertical_timeline(WflowB200* h, double* out_ms, int32_t capacity) {
   WFB_ENTER(h);
   const int n = 4;
@@ -1714,6 +2006,7 @@ int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value) {
     t.run_engine = value != 0;
     if (h->v_graph) { cudaGraphExecDestroy(h->v_graph); h->v_graph = nullptr; }
   }
+  else if (k == "wave_grid_percent") { if (value >= 1 && value <= 100) t.grid_percent = value; }
   else if (k == "kinwave_root_each_substep") h->kc.kw_root_each_substep = value != 0;
   else return fail(h, WFLOWB200_ERR_ARG, "unknown option: " + k);
   return WFLOWB200_OK;

@@ -76,6 +76,10 @@ struct WaveLaunch {
   unsigned smem_per_warp;     // bytes of a warp's region (0: the component's own layout);
                               // set when two components share one kernel
   unsigned* err;              // device: the handle's error word (bounded waits, routing.cu)
+  // cut edges (wflowb200_exchange_*): this step's import slots of the component (S x NV per
+  // import, written by the producers' GPUs) and, per export, the consumer's slots in ITS memory
+  const unsigned long long* imports;
+  unsigned long long* const* exports;
 };
 
 // Overland and river flow in ONE kernel (launch_surface_wave): the warps of the grid are split

@@ -65,6 +65,11 @@ struct DevNet {
   const uint8_t* node_level;    // per slot: level inside its chunk (0 = the chunk's first level)
   const int32_t* inl_src;       // per inlet edge: outlet number of the producer
   const uint8_t* inl_level;     // per inlet edge: level (inside the chunk) of the receiving node
+  // cut edges of a shard that is part of a basin (wflowb200_exchange_*): an inlet edge with
+  // inl_src >= n_outlets is IMPORT inl_src - n_outlets (its slots live in WaveLaunch::imports and
+  // are written by another GPU); node_export: per slot, the export the node feeds or -1 (nullptr:
+  // the shard exports nothing)
+  const int32_t* node_export;
 };
 
 struct KCfg {

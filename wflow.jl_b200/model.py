@@ -101,6 +101,17 @@ class SbmModel:
             setattr(c, k, int(cfg.get(k, 0)))
         d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
                         rli.ctypes.data, len(rri), rri.ctypes.data if len(rri) else None)
+        keep = []   # cut edges of a shard that is part of a basin (partition.cut_basin)
+        for dom_name in ("land", "river"):
+            for what in ("import_dst", "import_pos", "export_src"):
+                a = np.ascontiguousarray(domain.get(f"{dom_name}_{what}", np.zeros(0)), dtype=np.int64)
+                keep.append(a)
+                setattr(d, f"{dom_name}_{what}", a.ctypes.data if len(a) else None)
+                if what != "import_pos":
+                    setattr(d, f"n_{dom_name}_{what.split('_')[0]}s", len(a))
+        self.n_imports = (int(d.n_land_imports), int(d.n_river_imports))
+        self.n_exports = (int(d.n_land_exports), int(d.n_river_exports))
+        self.device = device
         rc = self._L.wflowb200_create(C.byref(c), C.byref(d), C.byref(self._h))
         if rc != 0:
             msg = self._L.wflowb200_last_error(None).decode()
@@ -282,6 +293,26 @@ class SbmModel:
         """One process per GPU: every rank passes the 128 bytes rank 0 got from comm_unique_id."""
         self._check(self._L.wflowb200_comm_init_nccl(self._h, int(rank), int(world), unique_id))
         self._has_comm = True
+
+    # ---- cut edges (wflowb200_exchange_*) -------------------------------------------------
+    def exchange_prepare(self, dt: float):
+        """-> (device pointer, 64-byte CUDA IPC handle, bytes) of this shard's import buffer"""
+        ptr, nbytes = C.c_uint64(0), C.c_int64(0)
+        ipc = C.create_string_buffer(64)
+        self._check(self._L.wflowb200_exchange_prepare(self._h, float(dt), C.byref(ptr), ipc,
+                                                       C.byref(nbytes)))
+        return int(ptr.value), ipc.raw, int(nbytes.value)
+
+    def exchange_open_peer(self, peer: int, n_imports, device_ptr: int = 0, peer_device: int = 0,
+                           ipc_handle: bytes | None = None):
+        buf = C.create_string_buffer(ipc_handle, 64) if ipc_handle is not None else None
+        self._check(self._L.wflowb200_exchange_open_peer(self._h, int(peer), int(device_ptr),
+                                                         int(peer_device), buf,
+                                                         int(n_imports[0]), int(n_imports[1])))
+
+    def exchange_bind(self, domain: int, export_index: int, peer: int, peer_import_index: int):
+        self._check(self._L.wflowb200_exchange_bind(self._h, int(domain), int(export_index),
+                                                    int(peer), int(peer_import_index)))
 
     def synchronize(self):
         self._check(self._L.wflowb200_synchronize(self._h))

@@ -136,3 +136,174 @@ def shard_config(cfg: dict, shard: Shard) -> dict:
     c["nriv"] = int(len(shard.river_cells))
     c["sharded"] = True
     return c
+
+
+# ---------------------------------------------------------------------------------------------
+# Cutting ONE basin across GPUs (second half). When a basin is larger than a GPU (or
+# than its fair share of the work) it is cut at confluences, like the reference cuts its basins
+# into sub-domains for its threads (subdomains.jl:169-255): a part owns whole upstream subtrees,
+# discharge crosses the cut on CUT EDGES. On the device a cut edge is one more inlet slot of the
+# consuming chunk, written by the producing GPU straight through NVLink (wflowb200_exchange_*),
+# so the parts run as one skewed wavefront; nothing here touches the data path.
+
+def bfs_levels(down: np.ndarray):
+    """(order, dist): nodes in downstream-to-upstream order (pits first) and their distance to
+    the pit; vectorised level by level."""
+    n = len(down)
+    src = np.nonzero(down > 0)[0]
+    by_dst = src[np.argsort(down[src] - 1, kind="stable")]
+    cnt = np.bincount(down[src] - 1, minlength=n)
+    ptr = np.concatenate([[0], np.cumsum(cnt)])
+    dist = np.zeros(n, dtype=np.int64)
+    frontier = np.nonzero(down == 0)[0]
+    order = [frontier]
+    d = 0
+    while len(frontier):
+        d += 1
+        lens = cnt[frontier]
+        if lens.sum() == 0:
+            break
+        starts = np.repeat(ptr[frontier], lens)
+        offs = np.arange(lens.sum()) - np.repeat(np.cumsum(lens) - lens, lens)
+        frontier = by_dst[starts + offs]
+        dist[frontier] = d
+        order.append(frontier)
+    return np.concatenate(order), dist
+
+
+def split_by_subtrees(down: np.ndarray, parts: int, weights: np.ndarray | None = None) -> np.ndarray:
+    """Part of every cell: parts - 1 times the upstream subtree whose (still unassigned) weight is
+    closest to the fair share is carved off; part 0 keeps the trunk. Every cut edge leads from a
+    carved subtree DOWN into what was left, so the parts form a DAG with part 0 at the bottom."""
+    n = len(down)
+    w = np.ones(n) if weights is None else np.asarray(weights, dtype=float)
+    order, _ = bfs_levels(down)
+    owner = np.zeros(n, dtype=np.int64)
+    target = w.sum() / parts
+    for p in range(1, parts):
+        free = owner == 0
+        acc = np.where(free, w, 0.0)
+        for v in order[::-1]:            # upstream first (small basins: the tests and the bench)
+            if down[v] > 0 and free[v] and free[down[v] - 1]:
+                acc[down[v] - 1] += acc[v]
+        cand = np.nonzero(free & (down > 0))[0]
+        if len(cand) == 0:
+            break
+        root = cand[np.argmin(np.abs(acc[cand] - target))]
+        take = np.zeros(n, dtype=bool)
+        take[root] = True
+        for v in order:                  # downstream first: a cell follows its downstream cell
+            if down[v] > 0 and free[v] and take[down[v] - 1]:
+                take[v] = True
+        owner[take] = p
+    return owner
+
+
+def _cut_one_graph(down: np.ndarray, owner: np.ndarray, parts: int):
+    """Cut edges of one drainage graph (1-based `down`, 0 = pit). Per part: node ids (global,
+    ascending), import (dst local 1-based, pos, global source) and export (src local 1-based,
+    peer, index of the peer's import) lists."""
+    n = len(down)
+    src = np.nonzero(down > 0)[0]
+    dst = down[src] - 1
+    # position of every edge among the in-edges of its destination, ascending source id
+    o = np.lexsort((src, dst))
+    pos = np.zeros(len(src), dtype=np.int64)
+    ds = dst[o]
+    first = np.r_[True, ds[1:] != ds[:-1]]
+    run_start = np.maximum.accumulate(np.where(first, np.arange(len(o)), 0))
+    pos[o] = np.arange(len(o)) - run_start
+    cut = owner[src] != owner[dst]
+    local = np.zeros(n, dtype=np.int64)
+    nodes = []
+    for p in range(parts):
+        ids = np.nonzero(owner == p)[0]
+        local[ids] = np.arange(1, len(ids) + 1)
+        nodes.append(ids)
+    out = []
+    import_index = {}
+    for p in range(parts):
+        e = np.nonzero(cut & (owner[dst] == p))[0]
+        e = e[np.lexsort((pos[e], dst[e]))]
+        for k, ee in enumerate(e):
+            import_index[int(src[ee])] = (p, k)
+        out.append(dict(nodes=nodes[p], import_dst=local[dst[e]], import_pos=pos[e],
+                        import_src_global=src[e]))
+    for p in range(parts):
+        e = np.nonzero(cut & (owner[src] == p))[0]
+        e = e[np.argsort(src[e])]
+        out[p]["export_src"] = local[src[e]]
+        out[p]["export_src_global"] = src[e]
+        out[p]["export_to"] = [import_index[int(u)] for u in src[e]]
+    return out
+
+
+def cut_basin(domain: dict, owner: np.ndarray, parts: int) -> list[dict]:
+    """Per part: `shard` (Shard), `domain` (for SbmModel, with the cut-edge arrays) and the
+    `links` of its exports: links[domain_id][export] = (peer part, import index of the peer)."""
+    down = downstream_ids(domain)
+    n = len(down)
+    owner = np.asarray(owner, dtype=np.int64)
+    rli = np.asarray(domain["river_land_indices"], dtype=np.int64) - 1
+    riv_of_land = np.full(n, -1, dtype=np.int64)
+    riv_of_land[rli] = np.arange(len(rli))
+    dl = down[rli]                      # downstream land cell of every river node
+    rdown = np.where(dl > 0, riv_of_land[np.maximum(dl, 1) - 1] + 1, 0)
+    land = _cut_one_graph(down, owner, parts)
+    river = _cut_one_graph(rdown, owner[rli], parts)
+    ldd = np.asarray(domain["ldd"]).copy()
+    plans = []
+    for p in range(parts):
+        sh = Shard(p, land[p]["nodes"], river[p]["nodes"], np.zeros(0, dtype=np.int64),
+                   float(len(land[p]["nodes"])))
+        local_of = np.zeros(n, dtype=np.int64)
+        local_of[sh.cells] = np.arange(1, len(sh.cells) + 1)
+        l = ldd[sh.cells].copy()
+        l[land[p]["export_src"] - 1] = 5        # the upstream end of a cut edge is a pit here
+        dn = down[sh.cells].copy()
+        dn[land[p]["export_src"] - 1] = 0
+        d = dict(d1=domain["d1"], d2=domain["d2"],
+                 indices=np.ascontiguousarray(np.asarray(domain["indices"])[sh.cells]),
+                 ldd=np.ascontiguousarray(l),
+                 river_land_indices=local_of[rli[sh.river_cells]] ,
+                 down=np.where(dn > 0, local_of[np.maximum(dn, 1) - 1], 0),
+                 reservoir_river_indices=np.zeros(0, dtype=np.int64),
+                 land_import_dst=land[p]["import_dst"], land_import_pos=land[p]["import_pos"],
+                 land_export_src=land[p]["export_src"],
+                 river_import_dst=river[p]["import_dst"], river_import_pos=river[p]["import_pos"],
+                 river_export_src=river[p]["export_src"])
+        assert np.all(d["river_land_indices"] > 0)
+        for k in ("gid", "upstream_cells"):
+            if k in domain:
+                d[k] = np.asarray(domain[k])[sh.cells]
+        plans.append(dict(shard=sh, domain=d, links=[land[p]["export_to"], river[p]["export_to"]]))
+    return plans
+
+
+def connect_in_process(models: list, plans: list[dict], dt: float) -> None:
+    """Handles of ONE process (one per GPU, or several on one GPU): exchange the import buffers as
+    device pointers and bind every export."""
+    bufs = [m.exchange_prepare(dt) for m in models]
+    for p, (m, plan) in enumerate(zip(models, plans)):
+        peers = sorted({q for links in plan["links"] for (q, _) in links})
+        for q in peers:
+            m.exchange_open_peer(q, models[q].n_imports, device_ptr=bufs[q][0],
+                                 peer_device=models[q].device)
+        for dom_id, links in enumerate(plan["links"]):
+            for e, (q, k) in enumerate(links):
+                m.exchange_bind(dom_id, e, q, k)
+
+
+def connect_distributed(model, plan: dict, dt: float, dist) -> None:
+    """One process per GPU: the import buffers travel as CUDA IPC handles (torch.distributed
+    all_gather_object)."""
+    ptr, ipc, nbytes = model.exchange_prepare(dt)
+    mine = dict(ipc=ipc, n_imports=model.n_imports, bytes=nbytes)
+    every = [None] * dist.get_world_size()
+    dist.all_gather_object(every, mine)
+    peers = sorted({q for links in plan["links"] for (q, _) in links})
+    for q in peers:
+        model.exchange_open_peer(q, every[q]["n_imports"], ipc_handle=every[q]["ipc"])
+    for dom_id, links in enumerate(plan["links"]):
+        for e, (q, k) in enumerate(links):
+            model.exchange_bind(dom_id, e, q, k)
