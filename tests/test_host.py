@@ -182,3 +182,54 @@ def test_create_rejects_bad_arguments_before_touching_the_device(pkg):
         assert rc == 1 and not h.value, bad
         assert L.wflowb200_last_error(None).decode()
     assert L.wflowb200_create(None, None, None) == 1
+
+
+def test_cut_basin_plan_is_consistent(pkg):
+    """partition.cut_basin: ONE basin cut at confluences into parts that own whole upstream
+    subtrees. Every cut edge is exactly one export of the upstream part and one import of the
+    downstream part, at the position its source has among the destination's upstream sources in
+    ascending GLOBAL id (the reference's summation order, utils.jl:472-477); the parts form a DAG
+    (a spinning consumer can never be what its producer waits for);
+    the host-side artefact builder accepts every part."""
+    P = pkg.partition
+    for network, parts in (("dendritic", 4), ("scheidegger", 3)):
+        kw = dict(network="dendritic") if network == "dendritic" else {}
+        cfg, dom, fields = pkg.synthetic.make_basin(40, 60, seed=5, **kw)
+        down = P.downstream_ids(dom)
+        n = len(down)
+        owner = P.split_by_subtrees(down, parts)
+        plans = P.cut_basin(dom, owner, parts)
+        assert sorted(np.concatenate([pl["shard"].cells for pl in plans]).tolist()) == list(range(n))
+        cut = [(u, down[u] - 1) for u in range(n) if down[u] > 0 and owner[u] != owner[down[u] - 1]]
+        assert len(cut) >= parts - 1
+        seen = 0
+        part_edges = set()
+        for p, pl in enumerate(plans):
+            d, cells = pl["domain"], pl["shard"].cells
+            assert np.all(d["down"][d["land_export_src"] - 1] == 0)
+            assert np.all(d["ldd"][d["land_export_src"] - 1] == 5)
+            for e, (q, k) in enumerate(pl["links"][0]):
+                u = cells[d["land_export_src"][e] - 1]
+                dq = plans[q]["domain"]
+                v = plans[q]["shard"].cells[dq["land_import_dst"][k] - 1]
+                assert down[u] - 1 == v and owner[v] == q and q != p
+                ups = np.sort(np.nonzero(down == v + 1)[0])
+                assert dq["land_import_pos"][k] == int(np.searchsorted(ups, u))
+                part_edges.add((p, q))
+                seen += 1
+            lcfg = P.shard_config(cfg, pl["shard"])
+            art = pkg.build_network_artifacts(lcfg, d)
+            assert sorted(art["land"]["order"].tolist()) == list(range(1, lcfg["n"] + 1))
+        assert seen == len(cut)
+        # a part never waits (directly or not) for a part that waits for it
+        left, edges = set(range(parts)), set(part_edges)
+        while left:
+            sinks = [p for p in left if not any(a == p and b in left for a, b in edges)]
+            assert sinks, "cycle between the parts"
+            left -= set(sinks)
+        # river cut edges are the land cut edges between river cells
+        rli = np.asarray(dom["river_land_indices"]) - 1
+        is_riv = np.zeros(n, dtype=bool)
+        is_riv[rli] = True
+        n_riv_cut = sum(1 for u, v in cut if is_riv[u] and is_riv[v])
+        assert sum(len(pl["links"][1]) for pl in plans) == n_riv_cut
