@@ -167,11 +167,12 @@ def config_block(workload, n, nriv, world):
             "parallelism": f"{world} x disjoint sub-catchment tiles, no collective"}
 
 
-def build_tile(pkg, d1, d2, rank, seed, adaptive):
+def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0):
     """One sub-catchment tile per rank: a d1 x d2 Scheidegger forest whose cell ids are offset so
     that every tile of the global raster is a different random forest. Only the rank's own
     cells are ever generated: everything is a pure function of (seed, global cell id)."""
-    return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive)
+    return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive,
+                                    catchment_length=catchment_length)
 
 
 # --------------------------------------------------------------------------------------------
@@ -282,6 +283,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1000, help="raster side per GPU")
     ap.add_argument("--shape", default="", metavar="D1xD2", help="raster shape per GPU (overrides --size)")
+    ap.add_argument("--catchment-length", type=int, default=0,
+                    help="outlet lines every so many columns (a mosaic of catchments)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-steps", type=int, default=2, help="oracle steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -303,7 +306,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cfg, dom, fields = build_tile(pkg, d1, d2, 0, args.seed, args.adaptive)
+        cfg, dom, fields = build_tile(pkg, d1, d2, 0, args.seed, args.adaptive, args.catchment_length)
         ora, cores = make_cpu_model(cfg, dom, fields)
         t_first = cpu_step(pkg, ora, cfg, dom["gid"], args.seed, 0)   # first warm-up step, timed
         # the requested W / K when they fit ~2 minutes of CPU work, else a bounded sample
@@ -338,7 +341,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    cfg, dom, fields = build_tile(pkg, d1, d2, rank, args.seed, args.adaptive)
+    cfg, dom, fields = build_tile(pkg, d1, d2, rank, args.seed, args.adaptive, args.catchment_length)
     for kv in args.cfg:
         k, v = kv.split("=")
         cfg[k] = int(v)
@@ -439,32 +442,44 @@ def main():
     model.close()
     del model
 
-    # ---- BASELINE configs[2]: ONE 10000 x 10000 raster (10^8 cells), sharded by sub-catchment ----
+    # ---- BASELINE configs[2]: ONE 10000 x 10000 multi-catchment raster (10^8 cells), sharded by
+    # sub-catchment. The raster is a mosaic of 64 catchments of 1250 x 1250 cells (about the size
+    # of configs[1]'s basin), 8 per GPU: a rank owns the strip of 1250 x 10000 cells that holds
+    # its 8 catchments and generates it alone from (seed, global cell id). `config3_deep` is the
+    # same raster WITHOUT the outlet lines -- every strip one forest whose drainage paths run the
+    # whole 10000 cells: the latency-bound extreme (10000 dependent wavefront levels).
     if world == 8 and not args.no_config3 and not args.adaptive:
-        # The global raster is 8 strips of 1250 x 10000 cells; drainage never leaves a strip (like
-        # at the raster edge), so a strip is a set of whole sub-catchments = one shard, and every
-        # rank generates its strip alone from (seed, global cell id).
         g1, g2 = 10000 // world, 10000
         steps3 = max(20, min(args.steps, 30))
-        cfg3, dom3, fields3 = build_tile(pkg, g1, g2, rank, args.seed + 1, False)
-        model3 = pkg.SbmModel(cfg3, dom3, fields3, device=local)
-        del fields3
-        m3 = measure(pkg, torch, dist, model3, cfg3, dom3, args.seed + 1, steps3, 5, world, local,
-                     e2e=False)
-        tot3 = torch.tensor([float(cfg3["n"])], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tot3, op=dist.ReduceOp.SUM)
-        st3 = m3["stats"]
-        k3 = max(st3["timed_steps"], 1)
-        line["config3"] = {
-            "workload": "ONE synthetic 10000x10000 raster (1e8 cells) of sub-catchments, sharded "
-                        "by sub-catchment over 8 GPUs (strips of 1250x10000 whose drainage stays "
-                        "inside the strip), fixed internal steps, no data-path collective",
-            "cells": float(tot3.item()), "steps": steps3, "warmup": 5,
-            "ms_per_step": m3["ms"] / steps3,
-            "value": float(tot3.item()) * steps3 / (m3["ms"] * 1e-3), "unit": UNIT,
-            "stage_ms_per_step": {kk[3:]: st3[kk] / k3 for kk in st3 if kk.startswith("ms_")},
-            "wave_levels_land": st3["wave_levels_land"]}
-        model3.close()
+        for key, clen, what in (
+                ("config3", 1250, "ONE synthetic 10000x10000 multi-catchment raster (1e8 cells): a "
+                 "mosaic of 64 catchments of 1250x1250 cells, sharded by sub-catchment over 8 GPUs "
+                 "(8 catchments = one strip of 1250x10000 cells per GPU)"),
+                ("config3_deep", 0, "the same raster without the outlet lines: every strip of "
+                 "1250x10000 cells is a forest whose drainage paths are 10000 cells long (10000 "
+                 "dependent wavefront levels, 1250 cells per level: the latency-bound extreme)")):
+            cfg3, dom3, fields3 = build_tile(pkg, g1, g2, rank, args.seed + 1, False, clen)
+            model3 = pkg.SbmModel(cfg3, dom3, fields3, device=local)
+            del fields3
+            m3 = measure(pkg, torch, dist, model3, cfg3, dom3, args.seed + 1, steps3, 5, world,
+                         local, e2e=False)
+            tot3 = torch.tensor([float(cfg3["n"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tot3, op=dist.ReduceOp.SUM)
+            st3 = m3["stats"]
+            k3 = max(st3["timed_steps"], 1)
+            line[key] = {
+                "workload": what + ", fixed internal steps, no data-path collective",
+                "cells": float(tot3.item()), "steps": steps3, "warmup": 5,
+                "ms_per_step": m3["ms"] / steps3,
+                "value": float(tot3.item()) * steps3 / (m3["ms"] * 1e-3), "unit": UNIT,
+                "stage_ms_per_step": {kk[3:]: st3[kk] / k3 for kk in st3 if kk.startswith("ms_")},
+                "wave_levels_land": st3["wave_levels_land"],
+                # the vertical update at this tile size (rank 0's 12.5e6 cells)
+                "roofline_v1_frac": (v1_bytes_per_cell(cfg3["n_layers"], cfg3) * cfg3["n"] /
+                                     (st3["ms_land_hydrology"] / k3 * 1e-3) / 1e9 / peak
+                                     if st3["ms_land_hydrology"] > 0 else None)}
+            model3.close()
+            del model3, cfg3, dom3
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -114,6 +114,8 @@ def test_device_math_selftest(pkg):
 @pytest.mark.parametrize("options,cfg_over", [
     ({"fuse_surface": 0}, {}),
     ({}, {"wave_piece_depth_land": 6}),
+    ({}, {"wave_piece_depth_land": 2}),
+    ({"fuse_surface": 0}, {"wave_piece_depth_land": 3}),
     ({"fuse_soil_storage": 0}, {"unsat_inline_iters": 2}),
     ({"overlap_subsurface": 0}, {"wave_piece_depth_land": -1}),
     ({"overlap_subsurface": 1, "overlap_subsurface_sms": 40}, {}),

@@ -113,11 +113,20 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
   // Shallow multi-piece chunks cut the warp-stages of a sweep (24 sub-steps: -31 % at depth 4,
   // one sub-step: -72 %) but add chunk-to-chunk hand-offs to the dependent chain of the sweep.
   // Measured on B200: a loss on a latency-bound domain (1000^2: 1000 nodes per level, +16 % step
-  // time at depth 6), a gain on a throughput-bound one (3536^2: -8 %), so the depth follows the
-  // mean level width.
+  // time at depth 6), a gain on a throughput-bound one, the more the wider its levels are (a
+  // chunk of depth d keeps its lanes busy S / (S + d - 1) of its stages: 1/d for the one sub-step
+  // of the subsurface flow). Step times by depth: 2500 nodes per level 6: 11.6 ms, 4: 12.2;
+  // 3536: 6: 21.3, 5: 20.4, 4: 20.4, 3: 21.3; 5000: 4: 14.9, 3: 15.1; 10000 (1250 levels):
+  // 6: 20.3, 5: 19.2, 4: 18.1, 3: 17.3, 2: 16.8, 1: 23.6. So the depth follows the mean level width.
   int64_t depth_land = WFB_PIECE_DEPTH_LAND;
-  if (land.n_wave_levels > 0 && land.n / land.n_wave_levels >= WFB_PIECE_WIDE_LEVEL)
-    depth_land = WFB_PIECE_DEPTH_LAND_WIDE;
+  if (land.n_wave_levels > 0) {
+    const int64_t width = land.n / land.n_wave_levels;
+    if (width >= 8500) depth_land = 2;
+    else if (width >= 6000) depth_land = 3;
+    else if (width >= 4500) depth_land = 4;
+    else if (width >= 3000) depth_land = 5;
+    else if (width >= WFB_PIECE_WIDE_LEVEL) depth_land = WFB_PIECE_DEPTH_LAND_WIDE;
+  }
   if (cfg->wave_piece_depth_land > 0) depth_land = cfg->wave_piece_depth_land;
   else if (cfg->wave_piece_depth_land < 0) depth_land = 0;
   build_chunks(land, WFB_CHUNK_NODES, depth_land);

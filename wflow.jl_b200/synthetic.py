@@ -43,9 +43,12 @@ def jl_pow(x, y):
         return np.exp(y * np.log(x))
 
 
-def scheidegger_ldd(d1: int, d2: int, seed: int, mask: np.ndarray | None = None):
+def scheidegger_ldd(d1: int, d2: int, seed: int, mask: np.ndarray | None = None,
+                    catchment_length: int = 0):
     """Random D8 forest: cell (i, j) drains to (i + delta, j + 1), delta in {-1, 0, +1};
-    the last row and cells draining out of the active domain are pits (LDD 5).
+    the last row and cells draining out of the active domain are pits (LDD 5). With
+    catchment_length > 0 every column that is a multiple of it is an outlet line as well: the
+    raster is a mosaic of catchments that are catchment_length cells long.
     Returns (indices (n,2) 1-based column-major, ldd uint8 (n,), down (n,) 1-based, 0 = pit,
     gid (n,) global cell id)."""
     if mask is None:
@@ -62,6 +65,8 @@ def scheidegger_ldd(d1: int, d2: int, seed: int, mask: np.ndarray | None = None)
     pos = np.searchsorted(lin, tlin)
     posc = np.minimum(pos, len(lin) - 1)
     ok = (j < d2) & (pos < len(lin)) & (lin[posc] == tlin)
+    if catchment_length > 0:
+        ok &= (j % catchment_length) != 0
     ldd = np.where(ok, 8 + delta, 5).astype(np.uint8)  # (-1,+1) = 7, (0,+1) = 8, (+1,+1) = 9
     down = np.where(ok, posc + 1, 0).astype(np.int64)
     indices = np.stack([i, j], axis=1).astype(np.int64)
@@ -200,7 +205,7 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                soil_infiltration_reduction: bool = False, id_offset: int = 0,
                external_inflow: bool = False, network: str = "scheidegger",
                n_active: int | None = None, n_river: int | None = None, reservoirs: int = 0,
-               snow_transport: bool = False, river_routing: int = 0):
+               snow_transport: bool = False, river_routing: int = 0, catchment_length: int = 0):
     """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
     the reference's field names; layered arrays are cell-major (n, N). network: "scheidegger"
     (a forest of many small basins, codes 5/7/8/9) or "dendritic" (one outlet, all eight
@@ -208,7 +213,7 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     if network == "dendritic":
         indices, ldd, down, lin = dendritic_ldd(d1, d2, seed, n_active)
     else:
-        indices, ldd, down, lin = scheidegger_ldd(d1, d2, seed, mask)
+        indices, ldd, down, lin = scheidegger_ldd(d1, d2, seed, mask, catchment_length)
     gid = lin + np.int64(id_offset)
     n = len(ldd)
     N = len(soil_layer_thickness_mm) + 1
