@@ -305,6 +305,11 @@ int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value);
  * times [ms since the start of the last vertical update] of its kernels: [0] = 0,
  * [1] land_hydrology_kernel, [2] unsat_engine_kernel, [3] soil_column_kernel. capacity >= 4. */
 int32_t wflowb200_get_vertical_timeline(WflowB200* h, double* out_ms, int32_t capacity);
+/* Diagnostic: cells the last vertical update handed to the loop engine, by the trip count of the
+ * loop they were suspended at: out[b], b < 6, for (8 * 2^b, 16 * 2^b] trips (the last bucket
+ * open-ended); out[6 + b]: the LATER loops the engine ran for those cells, [64 * 2^b, 128 * 2^b)
+ * trips. capacity >= 12. */
+int32_t wflowb200_get_unsat_buckets(WflowB200* h, int64_t* out, int32_t capacity);
 /* "kinwave_root_each_substep" = 1 additionally evaluates u_prev = pow(q_prev, 0.2) before EVERY
  * kinematic-wave solve like surface_process.jl:33 (default: the fifth root is carried from the
  * previous solve of the node, within half an ulp of it; one pow per node and model step). */

@@ -16,6 +16,9 @@ build() { # name, flags
 for v in "$@"; do
   case $v in
     slowtrips) build slowtrips -DWFB_ENGINE_FAST_TRIPS=0 ;;
+    e5) build e5 -DWFB_ENGINE_MINBLOCKS=5 ;;
+    e6) build e6 -DWFB_ENGINE_MINBLOCKS=6 ;;
+    e8) build e8 -DWFB_ENGINE_MINBLOCKS=8 ;;
     a4) build a4 -DWFB_V_MINBLOCKS=4 ;;
     a6) build a6 -DWFB_V_MINBLOCKS=6 ;;
     c3) build c3 -DWFB_VC_MINBLOCKS=3 ;;

@@ -18,4 +18,5 @@ for rep in range(3):
     m.update_model(dt)
     m.synchronize()
     print("land_hydrology, unsat_engine, soil_column done at [us]:", [round(1000 * x) for x in m.vertical_timeline()[1:]])
+print("suspended cells by trip count (8,16], (16,32], ... :", m.unsat_buckets())
 m.close()

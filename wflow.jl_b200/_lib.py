@@ -130,6 +130,7 @@ def lib():
     L.wflowb200_group_destroy.restype = None
     L.wflowb200_set_option.argtypes = [vp, C.c_char_p, i32]
     L.wflowb200_get_vertical_timeline.argtypes = [vp, C.POINTER(C.c_double), i32]
+    L.wflowb200_get_unsat_buckets.argtypes = [vp, C.POINTER(C.c_int64), i32]
     L.wflowb200_newton_trace.argtypes = [vp, i32]
     L.wflowb200_get_newton_trace.argtypes = [vp, i32, vp]
     L.wflowb200_selftest_math.argtypes = [i32, i64, C.POINTER(C.c_double)]

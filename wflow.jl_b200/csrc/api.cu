@@ -1044,7 +1044,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_pool, 5 * ns * sizeof(double)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_its, ns * sizeof(int32_t)));
     TRY_CREATE(cudaMalloc((void**)&h->d_unsat_list, (size_t)WFB_UNSAT_BUCKETS * ns * sizeof(int32_t)));
-    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count, WFB_UNSAT_BUCKETS * sizeof(unsigned)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_unsat_count, (2 * WFB_UNSAT_BUCKETS + 1) * sizeof(unsigned)));
     UnsatWork& u = h->unsat;
     u.usd = h->d_unsat_pool; u.sum_ast = u.usd + ns; u.kv_it = u.sum_ast + ns;
     u.l_sat = u.kv_it + ns; u.c = u.l_sat + ns;
@@ -1055,7 +1055,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 8;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-    h->engine_grid = std::max(1, sms) * 8;
+    h->engine_grid = std::max(1, sms);
   }
   TRY_CREATE(cudaMalloc((void**)&h->d_err, sizeof(unsigned)));
   TRY_CREATE(cudaMemset(h->d_err, 0, sizeof(unsigned)));
@@ -1976,6 +1976,16 @@ static int32_t exchange_begin_step(WflowB200* h) {
     CUDA_TRY(h, cudaMemsetAsync(x.imp + (size_t)next * x.lay.words, 0xff,
                                 x.lay.words * sizeof(unsigned long long), h->stream));
   }
+  return WFLOWB200_OK;
+}
+
+int32_t wflowb200_get_unsat_buckets(WflowB200* h, int64_t* out, int32_t capacity) {
+  WFB_ENTER(h);
+  if (!out || capacity < 2 * WFB_UNSAT_BUCKETS) return WFLOWB200_ERR_ARG;
+  unsigned cnt[2 * WFB_UNSAT_BUCKETS];
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(cnt, h->d_unsat_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < 2 * WFB_UNSAT_BUCKETS; ++b) out[b] = cnt[b];
   return WFLOWB200_OK;
 }
 

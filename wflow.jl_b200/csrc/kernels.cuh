@@ -36,7 +36,7 @@ struct VerticalStage {
   StageList second;            // soil_column_kernel
 };
 void build_vertical_stage(const DevFields& f, const KCfg& c, int n_layers, VerticalStage& vs);
-// engine_grid: CTAs of the engine kernel (a few per SM). phase: 0 the whole update; 1 interception
+// engine_grid: SMs of the device (the engine launches as many CTAs as are resident at once). phase: 0 the whole update; 1 interception
 // + snow only, 2 the rest (lateral snow transport runs between the two: launch_snow_transport).
 // run_engine = false leaves the suspended cells unfinished (timing experiments only). tl: optional
 // timing events of the kernels' completion (wflowb200_get_vertical_timeline).

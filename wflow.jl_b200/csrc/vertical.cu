@@ -980,63 +980,74 @@ soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const Sta
 // (~4000 on the benchmark basin, ~55 cycles each): sending the later long loops of a cell to a
 // further launch, regrouped by trip count, was built and measured -- no gain, the lanes' idling
 // is not what bounds it.
+#ifndef WFB_ENGINE_MINBLOCKS
+#define WFB_ENGINE_MINBLOCKS 4
+#endif
 template <int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, WFB_ENGINE_MINBLOCKS)
 unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const double dt) {
   const unsigned* cnt = w.count;
   const int32_t* list = w.list;
+  unsigned* const queue = w.count + 2 * kBuckets;  // next warp tile to hand out
   const int lane = (int)threadIdx.x & 31;
-  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
-  // consecutive tiles (the longest loops) go to different SMs
-  const int gw = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
   const int ns = c.ns;
   const Divisor ddt(dt);
-  for (int j = gw;; j += n_warps) {
+  // warp tiles are handed out from a queue, longest buckets first: a warp that finishes a short
+  // tile takes the next one, so every resident warp stays busy until the lists are empty (with a
+  // fixed assignment a CTA lived as long as its longest tile while its other warps idled)
+  for (;;) {
+    int j = 0;
+    if (lane == 0) j = (int)atomicAdd(queue, 1u);
+    j = __shfl_sync(0xffffffffu, j, 0);
     int b, first, n;
     if (!tile_of(cnt, j, b, first, n)) break;
     const int e = first + lane;
-    if (e >= n) continue;
-    const int i = list[(size_t)b * (size_t)w.cap + e];
-    UnsatTask t;
-    t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
-    t.c = w.c[i];
-    const int code = w.its_layer[i];
-    t.its = code & 0xffffff;
-    const int kl = code >> 24;  // the layer the cell was suspended at
+    if (e < n) {   // (no `continue`: the warp meets again at the queue)
+      const int i = list[(size_t)b * (size_t)w.cap + e];
+      UnsatTask t;
+      t.usd = w.usd[i]; t.sum_ast = w.sum_ast[i]; t.kv_it = w.kv_it[i]; t.l_sat = w.l_sat[i];
+      t.c = w.c[i];
+      const int code = w.its_layer[i];
+      t.its = code & 0xffffff;
+      const int kl = code >> 24;  // the layer the cell was suspended at
 #if WFB_ENGINE_FAST_TRIPS
-    unsatzone_flow_iterate_fast(t, dt, ddt);
+      unsatzone_flow_iterate_fast(t, dt, ddt);
 #else
-    unsatzone_flow_iterate(t, dt, ddt);
+      unsatzone_flow_iterate(t, dt, ddt);
 #endif
-    f.unsaturated_layer_depth[kl * ns + i] = t.usd;
-    double flow = t.sum_ast;
-    const int n_unsat = f.n_unsatlayers[i];
-    if (kl + 1 < n_unsat) {  // the layers below (soil.jl:770-801)
-      const KvCol<N> kv = load_kvcol<N>(f, c, i);
-      const double theta_e = __ldg(f.theta_s + i) - __ldg(f.theta_r + i);
-      double z = 0.0;
-      for (int k = 0; k <= kl; ++k) {  // same left-to-right sum as the first pass
-        const double ultk = f.unsaturated_layer_thickness[k * ns + i];
-        z = (k == 0) ? ultk : z + ultk;
-      }
-      for (int k = kl + 1; k < n_unsat; ++k) {
-        const double ultk = f.unsaturated_layer_thickness[k * ns + i];
-        z = z + ultk;
-        const double l_sat = ultk * theta_e;
-        const double kv_z = kv_at_depth<N>(c.kv_profile, kv, pick<N>(kv.k, k), z);
-        const double usd = f.unsaturated_layer_depth[k * ns + i] + flow * dt;
-        UnsatTask tk = unsatzone_flow_setup(usd, kv_z, l_sat,
-                                            __ldg(f.brooks_corey_exponent + k * ns + i), dt, ddt);
+      f.unsaturated_layer_depth[kl * ns + i] = t.usd;
+      double flow = t.sum_ast;
+      const int n_unsat = f.n_unsatlayers[i];
+      if (kl + 1 < n_unsat) {  // the layers below (soil.jl:770-801)
+        const KvCol<N> kv = load_kvcol<N>(f, c, i);
+        const double theta_e = __ldg(f.theta_s + i) - __ldg(f.theta_r + i);
+        double z = 0.0;
+        for (int k = 0; k <= kl; ++k) {  // same left-to-right sum as the first pass
+          const double ultk = f.unsaturated_layer_thickness[k * ns + i];
+          z = (k == 0) ? ultk : z + ultk;
+        }
+        for (int k = kl + 1; k < n_unsat; ++k) {
+          const double ultk = f.unsaturated_layer_thickness[k * ns + i];
+          z = z + ultk;
+          const double l_sat = ultk * theta_e;
+          const double kv_z = kv_at_depth<N>(c.kv_profile, kv, pick<N>(kv.k, k), z);
+          const double usd = f.unsaturated_layer_depth[k * ns + i] + flow * dt;
+          UnsatTask tk = unsatzone_flow_setup(usd, kv_z, l_sat,
+                                              __ldg(f.brooks_corey_exponent + k * ns + i), dt, ddt);
+          // diagnostic (wflowb200_get_unsat_buckets): later loops of the cell by trip count
+          if (tk.its > 64) atomicAdd(w.count + kBuckets + min(31 - __clz(tk.its) - 6, kBuckets - 1), 1u);
 #if WFB_ENGINE_FAST_TRIPS
-        unsatzone_flow_iterate_fast(tk, dt, ddt);
+          unsatzone_flow_iterate_fast(tk, dt, ddt);
 #else
-        unsatzone_flow_iterate(tk, dt, ddt);
+          unsatzone_flow_iterate(tk, dt, ddt);
 #endif
-        f.unsaturated_layer_depth[k * ns + i] = tk.usd;
-        flow = tk.sum_ast;
+          f.unsaturated_layer_depth[k * ns + i] = tk.usd;
+          flow = tk.sum_ast;
+        }
       }
+      f.transfer[i] = flow;  // n_unsat > 0 for a suspended cell
     }
-    f.transfer[i] = flow;  // n_unsat > 0 for a suspended cell
+    __syncwarp();
   }
 }
 
@@ -1322,11 +1333,19 @@ int launch_land_hydrology(const DevFields& f, const KCfg& c, int n_layers, doubl
     WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, smem1, s>>>(f, c, w, s1, dt, 0, 1)));
     return launches + 1;
   }
-  cudaMemsetAsync(w.count, 0, kBuckets * sizeof(unsigned), s);
+  cudaMemsetAsync(w.count, 0, (2 * kBuckets + 1) * sizeof(unsigned), s);
   WFB_DISPATCH_N(n_layers, (land_hydrology_kernel<N><<<n_tiles, kTile, smem1, s>>>(f, c, w, s1, dt, 0, phase)));
   if (tl) cudaEventRecord(tl[1], s);
-  if (run_engine)
-    WFB_DISPATCH_N(n_layers, (unsat_engine_kernel<N><<<engine_grid, 128, 0, s>>>(f, c, w, dt)));
+  if (run_engine) {  // as many CTAs as are resident at once: the engine hands out its work itself
+    static int per_sm[9] = {0};
+    if (per_sm[n_layers] == 0) {
+      int nb = 0;
+      WFB_DISPATCH_N(n_layers, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, unsat_engine_kernel<N>, 128, 0));
+      per_sm[n_layers] = nb > 0 ? nb : 1;
+    }
+    const int grid = engine_grid * per_sm[n_layers];   // engine_grid = SMs of the device
+    WFB_DISPATCH_N(n_layers, (unsat_engine_kernel<N><<<grid, 128, 0, s>>>(f, c, w, dt)));
+  }
   if (tl) cudaEventRecord(tl[2], s);
   WFB_DISPATCH_N(n_layers, (soil_column_kernel<N><<<n_tiles, kTile, smem2, s>>>(f, c, w, vs.second, dt, 0)));
   if (tl) cudaEventRecord(tl[3], s);
