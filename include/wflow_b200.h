@@ -71,7 +71,7 @@ typedef struct {
   /* B200 tuning, fixed at create; 0 = automatic (chosen from the shape of the domain) */
   int32_t wave_piece_depth_land; /* levels per piece of the land chunks; -1: one connected piece */
   int32_t vertical_slices;       /* unused (kept for ABI stability)                             */
-  int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (8)    */
+  int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (2)    */
   int32_t snow_gravitational_transport; /* snow_gravitational_transport__flag: lateral snow
                                   transport between snow and glacier model     sbm.jl:98-100 */
   /* river_routing = "local_inertial" (config_structure.jl; surface_staggered_scheme.jl): the
@@ -306,9 +306,9 @@ int32_t wflowb200_set_option(WflowB200* h, const char* name, int32_t value);
  * [1] land_hydrology_kernel, [2] unsat_engine_kernel, [3] soil_column_kernel. capacity >= 4. */
 int32_t wflowb200_get_vertical_timeline(WflowB200* h, double* out_ms, int32_t capacity);
 /* Diagnostic: cells the last vertical update handed to the loop engine, by the trip count of the
- * loop they were suspended at: out[b], b < 6, for (8 * 2^b, 16 * 2^b] trips (the last bucket
- * open-ended); out[6 + b]: the LATER loops the engine ran for those cells, [64 * 2^b, 128 * 2^b)
- * trips. capacity >= 12. */
+ * loop they were suspended at: out[b], b < 8, for (2 * 2^b, 4 * 2^b] trips (the first bucket
+ * from 2, the last open-ended); out[8 + b]: the LATER loops of more than 4 trips the engine ran
+ * for those cells, same classes. capacity >= 16. */
 int32_t wflowb200_get_unsat_buckets(WflowB200* h, int64_t* out, int32_t capacity);
 /* "kinwave_root_each_substep" = 1 additionally evaluates u_prev = pow(q_prev, 0.2) before EVERY
  * kinematic-wave solve like surface_process.jl:33 (default: the fifth root is carried from the

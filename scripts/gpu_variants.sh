@@ -1,4 +1,4 @@
-python scripts/vertical_timeline.py 2>&1 | tail -3 | head -2
-for v in e5 e6 e8; do
-echo $v; WFB_LIB=wflow.jl_b200/csrc/_obj/variants/lib_$v.so python scripts/vertical_timeline.py 2>&1 | tail -3 | head -2
+for it in 1 2; do
+echo inline $it; python scripts/vertical_timeline.py --cfg unsat_inline_iters=$it 2>&1 | tail -3
 done
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3

@@ -1052,7 +1052,10 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     u.list = h->d_unsat_list;
     u.count = h->d_unsat_count;
     u.cap = (int32_t)ns;
-    u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 8;
+    // in-line trip limit; measured on B200 (1000^2, V1 in us): 2: 365-376, 3: 374, 4: 374-381,
+    // 6: 385, 8: 386-390 (the first half's in-line loops beyond the first trip run with ~4 of 32
+    // lanes; the engine regroups them)
+    u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 2;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     h->engine_grid = std::max(1, sms);

@@ -11,7 +11,7 @@ int launch_scatter_river_depth(const DevFields& f, const KCfg& c, cudaStream_t s
 // Device scratch of the unsaturated-zone engine (vertical.cu): the operands of the suspended
 // Brooks-Corey loops (one record per cell) and the lists of suspended cells, bucketed by
 // log2(trip count).
-#define WFB_UNSAT_BUCKETS 6
+#define WFB_UNSAT_BUCKETS 8
 #define WFB_V_TILE 128                        // cells per tile (= CTA of land_hydrology_kernel)
 struct UnsatWork {
   double *usd, *sum_ast, *kv_it, *l_sat, *c;  // ns doubles each

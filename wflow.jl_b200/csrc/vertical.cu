@@ -186,8 +186,8 @@ __device__ __forceinline__ void unsatzone_flow_iterate_fast(UnsatTask& t, double
 
 // ---- the unsaturated-zone engine: suspended loops ------------------------------------------
 constexpr int kBuckets = WFB_UNSAT_BUCKETS;
-__device__ __forceinline__ int bucket_of(int its) {  // (8,16] -> 0 ... by log2, clamped
-  const int b = 28 - __clz(its - 1);                 // its in (2^(b+3), 2^(b+4)]
+__device__ __forceinline__ int bucket_of(int its) {  // <= 4 -> 0, (4,8] -> 1 ... by log2, clamped
+  const int b = 30 - __clz(its - 1);                 // its in (2^(b+1), 2^(b+2)]
   return b < 0 ? 0 : (b >= kBuckets ? kBuckets - 1 : b);
 }
 // record the loop of cell i (layer k) and append the cell to the list of its bucket
@@ -1035,7 +1035,7 @@ unsat_engine_kernel(const DevFields f, const KCfg c, const UnsatWork w, const do
           UnsatTask tk = unsatzone_flow_setup(usd, kv_z, l_sat,
                                               __ldg(f.brooks_corey_exponent + k * ns + i), dt, ddt);
           // diagnostic (wflowb200_get_unsat_buckets): later loops of the cell by trip count
-          if (tk.its > 64) atomicAdd(w.count + kBuckets + min(31 - __clz(tk.its) - 6, kBuckets - 1), 1u);
+          if (tk.its > 4) atomicAdd(w.count + kBuckets + bucket_of(tk.its), 1u);
 #if WFB_ENGINE_FAST_TRIPS
           unsatzone_flow_iterate_fast(tk, dt, ddt);
 #else

@@ -328,9 +328,9 @@ class SbmModel:
 
     def unsat_buckets(self):
         """cells handed to the loop engine in the last step, by log2 of the suspended loop's trips"""
-        buf = (C.c_int64 * 12)()
-        self._check(self._L.wflowb200_get_unsat_buckets(self._h, buf, 12))
-        return list(buf)[:6], list(buf)[6:]
+        buf = (C.c_int64 * 16)()
+        self._check(self._L.wflowb200_get_unsat_buckets(self._h, buf, 16))
+        return list(buf)[:8], list(buf)[8:]
 
     def newton_trace(self, enable: bool):
         self._check(self._L.wflowb200_newton_trace(self._h, int(enable)))
