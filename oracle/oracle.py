@@ -45,7 +45,8 @@ class _Cfg(C.Structure):
                 ("li_ghost_nodes", C.c_int32), ("li_alpha", C.c_double), ("li_h_thresh", C.c_double),
                 ("nthreads", C.c_int32),
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
-                ("ssf_alpha_coefficient", C.c_double)]
+                ("ssf_alpha_coefficient", C.c_double), ("fp_levels", C.c_int32),
+                ("fp_depth", C.c_double * 16)]
 
 
 def lib(variant: str = ""):
@@ -77,7 +78,8 @@ def lib(variant: str = ""):
         L.wfo_li_stable_timestep.argtypes = [C.c_void_p]
         L.wfo_li_stable_timestep.restype = C.c_double
         for f in ("wfo_li_update_river_channel_flow", "wfo_li_update_bc_reservoir_model",
-                  "wfo_li_update_water_depth_and_storage"):
+                  "wfo_li_update_water_depth_and_storage", "wfo_li_update_floodplain_flow",
+                  "wfo_li_update_floodplain_water_depth_and_storage"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_double]
             getattr(L, f).restype = None
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -150,6 +152,8 @@ INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_ind
               "reservoir_river_indices")
 # reservoir defaults (reservoir.jl:200-272): cumulative / average variables start at zero
 ZERO_DEFAULTS = ZERO_DEFAULTS + (
+    "fp_h", "fp_storage", "fp_q", "fp_q_cumulative", "fp_q_average", "fp_error",
+    "fp_water_depth_at_edge", "riv_q_channel_average",
     "res_inflow_cumulative", "res_inflow_average", "res_external_inflow",
     "res_actual_external_abstraction_cumulative", "res_actual_external_abstraction_average",
     "res_outflow_cumulative", "res_outflow_average", "res_actevap_cumulative")
@@ -198,9 +202,14 @@ class OracleModel:
         c.dt_river = float(cfg.get("dt_river", 900.0))
         c.dt_ssf = float(cfg.get("dt_ssf", 86400.0))
         c.ssf_alpha_coefficient = float(cfg.get("ssf_alpha_coefficient", 1.0))
+        fp_depth = [float(x) for x in cfg.get("fp_depth", [])]
+        c.fp_levels = len(fp_depth)
+        for k, x in enumerate(fp_depth):
+            c.fp_depth[k] = x
+        P = max(len(fp_depth), 1)
         self.cfg = dict(cfg)
         self.f = {}
-        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,), 4: (nres,)}
+        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,), 4: (nres,), 5: (nriv, P)}
         for name, kind in field_table():
             if name in fields and fields[name] is not None:
                 a = np.ascontiguousarray(np.array(fields[name], dtype=np.float64, copy=True))

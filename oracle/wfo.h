@@ -105,6 +105,15 @@
   X(li_zb, 3) X(li_zb_at_edge, 3) X(li_mannings_n_sq_at_edge, 3) X(li_flow_length_at_edge, 3) \
   X(li_flow_width_at_edge, 3) X(li_ghost_h, 3) X(li_error, 3) X(li_zs_at_edge, 3) \
   X(li_water_depth_at_edge, 3) \
+  /* 1-D floodplain of the local-inertial river (floodplain_1d__flag; floodplain.jl:150-215, \
+   * surface_staggered_scheme.jl:440-533,674-712): variables by node / by the edge leaving the \
+   * node; fp_profile_*: FloodPlainProfile tables (floodplain.jl:5-22), one row of fp_levels \
+   * values per node (Julia: profile.x[level, node]) */ \
+  X(fp_h, 3) X(fp_storage, 3) X(fp_q, 3) X(fp_q_cumulative, 3) X(fp_q_average, 3) X(fp_error, 3) \
+  X(fp_water_depth_at_edge, 3) X(fp_mannings_n_sq_at_edge, 3) X(fp_zb_at_edge, 3) \
+  X(li_bankfull_storage, 3) X(li_bankfull_depth, 3) X(riv_q_channel_average, 3) \
+  X(fp_profile_storage, 5) X(fp_profile_width, 5) X(fp_profile_flow_area, 5) \
+  X(fp_profile_wetted_perimeter, 5) \
   /* reservoirs (routing/surface/reservoir.jl:5-44 parameters, 200-217 variables, 251-272 BC); \
    * res_outflow_curve_type holds ReservoirOutflowType as a number (2 free_weir, 3 \
    * modified_puls, 4 simple) */ \
@@ -153,6 +162,8 @@ typedef struct {
   double li_alpha, li_h_thresh; /* river_local_inertial_flow__alpha_coefficient, river_water_flow_threshold__depth */
   int32_t nthreads;           /* OpenMP threads (0 = default)                         */
   double dt_land, dt_river, dt_ssf, ssf_alpha_coefficient;
+  int32_t fp_levels;          /* floodplain_1d__flag: flood depths of the profile, 0 = none */
+  double fp_depth[16];        /* profile.depth                                          */
 } wfo_config;
 
 typedef struct wfo_model {
@@ -210,6 +221,8 @@ double wfo_li_stable_timestep(wfo_model*);
 void wfo_li_update_river_channel_flow(wfo_model*, double dt_s);
 void wfo_li_update_bc_reservoir_model(wfo_model*, double dt_s);
 void wfo_li_update_water_depth_and_storage(wfo_model*, double dt_s);
+void wfo_li_update_floodplain_flow(wfo_model*, double dt_s);
+void wfo_li_update_floodplain_water_depth_and_storage(wfo_model*, double dt_s);
 void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182 */
 void wfo_update_model(wfo_model*, double dt);                  /* sbm_model.jl:60-92 */
 void wfo_update_diagnostic_vars(wfo_model*);                   /* soil.jl:1400-1436 */

@@ -869,6 +869,105 @@ void wfo_li_update_river_channel_flow(wfo_model* m, double dt) {
   }
 }
 
+/* ---- 1-D floodplain of the local-inertial river --------------------------------------------
+ * profile tables are [node][level] (Julia: profile.x[level, node])                           */
+#define FP(m, tab, i, l) ((m)->tab[(i) * (m)->cfg.fp_levels + (l)])
+/* interpolation_indices                                                floodplain.jl:287-300 */
+static void fp_interpolation_indices(const double* v, int64_t n, double x, int64_t* i1, int64_t* i2) {
+  int64_t a = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (v[i] <= x) a = i;
+  *i1 = a;
+  *i2 = a == n - 1 ? a : a + 1;
+}
+/* compute_floodplain_flow_area (compute_flood_flow_area minus the channel)   :306-318,343-354 */
+static double fp_floodplain_flow_area(const wfo_model* m, double h, int64_t idx, int64_t i1, int64_t i2) {
+  const double channel_area = FP(m, fp_profile_width, idx, 0) * h;
+  const double delta_h = h - m->cfg.fp_depth[i1];
+  const double flow_area = FP(m, fp_profile_flow_area, idx, i1) + (FP(m, fp_profile_width, idx, i2) * delta_h);
+  return jl_max(flow_area - channel_area, 0.0);
+}
+/* compute_wetted_perimeter                                                          :324-328 */
+static double fp_wetted_perimeter(const wfo_model* m, double h, int64_t idx, int64_t i1) {
+  const double delta_h = h - m->cfg.fp_depth[i1];
+  return FP(m, fp_profile_wetted_perimeter, idx, i1) + 2.0 * delta_h;
+}
+/* compute_flood_depth                                                               :331-341 */
+static double fp_flood_depth(const wfo_model* m, double flood_storage, double flow_length, int64_t i) {
+  int64_t i1, i2;
+  fp_interpolation_indices(&FP(m, fp_profile_storage, i, 0), m->cfg.fp_levels, flood_storage, &i1, &i2);
+  const double delta_A = (flood_storage - FP(m, fp_profile_storage, i, i1)) / flow_length;
+  const double delta_h = delta_A / FP(m, fp_profile_width, i, i2);
+  return m->cfg.fp_depth[i1] + delta_h;
+}
+
+/* update_floodplain_flow!(::LocalInertial)              surface_staggered_scheme.jl:440-533.
+ * floodplain q_previous .= q happens at the top of update_river_channel_flow! (:336-339), so
+ * fp_q still holds the previous sub-step's value here; zs_src / zs_dst / zs_at_edge are the
+ * values that sweep stored for the edge (the depths have not changed since). A ghost node
+ * copies the profile of its pit (floodplain.jl:176 index_pit) and holds no floodplain water. */
+void wfo_li_update_floodplain_flow(wfo_model* m, double dt) {
+  PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) {
+    const int64_t d = li_dst(m, i);
+    if (d == -1) continue;
+    if (m->cfg.nres > 0 && m->riv_reservoir[i] >= 0) continue;
+    const double q_previous = m->fp_q[i];
+    const double zs_src = m->li_zb[i] + m->riv_h[i];
+    const double h_dst = d == -2 ? m->li_ghost_h[i] : m->riv_h[d];
+    const double zs_dst = (d == -2 ? m->li_zb[i] : m->li_zb[d]) + h_dst;
+    const int64_t i_dst = d == -2 ? i : d;   /* profile of the ghost node = the pit's */
+    const double hf = jl_max(m->li_zs_at_edge[i] - m->fp_zb_at_edge[i], 0.0);
+    m->fp_water_depth_at_edge[i] = hf;
+    int64_t i1, i2;
+    fp_interpolation_indices(m->cfg.fp_depth, m->cfg.fp_levels, hf, &i1, &i2);
+    const double a_src = fp_floodplain_flow_area(m, hf, i, i1, i2);
+    const double a_dst = fp_floodplain_flow_area(m, hf, i_dst, i1, i2);
+    const double A = jl_min(a_src, a_dst);
+    const double R = a_src < a_dst ? a_src / fp_wetted_perimeter(m, hf, i, i1)
+                                   : a_dst / fp_wetted_perimeter(m, hf, i_dst, i1);
+    double q = A > 1.0e-05
+                   ? local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R,
+                                         m->li_flow_length_at_edge[i],
+                                         m->fp_mannings_n_sq_at_edge[i], m->cfg.li_froude_limit, dt)
+                   : 0.0;
+    if (m->fp_h[i] <= 0.0) q = jl_min(q, 0.0);
+    if ((d == -2 ? 0.0 : m->fp_h[d]) <= 0.0) q = jl_max(q, 0.0);
+    if (q * m->riv_q[i] < 0.0) q = 0.0;       /* opposite to the channel flow */
+    m->fp_q[i] = q;
+    m->fp_q_cumulative[i] += q * dt;
+  }
+}
+
+/* update_water_depth_and_storage!(floodplain_model, river_flow_model, ...)         :674-712 */
+void wfo_li_update_floodplain_water_depth_and_storage(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->river;
+  PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) {
+    if (m->cfg.nres > 0 && m->riv_reservoir[i] >= 0) continue;
+    double q_src = 0.0;
+    for (int64_t u = nw->in_ptr[i]; u < nw->in_ptr[i + 1]; ++u) q_src += m->fp_q[nw->in_idx[u]];
+    const double q_dst = li_dst(m, i) == -1 ? 0.0 : 0.0 + m->fp_q[i];
+    m->fp_storage[i] += (q_src - q_dst) * dt;
+    if (m->fp_storage[i] < 0.0) {
+      m->fp_error[i] += fabs(m->fp_storage[i]);
+      m->fp_storage[i] = 0.0;
+    }
+    const double storage_total = m->riv_storage[i] + m->fp_storage[i];
+    if (storage_total > m->li_bankfull_storage[i]) {
+      const double flood_storage = storage_total - m->li_bankfull_storage[i];
+      const double h = fp_flood_depth(m, flood_storage, m->riv_flow_length[i], i);
+      m->riv_h[i] = m->li_bankfull_depth[i] + h;
+      m->riv_storage[i] = m->riv_h[i] * m->riv_flow_width[i] * m->riv_flow_length[i];
+      m->fp_storage[i] = jl_max(storage_total - m->riv_storage[i], 0.0);
+      m->fp_h[i] = m->fp_storage[i] > 0.0 ? h : 0.0;
+    } else {
+      m->riv_h[i] = storage_total / (m->riv_flow_length[i] * m->riv_flow_width[i]);
+      m->riv_storage[i] = storage_total;
+      m->fp_h[i] = 0.0;
+      m->fp_storage[i] = 0.0;
+    }
+  }
+}
+
 /* update_bc_reservoir_model!                                                :627-661 */
 void wfo_li_update_bc_reservoir_model(wfo_model* m, double dt) {
   const wfo_network* nw = &m->river;
@@ -876,6 +975,11 @@ void wfo_li_update_bc_reservoir_model(wfo_model* m, double dt) {
     const int64_t i = m->reservoir_river_indices[v];
     double q_in = 0.0;  /* sum_at(q, edges_at_node.src[i]): edges entering the reservoir node */
     for (int64_t u = nw->in_ptr[i]; u < nw->in_ptr[i + 1]; ++u) q_in += m->riv_q[nw->in_idx[u]];
+    if (m->cfg.fp_levels > 0) {              /* get_inflow_reservoir :291-299 */
+      double q_fp = 0.0;
+      for (int64_t u = nw->in_ptr[i]; u < nw->in_ptr[i + 1]; ++u) q_fp += m->fp_q[nw->in_idx[u]];
+      q_in += q_fp;
+    }
     double inflow;
     if (m->res_external_inflow[v] < 0.0) {
       const double abstraction = jl_min(-m->res_external_inflow[v], (m->res_storage[v] / dt) * 0.98);
@@ -929,6 +1033,7 @@ static void li_update_river_flow_model(wfo_model* m, double dt) {
   PFOR for (int64_t i = 0; i < n; ++i) {
     m->riv_q_cumulative[i] = 0.0;
     m->riv_actual_external_abstraction_cumulative[i] = 0.0;
+    if (m->cfg.fp_levels > 0) m->fp_q_cumulative[i] = 0.0;
   }
   double t = 0.0;
   m->substeps_river = 0;
@@ -936,8 +1041,10 @@ static void li_update_river_flow_model(wfo_model* m, double dt) {
     double dt_s = wfo_li_stable_timestep(m);
     dt_s = check_timestepsize(dt_s, t, dt);
     wfo_li_update_river_channel_flow(m, dt_s);
+    if (m->cfg.fp_levels > 0) wfo_li_update_floodplain_flow(m, dt_s);
     wfo_li_update_bc_reservoir_model(m, dt_s);
     wfo_li_update_water_depth_and_storage(m, dt_s);
+    if (m->cfg.fp_levels > 0) wfo_li_update_floodplain_water_depth_and_storage(m, dt_s);
     t += dt_s;
     m->substeps_river++;
   }
@@ -951,6 +1058,13 @@ static void li_update_river_flow_model(wfo_model* m, double dt) {
     m->res_inflow_average[i] = m->res_inflow_cumulative[i] / dt;
     m->res_actual_external_abstraction_average[i] =
         m->res_actual_external_abstraction_cumulative[i] / dt;
+  }
+  if (m->cfg.fp_levels > 0) {  /* :826-835 */
+    PFOR for (int64_t i = 0; i < n; ++i) {
+      m->fp_q_average[i] = m->fp_q_cumulative[i] / dt;
+      m->riv_q_channel_average[i] = m->riv_q_average[i];
+      m->riv_q_average[i] = m->riv_q_channel_average[i] + m->fp_q_average[i];
+    }
   }
 }
 

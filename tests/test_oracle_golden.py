@@ -522,6 +522,94 @@ def test_local_inertial_river_with_reservoir_routing_process_385_528():
     assert m.f["riv_h"] == approx(np.array([0.03653704705843743, 0.0, 0.10966599406601261]))
 
 
+def test_local_inertial_river_with_floodplain_routing_process_530_690():
+    """3-node graph 1 -> 2 -> 3 with a 1-D floodplain (6-level profile): stable time step, channel
+    flow, floodplain flow (profile interpolation, opposite-direction rule), river and floodplain
+    water depth and storage (bankfull redistribution) -- each sub-step as the reference checks it."""
+    L = orc.lib()
+
+    class G:
+        down = np.array([2, 3, 0])
+    river = dict(graph=G, order=np.array([1, 2, 3]), up_ptr=np.array([0, 0, 1, 2]),
+                 up_idx=np.array([1, 2]), order_of_subdomains=[np.array([1])],
+                 order_subdomain=[np.array([1, 2, 3])], subdomain_indices=[np.array([1, 2, 3])])
+
+    class G1:
+        down = np.array([0, 0, 0])
+    land = dict(graph=G1, order=np.array([1, 2, 3]), up_ptr=np.zeros(4, np.int64),
+                up_idx=np.zeros(0, np.int64), order_of_subdomains=[np.array([1])],
+                order_subdomain=[np.array([1, 2, 3])], subdomain_indices=[np.array([1, 2, 3])])
+    w = 149.17837524414062
+    zb = 165.10784077644348
+    # FloodPlainProfile tables as in the reference test: rows = levels, columns = nodes
+    storage = np.array([[0.0, 0.0, 0.0], [77602.0, 281141.0, 111313.0],
+                        [189506.0, 609512.0, 256357.0], [346960.0, 981178.0, 420515.0],
+                        [526346.0, 1.39783e6, 602100.0], [747343.0, 1.87239e6, 814606.0]])
+    width = np.array([[w, w, w],
+                      [341.5768913342503, 666.778728923476, 758.7636596016615],
+                      [492.562310866575, 778.7935519733185, 988.6905953775695],
+                      [693.0574965612104, 881.4757828423199, 1118.9809351368624],
+                      [789.5944979367263, 988.1614230127849, 1237.7718606880392],
+                      [972.7515818431912, 1125.5153603853994, 1448.5444669293854]])
+    flow_area = np.array([[0.0, 0.0, 0.0],
+                          [170.78844566712516, 333.389364461738, 379.38182980083076],
+                          [417.0696011004127, 722.7861404483972, 873.7271274896154],
+                          [763.5983493810179, 1163.5240318695571, 1433.2175950580468],
+                          [1158.395598349381, 1657.6047433759495, 2052.103525402066],
+                          [1644.7713892709767, 2220.3624235686493, 2776.375758866759]])
+    perimeter = np.array([[192.3985160901097, 517.6003536793354, 609.5852843575209],
+                          [193.3985160901097, 518.6003536793354, 610.5852843575209],
+                          [345.38393562243436, 631.6151767291778, 841.5122201334289],
+                          [546.8791213170698, 735.2974075981792, 972.8025598927218],
+                          [644.4161226925856, 842.9830477686443, 1092.5934854438985],
+                          [828.5732065990505, 981.3369851412588, 1304.3660916852448]])
+    f = dict(riv_inwater=[0.001214603164946035, 0.0069799723162954465, 0.00022016439899281862],
+             riv_external_inflow=np.zeros(3), riv_abstraction=np.zeros(3),
+             li_zb=[zb, zb, zb], li_zb_at_edge=[zb, zb, 0.0],
+             li_mannings_n_sq_at_edge=[0.0008999999597668652, 0.0008999999597668652, 0.0],
+             li_flow_length_at_edge=[648.828125, 568.34375, 1.0],
+             li_flow_width_at_edge=[w, w, w], li_ghost_h=np.zeros(3),
+             li_bankfull_storage=[107921.00118967971, 200292.17449130033, 69688.46493603183],
+             li_bankfull_depth=[1.592156171798706] * 3,
+             riv_flow_width=[w, w, w], riv_flow_length=[454.375, 843.28125, 293.40625],
+             riv_h=[1.8817912224982847, 1.8197068314233162, 1.7619620034455687],
+             riv_storage=[127553.31189184493, 228917.89427333255, 77120.8437153619],
+             riv_q=[137.1750567107639, 133.74797838974442, 0.0],
+             fp_q=[3.306660222819796, 6.14041420989245, 0.0],
+             fp_h=[0.2896350506995787, 0.22755065962461016, 0.16980583164686275],
+             fp_storage=[25320.207706612186, 99321.92021301284, 30370.81429688439],
+             fp_mannings_n_sq_at_edge=[0.005184, 0.005184, 0.0],
+             fp_zb_at_edge=[166.6999969482422, 166.6999969482422, 0.0],
+             fp_profile_storage=storage.T, fp_profile_width=width.T,
+             fp_profile_flow_area=flow_area.T, fp_profile_wetted_perimeter=perimeter.T,
+             river_land_indices=np.array([0, 1, 2]))
+    f = {k: np.ascontiguousarray(v, dtype=np.int64 if k.endswith("indices") else np.float64)
+         for k, v in f.items()}
+    m = orc.OracleModel(dict(n=3, nriv=3, nres=0, N=1, river_routing=1, li_froude_limit=1,
+                             li_ghost_nodes=0, li_alpha=0.7, li_h_thresh=0.001,
+                             fp_depth=[0.0, 0.5, 1.0, 1.5, 2.0, 2.5]), f, land, river)
+    dt = L.wfo_li_stable_timestep(m.h)
+    L.wfo_li_update_river_channel_flow(m.h, dt)
+    assert dt == approx(49.40931052556788)
+    assert m.f["li_zs_at_edge"][:2] == approx(np.array([166.98963199894177, 166.92754760786679]))
+    assert m.f["li_water_depth_at_edge"][:2] == approx(np.array([1.8817912224982933, 1.8197068314233036]))
+    assert m.f["riv_q"][:2] == approx(np.array([137.1827776559179, 133.7538757670657]))
+    assert m.f["riv_q_cumulative"][:2] == approx(np.array([6778.106459961183, 6608.686781773178]))
+    L.wfo_li_update_floodplain_flow(m.h, dt)
+    assert m.f["fp_water_depth_at_edge"][:2] == approx(np.array([0.2896350506995873, 0.22755065962459753]))
+    assert m.f["fp_q"][:2] == approx(np.array([3.3074672215578524, 6.1421232455587536]))
+    assert m.f["fp_q_cumulative"][:2] == approx(np.array([163.41967500308917, 303.4780747261213]))
+    L.wfo_li_update_bc_reservoir_model(m.h, dt)
+    L.wfo_li_update_water_depth_and_storage(m.h, dt)
+    assert m.f["riv_storage"] == approx(np.array([120775.26544458869, 229087.6588271402, 83729.54137530623]))
+    assert m.f["riv_h"] == approx(np.array([1.7817948514048583, 1.8210563184054411, 1.9129493838748897]))
+    L.wfo_li_update_floodplain_water_depth_and_storage(m.h, dt)
+    assert m.f["riv_storage"] == approx(np.array([124521.73491986065, 228924.54042985922, 78479.82701991481]))
+    assert m.f["riv_h"] == approx(np.array([1.8370664336896243, 1.8197596628390198, 1.793010379352563]))
+    assert m.f["fp_storage"] == approx(np.array([21410.318556337137, 99344.98021057082, 35924.006727001935]))
+    assert m.f["fp_h"] == approx(np.array([0.2449102618909183, 0.22760349104031377, 0.20085420755385677]))
+
+
 def test_accucapacityflux_routing_process_255_288():
     """PCRaster accucapacity examples on a 6-node graph (lateral snow transport's engine)."""
     L = orc.lib()
