@@ -2,7 +2,8 @@
  * wflow_b200_fields.h -- the Float64 arrays of the Julia model structs that live on the device.
  *
  * X(name, kind): kind 0 = land scalar (n), 1 = land layered (n x N), 2 = land layered+1
- * (n x (N+1)), 3 = river scalar (nriv), 4 = reservoir scalar (nres). Names are the reference's struct field names; a
+ * (n x (N+1)), 3 = river scalar (nriv), 4 = reservoir scalar (nres), 5 = river x floodplain profile
+ * level (nriv x fp_levels, a node's levels contiguous like Julia's profile.x[level, node]). Names are the reference's struct field names; a
  * component prefix is added where two structs share a name (snow_/glacier_/ssf_/olf_/riv_/
  * recharge_/runoff_/soil_).
  *
@@ -19,6 +20,9 @@
  *   157-186 (li_*: local-inertial river flow; edge i is the edge leaving node i, so the edge
  *   arrays are river-sized and riv_q holds the edge discharge; li_ghost_h: water depth of the
  *   ghost node downstream of a pit, riverdepth_bc);
+ *   FloodPlainProfile / FloodPlainStaggeredParameters / Variables routing/surface/floodplain.jl:
+ *   5-22,150-163,216-236 (fp_*: 1-D floodplain of the local-inertial river; li_bankfull_*:
+ *   RiverFlowStaggeredParameters.bankfull_storage / bankfull_depth);
  *   ReservoirParameters routing/surface/reservoir.jl:5-44, ReservoirVariables :200-217,
  *   ReservoirBC :251-272 (res_outflow_curve_type holds ReservoirOutflowType as a number:
  *   2 free_weir, 3 modified_puls, 4 simple).
@@ -89,6 +93,11 @@
   X(li_zb, 3) X(li_zb_at_edge, 3) X(li_mannings_n_sq_at_edge, 3) X(li_flow_length_at_edge, 3) \
   X(li_flow_width_at_edge, 3) X(li_ghost_h, 3) X(li_error, 3) X(li_zs_at_edge, 3) \
   X(li_water_depth_at_edge, 3) \
+  X(fp_h, 3) X(fp_storage, 3) X(fp_q, 3) X(fp_q_cumulative, 3) X(fp_q_average, 3) X(fp_error, 3) \
+  X(fp_water_depth_at_edge, 3) X(fp_mannings_n_sq_at_edge, 3) X(fp_zb_at_edge, 3) \
+  X(li_bankfull_storage, 3) X(li_bankfull_depth, 3) X(riv_q_channel_average, 3) \
+  X(fp_profile_storage, 5) X(fp_profile_width, 5) X(fp_profile_flow_area, 5) \
+  X(fp_profile_wetted_perimeter, 5) \
   X(res_area, 4) X(res_outflow_curve_type, 4) X(res_maximum_storage, 4) X(res_threshold, 4) \
   X(res_rating_curve_coefficient, 4) X(res_rating_curve_exponent, 4) X(res_maximum_release, 4) \
   X(res_demand, 4) X(res_target_minimum_fraction, 4) X(res_target_full_fraction, 4) \

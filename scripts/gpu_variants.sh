@@ -1,4 +1,1 @@
-for it in 1 2; do
-echo inline $it; python scripts/vertical_timeline.py --cfg unsat_inline_iters=$it 2>&1 | tail -3
-done
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k "local_inertial" 2>&1 | tail -15

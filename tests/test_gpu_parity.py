@@ -247,6 +247,26 @@ def test_local_inertial_river_flow(pkg, reservoirs):
     _close(gpu)
 
 
+@pytest.mark.parametrize("reservoirs", [0, 3])
+def test_local_inertial_river_with_floodplain(pkg, reservoirs):
+    """floodplain_1d__flag with the local-inertial river (BASELINE config #4): floodplain flow at
+    the edges over the six-level FloodPlainProfile tables, the opposite-direction rule, bankfull
+    redistribution between channel and floodplain, reservoir inflow including the floodplain's
+    (surface_staggered_scheme.jl:291-299,440-533,674-712,826-835; floodplain.jl:287-354) -- in the
+    same two phases of the persistent kernel. Tolerances as for the river alone (chaotic scheme)."""
+    gpu, ora, cfg = parity.run_pair(pkg, 70, 110, steps=4, seed=43, river_routing=1,
+                                    floodplain=True, reservoirs=reservoirs)
+    assert len(cfg["fp_depth"]) == 6
+    rep = parity.compare_models(gpu, ora, outliers=(1.0, 1e-5))
+    st, o = gpu.stats(), ora.newton_stats()
+    assert abs(st["substeps_river"] - o["substeps_river"]) <= 1 and o["substeps_river"] > 20
+    wet = int((ora.f["fp_h"] > 0.0).sum())
+    assert wet > 10 and float(np.max(np.abs(ora.f["fp_q_average"]))) > 0.0
+    assert np.array_equal(gpu.get("fp_h") > 0.0, ora.f["fp_h"] > 0.0)
+    print(rep.summary(), "river sub-steps", st["substeps_river"], "nodes over bank", wet)
+    _close(gpu)
+
+
 def test_five_soil_layers(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 32, 48, steps=2, seed=2,
                                     soil_layer_thickness_mm=(50, 50, 300, 800))

@@ -26,7 +26,8 @@ class Config(C.Structure):
                 ("unsat_inline_iters", C.c_int32), ("snow_gravitational_transport", C.c_int32),
                 ("river_routing", C.c_int32), ("li_froude_limit", C.c_int32),
                 ("li_ghost_nodes", C.c_int32), ("reserved_", C.c_int32),
-                ("li_alpha", C.c_double), ("li_h_thresh", C.c_double)]
+                ("li_alpha", C.c_double), ("li_h_thresh", C.c_double),
+                ("fp_levels", C.c_int32), ("reserved2_", C.c_int32), ("fp_depth", C.c_double * 16)]
 
 
 class Domain(C.Structure):

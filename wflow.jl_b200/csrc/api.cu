@@ -389,10 +389,16 @@ int32_t check_device_error(WflowB200* h) {
   return WFLOWB200_OK;
 }
 
-int layers_of(const WflowB200* h, int kind) { return kind == 1 ? h->N : kind == 2 ? h->N + 1 : 1; }
-// slots / elements / slot map of a field kind (0-2 land, 3 river, 4 reservoir)
-int slots_of(const WflowB200* h, int kind) { return kind == 3 ? h->nrs : kind == 4 ? h->nress : h->ns; }
-int count_of(const WflowB200* h, int kind) { return kind == 3 ? h->nriv : kind == 4 ? h->nres : h->n; }
+int layers_of(const WflowB200* h, int kind) {
+  return kind == 1 ? h->N : kind == 2 ? h->N + 1 : kind == 5 ? std::max(h->cfg.fp_levels, 1) : 1;
+}
+// slots / elements / slot map of a field kind (0-2 land, 3 river, 4 reservoir, 5 river x level)
+int slots_of(const WflowB200* h, int kind) {
+  return (kind == 3 || kind == 5) ? h->nrs : kind == 4 ? h->nress : h->ns;
+}
+int count_of(const WflowB200* h, int kind) {
+  return (kind == 3 || kind == 5) ? h->nriv : kind == 4 ? h->nres : h->n;
+}
 
 template <class T>
 cudaError_t upload_i32(const std::vector<T>& src, int32_t** dst, int64_t offset) {
@@ -846,6 +852,11 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
 
   WflowB200* h = new WflowB200();
   h->cfg = *cfg;
+  if (cfg->fp_levels < 0 || cfg->fp_levels > 16 || (cfg->fp_levels > 0 && cfg->river_routing != 1)) {
+    g_create_error = "fp_levels: 0 .. 16, and the 1-D floodplain needs river_routing = local_inertial";
+    delete h;
+    return WFLOWB200_ERR_ARG;
+  }
   h->n = (int)cfg->n; h->nriv = (int)cfg->nriv; h->N = cfg->n_layers;
   h->ns = (h->n + 31) / 32 * 32;
   h->nrs = (h->nriv + 31) / 32 * 32;
@@ -905,6 +916,9 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   fill(h->f.li_error, 3, 0.0);                  // surface_staggered_scheme.jl:181-185
   fill(h->f.li_zs_at_edge, 3, 0.0);
   fill(h->f.li_water_depth_at_edge, 3, 0.0);
+  for (double* p : {h->f.fp_h, h->f.fp_storage, h->f.fp_q, h->f.fp_q_cumulative, h->f.fp_q_average,
+                    h->f.fp_error, h->f.fp_water_depth_at_edge, h->f.riv_q_channel_average})
+    fill(p, 3, 0.0);                            // floodplain.jl:216-236
   fill(h->f.waterdepth_river, 0, 0.0);          // runoff.jl:26
   fill(h->f.unsaturated_store_depth, 0, 0.0);   // soil.jl:71
   fill(h->f.total_storage, 0, 0.0);             // soil.jl:77
@@ -1034,7 +1048,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     }
   }
   h->stage_doubles = std::max<size_t>(std::max<size_t>((size_t)h->n * (h->N + 1), (size_t)3 * h->n),
-                                      (size_t)std::max(h->nriv, h->nres));
+                                      (size_t)std::max(h->nriv * std::max(cfg->fp_levels, 1), h->nres));
   TRY_CREATE(cudaMalloc((void**)&h->d_stage, h->stage_doubles * sizeof(double)));
   TRY_CREATE(cudaMalloc((void**)&h->d_forcing, (size_t)3 * h->n * sizeof(double)));
   TRY_CREATE(cudaMallocHost((void**)&h->h_pinned, (size_t)3 * h->n * sizeof(double)));
@@ -1194,7 +1208,7 @@ int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t
   if (count == 0) return WFLOWB200_OK;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, src, extent * sizeof(double), cudaMemcpyHostToDevice,
                               h->stream));
-  const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+  const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
   h->launches += launch_gather_field(h->field_ptr[id], h->d_stage, slot_map, count,
                                      slots_of(h, kind), layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1210,7 +1224,7 @@ int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, i
   if (count == 0) return WFLOWB200_OK;
   rc = wait_forcing(h);
   if (rc) return rc;
-  const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+  const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
   h->launches += launch_scatter_field(h->d_stage, h->field_ptr[id], slot_map, count,
                                       slots_of(h, kind), layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_stage, extent * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1375,7 +1389,7 @@ int32_t wflowb200_get_fields(WflowB200* h, const int32_t* ids, int32_t n_ids, do
     const int kind = kFieldKinds[ids[k]];
     const int layers = layers_of(h, kind), count = count_of(h, kind);
     if (count == 0) continue;
-    const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+    const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
     h->launches += launch_scatter_field(h->d_stage + off, h->field_ptr[ids[k]], slot_map, count,
                                         slots_of(h, kind), layers, layers, 1, h->stream);
     off += (size_t)count * layers;
@@ -1429,7 +1443,7 @@ int32_t wflowb200_get_fields_async(WflowB200* h, const int32_t* ids, int32_t n_i
     const int kind = kFieldKinds[ids[k]];
     const int layers = layers_of(h, kind), count = count_of(h, kind);
     if (count == 0) continue;
-    const int32_t* slot_map = kind == 4 ? h->res_ident : (kind == 3 ? h->river : h->land).node_of_slot;
+    const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
     h->launches += launch_scatter_field(h->d_out[b] + off, h->field_ptr[ids[k]], slot_map, count,
                                         slots_of(h, kind), layers, layers, 1, h->stream);
     off += (size_t)count * layers;
@@ -1543,6 +1557,8 @@ int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
     w.alpha = h->cfg.li_alpha > 0.0 ? h->cfg.li_alpha : 0.7;
     w.h_thresh = h->cfg.li_h_thresh;
     w.froude_limit = h->cfg.li_froude_limit;
+    w.fp_levels = h->cfg.fp_levels;
+    for (int l = 0; l < 16; ++l) w.fp_depth[l] = h->cfg.fp_depth[l];
     w.barrier = h->d_li_barrier;
     w.dt_bits = h->d_li_dt;
     w.err = h->d_err;

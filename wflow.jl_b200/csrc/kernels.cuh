@@ -126,6 +126,8 @@ struct LiLaunch {
   double dt;                    // model time step
   double alpha, h_thresh;       // stability coefficient, depth threshold for flow at an edge
   int froude_limit;
+  int fp_levels;                // 1-D floodplain: levels of the profile (0: none) and their depths
+  double fp_depth[16];
   unsigned* barrier;            // device: {arrivals, generation}
   unsigned long long* dt_bits;  // device: 2 slots for the minimum Courant step (bit patterns)
   unsigned* err;                // device: the handle's error word (bounded barrier waits)

@@ -7,6 +7,12 @@
 //   update_bc_reservoir_model!          :627-661     reservoirs (their node leaves the active
 //                                                     set, the edge carries the outflow)
 //   update_water_depth_and_storage!     :723-759     node storage and depth
+// and, with floodplain_1d__flag, the 1-D floodplain
+//   update_floodplain_flow!             :440-533     edge flow over the FloodPlainProfile tables
+//                                                     (floodplain.jl:287-354)
+//   update_water_depth_and_storage!(floodplain, ...) :674-712  bankfull redistribution
+// in the same two phases (an edge's floodplain flow needs only that edge's channel flow and
+// the depths of the previous sub-step), so the floodplain adds no grid barrier.
 // All reference paths are under /root/reference/Wflow/src.
 //
 // The scheme is explicit: every sub-step is edge-parallel, then node-parallel, and needs ONE
@@ -83,6 +89,44 @@ __device__ __forceinline__ double local_inertial_flow(double q0, double zs0, dou
   return q;
 }
 
+
+// ---- FloodPlainProfile (floodplain.jl:287-354); tables are [level][river slot] ---------------
+struct FpTables {
+  const double *storage, *width, *flow_area, *perimeter;
+  int nrs, levels;
+  const double* depth;  // kernel parameter space
+};
+// interpolation_indices: the last level with v[l] <= x (and the next one)
+__device__ __forceinline__ void fp_indices_depth(const FpTables& t, double x, int& i1, int& i2) {
+  int a = 0;
+  for (int l = 0; l < t.levels; ++l)
+    if (t.depth[l] <= x) a = l;
+  i1 = a;
+  i2 = a == t.levels - 1 ? a : a + 1;
+}
+// compute_floodplain_flow_area (flood flow area minus the channel's share)
+__device__ __forceinline__ double fp_flow_area(const FpTables& t, double h, int p, int i1, int i2) {
+  const double channel_area = __ldg(t.width + p) * h;
+  const double delta_h = h - t.depth[i1];
+  const double flow_area = __ldg(t.flow_area + i1 * t.nrs + p) + (__ldg(t.width + i2 * t.nrs + p) * delta_h);
+  return jmax(flow_area - channel_area, 0.0);
+}
+__device__ __forceinline__ double fp_wetted_perimeter(const FpTables& t, double h, int p, int i1) {
+  const double delta_h = h - t.depth[i1];
+  return __ldg(t.perimeter + i1 * t.nrs + p) + 2.0 * delta_h;
+}
+// compute_flood_depth
+__device__ __forceinline__ double fp_flood_depth(const FpTables& t, double flood_storage,
+                                                 double flow_length, int p) {
+  int a = 0;
+  for (int l = 0; l < t.levels; ++l)
+    if (__ldg(t.storage + l * t.nrs + p) <= flood_storage) a = l;
+  const int i2 = a == t.levels - 1 ? a : a + 1;
+  const double delta_A = (flood_storage - __ldg(t.storage + a * t.nrs + p)) / flow_length;
+  const double delta_h = delta_A / __ldg(t.width + i2 * t.nrs + p);
+  return t.depth[a] + delta_h;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kLiBlock, 2)
@@ -95,11 +139,15 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
   __shared__ unsigned long long s_min;
   const double dt = w.dt;
   const unsigned long long inf_bits = 0x7ff0000000000000ull;
+  const bool floodplain = w.fp_levels > 0;
+  const FpTables fp{f.fp_profile_storage, f.fp_profile_width, f.fp_profile_flow_area,
+                    f.fp_profile_wetted_perimeter, c.nrs, w.fp_levels, w.fp_depth};
 
   // set_reservoir_vars! / set_flow_vars!                          surface_kinwave.jl:227-237,269-275
   for (int p = tid; p < n; p += stride) {
     f.riv_q_cumulative[p] = 0.0;
     f.riv_actual_external_abstraction_cumulative[p] = 0.0;
+    if (floodplain) f.fp_q_cumulative[p] = 0.0;
   }
   for (int i = tid; i < c.nres; i += stride) {
     f.res_inflow_cumulative[i] = 0.0;
@@ -163,6 +211,29 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
       if (h_dst <= 0.0) q = jmax(q, 0.0);
       f.riv_q[p] = q;
       f.riv_q_cumulative[p] += q * dt_s;
+      if (floodplain) {  // update_floodplain_flow! of the same edge                 :440-533
+        const double q_fp_previous = f.fp_q[p];
+        const int pd = d == -2 ? p : d;  // a ghost node copies the profile of its pit
+        const double hfp = jmax(zs_at_edge - __ldg(f.fp_zb_at_edge + p), 0.0);
+        f.fp_water_depth_at_edge[p] = hfp;
+        int i1, i2;
+        fp_indices_depth(fp, hfp, i1, i2);
+        const double a_src = fp_flow_area(fp, hfp, p, i1, i2);
+        const double a_dst = fp_flow_area(fp, hfp, pd, i1, i2);
+        const double A_fp = jmin(a_src, a_dst);
+        const double R_fp = a_src < a_dst ? a_src / fp_wetted_perimeter(fp, hfp, p, i1)
+                                          : a_dst / fp_wetted_perimeter(fp, hfp, pd, i1);
+        double qf = A_fp > 1.0e-05
+                        ? local_inertial_flow(q_fp_previous, zs_src, zs_dst, hfp, A_fp, R_fp,
+                                              __ldg(f.li_flow_length_at_edge + p),
+                                              __ldg(f.fp_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
+                        : 0.0;
+        if (__ldcg(f.fp_h + p) <= 0.0) qf = jmin(qf, 0.0);
+        if ((d == -2 ? 0.0 : __ldcg(f.fp_h + d)) <= 0.0) qf = jmax(qf, 0.0);
+        if (qf * q < 0.0) qf = 0.0;  // opposite to the channel flow
+        f.fp_q[p] = qf;
+        f.fp_q_cumulative[p] += qf * dt_s;
+      }
     }
     alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
     if (!alive) break;
@@ -173,6 +244,11 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
         const int p = f.res_river_slot[v];
         double q_in = 0.0;  // sum_at(q, edges_at_node.src[i])
         for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_in += __ldcg(f.riv_q + f.li_in_idx[e]);
+        if (floodplain) {  // get_inflow_reservoir                                      :291-299
+          double q_fp = 0.0;
+          for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_fp += __ldcg(f.fp_q + f.li_in_idx[e]);
+          q_in += q_fp;
+        }
         const double outflow = reservoir_step(f, v, q_in, dt_s);
         f.riv_q[p] = outflow;
         f.riv_q_cumulative[p] += outflow * dt_s;
@@ -203,8 +279,38 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
         inflow = ext;
       }
       storage += inflow * dt_s;
+      const double length = __ldg(f.riv_flow_length + p), width = __ldg(f.riv_flow_width + p);
+      double h_new = storage / (length * width);
+      if (floodplain) {  // update_water_depth_and_storage!(floodplain, ...)           :674-712
+        double qf_src = 0.0;
+        for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) qf_src += __ldcg(f.fp_q + f.li_in_idx[e]);
+        const double qf_dst = f.li_dst_slot[p] == -1 ? 0.0 : 0.0 + f.fp_q[p];
+        double fs = f.fp_storage[p];
+        fs += (qf_src - qf_dst) * dt_s;
+        if (fs < 0.0) {
+          f.fp_error[p] += fabs(fs);
+          fs = 0.0;
+        }
+        const double storage_total = storage + fs;
+        const double bankfull = __ldg(f.li_bankfull_storage + p);
+        double fh;
+        if (storage_total > bankfull) {
+          const double hh = fp_flood_depth(fp, storage_total - bankfull, length, p);
+          h_new = __ldg(f.li_bankfull_depth + p) + hh;
+          storage = h_new * width * length;
+          fs = jmax(storage_total - storage, 0.0);
+          fh = fs > 0.0 ? hh : 0.0;
+        } else {
+          h_new = storage_total / (length * width);
+          storage = storage_total;
+          fh = 0.0;
+          fs = 0.0;
+        }
+        f.fp_storage[p] = fs;
+        f.fp_h[p] = fh;
+      }
       f.riv_storage[p] = storage;
-      f.riv_h[p] = storage / (__ldg(f.riv_flow_length + p) * __ldg(f.riv_flow_width + p));
+      f.riv_h[p] = h_new;
     }
     t += dt_s;
     ++count;
@@ -213,8 +319,15 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
   }
   // average_flow_vars! / average_reservoir_vars!                   surface_kinwave.jl:244-258,283-290
   for (int p = tid; p < n; p += stride) {
-    f.riv_q_average[p] = f.riv_q_cumulative[p] / dt;
+    const double q_av = f.riv_q_cumulative[p] / dt;
+    f.riv_q_average[p] = q_av;
     f.riv_actual_external_abstraction_average[p] = f.riv_actual_external_abstraction_cumulative[p] / dt;
+    if (floodplain) {  // :826-835
+      const double qf_av = f.fp_q_cumulative[p] / dt;
+      f.fp_q_average[p] = qf_av;
+      f.riv_q_channel_average[p] = q_av;
+      f.riv_q_average[p] = q_av + qf_av;
+    }
   }
   for (int i = tid; i < c.nres; i += stride) {
     f.res_outflow_average[i] = f.res_outflow_cumulative[i] / dt;

@@ -97,6 +97,11 @@ class SbmModel:
         c.li_ghost_nodes = int(cfg.get("li_ghost_nodes", 1))
         c.li_alpha = float(cfg.get("li_alpha", 0.7))
         c.li_h_thresh = float(cfg.get("li_h_thresh", 1.0e-3))
+        fp_depth = [float(x) for x in cfg.get("fp_depth", [])]
+        c.fp_levels = len(fp_depth)
+        for k, x in enumerate(fp_depth):
+            c.fp_depth[k] = x
+        self.P = max(len(fp_depth), 1)
         for k in ("wave_piece_depth_land", "vertical_slices", "unsat_inline_iters"):  # 0 = automatic
             setattr(c, k, int(cfg.get(k, 0)))
         d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
@@ -144,7 +149,7 @@ class SbmModel:
     def _shape(self, name):
         k = self._kinds[name]
         return {0: (self.n,), 1: (self.n, self.N), 2: (self.n, self.N + 1), 3: (self.nriv,),
-                4: (self.nres,)}[k]
+                4: (self.nres,), 5: (self.nriv, self.P)}[k]
 
     def set(self, name: str, a) -> None:
         if name in INT_FIELDS:

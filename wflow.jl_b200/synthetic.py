@@ -205,7 +205,8 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                soil_infiltration_reduction: bool = False, id_offset: int = 0,
                external_inflow: bool = False, network: str = "scheidegger",
                n_active: int | None = None, n_river: int | None = None, reservoirs: int = 0,
-               snow_transport: bool = False, river_routing: int = 0, catchment_length: int = 0):
+               snow_transport: bool = False, river_routing: int = 0, catchment_length: int = 0,
+               floodplain: bool = False):
     """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
     the reference's field names; layered arrays are cell-major (n, N). network: "scheidegger"
     (a forest of many small basins, codes 5/7/8/9) or "dendritic" (one outlet, all eight
@@ -440,6 +441,40 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
         F["li_mannings_n_sq_at_edge"] = n_at_edge * n_at_edge
         F["li_ghost_h"] = np.zeros(nriv)                        # riverdepth_bc
         F["li_error"] = np.zeros(nriv)
+        if floodplain:
+            # 1-D floodplain (floodplain.jl:50-147): a six-level profile per node whose first
+            # width is the channel's and whose widths grow with the depth; flow area, wetted
+            # perimeter and storage are its cumulative sums. A shallow bankfull depth so that
+            # the synthetic rivers do go over bank.
+            fp_depth = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.5])
+            P = len(fp_depth)
+            bankfull_depth = 0.02 + 0.06 * u01(seed, 95, rg)
+            grow = 1.5 + 2.0 * u01(seed, 96, rg)               # widening per level
+            width = np.empty((nriv, P))
+            width[:, 0] = W
+            for l in range(1, P):
+                width[:, l] = width[:, l - 1] * (1.0 + (grow - 1.0) / l)
+            dh = np.diff(fp_depth)
+            area = np.zeros((nriv, P))
+            perim = np.empty((nriv, P))
+            perim[:, 0] = W + 2.0 * bankfull_depth
+            perim[:, 1] = perim[:, 0] + 2.0 * dh[0]
+            for l in range(1, P):
+                area[:, l] = area[:, l - 1] + width[:, l] * dh[l - 1]
+                if l > 1:
+                    perim[:, l] = perim[:, l - 1] + (width[:, l] - width[:, l - 1]) + 2.0 * dh[l - 1]
+            F["fp_profile_width"] = width
+            F["fp_profile_flow_area"] = area
+            F["fp_profile_wetted_perimeter"] = perim
+            F["fp_profile_storage"] = area * L[:, None]
+            F["li_bankfull_depth"] = bankfull_depth
+            F["li_bankfull_storage"] = bankfull_depth * W * L
+            zb_fp = zb + bankfull_depth
+            F["fp_zb_at_edge"] = np.maximum(zb_fp, zb_fp[d])
+            n_fp = 0.072
+            F["fp_mannings_n_sq_at_edge"] = np.full(nriv, n_fp * n_fp)
+            for k in ("fp_h", "fp_storage", "fp_q", "fp_error"):
+                F[k] = np.zeros(nriv)
     # ---- reservoirs on the river (reservoir.jl; Moselle has two, test/sbm_config.toml:126) -----
     reservoir_river_indices = np.zeros(0, dtype=np.int64)
     nres = 0
@@ -489,6 +524,8 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                land_streamorder_min=5, river_streamorder_min=6, dt_land=3600.0, dt_river=900.0,
                dt_ssf=86400.0, ssf_alpha_coefficient=1.0, dt=dt,
                kin_wave_min_flow_qroot=1e-30 ** 0.2)
+    if floodplain and river_routing == 1 and nriv:
+        cfg["fp_depth"] = [0.0, 0.5, 1.0, 1.5, 2.0, 2.5]
     domain = dict(d1=d1, d2=d2, indices=indices, ldd=ldd, river_land_indices=river_land_indices,
                   down=down, gid=gid, upstream_cells=acc,
                   reservoir_river_indices=reservoir_river_indices)
