@@ -154,7 +154,12 @@ def dist_env():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
-def workload_text(d1, d2, adaptive):
+def workload_text(d1, d2, adaptive, local_inertial=False):
+    if local_inertial:
+        return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical + kinematic-wave "
+                "overland/subsurface + LOCAL-INERTIAL river with 1-D floodplain, daily step, fixed "
+                "internal steps 3600/86400 s (river: adaptive alpha L / sqrt(g h)), N=4 soil "
+                "layers, snow on")
     return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical + kinematic-wave "
             "river/overland/subsurface, daily step, "
             + ("adaptive internal steps" if adaptive else "fixed internal steps 3600/900/86400 s")
@@ -167,12 +172,13 @@ def config_block(workload, n, nriv, world):
             "parallelism": f"{world} x disjoint sub-catchment tiles, no collective"}
 
 
-def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0):
+def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0, local_inertial=False):
     """One sub-catchment tile per rank: a d1 x d2 Scheidegger forest whose cell ids are offset so
     that every tile of the global raster is a different random forest. Only the rank's own
     cells are ever generated: everything is a pure function of (seed, global cell id)."""
+    extra = dict(river_routing=1, floodplain=True) if local_inertial else {}
     return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive,
-                                    catchment_length=catchment_length)
+                                    catchment_length=catchment_length, **extra)
 
 
 # --------------------------------------------------------------------------------------------
@@ -285,6 +291,9 @@ def main():
     ap.add_argument("--shape", default="", metavar="D1xD2", help="raster shape per GPU (overrides --size)")
     ap.add_argument("--catchment-length", type=int, default=0,
                     help="outlet lines every so many columns (a mosaic of catchments)")
+    ap.add_argument("--local-inertial", action="store_true",
+                    help="BASELINE configs[3]: local-inertial river + 1-D floodplain instead of the "
+                         "kinematic-wave river")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-steps", type=int, default=2, help="oracle steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -300,13 +309,13 @@ def main():
     rank, world, local = dist_env()
     pkg = load_pkg()
     d1, d2 = (int(x) for x in args.shape.split("x")) if args.shape else (args.size, args.size)
-    workload = workload_text(d1, d2, args.adaptive)
+    workload = workload_text(d1, d2, args.adaptive, args.local_inertial)
 
     # ------------------------------------------------------------------ reference arm ----
     if args.impl == "reference":
         if rank != 0:
             return
-        cfg, dom, fields = build_tile(pkg, d1, d2, 0, args.seed, args.adaptive, args.catchment_length)
+        cfg, dom, fields = build_tile(pkg, d1, d2, 0, args.seed, args.adaptive, args.catchment_length, args.local_inertial)
         ora, cores = make_cpu_model(cfg, dom, fields)
         t_first = cpu_step(pkg, ora, cfg, dom["gid"], args.seed, 0)   # first warm-up step, timed
         # the requested W / K when they fit ~2 minutes of CPU work, else a bounded sample
@@ -341,7 +350,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    cfg, dom, fields = build_tile(pkg, d1, d2, rank, args.seed, args.adaptive, args.catchment_length)
+    cfg, dom, fields = build_tile(pkg, d1, d2, rank, args.seed, args.adaptive, args.catchment_length, args.local_inertial)
     for kv in args.cfg:
         k, v = kv.split("=")
         cfg[k] = int(v)
