@@ -20,11 +20,11 @@ for c in ${CFGS:-}; do
 done
 # every launch with its device time (cold-cache, serialised: compare SHARES); vertical_graph=0 so
 # that ncu lists the kernels of the vertical update one by one
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
-    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
+    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
     --option vertical_graph=0 > gpurun_out/bench_under_ncu_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'land_hydrology|unsat_loop|unsat_resume|tile_order' -s 60 -c 12 \
+    -k regex:'land_hydrology|unsat_engine|soil_column' -s 30 -c 3 \
     -o gpurun_out/prof_v1_$TAG python bench.py --steps 2 --warmup 10 --no-cpu-baseline \
     --option vertical_graph=0 > gpurun_out/bench_under_ncu2_$TAG.log 2>&1
 ls -la gpurun_out | tail -12
