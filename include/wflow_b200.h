@@ -71,7 +71,7 @@ typedef struct {
   /* B200 tuning, fixed at create; 0 = automatic (chosen from the shape of the domain) */
   int32_t wave_piece_depth_land; /* levels per piece of the land chunks; -1: one connected piece */
   int32_t vertical_slices;       /* unused (kept for ABI stability)                             */
-  int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (2)    */
+  int32_t unsat_inline_iters;    /* Brooks-Corey loops up to this many trips run in line (4)    */
   int32_t snow_gravitational_transport; /* snow_gravitational_transport__flag: lateral snow
                                   transport between snow and glacier model     sbm.jl:98-100 */
   /* river_routing = "local_inertial" (config_structure.jl; surface_staggered_scheme.jl): the

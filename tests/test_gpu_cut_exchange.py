@@ -57,7 +57,7 @@ def test_cut_basin_equals_one_handle_bit_for_bit(pkg, network, parts):
         got = np.empty_like(want)
         for m, pl in zip(shards, plans):
             sh = pl["shard"]
-            got[sh.river_cells if kind == 3 else sh.cells] = m.get(name)
+            got[sh.river_cells if kind in (3, 5) else sh.cells] = m.get(name)
         if not np.array_equal(got, want, equal_nan=True):
             worst.append(name)
     print(f"{network}: {parts} parts on {min(ndev, parts)} GPU(s), cut edges land/river {n_cut}")

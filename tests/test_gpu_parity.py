@@ -377,7 +377,7 @@ def test_two_shards_equal_one_handle_bit_for_bit(pkg, adaptive):
         want = one.get(name)
         got = np.empty_like(want)
         for m, sh in zip(parts, shards):
-            got[sh.river_cells if kind == 3 else sh.cells] = m.get(name)
+            got[sh.river_cells if kind in (3, 5) else sh.cells] = m.get(name)
         assert np.array_equal(got, want, equal_nan=True), name
     print("sub-steps", {k: st[k] for k in st if k.startswith("substeps")})
     group.close()

@@ -1066,10 +1066,11 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     u.list = h->d_unsat_list;
     u.count = h->d_unsat_count;
     u.cap = (int32_t)ns;
-    // in-line trip limit; measured on B200 (1000^2, V1 in us): 2: 365-376, 3: 374, 4: 374-381,
-    // 6: 385, 8: 386-390 (the first half's in-line loops beyond the first trip run with ~4 of 32
-    // lanes; the engine regroups them)
-    u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 2;
+    // in-line trip limit (the first half's in-line loops beyond the first trip run with ~4 of 32
+    // lanes; the engine regroups them, but pays scratch traffic per suspended cell). Measured on
+    // B200, 1000^2: V1 of steps 12-14 [us] 2: 365-376, 3: 374, 4: 374-381, 6: 385, 8: 386-390;
+    // mean over steps 10-59 (the basin keeps getting wetter) 2: 436, 4: 417, 8: 427
+    u.inline_iters = cfg->unsat_inline_iters > 0 ? cfg->unsat_inline_iters : 4;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     h->engine_grid = std::max(1, sms);

@@ -120,7 +120,7 @@ def shard_fields(fields: dict, table: dict, shard: Shard) -> dict:
             continue
         kind = table.get(name, 0)
         a = np.asarray(a)
-        out[name] = np.ascontiguousarray(a[shard.river_cells] if kind == 3 else a[shard.cells])
+        out[name] = np.ascontiguousarray(a[shard.river_cells] if kind in (3, 5) else a[shard.cells])
     return out
 
 
