@@ -233,3 +233,26 @@ def test_cut_basin_plan_is_consistent(pkg):
         is_riv[rli] = True
         n_riv_cut = sum(1 for u, v in cut if is_riv[u] and is_riv[v])
         assert sum(len(pl["links"][1]) for pl in plans) == n_riv_cut
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port on the host cores) prints ONE JSON line with the
+    keys of the bench contract and the same `config` keys as the GPU arm."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                          "--size", "40", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert set(d["config"]) == {"workload", "cells_per_gpu", "river_cells_per_gpu", "parallelism"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
