@@ -79,7 +79,8 @@ def lib(variant: str = ""):
         L.wfo_li_stable_timestep.restype = C.c_double
         for f in ("wfo_li_update_river_channel_flow", "wfo_li_update_bc_reservoir_model",
                   "wfo_li_update_water_depth_and_storage", "wfo_li_update_floodplain_flow",
-                  "wfo_li_update_floodplain_water_depth_and_storage"):
+                  "wfo_li_update_floodplain_water_depth_and_storage",
+                  "wfo_river_channel_floodplain_exchange", "wfo_update_floodplain_model"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_double]
             getattr(L, f).restype = None
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -153,7 +154,8 @@ INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_ind
 # reservoir defaults (reservoir.jl:200-272): cumulative / average variables start at zero
 ZERO_DEFAULTS = ZERO_DEFAULTS + (
     "fp_h", "fp_storage", "fp_q", "fp_q_cumulative", "fp_q_average", "fp_error",
-    "fp_water_depth_at_edge", "riv_q_channel_average",
+    "fp_water_depth_at_edge", "riv_q_channel_average", "fp_flow_capacity", "fp_qin",
+    "fp_qin_cumulative", "fp_qin_average", "riv_floodplain_water_exchange",
     "res_inflow_cumulative", "res_inflow_average", "res_external_inflow",
     "res_actual_external_abstraction_cumulative", "res_actual_external_abstraction_average",
     "res_outflow_cumulative", "res_outflow_average", "res_actevap_cumulative")

@@ -112,6 +112,10 @@
   X(fp_h, 3) X(fp_storage, 3) X(fp_q, 3) X(fp_q_cumulative, 3) X(fp_q_average, 3) X(fp_error, 3) \
   X(fp_water_depth_at_edge, 3) X(fp_mannings_n_sq_at_edge, 3) X(fp_zb_at_edge, 3) \
   X(li_bankfull_storage, 3) X(li_bankfull_depth, 3) X(riv_q_channel_average, 3) \
+  /* 1-D floodplain of the KINEMATIC-WAVE river (floodplain.jl:238-262 FloodPlainParameters / \
+   * Variables; surface_kinwave.jl:387-432,567-601): Manning flow capacity + accucapacityflux */ \
+  X(fp_mannings_n, 3) X(fp_slope, 3) X(fp_flow_capacity, 3) X(fp_qin, 3) \
+  X(fp_qin_cumulative, 3) X(fp_qin_average, 3) X(riv_floodplain_water_exchange, 3) \
   X(fp_profile_storage, 5) X(fp_profile_width, 5) X(fp_profile_flow_area, 5) \
   X(fp_profile_wetted_perimeter, 5) \
   /* reservoirs (routing/surface/reservoir.jl:5-44 parameters, 200-217 variables, 251-272 BC); \
@@ -223,6 +227,8 @@ void wfo_li_update_bc_reservoir_model(wfo_model*, double dt_s);
 void wfo_li_update_water_depth_and_storage(wfo_model*, double dt_s);
 void wfo_li_update_floodplain_flow(wfo_model*, double dt_s);
 void wfo_li_update_floodplain_water_depth_and_storage(wfo_model*, double dt_s);
+void wfo_river_channel_floodplain_exchange(wfo_model*, double dt_s);
+void wfo_update_floodplain_model(wfo_model*, double dt_s);
 void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182 */
 void wfo_update_model(wfo_model*, double dt);                  /* sbm_model.jl:60-92 */
 void wfo_update_diagnostic_vars(wfo_model*);                   /* soil.jl:1400-1436 */

@@ -730,6 +730,8 @@ static void kinwave_river_update(wfo_model* m, double dt) {
           inflow = m->riv_external_inflow[v] / m->riv_flow_length[v];
         }
         inflow -= m->riv_abstraction[v] / m->riv_flow_length[v];
+        if (m->cfg.fp_levels > 0)                          /* surface_kinwave.jl:530-532 */
+          inflow += m->riv_floodplain_water_exchange[v] / m->riv_flow_length[v];
         double o[2];
         int64_t it;
         wfo_kinematic_wave(m->riv_qin[v], m->riv_q[v], m->riv_qlat[v] + inflow, m->riv_alpha[v], dt,
@@ -762,6 +764,8 @@ void wfo_update_lateral_inflow_river(wfo_model* m) {
 }
 
 static void li_update_river_flow_model(wfo_model* m, double dt);
+void wfo_accucapacityflux(double* flux, double* material, const int64_t* order,
+                          const int64_t* down, int64_t n, const double* capacity, double dt);
 
 /* surface_kinwave.jl:613-662 */
 void wfo_update_river_flow_model(wfo_model* m, double dt) {
@@ -772,6 +776,7 @@ void wfo_update_river_flow_model(wfo_model* m, double dt) {
     m->riv_q_cumulative[i] = 0.0;
     m->riv_actual_external_abstraction_cumulative[i] = 0.0;
     m->riv_qin_cumulative[i] = 0.0;
+    if (m->cfg.fp_levels > 0) { m->fp_q_cumulative[i] = 0.0; m->fp_qin_cumulative[i] = 0.0; }
   }
   for (int64_t i = 0; i < m->cfg.nres; ++i) {  /* set_reservoir_vars!  surface_kinwave.jl:227-237 */
     m->res_inflow_cumulative[i] = 0.0;
@@ -787,7 +792,9 @@ void wfo_update_river_flow_model(wfo_model* m, double dt) {
                                                     0.05, m->scratch)
                       : m->cfg.dt_river;
     dt_s = check_timestepsize(dt_s, t, dt);
+    if (m->cfg.fp_levels > 0) wfo_river_channel_floodplain_exchange(m, dt_s);
     kinwave_river_update(m, dt_s);
+    if (m->cfg.fp_levels > 0) wfo_update_floodplain_model(m, dt_s);
     t += dt_s;
     m->substeps_river++;
   }
@@ -796,6 +803,15 @@ void wfo_update_river_flow_model(wfo_model* m, double dt) {
     m->riv_actual_external_abstraction_average[i] =
         m->riv_actual_external_abstraction_cumulative[i] / dt;
     m->riv_qin_average[i] = m->riv_qin_cumulative[i] / dt;
+  }
+  if (m->cfg.fp_levels > 0) {                              /* surface_kinwave.jl:650-659 */
+    PFOR for (int64_t i = 0; i < n; ++i) {
+      m->fp_q_average[i] = m->fp_q_cumulative[i] / dt;
+      m->riv_q_channel_average[i] = m->riv_q_average[i];
+      m->riv_q_average[i] = m->riv_q_channel_average[i] + m->fp_q_average[i];
+      m->fp_qin_average[i] = m->fp_qin_cumulative[i] / dt;
+      m->riv_qin_average[i] = m->riv_qin_average[i] + m->fp_qin_average[i];
+    }
   }
   for (int64_t i = 0; i < m->cfg.nres; ++i) {  /* average_reservoir_vars!  surface_kinwave.jl:244-258 */
     m->res_outflow_average[i] = m->res_outflow_cumulative[i] / dt;
@@ -966,6 +982,68 @@ void wfo_li_update_floodplain_water_depth_and_storage(wfo_model* m, double dt) {
       m->fp_storage[i] = 0.0;
     }
   }
+}
+
+/* ---- 1-D floodplain of the kinematic-wave river ------------------------------------------- */
+/* manning_flow                                                    surface_process.jl:166-169 */
+static double manning_flow(double mannings_n, double hydraulic_radius, double slope, double area) {
+  return cbrt(hydraulic_radius * hydraulic_radius) * sqrt(slope) * area / mannings_n;
+}
+
+/* river_channel_floodplain_exchange!                               surface_kinwave.jl:567-601 */
+void wfo_river_channel_floodplain_exchange(wfo_model* m, double dt) {
+  PFOR for (int64_t i = 0; i < m->cfg.nriv; ++i) {
+    const double storage_total = m->riv_storage[i] + m->fp_storage[i];
+    double delta_river_storage;
+    if (storage_total > m->li_bankfull_storage[i]) {
+      const double flood_storage = storage_total - m->li_bankfull_storage[i];
+      const double h = fp_flood_depth(m, flood_storage, m->riv_flow_length[i], i);
+      const double river_storage = (m->li_bankfull_depth[i] + h) * m->riv_flow_width[i] * m->riv_flow_length[i];
+      delta_river_storage = river_storage - m->riv_storage[i];
+      m->fp_storage[i] = jl_max(storage_total - river_storage, 0.0);
+      m->fp_h[i] = m->fp_storage[i] > 0.0 ? h : 0.0;
+    } else {
+      delta_river_storage = jl_max(storage_total - m->riv_storage[i], 0.0);
+      m->fp_h[i] = 0.0;
+      m->fp_storage[i] = 0.0;
+    }
+    m->riv_floodplain_water_exchange[i] = delta_river_storage / dt;
+  }
+}
+
+/* update_floodplain_model!(::KinematicWave, ::FloodPlainModel{<:Manning})          :387-432 */
+void wfo_update_floodplain_model(wfo_model* m, double dt) {
+  const wfo_network* nw = &m->river;
+  const int64_t n = m->cfg.nriv;
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t v = nw->order[k];
+    const int64_t ds = nw->down[v];
+    double cap = 0.0;
+    if (m->fp_h[v] > 0.0) {
+      int64_t i1, i2;
+      fp_interpolation_indices(m->cfg.fp_depth, m->cfg.fp_levels, m->fp_h[v], &i1, &i2);
+      const double flow_area = fp_floodplain_flow_area(m, m->fp_h[v], v, i1, i2);
+      const double flow_area_ds = ds >= 0 ? fp_floodplain_flow_area(m, m->fp_h[v], ds, i1, i2) : flow_area;
+      if (flow_area > 1.0e-05 && flow_area_ds > 1.0e-05) {
+        const double wetted_perimeter = fp_wetted_perimeter(m, m->fp_h[v], v, i1);
+        const double hydraulic_radius = flow_area / wetted_perimeter;
+        cap = manning_flow(m->fp_mannings_n[v], hydraulic_radius, m->fp_slope[v], flow_area);
+      }
+    }
+    m->fp_flow_capacity[v] = cap;
+  }
+  /* q .= accucapacityflux(storage, network, flow_capacity, dt): `accucapacityflux` only
+   * allocates the flux and calls accucapacityflux! on `storage` itself
+   * (routing/utils.jl:131-135), so the floodplain storage moves downstream here */
+  wfo_accucapacityflux(m->fp_q, m->fp_storage, nw->order, nw->down, n, m->fp_flow_capacity, dt);
+  for (int64_t i = 0; i < n; ++i) m->fp_q_cumulative[i] += m->fp_q[i] * dt;
+  for (int64_t k = 0; k < n; ++k) {   /* flux_in!  routing/utils.jl:161-167 */
+    const int64_t v = nw->order[k];
+    double ssum = 0.0;
+    for (int64_t u = nw->up_ptr[k]; u < nw->up_ptr[k + 1]; ++u) ssum += m->fp_q[nw->up_idx[u]];
+    m->fp_qin[v] = ssum;
+  }
+  for (int64_t i = 0; i < n; ++i) m->fp_qin_cumulative[i] += m->fp_qin[i] * dt;
 }
 
 /* update_bc_reservoir_model!                                                :627-661 */

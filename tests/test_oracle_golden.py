@@ -610,6 +610,76 @@ def test_local_inertial_river_with_floodplain_routing_process_530_690():
     assert m.f["fp_h"] == approx(np.array([0.2449102618909183, 0.22760349104031377, 0.20085420755385677]))
 
 
+def test_kinwave_river_with_floodplain_routing_process_858_987():
+    """2-node river (1 -> 2) with the kinematic wave's 1-D floodplain: channel-floodplain exchange,
+    kinwave_river_update! with the exchange as lateral inflow, Manning flow capacity of the
+    floodplain and its accucapacityflux -- step by step as the reference's unit test."""
+    L = orc.lib()
+    q = np.array([296.52948301601174, 192.8313119108856])
+    alpha = np.array([34.0789466790827, 34.0789466790827])
+    length = np.array([750.953125, 851.8125])
+    width = np.array([229.91920471191406, 229.91920471191406])
+    work = np.zeros(2)
+    dt = L.wfo_stable_timestep_surface(q.ctypes.data, alpha.ctypes.data, length.ctypes.data, 2,
+                                       0.05, work.ctypes.data)
+    assert dt == approx(1602.881460805217)
+
+    class G:
+        down = np.array([2, 0])
+    river = dict(graph=G, order=np.array([1, 2]), up_ptr=np.array([0, 0, 1]), up_idx=np.array([1]),
+                 order_of_subdomains=[np.array([1])], order_subdomain=[np.array([1, 2])],
+                 subdomain_indices=[np.array([1, 2])])
+
+    class G1:
+        down = np.array([0, 0])
+    land = dict(graph=G1, order=np.array([1, 2]), up_ptr=np.zeros(3, np.int64), up_idx=np.zeros(0, np.int64),
+                order_of_subdomains=[np.array([1, 2])], order_subdomain=[np.array([1]), np.array([2])],
+                subdomain_indices=[np.array([1]), np.array([2])])
+    storage = np.array([[0.0, 0.0], [86329.2726379633, 97924.02628183365],
+                        [172659.2726379633, 207762.02628183365], [258989.2726379633, 386716.02628183365],
+                        [369518.2726379633, 605009.0262818336], [724648.2726379633, 869843.0262818336]])
+    w0 = 229.91920471191406
+    pwidth = np.array([[w0, w0], [w0, w0], [229.9211418821914, 257.89243524836746],
+                       [229.9211418821914, 420.1722796977034], [294.369904912507, 512.5376770122533],
+                       [945.8113647239966, 621.8128989654414]])
+    flow_area = np.array([[0.0, 0.0], [114.95960235595703, 114.95960235595703],
+                          [229.9201732970527, 243.90581998014076], [344.8807442381484, 453.99195982899244],
+                          [492.06569669440194, 710.260798335119], [964.9713790564002, 1021.1672478178398]])
+    perimeter = np.array([[0.0, 0.0], [1.0, 1.0], [2.00193717027733, 29.9732305364534],
+                          [3.00193717027733, 193.25307498578934], [68.45070020059296, 286.61847230033925],
+                          [720.8921600120825, 396.8936942535273]])
+    f = dict(riv_q=q, riv_alpha=alpha, riv_flow_length=length, riv_flow_width=width,
+             riv_qlat=[3.9326064945614956e-5, 2.1713344971219756e-7], riv_qin=np.zeros(2),
+             riv_h=[4.509741437854894, 3.4835130995322534],
+             riv_storage=[778645.3962305915, 682239.2566234164],
+             riv_external_inflow=np.zeros(2), riv_abstraction=np.zeros(2),
+             li_bankfull_depth=[2.1051321029663086, 2.1051321029663086],
+             li_bankfull_storage=[363469.04651181493, 412286.02275520907],
+             fp_q=[1.2861909826521447, 1.9846650910027395], fp_h=np.zeros(2), fp_storage=np.zeros(2),
+             fp_mannings_n=[0.072, 0.072], fp_slope=[1.0e-5, 1.0e-5],
+             fp_profile_storage=storage.T, fp_profile_width=pwidth.T,
+             fp_profile_flow_area=flow_area.T, fp_profile_wetted_perimeter=perimeter.T,
+             river_land_indices=np.array([0, 1]))
+    f = {k: np.ascontiguousarray(v, dtype=np.int64 if k.endswith("indices") else np.float64)
+         for k, v in f.items()}
+    m = orc.OracleModel(dict(n=2, nriv=2, nres=0, N=1, fp_depth=[0.0, 0.5, 1.0, 1.5, 2.0, 2.5]),
+                        f, land, river)
+    L.wfo_river_channel_floodplain_exchange(m.h, dt)
+    assert m.f["riv_h"] == approx(np.array([4.509741437854894, 3.4835130995322534]))
+    assert m.f["riv_storage"] == approx(np.array([778645.3962305915, 682239.2566234164]))
+    assert m.f["fp_h"] == approx(np.array([2.0642836103410205, 1.1737631111525133]))
+    assert m.f["fp_storage"] == approx(np.array([58760.1445203583, 40074.01437791623]))
+    L.wfo_kinwave_river_update(m.h, dt)
+    assert m.f["riv_h"] == approx(np.array([2.872002930358695, 3.1138609375883397]))
+    assert m.f["riv_storage"] == approx(np.array([495875.84798393055, 609843.6005807515]))
+    assert m.f["riv_q"] == approx(np.array([139.7837242183345, 159.9486203252721]))
+    assert m.f["riv_q_cumulative"] == approx(np.array([224056.7400718776, 256378.67820075116]))
+    L.wfo_update_floodplain_model(m.h, dt)
+    assert m.f["fp_storage"] == approx(np.array([52745.30941770246, 41649.967280840756]))
+    assert m.f["fp_q"] == approx(np.array([3.752513987924126, 2.7693140810933157]))
+    assert m.f["fp_q_cumulative"] == approx(np.array([6014.835102655834, 4438.882199731312]))
+
+
 def test_accucapacityflux_routing_process_255_288():
     """PCRaster accucapacity examples on a 6-node graph (lateral snow transport's engine)."""
     L = orc.lib()
