@@ -21,8 +21,10 @@
  *   arrays are river-sized and riv_q holds the edge discharge; li_ghost_h: water depth of the
  *   ghost node downstream of a pit, riverdepth_bc);
  *   FloodPlainProfile / FloodPlainStaggeredParameters / Variables routing/surface/floodplain.jl:
- *   5-22,150-163,216-236 (fp_*: 1-D floodplain of the local-inertial river; li_bankfull_*:
- *   RiverFlowStaggeredParameters.bankfull_storage / bankfull_depth);
+ *   5-22,150-163,216-262 (fp_*: 1-D floodplain of the local-inertial river -- edge arrays by the
+ *   edge leaving the node -- or of the kinematic-wave river -- fp_mannings_n, fp_slope,
+ *   fp_flow_capacity, fp_qin*, riv_floodplain_water_exchange (RiverFlowBC); li_bankfull_*:
+ *   bankfull_storage / bankfull_depth of the river parameters);
  *   ReservoirParameters routing/surface/reservoir.jl:5-44, ReservoirVariables :200-217,
  *   ReservoirBC :251-272 (res_outflow_curve_type holds ReservoirOutflowType as a number:
  *   2 free_weir, 3 modified_puls, 4 simple).
@@ -96,6 +98,8 @@
   X(fp_h, 3) X(fp_storage, 3) X(fp_q, 3) X(fp_q_cumulative, 3) X(fp_q_average, 3) X(fp_error, 3) \
   X(fp_water_depth_at_edge, 3) X(fp_mannings_n_sq_at_edge, 3) X(fp_zb_at_edge, 3) \
   X(li_bankfull_storage, 3) X(li_bankfull_depth, 3) X(riv_q_channel_average, 3) \
+  X(fp_mannings_n, 3) X(fp_slope, 3) X(fp_flow_capacity, 3) X(fp_qin, 3) \
+  X(fp_qin_cumulative, 3) X(fp_qin_average, 3) X(riv_floodplain_water_exchange, 3) \
   X(fp_profile_storage, 5) X(fp_profile_width, 5) X(fp_profile_flow_area, 5) \
   X(fp_profile_wetted_perimeter, 5) \
   X(res_area, 4) X(res_outflow_curve_type, 4) X(res_maximum_storage, 4) X(res_threshold, 4) \

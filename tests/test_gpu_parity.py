@@ -267,6 +267,26 @@ def test_local_inertial_river_with_floodplain(pkg, reservoirs):
     _close(gpu)
 
 
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_kinematic_wave_river_with_floodplain(pkg, adaptive):
+    """floodplain_1d__flag with the kinematic-wave river: per sub-step the channel-floodplain
+    exchange (bankfull redistribution, lateral inflow of the wave), the Manning flow capacity of
+    the floodplain from its profile and accucapacityflux! of the floodplain storage
+    (surface_kinwave.jl:387-432,567-601,650-659) -- inside the river's skewed wavefront, three
+    published values per node and sub-step."""
+    gpu, ora, cfg = parity.run_pair(pkg, 70, 110, steps=4, seed=43, floodplain=True,
+                                    adaptive=adaptive)
+    assert len(cfg["fp_depth"]) == 6 and cfg["river_routing"] == 0
+    rep = parity.compare_models(gpu, ora)
+    st, o = gpu.stats(), ora.newton_stats()
+    assert st["substeps_river"] == o["substeps_river"]
+    wet = int((ora.f["fp_h"] > 0.0).sum())
+    assert wet > 10 and float(np.max(ora.f["fp_q_average"])) > 0.0
+    assert np.array_equal(gpu.get("fp_h") > 0.0, ora.f["fp_h"] > 0.0)
+    print(rep.summary(), "river sub-steps", st["substeps_river"], "nodes over bank", wet)
+    _close(gpu)
+
+
 def test_five_soil_layers(pkg):
     gpu, ora, cfg = parity.run_pair(pkg, 32, 48, steps=2, seed=2,
                                     soil_layer_thickness_mm=(50, 50, 300, 800))

@@ -852,8 +852,10 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
 
   WflowB200* h = new WflowB200();
   h->cfg = *cfg;
-  if (cfg->fp_levels < 0 || cfg->fp_levels > 16 || (cfg->fp_levels > 0 && cfg->river_routing != 1)) {
-    g_create_error = "fp_levels: 0 .. 16, and the 1-D floodplain needs river_routing = local_inertial";
+  if (cfg->fp_levels < 0 || cfg->fp_levels > 16 ||
+      (cfg->fp_levels > 0 && cfg->river_routing == 0 && dom->nres > 0)) {
+    g_create_error = "fp_levels: 0 .. 16; the kinematic wave's 1-D floodplain is not supported "
+                     "together with reservoirs";
     delete h;
     return WFLOWB200_ERR_ARG;
   }
@@ -917,7 +919,9 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   fill(h->f.li_zs_at_edge, 3, 0.0);
   fill(h->f.li_water_depth_at_edge, 3, 0.0);
   for (double* p : {h->f.fp_h, h->f.fp_storage, h->f.fp_q, h->f.fp_q_cumulative, h->f.fp_q_average,
-                    h->f.fp_error, h->f.fp_water_depth_at_edge, h->f.riv_q_channel_average})
+                    h->f.fp_error, h->f.fp_water_depth_at_edge, h->f.riv_q_channel_average,
+                    h->f.fp_flow_capacity, h->f.fp_qin, h->f.fp_qin_cumulative, h->f.fp_qin_average,
+                    h->f.riv_floodplain_water_exchange})
     fill(p, 3, 0.0);                            // floodplain.jl:216-236
   fill(h->f.waterdepth_river, 0, 0.0);          // runoff.jl:26
   fill(h->f.unsaturated_store_depth, 0, 0.0);   // soil.jl:71
@@ -988,7 +992,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
       return bail(WFLOWB200_ERR_ARG);
     }
     if (nli + nle + nri + nre > 0 &&
-        (cfg->adaptive || h->nres > 0 || cfg->snow_gravitational_transport || cfg->river_routing != 0)) {
+        (cfg->adaptive || h->nres > 0 || cfg->snow_gravitational_transport || cfg->river_routing != 0 ||
+         cfg->fp_levels > 0)) {
       h->err = "cut edges are supported for kinematic-wave routing with fixed internal time steps, "
                "without reservoirs and lateral snow transport";
       return bail(WFLOWB200_ERR_ARG);
@@ -1094,7 +1099,16 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->kc.qroot = h->cfg.kin_wave_min_flow_qroot;
   build_vertical_stage(h->f, h->kc, h->N, h->v_stage);
   h->kc.river_routing = cfg->river_routing;
-  if (cfg->river_routing == 1) {   // the staggered grid by river slot (network.jl:281-293)
+  h->kc.fp_levels = cfg->fp_levels;
+  for (int l = 0; l < 16; ++l) h->kc.fp_depth[l] = cfg->fp_depth[l];
+  {
+    double* d = nullptr;
+    TRY_CREATE(cudaMalloc((void**)&d, 16 * sizeof(double)));
+    TRY_CREATE(cudaMemcpy(d, cfg->fp_depth, 16 * sizeof(double), cudaMemcpyHostToDevice));
+    h->f.fp_depth = d;
+  }
+  if (cfg->river_routing == 1 || cfg->fp_levels > 0) {   // the staggered grid by river slot (network.jl:281-293);
+                                                           // the kinematic wave's floodplain needs the downstream slot
     const Network& rn = h->river.nw;
     std::vector<int64_t> dst(std::max(h->nrs, 1), -1), in_ptr(h->nriv + 1, 0), in_idx;
     for (int p = 0; p < h->nriv; ++p) {
@@ -1118,10 +1132,11 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
 
   // persistent cooperative grids: as many co-resident CTAs as the device holds
   h->smem_olf = wave_smem(0, h->land.dev.max_inlets);
-  h->smem_riv = wave_smem(1, h->river.dev.max_inlets);
+  const bool kw_floodplain = cfg->fp_levels > 0 && cfg->river_routing == 0;
+  h->smem_riv = wave_smem(kw_floodplain ? 4 : 1, h->river.dev.max_inlets);
   h->smem_ssf = wave_smem(2, h->land.dev.max_inlets);
   h->grid_olf = wave_max_grid(0, h->N, h->smem_olf, cfg->device);
-  h->grid_riv = wave_max_grid(1, h->N, h->smem_riv, cfg->device);
+  h->grid_riv = wave_max_grid(kw_floodplain ? 4 : 1, h->N, h->smem_riv, cfg->device);
   h->grid_ssf = wave_max_grid(2, h->N, h->smem_ssf, cfg->device);
   if (cfg->snow_gravitational_transport) {
     h->smem_snow = wave_smem(3, std::max(h->land.dev.max_inlets, h->land_full.dev.max_inlets));
@@ -1131,7 +1146,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
   h->smem_surface = surface_smem(h->land.dev.max_inlets, h->river.dev.max_inlets,
                                  &h->smem_surface_per_warp);
   h->grid_surface = surface_max_grid(h->smem_surface, cfg->device);
-  h->fuse_surface = h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive && cfg->river_routing == 0;
+  h->fuse_surface = h->grid_surface > 0 && h->nriv > 0 && !cfg->adaptive && cfg->river_routing == 0 &&
+                    !kw_floodplain;   // (the river with floodplain publishes three values: own kernel)
   if (h->grid_olf <= 0 || h->grid_riv <= 0 || h->grid_ssf <= 0) {
     h->err = "occupancy query failed";
     return bail(WFLOWB200_ERR_CUDA);
@@ -1155,6 +1171,7 @@ void wflowb200_destroy(WflowB200* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   cudaFree(h->pool); cudaFree(h->f.number_of_layers); cudaFree(h->f.n_unsatlayers);
   cudaFree(h->f.nlayers_kv); cudaFree(h->f.olf_newton_trace); cudaFree(h->f.riv_newton_trace);
+  cudaFree((void*)h->f.fp_depth);
   cudaFree(h->f.riv_reservoir); cudaFree(h->f.res_land_slot); cudaFree(h->res_ident);
   cudaFree(h->f.res_river_slot); cudaFree(h->f.li_dst_slot); cudaFree(h->f.li_in_ptr);
   cudaFree(h->f.li_in_idx); cudaFree(h->d_li_barrier); cudaFree(h->d_li_dt); cudaFree(h->d_li_substeps);
@@ -1568,15 +1585,17 @@ int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
     return check_launch(h, launch_local_inertial_river(h->f, h->kc, w, h->stream),
                         "update_river_flow_model (local inertial)");
   }
+  const bool fp = h->cfg.fp_levels > 0;   // the kinematic wave's 1-D floodplain: 3 values per node
+  const int nv = fp ? 3 : 1;
+  auto launch = [&](const WaveLaunch& w) {
+    return fp ? launch_river_floodplain_wave(h->f, h->kc, h->river.dev, w, h->stream)
+              : launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
+  };
   if (h->cfg.adaptive)
-    return run_wave_adaptive(h, h->river, dt, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
-                             [&](const WaveLaunch& w) {
-                               return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
-                             }, "update_river_flow_model");
-  return run_wave(h, h->river, dt, h->cfg.dt_river, 1, 1, h->grid_riv, h->smem_riv, h->sub_river,
-                  [&](const WaveLaunch& w) {
-                    return launch_river_wave(h->f, h->kc, h->river.dev, w, h->stream);
-                  }, "update_river_flow_model");
+    return run_wave_adaptive(h, h->river, dt, 1, nv, h->grid_riv, h->smem_riv, h->sub_river, launch,
+                             "update_river_flow_model");
+  return run_wave(h, h->river, dt, h->cfg.dt_river, 1, nv, h->grid_riv, h->smem_riv, h->sub_river,
+                  launch, "update_river_flow_model");
 }
 
 // update_overland_flow_model! + update_lateral_inflow!(river) + update_river_flow_model! in one
@@ -2088,7 +2107,7 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
   out->newton_calls_river = (int64_t)rs.newton_calls_river;
   out->newton_iters_river = (int64_t)rs.newton_iters_river;
   out->newton_maxit_river = (int64_t)rs.newton_maxit_river;
-  if (h->d_li_substeps) {
+  if (h->d_li_substeps && h->cfg.river_routing == 1) {
     int cnt = 0;
     cudaMemcpy(&cnt, h->d_li_substeps, sizeof(int), cudaMemcpyDeviceToHost);
     h->sub_river = cnt;

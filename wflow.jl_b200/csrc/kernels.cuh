@@ -112,6 +112,8 @@ size_t wave_smem(int kind, int max_inlets);
 int wave_max_grid(int kind, int n_layers, size_t smem, int device);  // co-resident CTAs
 int launch_overland_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
                          cudaStream_t s);
+int launch_river_floodplain_wave(const DevFields& f, const KCfg& c, const DevNet& net,
+                                 const WaveLaunch& w, cudaStream_t s);
 int launch_river_wave(const DevFields& f, const KCfg& c, const DevNet& net, const WaveLaunch& w,
                       cudaStream_t s);
 int launch_subsurface_wave(const DevFields& f, const KCfg& c, const DevNet& net, int n_layers,

@@ -32,6 +32,7 @@
 #include "kernels.cuh"
 #include "model.cuh"
 #include "reservoir.cuh"
+#include "floodplain.cuh"
 
 namespace wfb {
 
@@ -90,43 +91,6 @@ __device__ __forceinline__ double local_inertial_flow(double q0, double zs0, dou
 }
 
 
-// ---- FloodPlainProfile (floodplain.jl:287-354); tables are [level][river slot] ---------------
-struct FpTables {
-  const double *storage, *width, *flow_area, *perimeter;
-  int nrs, levels;
-  const double* depth;  // kernel parameter space
-};
-// interpolation_indices: the last level with v[l] <= x (and the next one)
-__device__ __forceinline__ void fp_indices_depth(const FpTables& t, double x, int& i1, int& i2) {
-  int a = 0;
-  for (int l = 0; l < t.levels; ++l)
-    if (t.depth[l] <= x) a = l;
-  i1 = a;
-  i2 = a == t.levels - 1 ? a : a + 1;
-}
-// compute_floodplain_flow_area (flood flow area minus the channel's share)
-__device__ __forceinline__ double fp_flow_area(const FpTables& t, double h, int p, int i1, int i2) {
-  const double channel_area = __ldg(t.width + p) * h;
-  const double delta_h = h - t.depth[i1];
-  const double flow_area = __ldg(t.flow_area + i1 * t.nrs + p) + (__ldg(t.width + i2 * t.nrs + p) * delta_h);
-  return jmax(flow_area - channel_area, 0.0);
-}
-__device__ __forceinline__ double fp_wetted_perimeter(const FpTables& t, double h, int p, int i1) {
-  const double delta_h = h - t.depth[i1];
-  return __ldg(t.perimeter + i1 * t.nrs + p) + 2.0 * delta_h;
-}
-// compute_flood_depth
-__device__ __forceinline__ double fp_flood_depth(const FpTables& t, double flood_storage,
-                                                 double flow_length, int p) {
-  int a = 0;
-  for (int l = 0; l < t.levels; ++l)
-    if (__ldg(t.storage + l * t.nrs + p) <= flood_storage) a = l;
-  const int i2 = a == t.levels - 1 ? a : a + 1;
-  const double delta_A = (flood_storage - __ldg(t.storage + a * t.nrs + p)) / flow_length;
-  const double delta_h = delta_A / __ldg(t.width + i2 * t.nrs + p);
-  return t.depth[a] + delta_h;
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(kLiBlock, 2)
@@ -141,7 +105,7 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
   const unsigned long long inf_bits = 0x7ff0000000000000ull;
   const bool floodplain = w.fp_levels > 0;
   const FpTables fp{f.fp_profile_storage, f.fp_profile_width, f.fp_profile_flow_area,
-                    f.fp_profile_wetted_perimeter, c.nrs, w.fp_levels, w.fp_depth};
+                    f.fp_profile_wetted_perimeter, c.nrs, w.fp_levels, f.fp_depth};
 
   // set_reservoir_vars! / set_flow_vars!                          surface_kinwave.jl:227-237,269-275
   for (int p = tid; p < n; p += stride) {

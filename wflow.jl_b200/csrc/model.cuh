@@ -20,6 +20,7 @@ struct DevFields {
   int32_t* number_of_layers;   // land
   int32_t* n_unsatlayers;      // land
   int32_t* riv_land_slot;      // river slot -> land slot
+  const double* fp_depth;      // floodplain profile depths (cfg.fp_levels values), device
   int32_t* nlayers_kv;         // land (KvLayeredExponential only)
   int32_t* riv_reservoir;      // river slot -> reservoir (0-based) or -1; nullptr without reservoirs
   int32_t* res_land_slot;      // reservoir -> land slot of its outlet cell
@@ -79,6 +80,8 @@ struct KCfg {
   int32_t river_routing;       // 0 kinematic wave, 1 local inertial
   int32_t kw_root_each_substep; // 1: u_prev = pow(q_prev, 0.2) before every solve, like the
                                // reference (default 0: carried, see routing.cu: KwState)
+  int32_t fp_levels;           // 1-D floodplain: levels of the profile (0: none) and their depths
+  double fp_depth[16];
 };
 
 }  // namespace wfb

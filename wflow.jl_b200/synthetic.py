@@ -441,40 +441,45 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
         F["li_mannings_n_sq_at_edge"] = n_at_edge * n_at_edge
         F["li_ghost_h"] = np.zeros(nriv)                        # riverdepth_bc
         F["li_error"] = np.zeros(nriv)
-        if floodplain:
-            # 1-D floodplain (floodplain.jl:50-147): a six-level profile per node whose first
-            # width is the channel's and whose widths grow with the depth; flow area, wetted
-            # perimeter and storage are its cumulative sums. A shallow bankfull depth so that
-            # the synthetic rivers do go over bank.
-            fp_depth = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.5])
-            P = len(fp_depth)
-            bankfull_depth = 0.02 + 0.06 * u01(seed, 95, rg)
-            grow = 1.5 + 2.0 * u01(seed, 96, rg)               # widening per level
-            width = np.empty((nriv, P))
-            width[:, 0] = W
-            for l in range(1, P):
-                width[:, l] = width[:, l - 1] * (1.0 + (grow - 1.0) / l)
-            dh = np.diff(fp_depth)
-            area = np.zeros((nriv, P))
-            perim = np.empty((nriv, P))
-            perim[:, 0] = W + 2.0 * bankfull_depth
-            perim[:, 1] = perim[:, 0] + 2.0 * dh[0]
-            for l in range(1, P):
-                area[:, l] = area[:, l - 1] + width[:, l] * dh[l - 1]
-                if l > 1:
-                    perim[:, l] = perim[:, l - 1] + (width[:, l] - width[:, l - 1]) + 2.0 * dh[l - 1]
-            F["fp_profile_width"] = width
-            F["fp_profile_flow_area"] = area
-            F["fp_profile_wetted_perimeter"] = perim
-            F["fp_profile_storage"] = area * L[:, None]
-            F["li_bankfull_depth"] = bankfull_depth
-            F["li_bankfull_storage"] = bankfull_depth * W * L
-            zb_fp = zb + bankfull_depth
-            F["fp_zb_at_edge"] = np.maximum(zb_fp, zb_fp[d])
-            n_fp = 0.072
+    if floodplain and nriv:
+        # 1-D floodplain (floodplain.jl:50-147): a six-level profile per node whose first
+        # width is the channel's and whose widths grow with the depth; flow area, wetted
+        # perimeter and storage are its cumulative sums. A shallow bankfull depth so that
+        # the synthetic rivers do go over bank.
+        fp_depth = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.5])
+        P = len(fp_depth)
+        bankfull_depth = 0.02 + 0.06 * u01(seed, 95, rg)
+        grow = 1.5 + 2.0 * u01(seed, 96, rg)               # widening per level
+        width = np.empty((nriv, P))
+        width[:, 0] = F["riv_flow_width"]
+        for l in range(1, P):
+            width[:, l] = width[:, l - 1] * (1.0 + (grow - 1.0) / l)
+        dh = np.diff(fp_depth)
+        area = np.zeros((nriv, P))
+        perim = np.empty((nriv, P))
+        perim[:, 0] = F["riv_flow_width"] + 2.0 * bankfull_depth
+        perim[:, 1] = perim[:, 0] + 2.0 * dh[0]
+        for l in range(1, P):
+            area[:, l] = area[:, l - 1] + width[:, l] * dh[l - 1]
+            if l > 1:
+                perim[:, l] = perim[:, l - 1] + (width[:, l] - width[:, l - 1]) + 2.0 * dh[l - 1]
+        F["fp_profile_width"] = width
+        F["fp_profile_flow_area"] = area
+        F["fp_profile_wetted_perimeter"] = perim
+        F["fp_profile_storage"] = area * F["riv_flow_length"][:, None]
+        F["li_bankfull_depth"] = bankfull_depth
+        F["li_bankfull_storage"] = bankfull_depth * F["riv_flow_width"] * F["riv_flow_length"]
+        n_fp = 0.072
+        if river_routing == 1:      # local inertial: edge parameters (floodplain.jl:164-215)
+            zb_fp = F["li_zb"] + bankfull_depth
+            rd = np.where(rdown > 0, rdown - 1, np.arange(nriv))
+            F["fp_zb_at_edge"] = np.maximum(zb_fp, zb_fp[rd])
             F["fp_mannings_n_sq_at_edge"] = np.full(nriv, n_fp * n_fp)
-            for k in ("fp_h", "fp_storage", "fp_q", "fp_error"):
-                F[k] = np.zeros(nriv)
+        else:                       # kinematic wave: Manning flow capacity (floodplain.jl:238-246)
+            F["fp_mannings_n"] = np.full(nriv, n_fp)
+            F["fp_slope"] = riv_slope.copy()
+        for k in ("fp_h", "fp_storage", "fp_q", "fp_error"):
+            F[k] = np.zeros(nriv)
     # ---- reservoirs on the river (reservoir.jl; Moselle has two, test/sbm_config.toml:126) -----
     reservoir_river_indices = np.zeros(0, dtype=np.int64)
     nres = 0
@@ -524,7 +529,7 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                land_streamorder_min=5, river_streamorder_min=6, dt_land=3600.0, dt_river=900.0,
                dt_ssf=86400.0, ssf_alpha_coefficient=1.0, dt=dt,
                kin_wave_min_flow_qroot=1e-30 ** 0.2)
-    if floodplain and river_routing == 1 and nriv:
+    if floodplain and nriv:
         cfg["fp_depth"] = [0.0, 0.5, 1.0, 1.5, 2.0, 2.5]
     domain = dict(d1=d1, d2=d2, indices=indices, ldd=ldd, river_land_indices=river_land_indices,
                   down=down, gid=gid, upstream_cells=acc,
