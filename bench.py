@@ -155,6 +155,11 @@ def dist_env():
 
 
 def workload_text(d1, d2, adaptive, local_inertial=False):
+    if local_inertial == 2:
+        return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical + kinematic-wave "
+                "subsurface + 2-D LOCAL-INERTIAL overland flow coupled to the LOCAL-INERTIAL river "
+                "(subgrid channel), daily step, sub-steps min(alpha L / sqrt(g h)) of land and "
+                "river, N=4 soil layers, snow on")
     if local_inertial:
         return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical + kinematic-wave "
                 "overland/subsurface + LOCAL-INERTIAL river with 1-D floodplain, daily step, fixed "
@@ -177,6 +182,8 @@ def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0, local_iner
     that every tile of the global raster is a different random forest. Only the rank's own
     cells are ever generated: everything is a pure function of (seed, global cell id)."""
     extra = dict(river_routing=1, floodplain=True) if local_inertial else {}
+    if local_inertial == 2:
+        extra = dict(river_routing=1, land_routing=1)
     return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive,
                                     catchment_length=catchment_length, **extra)
 
@@ -294,6 +301,9 @@ def main():
     ap.add_argument("--local-inertial", action="store_true",
                     help="BASELINE configs[3]: local-inertial river + 1-D floodplain instead of the "
                          "kinematic-wave river")
+    ap.add_argument("--local-inertial-land", action="store_true",
+                    help="2-D local-inertial overland flow coupled to the local-inertial river "
+                         "(land_routing = river_routing = local_inertial)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-steps", type=int, default=2, help="oracle steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -306,6 +316,8 @@ def main():
     ap.add_argument("--cfg", action="append", default=[], metavar="NAME=INT",
                     help="WflowB200Config tuning field, e.g. vertical_slices=1")
     args = ap.parse_args()
+    if args.local_inertial_land:
+        args.local_inertial = 2
     rank, world, local = dist_env()
     pkg = load_pkg()
     d1, d2 = (int(x) for x in args.shape.split("x")) if args.shape else (args.size, args.size)
@@ -433,11 +445,14 @@ def main():
             model.set_forcing(*pkg.synthetic.make_forcing(args.seed, first + s, dom["gid"], dt))
             model.update_model(dt)
         try:
-            rep = parity.compare_models(model, ora)
+            # (the explicit local-inertial schemes turn last-bit noise into 1e-6: tests/test_tolerances.py)
+            rep = parity.compare_models(model, ora, outliers=(1.0, 1e-5) if args.local_inertial else None)
             line["parity_checked"] = {"worst_rel": rep.worst_rel, "n_fields": len(rep),
                                       "cells": n, "steps": 1 + args.cpu_steps,
-                                      "tolerance": "elementwise 1e-10 relative + per-element atol "
-                                                   "(tests/parity.py)", "ok": True}
+                                      "tolerance": ("elementwise 1e-10 relative + per-element atol "
+                                                    "(tests/parity.py)" +
+                                                    ("; local-inertial fields 1e-5" if args.local_inertial else "")),
+                                      "ok": True}
         except AssertionError as e:
             line["parity_checked"] = {"ok": False, "error": str(e)[:300]}
         line["cpu_baseline"] = {

@@ -89,6 +89,15 @@ typedef struct {
   int32_t fp_levels;           /* length(profile.depth), <= 16                                 */
   int32_t reserved2_;
   double fp_depth[16];         /* profile.depth [m], ascending from 0                          */
+  /* land_routing = "local_inertial" (needs river_routing = 1, no 1-D floodplain): 2-D overland
+   * flow on the staggered grid coupled to the local-inertial river with its subgrid channel,
+   * update_overland_flow_model!(overland, river, domain, clock, dt)
+   * (surface_staggered_scheme.jl:1153-1194); the fields li_land_* exist only then */
+  int32_t land_routing;        /* 0 kinematic_wave, 1 local_inertial                           */
+  int32_t li_land_froude_limit;/* land_surface_water_flow__froude_limit_flag                   */
+  double li_land_alpha;        /* land_local_inertial_flow__alpha_coefficient (0.7)            */
+  double li_land_theta;        /* land_local_inertial_flow__theta_coefficient (1.0)            */
+  double li_land_h_thresh;     /* land_surface_water_flow_threshold__depth (1e-3 m)            */
 } WflowB200Config;
 
 /* The drainage network as the Julia model holds it (network.jl:48-81,175-208). */
@@ -144,6 +153,12 @@ typedef struct {
 #define WFLOWB200_A_WAVE_NODE_LEVEL 12 /* level of every node (0-based), by node id            */
 #define WFLOWB200_A_WAVE_CHUNK_PTR 13  /* slot offsets of the chunks (0-based, n_chunks + 1)   */
 #define WFLOWB200_A_WAVE_CHUNK_OUTLET 14 /* outlet node id of every chunk                      */
+/* EdgeConnectivity of the land network (network.jl:27-33,136-153; land_routing = 1): index of the
+ * active neighbour of every cell, n + 1 where there is none */
+#define WFLOWB200_A_EDGE_X_UP 15       /* CartesianIndex(1, 0)                                 */
+#define WFLOWB200_A_EDGE_X_DOWN 16     /* CartesianIndex(-1, 0)                                */
+#define WFLOWB200_A_EDGE_Y_UP 17       /* CartesianIndex(0, 1)                                 */
+#define WFLOWB200_A_EDGE_Y_DOWN 18     /* CartesianIndex(0, -1)                                */
 #define WFLOWB200_DOMAIN_LAND 0
 #define WFLOWB200_DOMAIN_RIVER 1
 
@@ -223,8 +238,19 @@ int32_t wflowb200_update_subsurface_flow_model(WflowB200* h, double dt);
 int32_t wflowb200_update_soil_water_storage(WflowB200* h, double dt);
 /* update_lateral_inflow!(overland, ...)               routing/surface/surface_kinwave.jl:740-766 */
 int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h);
-/* update_overland_flow_model!(overland, domain.land, dt)              surface_kinwave.jl:347-385 */
+/* update_overland_flow_model!(overland, domain.land, dt)              surface_kinwave.jl:347-385
+ * land_routing = 1: update_overland_flow_model!(overland, river, domain, clock, dt) -- the 2-D
+ * local-inertial overland flow AND the local-inertial river flow of the model step: per sub-step
+ * dt_s = min(stable_timestep(river), stable_timestep(land)), the x / y edge flows of every cell
+ * (update_directional_flow!, local_inertial_flow of de Almeida et al. 2012), the reservoirs'
+ * overland inflow, river edge flow, reservoirs, and the water depth and storage of land and
+ * river cells (subgrid channel, bankfull spill) -- all sub-steps inside ONE persistent kernel
+ * surface_staggered_scheme.jl:1022-1043,1153-1546; surface_process.jl:123-159 */
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt);
+/* update_bc_overland_flow_model!(overland, (; soil, runoff, subsurface_flow), domain, dt): runoff
+ * = (net_runoff + net_runoff_river) * area, plus the subsurface flow to the river at river cells
+ * (land_routing = 1)                                       surface_staggered_scheme.jl:1080-1097 */
+int32_t wflowb200_update_bc_overland_flow_model(WflowB200* h);
 /* update_lateral_inflow!(river, ...)                                  surface_kinwave.jl:710-734 */
 int32_t wflowb200_update_lateral_inflow_river(WflowB200* h);
 /* update_inflow!(reservoir, river_flow, (; overland_flow, subsurface_flow), network): overland

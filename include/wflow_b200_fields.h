@@ -3,7 +3,9 @@
  *
  * X(name, kind): kind 0 = land scalar (n), 1 = land layered (n x N), 2 = land layered+1
  * (n x (N+1)), 3 = river scalar (nriv), 4 = reservoir scalar (nres), 5 = river x floodplain profile
- * level (nriv x fp_levels, a node's levels contiguous like Julia's profile.x[level, node]). Names are the reference's struct field names; a
+ * level (nriv x fp_levels, a node's levels contiguous like Julia's profile.x[level, node]), 6 = land
+ * scalar of the 2-D local-inertial overland flow (n values with land_routing = 1, else none: no HBM
+ * is spent on them). Names are the reference's struct field names; a
  * component prefix is added where two structs share a name (snow_/glacier_/ssf_/olf_/riv_/
  * recharge_/runoff_/soil_).
  *
@@ -27,7 +29,12 @@
  *   bankfull_storage / bankfull_depth of the river parameters);
  *   ReservoirParameters routing/surface/reservoir.jl:5-44, ReservoirVariables :200-217,
  *   ReservoirBC :251-272 (res_outflow_curve_type holds ReservoirOutflowType as a number:
- *   2 free_weir, 3 modified_puls, 4 simple).
+ *   2 free_weir, 3 modified_puls, 4 simple);
+ *   LocalInertialOverlandFlowParameters / Variables / BC routing/surface/surface_staggered_scheme.jl:
+ *   840-891,963-968 and x_length / y_length of LandParameters (li_land_*: the 2-D local-inertial
+ *   overland flow. The reference's flow vectors qx, qy, ... hold n + 1 entries whose last one -- the
+ *   edge to "outside" -- stays 0; here they hold n. The model's h and storage live in olf_h /
+ *   olf_storage: overland_flow.variables.h / .storage whatever the routing method).
  */
 #ifndef WFLOW_B200_FIELDS_H
 #define WFLOW_B200_FIELDS_H
@@ -110,6 +117,12 @@
   X(res_actual_external_abstraction_cumulative, 4) X(res_actual_external_abstraction_average, 4) \
   X(res_precipitation, 4) X(res_evaporation, 4) X(res_waterlevel, 4) X(res_storage, 4) \
   X(res_outflow, 4) X(res_outflow_cumulative, 4) X(res_outflow_average, 4) X(res_outflow_obs, 4) \
-  X(res_actevap_cumulative, 4)
+  X(res_actevap_cumulative, 4) \
+  X(li_land_xwidth_at_edge, 6) X(li_land_ywidth_at_edge, 6) X(li_land_zx_max_at_edge, 6) \
+  X(li_land_zy_max_at_edge, 6) X(li_land_mannings_n_sq_at_edge, 6) X(li_land_z, 6) \
+  X(li_land_x_length, 6) X(li_land_y_length, 6) X(li_land_runoff, 6) \
+  X(li_land_qx0, 6) X(li_land_qy0, 6) X(li_land_qx, 6) X(li_land_qy, 6) \
+  X(li_land_qx_cumulative, 6) X(li_land_qy_cumulative, 6) X(li_land_qx_average, 6) \
+  X(li_land_qy_average, 6) X(li_land_error, 6)
 
 #endif

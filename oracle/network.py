@@ -13,6 +13,7 @@ Python/numpy, the reference's integer artefacts that must be reproduced BIT-EXAC
     kinwave_set_subdomains         Wflow/src/subdomains.jl:1-255
   * filter_upstream_nodes          Wflow/src/utils.jl:61-71
   * get_flow_fraction_to_river     Wflow/src/utils.jl:493-510
+  * EdgeConnectivity               Wflow/src/network.jl:27-33,136-153
 
 Pinned against the reference's own golden vectors (Wflow/test/subdomains.jl:48-87) in
 tests/test_oracle_golden.py.
@@ -328,6 +329,25 @@ def get_flow_fraction_to_river(g: DiGraph1, ldd, inds_river, slope) -> np.ndarra
             if ldd[j - 1] != ldd[i - 1]:
                 fraction[j - 1] = slope[j - 1] / (slope[i - 1] + slope[j - 1])
     return fraction
+
+
+# DIRS / NEIGHBORS                  Wflow/src/network.jl:3, routing/subsurface/connectivity.jl:61-66
+EDGE_DIRS = (("ind_y_down", (0, -1)), ("ind_x_down", (-1, 0)), ("ind_x_up", (1, 0)),
+             ("ind_y_up", (0, 1)))
+
+
+def edge_connectivity(indices: np.ndarray, d1: int, d2: int) -> dict:
+    """EdgeConnectivity(network::NetworkLand)                    Wflow/src/network.jl:136-153:
+    for every active cell the index (1-based) of the active neighbour in each of the four
+    directions, n + 1 where the neighbour is outside the raster or inactive."""
+    n = len(indices)
+    rev = np.zeros((d1 + 2, d2 + 2), dtype=np.int64)          # reverse_indices, padded
+    rev[indices[:, 0], indices[:, 1]] = np.arange(1, n + 1)
+    out = {}
+    for name, (di, dj) in EDGE_DIRS:
+        r = rev[indices[:, 0] + di, indices[:, 1] + dj]
+        out[name] = np.where(r != 0, r, n + 1).astype(np.int64)
+    return out
 
 
 def build_domain_network(ldd, indices, d1, min_sto, nthreads, streamorder=None, pits_mask=None):

@@ -46,7 +46,10 @@ class _Cfg(C.Structure):
                 ("nthreads", C.c_int32),
                 ("dt_land", C.c_double), ("dt_river", C.c_double), ("dt_ssf", C.c_double),
                 ("ssf_alpha_coefficient", C.c_double), ("fp_levels", C.c_int32),
-                ("fp_depth", C.c_double * 16)]
+                ("fp_depth", C.c_double * 16),
+                ("land_routing", C.c_int32), ("li_land_froude_limit", C.c_int32),
+                ("li_land_alpha", C.c_double), ("li_land_theta", C.c_double),
+                ("li_land_h_thresh", C.c_double)]
 
 
 def lib(variant: str = ""):
@@ -83,6 +86,30 @@ def lib(variant: str = ""):
                   "wfo_river_channel_floodplain_exchange", "wfo_update_floodplain_model"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_double]
             getattr(L, f).restype = None
+        # 2-D local-inertial overland flow (test hooks of the reference's unit tests)
+        L.wfo_lil_stable_timestep.argtypes = [C.c_void_p]
+        L.wfo_lil_stable_timestep.restype = C.c_double
+        L.wfo_lil_update_directional_flow.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int]
+        L.wfo_lil_update_directional_flow.restype = None
+        for f in ("wfo_lil_compute_river_storage_change", "wfo_lil_compute_land_storage_change"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int64, C.c_double]
+            getattr(L, f).restype = C.c_double
+        L.wfo_lil_compute_water_depths.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_int64,
+                                                   C.POINTER(C.c_double)]
+        L.wfo_lil_compute_water_depths.restype = None
+        for f in ("wfo_lil_update_river_and_land_storage_and_depth",
+                  "wfo_lil_update_land_storage_and_depth"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int64, C.c_double]
+            getattr(L, f).restype = None
+        for f in ("wfo_lil_update_fluxes", "wfo_lil_update_water_depth",
+                  "wfo_lil_update_overland_flow_model"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_double]
+            getattr(L, f).restype = None
+        for f in ("wfo_lil_update_inflow_reservoir", "wfo_update_bc_overland_flow_model"):
+            getattr(L, f).argtypes = [C.c_void_p]
+            getattr(L, f).restype = None
+        L.wfo_local_inertial_flow_rect.argtypes = [C.c_double] * 10 + [C.c_int, C.c_double]
+        L.wfo_local_inertial_flow_rect.restype = C.c_double
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.wfo_get_stats.restype = None
         L.wfo_set_num_threads.argtypes = [C.c_int]
@@ -150,7 +177,8 @@ ZERO_DEFAULTS = (
 VALUE_DEFAULTS = {"f_infiltration_reduction": 1.0, "soil_surface_temperature": 10.0 + 273.15}
 
 INT_FIELDS = ("number_of_layers", "n_unsatlayers", "nlayers_kv", "river_land_indices",
-              "reservoir_river_indices")
+              "reservoir_river_indices", "edge_x_up", "edge_x_down", "edge_y_up", "edge_y_down",
+              "land_river_indices")
 # reservoir defaults (reservoir.jl:200-272): cumulative / average variables start at zero
 ZERO_DEFAULTS = ZERO_DEFAULTS + (
     "fp_h", "fp_storage", "fp_q", "fp_q_cumulative", "fp_q_average", "fp_error",
@@ -158,7 +186,11 @@ ZERO_DEFAULTS = ZERO_DEFAULTS + (
     "fp_qin_cumulative", "fp_qin_average", "riv_floodplain_water_exchange",
     "res_inflow_cumulative", "res_inflow_average", "res_external_inflow",
     "res_actual_external_abstraction_cumulative", "res_actual_external_abstraction_average",
-    "res_outflow_cumulative", "res_outflow_average", "res_actevap_cumulative")
+    "res_outflow_cumulative", "res_outflow_average", "res_actevap_cumulative",
+    # LocalInertialOverlandFlowVariables / BC (surface_staggered_scheme.jl:840-865,963-968)
+    "li_land_runoff", "li_land_qx0", "li_land_qy0", "li_land_qx", "li_land_qy",
+    "li_land_qx_cumulative", "li_land_qy_cumulative", "li_land_qx_average", "li_land_qy_average",
+    "li_land_error")
 
 
 def call_out(fn_name, nout, *args):
@@ -199,6 +231,11 @@ class OracleModel:
             setattr(c, k, int(cfg.get(k, 0)))
         c.li_alpha = float(cfg.get("li_alpha", 0.7))
         c.li_h_thresh = float(cfg.get("li_h_thresh", 1.0e-3))
+        c.land_routing = int(cfg.get("land_routing", 0))
+        c.li_land_froude_limit = int(cfg.get("li_land_froude_limit", 1))
+        c.li_land_alpha = float(cfg.get("li_land_alpha", 0.7))
+        c.li_land_theta = float(cfg.get("li_land_theta", 1.0))
+        c.li_land_h_thresh = float(cfg.get("li_land_h_thresh", 1.0e-3))
         c.nthreads = int(cfg.get("nthreads", 0))
         c.dt_land = float(cfg.get("dt_land", 3600.0))
         c.dt_river = float(cfg.get("dt_river", 900.0))
@@ -211,7 +248,8 @@ class OracleModel:
         P = max(len(fp_depth), 1)
         self.cfg = dict(cfg)
         self.f = {}
-        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,), 4: (nres,), 5: (nriv, P)}
+        n6 = n if int(cfg.get("land_routing", 0)) == 1 else 0
+        shapes = {0: (n,), 1: (n, N), 2: (n, N + 1), 3: (nriv,), 4: (nres,), 5: (nriv, P), 6: (n6,)}
         for name, kind in field_table():
             if name in fields and fields[name] is not None:
                 a = np.ascontiguousarray(np.array(fields[name], dtype=np.float64, copy=True))
@@ -226,6 +264,9 @@ class OracleModel:
             L.wfo_set_ptr(self.h, name.encode(), a.ctypes.data)
         for name in INT_FIELDS:
             size = {"river_land_indices": nriv, "reservoir_river_indices": nres}.get(name, n)
+            if name.startswith("edge_") or name == "land_river_indices":
+                if name not in fields:      # only the 2-D local-inertial overland flow reads them
+                    continue
             if name in fields and fields[name] is not None:
                 a = np.ascontiguousarray(np.array(fields[name], dtype=np.int64, copy=True))
             else:

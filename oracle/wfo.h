@@ -24,7 +24,8 @@
 #include <stdint.h>
 
 /* kind: 0 = land scalar (n), 1 = land layered (n*N), 2 = land layered+1 (n*(N+1)),
- *       3 = river scalar (nriv), 4 = reservoir scalar (nres) */
+ *       3 = river scalar (nriv), 4 = reservoir scalar (nres), 5 = river x floodplain level,
+ *       6 = land scalar of the local-inertial overland flow (n with land_routing = 1, else 0) */
 #define WFO_FIELDS(X) \
   /* forcing (forcing.jl:2-10) */ \
   X(precipitation, 0) X(potential_evaporation, 0) X(temperature, 0) \
@@ -129,7 +130,19 @@
   X(res_actual_external_abstraction_cumulative, 4) X(res_actual_external_abstraction_average, 4) \
   X(res_precipitation, 4) X(res_evaporation, 4) X(res_waterlevel, 4) X(res_storage, 4) \
   X(res_outflow, 4) X(res_outflow_cumulative, 4) X(res_outflow_average, 4) X(res_outflow_obs, 4) \
-  X(res_actevap_cumulative, 4)
+  X(res_actevap_cumulative, 4) \
+  /* 2-D local-inertial overland flow (land_routing = "local_inertial"): \
+   * LocalInertialOverlandFlowParameters / Variables / BC (surface_staggered_scheme.jl:840-891, \
+   * 963-968) and x_length / y_length of LandParameters (domain.jl). The reference's flow vectors \
+   * hold n + 1 entries whose last one stays 0 (the edge "outside"); here they hold n and index \
+   * n reads as 0. The model's h and storage live in olf_h / olf_storage \
+   * (overland_flow.variables.h / .storage whatever the routing method). */ \
+  X(li_land_xwidth_at_edge, 6) X(li_land_ywidth_at_edge, 6) X(li_land_zx_max_at_edge, 6) \
+  X(li_land_zy_max_at_edge, 6) X(li_land_mannings_n_sq_at_edge, 6) X(li_land_z, 6) \
+  X(li_land_x_length, 6) X(li_land_y_length, 6) X(li_land_runoff, 6) \
+  X(li_land_qx0, 6) X(li_land_qy0, 6) X(li_land_qx, 6) X(li_land_qy, 6) \
+  X(li_land_qx_cumulative, 6) X(li_land_qy_cumulative, 6) X(li_land_qx_average, 6) \
+  X(li_land_qy_average, 6) X(li_land_error, 6)
 
 /* Per-domain network artefacts needed to walk the routing in the reference's order
  * (network.jl:48-81): all 0-based here. */
@@ -168,6 +181,12 @@ typedef struct {
   double dt_land, dt_river, dt_ssf, ssf_alpha_coefficient;
   int32_t fp_levels;          /* floodplain_1d__flag: flood depths of the profile, 0 = none */
   double fp_depth[16];        /* profile.depth                                          */
+  /* land_routing = "local_inertial" (with river_routing = "local_inertial"): 2-D overland flow */
+  int32_t land_routing;       /* 0 kinematic_wave, 1 local_inertial                     */
+  int32_t li_land_froude_limit; /* land_surface_water_flow__froude_limit_flag           */
+  double li_land_alpha;       /* land_local_inertial_flow__alpha_coefficient (0.7)      */
+  double li_land_theta;       /* land_local_inertial_flow__theta_coefficient (1.0)      */
+  double li_land_h_thresh;    /* land_surface_water_flow_threshold__depth (1e-3)        */
 } wfo_config;
 
 typedef struct wfo_model {
@@ -181,6 +200,9 @@ typedef struct wfo_model {
   int64_t* river_land_indices;/* nriv, 0-based land index of each river cell */
   int64_t* reservoir_river_indices; /* nres, 0-based river node of each reservoir     */
   int64_t* riv_reservoir;     /* nriv: NetworkRiver.reservoir_indices - 1 (-1 = none), derived */
+  /* EdgeConnectivity of the land network (network.jl:27-33,136-153), 0-based, n = no neighbour */
+  int64_t *edge_x_up, *edge_x_down, *edge_y_up, *edge_y_down;
+  int64_t* land_river_indices;/* n: NetworkLand.river_indices - 1 (-1: the cell holds no river) */
   int64_t* newton_trace_land; /* n / nriv or NULL: Newton iterations of kinematic_wave per node, */
   int64_t* newton_trace_river;/* summed over the sub-steps (iteration-count parity tests)       */
   wfo_network land, river;
@@ -227,6 +249,27 @@ void wfo_li_update_bc_reservoir_model(wfo_model*, double dt_s);
 void wfo_li_update_water_depth_and_storage(wfo_model*, double dt_s);
 void wfo_li_update_floodplain_flow(wfo_model*, double dt_s);
 void wfo_li_update_floodplain_water_depth_and_storage(wfo_model*, double dt_s);
+/* 2-D local-inertial overland flow coupled to the local-inertial river (surface_staggered_scheme.jl):
+ * stable_timestep (:1022-1043), update_directional_flow! (:1201-1271; i 0-based),
+ * local_inertial_update_fluxes! (:1276-1295), update_inflow_reservoir! (:1301-1319),
+ * local_inertial_update_water_depth! (:1520-1546) and its per-cell parts (:1325-1514),
+ * update_bc_overland_flow_model! (:1080-1097), update_overland_flow_model! (:1153-1194) */
+double wfo_lil_stable_timestep(wfo_model*);
+void wfo_lil_update_directional_flow(wfo_model*, int64_t i, double dt_s, int is_x_direction);
+void wfo_lil_update_fluxes(wfo_model*, double dt_s);
+void wfo_lil_update_inflow_reservoir(wfo_model*);
+double wfo_lil_compute_river_storage_change(wfo_model*, int64_t i, double dt_s);
+double wfo_lil_compute_land_storage_change(wfo_model*, int64_t i, double dt_s);
+void wfo_lil_compute_water_depths(wfo_model*, double total_storage, int64_t river_idx, int64_t i,
+                                  double out[3]);
+void wfo_lil_update_river_and_land_storage_and_depth(wfo_model*, int64_t i, double dt_s);
+void wfo_lil_update_land_storage_and_depth(wfo_model*, int64_t i, double dt_s);
+void wfo_lil_update_water_depth(wfo_model*, double dt_s);
+void wfo_update_bc_overland_flow_model(wfo_model*);
+void wfo_lil_update_overland_flow_model(wfo_model*, double dt);
+double wfo_local_inertial_flow_rect(double theta, double q0, double qd, double qu, double zs0,
+                                    double zs1, double hf, double width, double length,
+                                    double mannings_n_sq, int froude_limit, double dt);
 void wfo_river_channel_floodplain_exchange(wfo_model*, double dt_s);
 void wfo_update_floodplain_model(wfo_model*, double dt_s);
 void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182 */

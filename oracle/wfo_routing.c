@@ -1146,8 +1146,259 @@ static void li_update_river_flow_model(wfo_model* m, double dt) {
   }
 }
 
-/* surface_routing.jl:7-46 */
+/* ---------------------------------------------------------------------------------------- */
+/* 2-D local-inertial overland flow coupled to the local-inertial river                        */
+/*                                          routing/surface/surface_staggered_scheme.jl:840-1546 */
+/* ---------------------------------------------------------------------------------------- */
+/* The reference's flow vectors hold n + 1 entries, the last one (the edge to "outside") stays 0 */
+static inline double lil_at(const double* q, int64_t idx, int64_t n) { return idx < n ? q[idx] : 0.0; }
+
+/* local_inertial_flow(theta, q0, qd, qu, zs0, zs1, hf, width, length, mannings_n_sq,
+ * froude_limit, dt): rectangular area, de Almeida et al. (2012)      surface_process.jl:123-159 */
+double wfo_local_inertial_flow_rect(double theta, double q0, double qd, double qu, double zs0,
+                                    double zs1, double hf, double width, double length,
+                                    double mannings_n_sq, int froude_limit, double dt) {
+  const double slope = (zs1 - zs0) / length;
+  const double pow_hf = cbrt(hf * hf * hf * hf * hf * hf * hf);
+  double q = (((theta * q0 + 0.5 * (1.0 - theta) * (qu + qd)) - WFO_G * hf * width * dt * slope) /
+              (1.0 + WFO_G * dt * mannings_n_sq * fabs(q0) / (pow_hf * width)));
+  if (froude_limit) {
+    const double fr = (q / width / hf) / sqrt(WFO_G * hf);
+    if (fabs(fr) > 1.0 && q > 0.0) q = hf * sqrt(WFO_G * hf) * width;
+    else if (fabs(fr) > 1.0 && q < 0.0) q = -hf * sqrt(WFO_G * hf) * width;
+  }
+  return q;
+}
+
+/* stable_timestep(::OverlandFlowModel{<:LocalInertial}, ::LandParameters)          :1022-1043 */
+double wfo_lil_stable_timestep(wfo_model* m) {
+  double dt_min = INFINITY;
+  for (int64_t i = 0; i < m->cfg.n; ++i) {
+    if (m->land_river_indices[i] >= 0) continue;                 /* river_location[i] != 0 */
+    const double dt = m->cfg.li_land_alpha * jl_min(m->li_land_x_length[i], m->li_land_y_length[i]) /
+                      sqrt(WFO_G * m->olf_h[i]);
+    dt_min = dt < dt_min ? dt : dt_min;
+  }
+  return isinf(dt_min) ? 60.0 : dt_min;
+}
+
+/* update_directional_flow!(model, domain, i, dt, is_x_direction)                   :1201-1271 */
+void wfo_lil_update_directional_flow(wfo_model* m, int64_t i, double dt, int is_x) {
+  const int64_t n = m->cfg.n;
+  const int64_t up = is_x ? m->edge_x_up[i] : m->edge_y_up[i];
+  const int64_t down = is_x ? m->edge_x_down[i] : m->edge_y_down[i];
+  const double width_at_edge = is_x ? m->li_land_ywidth_at_edge[i] : m->li_land_xwidth_at_edge[i];
+  const double z_max_at_edge = is_x ? m->li_land_zx_max_at_edge[i] : m->li_land_zy_max_at_edge[i];
+  const double* length_vec = is_x ? m->li_land_x_length : m->li_land_y_length;
+  double* q_current = is_x ? m->li_land_qx : m->li_land_qy;
+  const double* q_prev = is_x ? m->li_land_qx0 : m->li_land_qy0;
+  double* q_cumulative = is_x ? m->li_land_qx_cumulative : m->li_land_qy_cumulative;
+  if (up < n && width_at_edge != 0.0) {
+    const double zs_current = m->li_land_z[i] + m->olf_h[i];
+    const double zs_upstream = m->li_land_z[up] + m->olf_h[up];
+    const double zs_max_at_edge = jl_max(zs_current, zs_upstream);
+    const double water_depth_at_edge = (zs_max_at_edge - z_max_at_edge);
+    if (water_depth_at_edge > m->cfg.li_land_h_thresh) {
+      const double length_at_edge = 0.5 * (length_vec[i] + length_vec[up]);
+      double q = wfo_local_inertial_flow_rect(m->cfg.li_land_theta, q_prev[i], lil_at(q_prev, down, n),
+                                              lil_at(q_prev, up, n), zs_current, zs_upstream,
+                                              water_depth_at_edge, width_at_edge, length_at_edge,
+                                              m->li_land_mannings_n_sq_at_edge[i],
+                                              m->cfg.li_land_froude_limit, dt);
+      if (m->olf_h[i] <= 0.0) q = jl_min(q, 0.0);
+      if (m->olf_h[up] <= 0.0) q = jl_max(q, 0.0);
+      q_current[i] = q;
+    } else {
+      q_current[i] = 0.0;
+    }
+    q_cumulative[i] += q_current[i] * dt;
+  }
+}
+
+/* local_inertial_update_fluxes!                                                    :1276-1295 */
+void wfo_lil_update_fluxes(wfo_model* m, double dt) {
+  const int64_t n = m->cfg.n;
+  PFOR for (int64_t i = 0; i < n; ++i) { m->li_land_qx0[i] = m->li_land_qx[i]; m->li_land_qy0[i] = m->li_land_qy[i]; }
+  PFOR for (int64_t i = 0; i < n; ++i) {
+    wfo_lil_update_directional_flow(m, i, dt, 1);
+    wfo_lil_update_directional_flow(m, i, dt, 0);
+  }
+}
+
+/* qx[ind_x_down] - qx[i] + qy[ind_y_down] - qy[i] as the reference writes it (:1343-1345,1433-1434) */
+static inline double lil_net_land_flow(const wfo_model* m, int64_t i) {
+  const int64_t n = m->cfg.n;
+  return lil_at(m->li_land_qx, m->edge_x_down[i], n) - m->li_land_qx[i] +
+         lil_at(m->li_land_qy, m->edge_y_down[i], n) - m->li_land_qy[i];
+}
+
+/* update_inflow_reservoir!                                                         :1301-1319 */
+void wfo_lil_update_inflow_reservoir(wfo_model* m) {
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {
+    const int64_t j = m->river_land_indices[m->reservoir_river_indices[i]];
+    m->res_inflow_overland[i] = m->li_land_runoff[j] + (lil_net_land_flow(m, j));
+  }
+}
+
+/* compute_river_storage_change                                                     :1325-1352 */
+double wfo_lil_compute_river_storage_change(wfo_model* m, int64_t i, double dt) {
+  const wfo_network* nw = &m->river;
+  const int64_t r = m->land_river_indices[i];
+  double q_src = 0.0;     /* sum_at(q, edges_at_node.src[r]): the edges entering the node */
+  for (int64_t u = nw->in_ptr[r]; u < nw->in_ptr[r + 1]; ++u) q_src += m->riv_q[nw->in_idx[u]];
+  const double q_dst = li_dst(m, r) == -1 ? 0.0 : 0.0 + m->riv_q[r];
+  const double net_river_flow = q_src - q_dst;
+  const double net_land_flow = lil_net_land_flow(m, i);
+  const double net_flow = net_river_flow + net_land_flow + m->li_land_runoff[i] - m->riv_abstraction[r];
+  return net_flow * dt;
+}
+
+/* compute_external_inflow -> (inflow, abstraction_to_add)                          :1359-1382 */
+static void lil_compute_external_inflow(const wfo_model* m, int64_t i, int64_t r, double dt, double out[2]) {
+  if (m->riv_external_inflow[r] < 0.0) {
+    const double available_volume = m->olf_storage[i] >= m->li_bankfull_storage[r]
+                                        ? m->li_bankfull_storage[r] : m->riv_storage[r];
+    const double abstraction = jl_min(-m->riv_external_inflow[r], available_volume / dt * 0.80);
+    out[0] = -abstraction; out[1] = abstraction;
+  } else {
+    out[0] = m->riv_external_inflow[r]; out[1] = 0.0;
+  }
+}
+
+/* compute_water_depths -> (river_h, land_h, river_storage)                         :1388-1416 */
+void wfo_lil_compute_water_depths(wfo_model* m, double total_storage, int64_t r, int64_t i, double out[3]) {
+  if (total_storage >= m->li_bankfull_storage[r]) {
+    const double river_h = m->li_bankfull_depth[r] + (total_storage - m->li_bankfull_storage[r]) /
+                                                         (m->li_land_x_length[i] * m->li_land_y_length[i]);
+    out[0] = river_h;
+    out[1] = river_h - m->li_bankfull_depth[r];
+    out[2] = river_h * m->riv_flow_length[r] * m->riv_flow_width[r];
+  } else {
+    out[0] = total_storage / (m->riv_flow_length[r] * m->riv_flow_width[r]);
+    out[1] = 0.0;
+    out[2] = total_storage;
+  }
+}
+
+/* compute_land_storage_change                                                      :1422-1437 */
+double wfo_lil_compute_land_storage_change(wfo_model* m, int64_t i, double dt) {
+  return (lil_net_land_flow(m, i) + m->li_land_runoff[i]) * dt;
+}
+
+/* update_river_and_land_storage_and_depth!                                         :1443-1485 */
+void wfo_lil_update_river_and_land_storage_and_depth(wfo_model* m, int64_t i, double dt) {
+  const int64_t r = m->land_river_indices[i];
+  m->olf_storage[i] += wfo_lil_compute_river_storage_change(m, i, dt);
+  if (m->olf_storage[i] < 0.0) {
+    m->li_land_error[i] += fabs(m->olf_storage[i]);
+    m->olf_storage[i] = 0.0;
+  }
+  double io[2], d[3];
+  lil_compute_external_inflow(m, i, r, dt, io);
+  m->olf_storage[i] += io[0] * dt;
+  m->riv_actual_external_abstraction_cumulative[r] += io[1] * dt;
+  wfo_lil_compute_water_depths(m, m->olf_storage[i], r, i, d);
+  m->riv_h[r] = d[0];
+  m->olf_h[i] = d[1];
+  m->riv_storage[r] = d[2];
+}
+
+/* update_land_storage_and_depth!                                                   :1491-1514 */
+void wfo_lil_update_land_storage_and_depth(wfo_model* m, int64_t i, double dt) {
+  m->olf_storage[i] += wfo_lil_compute_land_storage_change(m, i, dt);
+  if (m->olf_storage[i] < 0.0) {
+    m->li_land_error[i] += fabs(m->olf_storage[i]);
+    m->olf_storage[i] = 0.0;
+  }
+  m->olf_h[i] = m->olf_storage[i] / (m->li_land_x_length[i] * m->li_land_y_length[i]);
+}
+
+/* local_inertial_update_water_depth!                                               :1520-1546 */
+void wfo_lil_update_water_depth(wfo_model* m, double dt) {
+  PFOR for (int64_t i = 0; i < m->cfg.n; ++i) {
+    const int64_t r = m->land_river_indices[i];
+    if (r >= 0) {
+      if (!(m->cfg.nres > 0 && m->riv_reservoir[r] >= 0))      /* !reservoir_outlet[i] */
+        wfo_lil_update_river_and_land_storage_and_depth(m, i, dt);
+    } else {
+      wfo_lil_update_land_storage_and_depth(m, i, dt);
+    }
+  }
+}
+
+/* update_bc_overland_flow_model!                                                   :1080-1097 */
+void wfo_update_bc_overland_flow_model(wfo_model* m) {
+  PFOR for (int64_t i = 0; i < m->cfg.n; ++i)
+    m->li_land_runoff[i] = (m->net_runoff[i] + m->net_runoff_river[i]) * m->area[i];
+  for (int64_t r = 0; r < m->cfg.nriv; ++r) {
+    const int64_t li = m->river_land_indices[r];
+    m->li_land_runoff[li] += m->ssf_to_river_average[li];      /* get_flux_to_river  lsf.jl:346 */
+  }
+}
+
+/* update_overland_flow_model!(overland, river, domain, clock, dt; update_h = false) :1153-1194 */
+void wfo_lil_update_overland_flow_model(wfo_model* m, double dt) {
+  const int64_t n = m->cfg.n, nriv = m->cfg.nriv;
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {                  /* set_reservoir_vars! */
+    m->res_inflow_cumulative[i] = 0.0;
+    m->res_actual_external_abstraction_cumulative[i] = 0.0;
+    m->res_outflow_cumulative[i] = 0.0;
+    m->res_actevap_cumulative[i] = 0.0;
+  }
+  PFOR for (int64_t i = 0; i < nriv; ++i) {                    /* set_flow_vars!(river) */
+    m->riv_q_cumulative[i] = 0.0;
+    m->riv_actual_external_abstraction_cumulative[i] = 0.0;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {                       /* set_flow_vars!(overland) :1127-1132 */
+    m->li_land_qx_cumulative[i] = 0.0;
+    m->li_land_qy_cumulative[i] = 0.0;
+  }
+  double t = 0.0;
+  m->substeps_river = 0;
+  while (t < dt) {
+    const double dt_river = wfo_li_stable_timestep(m);
+    const double dt_land = wfo_lil_stable_timestep(m);
+    double dt_s = jl_min(dt_river, dt_land);
+    dt_s = check_timestepsize(dt_s, t, dt);
+    wfo_lil_update_fluxes(m, dt_s);
+    wfo_lil_update_inflow_reservoir(m);
+    /* staggered_scheme_river_update!(river, domain, dt_s, update_h = false)      :762-794 */
+    wfo_li_update_river_channel_flow(m, dt_s);
+    wfo_li_update_bc_reservoir_model(m, dt_s);
+    wfo_lil_update_water_depth(m, dt_s);
+    t += dt_s;
+    m->substeps_river++;
+  }
+  m->substeps_land = m->substeps_river;
+  PFOR for (int64_t i = 0; i < nriv; ++i) {                    /* average_flow_vars!(river) */
+    m->riv_q_average[i] = m->riv_q_cumulative[i] / dt;
+    m->riv_actual_external_abstraction_average[i] =
+        m->riv_actual_external_abstraction_cumulative[i] / dt;
+  }
+  PFOR for (int64_t i = 0; i < n; ++i) {                       /* average_flow_vars!(overland) :1138-1147 */
+    m->li_land_qx_average[i] = m->li_land_qx_cumulative[i] / dt;
+    m->li_land_qy_average[i] = m->li_land_qy_cumulative[i] / dt;
+  }
+  for (int64_t i = 0; i < m->cfg.nres; ++i) {                  /* average_reservoir_vars! */
+    m->res_outflow_average[i] = m->res_outflow_cumulative[i] / dt;
+    m->res_inflow_average[i] = m->res_inflow_cumulative[i] / dt;
+    m->res_actual_external_abstraction_average[i] =
+        m->res_actual_external_abstraction_cumulative[i] / dt;
+  }
+}
+
+/* surface_routing.jl:7-46; :62-86 with local-inertial land AND river routing */
 void wfo_surface_routing(wfo_model* m, double dt) {
+  if (m->cfg.land_routing == 1) {
+    wfo_update_bc_overland_flow_model(m);
+    /* update_inflow!(reservoir, river_flow, subsurface_flow, network)  surface_staggered_scheme.jl:1103-1114 */
+    for (int64_t i = 0; i < m->cfg.nres; ++i) {
+      const int64_t li = m->river_land_indices[m->reservoir_river_indices[i]];
+      m->res_inflow_subsurface[i] = m->ssf_q_average[li] + m->ssf_to_river_average[li];
+    }
+    wfo_lil_update_overland_flow_model(m, dt);
+    return;
+  }
   wfo_update_lateral_inflow_overland(m);
   wfo_update_overland_flow_model(m, dt);
   wfo_update_lateral_inflow_river(m);

@@ -51,6 +51,11 @@ int wfo_set_iptr(wfo_model* m, const char* name, int64_t* p) {
   }
   if (!strcmp(name, "newton_trace_river")) { m->newton_trace_river = p; return 0; }
   if (!strcmp(name, "river_land_indices")) { m->river_land_indices = p; return 0; }
+  if (!strcmp(name, "edge_x_up")) { m->edge_x_up = p; return 0; }
+  if (!strcmp(name, "edge_x_down")) { m->edge_x_down = p; return 0; }
+  if (!strcmp(name, "edge_y_up")) { m->edge_y_up = p; return 0; }
+  if (!strcmp(name, "edge_y_down")) { m->edge_y_down = p; return 0; }
+  if (!strcmp(name, "land_river_indices")) { m->land_river_indices = p; return 0; }
   return -1;
 }
 void wfo_set_network(wfo_model* m, int which, const wfo_network* net) {

@@ -61,6 +61,13 @@ def make_oracle(cfg, dom, fields, nets=None, variant=""):
     f["river_land_indices"] = dom["river_land_indices"] - 1
     if cfg.get("nres", 0):
         f["reservoir_river_indices"] = dom["reservoir_river_indices"] - 1
+    if cfg.get("land_routing", 0) == 1:   # the oracle's OWN EdgeConnectivity (oracle/network.py)
+        e = onw.edge_connectivity(dom["indices"], dom["d1"], dom["d2"])
+        for k in ("x_up", "x_down", "y_up", "y_down"):
+            f["edge_" + k] = e["ind_" + k] - 1
+        lri = np.full(len(dom["ldd"]), -1, dtype=np.int64)     # network_land.river_indices
+        lri[dom["river_land_indices"] - 1] = np.arange(len(dom["river_land_indices"]))
+        f["land_river_indices"] = lri
     return orc.OracleModel(cfg, f, land, river, variant=variant)
 
 
@@ -306,8 +313,13 @@ def compare_models(gpu, ora, rtol=RTOL, skip=(), verbose=False, names=None, outl
     rep = Report()
     if names is None:
         names = gpu.field_names() if hasattr(gpu, "field_names") else list(ora.f)
+    if cfg.get("land_routing", 0) == 1:
+        # LocalInertialOverlandFlow has no kinematic-wave variables (surface_staggered_scheme.jl:
+        # 840-865): of the olf_* fields only h and storage exist in the reference's model
+        skip = tuple(skip) + tuple(n for n in names if n.startswith("olf_") and
+                                   n not in ("olf_h", "olf_storage"))
     for name in names:
-        if name in skip or name == "river_land_indices":
+        if name in skip or name in ("river_land_indices", "land_river_indices") or name.startswith("edge_"):
             continue
         g = gget(name)
         o = oget(name)

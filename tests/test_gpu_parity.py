@@ -267,6 +267,41 @@ def test_local_inertial_river_with_floodplain(pkg, reservoirs):
     _close(gpu)
 
 
+@pytest.mark.parametrize("reservoirs,fine_grained", [(0, False), (3, False), (3, True)])
+def test_local_inertial_land_and_river_flow(pkg, reservoirs, fine_grained):
+    """land_routing = river_routing = "local_inertial" (BASELINE config #4): the 2-D local-inertial
+    overland flow on the staggered grid coupled to the local-inertial river with its subgrid
+    channel -- dt_s = min(stable_timestep(river), stable_timestep(land)), x / y edge flows
+    (de Almeida et al. 2012), overland inflow of the reservoirs, river edge flow, reservoirs, water
+    depth and storage of land and river cells with bankfull spill
+    (surface_staggered_scheme.jl:1022-1043,1080-1097,1153-1546; surface_process.jl:123-159;
+    surface_routing.jl:62-86) -- all sub-steps of a model step inside one persistent kernel. The
+    EdgeConnectivity artefact is bit-exact; tolerances as for the river alone (an explicit scheme
+    with wet/dry thresholds: the oracle against itself on a +-1 ulp libm needs them too)."""
+    from oracle import network as onw
+    gpu, ora, cfg = parity.run_pair(pkg, 70, 110, steps=4, seed=43, river_routing=1, land_routing=1,
+                                    reservoirs=reservoirs, fine_grained=fine_grained)
+    assert cfg["land_routing"] == 1 and cfg["li_land_theta"] == 0.9
+    dom = pkg.synthetic.make_basin(70, 110, seed=43, river_routing=1, land_routing=1,
+                                   reservoirs=reservoirs)[1]
+    e = onw.edge_connectivity(dom["indices"], dom["d1"], dom["d2"])
+    for k in ("x_up", "x_down", "y_up", "y_down"):
+        assert np.array_equal(gpu.artifact("land", "edge_" + k), e["ind_" + k]), k
+    rep = parity.compare_models(gpu, ora, outliers=(1.0, 1e-5))
+    st, o = gpu.stats(), ora.newton_stats()
+    assert abs(st["substeps_river"] - o["substeps_river"]) <= 1 and o["substeps_river"] > 20
+    assert st["substeps_land"] == st["substeps_river"]
+    wet = int((ora.f["olf_h"] > 0.0).sum())
+    assert wet > 100 and float(np.max(np.abs(ora.f["li_land_qx_average"]))) > 0.0
+    assert float(np.max(np.abs(ora.f["li_land_qy_average"]))) > 0.0
+    over_bank = int((ora.f["olf_h"][dom["river_land_indices"] - 1] > 0.0).sum())
+    assert over_bank > 0                    # the subgrid channels do spill onto their cells
+    n_out = sum(v.get("outliers", 0) for v in rep.values())
+    print(rep.summary(), "sub-steps", st["substeps_river"], o["substeps_river"], "wet cells", wet,
+          "river cells over bank", over_bank, "threshold outliers", n_out)
+    _close(gpu)
+
+
 @pytest.mark.parametrize("adaptive", [False, True])
 def test_kinematic_wave_river_with_floodplain(pkg, adaptive):
     """floodplain_1d__flag with the kinematic-wave river: per sub-step the channel-floodplain

@@ -162,6 +162,55 @@ def test_oracle_water_balance_and_determinism(pkg):
         assert np.array_equal(ora1.f[k], f[k]), k
 
 
+def test_edge_connectivity_bit_exact(pkg):
+    """EdgeConnectivity of the land network (network.jl:136-153), host C++ against the oracle's
+    restatement, on a masked raster."""
+    from oracle import network as onw
+    mask = np.ones((37, 53), dtype=bool)
+    mask[:5, :7] = False
+    mask[20:, 40:] = False
+    mask[10:14, 22:30] = False
+    cfg, dom, _ = pkg.synthetic.make_basin(37, 53, seed=4, mask=mask)
+    art = pkg.build_network_artifacts(dict(cfg, land_routing=1, river_routing=1), dom)["land"]
+    e = onw.edge_connectivity(dom["indices"], dom["d1"], dom["d2"])
+    n = cfg["n"]
+    for k in ("x_up", "x_down", "y_up", "y_down"):
+        assert np.array_equal(art["edge_" + k], e["ind_" + k]), k
+        assert int((e["ind_" + k] == n + 1).sum()) > 0
+    # x_up and x_down are inverse to each other where both cells exist
+    xu = e["ind_x_up"]
+    has = xu <= n
+    assert np.array_equal(e["ind_x_down"][xu[has] - 1], np.nonzero(has)[0] + 1)
+
+
+def test_oracle_local_inertial_land_conserves_water(pkg):
+    """2-D local-inertial overland flow coupled to the river (the oracle itself): what the cells
+    hold changes by the runoff they receive, minus what leaves through the pits' ghost edges, plus
+    what the negative-storage clip adds (li_land_error) -- every other flux is internal. The
+    reference's data-free invariant (mass_balance.jl:61-62 pairs the two routing models)."""
+    cfg, dom, fields = pkg.synthetic.make_basin(40, 56, seed=11, river_routing=1, land_routing=1)
+    dt = cfg["dt"]
+    ora = parity.make_oracle(cfg, dom, fields)
+    down_r = np.asarray(parity.oracle_networks(cfg, dom)[1]["graph"].down)
+    pits = down_r == 0
+    for step in range(3):
+        p, e, t = pkg.synthetic.make_forcing(11, step, dom["gid"], dt)
+        ora.f["precipitation"][:], ora.f["potential_evaporation"][:], ora.f["temperature"][:] = p, e, t
+        s0, err0 = ora.f["olf_storage"].sum(), ora.f["li_land_error"].sum()
+        ora.update_model(dt)
+        f = ora.f
+        gained = f["li_land_runoff"].sum() * dt - f["riv_q_cumulative"][pits].sum() \
+            + (f["li_land_error"].sum() - err0)
+        assert abs((f["olf_storage"].sum() - s0) - gained) <= 1e-9 * max(abs(gained), f["olf_storage"].sum())
+    assert ora.newton_stats()["substeps_river"] > 20
+    assert (f["olf_h"] > 0).sum() > 50 and np.abs(f["li_land_qx_average"]).max() > 0
+    # river cells: land h is the depth above bankfull, river storage never exceeds the cell's
+    rl = dom["river_land_indices"] - 1
+    over = f["olf_h"][rl] > 0
+    assert np.all(f["riv_h"][over] >= f["li_bankfull_depth"][over])
+    assert np.all(f["riv_h"][~over] <= f["li_bankfull_depth"][~over] * (1 + 1e-12))
+
+
 def test_create_rejects_bad_arguments_before_touching_the_device(pkg):
     """Argument validation of wflowb200_create happens before any CUDA call: status
     WFLOWB200_ERR_ARG (1) and a message, never a crash (the shim turns it into error(...))."""
@@ -172,7 +221,8 @@ def test_create_rejects_bad_arguments_before_touching_the_device(pkg):
     ldd = np.ascontiguousarray(dom["ldd"], dtype=np.uint8)
     rli = np.ascontiguousarray(dom["river_land_indices"], dtype=np.int64)
     d = pkg._lib.Domain(dom["d1"], dom["d2"], idx.ctypes.data, ldd.ctypes.data, rli.ctypes.data)
-    for bad in (dict(n=0), dict(n_layers=0), dict(n_layers=9), dict(kv_profile=7)):
+    for bad in (dict(n=0), dict(n_layers=0), dict(n_layers=9), dict(kv_profile=7),
+                dict(land_routing=1), dict(land_routing=2, river_routing=1)):
         c = pkg._lib.Config()
         c.n, c.nriv, c.n_layers = cfg["n"], cfg["nriv"], cfg["n_layers"]
         for k, v in bad.items():

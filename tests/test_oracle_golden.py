@@ -680,6 +680,131 @@ def test_kinwave_river_with_floodplain_routing_process_858_987():
     assert m.f["fp_q_cumulative"] == approx(np.array([6014.835102655834, 4438.882199731312]))
 
 
+def _lil_nets(nriv_down):
+    """a river chain given by `down` (1-based, 0 = pit) and a land domain without drainage"""
+    nr = len(nriv_down)
+
+    class G:
+        down = np.array(nriv_down)
+    up_ptr, up_idx = [0], []
+    for v in range(1, nr + 1):
+        up_idx += [u + 1 for u in range(nr) if nriv_down[u] == v]
+        up_ptr.append(len(up_idx))
+    river = dict(graph=G, order=np.arange(1, nr + 1), up_ptr=np.array(up_ptr),
+                 up_idx=np.array(up_idx, dtype=np.int64), order_of_subdomains=[np.array([1])],
+                 order_subdomain=[np.arange(1, nr + 1)], subdomain_indices=[np.arange(1, nr + 1)])
+
+    class G1:
+        down = np.array([0, 0, 0])
+    land = dict(graph=G1, order=np.array([1, 2, 3]), up_ptr=np.zeros(4, np.int64),
+                up_idx=np.zeros(0, np.int64), order_of_subdomains=[np.array([1])],
+                order_subdomain=[np.array([1, 2, 3])], subdomain_indices=[np.array([1, 2, 3])])
+    return land, river
+
+
+def _as_fields(f):
+    ints = ("indices", "edge_x_up", "edge_x_down", "edge_y_up", "edge_y_down")
+    return {k: np.asarray(v, dtype=np.int64 if k.endswith(ints) else np.float64) for k, v in f.items()}
+
+
+def test_local_inertial_flow_rectangular_routing_process_1346_1373():
+    """local_inertial_flow(theta, q0, qd, qu, ...), the rectangular-area method of the overland
+    flow (surface_process.jl:123-159; de Almeida et al. 2012)."""
+    q = orc.lib().wfo_local_inertial_flow_rect(
+        1.0, 0.0001769756305800402, 0.0, 0.0, 601.4761297394623, 601.4730243288751,
+        0.00310727852479431, 620.6649135473787, 926.602742473319, 0.1773345894316103, 1,
+        49.774905820268735)
+    assert q == approx(0.00017992597962222483)
+
+
+def test_update_directional_flow_routing_process_989_1048():
+    """2-D local-inertial overland flow in the x direction at edge 2 of three cells
+    | land | land | river |: stable time step of the land cells and the edge flow. The reference's
+    flow vectors hold n + 1 entries (the last one, the edge to outside, is 0): n here."""
+    L = orc.lib()
+    land, river = _lil_nets([0])
+    f = dict(li_land_runoff=[0.0, 0.0, 0.003001456821567986],
+             li_land_ywidth_at_edge=[926.6857061478484, 869.7426481339323, 812.7995901200163],
+             li_land_zx_max_at_edge=[257.3280029296875, 232.67100524902344, 232.67100524902344],
+             li_land_mannings_n_sq_at_edge=[0.24167056670421605, 0.2883451232664811, 0.3928782408368683],
+             li_land_z=[257.3280029296875, 227.5050048828125, 232.67100524902344],
+             li_land_qx0=[0.0, -3.6332616217117395, -0.7525806207906618],
+             li_land_qx=[0.0, -3.63341089804407, -0.7526187151790501],
+             olf_h=[0.0, 1.3754708010382453, 0.11735139800699446],
+             olf_storage=[0.0, 783157.9568615163, 237954.47204911432],
+             li_land_x_length=[614.4202561305977] * 3, li_land_y_length=[926.6857061478484] * 3,
+             edge_x_up=[1, 2, 3], edge_x_down=[3, 0, 1], edge_y_up=[3, 3, 3], edge_y_down=[3, 3, 3],
+             land_river_indices=[-1, -1, 0], river_land_indices=[2],
+             riv_flow_length=[1000.0], riv_h=[0.0])
+    m = orc.OracleModel(dict(n=3, nriv=1, N=1, river_routing=1, land_routing=1, li_land_alpha=0.7,
+                             li_land_theta=1.0, li_land_h_thresh=1e-3, li_land_froude_limit=1),
+                        _as_fields(f), land, river)
+    dt = L.wfo_lil_stable_timestep(m.h)
+    assert dt == approx(117.10556654947368)
+    m.f["li_land_qx0"][:] = m.f["li_land_qx"]
+    L.wfo_lil_update_directional_flow(m.h, 1, dt, 1)
+    assert m.f["li_land_qx"][1] == approx(-3.633493490896127)
+    assert m.f["li_land_qx_cumulative"][1] == approx(-3.633493490896127 * dt)
+
+
+def test_local_inertial_update_water_depth_routing_process_1050_1187():
+    """River and land water depth and storage of the coupled local-inertial overland / river flow
+    (subgrid channel), cells | land | land | river |. The reference's single river node has one
+    entering edge (q = 56.69) and one leaving edge (q = 53.71); edge i is the edge leaving node i
+    here, so the entering edge belongs to an upstream node and the leaving one ends in the ghost
+    node of the pit."""
+    L = orc.lib()
+    land, river = _lil_nets([2, 0])
+    f = dict(li_land_qx=[0.0, -3.63341089804407, -0.7526187151790501],
+             li_land_qy=[0.0, -0.7369647824685662, 0.0],
+             olf_storage=[0.0, 783157.9568615163, 237954.47204911432],
+             olf_h=[0.0, 1.3754708010382453, 0.11735139800699446],
+             li_land_runoff=[0.0, 0.0, 0.003001456821567986],
+             li_land_x_length=[614.4202561305977] * 3, li_land_y_length=[926.6857061478484] * 3,
+             edge_x_up=[1, 2, 3], edge_x_down=[3, 0, 1], edge_y_up=[3, 3, 3], edge_y_down=[3, 3, 3],
+             land_river_indices=[-1, -1, 1], river_land_indices=[0, 2],
+             li_bankfull_storage=[1.0, 171137.5821314017], li_bankfull_depth=[1.0, 1.3683528900146484],
+             riv_q=[56.685647296907476, 53.70963118023338],
+             riv_h=[0.0, 1.485704288021643], riv_storage=[0.0, 185814.5230442402],
+             riv_flow_width=[113.88611602783203] * 2, riv_flow_length=[1098.1875] * 2,
+             riv_external_inflow=[0.0, 0.0], riv_abstraction=[0.0, 0.0], li_ghost_h=[0.0, 0.0])
+    m = orc.OracleModel(dict(n=3, nriv=2, N=1, river_routing=1, land_routing=1, li_ghost_nodes=1,
+                             li_alpha=0.7, li_land_alpha=0.7, li_land_theta=1.0,
+                             li_land_h_thresh=1e-3), _as_fields(f), land, river)
+    dt = L.wfo_li_stable_timestep(m.h)
+    assert dt == approx(201.394687315008)
+    sc = L.wfo_lil_compute_river_storage_change(m.h, 2, dt)
+    assert sc == approx(19.782071832453088)
+    river_h, land_h, river_storage = 1.4857390315391559, 0.11738614152450744, 185818.86835722585
+    out = (orc.C.c_double * 3)()
+    L.wfo_lil_compute_water_depths(m.h, m.f["olf_storage"][2] + sc, 1, 2, out)
+    assert list(out) == approx([river_h, land_h, river_storage])
+    L.wfo_lil_update_river_and_land_storage_and_depth(m.h, 2, dt)
+    assert m.f["riv_h"][1] == approx(river_h)
+    assert m.f["olf_h"][2] == approx(land_h)
+    assert m.f["riv_storage"][1] == approx(river_storage)
+    assert m.f["riv_actual_external_abstraction_cumulative"][1] == 0.0
+    assert L.wfo_lil_compute_land_storage_change(m.h, 1, dt) == approx(880.1704436259577)
+    L.wfo_lil_update_land_storage_and_depth(m.h, 1, dt)
+    assert m.f["olf_storage"][1] == approx(784038.1273051423)
+    assert m.f["olf_h"][1] == approx(1.3770166561681556)
+
+
+def test_edge_connectivity_network_136_153():
+    """EdgeConnectivity of a masked 3 x 3 raster: DIRS / NEIGHBORS order (network.jl:3,
+    connectivity.jl:61-66), n + 1 where there is no active neighbour."""
+    mask = np.array([[1, 1, 0], [1, 1, 1], [0, 1, 1]], dtype=bool)
+    idx, rev = nw.active_indices(mask)
+    e = nw.edge_connectivity(idx, 3, 3)
+    n = len(idx)
+    # column-major numbering: (1,1)=1 (2,1)=2 (1,2)=3 (2,2)=4 (3,2)=5 (2,3)=6 (3,3)=7
+    assert n == 7
+    assert list(e["ind_x_up"]) == [2, 8, 4, 5, 8, 7, 8]      # CartesianIndex(1, 0)
+    assert list(e["ind_x_down"]) == [8, 1, 8, 3, 4, 8, 6]    # CartesianIndex(-1, 0)
+    assert list(e["ind_y_up"]) == [3, 4, 8, 6, 7, 8, 8]      # CartesianIndex(0, 1)
+    assert list(e["ind_y_down"]) == [8, 8, 1, 2, 8, 4, 5]    # CartesianIndex(0, -1)
+
+
 def test_accucapacityflux_routing_process_255_288():
     """PCRaster accucapacity examples on a 6-node graph (lateral snow transport's engine)."""
     L = orc.lib()

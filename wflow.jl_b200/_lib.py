@@ -27,7 +27,10 @@ class Config(C.Structure):
                 ("river_routing", C.c_int32), ("li_froude_limit", C.c_int32),
                 ("li_ghost_nodes", C.c_int32), ("reserved_", C.c_int32),
                 ("li_alpha", C.c_double), ("li_h_thresh", C.c_double),
-                ("fp_levels", C.c_int32), ("reserved2_", C.c_int32), ("fp_depth", C.c_double * 16)]
+                ("fp_levels", C.c_int32), ("reserved2_", C.c_int32), ("fp_depth", C.c_double * 16),
+                ("land_routing", C.c_int32), ("li_land_froude_limit", C.c_int32),
+                ("li_land_alpha", C.c_double), ("li_land_theta", C.c_double),
+                ("li_land_h_thresh", C.c_double)]
 
 
 class Domain(C.Structure):
@@ -56,6 +59,8 @@ ARTIFACTS = dict(order=0, streamorder=1, upstream_ptr=2, upstream_idx=3, subdoma
                  subdomain_level_idx=5, subdomain_ptr=6, subdomain_order=7, subdomain_indices=8,
                  ldd=9, wave_level_ptr=10, wave_perm=11, wave_node_level=12, wave_chunk_ptr=13,
                  wave_chunk_outlet=14)
+# EdgeConnectivity of the land network (land_routing = 1 only)
+EDGE_ARTIFACTS = dict(edge_x_up=15, edge_x_down=16, edge_y_up=17, edge_y_down=18)
 
 
 def header_symbols():
@@ -104,7 +109,8 @@ def lib():
               "update_river_flow_model", "update_model"):
         getattr(L, "wflowb200_" + f).argtypes = [vp, dbl]
     for f in ("exchange_recharge", "update_lateral_inflow_overland", "update_lateral_inflow_river",
-              "update_inflow_reservoir", "update_total_water_storage", "synchronize"):
+              "update_inflow_reservoir", "update_total_water_storage", "synchronize",
+              "update_bc_overland_flow_model"):
         getattr(L, "wflowb200_" + f).argtypes = [vp]
     L.wflowb200_get_artifact.argtypes = [vp, i32, i32, vp, i64, C.POINTER(i64)]
     L.wflowb200_get_stats.argtypes = [vp, C.POINTER(Stats)]

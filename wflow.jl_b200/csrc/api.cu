@@ -92,6 +92,10 @@ int32_t build_networks(const WflowB200Config* cfg, const WflowB200Domain* dom, N
     errmsg = "land network: " + err;
     return WFLOWB200_ERR_GRAPH;
   }
+  if (cfg->land_routing == 1 && !build_edge_connectivity(land, dom->d1, dom->d2, dom->indices, n, err)) {
+    errmsg = "land network: " + err;
+    return WFLOWB200_ERR_GRAPH;
+  }
   std::vector<int64_t> ridx(2 * (size_t)nriv), rso(nriv);
   std::vector<uint8_t> rldd(nriv);
   for (int64_t r = 0; r < nriv; ++r) {
@@ -154,6 +158,10 @@ int32_t copy_artifact(const Network& nw, int32_t id, int64_t* dst, int64_t capac
     case WFLOWB200_A_WAVE_NODE_LEVEL: src = &nw.node_level; break;
     case WFLOWB200_A_WAVE_CHUNK_PTR: src = &nw.chunk_ptr; break;
     case WFLOWB200_A_WAVE_CHUNK_OUTLET: src = &nw.chunk_outlet; break;
+    case WFLOWB200_A_EDGE_X_UP: src = &nw.edge_x_up; break;
+    case WFLOWB200_A_EDGE_X_DOWN: src = &nw.edge_x_down; break;
+    case WFLOWB200_A_EDGE_Y_UP: src = &nw.edge_y_up; break;
+    case WFLOWB200_A_EDGE_Y_DOWN: src = &nw.edge_y_down; break;
     default: errmsg = "bad artefact id"; return WFLOWB200_ERR_ARG;
   }
   *len_out = (int64_t)src->size();
@@ -278,6 +286,7 @@ struct WflowB200 {
   unsigned* d_li_barrier = nullptr;  // {arrivals, generation}
   unsigned long long* d_li_dt = nullptr;
   int* d_li_substeps = nullptr;
+  int grid_lil = 0;                  // 2-D local-inertial overland + river flow: co-resident CTAs
   DevFields f{};
   KCfg kc{};
   double* pool = nullptr;  // one HBM allocation holding every Float64 field
@@ -393,10 +402,13 @@ int layers_of(const WflowB200* h, int kind) {
   return kind == 1 ? h->N : kind == 2 ? h->N + 1 : kind == 5 ? std::max(h->cfg.fp_levels, 1) : 1;
 }
 // slots / elements / slot map of a field kind (0-2 land, 3 river, 4 reservoir, 5 river x level)
+// kind 6: land scalars of the 2-D local-inertial overland flow, present with land_routing = 1 only
 int slots_of(const WflowB200* h, int kind) {
+  if (kind == 6) return h->cfg.land_routing == 1 ? h->ns : 0;
   return (kind == 3 || kind == 5) ? h->nrs : kind == 4 ? h->nress : h->ns;
 }
 int count_of(const WflowB200* h, int kind) {
+  if (kind == 6) return h->cfg.land_routing == 1 ? h->n : 0;
   return (kind == 3 || kind == 5) ? h->nriv : kind == 4 ? h->nres : h->n;
 }
 
@@ -843,6 +855,12 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     return fail(nullptr, WFLOWB200_ERR_ARG, "kv_profile must be 0 .. 3");
   if (cfg->snow_gravitational_transport && !cfg->snow)
     return fail(nullptr, WFLOWB200_ERR_ARG, "snow_gravitational_transport needs the snow model");
+  if (cfg->land_routing != 0 &&
+      (cfg->land_routing != 1 || cfg->river_routing != 1 || cfg->fp_levels > 0 ||
+       cfg->snow_gravitational_transport))
+    return fail(nullptr, WFLOWB200_ERR_ARG,
+                "land_routing: 0 or 1; the 2-D local-inertial overland flow needs river_routing = 1 "
+                "and runs without 1-D floodplain and lateral snow transport");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, WFLOWB200_ERR_CUDA, "no CUDA device: libwflow_b200 has no CPU fallback");
@@ -923,6 +941,11 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
                     h->f.fp_flow_capacity, h->f.fp_qin, h->f.fp_qin_cumulative, h->f.fp_qin_average,
                     h->f.riv_floodplain_water_exchange})
     fill(p, 3, 0.0);                            // floodplain.jl:216-236
+  if (cfg->land_routing == 1)                   // surface_staggered_scheme.jl:840-865,963-968
+    for (double* p : {h->f.li_land_runoff, h->f.li_land_qx0, h->f.li_land_qy0, h->f.li_land_qx,
+                      h->f.li_land_qy, h->f.li_land_qx_cumulative, h->f.li_land_qy_cumulative,
+                      h->f.li_land_qx_average, h->f.li_land_qy_average, h->f.li_land_error})
+      fill(p, 6, 0.0);
   fill(h->f.waterdepth_river, 0, 0.0);          // runoff.jl:26
   fill(h->f.unsaturated_store_depth, 0, 0.0);   // soil.jl:71
   fill(h->f.total_storage, 0, 0.0);             // soil.jl:77
@@ -993,7 +1016,7 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     }
     if (nli + nle + nri + nre > 0 &&
         (cfg->adaptive || h->nres > 0 || cfg->snow_gravitational_transport || cfg->river_routing != 0 ||
-         cfg->fp_levels > 0)) {
+         cfg->fp_levels > 0 || cfg->land_routing != 0)) {
       h->err = "cut edges are supported for kinematic-wave routing with fixed internal time steps, "
                "without reservoirs and lateral snow transport";
       return bail(WFLOWB200_ERR_ARG);
@@ -1123,11 +1146,31 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     TRY_CREATE(upload_i32(in_idx, &h->f.li_in_idx, 0));
     TRY_CREATE(cudaMalloc((void**)&h->d_li_barrier, 2 * sizeof(unsigned)));
     TRY_CREATE(cudaMemset(h->d_li_barrier, 0, 2 * sizeof(unsigned)));
-    TRY_CREATE(cudaMalloc((void**)&h->d_li_dt, 2 * sizeof(unsigned long long)));
+    TRY_CREATE(cudaMalloc((void**)&h->d_li_dt, 4 * sizeof(unsigned long long)));
     TRY_CREATE(cudaMalloc((void**)&h->d_li_substeps, sizeof(int)));
     TRY_CREATE(cudaMemset(h->d_li_substeps, 0, sizeof(int)));
     h->grid_li = li_max_grid(cfg->device);
     if (h->grid_li <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
+  }
+  h->kc.land_routing = cfg->land_routing;
+  if (cfg->land_routing == 1) {   // EdgeConnectivity by land slot (network.jl:136-153): -1 = no neighbour
+    const Network& ln = h->land.nw;
+    std::vector<int64_t> e[4];
+    const std::vector<int64_t>* src[4] = {&ln.edge_x_up, &ln.edge_x_down, &ln.edge_y_up, &ln.edge_y_down};
+    for (int k = 0; k < 4; ++k) {
+      e[k].assign(std::max(h->ns, 1), -1);
+      for (int p = 0; p < h->n; ++p) {
+        const int64_t nb = (*src[k])[ln.perm[p] - 1];
+        e[k][p] = nb <= h->n ? ln.slot_of[nb - 1] : -1;
+      }
+    }
+    TRY_CREATE(upload_i32(e[0], &h->f.edge_x_up, 0));
+    TRY_CREATE(upload_i32(e[1], &h->f.edge_x_down, 0));
+    TRY_CREATE(upload_i32(e[2], &h->f.edge_y_up, 0));
+    TRY_CREATE(upload_i32(e[3], &h->f.edge_y_down, 0));
+    h->f.land_river_slot = h->riv_of_land;   // domain.land.network.river_indices by slot
+    h->grid_lil = lil_max_grid(cfg->device);
+    if (h->grid_lil <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
   }
 
   // persistent cooperative grids: as many co-resident CTAs as the device holds
@@ -1174,6 +1217,7 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree((void*)h->f.fp_depth);
   cudaFree(h->f.riv_reservoir); cudaFree(h->f.res_land_slot); cudaFree(h->res_ident);
   cudaFree(h->f.res_river_slot); cudaFree(h->f.li_dst_slot); cudaFree(h->f.li_in_ptr);
+  cudaFree(h->f.edge_x_up); cudaFree(h->f.edge_x_down); cudaFree(h->f.edge_y_up); cudaFree(h->f.edge_y_down);
   cudaFree(h->f.li_in_idx); cudaFree(h->d_li_barrier); cudaFree(h->d_li_dt); cudaFree(h->d_li_substeps);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
@@ -1541,8 +1585,40 @@ int32_t wflowb200_update_lateral_inflow_overland(WflowB200* h) {
                       "update_lateral_inflow(overland)");
 }
 
+static LiLaunch li_launch(WflowB200* h, double dt) {
+  LiLaunch w{};
+  w.dt = dt;
+  w.alpha = h->cfg.li_alpha > 0.0 ? h->cfg.li_alpha : 0.7;
+  w.h_thresh = h->cfg.li_h_thresh;
+  w.froude_limit = h->cfg.li_froude_limit;
+  w.fp_levels = h->cfg.fp_levels;
+  for (int l = 0; l < 16; ++l) w.fp_depth[l] = h->cfg.fp_depth[l];
+  w.barrier = h->d_li_barrier;
+  w.dt_bits = h->d_li_dt;
+  w.err = h->d_err;
+  w.substeps = h->d_li_substeps;
+  w.land_alpha = h->cfg.li_land_alpha > 0.0 ? h->cfg.li_land_alpha : 0.7;
+  w.land_theta = h->cfg.li_land_theta;
+  w.land_h_thresh = h->cfg.li_land_h_thresh;
+  w.land_froude_limit = h->cfg.li_land_froude_limit;
+  return w;
+}
+
+int32_t wflowb200_update_bc_overland_flow_model(WflowB200* h) {
+  WFB_ENTER(h);
+  if (h->cfg.land_routing != 1)
+    return fail(h, WFLOWB200_ERR_STATE, "update_bc_overland_flow_model: land_routing is not local_inertial");
+  return check_launch(h, launch_bc_overland_flow(h->f, h->kc, h->stream), "update_bc_overland_flow_model");
+}
+
 int32_t wflowb200_update_overland_flow_model(WflowB200* h, double dt) {
   WFB_ENTER(h);
+  if (h->cfg.land_routing == 1) {  // 2-D local-inertial overland flow + local-inertial river flow
+    LiLaunch w = li_launch(h, dt);
+    w.grid = std::max(1, std::min(h->grid_lil, (h->n + 255) / 256));
+    return check_launch(h, launch_local_inertial_land_river(h->f, h->kc, w, h->stream),
+                        "update_overland_flow_model (local inertial)");
+  }
   if (h->cfg.adaptive)
     return run_wave_adaptive(h, h->land, dt, 0, 2, h->grid_olf, h->smem_olf, h->sub_land,
                              [&](const WaveLaunch& w) {
@@ -1569,18 +1645,11 @@ int32_t wflowb200_update_inflow_reservoir(WflowB200* h) {
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt) {
   WFB_ENTER(h);
   if (h->nriv == 0) return WFLOWB200_OK;
+  if (h->cfg.land_routing == 1)   // the river is routed together with the land (one scheme, one dt_s)
+    return fail(h, WFLOWB200_ERR_STATE, "land_routing = local_inertial: the river flow is part of "
+                                        "wflowb200_update_overland_flow_model");
   if (h->cfg.river_routing == 1) {  // local-inertial river flow: the whole model step in one kernel
-    LiLaunch w{};
-    w.dt = dt;
-    w.alpha = h->cfg.li_alpha > 0.0 ? h->cfg.li_alpha : 0.7;
-    w.h_thresh = h->cfg.li_h_thresh;
-    w.froude_limit = h->cfg.li_froude_limit;
-    w.fp_levels = h->cfg.fp_levels;
-    for (int l = 0; l < 16; ++l) w.fp_depth[l] = h->cfg.fp_depth[l];
-    w.barrier = h->d_li_barrier;
-    w.dt_bits = h->d_li_dt;
-    w.err = h->d_err;
-    w.substeps = h->d_li_substeps;
+    LiLaunch w = li_launch(h, dt);
     w.grid = std::max(1, std::min(h->grid_li, (h->nriv + 255) / 256));
     return check_launch(h, launch_local_inertial_river(h->f, h->kc, w, h->stream),
                         "update_river_flow_model (local inertial)");
@@ -1758,6 +1827,16 @@ static int32_t update_model_step(WflowB200* h, double dt) {
   mark(4);
   if (!soil_fused && (rc = wflowb200_update_soil_water_storage(h, dt))) return rc;  // also fills olf_inwater
   mark(5);
+  if (h->cfg.land_routing == 1) {  // surface_routing! with local-inertial land AND river routing
+    if ((rc = wflowb200_update_bc_overland_flow_model(h))) return rc;   // surface_routing.jl:62-86
+    if ((rc = wflowb200_update_inflow_reservoir(h))) return rc;
+    mark(6);
+    if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
+    mark(7); mark(8);
+    if ((rc = wflowb200_update_total_water_storage(h))) return rc;
+    mark(9);
+    return book_stage_times(h);
+  }
   if (h->fuse_surface && h->tune.fuse_surface) {  // overland and river wavefronts overlapped (timed as "overland")
     if ((rc = update_surface_fused(h, dt))) return rc;
     mark(6);
@@ -2111,6 +2190,7 @@ int32_t wflowb200_get_stats(WflowB200* h, WflowB200Stats* out) {
     int cnt = 0;
     cudaMemcpy(&cnt, h->d_li_substeps, sizeof(int), cudaMemcpyDeviceToHost);
     h->sub_river = cnt;
+    if (h->cfg.land_routing == 1) h->sub_land = cnt;
   }
   out->substeps_land = h->sub_land; out->substeps_river = h->sub_river;
   out->substeps_ssf = h->sub_ssf;

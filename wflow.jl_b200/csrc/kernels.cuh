@@ -135,8 +135,18 @@ struct LiLaunch {
   unsigned* err;                // device: the handle's error word (bounded barrier waits)
   int* substeps;                // device: number of sub-steps of the model step (out)
   int grid;                     // co-resident CTAs
+  // 2-D local-inertial overland flow coupled to the river (land_routing = 1)
+  double land_alpha, land_theta, land_h_thresh;
+  int land_froude_limit;
 };
 int li_max_grid(int device);
+// update_overland_flow_model!(overland, river, ...) (surface_staggered_scheme.jl:1153-1194): the
+// 2-D local-inertial overland flow and the local-inertial river flow, all sub-steps of a model
+// step in one persistent kernel
+int lil_max_grid(int device);
+int launch_local_inertial_land_river(const DevFields& f, const KCfg& c, const LiLaunch& w, cudaStream_t s);
+// update_bc_overland_flow_model! (surface_staggered_scheme.jl:1080-1097)
+int launch_bc_overland_flow(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_local_inertial_river(const DevFields& f, const KCfg& c, const LiLaunch& w, cudaStream_t s);
 int launch_lateral_inflow_overland(const DevFields& f, const KCfg& c, cudaStream_t s);
 int launch_lateral_inflow_river(const DevFields& f, const KCfg& c, cudaStream_t s);

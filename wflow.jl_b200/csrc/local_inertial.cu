@@ -301,6 +301,344 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
   if (tid == 0) *w.substeps = count;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-D local-inertial overland flow coupled to the local-inertial river (land_routing = 1):
+// update_overland_flow_model!(overland, river, domain, clock, dt; update_h = false)
+// (surface_staggered_scheme.jl:1153-1194) with
+//   stable_timestep (land)              :1022-1043   alpha min(dx, dy) / sqrt(g h), non-river cells
+//   local_inertial_update_fluxes!       :1276-1295   x / y edge flow of every cell
+//     update_directional_flow!          :1201-1271   local_inertial_flow(theta, ...), de Almeida
+//                                                     et al. 2012 (surface_process.jl:123-159)
+//   update_inflow_reservoir!            :1301-1319   overland flow into the reservoirs
+//   staggered_scheme_river_update!      :762-794     river edge flow + reservoirs (update_h = false)
+//   local_inertial_update_water_depth!  :1520-1546   land cells; river cells with their subgrid
+//                                                     channel (bankfull spill), :1325-1514
+// The same persistent-kernel organisation as the river alone: per sub-step one global minimum,
+// an edge phase (the two edges of every land cell AND the river edges: both read only depths),
+// the reservoirs, a node phase -- separated by grid barriers. The thread that owns a LAND cell
+// also owns the water depth and storage of the river node in it, so the Courant steps of the next
+// sub-step are formed right where the new depths are computed and need no pass of their own.
+// Values another thread may have written since the last barrier are read past the L1 (__ldcg).
+namespace {
+
+// local_inertial_flow(theta, q0, qd, qu, zs0, zs1, hf, width, length, mannings_n_sq, froude_limit,
+// dt): flow through a rectangular area                              surface_process.jl:123-159
+__device__ __forceinline__ double local_inertial_flow_rect(double theta, double q0, double qd, double qu,
+                                                           double zs0, double zs1, double hf,
+                                                           double width, double length,
+                                                           double mannings_n_sq, int froude_limit,
+                                                           double dt) {
+  const double slope = (zs1 - zs0) / length;
+  const double pow_hf = cbrt(hf * hf * hf * hf * hf * hf * hf);
+  double q = (((theta * q0 + 0.5 * (1.0 - theta) * (qu + qd)) - kG * hf * width * dt * slope) /
+              (1.0 + kG * dt * mannings_n_sq * fabs(q0) / (pow_hf * width)));
+  if (froude_limit) {
+    const double fr = (q / width / hf) / sqrt(kG * hf);
+    if (fabs(fr) > 1.0 && q > 0.0) q = hf * sqrt(kG * hf) * width;
+    else if (fabs(fr) > 1.0 && q < 0.0) q = -hf * sqrt(kG * hf) * width;
+  }
+  return q;
+}
+
+// update_directional_flow! for the edge of cell p in one direction              :1201-1271
+__device__ __forceinline__ void lil_directional_flow(const LiLaunch& w, const int p, const int up,
+                                                     const int down, const double width_at_edge,
+                                                     const double z_max_at_edge, const double* length_vec,
+                                                     const double* z, const double* h, const double h_p,
+                                                     const double z_p, const double mannings_n_sq,
+                                                     const double* q_prev, double* q_current,
+                                                     double* q_cumulative, const double dt_s) {
+  if (up < 0 || width_at_edge == 0.0) return;   // the flow of this edge stays what it is (0)
+  const double h_up = __ldcg(h + up);
+  const double zs_current = z_p + h_p;
+  const double zs_upstream = __ldg(z + up) + h_up;
+  const double zs_max_at_edge = jmax(zs_current, zs_upstream);
+  const double water_depth_at_edge = (zs_max_at_edge - z_max_at_edge);
+  double q = 0.0;
+  if (water_depth_at_edge > w.land_h_thresh) {
+    const double length_at_edge = 0.5 * (__ldg(length_vec + p) + __ldg(length_vec + up));
+    q = local_inertial_flow_rect(w.land_theta, __ldcg(q_prev + p), down >= 0 ? __ldcg(q_prev + down) : 0.0,
+                                 __ldcg(q_prev + up), zs_current, zs_upstream, water_depth_at_edge,
+                                 width_at_edge, length_at_edge, mannings_n_sq, w.land_froude_limit, dt_s);
+    if (h_p <= 0.0) q = jmin(q, 0.0);
+    if (h_up <= 0.0) q = jmax(q, 0.0);
+  }
+  __stcg(q_current + p, q);
+  q_cumulative[p] += q * dt_s;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kLiBlock, 2)
+local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg c, const LiLaunch w) {
+  const int n = c.n, nriv = c.nriv;
+  const int stride = (int)(gridDim.x * blockDim.x);
+  const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const unsigned n_blocks = gridDim.x;
+  unsigned gen = li_ld_u32(&w.barrier[1]);
+  __shared__ unsigned long long s_min[2];   // river, land
+  const double dt = w.dt;
+  const unsigned long long inf_bits = 0x7ff0000000000000ull;
+  const double inf = __longlong_as_double((long long)inf_bits);
+
+  // The Courant steps of the cells this thread owns: river nodes alpha L / sqrt(g h) (:1004-1020),
+  // non-river land cells alpha min(dx, dy) / sqrt(g h) (:1022-1043)
+  double mine_river = inf, mine_land = inf;
+  auto courant = [&](const int p, const int r, const double h_land, const double h_river) {
+    if (r >= 0) {
+      const double d = w.alpha * __ldg(f.riv_flow_length + r) / sqrt(kG * h_river);
+      mine_river = d < mine_river ? d : mine_river;
+    } else {
+      const double d = w.land_alpha * jmin(__ldg(f.li_land_x_length + p), __ldg(f.li_land_y_length + p)) /
+                       sqrt(kG * h_land);
+      mine_land = d < mine_land ? d : mine_land;
+    }
+  };
+
+  // set_reservoir_vars! / set_flow_vars! (river :269-275, overland :1127-1132); qx0 .= qx, qy0 .= qy
+  // of the first sub-step (:1284-1285)
+  for (int p = tid; p < nriv; p += stride) f.riv_q_cumulative[p] = 0.0;
+  for (int p = tid; p < n; p += stride) {
+    f.li_land_qx_cumulative[p] = 0.0;
+    f.li_land_qy_cumulative[p] = 0.0;
+    f.li_land_qx0[p] = f.li_land_qx[p];
+    f.li_land_qy0[p] = f.li_land_qy[p];
+    const int r = f.land_river_slot[p];
+    if (r >= 0) f.riv_actual_external_abstraction_cumulative[r] = 0.0;
+    courant(p, r, f.olf_h[p], r >= 0 ? f.riv_h[r] : 0.0);
+  }
+  for (int i = tid; i < c.nres; i += stride) {
+    f.res_inflow_cumulative[i] = 0.0;
+    f.res_actual_external_abstraction_cumulative[i] = 0.0;
+    f.res_outflow_cumulative[i] = 0.0;
+    f.res_actevap_cumulative[i] = 0.0;
+  }
+
+  double t = 0.0;
+  int count = 0;
+  bool alive = true;
+  while (t < dt && alive) {
+    // ---- dt_s = min(stable_timestep(river), stable_timestep(land))                  :1172-1175 ----
+    if (threadIdx.x == 0) { s_min[0] = inf_bits; s_min[1] = inf_bits; }
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+      const double a = __shfl_xor_sync(0xffffffffu, mine_river, o);
+      const double b = __shfl_xor_sync(0xffffffffu, mine_land, o);
+      mine_river = a < mine_river ? a : mine_river;
+      mine_land = b < mine_land ? b : mine_land;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_min[0], (unsigned long long)__double_as_longlong(mine_river));
+      atomicMin(&s_min[1], (unsigned long long)__double_as_longlong(mine_land));
+    }
+    __syncthreads();
+    unsigned long long* slot = w.dt_bits + 2 * (count & 1);
+    if (threadIdx.x == 0) {
+      if (s_min[0] != inf_bits) atomicMin(slot, s_min[0]);
+      if (s_min[1] != inf_bits) atomicMin(slot + 1, s_min[1]);
+    }
+    alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
+    if (!alive) break;
+    const unsigned long long mb_river = __ldcg(slot), mb_land = __ldcg(slot + 1);
+    if (tid == 0) {  // the slots of the next sub-step
+      w.dt_bits[2 * ((count + 1) & 1)] = inf_bits;
+      w.dt_bits[2 * ((count + 1) & 1) + 1] = inf_bits;
+    }
+    const double dt_river = mb_river == inf_bits ? 60.0 : __longlong_as_double((long long)mb_river);
+    const double dt_land = mb_land == inf_bits ? 60.0 : __longlong_as_double((long long)mb_land);
+    double dt_s = jmin(dt_river, dt_land);
+    if (t + dt_s > dt) dt_s = dt - t;  // check_timestepsize  routing/timestepping.jl:11-16
+
+    // ---- local_inertial_update_fluxes!: the x and the y edge of every cell          :1276-1295 ----
+    for (int p = tid; p < n; p += stride) {
+      const double h_p = __ldcg(f.olf_h + p);
+      const double z_p = __ldg(f.li_land_z + p);
+      const double mann = __ldg(f.li_land_mannings_n_sq_at_edge + p);
+      lil_directional_flow(w, p, f.edge_x_up[p], f.edge_x_down[p], __ldg(f.li_land_ywidth_at_edge + p),
+                           __ldg(f.li_land_zx_max_at_edge + p), f.li_land_x_length, f.li_land_z, f.olf_h,
+                           h_p, z_p, mann, f.li_land_qx0, f.li_land_qx, f.li_land_qx_cumulative, dt_s);
+      lil_directional_flow(w, p, f.edge_y_up[p], f.edge_y_down[p], __ldg(f.li_land_xwidth_at_edge + p),
+                           __ldg(f.li_land_zy_max_at_edge + p), f.li_land_y_length, f.li_land_z, f.olf_h,
+                           h_p, z_p, mann, f.li_land_qy0, f.li_land_qy, f.li_land_qy_cumulative, dt_s);
+    }
+    // ---- update_river_channel_flow!: the edge leaving every active river node        :326-383 ----
+    for (int p = tid; p < nriv; p += stride) {
+      const int d = f.li_dst_slot[p];
+      if (d == -1) continue;
+      if (f.riv_reservoir && f.riv_reservoir[p] >= 0) continue;  // not in active_e
+      const double q_previous = __ldcg(f.riv_q + p);
+      const double h_src = __ldcg(f.riv_h + p);
+      const double zb = __ldg(f.li_zb + p);
+      const double zs_src = zb + h_src;
+      const double h_dst = d == -2 ? __ldg(f.li_ghost_h + p) : __ldcg(f.riv_h + d);
+      const double zs_dst = (d == -2 ? zb : __ldg(f.li_zb + d)) + h_dst;
+      const double zs_at_edge = jmax(zs_src, zs_dst);
+      const double hf = zs_at_edge - __ldg(f.li_zb_at_edge + p);
+      f.li_zs_at_edge[p] = zs_at_edge;
+      f.li_water_depth_at_edge[p] = hf;
+      const double width = __ldg(f.li_flow_width_at_edge + p);
+      const double A = width * hf;
+      const double R = A / (2.0 * hf + width);
+      double q = hf > w.h_thresh
+                     ? local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R,
+                                           __ldg(f.li_flow_length_at_edge + p),
+                                           __ldg(f.li_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
+                     : 0.0;
+      if (h_src <= 0.0) q = jmin(q, 0.0);
+      if (h_dst <= 0.0) q = jmax(q, 0.0);
+      __stcg(f.riv_q + p, q);
+      __stcg(f.riv_q_cumulative + p, __ldcg(f.riv_q_cumulative + p) + q * dt_s);
+    }
+    alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
+    if (!alive) break;
+
+    // ---- update_inflow_reservoir! (:1301-1319) + update_bc_reservoir_model! (:627-661) -----------
+    if (c.nres > 0) {
+      for (int v = tid; v < c.nres; v += stride) {
+        const int p = f.res_river_slot[v];
+        const int j = f.res_land_slot[v];
+        const int xd = f.edge_x_down[j], yd = f.edge_y_down[j];
+        const double net_land_flow = (xd >= 0 ? __ldcg(f.li_land_qx + xd) : 0.0) - __ldcg(f.li_land_qx + j) +
+                                     (yd >= 0 ? __ldcg(f.li_land_qy + yd) : 0.0) - __ldcg(f.li_land_qy + j);
+        f.res_inflow_overland[v] = f.li_land_runoff[j] + (net_land_flow);
+        double q_in = 0.0;  // sum_at(q, edges_at_node.src[i])
+        for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_in += __ldcg(f.riv_q + f.li_in_idx[e]);
+        const double outflow = reservoir_step(f, v, q_in, dt_s);
+        __stcg(f.riv_q + p, outflow);
+        __stcg(f.riv_q_cumulative + p, __ldcg(f.riv_q_cumulative + p) + outflow * dt_s);
+      }
+      alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
+      if (!alive) break;
+    }
+
+    // ---- local_inertial_update_water_depth!                                         :1520-1546 ----
+    const bool last = !(t + dt_s < dt);
+    mine_river = inf;
+    mine_land = inf;
+    for (int p = tid; p < n; p += stride) {
+      const int r = f.land_river_slot[p];
+      const int xd = f.edge_x_down[p], yd = f.edge_y_down[p];
+      const double qx_p = __ldcg(f.li_land_qx + p), qy_p = __ldcg(f.li_land_qy + p);
+      const double net_land_flow = (xd >= 0 ? __ldcg(f.li_land_qx + xd) : 0.0) - qx_p +
+                                   (yd >= 0 ? __ldcg(f.li_land_qy + yd) : 0.0) - qy_p;
+      if (!last) {  // qx0 .= qx, qy0 .= qy of the next sub-step (:1284-1285): this thread's own edges
+        __stcg(f.li_land_qx0 + p, qx_p);
+        __stcg(f.li_land_qy0 + p, qy_p);
+      }
+      const double runoff = f.li_land_runoff[p];
+      double storage = f.olf_storage[p];
+      if (r < 0) {  // update_land_storage_and_depth!                                  :1491-1514
+        storage += (net_land_flow + runoff) * dt_s;
+        if (storage < 0.0) {
+          f.li_land_error[p] += fabs(storage);
+          storage = 0.0;
+        }
+        const double h_new = storage / (__ldg(f.li_land_x_length + p) * __ldg(f.li_land_y_length + p));
+        f.olf_storage[p] = storage;
+        __stcg(f.olf_h + p, h_new);
+        courant(p, r, h_new, 0.0);
+        continue;
+      }
+      if (f.riv_reservoir && f.riv_reservoir[r] >= 0) {  // reservoir outlet: h stays as it is
+        courant(p, r, 0.0, f.riv_h[r]);
+        continue;
+      }
+      // update_river_and_land_storage_and_depth!                                      :1443-1485
+      double q_src = 0.0;  // compute_river_storage_change                             :1325-1352
+      for (int e = f.li_in_ptr[r]; e < f.li_in_ptr[r + 1]; ++e) q_src += __ldcg(f.riv_q + f.li_in_idx[e]);
+      const double q_dst = f.li_dst_slot[r] == -1 ? 0.0 : 0.0 + __ldcg(f.riv_q + r);
+      const double net_river_flow = q_src - q_dst;
+      const double net_flow = net_river_flow + net_land_flow + runoff - __ldg(f.riv_abstraction + r);
+      storage += net_flow * dt_s;
+      if (storage < 0.0) {
+        f.li_land_error[p] += fabs(storage);
+        storage = 0.0;
+      }
+      const double bankfull_storage = __ldg(f.li_bankfull_storage + r);
+      const double ext = __ldg(f.riv_external_inflow + r);
+      double inflow;  // compute_external_inflow                                       :1359-1382
+      if (ext < 0.0) {
+        const double available_volume = storage >= bankfull_storage ? bankfull_storage : f.riv_storage[r];
+        const double abstraction = jmin(-ext, available_volume / dt_s * 0.80);
+        f.riv_actual_external_abstraction_cumulative[r] += abstraction * dt_s;
+        inflow = -abstraction;
+      } else {
+        inflow = ext;   // (the cumulative abstraction grows by 0.0 * dt: unchanged)
+      }
+      storage += inflow * dt_s;
+      const double length = __ldg(f.riv_flow_length + r), width = __ldg(f.riv_flow_width + r);
+      double river_h, land_h, river_storage;  // compute_water_depths                  :1388-1416
+      if (storage >= bankfull_storage) {
+        const double bankfull_depth = __ldg(f.li_bankfull_depth + r);
+        river_h = bankfull_depth + (storage - bankfull_storage) /
+                                       (__ldg(f.li_land_x_length + p) * __ldg(f.li_land_y_length + p));
+        land_h = river_h - bankfull_depth;
+        river_storage = river_h * length * width;
+      } else {
+        river_h = storage / (length * width);
+        land_h = 0.0;
+        river_storage = storage;
+      }
+      f.olf_storage[p] = storage;
+      __stcg(f.riv_h + r, river_h);
+      __stcg(f.olf_h + p, land_h);
+      f.riv_storage[r] = river_storage;
+      courant(p, r, land_h, river_h);
+    }
+    t += dt_s;
+    ++count;
+    // (no barrier here: the next sub-step's minimum is formed from this thread's own new depths,
+    // and its edge phase comes after the barrier that follows the minimum)
+  }
+  // average_flow_vars! (river :283-290, overland :1138-1147) / average_reservoir_vars!
+  for (int p = tid; p < nriv; p += stride) f.riv_q_average[p] = __ldcg(f.riv_q_cumulative + p) / dt;
+  for (int p = tid; p < n; p += stride) {
+    f.li_land_qx_average[p] = f.li_land_qx_cumulative[p] / dt;
+    f.li_land_qy_average[p] = f.li_land_qy_cumulative[p] / dt;
+    const int r = f.land_river_slot[p];
+    if (r >= 0)
+      f.riv_actual_external_abstraction_average[r] = f.riv_actual_external_abstraction_cumulative[r] / dt;
+  }
+  for (int i = tid; i < c.nres; i += stride) {
+    f.res_outflow_average[i] = f.res_outflow_cumulative[i] / dt;
+    f.res_inflow_average[i] = f.res_inflow_cumulative[i] / dt;
+    f.res_actual_external_abstraction_average[i] = f.res_actual_external_abstraction_cumulative[i] / dt;
+  }
+  if (tid == 0) *w.substeps = count;
+}
+
+int lil_max_grid(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, local_inertial_land_river_kernel, kLiBlock, 0) !=
+      cudaSuccess)
+    return -1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return per_sm * sms;
+}
+
+int launch_local_inertial_land_river(const DevFields& f, const KCfg& c, const LiLaunch& w, cudaStream_t s) {
+  static const unsigned long long inf4[4] = {0x7ff0000000000000ull, 0x7ff0000000000000ull,
+                                             0x7ff0000000000000ull, 0x7ff0000000000000ull};
+  cudaMemcpyAsync(w.dt_bits, inf4, sizeof(inf4), cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(w.barrier, 0, sizeof(unsigned), s);  // arrivals; the generation keeps counting
+  local_inertial_land_river_kernel<<<w.grid, kLiBlock, 0, s>>>(f, c, w);
+  return 1;
+}
+
+// update_bc_overland_flow_model!                              surface_staggered_scheme.jl:1080-1097
+__global__ void bc_overland_flow_kernel(const DevFields f, const KCfg c) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.n) return;
+  double runoff = (f.net_runoff[p] + f.net_runoff_river[p]) * f.area[p];
+  if (f.land_river_slot[p] >= 0) runoff += f.ssf_to_river_average[p];  // get_flux_to_river  lsf.jl:346
+  f.li_land_runoff[p] = runoff;
+}
+
+int launch_bc_overland_flow(const DevFields& f, const KCfg& c, cudaStream_t s) {
+  bc_overland_flow_kernel<<<(c.n + 255) / 256, 256, 0, s>>>(f, c);
+  return 1;
+}
+
 int li_max_grid(int device) {
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, local_inertial_river_kernel, kLiBlock, 0) !=

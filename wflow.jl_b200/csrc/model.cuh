@@ -29,6 +29,10 @@ struct DevFields {
   int32_t* li_dst_slot;        // slot of the node the leaving edge ends in, -1 none, -2 ghost
   int32_t* li_in_ptr;          // edges entering a node (= their source slots), CSR by slot,
   int32_t* li_in_idx;          // ascending source NODE id (sum_at order)
+  // 2-D local-inertial overland flow: EdgeConnectivity by land slot (-1: no active neighbour) and
+  // domain.land.network.river_indices (land slot -> river slot, -1: no river in the cell)
+  int32_t *edge_x_up, *edge_x_down, *edge_y_up, *edge_y_down;
+  int32_t* land_river_slot;
   uint8_t* land_is_res_outlet; // land slot is a reservoir outlet (nullptr without reservoirs)
   int32_t* olf_newton_trace;   // land / river, or nullptr: Newton iterations of kinematic_wave
   int32_t* riv_newton_trace;   // per node since wflowb200_newton_trace(h, 1)
@@ -78,6 +82,7 @@ struct KCfg {
   int32_t gash, has_lai, snow, glacier, soil_infiltration_reduction, kv_profile;
   double qroot;                // KIN_WAVE_MIN_FLOW^0.2
   int32_t river_routing;       // 0 kinematic wave, 1 local inertial
+  int32_t land_routing;        // 0 kinematic wave, 1 local inertial (2-D, with river_routing = 1)
   int32_t kw_root_each_substep; // 1: u_prev = pow(q_prev, 0.2) before every solve, like the
                                // reference (default 0: carried, see routing.cu: KwState)
   int32_t fp_levels;           // 1-D floodplain: levels of the profile (0: none) and their depths

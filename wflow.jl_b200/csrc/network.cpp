@@ -119,6 +119,33 @@ bool build_graph(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, co
   return true;
 }
 
+// NEIGHBORS (routing/subsurface/connectivity.jl:61-66) paired with DIRS (network.jl:3):
+// (0,-1) ind_y_down, (-1,0) ind_x_down, (1,0) ind_x_up, (0,1) ind_y_up
+bool build_edge_connectivity(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, int64_t n,
+                             std::string& err) {
+  std::vector<int64_t> lin(n);
+  for (int64_t v = 0; v < n; ++v) {
+    const int64_t i = indices[2 * v], j = indices[2 * v + 1];
+    if (i < 1 || i > d1 || j < 1 || j > d2) { err = "index outside raster"; return false; }
+    lin[v] = (j - 1) * d1 + (i - 1);
+  }
+  auto neighbour = [&](int64_t v, int di, int dj) -> int64_t {
+    const int64_t ti = indices[2 * v] + di, tj = indices[2 * v + 1] + dj;
+    if (ti < 1 || ti > d1 || tj < 1 || tj > d2) return n + 1;
+    const int64_t tl = (tj - 1) * d1 + (ti - 1);
+    auto it = std::lower_bound(lin.begin(), lin.end(), tl);   // indices are column-major ascending
+    return (it != lin.end() && *it == tl) ? (int64_t)(it - lin.begin()) + 1 : n + 1;
+  };
+  nw.edge_x_up.resize(n); nw.edge_x_down.resize(n); nw.edge_y_up.resize(n); nw.edge_y_down.resize(n);
+  for (int64_t v = 0; v < n; ++v) {
+    nw.edge_y_down[v] = neighbour(v, 0, -1);
+    nw.edge_x_down[v] = neighbour(v, -1, 0);
+    nw.edge_x_up[v] = neighbour(v, 1, 0);
+    nw.edge_y_up[v] = neighbour(v, 0, 1);
+  }
+  return true;
+}
+
 bool build_artifacts(Network& nw, int nthreads, int min_sto, const int64_t* so_override,
                      std::string& err) {
   const int64_t n = nw.n;

@@ -51,12 +51,18 @@ struct Network {
   int64_t n_outlets = 0;
   std::vector<int64_t> chunk_clp_off;  // n_chunks + 1 offsets into clp
   std::vector<int64_t> clp;            // per chunk: (l1 - l0 + 2) absolute slot offsets of its levels
+  // EdgeConnectivity (network.jl:27-33,136-153; built on request): 1-based index of the active
+  // neighbour in the four grid directions, n + 1 where there is none
+  std::vector<int64_t> edge_x_up, edge_x_down, edge_y_up, edge_y_down;
 };
 
 // Build `down` from a gridded LDD (flowgraph). `indices` holds 2n CartesianIndex pairs.
 // Returns false (and sets err) on a cycle.
 bool build_graph(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, const uint8_t* ldd,
                  int64_t n, std::string& err);
+// EdgeConnectivity(network::NetworkLand) (network.jl:136-153) of the cells in `indices`.
+bool build_edge_connectivity(Network& nw, int64_t d1, int64_t d2, const int64_t* indices, int64_t n,
+                             std::string& err);
 // order, stream order (unless `streamorder_override` given), upstream CSR, partition, wavefront.
 bool build_artifacts(Network& nw, int nthreads, int min_streamorder,
                      const int64_t* streamorder_override, std::string& err);

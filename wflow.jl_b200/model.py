@@ -102,6 +102,12 @@ class SbmModel:
         for k, x in enumerate(fp_depth):
             c.fp_depth[k] = x
         self.P = max(len(fp_depth), 1)
+        c.land_routing = int(cfg.get("land_routing", 0))
+        c.li_land_froude_limit = int(cfg.get("li_land_froude_limit", 1))
+        c.li_land_alpha = float(cfg.get("li_land_alpha", 0.7))
+        c.li_land_theta = float(cfg.get("li_land_theta", 1.0))
+        c.li_land_h_thresh = float(cfg.get("li_land_h_thresh", 1.0e-3))
+        self.n6 = self.n if c.land_routing == 1 else 0   # li_land_* fields exist with land_routing = 1
         for k in ("wave_piece_depth_land", "vertical_slices", "unsat_inline_iters"):  # 0 = automatic
             setattr(c, k, int(cfg.get(k, 0)))
         d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
@@ -149,7 +155,7 @@ class SbmModel:
     def _shape(self, name):
         k = self._kinds[name]
         return {0: (self.n,), 1: (self.n, self.N), 2: (self.n, self.N + 1), 3: (self.nriv,),
-                4: (self.nres,), 5: (self.nriv, self.P)}[k]
+                4: (self.nres,), 5: (self.nriv, self.P), 6: (self.n6,)}[k]
 
     def set(self, name: str, a) -> None:
         if name in INT_FIELDS:
@@ -264,8 +270,17 @@ class SbmModel:
     def update_river_flow_model(self, dt):
         self._check(self._L.wflowb200_update_river_flow_model(self._h, dt))
 
+    def update_bc_overland_flow_model(self):
+        self._check(self._L.wflowb200_update_bc_overland_flow_model(self._h))
+
     def surface_routing(self, dt):
-        """surface_routing! (routing/surface/surface_routing.jl:7-46)."""
+        """surface_routing! (routing/surface/surface_routing.jl:7-46; :62-86 with local-inertial
+        land and river routing)."""
+        if self.cfg.get("land_routing", 0) == 1:
+            self.update_bc_overland_flow_model()
+            self.update_inflow_reservoir()
+            self.update_overland_flow_model(dt)   # overland and river flow, one scheme
+            return
         self.update_lateral_inflow_overland()
         self.update_overland_flow_model(dt)
         self.update_lateral_inflow_river()
@@ -350,7 +365,7 @@ class SbmModel:
     def artifact(self, domain: str, name: str) -> np.ndarray:
         dom = {"land": 0, "river": 1}[domain]
         n = C.c_int64()
-        aid = _lib.ARTIFACTS[name]
+        aid = _lib.ARTIFACTS[name] if name in _lib.ARTIFACTS else _lib.EDGE_ARTIFACTS[name]
         self._check(self._L.wflowb200_get_artifact(self._h, dom, aid, None, 0, C.byref(n)))
         a = np.zeros(n.value, dtype=np.int64)
         self._check(self._L.wflowb200_get_artifact(self._h, dom, aid, a.ctypes.data, n.value,

@@ -27,6 +27,8 @@ def build_network_artifacts(cfg: dict, domain: dict) -> dict:
     c.nthreads = int(cfg.get("nthreads", 1))
     c.land_streamorder_min = int(cfg.get("land_streamorder_min", 5))
     c.river_streamorder_min = int(cfg.get("river_streamorder_min", 6))
+    c.land_routing = int(cfg.get("land_routing", 0))     # 1: also EdgeConnectivity of the land
+    c.river_routing = int(cfg.get("river_routing", 0))
     d = _lib.Domain(int(domain["d1"]), int(domain["d2"]), idx.ctypes.data, ldd.ctypes.data,
                     rli.ctypes.data, 0, None)
     net = C.c_void_p()
@@ -38,7 +40,10 @@ def build_network_artifacts(cfg: dict, domain: dict) -> dict:
     try:
         for dom_name, dom_id in (("land", 0), ("river", 1)):
             o = {}
-            for name, aid in _lib.ARTIFACTS.items():
+            ids = dict(_lib.ARTIFACTS)
+            if dom_id == 0 and c.land_routing == 1:
+                ids.update(_lib.EDGE_ARTIFACTS)
+            for name, aid in ids.items():
                 m = C.c_int64()
                 L.wflowb200_network_get(net, dom_id, aid, None, 0, C.byref(m))
                 a = np.zeros(m.value, dtype=np.int64)

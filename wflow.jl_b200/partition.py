@@ -131,6 +131,11 @@ def shard_config(cfg: dict, shard: Shard) -> dict:
     a communicator is attached (comm_init_nccl, ShardGroup)."""
     if cfg.get("nres", 0):
         raise ValueError("sharding a domain with reservoirs is not implemented")
+    if cfg.get("river_routing", 0) or cfg.get("land_routing", 0):
+        # the staggered schemes take ONE sub-step length for the whole domain (the minimum Courant
+        # step, surface_staggered_scheme.jl:1004-1043) and the 2-D overland flow crosses basin
+        # divides: basin-aligned shards are not independent
+        raise ValueError("sharding a domain with local-inertial routing is not implemented")
     c = dict(cfg)
     c["n"] = int(len(shard.cells))
     c["nriv"] = int(len(shard.river_cells))

@@ -198,6 +198,67 @@ def _kh_layered(profile, F, nlayers, zi, N):
     return kh
 
 
+def edge_connectivity(indices: np.ndarray, d1: int, d2: int) -> dict:
+    """EdgeConnectivity(network::NetworkLand) (network.jl:136-153), 1-based, n + 1 = no active
+    neighbour; the model holds it in domain.land.network.edge_indices."""
+    n = len(indices)
+    rev = np.zeros((d1 + 2, d2 + 2), dtype=np.int64)
+    rev[indices[:, 0], indices[:, 1]] = np.arange(1, n + 1)
+    out = {}
+    for name, (di, dj) in (("ind_y_down", (0, -1)), ("ind_x_down", (-1, 0)), ("ind_x_up", (1, 0)),
+                           ("ind_y_up", (0, 1))):
+        r = rev[indices[:, 0] + di, indices[:, 1] + dj]
+        out[name] = np.where(r != 0, r, n + 1).astype(np.int64)
+    return out
+
+
+_PCR_DIR = [(-1, -1), (0, -1), (1, -1), (-1, 0), (0, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]
+
+
+def _set_effective_flowwidth(we_x, we_y, rldd, rdown_land, ridx, river, flow_width, res_outlet,
+                             x_down, y_down, n, racc):
+    """set_effective_flowwidth! (utils.jl:604-669): the river width is taken off the cell edges
+    the river crosses (half of it off two edges for a diagonal direction). rdown_land: downstream
+    LAND cell (1-based, 0 = none) of every river cell; x_down / y_down 0-based (n = none)."""
+    riv_of_land = np.full(n, -1, dtype=np.int64)
+    riv_of_land[ridx] = np.arange(len(ridx))
+    sub = lambda a, k, w: max(a[k] - w, 0.0)
+    for v in np.argsort(racc, kind="stable"):              # any topological order gives the same result
+        dl = rdown_land[v]
+        if dl <= 0 or not river[dl - 1]:
+            continue
+        w = min(flow_width[v], flow_width[riv_of_land[dl - 1]])
+        di, dj = _PCR_DIR[int(rldd[v]) - 1]
+        idx, res = ridx[v], bool(res_outlet[v])
+        xd, yd = x_down[idx], y_down[idx]
+        if (di, dj) == (1, 1):
+            we_x[idx] = 0.0 if res else sub(we_x, idx, 0.5 * w)
+            we_y[idx] = 0.0 if res else sub(we_y, idx, 0.5 * w)
+        elif (di, dj) == (-1, -1):
+            if xd < n:
+                we_y[xd] = 0.0 if res else sub(we_y, xd, 0.5 * w)
+            if yd < n:
+                we_x[yd] = 0.0 if res else sub(we_x, yd, 0.5 * w)
+        elif (di, dj) == (1, 0):
+            we_y[idx] = 0.0 if res else sub(we_y, idx, w)
+        elif (di, dj) == (0, 1):
+            we_x[idx] = 0.0 if res else sub(we_x, idx, w)
+        elif (di, dj) == (-1, 0):
+            if xd < n:
+                we_y[xd] = 0.0 if res else sub(we_y, xd, w)
+        elif (di, dj) == (0, -1):
+            if yd < n:
+                we_x[yd] = 0.0 if res else sub(we_x, yd, w)
+        elif (di, dj) == (1, -1):
+            we_y[idx] = sub(we_y, idx, 0.5 * w)
+            if yd < n:
+                we_x[yd] = 0.0 if res else sub(we_x, yd, 0.5 * w)
+        elif (di, dj) == (-1, 1):
+            if xd < n:
+                we_y[xd] = 0.0 if res else sub(we_y, xd, 0.5 * w)
+            we_x[idx] = 0.0 if res else sub(we_x, idx, 0.5 * w)
+
+
 def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                soil_layer_thickness_mm=(100, 300, 800), mask=None, river_fraction_target=0.116,
                cell_length: float = 1000.0, snow: bool = True, glacier: bool = False,
@@ -206,7 +267,7 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
                external_inflow: bool = False, network: str = "scheidegger",
                n_active: int | None = None, n_river: int | None = None, reservoirs: int = 0,
                snow_transport: bool = False, river_routing: int = 0, catchment_length: int = 0,
-               floodplain: bool = False):
+               floodplain: bool = False, land_routing: int = 0):
     """Returns (cfg, domain, fields). `fields` holds every input array of the hot path under
     the reference's field names; layered arrays are cell-major (n, N). network: "scheidegger"
     (a forest of many small basins, codes 5/7/8/9) or "dendritic" (one outlet, all eight
@@ -520,6 +581,52 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
         for name in ("res_inflow_overland", "res_inflow_subsurface", "res_outflow"):
             F[name] = np.zeros(nres)
 
+    # ---- 2-D local-inertial overland flow coupled to the local-inertial river ------------------
+    # (LocalInertialOverlandFlowParameters surface_staggered_scheme.jl:894-961; the host prepares
+    # the edge parameters like the Julia model does: EdgeConnectivity network.jl:136-153,
+    # set_effective_flowwidth! utils.jl:604-669)
+    edges = None
+    if land_routing == 1:
+        assert river_routing == 1 and not floodplain, "land_routing = 1 needs river_routing = 1, no 1-D floodplain"
+        edges = edge_connectivity(indices, d1, d2)
+        x_up, y_up = edges["ind_x_up"] - 1, edges["ind_y_up"] - 1       # 0-based, n = none
+        x_down, y_down = edges["ind_x_down"] - 1, edges["ind_y_down"] - 1
+        x_len = cell_length * (0.9 + 0.2 * u01(seed, 100, gid))
+        y_len = F["area"] / x_len
+        # ground elevation: falls along the drainage paths (2 per mille), pits at 10 .. 12 m
+        z = 10.0 + 2.0 * u01(seed, 101, gid)
+        rise = 0.002 * F["flow_length"] * (0.5 + u01(seed, 102, gid))
+        for v in np.argsort(-acc, kind="stable"):                   # downstream cells first
+            if down[v] > 0:
+                z[v] = z[down[v] - 1] + rise[v]
+        zx_max, zy_max = np.zeros(n), np.zeros(n)
+        sx, sy = x_up < n, y_up < n
+        zx_max[sx] = np.maximum(z[sx], z[x_up[sx]])
+        zy_max[sy] = np.maximum(z[sy], z[y_up[sy]])
+        mann = _pm20(seed, 103, gid, 0.072)
+        we_x, we_y = x_len.copy(), y_len.copy()
+        res_outlet = np.zeros(nriv, dtype=bool)
+        if nres:
+            res_outlet[reservoir_river_indices - 1] = True
+        if nriv:
+            _set_effective_flowwidth(we_x, we_y, ldd[ridx], down[ridx], ridx, river,
+                                     F["riv_flow_width"], res_outlet, x_down, y_down, n, acc[ridx])
+            bankfull_depth = 0.05 + 0.5 * u01(seed, 104, rg)
+            F["li_bankfull_depth"] = bankfull_depth
+            F["li_bankfull_storage"] = bankfull_depth * F["riv_flow_width"] * F["riv_flow_length"]
+            zb = z[ridx] - bankfull_depth                           # bankfull elevation - depth
+            rd = np.where(rdown > 0, rdown - 1, np.arange(nriv))
+            F["li_zb"] = zb
+            F["li_zb_at_edge"] = np.maximum(zb, zb[rd])
+        F["li_land_xwidth_at_edge"], F["li_land_ywidth_at_edge"] = we_x, we_y
+        F["li_land_zx_max_at_edge"], F["li_land_zy_max_at_edge"] = zx_max, zy_max
+        F["li_land_mannings_n_sq_at_edge"] = mann * mann
+        F["li_land_z"] = z
+        F["li_land_x_length"], F["li_land_y_length"] = x_len, y_len
+        for k in ("li_land_qx", "li_land_qy", "li_land_qx0", "li_land_qy0", "li_land_error",
+                  "li_land_runoff"):
+            F[k] = np.zeros(n)
+
     cfg = dict(n=n, nriv=nriv, nres=nres, n_layers=N, N=N, gash=int(dt >= 23 * 3600.0), has_lai=1,
                snow=int(snow), glacier=int(glacier),
                soil_infiltration_reduction=int(soil_infiltration_reduction),
@@ -534,6 +641,10 @@ def make_basin(d1: int, d2: int, seed: int = 42, dt: float = 86400.0,
     domain = dict(d1=d1, d2=d2, indices=indices, ldd=ldd, river_land_indices=river_land_indices,
                   down=down, gid=gid, upstream_cells=acc,
                   reservoir_river_indices=reservoir_river_indices)
+    if land_routing == 1:
+        cfg.update(land_routing=1, li_land_alpha=0.7, li_land_theta=0.9, li_land_h_thresh=1.0e-3,
+                   li_land_froude_limit=1)
+        domain["edges"] = edges
     return cfg, domain, F
 
 
