@@ -1830,9 +1830,8 @@ static int32_t update_model_step(WflowB200* h, double dt) {
   if (h->cfg.land_routing == 1) {  // surface_routing! with local-inertial land AND river routing
     if ((rc = wflowb200_update_bc_overland_flow_model(h))) return rc;   // surface_routing.jl:62-86
     if ((rc = wflowb200_update_inflow_reservoir(h))) return rc;
-    mark(6);
-    if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;
-    mark(7); mark(8);
+    if ((rc = wflowb200_update_overland_flow_model(h, dt))) return rc;  // (timed as "overland")
+    mark(6); mark(7); mark(8);
     if ((rc = wflowb200_update_total_water_storage(h))) return rc;
     mark(9);
     return book_stage_times(h);
