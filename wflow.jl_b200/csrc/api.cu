@@ -277,6 +277,7 @@ struct WflowB200 {
   Tuning tune{};
   int n = 0, nriv = 0, N = 0, ns = 0, nrs = 0, nres = 0, nress = 0;
   int32_t* res_ident = nullptr;      // identity slot map of the reservoir fields
+  int32_t* land_ident = nullptr;     // ... and of the node-ordered li_land_* fields (kind 6)
   DomainDev land, river;
   DomainDev land_full;               // device arrays only (nw unused): land chunks without the
   DomainDev* snow_net = nullptr;     // reservoir cut, for lateral snow transport
@@ -398,6 +399,13 @@ int32_t check_device_error(WflowB200* h) {
   return WFLOWB200_OK;
 }
 
+// device slot -> host element of a field kind: the drainage-order permutation of the land / river
+// fields, the identity for reservoirs and for the node-ordered 2-D overland-flow fields (kind 6)
+const int32_t* slot_map_of(const WflowB200* h, int kind) {
+  if (kind == 4) return h->res_ident;
+  if (kind == 6) return h->land_ident;
+  return ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
+}
 int layers_of(const WflowB200* h, int kind) {
   return kind == 1 ? h->N : kind == 2 ? h->N + 1 : kind == 5 ? std::max(h->cfg.fp_levels, 1) : 1;
 }
@@ -1153,22 +1161,32 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     if (h->grid_li <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
   }
   h->kc.land_routing = cfg->land_routing;
-  if (cfg->land_routing == 1) {   // EdgeConnectivity by land slot (network.jl:136-153): -1 = no neighbour
-    const Network& ln = h->land.nw;
-    std::vector<int64_t> e[4];
-    const std::vector<int64_t>* src[4] = {&ln.edge_x_up, &ln.edge_x_down, &ln.edge_y_up, &ln.edge_y_down};
-    for (int k = 0; k < 4; ++k) {
-      e[k].assign(std::max(h->ns, 1), -1);
-      for (int p = 0; p < h->n; ++p) {
-        const int64_t nb = (*src[k])[ln.perm[p] - 1];
-        e[k][p] = nb <= h->n ? ln.slot_of[nb - 1] : -1;
-      }
+  if (cfg->land_routing == 1) {   // the 2-D state is kept in NODE order (local_inertial.cu)
+    const Network& ln = h->land.nw;   // EdgeConnectivity (network.jl:136-153): -1 = no neighbour
+    auto by_node = [&](const std::vector<int64_t>& src) {
+      std::vector<int64_t> e(std::max(h->n, 1), -1);
+      for (int v = 0; v < h->n; ++v) e[v] = src[v] <= h->n ? src[v] - 1 : -1;
+      return e;
+    };
+    TRY_CREATE(upload_i32(by_node(ln.edge_x_up), &h->f.edge_x_up, 0));
+    TRY_CREATE(upload_i32(by_node(ln.edge_x_down), &h->f.edge_x_down, 0));
+    TRY_CREATE(upload_i32(by_node(ln.edge_y_up), &h->f.edge_y_up, 0));
+    TRY_CREATE(upload_i32(by_node(ln.edge_y_down), &h->f.edge_y_down, 0));
+    std::vector<int64_t> river_of_node(h->n, -1), ident(h->n);   // domain.land.network.river_indices
+    for (int r = 0; r < h->nriv; ++r)
+      river_of_node[dom->river_land_indices[r] - 1] = h->river.nw.slot_of[r];
+    for (int v = 0; v < h->n; ++v) ident[v] = v;
+    TRY_CREATE(upload_i32(river_of_node, &h->f.lil_river_slot, 0));
+    TRY_CREATE(upload_i32(ln.slot_of, &h->f.land_slot_of_node, 0));
+    TRY_CREATE(upload_i32(ident, &h->land_ident, 0));
+    if (h->nres > 0) {
+      std::vector<int64_t> res_node(h->nres);
+      for (int i = 0; i < h->nres; ++i)
+        res_node[i] = dom->river_land_indices[dom->reservoir_river_indices[i] - 1] - 1;
+      TRY_CREATE(upload_i32(res_node, &h->f.res_land_node, 0));
     }
-    TRY_CREATE(upload_i32(e[0], &h->f.edge_x_up, 0));
-    TRY_CREATE(upload_i32(e[1], &h->f.edge_x_down, 0));
-    TRY_CREATE(upload_i32(e[2], &h->f.edge_y_up, 0));
-    TRY_CREATE(upload_i32(e[3], &h->f.edge_y_down, 0));
-    h->f.land_river_slot = h->riv_of_land;   // domain.land.network.river_indices by slot
+    TRY_CREATE(cudaMalloc((void**)&h->f.lil_h, (size_t)h->n * sizeof(double)));
+    TRY_CREATE(cudaMalloc((void**)&h->f.lil_storage, (size_t)h->n * sizeof(double)));
     h->grid_lil = lil_max_grid(cfg->device);
     if (h->grid_lil <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
   }
@@ -1218,6 +1236,8 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->f.riv_reservoir); cudaFree(h->f.res_land_slot); cudaFree(h->res_ident);
   cudaFree(h->f.res_river_slot); cudaFree(h->f.li_dst_slot); cudaFree(h->f.li_in_ptr);
   cudaFree(h->f.edge_x_up); cudaFree(h->f.edge_x_down); cudaFree(h->f.edge_y_up); cudaFree(h->f.edge_y_down);
+  cudaFree(h->f.lil_river_slot); cudaFree(h->f.land_slot_of_node); cudaFree(h->f.res_land_node);
+  cudaFree(h->f.lil_h); cudaFree(h->f.lil_storage); cudaFree(h->land_ident);
   cudaFree(h->f.li_in_idx); cudaFree(h->d_li_barrier); cudaFree(h->d_li_dt); cudaFree(h->d_li_substeps);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);
@@ -1270,7 +1290,7 @@ int32_t wflowb200_set_field(WflowB200* h, int32_t id, const double* src, int64_t
   if (count == 0) return WFLOWB200_OK;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, src, extent * sizeof(double), cudaMemcpyHostToDevice,
                               h->stream));
-  const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
+  const int32_t* slot_map = slot_map_of(h, kind);
   h->launches += launch_gather_field(h->field_ptr[id], h->d_stage, slot_map, count,
                                      slots_of(h, kind), layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1286,7 +1306,7 @@ int32_t wflowb200_get_field(WflowB200* h, int32_t id, double* dst, int64_t sc, i
   if (count == 0) return WFLOWB200_OK;
   rc = wait_forcing(h);
   if (rc) return rc;
-  const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
+  const int32_t* slot_map = slot_map_of(h, kind);
   h->launches += launch_scatter_field(h->d_stage, h->field_ptr[id], slot_map, count,
                                       slots_of(h, kind), layers, sc, sl, h->stream);
   CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_stage, extent * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1451,7 +1471,7 @@ int32_t wflowb200_get_fields(WflowB200* h, const int32_t* ids, int32_t n_ids, do
     const int kind = kFieldKinds[ids[k]];
     const int layers = layers_of(h, kind), count = count_of(h, kind);
     if (count == 0) continue;
-    const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
+    const int32_t* slot_map = slot_map_of(h, kind);
     h->launches += launch_scatter_field(h->d_stage + off, h->field_ptr[ids[k]], slot_map, count,
                                         slots_of(h, kind), layers, layers, 1, h->stream);
     off += (size_t)count * layers;
@@ -1505,7 +1525,7 @@ int32_t wflowb200_get_fields_async(WflowB200* h, const int32_t* ids, int32_t n_i
     const int kind = kFieldKinds[ids[k]];
     const int layers = layers_of(h, kind), count = count_of(h, kind);
     if (count == 0) continue;
-    const int32_t* slot_map = kind == 4 ? h->res_ident : ((kind == 3 || kind == 5) ? h->river : h->land).node_of_slot;
+    const int32_t* slot_map = slot_map_of(h, kind);
     h->launches += launch_scatter_field(h->d_out[b] + off, h->field_ptr[ids[k]], slot_map, count,
                                         slots_of(h, kind), layers, layers, 1, h->stream);
     off += (size_t)count * layers;

@@ -328,14 +328,18 @@ __device__ __forceinline__ double local_inertial_flow_rect(double theta, double 
                                                            double width, double length,
                                                            double mannings_n_sq, int froude_limit,
                                                            double dt) {
-  const double slope = (zs1 - zs0) / length;
+  // fdiv: the correctly rounded quotient without nvcc's guard, which sends every ZERO numerator
+  // (still water: the common case) through a ~90-instruction slow path; every divisor here is a
+  // normal number (cell lengths, hf > h_thresh, width != 0, 1 + a non-negative term)
+  const double slope = fdiv(zs1 - zs0, length);
   const double pow_hf = cbrt(hf * hf * hf * hf * hf * hf * hf);
-  double q = (((theta * q0 + 0.5 * (1.0 - theta) * (qu + qd)) - kG * hf * width * dt * slope) /
-              (1.0 + kG * dt * mannings_n_sq * fabs(q0) / (pow_hf * width)));
+  double q = fdiv((theta * q0 + 0.5 * (1.0 - theta) * (qu + qd)) - kG * hf * width * dt * slope,
+                  1.0 + fdiv(kG * dt * mannings_n_sq * fabs(q0), pow_hf * width));
   if (froude_limit) {
-    const double fr = (q / width / hf) / sqrt(kG * hf);
-    if (fabs(fr) > 1.0 && q > 0.0) q = hf * sqrt(kG * hf) * width;
-    else if (fabs(fr) > 1.0 && q < 0.0) q = -hf * sqrt(kG * hf) * width;
+    const double celerity = sqrt(kG * hf);
+    const double fr = fdiv(fdiv(fdiv(q, width), hf), celerity);
+    if (fabs(fr) > 1.0 && q > 0.0) q = hf * celerity * width;
+    else if (fabs(fr) > 1.0 && q < 0.0) q = -hf * celerity * width;
   }
   return q;
 }
@@ -371,6 +375,12 @@ __device__ __forceinline__ void lil_directional_flow(const LiLaunch& w, const in
 
 __global__ void __launch_bounds__(kLiBlock, 2)
 local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg c, const LiLaunch w) {
+  // The 2-D state lives in NODE order (the reference's own order: column-major over the raster),
+  // not in the slot order of the wavefront kernels: a cell's x neighbours are its neighbours in
+  // memory and its y neighbours sit one raster column away, so the neighbour loads of a warp are
+  // coalesced. h and storage (olf_h / olf_storage, slot order, shared with the vertical update)
+  // are gathered into node-ordered work arrays at the start of the model step and scattered back
+  // at its end.
   const int n = c.n, nriv = c.nriv;
   const int stride = (int)(gridDim.x * blockDim.x);
   const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -380,17 +390,22 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
   const double dt = w.dt;
   const unsigned long long inf_bits = 0x7ff0000000000000ull;
   const double inf = __longlong_as_double((long long)inf_bits);
+  double* const land_h = f.lil_h;
+  double* const land_storage = f.lil_storage;
 
   // The Courant steps of the cells this thread owns: river nodes alpha L / sqrt(g h) (:1004-1020),
   // non-river land cells alpha min(dx, dy) / sqrt(g h) (:1022-1043)
   double mine_river = inf, mine_land = inf;
-  auto courant = [&](const int p, const int r, const double h_land, const double h_river) {
+  auto courant = [&](const int v, const int r, const double h_land, const double h_river) {
+    // (a dry cell gives alpha L / 0 = Inf, which never is the minimum: skipped)
     if (r >= 0) {
-      const double d = w.alpha * __ldg(f.riv_flow_length + r) / sqrt(kG * h_river);
-      mine_river = d < mine_river ? d : mine_river;
-    } else {
-      const double d = w.land_alpha * jmin(__ldg(f.li_land_x_length + p), __ldg(f.li_land_y_length + p)) /
-                       sqrt(kG * h_land);
+      if (h_river > 0.0) {
+        const double d = fdiv(w.alpha * __ldg(f.riv_flow_length + r), sqrt(kG * h_river));
+        mine_river = d < mine_river ? d : mine_river;
+      }
+    } else if (h_land > 0.0) {
+      const double d = fdiv(w.land_alpha * jmin(__ldg(f.li_land_x_length + v), __ldg(f.li_land_y_length + v)),
+                            sqrt(kG * h_land));
       mine_land = d < mine_land ? d : mine_land;
     }
   };
@@ -398,14 +413,18 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
   // set_reservoir_vars! / set_flow_vars! (river :269-275, overland :1127-1132); qx0 .= qx, qy0 .= qy
   // of the first sub-step (:1284-1285)
   for (int p = tid; p < nriv; p += stride) f.riv_q_cumulative[p] = 0.0;
-  for (int p = tid; p < n; p += stride) {
-    f.li_land_qx_cumulative[p] = 0.0;
-    f.li_land_qy_cumulative[p] = 0.0;
-    f.li_land_qx0[p] = f.li_land_qx[p];
-    f.li_land_qy0[p] = f.li_land_qy[p];
-    const int r = f.land_river_slot[p];
+  for (int v = tid; v < n; v += stride) {
+    f.li_land_qx_cumulative[v] = 0.0;
+    f.li_land_qy_cumulative[v] = 0.0;
+    f.li_land_qx0[v] = f.li_land_qx[v];
+    f.li_land_qy0[v] = f.li_land_qy[v];
+    const int slot = f.land_slot_of_node[v];
+    const double h0 = f.olf_h[slot];
+    land_h[v] = h0;
+    land_storage[v] = f.olf_storage[slot];
+    const int r = f.lil_river_slot[v];
     if (r >= 0) f.riv_actual_external_abstraction_cumulative[r] = 0.0;
-    courant(p, r, f.olf_h[p], r >= 0 ? f.riv_h[r] : 0.0);
+    courant(v, r, h0, r >= 0 ? f.riv_h[r] : 0.0);
   }
   for (int i = tid; i < c.nres; i += stride) {
     f.res_inflow_cumulative[i] = 0.0;
@@ -450,16 +469,16 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
     if (t + dt_s > dt) dt_s = dt - t;  // check_timestepsize  routing/timestepping.jl:11-16
 
     // ---- local_inertial_update_fluxes!: the x and the y edge of every cell          :1276-1295 ----
-    for (int p = tid; p < n; p += stride) {
-      const double h_p = __ldcg(f.olf_h + p);
-      const double z_p = __ldg(f.li_land_z + p);
-      const double mann = __ldg(f.li_land_mannings_n_sq_at_edge + p);
-      lil_directional_flow(w, p, f.edge_x_up[p], f.edge_x_down[p], __ldg(f.li_land_ywidth_at_edge + p),
-                           __ldg(f.li_land_zx_max_at_edge + p), f.li_land_x_length, f.li_land_z, f.olf_h,
-                           h_p, z_p, mann, f.li_land_qx0, f.li_land_qx, f.li_land_qx_cumulative, dt_s);
-      lil_directional_flow(w, p, f.edge_y_up[p], f.edge_y_down[p], __ldg(f.li_land_xwidth_at_edge + p),
-                           __ldg(f.li_land_zy_max_at_edge + p), f.li_land_y_length, f.li_land_z, f.olf_h,
-                           h_p, z_p, mann, f.li_land_qy0, f.li_land_qy, f.li_land_qy_cumulative, dt_s);
+    for (int v = tid; v < n; v += stride) {
+      const double h_v = __ldcg(land_h + v);
+      const double z_v = __ldg(f.li_land_z + v);
+      const double mann = __ldg(f.li_land_mannings_n_sq_at_edge + v);
+      lil_directional_flow(w, v, f.edge_x_up[v], f.edge_x_down[v], __ldg(f.li_land_ywidth_at_edge + v),
+                           __ldg(f.li_land_zx_max_at_edge + v), f.li_land_x_length, f.li_land_z, land_h,
+                           h_v, z_v, mann, f.li_land_qx0, f.li_land_qx, f.li_land_qx_cumulative, dt_s);
+      lil_directional_flow(w, v, f.edge_y_up[v], f.edge_y_down[v], __ldg(f.li_land_xwidth_at_edge + v),
+                           __ldg(f.li_land_zy_max_at_edge + v), f.li_land_y_length, f.li_land_z, land_h,
+                           h_v, z_v, mann, f.li_land_qy0, f.li_land_qy, f.li_land_qy_cumulative, dt_s);
     }
     // ---- update_river_channel_flow!: the edge leaving every active river node        :326-383 ----
     for (int p = tid; p < nriv; p += stride) {
@@ -494,16 +513,16 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
 
     // ---- update_inflow_reservoir! (:1301-1319) + update_bc_reservoir_model! (:627-661) -----------
     if (c.nres > 0) {
-      for (int v = tid; v < c.nres; v += stride) {
-        const int p = f.res_river_slot[v];
-        const int j = f.res_land_slot[v];
+      for (int i = tid; i < c.nres; i += stride) {
+        const int p = f.res_river_slot[i];
+        const int j = f.res_land_node[i];
         const int xd = f.edge_x_down[j], yd = f.edge_y_down[j];
         const double net_land_flow = (xd >= 0 ? __ldcg(f.li_land_qx + xd) : 0.0) - __ldcg(f.li_land_qx + j) +
                                      (yd >= 0 ? __ldcg(f.li_land_qy + yd) : 0.0) - __ldcg(f.li_land_qy + j);
-        f.res_inflow_overland[v] = f.li_land_runoff[j] + (net_land_flow);
+        f.res_inflow_overland[i] = f.li_land_runoff[j] + (net_land_flow);
         double q_in = 0.0;  // sum_at(q, edges_at_node.src[i])
         for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_in += __ldcg(f.riv_q + f.li_in_idx[e]);
-        const double outflow = reservoir_step(f, v, q_in, dt_s);
+        const double outflow = reservoir_step(f, i, q_in, dt_s);
         __stcg(f.riv_q + p, outflow);
         __stcg(f.riv_q_cumulative + p, __ldcg(f.riv_q_cumulative + p) + outflow * dt_s);
       }
@@ -515,32 +534,32 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
     const bool last = !(t + dt_s < dt);
     mine_river = inf;
     mine_land = inf;
-    for (int p = tid; p < n; p += stride) {
-      const int r = f.land_river_slot[p];
-      const int xd = f.edge_x_down[p], yd = f.edge_y_down[p];
-      const double qx_p = __ldcg(f.li_land_qx + p), qy_p = __ldcg(f.li_land_qy + p);
-      const double net_land_flow = (xd >= 0 ? __ldcg(f.li_land_qx + xd) : 0.0) - qx_p +
-                                   (yd >= 0 ? __ldcg(f.li_land_qy + yd) : 0.0) - qy_p;
+    for (int v = tid; v < n; v += stride) {
+      const int r = f.lil_river_slot[v];
+      const int xd = f.edge_x_down[v], yd = f.edge_y_down[v];
+      const double qx_v = __ldcg(f.li_land_qx + v), qy_v = __ldcg(f.li_land_qy + v);
+      const double net_land_flow = (xd >= 0 ? __ldcg(f.li_land_qx + xd) : 0.0) - qx_v +
+                                   (yd >= 0 ? __ldcg(f.li_land_qy + yd) : 0.0) - qy_v;
       if (!last) {  // qx0 .= qx, qy0 .= qy of the next sub-step (:1284-1285): this thread's own edges
-        __stcg(f.li_land_qx0 + p, qx_p);
-        __stcg(f.li_land_qy0 + p, qy_p);
+        __stcg(f.li_land_qx0 + v, qx_v);
+        __stcg(f.li_land_qy0 + v, qy_v);
       }
-      const double runoff = f.li_land_runoff[p];
-      double storage = f.olf_storage[p];
+      const double runoff = f.li_land_runoff[v];
+      double storage = land_storage[v];
       if (r < 0) {  // update_land_storage_and_depth!                                  :1491-1514
         storage += (net_land_flow + runoff) * dt_s;
         if (storage < 0.0) {
-          f.li_land_error[p] += fabs(storage);
+          f.li_land_error[v] += fabs(storage);
           storage = 0.0;
         }
-        const double h_new = storage / (__ldg(f.li_land_x_length + p) * __ldg(f.li_land_y_length + p));
-        f.olf_storage[p] = storage;
-        __stcg(f.olf_h + p, h_new);
-        courant(p, r, h_new, 0.0);
+        const double h_new = fdiv(storage, __ldg(f.li_land_x_length + v) * __ldg(f.li_land_y_length + v));
+        land_storage[v] = storage;
+        __stcg(land_h + v, h_new);
+        courant(v, r, h_new, 0.0);
         continue;
       }
       if (f.riv_reservoir && f.riv_reservoir[r] >= 0) {  // reservoir outlet: h stays as it is
-        courant(p, r, 0.0, f.riv_h[r]);
+        courant(v, r, 0.0, f.riv_h[r]);
         continue;
       }
       // update_river_and_land_storage_and_depth!                                      :1443-1485
@@ -551,7 +570,7 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
       const double net_flow = net_river_flow + net_land_flow + runoff - __ldg(f.riv_abstraction + r);
       storage += net_flow * dt_s;
       if (storage < 0.0) {
-        f.li_land_error[p] += fabs(storage);
+        f.li_land_error[v] += fabs(storage);
         storage = 0.0;
       }
       const double bankfull_storage = __ldg(f.li_bankfull_storage + r);
@@ -567,35 +586,39 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
       }
       storage += inflow * dt_s;
       const double length = __ldg(f.riv_flow_length + r), width = __ldg(f.riv_flow_width + r);
-      double river_h, land_h, river_storage;  // compute_water_depths                  :1388-1416
+      double river_h, h_new, river_storage;  // compute_water_depths                   :1388-1416
       if (storage >= bankfull_storage) {
         const double bankfull_depth = __ldg(f.li_bankfull_depth + r);
-        river_h = bankfull_depth + (storage - bankfull_storage) /
-                                       (__ldg(f.li_land_x_length + p) * __ldg(f.li_land_y_length + p));
-        land_h = river_h - bankfull_depth;
+        river_h = bankfull_depth + fdiv(storage - bankfull_storage,
+                                        __ldg(f.li_land_x_length + v) * __ldg(f.li_land_y_length + v));
+        h_new = river_h - bankfull_depth;
         river_storage = river_h * length * width;
       } else {
-        river_h = storage / (length * width);
-        land_h = 0.0;
+        river_h = fdiv(storage, length * width);
+        h_new = 0.0;
         river_storage = storage;
       }
-      f.olf_storage[p] = storage;
+      land_storage[v] = storage;
       __stcg(f.riv_h + r, river_h);
-      __stcg(f.olf_h + p, land_h);
+      __stcg(land_h + v, h_new);
       f.riv_storage[r] = river_storage;
-      courant(p, r, land_h, river_h);
+      courant(v, r, h_new, river_h);
     }
     t += dt_s;
     ++count;
     // (no barrier here: the next sub-step's minimum is formed from this thread's own new depths,
     // and its edge phase comes after the barrier that follows the minimum)
   }
-  // average_flow_vars! (river :283-290, overland :1138-1147) / average_reservoir_vars!
+  // average_flow_vars! (river :283-290, overland :1138-1147) / average_reservoir_vars!; h and
+  // storage back into the arrays the vertical update and the output read (this thread's own cells)
   for (int p = tid; p < nriv; p += stride) f.riv_q_average[p] = __ldcg(f.riv_q_cumulative + p) / dt;
-  for (int p = tid; p < n; p += stride) {
-    f.li_land_qx_average[p] = f.li_land_qx_cumulative[p] / dt;
-    f.li_land_qy_average[p] = f.li_land_qy_cumulative[p] / dt;
-    const int r = f.land_river_slot[p];
+  for (int v = tid; v < n; v += stride) {
+    f.li_land_qx_average[v] = f.li_land_qx_cumulative[v] / dt;
+    f.li_land_qy_average[v] = f.li_land_qy_cumulative[v] / dt;
+    const int slot = f.land_slot_of_node[v];
+    f.olf_h[slot] = __ldcg(land_h + v);
+    f.olf_storage[slot] = land_storage[v];
+    const int r = f.lil_river_slot[v];
     if (r >= 0)
       f.riv_actual_external_abstraction_average[r] = f.riv_actual_external_abstraction_cumulative[r] / dt;
   }
@@ -627,11 +650,12 @@ int launch_local_inertial_land_river(const DevFields& f, const KCfg& c, const Li
 
 // update_bc_overland_flow_model!                              surface_staggered_scheme.jl:1080-1097
 __global__ void bc_overland_flow_kernel(const DevFields f, const KCfg c) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= c.n) return;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;   // node order (the 2-D state's order)
+  if (v >= c.n) return;
+  const int p = f.land_slot_of_node[v];
   double runoff = (f.net_runoff[p] + f.net_runoff_river[p]) * f.area[p];
-  if (f.land_river_slot[p] >= 0) runoff += f.ssf_to_river_average[p];  // get_flux_to_river  lsf.jl:346
-  f.li_land_runoff[p] = runoff;
+  if (f.lil_river_slot[v] >= 0) runoff += f.ssf_to_river_average[p];  // get_flux_to_river  lsf.jl:346
+  f.li_land_runoff[v] = runoff;
 }
 
 int launch_bc_overland_flow(const DevFields& f, const KCfg& c, cudaStream_t s) {

@@ -31,8 +31,12 @@ struct DevFields {
   int32_t* li_in_idx;          // ascending source NODE id (sum_at order)
   // 2-D local-inertial overland flow: EdgeConnectivity by land slot (-1: no active neighbour) and
   // domain.land.network.river_indices (land slot -> river slot, -1: no river in the cell)
+  // (all by NODE id: the 2-D state li_land_* is kept in node order, see local_inertial.cu)
   int32_t *edge_x_up, *edge_x_down, *edge_y_up, *edge_y_down;
-  int32_t* land_river_slot;
+  int32_t* lil_river_slot;     // node -> river slot or -1
+  int32_t* land_slot_of_node;  // node -> land slot (olf_h / olf_storage, the vertical fields)
+  int32_t* res_land_node;      // reservoir -> node of its outlet cell
+  double *lil_h, *lil_storage; // work arrays: h and storage by node during a model step
   uint8_t* land_is_res_outlet; // land slot is a reservoir outlet (nullptr without reservoirs)
   int32_t* olf_newton_trace;   // land / river, or nullptr: Newton iterations of kinematic_wave
   int32_t* riv_newton_trace;   // per node since wflowb200_newton_trace(h, 1)
