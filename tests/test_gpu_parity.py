@@ -302,6 +302,27 @@ def test_local_inertial_land_and_river_flow(pkg, reservoirs, fine_grained):
     _close(gpu)
 
 
+def test_local_inertial_land_edge_cases(pkg):
+    """The 2-D local-inertial overland flow on a masked raster (cells whose neighbours are inactive
+    or outside: EdgeConnectivity n + 1), on a domain without any river cell, on one-cell and
+    two-cell domains, and together with adaptive internal time steps of the subsurface flow."""
+    mask = np.ones((37, 53), dtype=bool)
+    mask[:5, :7] = False
+    mask[20:, 40:] = False
+    mask[10:14, 22:30] = False
+    cases = [dict(d=(37, 53), kw=dict(mask=mask)), dict(d=(24, 30), kw=dict(river_fraction_target=0.0)),
+             dict(d=(1, 1), kw={}), dict(d=(2, 1), kw={}), dict(d=(1, 40), kw={}),
+             dict(d=(30, 44), kw=dict(adaptive=True))]
+    for case in cases:
+        gpu, ora, cfg = parity.run_pair(pkg, *case["d"], steps=3, seed=5, river_routing=1,
+                                        land_routing=1, **case["kw"])
+        rep = parity.compare_models(gpu, ora, outliers=(1.0, 1e-5))
+        st, o = gpu.stats(), ora.newton_stats()
+        assert abs(st["substeps_river"] - o["substeps_river"]) <= 1, case["d"]
+        print(case["d"], "n", cfg["n"], "nriv", cfg["nriv"], rep.summary(), "sub-steps", st["substeps_river"])
+        _close(gpu)
+
+
 @pytest.mark.parametrize("adaptive", [False, True])
 def test_kinematic_wave_river_with_floodplain(pkg, adaptive):
     """floodplain_1d__flag with the kinematic-wave river: per sub-step the channel-floodplain
