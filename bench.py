@@ -155,6 +155,11 @@ def dist_env():
 
 
 def workload_text(d1, d2, adaptive, local_inertial=False):
+    if HOURLY and not local_inertial:
+        return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical (HOURLY step: modified "
+                "Rutter interception) + kinematic-wave river/overland/subsurface, "
+                + ("adaptive internal steps" if adaptive else "fixed internal steps 3600/900/86400 s "
+                   "(1 / 4 / 1 sub-steps per hour)") + ", N=4 soil layers, snow on")
     if local_inertial == 2:
         return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical + kinematic-wave "
                 "subsurface + 2-D LOCAL-INERTIAL overland flow coupled to the LOCAL-INERTIAL river "
@@ -177,6 +182,9 @@ def config_block(workload, n, nriv, world):
             "parallelism": f"{world} x disjoint sub-catchment tiles, no collective"}
 
 
+HOURLY = False   # --hourly: BASELINE configs[4] (hourly forcing => modified Rutter interception)
+
+
 def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0, local_inertial=False):
     """One sub-catchment tile per rank: a d1 x d2 Scheidegger forest whose cell ids are offset so
     that every tile of the global raster is a different random forest. Only the rank's own
@@ -184,6 +192,8 @@ def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0, local_iner
     extra = dict(river_routing=1, floodplain=True) if local_inertial else {}
     if local_inertial == 2:
         extra = dict(river_routing=1, land_routing=1)
+    if HOURLY:
+        extra["dt"] = 3600.0
     return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive,
                                     catchment_length=catchment_length, **extra)
 
@@ -304,6 +314,8 @@ def main():
     ap.add_argument("--local-inertial-land", action="store_true",
                     help="2-D local-inertial overland flow coupled to the local-inertial river "
                          "(land_routing = river_routing = local_inertial)")
+    ap.add_argument("--hourly", action="store_true",
+                    help="BASELINE configs[4]: hourly model step (modified Rutter interception)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-steps", type=int, default=2, help="oracle steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -316,6 +328,8 @@ def main():
     ap.add_argument("--cfg", action="append", default=[], metavar="NAME=INT",
                     help="WflowB200Config tuning field, e.g. vertical_slices=1")
     args = ap.parse_args()
+    global HOURLY
+    HOURLY = bool(args.hourly)
     if args.local_inertial_land:
         args.local_inertial = 2
     rank, world, local = dist_env()
