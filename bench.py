@@ -32,9 +32,10 @@ from __graft_entry__ import load_pkg  # noqa: E402
 METRIC = "cell-timesteps/s (SBM vertical + kinwave)"
 UNIT = "cell-timesteps/s"
 # DRAM bytes per cell of the vertical update (ncu dram__bytes_read.sum + dram__bytes_write.sum of
-# its kernels, profiles/r2_vertical_ncu.md), N = 4, Gash + snow
-V1_DRAM_BYTES_PER_CELL = 1618
-V1_TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_vertical_ncu.md"
+# its kernels, profiles/r2final_vertical_ncu.md: 448 + 314 + 258 + 13 + 512 + 177 MB per 10^6
+# cells), N = 4, Gash + snow, daily step
+V1_DRAM_BYTES_PER_CELL = 1722
+V1_TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2final_vertical_ncu.md"
 # a realistic per-step output set (write_output, io.jl:815-899; the Moselle TOML writes ~8 vectors)
 OUTPUT_FIELDS = ["riv_q_average", "riv_h", "snow_storage", "saturated_water_depth",
                  "unsaturated_store_depth", "total_storage", "olf_q_average",

@@ -1187,6 +1187,9 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
     }
     TRY_CREATE(cudaMalloc((void**)&h->f.lil_h, (size_t)h->n * sizeof(double)));
     TRY_CREATE(cudaMalloc((void**)&h->f.lil_storage, (size_t)h->n * sizeof(double)));
+    TRY_CREATE(cudaMalloc((void**)&h->f.lil_cell_area, (size_t)h->n * sizeof(double)));
+    TRY_CREATE(cudaMalloc((void**)&h->f.lil_xu_eff, (size_t)h->n * sizeof(int32_t)));
+    TRY_CREATE(cudaMalloc((void**)&h->f.lil_yu_eff, (size_t)h->n * sizeof(int32_t)));
     h->grid_lil = lil_max_grid(cfg->device);
     if (h->grid_lil <= 0) { h->err = "occupancy query failed"; return bail(WFLOWB200_ERR_CUDA); }
   }
@@ -1238,6 +1241,7 @@ void wflowb200_destroy(WflowB200* h) {
   cudaFree(h->f.edge_x_up); cudaFree(h->f.edge_x_down); cudaFree(h->f.edge_y_up); cudaFree(h->f.edge_y_down);
   cudaFree(h->f.lil_river_slot); cudaFree(h->f.land_slot_of_node); cudaFree(h->f.res_land_node);
   cudaFree(h->f.lil_h); cudaFree(h->f.lil_storage); cudaFree(h->land_ident);
+  cudaFree(h->f.lil_cell_area); cudaFree(h->f.lil_xu_eff); cudaFree(h->f.lil_yu_eff);
   cudaFree(h->f.li_in_idx); cudaFree(h->d_li_barrier); cudaFree(h->d_li_dt); cudaFree(h->d_li_substeps);
   cudaFree(h->f.riv_land_slot); cudaFree(h->riv_of_land); cudaFree(h->d_stage);
   cudaFree(h->d_forcing); cudaFreeHost(h->h_pinned); cudaFree(h->d_queue);

@@ -344,36 +344,9 @@ __device__ __forceinline__ double local_inertial_flow_rect(double theta, double 
   return q;
 }
 
-// update_directional_flow! for the edge of cell p in one direction              :1201-1271
-__device__ __forceinline__ void lil_directional_flow(const LiLaunch& w, const int p, const int up,
-                                                     const int down, const double width_at_edge,
-                                                     const double z_max_at_edge, const double* length_vec,
-                                                     const double* z, const double* h, const double h_p,
-                                                     const double z_p, const double mannings_n_sq,
-                                                     const double* q_prev, double* q_current,
-                                                     double* q_cumulative, const double dt_s) {
-  if (up < 0 || width_at_edge == 0.0) return;   // the flow of this edge stays what it is (0)
-  const double h_up = __ldcg(h + up);
-  const double zs_current = z_p + h_p;
-  const double zs_upstream = __ldg(z + up) + h_up;
-  const double zs_max_at_edge = jmax(zs_current, zs_upstream);
-  const double water_depth_at_edge = (zs_max_at_edge - z_max_at_edge);
-  double q = 0.0;
-  if (water_depth_at_edge > w.land_h_thresh) {
-    const double length_at_edge = 0.5 * (__ldg(length_vec + p) + __ldg(length_vec + up));
-    q = local_inertial_flow_rect(w.land_theta, __ldcg(q_prev + p), down >= 0 ? __ldcg(q_prev + down) : 0.0,
-                                 __ldcg(q_prev + up), zs_current, zs_upstream, water_depth_at_edge,
-                                 width_at_edge, length_at_edge, mannings_n_sq, w.land_froude_limit, dt_s);
-    if (h_p <= 0.0) q = jmin(q, 0.0);
-    if (h_up <= 0.0) q = jmax(q, 0.0);
-  }
-  __stcg(q_current + p, q);
-  q_cumulative[p] += q * dt_s;
-}
-
 }  // namespace
 
-__global__ void __launch_bounds__(kLiBlock, 2)
+__global__ void __launch_bounds__(kLiBlock, 4)
 local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg c, const LiLaunch w) {
   // The 2-D state lives in NODE order (the reference's own order: column-major over the raster),
   // not in the slot order of the wavefront kernels: a cell's x neighbours are its neighbours in
@@ -425,6 +398,11 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
     const int r = f.lil_river_slot[v];
     if (r >= 0) f.riv_actual_external_abstraction_cumulative[r] = 0.0;
     courant(v, r, h0, r >= 0 ? f.riv_h[r] : 0.0);
+    // the edges that carry flow (:1236: upstream_idx <= n && width_at_edge != 0) and the cell's
+    // area, once per model step (the widths are fields the host may have set since the last one)
+    f.lil_xu_eff[v] = f.li_land_ywidth_at_edge[v] != 0.0 ? f.edge_x_up[v] : -1;
+    f.lil_yu_eff[v] = f.li_land_xwidth_at_edge[v] != 0.0 ? f.edge_y_up[v] : -1;
+    f.lil_cell_area[v] = f.li_land_x_length[v] * f.li_land_y_length[v];
   }
   for (int i = tid; i < c.nres; i += stride) {
     f.res_inflow_cumulative[i] = 0.0;
@@ -470,15 +448,56 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
 
     // ---- local_inertial_update_fluxes!: the x and the y edge of every cell          :1276-1295 ----
     for (int v = tid; v < n; v += stride) {
+      // batch 1: the cell's own values and its edges (xu / yu: -1 also where the effective flow
+      // width is zero, see the prologue); batch 2: depth and elevation of the two upstream cells (a
+      // missing neighbour reads the cell itself). Everything else -- widths, roughness, lengths,
+      // the neighbours' previous flows -- is only loaded for an edge that is wet: most edges of a
+      // basin are dry, and the scheme is bound by the bytes it moves.
+      const int xu = f.lil_xu_eff[v], yu = f.lil_yu_eff[v];
       const double h_v = __ldcg(land_h + v);
       const double z_v = __ldg(f.li_land_z + v);
-      const double mann = __ldg(f.li_land_mannings_n_sq_at_edge + v);
-      lil_directional_flow(w, v, f.edge_x_up[v], f.edge_x_down[v], __ldg(f.li_land_ywidth_at_edge + v),
-                           __ldg(f.li_land_zx_max_at_edge + v), f.li_land_x_length, f.li_land_z, land_h,
-                           h_v, z_v, mann, f.li_land_qx0, f.li_land_qx, f.li_land_qx_cumulative, dt_s);
-      lil_directional_flow(w, v, f.edge_y_up[v], f.edge_y_down[v], __ldg(f.li_land_xwidth_at_edge + v),
-                           __ldg(f.li_land_zy_max_at_edge + v), f.li_land_y_length, f.li_land_z, land_h,
-                           h_v, z_v, mann, f.li_land_qy0, f.li_land_qy, f.li_land_qy_cumulative, dt_s);
+      const double zx_max = __ldg(f.li_land_zx_max_at_edge + v), zy_max = __ldg(f.li_land_zy_max_at_edge + v);
+      const double q0x = __ldcg(f.li_land_qx0 + v), q0y = __ldcg(f.li_land_qy0 + v);
+      const int xu_c = xu >= 0 ? xu : v, yu_c = yu >= 0 ? yu : v;
+      const double h_xu = __ldcg(land_h + xu_c), h_yu = __ldcg(land_h + yu_c);
+      const double z_xu = __ldg(f.li_land_z + xu_c), z_yu = __ldg(f.li_land_z + yu_c);
+      const double zs_v = z_v + h_v;
+      if (xu >= 0) {  // update_directional_flow!, x direction                        :1201-1271
+        const double zs_up = z_xu + h_xu;
+        const double hf = (jmax(zs_v, zs_up) - zx_max);
+        double q = 0.0;
+        if (hf > w.land_h_thresh) {
+          const int xd = f.edge_x_down[v];
+          const double length_at_edge = 0.5 * (__ldg(f.li_land_x_length + v) + __ldg(f.li_land_x_length + xu));
+          q = local_inertial_flow_rect(w.land_theta, q0x, xd >= 0 ? __ldcg(f.li_land_qx0 + xd) : 0.0,
+                                       __ldcg(f.li_land_qx0 + xu), zs_v, zs_up, hf,
+                                       __ldg(f.li_land_ywidth_at_edge + v), length_at_edge,
+                                       __ldg(f.li_land_mannings_n_sq_at_edge + v), w.land_froude_limit, dt_s);
+          if (h_v <= 0.0) q = jmin(q, 0.0);
+          if (h_xu <= 0.0) q = jmax(q, 0.0);
+        }
+        // qx[v] still holds q0x (qx0 .= qx): a flow that did not change is not written, and a flow
+        // of zero adds nothing to the cumulative flow (x + 0.0 == x)
+        if (__double_as_longlong(q) != __double_as_longlong(q0x)) __stcg(f.li_land_qx + v, q);
+        if (q != 0.0) f.li_land_qx_cumulative[v] += q * dt_s;
+      }
+      if (yu >= 0) {  // y direction
+        const double zs_up = z_yu + h_yu;
+        const double hf = (jmax(zs_v, zs_up) - zy_max);
+        double q = 0.0;
+        if (hf > w.land_h_thresh) {
+          const int yd = f.edge_y_down[v];
+          const double length_at_edge = 0.5 * (__ldg(f.li_land_y_length + v) + __ldg(f.li_land_y_length + yu));
+          q = local_inertial_flow_rect(w.land_theta, q0y, yd >= 0 ? __ldcg(f.li_land_qy0 + yd) : 0.0,
+                                       __ldcg(f.li_land_qy0 + yu), zs_v, zs_up, hf,
+                                       __ldg(f.li_land_xwidth_at_edge + v), length_at_edge,
+                                       __ldg(f.li_land_mannings_n_sq_at_edge + v), w.land_froude_limit, dt_s);
+          if (h_v <= 0.0) q = jmin(q, 0.0);
+          if (h_yu <= 0.0) q = jmax(q, 0.0);
+        }
+        if (__double_as_longlong(q) != __double_as_longlong(q0y)) __stcg(f.li_land_qy + v, q);
+        if (q != 0.0) f.li_land_qy_cumulative[v] += q * dt_s;
+      }
     }
     // ---- update_river_channel_flow!: the edge leaving every active river node        :326-383 ----
     for (int p = tid; p < nriv; p += stride) {
@@ -538,8 +557,9 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
       const int r = f.lil_river_slot[v];
       const int xd = f.edge_x_down[v], yd = f.edge_y_down[v];
       const double qx_v = __ldcg(f.li_land_qx + v), qy_v = __ldcg(f.li_land_qy + v);
-      const double net_land_flow = (xd >= 0 ? __ldcg(f.li_land_qx + xd) : 0.0) - qx_v +
-                                   (yd >= 0 ? __ldcg(f.li_land_qy + yd) : 0.0) - qy_v;
+      const double qx_xd = __ldcg(f.li_land_qx + (xd >= 0 ? xd : v));   // (a missing neighbour reads
+      const double qy_yd = __ldcg(f.li_land_qy + (yd >= 0 ? yd : v));   // the cell itself: unused)
+      const double net_land_flow = (xd >= 0 ? qx_xd : 0.0) - qx_v + (yd >= 0 ? qy_yd : 0.0) - qy_v;
       if (!last) {  // qx0 .= qx, qy0 .= qy of the next sub-step (:1284-1285): this thread's own edges
         __stcg(f.li_land_qx0 + v, qx_v);
         __stcg(f.li_land_qy0 + v, qy_v);
@@ -552,7 +572,7 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
           f.li_land_error[v] += fabs(storage);
           storage = 0.0;
         }
-        const double h_new = fdiv(storage, __ldg(f.li_land_x_length + v) * __ldg(f.li_land_y_length + v));
+        const double h_new = fdiv(storage, f.lil_cell_area[v]);
         land_storage[v] = storage;
         __stcg(land_h + v, h_new);
         courant(v, r, h_new, 0.0);
@@ -589,8 +609,7 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
       double river_h, h_new, river_storage;  // compute_water_depths                   :1388-1416
       if (storage >= bankfull_storage) {
         const double bankfull_depth = __ldg(f.li_bankfull_depth + r);
-        river_h = bankfull_depth + fdiv(storage - bankfull_storage,
-                                        __ldg(f.li_land_x_length + v) * __ldg(f.li_land_y_length + v));
+        river_h = bankfull_depth + fdiv(storage - bankfull_storage, f.lil_cell_area[v]);
         h_new = river_h - bankfull_depth;
         river_storage = river_h * length * width;
       } else {

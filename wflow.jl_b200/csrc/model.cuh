@@ -36,7 +36,9 @@ struct DevFields {
   int32_t* lil_river_slot;     // node -> river slot or -1
   int32_t* land_slot_of_node;  // node -> land slot (olf_h / olf_storage, the vertical fields)
   int32_t* res_land_node;      // reservoir -> node of its outlet cell
-  double *lil_h, *lil_storage; // work arrays: h and storage by node during a model step
+  double *lil_h, *lil_storage; // work arrays: h and storage by node during a model step,
+  double* lil_cell_area;       // x_length * y_length,
+  int32_t *lil_xu_eff, *lil_yu_eff;  // edge_x_up / edge_y_up, -1 also where the flow width is zero
   uint8_t* land_is_res_outlet; // land slot is a reservoir outlet (nullptr without reservoirs)
   int32_t* olf_newton_trace;   // land / river, or nullptr: Newton iterations of kinematic_wave
   int32_t* riv_newton_trace;   // per node since wflowb200_newton_trace(h, 1)
