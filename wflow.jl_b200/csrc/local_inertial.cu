@@ -93,8 +93,8 @@ __device__ __forceinline__ double local_inertial_flow(double q0, double zs0, dou
 
 }  // namespace
 
-__global__ void __launch_bounds__(kLiBlock, 2)
-local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
+__global__ void __launch_bounds__(kLiBlock, 3)
+local_inertial_river_kernel(const __grid_constant__ DevFields f, const KCfg c, const LiLaunch w) {
   const int n = c.nriv;
   const int stride = (int)(gridDim.x * blockDim.x);
   const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -149,6 +149,12 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
     if (t + dt_s > dt) dt_s = dt - t;  // check_timestepsize  routing/timestepping.jl:11-16
 
     // ---- update_river_channel_flow!: the edge leaving every active node ------------------------
+    // The scheme is bound by the bytes it moves: a discharge that did not change is not written
+    // back, a discharge of zero is not added to its cumulative value (x + 0.0 == x), the edge
+    // diagnostics (zs_at_edge, water_depth_at_edge) are written by the last sub-step only (every
+    // sub-step overwrites them), and the floodplain profile is only looked up where water stands
+    // above the floodplain's bed.
+    const bool last = !(t + dt_s < dt);
     for (int p = tid; p < n; p += stride) {
       const int d = f.li_dst_slot[p];
       if (d == -1) continue;
@@ -161,42 +167,49 @@ local_inertial_river_kernel(const DevFields f, const KCfg c, const LiLaunch w) {
       const double zs_dst = (d == -2 ? zb : __ldg(f.li_zb + d)) + h_dst;
       const double zs_at_edge = jmax(zs_src, zs_dst);
       const double hf = zs_at_edge - __ldg(f.li_zb_at_edge + p);
-      f.li_zs_at_edge[p] = zs_at_edge;
-      f.li_water_depth_at_edge[p] = hf;
-      const double width = __ldg(f.li_flow_width_at_edge + p);
-      const double A = width * hf;
-      const double R = A / (2.0 * hf + width);
-      double q = hf > w.h_thresh
-                     ? local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R,
-                                           __ldg(f.li_flow_length_at_edge + p),
-                                           __ldg(f.li_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
-                     : 0.0;
+      if (last) {
+        f.li_zs_at_edge[p] = zs_at_edge;
+        f.li_water_depth_at_edge[p] = hf;
+      }
+      double q = 0.0;
+      if (hf > w.h_thresh) {
+        const double width = __ldg(f.li_flow_width_at_edge + p);
+        const double A = width * hf;
+        const double R = A / (2.0 * hf + width);
+        q = local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R, __ldg(f.li_flow_length_at_edge + p),
+                                __ldg(f.li_mannings_n_sq_at_edge + p), w.froude_limit, dt_s);
+      }
       if (h_src <= 0.0) q = jmin(q, 0.0);
       if (h_dst <= 0.0) q = jmax(q, 0.0);
-      f.riv_q[p] = q;
-      f.riv_q_cumulative[p] += q * dt_s;
+      if (__double_as_longlong(q) != __double_as_longlong(q_previous)) f.riv_q[p] = q;
+      if (q != 0.0) f.riv_q_cumulative[p] += q * dt_s;
       if (floodplain) {  // update_floodplain_flow! of the same edge                 :440-533
         const double q_fp_previous = f.fp_q[p];
-        const int pd = d == -2 ? p : d;  // a ghost node copies the profile of its pit
         const double hfp = jmax(zs_at_edge - __ldg(f.fp_zb_at_edge + p), 0.0);
-        f.fp_water_depth_at_edge[p] = hfp;
-        int i1, i2;
-        fp_indices_depth(fp, hfp, i1, i2);
-        const double a_src = fp_flow_area(fp, hfp, p, i1, i2);
-        const double a_dst = fp_flow_area(fp, hfp, pd, i1, i2);
-        const double A_fp = jmin(a_src, a_dst);
-        const double R_fp = a_src < a_dst ? a_src / fp_wetted_perimeter(fp, hfp, p, i1)
-                                          : a_dst / fp_wetted_perimeter(fp, hfp, pd, i1);
-        double qf = A_fp > 1.0e-05
-                        ? local_inertial_flow(q_fp_previous, zs_src, zs_dst, hfp, A_fp, R_fp,
-                                              __ldg(f.li_flow_length_at_edge + p),
-                                              __ldg(f.fp_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
-                        : 0.0;
-        if (__ldcg(f.fp_h + p) <= 0.0) qf = jmin(qf, 0.0);
-        if ((d == -2 ? 0.0 : __ldcg(f.fp_h + d)) <= 0.0) qf = jmax(qf, 0.0);
-        if (qf * q < 0.0) qf = 0.0;  // opposite to the channel flow
-        f.fp_q[p] = qf;
-        f.fp_q_cumulative[p] += qf * dt_s;
+        if (last) f.fp_water_depth_at_edge[p] = hfp;
+        double qf = 0.0;
+        // (no water above the floodplain's bed and an empty first level of the profile: the flow
+        // area min(a_src, a_dst) is 0, the flow 0.0 -- without the lookups)
+        if (hfp > 0.0 || __ldg(f.fp_profile_flow_area + p) > 0.0) {
+          const int pd = d == -2 ? p : d;  // a ghost node copies the profile of its pit
+          int i1, i2;
+          fp_indices_depth(fp, hfp, i1, i2);
+          const double a_src = fp_flow_area(fp, hfp, p, i1, i2);
+          const double a_dst = fp_flow_area(fp, hfp, pd, i1, i2);
+          const double A_fp = jmin(a_src, a_dst);
+          const double R_fp = a_src < a_dst ? a_src / fp_wetted_perimeter(fp, hfp, p, i1)
+                                            : a_dst / fp_wetted_perimeter(fp, hfp, pd, i1);
+          qf = A_fp > 1.0e-05
+                   ? local_inertial_flow(q_fp_previous, zs_src, zs_dst, hfp, A_fp, R_fp,
+                                         __ldg(f.li_flow_length_at_edge + p),
+                                         __ldg(f.fp_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
+                   : 0.0;
+          if (__ldcg(f.fp_h + p) <= 0.0) qf = jmin(qf, 0.0);
+          if ((d == -2 ? 0.0 : __ldcg(f.fp_h + d)) <= 0.0) qf = jmax(qf, 0.0);
+          if (qf * q < 0.0) qf = 0.0;  // opposite to the channel flow
+        }
+        if (__double_as_longlong(qf) != __double_as_longlong(q_fp_previous)) f.fp_q[p] = qf;
+        if (qf != 0.0) f.fp_q_cumulative[p] += qf * dt_s;
       }
     }
     alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
@@ -446,6 +459,7 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
     double dt_s = jmin(dt_river, dt_land);
     if (t + dt_s > dt) dt_s = dt - t;  // check_timestepsize  routing/timestepping.jl:11-16
 
+    const bool last = !(t + dt_s < dt);   // the last sub-step of the model step
     // ---- local_inertial_update_fluxes!: the x and the y edge of every cell          :1276-1295 ----
     for (int v = tid; v < n; v += stride) {
       // batch 1: the cell's own values and its edges (xu / yu: -1 also where the effective flow
@@ -512,20 +526,22 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
       const double zs_dst = (d == -2 ? zb : __ldg(f.li_zb + d)) + h_dst;
       const double zs_at_edge = jmax(zs_src, zs_dst);
       const double hf = zs_at_edge - __ldg(f.li_zb_at_edge + p);
-      f.li_zs_at_edge[p] = zs_at_edge;
-      f.li_water_depth_at_edge[p] = hf;
-      const double width = __ldg(f.li_flow_width_at_edge + p);
-      const double A = width * hf;
-      const double R = A / (2.0 * hf + width);
-      double q = hf > w.h_thresh
-                     ? local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R,
-                                           __ldg(f.li_flow_length_at_edge + p),
-                                           __ldg(f.li_mannings_n_sq_at_edge + p), w.froude_limit, dt_s)
-                     : 0.0;
+      if (last) {  // (every sub-step overwrites the edge diagnostics: the last one's stay)
+        f.li_zs_at_edge[p] = zs_at_edge;
+        f.li_water_depth_at_edge[p] = hf;
+      }
+      double q = 0.0;
+      if (hf > w.h_thresh) {
+        const double width = __ldg(f.li_flow_width_at_edge + p);
+        const double A = width * hf;
+        const double R = A / (2.0 * hf + width);
+        q = local_inertial_flow(q_previous, zs_src, zs_dst, hf, A, R, __ldg(f.li_flow_length_at_edge + p),
+                                __ldg(f.li_mannings_n_sq_at_edge + p), w.froude_limit, dt_s);
+      }
       if (h_src <= 0.0) q = jmin(q, 0.0);
       if (h_dst <= 0.0) q = jmax(q, 0.0);
-      __stcg(f.riv_q + p, q);
-      __stcg(f.riv_q_cumulative + p, __ldcg(f.riv_q_cumulative + p) + q * dt_s);
+      if (__double_as_longlong(q) != __double_as_longlong(q_previous)) __stcg(f.riv_q + p, q);
+      if (q != 0.0) __stcg(f.riv_q_cumulative + p, __ldcg(f.riv_q_cumulative + p) + q * dt_s);
     }
     alive = li_grid_barrier(w.barrier, n_blocks, gen, w.err);
     if (!alive) break;
@@ -550,7 +566,6 @@ local_inertial_land_river_kernel(const __grid_constant__ DevFields f, const KCfg
     }
 
     // ---- local_inertial_update_water_depth!                                         :1520-1546 ----
-    const bool last = !(t + dt_s < dt);
     mine_river = inf;
     mine_land = inf;
     for (int v = tid; v < n; v += stride) {
