@@ -156,6 +156,12 @@ def dist_env():
 
 
 def workload_text(d1, d2, adaptive, local_inertial=False):
+    if MOSELLE:
+        return ("synthetic Moselle-shape basin per GPU (264x291 raster, 50 063 land / ~5 809 river cells, "
+                "ONE outlet, all eight LDD codes), wflow_sbm vertical + kinematic-wave "
+                "river/overland/subsurface with 2 reservoirs and lateral snow transport, daily step, "
+                + ("adaptive internal steps (test/sbm_config.toml)" if adaptive else
+                   "fixed internal steps 3600/900/86400 s") + ", N=4 soil layers, snow on")
     if HOURLY and not local_inertial:
         return (f"synthetic {d1}x{d2} D8 basin per GPU, wflow_sbm vertical (HOURLY step: modified "
                 "Rutter interception) + kinematic-wave river/overland/subsurface, "
@@ -184,6 +190,7 @@ def config_block(workload, n, nriv, world):
 
 
 HOURLY = False   # --hourly: BASELINE configs[4] (hourly forcing => modified Rutter interception)
+MOSELLE = False  # --moselle: BASELINE configs[0] shape and switches (test/sbm_config.toml:122-130)
 
 
 def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0, local_inertial=False):
@@ -195,6 +202,10 @@ def build_tile(pkg, d1, d2, rank, seed, adaptive, catchment_length=0, local_iner
         extra = dict(river_routing=1, land_routing=1)
     if HOURLY:
         extra["dt"] = 3600.0
+    if MOSELLE:   # one outlet, all eight LDD codes, 50 063 land / ~5 809 river cells (test/bmi.jl:108-115)
+        return pkg.synthetic.make_basin(264, 291, seed=seed, id_offset=rank * 264 * 291, network="dendritic",
+                                        n_active=50063, n_river=5809, adaptive=adaptive, reservoirs=2,
+                                        snow_transport=True, **extra)
     return pkg.synthetic.make_basin(d1, d2, seed=seed, id_offset=rank * d1 * d2, adaptive=adaptive,
                                     catchment_length=catchment_length, **extra)
 
@@ -315,6 +326,9 @@ def main():
     ap.add_argument("--local-inertial-land", action="store_true",
                     help="2-D local-inertial overland flow coupled to the local-inertial river "
                          "(land_routing = river_routing = local_inertial)")
+    ap.add_argument("--moselle", action="store_true",
+                    help="BASELINE configs[0]: Moselle-shape dendritic basin (50 063 cells) with its "
+                         "reservoirs and lateral snow transport; add --adaptive for the TOML's time stepping")
     ap.add_argument("--hourly", action="store_true",
                     help="BASELINE configs[4]: hourly model step (modified Rutter interception)")
     ap.add_argument("--seed", type=int, default=42)
@@ -329,13 +343,16 @@ def main():
     ap.add_argument("--cfg", action="append", default=[], metavar="NAME=INT",
                     help="WflowB200Config tuning field, e.g. vertical_slices=1")
     args = ap.parse_args()
-    global HOURLY
+    global HOURLY, MOSELLE
     HOURLY = bool(args.hourly)
+    MOSELLE = bool(args.moselle)
     if args.local_inertial_land:
         args.local_inertial = 2
     rank, world, local = dist_env()
     pkg = load_pkg()
     d1, d2 = (int(x) for x in args.shape.split("x")) if args.shape else (args.size, args.size)
+    if MOSELLE:
+        d1, d2 = 264, 291
     workload = workload_text(d1, d2, args.adaptive, args.local_inertial)
 
     # ------------------------------------------------------------------ reference arm ----
