@@ -254,7 +254,10 @@ int32_t wflowb200_update_bc_overland_flow_model(WflowB200* h);
 /* update_lateral_inflow!(river, ...)                                  surface_kinwave.jl:710-734 */
 int32_t wflowb200_update_lateral_inflow_river(WflowB200* h);
 /* update_inflow!(reservoir, river_flow, (; overland_flow, subsurface_flow), network): overland
- * and subsurface flow into the reservoirs                             surface_kinwave.jl:772-805 */
+ * and subsurface flow into the reservoirs                             surface_kinwave.jl:772-805
+ * land_routing = 1: update_inflow!(reservoir, river_flow, subsurface_flow, network) -- the
+ * subsurface flow only, the overland inflow is formed inside the overland routing
+ * (update_inflow_reservoir!)                        surface_staggered_scheme.jl:1103-1114,1301-1319 */
 int32_t wflowb200_update_inflow_reservoir(WflowB200* h);
 /* update_river_flow_model!(river, domain, clock, dt), incl. the reservoirs on the river
  * (update_reservoir_model! reservoir.jl:585-634: simple, modified_puls, free_weir without a
@@ -263,6 +266,8 @@ int32_t wflowb200_update_inflow_reservoir(WflowB200* h);
  * sub-steps dt_s = alpha min(L / sqrt(g h)), edge flow, reservoirs, node depth and storage, all
  * sub-steps of the model step inside ONE persistent kernel   surface_staggered_scheme.jl:326-383,
  * 627-661, 723-759, 800-838, 1004-1020; surface_process.jl:88-115 */
+/* land_routing = 1: WFLOWB200_ERR_STATE -- the river is routed together with the land by
+ * wflowb200_update_overland_flow_model (one scheme, one sub-step length for both). */
 int32_t wflowb200_update_river_flow_model(WflowB200* h, double dt);
 /* update_total_water_storage!(land, domain, routing)                          sbm.jl:143-182 */
 int32_t wflowb200_update_total_water_storage(WflowB200* h);

@@ -211,6 +211,18 @@ def test_oracle_local_inertial_land_conserves_water(pkg):
     assert np.all(f["riv_h"][~over] <= f["li_bankfull_depth"][~over] * (1 + 1e-12))
 
 
+def test_sharding_refuses_what_it_cannot_keep_exact(pkg):
+    """Basin-aligned shards are independent only for the kinematic wave without reservoirs: the
+    staggered (local-inertial) schemes take ONE sub-step length for the whole domain and the 2-D
+    overland flow crosses basin divides -- shard_config refuses instead of changing the result."""
+    cfg, dom, _ = pkg.synthetic.make_basin(24, 32, seed=3)
+    sh = pkg.partition.partition_basins(dom, 2)[0]
+    assert pkg.partition.shard_config(cfg, sh)["sharded"] is True
+    for bad in (dict(river_routing=1), dict(river_routing=1, land_routing=1), dict(nres=2)):
+        with pytest.raises(ValueError):
+            pkg.partition.shard_config(dict(cfg, **bad), sh)
+
+
 def test_create_rejects_bad_arguments_before_touching_the_device(pkg):
     """Argument validation of wflowb200_create happens before any CUDA call: status
     WFLOWB200_ERR_ARG (1) and a message, never a crash (the shim turns it into error(...))."""
