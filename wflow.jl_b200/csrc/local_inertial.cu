@@ -93,7 +93,7 @@ __device__ __forceinline__ double local_inertial_flow(double q0, double zs0, dou
 
 }  // namespace
 
-__global__ void __launch_bounds__(kLiBlock, 3)
+__global__ void __launch_bounds__(kLiBlock, 4)
 local_inertial_river_kernel(const __grid_constant__ DevFields f, const KCfg c, const LiLaunch w) {
   const int n = c.nriv;
   const int stride = (int)(gridDim.x * blockDim.x);
@@ -237,9 +237,16 @@ local_inertial_river_kernel(const __grid_constant__ DevFields f, const KCfg c, c
     // ---- update_water_depth_and_storage! --------------------------------------------------------
     for (int p = tid; p < n; p += stride) {
       if (f.riv_reservoir && f.riv_reservoir[p] >= 0) continue;  // not in active_n
-      double q_src = 0.0;
-      for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) q_src += __ldcg(f.riv_q + f.li_in_idx[e]);
-      const double q_dst = f.li_dst_slot[p] == -1 ? 0.0 : 0.0 + f.riv_q[p];
+      // both sums over the entering edges in one walk (ascending source id each, like sum_at):
+      // the index loads are shared and the two gathers of an edge are in flight together
+      double q_src = 0.0, qf_src = 0.0;
+      for (int e = f.li_in_ptr[p], e1 = f.li_in_ptr[p + 1]; e < e1; ++e) {
+        const int u = f.li_in_idx[e];
+        q_src += __ldcg(f.riv_q + u);
+        if (floodplain) qf_src += __ldcg(f.fp_q + u);
+      }
+      const int dst = f.li_dst_slot[p];
+      const double q_dst = dst == -1 ? 0.0 : 0.0 + f.riv_q[p];
       double storage = f.riv_storage[p];
       storage += (q_src - q_dst + f.riv_inwater[p] - __ldg(f.riv_abstraction + p)) * dt_s;
       if (storage < 0.0) {
@@ -259,9 +266,7 @@ local_inertial_river_kernel(const __grid_constant__ DevFields f, const KCfg c, c
       const double length = __ldg(f.riv_flow_length + p), width = __ldg(f.riv_flow_width + p);
       double h_new = storage / (length * width);
       if (floodplain) {  // update_water_depth_and_storage!(floodplain, ...)           :674-712
-        double qf_src = 0.0;
-        for (int e = f.li_in_ptr[p]; e < f.li_in_ptr[p + 1]; ++e) qf_src += __ldcg(f.fp_q + f.li_in_idx[e]);
-        const double qf_dst = f.li_dst_slot[p] == -1 ? 0.0 : 0.0 + f.fp_q[p];
+        const double qf_dst = dst == -1 ? 0.0 : 0.0 + f.fp_q[p];
         double fs = f.fp_storage[p];
         fs += (qf_src - qf_dst) * dt_s;
         if (fs < 0.0) {
