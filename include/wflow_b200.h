@@ -85,7 +85,7 @@ typedef struct {
   double li_h_thresh;          /* river_water_flow_threshold__depth (1e-3 m)                   */
   /* floodplain_1d__flag: with the local-inertial river (floodplain.jl, surface_staggered_scheme.jl:
    * 440-533,674-712) or with the kinematic-wave river (surface_kinwave.jl:387-432,567-601;
-   * without reservoirs): the flood depths of the FloodPlainProfile; fp_levels = 0: no floodplain */
+   * with or without reservoirs): the flood depths of the FloodPlainProfile; fp_levels = 0: none */
   int32_t fp_levels;           /* length(profile.depth), <= 16                                 */
   int32_t reserved2_;
   double fp_depth[16];         /* profile.depth [m], ascending from 0                          */

@@ -323,16 +323,16 @@ def test_local_inertial_land_edge_cases(pkg):
         _close(gpu)
 
 
-@pytest.mark.parametrize("adaptive", [False, True])
-def test_kinematic_wave_river_with_floodplain(pkg, adaptive):
+@pytest.mark.parametrize("adaptive,reservoirs", [(False, 0), (True, 0), (False, 3), (True, 3)])
+def test_kinematic_wave_river_with_floodplain(pkg, adaptive, reservoirs):
     """floodplain_1d__flag with the kinematic-wave river: per sub-step the channel-floodplain
     exchange (bankfull redistribution, lateral inflow of the wave), the Manning flow capacity of
     the floodplain from its profile and accucapacityflux! of the floodplain storage
     (surface_kinwave.jl:387-432,567-601,650-659) -- inside the river's skewed wavefront, three
     published values per node and sub-step."""
     gpu, ora, cfg = parity.run_pair(pkg, 70, 110, steps=4, seed=43, floodplain=True,
-                                    adaptive=adaptive)
-    assert len(cfg["fp_depth"]) == 6 and cfg["river_routing"] == 0
+                                    adaptive=adaptive, reservoirs=reservoirs)
+    assert len(cfg["fp_depth"]) == 6 and cfg["river_routing"] == 0 and cfg["nres"] == reservoirs
     rep = parity.compare_models(gpu, ora)
     st, o = gpu.stats(), ora.newton_stats()
     assert st["substeps_river"] == o["substeps_river"]

@@ -878,10 +878,8 @@ int32_t wflowb200_create(const WflowB200Config* cfg, const WflowB200Domain* dom,
 
   WflowB200* h = new WflowB200();
   h->cfg = *cfg;
-  if (cfg->fp_levels < 0 || cfg->fp_levels > 16 ||
-      (cfg->fp_levels > 0 && cfg->river_routing == 0 && dom->nres > 0)) {
-    g_create_error = "fp_levels: 0 .. 16; the kinematic wave's 1-D floodplain is not supported "
-                     "together with reservoirs";
+  if (cfg->fp_levels < 0 || cfg->fp_levels > 16) {
+    g_create_error = "fp_levels: 0 .. 16";
     delete h;
     return WFLOWB200_ERR_ARG;
   }
