@@ -976,10 +976,13 @@ soil_column_kernel(const DevFields f, const KCfg c, const UnsatWork w, const Sta
 // The loop engine: one lane per suspended cell, 32 cells of one bucket (trip counts within a factor
 // of two) per warp, longest buckets first. A lane runs the long loop its cell was suspended at
 // (tracked trips), then the layers below with loops of any length in line. Per-layer operands are
-// fetched when their layer is reached. The kernel lasts as long as the trips of the wettest cell
-// (~4000 on the benchmark basin, ~55 cycles each): sending the later long loops of a cell to a
-// further launch, regrouped by trip count, was built and measured -- no gain, the lanes' idling
-// is not what bounds it.
+// fetched when their layer is reached. What bounds the kernel is the latency of every warp's
+// dependent instruction stream at the four warps per scheduler that 102 registers allow (ncu,
+// profiles/r2final_engine_ncu.md: 44e6 warp instructions over 2368 resident warps, one issued
+// every ~10 cycles; a loop itself has at most ~850 trips). 42 % of the instructions are issued for
+// the 4.5-8 lanes still in the layers below the suspended one; sending those loops to a further
+// launch, regrouped by trip count, was built and measured -- scratch traffic and launches ate
+// the gain.
 #ifndef WFB_ENGINE_MINBLOCKS
 #define WFB_ENGINE_MINBLOCKS 4
 #endif
