@@ -680,6 +680,64 @@ def test_kinwave_river_with_floodplain_routing_process_858_987():
     assert m.f["fp_q_cumulative"] == approx(np.array([6014.835102655834, 4438.882199731312]))
 
 
+def test_local_inertial_long_channel_macdonald_routing_process_1189_1318():
+    """The reference's analytical check of the local-inertial river scheme: MacDonald (1997), a
+    1000 m channel (dx = 5 m, width 10 m, Manning n 0.03, 20 m3/s in at the upper end, the
+    analytical depth as downstream boundary); bed levels by integrating the analytical slope (QuadGK
+    in the reference, scipy.integrate.quad here: hence the reference's own `isapprox` tolerance,
+    1.5e-8). Run to a steady state (|change of the mean depth| <= 1e-12) with
+    stable_timestep / update_river_channel_flow! / update_water_depth_and_storage!; the mean
+    absolute error against the analytical profile is the reference's number."""
+    from scipy.integrate import quad
+    G = 9.80665
+    L_, dx = 1000.0, 5.0
+    n = int(L_ / dx)
+    h = lambda x: np.cbrt(4 / G) * (1.0 + 0.5 * math.exp(-16.0 * (x / L_ - 0.5) ** 2))
+    h_acc = lambda x: -np.cbrt(4 / G) * 16.0 / L_ * (x / L_ - 0.5) * math.exp(-16 * (x / L_ - 0.5) ** 2)
+    slope = lambda x: ((1.0 - 4.0 / (G * h(x) ** 3)) * h_acc(x)
+                       + 0.36 * (2 * h(x) + 10.0) ** (4.0 / 3.0) / ((10.0 * h(x)) ** (10.0 / 3.0)))
+    x = np.arange(dx, L_ + dx / 2, dx)
+    h_a = np.array([h(xi) for xi in x])
+    zb = np.array([quad(slope, xi, L_, epsabs=0, epsrel=1e-12)[0] for xi in x])
+    down = np.concatenate([np.arange(2, n + 1), [0]])      # node i -> i + 1; node n has no edge
+
+    class G_:
+        pass
+    G_.down = down
+    river = dict(graph=G_, order=np.arange(1, n + 1), up_ptr=np.concatenate([[0, 0], np.arange(1, n)]),
+                 up_idx=np.arange(1, n), order_of_subdomains=[np.array([1])],
+                 order_subdomain=[np.arange(1, n + 1)], subdomain_indices=[np.arange(1, n + 1)])
+
+    class G1:
+        down = np.zeros(1, dtype=np.int64)
+    land = dict(graph=G1, order=np.array([1]), up_ptr=np.zeros(2, np.int64), up_idx=np.zeros(0, np.int64),
+                order_of_subdomains=[np.array([1])], order_subdomain=[np.array([1])],
+                subdomain_indices=[np.array([1])])
+    d = np.where(down > 0, down - 1, np.arange(n))
+    f = dict(riv_inwater=np.zeros(n), riv_external_inflow=np.zeros(n), riv_abstraction=np.zeros(n),
+             li_zb=zb, li_zb_at_edge=np.maximum(zb, zb[d]),
+             li_mannings_n_sq_at_edge=np.full(n, 0.03 * 0.03), li_flow_length_at_edge=np.full(n, dx),
+             li_flow_width_at_edge=np.full(n, 10.0), li_ghost_h=np.zeros(n),
+             riv_flow_width=np.full(n, 10.0), riv_flow_length=np.full(n, dx),
+             riv_h=np.concatenate([np.zeros(n - 1), [h_a[-1]]]), riv_storage=np.zeros(n),
+             riv_q=np.zeros(n), river_land_indices=np.zeros(n, dtype=np.int64))
+    m = orc.OracleModel(dict(n=1, nriv=n, N=1, river_routing=1, li_froude_limit=1, li_ghost_nodes=0,
+                             li_alpha=0.7, li_h_thresh=1e-3), f, land, river)
+    L = orc.lib()
+    for it in range(200000):
+        m.f["riv_inwater"][0] = 20.0
+        h0 = m.f["riv_h"].mean()
+        dt = L.wfo_li_stable_timestep(m.h)
+        L.wfo_li_update_river_channel_flow(m.h, dt)
+        L.wfo_li_update_water_depth_and_storage(m.h, dt)
+        m.f["riv_h"][-1] = h_a[-1]   # node n is not in active_n: its depth is the boundary condition
+        if abs(h0 - m.f["riv_h"].mean()) <= 1e-12:
+            break
+    else:
+        raise AssertionError("no steady state")
+    assert np.mean(np.abs(m.f["riv_h"] - h_a)) == pytest.approx(0.01873574206931199, rel=1.5e-8)
+
+
 def _lil_nets(nriv_down):
     """a river chain given by `down` (1-based, 0 = pit) and a land domain without drainage"""
     nr = len(nriv_down)
