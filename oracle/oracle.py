@@ -108,6 +108,12 @@ def lib(variant: str = ""):
         for f in ("wfo_lil_update_inflow_reservoir", "wfo_update_bc_overland_flow_model"):
             getattr(L, f).argtypes = [C.c_void_p]
             getattr(L, f).restype = None
+        L.wfo_update_reservoir_model.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double]
+        L.wfo_update_reservoir_model.restype = None
+        L.wfo_update_reservoir_at_node.argtypes = [C.c_void_p, C.c_int64, C.c_double]
+        L.wfo_update_reservoir_at_node.restype = None
+        L.wfo_local_inertial_flow.argtypes = [C.c_double] * 8 + [C.c_int, C.c_double]
+        L.wfo_local_inertial_flow.restype = C.c_double
         L.wfo_local_inertial_flow_rect.argtypes = [C.c_double] * 10 + [C.c_int, C.c_double]
         L.wfo_local_inertial_flow_rect.restype = C.c_double
         L.wfo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]

@@ -270,6 +270,12 @@ void wfo_lil_update_overland_flow_model(wfo_model*, double dt);
 double wfo_local_inertial_flow_rect(double theta, double q0, double qd, double qu, double zs0,
                                     double zs1, double hf, double width, double length,
                                     double mannings_n_sq, int froude_limit, double dt);
+/* test hooks: update_reservoir_model!(reservoir, i, inflow, dt) reservoir.jl:585-634 and
+ * update_reservoir_model!(reservoir, river variables, network, v, dt) surface_kinwave.jl:441-489 */
+void wfo_update_reservoir_model(wfo_model*, int64_t i, double inflow, double dt);
+void wfo_update_reservoir_at_node(wfo_model*, int64_t v, double dt);
+double wfo_local_inertial_flow(double q0, double zs0, double zs1, double hf, double A, double R,
+                               double length, double mannings_n_sq, int froude_limit, double dt);
 void wfo_river_channel_floodplain_exchange(wfo_model*, double dt_s);
 void wfo_update_floodplain_model(wfo_model*, double dt_s);
 void wfo_update_total_water_storage(wfo_model*);               /* sbm.jl:143-182 */

@@ -693,6 +693,19 @@ static void update_reservoir_at_node(wfo_model* m, int64_t v, double dt) {
   if (j >= 0) m->riv_qin[j] = m->res_outflow[i];
 }
 
+/* test hooks of the reference's reservoir unit tests (test/reservoir.jl) */
+void wfo_update_reservoir_model(wfo_model* m, int64_t i, double inflow, double dt) {
+  update_reservoir_model_i(m, i, inflow, dt);
+}
+void wfo_update_reservoir_at_node(wfo_model* m, int64_t v, double dt) { update_reservoir_at_node(m, v, dt); }
+/* local_inertial_flow(q0, zs0, zs1, hf, A, R, length, mannings_n_sq, froude_limit, dt) */
+static double local_inertial_flow(double q0, double zs0, double zs1, double hf, double A, double R,
+                                  double length, double mannings_n_sq, int froude_limit, double dt);
+double wfo_local_inertial_flow(double q0, double zs0, double zs1, double hf, double A, double R,
+                               double length, double mannings_n_sq, int froude_limit, double dt) {
+  return local_inertial_flow(q0, zs0, zs1, hf, A, R, length, mannings_n_sq, froude_limit, dt);
+}
+
 /* update_inflow!(reservoir, river_flow, external_models, network)      surface_kinwave.jl:772-805 */
 void wfo_update_inflow_reservoir(wfo_model* m) {
   for (int64_t i = 0; i < m->cfg.nres; ++i) {

@@ -765,6 +765,101 @@ def _as_fields(f):
     return {k: np.asarray(v, dtype=np.int64 if k.endswith(ints) else np.float64) for k, v in f.items()}
 
 
+def _reservoir_model(nriv_down, **res):
+    """one reservoir on river node 1 of a chain given by `down`"""
+    land, river = _lil_nets(nriv_down)
+    nr = len(nriv_down)
+    f = dict(river_land_indices=np.arange(nr), reservoir_river_indices=[0],
+             riv_q=np.zeros(nr), riv_qin=np.zeros(nr), res_outflow_obs=[np.nan],
+             res_external_inflow=[0.0], res_inflow_overland=[0.0], res_inflow_subsurface=[0.0],
+             res_threshold=[0.0], res_rating_curve_coefficient=[0.0], res_rating_curve_exponent=[0.0],
+             res_maximum_storage=[np.nan], res_maximum_release=[np.nan], res_demand=[np.nan],
+             res_target_minimum_fraction=[np.nan], res_target_full_fraction=[np.nan])
+    f.update(res)
+    return orc.OracleModel(dict(n=3, nriv=nr, nres=1, N=1), _as_fields(f), land, river)
+
+
+def test_update_reservoir_simple_reservoir_1_58():
+    """update_reservoir_model!(res, 1, 100.0, dt), simple reservoir, without and with an observed
+    outflow (test/reservoir.jl:1-58)."""
+    L = orc.lib()
+    dt = 86400.0
+    kw = dict(res_precipitation=[4.861111111111111e-8], res_evaporation=[1.736111111111111e-8],
+              res_demand=[52.523], res_maximum_release=[420.184], res_maximum_storage=[25_000_000.0],
+              res_area=[1885665.353626924], res_target_full_fraction=[0.8],
+              res_target_minimum_fraction=[0.2425554726620697], res_outflow_curve_type=[4.0],
+              res_storage=[1.925e7], res_waterlevel=[10.208598234556407])
+    m = _reservoir_model([2, 0], **kw)
+    L.wfo_update_reservoir_model(m.h, 0, 100.0, dt)
+    assert m.f["res_outflow"][0] == approx(91.3783714867453)
+    assert m.f["res_storage"][0] == approx(2.0e7)
+    assert m.f["res_actevap_cumulative"][0] == approx(0.0014999999999999998)
+    assert m.f["res_outflow_cumulative"][0] == m.f["res_outflow"][0] * dt
+    m = _reservoir_model([2, 0], **dict(kw, res_outflow_obs=[80.0]))
+    L.wfo_update_reservoir_model(m.h, 0, 100.0, dt)
+    assert m.f["res_outflow"][0] == approx(80.0)
+    assert m.f["res_storage"][0] == approx(2.0983091296454795e7)
+
+
+def test_update_reservoir_modified_puls_reservoir_60_115():
+    """Modified Puls approach (outflow_curve_type = 3), linear storage curve (test/reservoir.jl:60-115)."""
+    L = orc.lib()
+    area = 180510409.0
+    m = _reservoir_model([2, 0], res_precipitation=[2.3148148148148148e-7],
+                         res_evaporation=[3.7037037037037036e-8], res_area=[area], res_threshold=[0.0],
+                         res_outflow_curve_type=[3.0], res_rating_curve_coefficient=[0.22],
+                         res_rating_curve_exponent=[2.0], res_waterlevel=[18.5],
+                         res_storage=[area * 18.5])          # initialize_storage, linear
+    L.wfo_update_reservoir_model(m.h, 0, 2500.0, 86400.0)
+    assert m.f["res_outflow"][0] == approx(85.14292808113598)
+    assert m.f["res_storage"][0] == approx(3.55111879238499e9)
+    assert m.f["res_waterlevel"][0] == approx(19.672653848925634)
+    assert m.f["res_storage"][0] / area == approx(19.672653848925634)   # waterlevel(linear, ...)
+    assert m.f["res_actevap_cumulative"][0] == approx(0.0032)
+
+
+def test_update_reservoir_model_at_node_reservoir_117_221():
+    """update_reservoir_model!(reservoir, river variables, network, v, dt): limited abstraction,
+    overland / subsurface / river inflow, observed outflow and the simple rule; the outflow becomes
+    qin of the downstream node (test/reservoir.jl:117-221)."""
+    L = orc.lib()
+    m = _reservoir_model([2, 0], res_external_inflow=[-1.0], res_inflow_overland=[0.02],
+                         res_inflow_subsurface=[0.04], res_precipitation=[5.787037037037037e-9],
+                         res_evaporation=[1.1574074074074074e-9], res_outflow_curve_type=[4.0],
+                         res_area=[6.0e4], res_waterlevel=[1.0], res_storage=[4.5e7],
+                         res_outflow=[3.0], res_outflow_obs=[1.0], riv_q=[0.04, 0.04])
+    L.wfo_update_reservoir_at_node(m.h, 0, 1000.0)
+    assert m.f["riv_qin"][1] == approx(1.0)
+    assert m.f["res_actual_external_abstraction_cumulative"][0] == approx(1e3)
+    assert m.f["res_storage"][0] == approx(4.4998100277777776e7)
+    assert m.f["res_waterlevel"][0] == approx(0.9683379629629354)
+    assert m.f["res_outflow"][0] == approx(1.0)
+    m = _reservoir_model([2, 0], res_external_inflow=[-1.0], res_inflow_overland=[0.0],
+                         res_inflow_subsurface=[0.00041241066945499203],
+                         res_precipitation=[8.101853611016715e-10], res_evaporation=[6.134257548385196e-9],
+                         res_outflow_curve_type=[4.0], res_area=[9.069779e4], res_maximum_release=[1.74],
+                         res_demand=[0.2175], res_target_minimum_fraction=[0.358469158],
+                         res_target_full_fraction=[0.83492106199], res_maximum_storage=[3.3e7],
+                         res_waterlevel=[3.0266425035195113], res_storage=[2.7450978618928656e7],
+                         riv_q=[0.00012002923701686638, 0.21747539140212965])
+    L.wfo_update_reservoir_at_node(m.h, 0, 1000.0)
+    assert m.f["riv_qin"][1] == approx(0.21749985206208133)
+    assert m.f["res_actual_external_abstraction_cumulative"][0] == approx(1000.0)
+    assert m.f["res_storage"][0] == approx(2.744976116863499e7)
+    assert m.f["res_waterlevel"][0] == approx(3.013219350720886)
+    assert m.f["res_outflow"][0] == approx(0.21749985206208133)
+
+
+def test_local_inertial_flow_general_area_routing_process_1320_1344():
+    """local_inertial_flow(q0, zs0, zs1, hf, A, R, ...), the general-area method of the river
+    (surface_process.jl:88-115)."""
+    q = orc.lib().wfo_local_inertial_flow(0.0004713562869434079, 206.10117949049967, 201.9003737619653,
+                                          0.0011733869840497846, 0.04970535373017763,
+                                          0.0011733219820725962, 533.453125, 0.0008999999597668652, 1,
+                                          89.29563868855615)
+    assert q == approx(0.005331926324969742)
+
+
 def test_local_inertial_flow_rectangular_routing_process_1346_1373():
     """local_inertial_flow(theta, q0, qd, qu, ...), the rectangular-area method of the overland
     flow (surface_process.jl:123-159; de Almeida et al. 2012)."""
