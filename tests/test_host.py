@@ -297,14 +297,16 @@ def test_cut_basin_plan_is_consistent(pkg):
         assert sum(len(pl["links"][1]) for pl in plans) == n_riv_cut
 
 
-def test_bench_reference_arm_prints_the_contract_line():
+@pytest.mark.parametrize("flags", [[], ["--local-inertial-land"], ["--hourly"]])
+def test_bench_reference_arm_prints_the_contract_line(flags):
     """`bench.py --impl reference` (the CPU port on the host cores) prints ONE JSON line with the
-    keys of the bench contract and the same `config` keys as the GPU arm."""
+    keys of the bench contract and the same `config` keys as the GPU arm -- also for the workload
+    variants (2-D local-inertial overland flow, hourly step)."""
     import json
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
-                          "--size", "40", "--steps", "2", "--warmup", "1"],
+                          "--size", "40", "--steps", "2", "--warmup", "1"] + flags,
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
