@@ -55,6 +55,22 @@ def test_local_inertial_amplifies_last_bit_noise(pkg):
     print(rep.summary())
 
 
+@pytest.mark.parametrize("reservoirs", [0, 3])
+def test_local_inertial_land_tolerance_is_calibrated(pkg, reservoirs):
+    """The tolerance of the GPU test of the 2-D local-inertial overland flow (same basin, same four
+    steps): the oracle against itself on the +-1 ulp libm passes it, with some elements between
+    1e-10 and 1e-5 (the scheme's thresholds at work) -- and an error of 1e-3 planted in one wet
+    cell's depth does not pass."""
+    a, b, cfg = _pair(pkg, 70, 110, 4, seed=43, river_routing=1, land_routing=1, reservoirs=reservoirs)
+    assert a.newton_stats()["substeps_river"] == b.newton_stats()["substeps_river"] > 100
+    rep = parity.compare_models(b, a, outliers=(1.0, 1e-5))
+    assert sum(v.get("outliers", 0) for v in rep.values()) > 0
+    k = int(np.argmax(a.f["olf_h"]))
+    b.f["olf_h"][k] *= 1.0 + 1e-3
+    with pytest.raises(AssertionError, match="olf_h"):
+        parity.compare_models(b, a, outliers=(1.0, 1e-5))
+
+
 def test_planted_error_is_caught(pkg):
     """A relative error of 1e-8 in ONE element fails the comparison, whatever the field's largest
     magnitude is: for every flux / storage / discharge field, at its smallest element that lies
